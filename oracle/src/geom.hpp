@@ -1,0 +1,575 @@
+// oracle/src/geom.hpp — scalar fp64 geometry of the CPU oracle (TEST
+// INFRASTRUCTURE, see oracle/kmo.h).  Restates, from SURVEY.md Appendix A
+// (the upstream sources are not vendored in /root/reference):
+//   A.6  opengv relative_pose::fivept_nister + essential decomposition +
+//        triangulate2 + bearing reprojection residual
+//        (opengv/src/relative_pose/methods.cpp, modules/fivept_nister/modules.cpp,
+//         src/sac_problems/relative_pose/CentralRelativePoseSacProblem.cpp,
+//         src/triangulation/methods.cpp, src/math/Sturm.cpp)
+//   A.8  opengv point_cloud::threept_arun + 3-D residual
+//        (opengv/src/point_cloud/methods.cpp, PointCloudSacProblem.cpp)
+// The ARITHMETIC CONTRACT (operation order, fixed sweep counts, tie rules) is
+// written out in DESIGN.md §4; the CUDA kernels implement the same contract
+// independently.  Compile with -ffp-contract=off.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+namespace kmo {
+
+// ---------------------------------------------------------------- 3-vectors
+static inline double dot3(const double* a, const double* b) {
+  return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+}
+static inline void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// y = M x (M row-major 3x3)
+static inline void matvec3(const double* M, const double* x, double* y) {
+  y[0] = (M[0] * x[0] + M[1] * x[1]) + M[2] * x[2];
+  y[1] = (M[3] * x[0] + M[4] * x[1]) + M[5] * x[2];
+  y[2] = (M[6] * x[0] + M[7] * x[1]) + M[8] * x[2];
+}
+// y = M^T x
+static inline void matTvec3(const double* M, const double* x, double* y) {
+  y[0] = (M[0] * x[0] + M[3] * x[1]) + M[6] * x[2];
+  y[1] = (M[1] * x[0] + M[4] * x[1]) + M[7] * x[2];
+  y[2] = (M[2] * x[0] + M[5] * x[1]) + M[8] * x[2];
+}
+
+// ------------------------------------------------------------------- svd3
+// One-sided (Hestenes) Jacobi SVD of a 3x3 matrix, "proper" form:
+// A = U diag(S) V^T with S sorted descending, U = [u0 u1 u0xu1],
+// V = [v0 v1 v0xv1] (both det +1).  The third singular value is reported as
+// the norm of the third rotated column.  At most 12 sweeps over the pairs
+// (0,1),(0,2),(1,2); a rotation is skipped when g*g <= 1e-30*a*b.
+static const int kSvdSweeps = 12;
+static inline void svd3(const double* A, double* U, double* S, double* V) {
+  double G[9], W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) G[i] = A[i];
+  static const int P[3] = {0, 0, 1}, Q[3] = {1, 2, 2};
+  for (int sweep = 0; sweep < kSvdSweeps; ++sweep) {
+    bool rotated = false;
+    for (int k = 0; k < 3; ++k) {
+      const int p = P[k], q = Q[k];
+      double a = (G[p] * G[p] + G[3 + p] * G[3 + p]) + G[6 + p] * G[6 + p];
+      double b = (G[q] * G[q] + G[3 + q] * G[3 + q]) + G[6 + q] * G[6 + q];
+      double g = (G[p] * G[q] + G[3 + p] * G[3 + q]) + G[6 + p] * G[6 + q];
+      if (g * g <= 1e-30 * a * b) continue;
+      rotated = true;
+      double zeta = (b - a) / (2.0 * g);
+      double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+      double c = 1.0 / std::sqrt(1.0 + t * t);
+      double s = c * t;
+      for (int i = 0; i < 3; ++i) {
+        double gp = G[3 * i + p], gq = G[3 * i + q];
+        G[3 * i + p] = c * gp - s * gq;
+        G[3 * i + q] = s * gp + c * gq;
+        double wp = W[3 * i + p], wq = W[3 * i + q];
+        W[3 * i + p] = c * wp - s * wq;
+        W[3 * i + q] = s * wp + c * wq;
+      }
+    }
+    if (!rotated) break;
+  }
+  double n[3];
+  for (int j = 0; j < 3; ++j)
+    n[j] = std::sqrt((G[j] * G[j] + G[3 + j] * G[3 + j]) + G[6 + j] * G[6 + j]);
+  // stable descending order of the three column norms
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (n[i1] > n[i0]) { int t = i0; i0 = i1; i1 = t; }
+  if (n[i2] > n[i1]) { int t = i1; i1 = i2; i2 = t; }
+  if (n[i1] > n[i0]) { int t = i0; i0 = i1; i1 = t; }
+  S[0] = n[i0]; S[1] = n[i1]; S[2] = n[i2];
+  double u0[3], u1[3], u2[3], v0[3], v1[3], v2[3];
+  if (n[i0] > 0.0) {
+    for (int i = 0; i < 3; ++i) u0[i] = G[3 * i + i0] / n[i0];
+  } else {
+    u0[0] = 1.0; u0[1] = 0.0; u0[2] = 0.0;
+  }
+  if (n[i1] > 0.0) {
+    for (int i = 0; i < 3; ++i) u1[i] = G[3 * i + i1] / n[i1];
+  } else {
+    // rank <= 1: any unit vector orthogonal to u0 (deterministic choice)
+    int k = 0;
+    if (std::fabs(u0[1]) < std::fabs(u0[k])) k = 1;
+    if (std::fabs(u0[2]) < std::fabs(u0[k])) k = 2;
+    double e[3] = {0, 0, 0};
+    e[k] = 1.0;
+    cross3(u0, e, u1);
+    double nn = std::sqrt(dot3(u1, u1));
+    for (int i = 0; i < 3; ++i) u1[i] = u1[i] / nn;
+  }
+  cross3(u0, u1, u2);
+  for (int i = 0; i < 3; ++i) { v0[i] = W[3 * i + i0]; v1[i] = W[3 * i + i1]; }
+  cross3(v0, v1, v2);
+  for (int i = 0; i < 3; ++i) {
+    U[3 * i + 0] = u0[i]; U[3 * i + 1] = u1[i]; U[3 * i + 2] = u2[i];
+    V[3 * i + 0] = v0[i]; V[3 * i + 1] = v1[i]; V[3 * i + 2] = v2[i];
+  }
+}
+
+// ------------------------------------------------------------------- Arun
+// A.8 arun_complete on 3 correspondences: p1 = R p2 + t.
+// model = [R | t] row-major 3x4.
+static inline void arun3(const double* a1, const double* b1, const double* c1,
+                         const double* a2, const double* b2, const double* c2,
+                         double* model) {
+  double m1[3], m2[3];
+  for (int i = 0; i < 3; ++i) {
+    m1[i] = ((a1[i] + b1[i]) + c1[i]) / 3.0;
+    m2[i] = ((a2[i] + b2[i]) + c2[i]) / 3.0;
+  }
+  const double* P1[3] = {a1, b1, c1};
+  const double* P2[3] = {a2, b2, c2};
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    double d1[3], d2[3];
+    for (int i = 0; i < 3; ++i) { d1[i] = P1[k][i] - m1[i]; d2[i] = P2[k][i] - m2[i]; }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + d2[r] * d1[c];
+  }
+  double U[9], S[3], V[9];
+  svd3(H, U, S, V);
+  // R = V U^T
+  double* R = model;  // write into strided 3x4
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      R[4 * r + c] = (V[3 * r + 0] * U[3 * c + 0] + V[3 * r + 1] * U[3 * c + 1]) +
+                     V[3 * r + 2] * U[3 * c + 2];
+  for (int r = 0; r < 3; ++r) {
+    double rc = (R[4 * r + 0] * m2[0] + R[4 * r + 1] * m2[1]) + R[4 * r + 2] * m2[2];
+    model[4 * r + 3] = m1[r] - rc;
+  }
+}
+
+// squared 3-D residual |p1 - (R p2 + t)|^2 with the contract's op order
+static inline double arun_sqdist(const double* M, const double* p1, const double* p2) {
+  double x = ((M[0] * p2[0] + M[1] * p2[1]) + M[2] * p2[2]) + M[3];
+  double y = ((M[4] * p2[0] + M[5] * p2[1]) + M[6] * p2[2]) + M[7];
+  double z = ((M[8] * p2[0] + M[9] * p2[1]) + M[10] * p2[2]) + M[11];
+  double ex = p1[0] - x, ey = p1[1] - y, ez = p1[2] - z;
+  return (ex * ex + ey * ey) + ez * ez;
+}
+
+// ---------------------------------------------------------- mono residual
+// A.6 getSelectedDistancesToModel: (1 - f1.p^) + (1 - f2.q^),
+// p = triangulate2(f1,f2 | R12,t12), q = R^T p - R^T t.
+// M = [R12 | t12] row-major 3x4; tinv = -(R^T t) is passed precomputed.
+static inline void mono_tinv(const double* M, double* tinv) {
+  double t[3] = {M[3], M[7], M[11]};
+  tinv[0] = -((M[0] * t[0] + M[4] * t[1]) + M[8] * t[2]);
+  tinv[1] = -((M[1] * t[0] + M[5] * t[1]) + M[9] * t[2]);
+  tinv[2] = -((M[2] * t[0] + M[6] * t[1]) + M[10] * t[2]);
+}
+static inline double mono_residual(const double* M, const double* tinv,
+                                   const double* f1, const double* f2) {
+  const double t[3] = {M[3], M[7], M[11]};
+  double f2u[3];
+  f2u[0] = (M[0] * f2[0] + M[1] * f2[1]) + M[2] * f2[2];
+  f2u[1] = (M[4] * f2[0] + M[5] * f2[1]) + M[6] * f2[2];
+  f2u[2] = (M[8] * f2[0] + M[9] * f2[1]) + M[10] * f2[2];
+  double b0 = dot3(t, f1), b1 = dot3(t, f2u);
+  double d12 = dot3(f1, f2u);
+  double A00 = dot3(f1, f1), A01 = -d12, A10 = d12, A11 = -dot3(f2u, f2u);
+  double det = A00 * A11 - A01 * A10;
+  double l0 = (A11 * b0 - A01 * b1) / det;
+  double l1 = (A00 * b1 - A10 * b0) / det;
+  double p[3], q[3];
+  for (int i = 0; i < 3; ++i) p[i] = 0.5 * (l0 * f1[i] + (t[i] + l1 * f2u[i]));
+  q[0] = ((M[0] * p[0] + M[4] * p[1]) + M[8] * p[2]) + tinv[0];
+  q[1] = ((M[1] * p[0] + M[5] * p[1]) + M[9] * p[2]) + tinv[1];
+  q[2] = ((M[2] * p[0] + M[6] * p[1]) + M[10] * p[2]) + tinv[2];
+  double np = std::sqrt(dot3(p, p)), nq = std::sqrt(dot3(q, q));
+  double e1 = 1.0 - dot3(f1, p) / np;
+  double e2 = 1.0 - dot3(f2, q) / nq;
+  return e1 + e2;
+}
+
+// ------------------------------------------------------ 5-point (Nister)
+// polynomial bookkeeping in (x,y,z):
+//  deg1 [x y z 1]
+//  deg2 [x2 xy xz y2 yz z2 x y z 1]
+//  deg3 [x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1]
+// M12[i][j]: deg2 slot of (deg1 i)*(deg1 j); M23[i][j]: deg3 slot of (deg2 i)*(deg1 j)
+static const int M12[4][4] = {{0, 1, 2, 6}, {1, 3, 4, 7}, {2, 4, 5, 8}, {6, 7, 8, 9}};
+static const int M23[10][4] = {
+    {0, 2, 4, 5},      // x2 * {x,y,z,1}
+    {2, 3, 8, 9},      // xy
+    {4, 8, 10, 11},    // xz
+    {3, 1, 6, 7},      // y2
+    {8, 6, 13, 14},    // yz
+    {10, 13, 16, 17},  // z2
+    {5, 9, 11, 12},    // x
+    {9, 7, 14, 15},    // y
+    {11, 14, 17, 18},  // z
+    {12, 15, 18, 19}}; // 1
+
+// out(deg2) = a(deg1)*b(deg1); products accumulated in (i,j) loop order
+static inline void pmul11(const double* a, const double* b, double* out) {
+  for (int k = 0; k < 10; ++k) out[k] = 0.0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) out[M12[i][j]] = out[M12[i][j]] + a[i] * b[j];
+}
+// out(deg3) += a(deg2)*b(deg1)
+static inline void pmul21_acc(const double* a, const double* b, double* out) {
+  for (int i = 0; i < 10; ++i)
+    for (int j = 0; j < 4; ++j) out[M23[i][j]] = out[M23[i][j]] + a[i] * b[j];
+}
+
+// Null space of the 5x9 epipolar system by Householder QR of its transpose:
+// basis[4][9] = last four columns of the 9x9 orthogonal factor.
+static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
+  double A[9][5];
+  for (int r = 0; r < 5; ++r)
+    for (int c = 0; c < 9; ++c) A[c][r] = Q[r][c];
+  double v[5][9];
+  double vn2[5];
+  for (int k = 0; k < 5; ++k) {
+    double s2 = 0.0;
+    for (int i = k; i < 9; ++i) s2 = s2 + A[i][k] * A[i][k];
+    double nrm = std::sqrt(s2);
+    double alpha = (A[k][k] >= 0.0) ? -nrm : nrm;
+    for (int i = 0; i < 9; ++i) v[k][i] = (i < k) ? 0.0 : A[i][k];
+    v[k][k] = v[k][k] - alpha;
+    double n2 = 0.0;
+    for (int i = k; i < 9; ++i) n2 = n2 + v[k][i] * v[k][i];
+    vn2[k] = n2;
+    if (n2 > 0.0) {
+      for (int j = k; j < 5; ++j) {
+        double d = 0.0;
+        for (int i = k; i < 9; ++i) d = d + v[k][i] * A[i][j];
+        double f = (2.0 * d) / n2;
+        for (int i = k; i < 9; ++i) A[i][j] = A[i][j] - f * v[k][i];
+      }
+    }
+  }
+  for (int b = 0; b < 4; ++b) {
+    double x[9];
+    for (int i = 0; i < 9; ++i) x[i] = (i == 5 + b) ? 1.0 : 0.0;
+    for (int k = 4; k >= 0; --k) {
+      if (!(vn2[k] > 0.0)) continue;
+      double d = 0.0;
+      for (int i = k; i < 9; ++i) d = d + v[k][i] * x[i];
+      double f = (2.0 * d) / vn2[k];
+      for (int i = k; i < 9; ++i) x[i] = x[i] - f * v[k][i];
+    }
+    for (int i = 0; i < 9; ++i) basis[b][i] = x[i];
+  }
+}
+
+// ---- univariate polynomials, coefficients ascending (c[0] + c[1] z + ...)
+static inline double horner(const double* c, int deg, double x) {
+  double r = c[deg];
+  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i];
+  return r;
+}
+// out = a*b  (degrees da, db), accumulation in (i,j) loop order
+static inline void upmul(const double* a, int da, const double* b, int db, double* out) {
+  for (int k = 0; k <= da + db; ++k) out[k] = 0.0;
+  for (int i = 0; i <= da; ++i)
+    for (int j = 0; j <= db; ++j) out[i + j] = out[i + j] + a[i] * b[j];
+}
+
+// Sturm chain of a degree-10 polynomial.  chain[k] has degree deg[k];
+// every remainder is negated and scaled by 1/|leading coefficient|.
+struct Sturm {
+  double c[12][11];
+  int deg[12];
+  int len;
+};
+static inline void sturm_build(const double* p, int n, Sturm* st) {
+  // strip exact-zero leading coefficients
+  while (n > 0 && p[n] == 0.0) --n;
+  for (int i = 0; i <= n; ++i) st->c[0][i] = p[i];
+  st->deg[0] = n;
+  st->len = 1;
+  if (n < 1) return;
+  for (int i = 0; i < n; ++i) st->c[1][i] = (double)(i + 1) * p[i + 1];
+  st->deg[1] = n - 1;
+  st->len = 2;
+  while (st->deg[st->len - 1] > 0 && st->len < 12) {
+    const double* a = st->c[st->len - 2];
+    const double* b = st->c[st->len - 1];
+    int da = st->deg[st->len - 2], db = st->deg[st->len - 1];
+    double r[11];
+    for (int i = 0; i <= da; ++i) r[i] = a[i];
+    for (int d = da; d >= db; --d) {
+      double f = r[d] / b[db];
+      for (int i = 0; i < db; ++i) r[d - db + i] = r[d - db + i] - f * b[i];
+      r[d] = 0.0;
+    }
+    int dr = db - 1;
+    while (dr >= 0 && r[dr] == 0.0) --dr;
+    if (dr < 0) break;  // exact gcd reached
+    double sc = std::fabs(r[dr]);
+    double* o = st->c[st->len];
+    for (int i = 0; i <= dr; ++i) o[i] = -(r[i] / sc);
+    st->deg[st->len] = dr;
+    st->len++;
+  }
+}
+static inline int sturm_count(const Sturm* st, double x) {
+  int changes = 0, last = 0;
+  for (int k = 0; k < st->len; ++k) {
+    double v = horner(st->c[k], st->deg[k], x);
+    int s = (v > 0.0) - (v < 0.0);
+    if (s != 0) {
+      if (last != 0 && s != last) ++changes;
+      last = s;
+    }
+  }
+  return changes;
+}
+
+static const int kRootGrid = 16;    // cells on [-1,1]
+static const int kRootDepth = 40;   // max Sturm bisection depth per cell
+static const int kRootBisect = 60;  // sign bisection steps per bracket
+
+// Real roots of p (degree n<=10) in (-1,1]: Sturm isolation on a 16-cell
+// grid with per-cell Sturm bisection, then 60 sign-bisection steps on p.
+// Roots are emitted in ascending order.  Returns the count (<= 10).
+static inline int roots_unit(const double* p, int n, double* roots) {
+  Sturm st;
+  sturm_build(p, n, &st);
+  if (st.deg[0] < 1) return 0;
+  int nr = 0;
+  int V[kRootGrid + 1];
+  for (int i = 0; i <= kRootGrid; ++i) V[i] = sturm_count(&st, -1.0 + (double)i * (2.0 / kRootGrid));
+  for (int cell = 0; cell < kRootGrid; ++cell) {
+    // explicit stack of (lo, hi, Vlo, Vhi, depth); left half is explored first
+    double slo[kRootDepth + 2], shi[kRootDepth + 2];
+    int svlo[kRootDepth + 2], svhi[kRootDepth + 2], sd[kRootDepth + 2];
+    int sp = 0;
+    slo[0] = -1.0 + (double)cell * (2.0 / kRootGrid);
+    shi[0] = -1.0 + (double)(cell + 1) * (2.0 / kRootGrid);
+    svlo[0] = V[cell]; svhi[0] = V[cell + 1]; sd[0] = 0;
+    sp = 1;
+    while (sp > 0) {
+      --sp;
+      double lo = slo[sp], hi = shi[sp];
+      int vlo = svlo[sp], vhi = svhi[sp], d = sd[sp];
+      int r = vlo - vhi;
+      if (r <= 0) continue;
+      if (r == 1 || d >= kRootDepth) {
+        double flo = horner(st.c[0], st.deg[0], lo);
+        double fhi = horner(st.c[0], st.deg[0], hi);
+        if (fhi == 0.0) {
+          if (nr < 10) roots[nr++] = hi;
+          continue;
+        }
+        if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) continue;
+        for (int it = 0; it < kRootBisect; ++it) {
+          double mid = 0.5 * (lo + hi);
+          double fm = horner(st.c[0], st.deg[0], mid);
+          if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
+        }
+        if (nr < 10) roots[nr++] = 0.5 * (lo + hi);
+        continue;
+      }
+      double mid = 0.5 * (lo + hi);
+      int vm = sturm_count(&st, mid);
+      // push right half first so that the left half is popped first
+      slo[sp] = mid; shi[sp] = hi; svlo[sp] = vm; svhi[sp] = vhi; sd[sp] = d + 1; ++sp;
+      slo[sp] = lo; shi[sp] = mid; svlo[sp] = vlo; svhi[sp] = vm; sd[sp] = d + 1; ++sp;
+    }
+  }
+  return nr;
+}
+
+// A.6 fivept_nister: f1 = bearings in frame 1 (query), f2 = frame 2 (match);
+// solves f1^T E f2 = 0 with E = [t12]x R12.  Returns #solutions, E row-major.
+static inline int fivept_nister(const double f1[5][3], const double f2[5][3], double E[10][9]) {
+  double Q[5][9];
+  for (int k = 0; k < 5; ++k)
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) Q[k][3 * j + i] = f2[k][i] * f1[k][j];
+  double B[4][9];
+  nullspace5x9(Q, B);  // B[0]=X, B[1]=Y, B[2]=Z, B[3]=W (row-major 3x3 each)
+  // entries of E(x,y,z) as deg1 polynomials
+  double Ep[9][4];
+  for (int e = 0; e < 9; ++e)
+    for (int b = 0; b < 4; ++b) Ep[e][b] = B[b][e];
+  double A[10][20];
+  for (int r = 0; r < 10; ++r)
+    for (int c = 0; c < 20; ++c) A[r][c] = 0.0;
+  // row 0: det(E)
+  {
+    double m[10], n[10], d[10];
+    // E00 (E11 E22 - E12 E21)
+    pmul11(Ep[4], Ep[8], m); pmul11(Ep[5], Ep[7], n);
+    for (int k = 0; k < 10; ++k) d[k] = m[k] - n[k];
+    pmul21_acc(d, Ep[0], A[0]);
+    // - E01 (E10 E22 - E12 E20)  ==  + E01 (E12 E20 - E10 E22)
+    pmul11(Ep[5], Ep[6], m); pmul11(Ep[3], Ep[8], n);
+    for (int k = 0; k < 10; ++k) d[k] = m[k] - n[k];
+    pmul21_acc(d, Ep[1], A[0]);
+    // + E02 (E10 E21 - E11 E20)
+    pmul11(Ep[3], Ep[7], m); pmul11(Ep[4], Ep[6], n);
+    for (int k = 0; k < 10; ++k) d[k] = m[k] - n[k];
+    pmul21_acc(d, Ep[2], A[0]);
+  }
+  // rows 1..9: (E E^T - 0.5 tr(E E^T) I) E
+  {
+    double EEt[3][3][10];
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) {
+        double a[10], b[10], c[10];
+        pmul11(Ep[3 * i + 0], Ep[3 * j + 0], a);
+        pmul11(Ep[3 * i + 1], Ep[3 * j + 1], b);
+        pmul11(Ep[3 * i + 2], Ep[3 * j + 2], c);
+        for (int k = 0; k < 10; ++k) {
+          EEt[i][j][k] = (a[k] + b[k]) + c[k];
+          EEt[j][i][k] = EEt[i][j][k];
+        }
+      }
+    double htr[10];
+    for (int k = 0; k < 10; ++k) htr[k] = 0.5 * ((EEt[0][0][k] + EEt[1][1][k]) + EEt[2][2][k]);
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 10; ++k) EEt[i][i][k] = EEt[i][i][k] - htr[k];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double* row = A[1 + 3 * i + j];
+        for (int k = 0; k < 3; ++k) pmul21_acc(EEt[i][k], Ep[3 * k + j], row);
+      }
+  }
+  // Gauss-Jordan with partial pivoting on the first 10 columns
+  for (int c = 0; c < 10; ++c) {
+    int pr = c;
+    double pv = std::fabs(A[c][c]);
+    for (int r = c + 1; r < 10; ++r) {
+      double v = std::fabs(A[r][c]);
+      if (v > pv) { pv = v; pr = r; }
+    }
+    if (!(pv > 0.0)) return 0;  // singular constraint system
+    if (pr != c)
+      for (int j = 0; j < 20; ++j) { double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
+    double piv = A[c][c];
+    for (int j = 0; j < 20; ++j) A[c][j] = A[c][j] / piv;
+    for (int r = 0; r < 10; ++r) {
+      if (r == c) continue;
+      double f = A[r][c];
+      for (int j = 0; j < 20; ++j) A[r][j] = A[r][j] - f * A[c][j];
+    }
+  }
+  // B(z): rows <k>=<e>-z<f>, <l>=<g>-z<h>, <m>=<i>-z<j>; columns [x y 1];
+  // coefficients ascending in z.
+  double Bz[3][3][5];
+  static const int RE[3] = {4, 6, 8}, RF[3] = {5, 7, 9};
+  for (int r = 0; r < 3; ++r) {
+    const double* e = A[RE[r]];
+    const double* f = A[RF[r]];
+    for (int col = 0; col < 2; ++col) {
+      int o = 10 + 3 * col;  // [.. z2, z, 1] blocks for x then y
+      Bz[r][col][0] = e[o + 2];
+      Bz[r][col][1] = e[o + 1] - f[o + 2];
+      Bz[r][col][2] = e[o + 0] - f[o + 1];
+      Bz[r][col][3] = -f[o + 0];
+      Bz[r][col][4] = 0.0;
+    }
+    Bz[r][2][0] = e[19];
+    Bz[r][2][1] = e[18] - f[19];
+    Bz[r][2][2] = e[17] - f[18];
+    Bz[r][2][3] = e[16] - f[17];
+    Bz[r][2][4] = -f[16];
+  }
+  // cofactors of the third row -> p1,p2,p3; det via expansion along row 2
+  double t1[9], t2[9], p1[8], p2[8], p3[7];
+  upmul(Bz[0][1], 3, Bz[1][2], 4, t1); upmul(Bz[0][2], 4, Bz[1][1], 3, t2);
+  for (int k = 0; k < 8; ++k) p1[k] = t1[k] - t2[k];
+  upmul(Bz[0][2], 4, Bz[1][0], 3, t1); upmul(Bz[0][0], 3, Bz[1][2], 4, t2);
+  for (int k = 0; k < 8; ++k) p2[k] = t1[k] - t2[k];
+  upmul(Bz[0][0], 3, Bz[1][1], 3, t1); upmul(Bz[0][1], 3, Bz[1][0], 3, t2);
+  for (int k = 0; k < 7; ++k) p3[k] = t1[k] - t2[k];
+  double n1[11], n2[11], n3[11], nz[11];
+  upmul(p1, 7, Bz[2][0], 3, n1);
+  upmul(p2, 7, Bz[2][1], 3, n2);
+  upmul(p3, 6, Bz[2][2], 4, n3);
+  for (int k = 0; k < 11; ++k) nz[k] = (n1[k] + n2[k]) + n3[k];
+  // reversed polynomial for |z| > 1
+  double rz[11];
+  for (int k = 0; k < 11; ++k) rz[k] = nz[10 - k];
+  double zr[20];
+  int nroots = 0;
+  {
+    double r[10];
+    int n = roots_unit(nz, 10, r);
+    for (int i = 0; i < n; ++i) zr[nroots++] = r[i];
+    n = roots_unit(rz, 10, r);
+    for (int i = 0; i < n; ++i) {
+      if (r[i] == 1.0 || r[i] == 0.0) continue;  // z=1 already covered; u=0 is z=inf
+      zr[nroots++] = 1.0 / r[i];
+    }
+  }
+  int ns = 0;
+  for (int k = 0; k < nroots && ns < 10; ++k) {
+    double z = zr[k];
+    double d = horner(p3, 6, z);
+    double x = horner(p1, 7, z) / d;
+    double y = horner(p2, 7, z) / d;
+    bool ok = true;
+    for (int e = 0; e < 9; ++e) {
+      double v = ((x * B[0][e] + y * B[1][e]) + z * B[2][e]) + B[3][e];
+      if (!std::isfinite(v)) ok = false;
+      E[ns][e] = v;
+    }
+    if (ok) ++ns;
+  }
+  return ns;
+}
+
+// A.6 computeModelCoefficients for NISTER: sample of 8 (5 solve + 3 extra).
+// f1/f2 are the full correspondence arrays [N][3]; model = [R12|t12] 3x4.
+static inline bool mono_model(const double* f1, const double* f2, const uint16_t* sample,
+                              double* model) {
+  double a[5][3], b[5][3];
+  for (int k = 0; k < 5; ++k)
+    for (int i = 0; i < 3; ++i) {
+      a[k][i] = f1[3 * sample[k] + i];
+      b[k][i] = f2[3 * sample[k] + i];
+    }
+  double E[10][9];
+  int ne = fivept_nister(a, b, E);
+  double best = 1000000.0;
+  bool found = false;
+  for (int e = 0; e < ne; ++e) {
+    double U[9], S[3], V[9];
+    svd3(E[e], U, S, V);
+    // Ra = U W V^T, Rb = U W^T V^T, W = [0 -1 0; 1 0 0; 0 0 1]
+    // U W   = [ u1 -u0 u2 ],  U W^T = [ -u1 u0 u2 ]  (columns)
+    double Ra[9], Rb[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double u0 = U[3 * r + 0], u1 = U[3 * r + 1], u2 = U[3 * r + 2];
+        double v0 = V[3 * c + 0], v1 = V[3 * c + 1], v2 = V[3 * c + 2];
+        Ra[3 * r + c] = (u1 * v0 - u0 * v1) + u2 * v2;
+        Rb[3 * r + c] = (u0 * v1 - u1 * v0) + u2 * v2;
+      }
+    double tt[3] = {S[0] * U[2], S[0] * U[5], S[0] * U[8]};
+    for (int cand = 0; cand < 4; ++cand) {
+      const double* R = (cand < 2) ? Ra : Rb;
+      double sgn = (cand & 1) ? -1.0 : 1.0;
+      double M[12];
+      for (int r = 0; r < 3; ++r) {
+        M[4 * r + 0] = R[3 * r + 0]; M[4 * r + 1] = R[3 * r + 1]; M[4 * r + 2] = R[3 * r + 2];
+        M[4 * r + 3] = sgn * tt[r];
+      }
+      double tinv[3];
+      mono_tinv(M, tinv);
+      double q = 0.0;
+      for (int k = 0; k < 8; ++k)
+        q = q + mono_residual(M, tinv, f1 + 3 * sample[k], f2 + 3 * sample[k]);
+      if (q < best) {
+        best = q;
+        found = true;
+        for (int i = 0; i < 12; ++i) model[i] = M[i];
+      }
+    }
+  }
+  return found;
+}
+
+}  // namespace kmo

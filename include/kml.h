@@ -1,0 +1,225 @@
+/*
+ * kml.h — C ABI of libkml.so, the B200-native loop-closure front end.
+ *
+ * Drop-in boundary for the data-parallel hot path of Kimera-Multi's
+ * distributed place recognition: kimera_multi_lcd::LoopClosureDetector
+ * (detectLoop / detectLoopWithRobot / computeMatchedIndices /
+ * geometricVerificationNister / recoverPose) with the DBoW2 database query,
+ * OpenCV BFMatcher kNN and OpenGV RANSAC underneath.  The reference keeps
+ * that code in un-vendored repositories (/root/reference/kimera_multi.repos:
+ * 14-17 dbow2_catkin, 54-57 kimera_multi_lcd, 102-105 opencv3_catkin,
+ * 106-109 opengv_catkin); the call graph each entry point replaces is drawn
+ * in /root/reference/images/kimera-multi.drawio:2533-2662 and the only
+ * literal source lines are /root/reference/docker/copy/kimera_multi_lcd.patch:
+ * 30-38 (LoopClosureDetector::loadAndInitialize).  Each declaration below
+ * cites the reference interface it stands in for.
+ *
+ * Conventions: plain C, every function returns int: 0 = ok, >0 = "no result"
+ * (the reference's `false` returns), <0 = error (kml_last_error() explains).
+ * Caller owns all inputs; the library copies what it keeps.  Outputs are
+ * caller-allocated (ptr, capacity, *count).  Arrays are row-major, packed,
+ * little-endian.  All host pointers are ordinary host memory.  There is no
+ * CPU fallback: every compute entry point launches sm_100a kernels and fails
+ * with KML_ERR_CUDA when no B200-class device is usable.
+ */
+#ifndef KML_H_
+#define KML_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KML_OK 0
+/* "no result" codes (reference returns false / empty) */
+#define KML_NO_DB 1             /* detectLoopWithRobot: no database for robot */
+#define KML_NO_PREV_BOW 2       /* no previous BoW vector for the NSS factor */
+#define KML_NSS_TOO_LOW 3       /* nss < min_nss_factor */
+#define KML_NO_MATCH 4          /* nothing survived the alpha*nss cut */
+#define KML_NO_FRAME 5          /* frameExists() false for one of the ids */
+#define KML_TOO_FEW_POINTS 6    /* fewer correspondences than the sample size */
+#define KML_RANSAC_FAIL 7       /* computeModel() returned false */
+#define KML_TOO_FEW_INLIERS 8   /* inlier count / ratio gate failed */
+#define KML_INTER_ROBOT_ONLY 9  /* intra-robot query with inter_robot_only */
+/* errors */
+#define KML_ERR_ARG (-1)
+#define KML_ERR_CUDA (-2)
+#define KML_ERR_NCCL (-3)
+#define KML_ERR_CAPACITY (-4)
+#define KML_ERR_STREAM_EXHAUSTED (-5) /* pre-drawn sample stream ran out */
+
+/* LcdParams / LcdTpParams (kimera_multi_lcd include/kimera_multi_lcd/types.h;
+ * set once in loadAndInitialize, kimera_multi_lcd.patch:30-31).  Defaults:
+ * /root/reference/params/D455/LcdParams.yaml and SURVEY.md Appendix D. */
+typedef struct kml_params {
+  int32_t inter_robot_only;
+  double alpha;
+  int32_t dist_local;
+  int32_t max_db_results;
+  double min_nss_factor;
+  int32_t max_nrFrames_between_queries;
+  int32_t max_nrFrames_between_islands; /* row f3 (islands) — stored, unused */
+  int32_t min_temporal_matches;         /* row f3 — stored, unused */
+  int32_t max_intraisland_gap;          /* row f3 — stored, unused */
+  int32_t min_matches_per_island;       /* row f3 — stored, unused */
+  double lowe_ratio;
+  double ransac_threshold_mono;
+  double ransac_inlier_percentage_mono;
+  int32_t max_ransac_iterations_mono;
+  double ransac_probability_mono;
+  double ransac_threshold;
+  int32_t max_ransac_iterations;
+  double ransac_probability;
+  int32_t geometric_verification_min_inlier_count;
+  double geometric_verification_min_inlier_percentage;
+  int32_t ransac_randomize; /* must be 0: the sample stream is pre-drawn */
+  uint32_t ransac_seed;     /* 12345 = OpenGV's fixed seed */
+  int32_t top_k_verify;     /* benchmark knob: candidates verified per query */
+} kml_params;
+
+/* One verified candidate (VLCEdge of kimera_distributed + the counters the
+ * evaluation scripts read: /root/reference/evaluation/lc_result.py:117-138). */
+typedef struct kml_result {
+  uint64_t q_robot, q_pose, m_robot, m_pose;
+  double norm_bow_score;
+  int32_t n_matches, mono_inliers, stereo_inliers;
+  int32_t status; /* 0 loop closure, 1 mono verification failed, 2 pose recovery failed, 3 frame missing */
+  double R_mono[9]; /* R_query_match of geometricVerificationNister */
+  double T[12];     /* T_query_match = [R|t] row-major 3x4, x_q = R x_m + t */
+} kml_result;
+
+/* logLcdStat() counters (/root/reference/images/kimera-multi.drawio:86-100)
+ * plus device timings (CUDA events on the handle's stream, last batch). */
+typedef struct kml_stats {
+  uint64_t total_bow_matches;
+  uint64_t total_geom_verifications_mono;
+  uint64_t total_geometric_verifications;
+  uint64_t kernel_launches; /* kernels launched by this handle so far */
+  float ms_bow, ms_match, ms_mono, ms_stereo, ms_total;
+  uint64_t bow_postings_last; /* inverted-file postings touched by the last batch */
+  uint64_t mono_hypotheses_last, stereo_hypotheses_last, pairs_last;
+} kml_stats;
+
+typedef struct kml_handle kml_handle;
+
+void kml_default_params(kml_params* p);
+/* loadAndInitialize(params) on CUDA device `device` */
+int kml_create(const kml_params* p, int device, kml_handle** out);
+int kml_destroy(kml_handle* h);
+const char* kml_last_error(const kml_handle* h); /* h may be NULL: last create error */
+int kml_get_stats(kml_handle* h, kml_stats* out);
+int kml_device_count(void);
+
+/* ---- database side ------------------------------------------------------ */
+/* LoopClosureDetector::addBowVector(RobotPoseId, BowVector); word ids must
+ * be ascending (DBoW2::BowVector is a std::map).  Weights are float32 as in
+ * pose_graph_tools BowVector.msg. */
+int kml_add_bow(kml_handle* h, uint64_t robot, uint64_t pose, const uint32_t* word_ids,
+                const float* word_vals, int n);
+/* bulk variant: `count` vectors in CSR form (off[count+1]) for one robot */
+int kml_add_bow_bulk(kml_handle* h, uint64_t robot, const uint64_t* poses, int count,
+                     const int64_t* off, const uint32_t* word_ids, const float* word_vals);
+/* LoopClosureDetector::addVLCFrame(RobotPoseId, VLCFrame): descriptors_mat_
+ * [F][32] CV_8U, versors_ [F][3] unit bearings, keypoints_ [F][3] 3-D points
+ * (zero = invalid depth). */
+int kml_add_frame(kml_handle* h, uint64_t robot, uint64_t pose, const uint8_t* desc,
+                  const double* bearings, const double* points, int F);
+int kml_add_frames_bulk(kml_handle* h, uint64_t robot, const uint64_t* poses, int count,
+                        const uint8_t* desc, const double* bearings, const double* points,
+                        int F);
+int kml_frame_exists(kml_handle* h, uint64_t robot, uint64_t pose); /* 1/0 */
+int kml_bow_exists(kml_handle* h, uint64_t robot, uint64_t pose);   /* 1/0 */
+int kml_num_bow_for_robot(kml_handle* h, uint64_t robot);
+int kml_get_bow_vector(kml_handle* h, uint64_t robot, uint64_t pose, uint32_t* ids,
+                       float* vals, int cap, int* count);
+
+/* DBoW2::TemplatedDatabase::query(vec, ret, max_results, max_id) on the
+ * database of `robot`; results best first, Score in [0,1]. */
+int kml_db_query(kml_handle* h, uint64_t robot, const uint32_t* ids, const float* vals, int n,
+                 int max_results, int max_id, uint32_t* out_entry, double* out_score, int cap,
+                 int* count);
+/* TemplatedVocabulary::score == L1Scoring::score */
+int kml_bow_score(kml_handle* h, const uint32_t* ids1, const float* vals1, int n1,
+                  const uint32_t* ids2, const float* vals2, int n2, double* out);
+
+/* ---- LoopClosureDetector query API -------------------------------------- */
+int kml_detect_loop_with_robot(kml_handle* h, uint64_t robot, uint64_t q_robot, uint64_t q_pose,
+                               const uint32_t* ids, const float* vals, int n,
+                               uint64_t* out_robot, uint64_t* out_pose, double* out_score,
+                               int cap, int* count);
+int kml_detect_loop(kml_handle* h, uint64_t q_robot, uint64_t q_pose, const uint32_t* ids,
+                    const float* vals, int n, uint64_t* out_robot, uint64_t* out_pose,
+                    double* out_score, int cap, int* count);
+int kml_compute_matched_indices(kml_handle* h, uint64_t q_robot, uint64_t q_pose,
+                                uint64_t m_robot, uint64_t m_pose, uint32_t* i_query,
+                                uint32_t* i_match, int cap, int* count);
+/* inl_q / inl_m / count are in-out, R = R_query_match (row-major 3x3) */
+int kml_geometric_verification_nister(kml_handle* h, uint64_t q_robot, uint64_t q_pose,
+                                      uint64_t m_robot, uint64_t m_pose, uint32_t* inl_q,
+                                      uint32_t* inl_m, int* count, double* R);
+/* T = T_query_match row-major 3x4; R_prior may be NULL (unused by Arun) */
+int kml_recover_pose(kml_handle* h, uint64_t q_robot, uint64_t q_pose, uint64_t m_robot,
+                     uint64_t m_pose, uint32_t* inl_q, uint32_t* inl_m, int* count,
+                     const double* R_prior, double* T);
+
+/* ---- batched fast paths -------------------------------------------------- */
+/* B full loop-closure queries: NSS + BoW scoring against every resident
+ * robot DB + alpha*nss cut + top_k_verify candidates + kNN/Lowe + mono 5-pt
+ * RANSAC + stereo Arun RANSAC.  BoW vectors in CSR form; query frames
+ * [B][F][...] travel with the batch; out[B][cap_per_query], counts[B]. */
+int kml_query_batch(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,
+                    const int64_t* bow_off, const uint32_t* ids, const float* vals,
+                    const int64_t* prev_off, const uint32_t* prev_ids, const float* prev_vals,
+                    const uint8_t* desc, const double* bearings, const double* points, int F,
+                    kml_result* out, int cap_per_query, int32_t* counts);
+/* Same, two-phase for measurement with inputs resident in HBM: upload once,
+ * then run the device pipeline any number of times. */
+int kml_query_batch_upload(kml_handle* h, int B, const uint64_t* q_robot,
+                           const uint64_t* q_pose, const int64_t* bow_off, const uint32_t* ids,
+                           const float* vals, const int64_t* prev_off, const uint32_t* prev_ids,
+                           const float* prev_vals, const uint8_t* desc, const double* bearings,
+                           const double* points, int F);
+int kml_query_batch_run(kml_handle* h, kml_result* out, int cap_per_query, int32_t* counts);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2): idx/dist are [nq][2];
+ * a missing neighbour is idx 0xFFFFFFFF, dist 0xFFFF.  ms_kernel (nullable)
+ * receives the device time of the matching kernels. */
+int kml_hamming_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+                     uint32_t* idx, uint16_t* dist, float* ms_kernel);
+/* resident variant for roofline measurement: upload once, run `reps` times */
+int kml_hamming_knn2_bench(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t,
+                           int64_t nt, int reps, uint32_t* idx, uint16_t* dist, float* ms_avg);
+
+/* Batched opengv::sac::Ransac<PointCloudSacProblem> (Arun): P problems with
+ * N correspondences each, p1/p2 [P][N][3].  Evaluates the draws the
+ * reference loop would consume; per problem: model[12], n_inliers,
+ * iterations, best_draw, inlier mask bits [P][ceil(N/32)] (nullable).
+ * full_hypotheses != 0 disables the adaptive stop (config C4: evaluate all
+ * max_iterations+1 hypotheses, the winner is the first best). */
+int kml_ransac_arun_batch(kml_handle* h, int P, int N, const double* p1, const double* p2,
+                          int full_hypotheses, double* models, int32_t* n_inliers,
+                          int32_t* iterations, int32_t* best_draw, uint32_t* inlier_mask,
+                          float* ms_kernel);
+/* Batched Ransac<CentralRelativePoseSacProblem>(NISTER): f1/f2 [P][N][3]. */
+int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const double* f2,
+                            int full_hypotheses, double* models, int32_t* n_inliers,
+                            int32_t* iterations, int32_t* best_draw, uint32_t* inlier_mask,
+                            float* ms_kernel);
+
+/* microbenchmarks for the roofline denominators (ops per second) */
+int kml_peak_popc(kml_handle* h, double* popc32_per_s);
+int kml_peak_fp64(kml_handle* h, double* flop_per_s);
+
+/* ---- multi-GPU (one process per GPU; databases sharded by robot) -------- */
+#define KML_UNIQUE_ID_BYTES 128
+int kml_comm_unique_id(void* id_out /* KML_UNIQUE_ID_BYTES */);
+int kml_comm_init(kml_handle* h, int nranks, int rank, const void* unique_id);
+/* every rank passes the same batch; each scores/verifies against its own
+ * shard; per-rank top-k records are merged with one ncclAllGather and every
+ * rank receives the merged, globally re-ranked list. */
+int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap_per_query,
+                            int32_t* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,239 @@
+// api_core.cu — handle lifecycle, Hamming kNN entry points, peak probes.
+#include <algorithm>
+#include <cstring>
+#include <random>
+
+#include "handle.h"
+
+using namespace kml;
+
+static thread_local std::string g_create_err;
+
+#define KML_API_BEGIN(h)                              \
+  if (!(h)) return KML_ERR_ARG;                       \
+  try {                                               \
+    KML_CUDA(cudaSetDevice((h)->device));
+#define KML_API_END(h)                                \
+  }                                                   \
+  catch (const kml::CudaError& e) {                   \
+    (h)->err = e.what();                              \
+    cudaGetLastError();                               \
+    return KML_ERR_CUDA;                              \
+  }                                                   \
+  catch (const std::exception& e) {                   \
+    (h)->err = e.what();                              \
+    return KML_ERR_ARG;                               \
+  }
+
+extern "C" {
+
+void kml_default_params(kml_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->inter_robot_only = 0;
+  p->alpha = 0.5;
+  p->dist_local = 90;
+  p->max_db_results = 50;
+  p->min_nss_factor = 0.05;
+  p->max_nrFrames_between_queries = 2;
+  p->max_nrFrames_between_islands = 3;
+  p->min_temporal_matches = 1;
+  p->max_intraisland_gap = 3;
+  p->min_matches_per_island = 1;
+  p->lowe_ratio = 0.9;
+  p->ransac_threshold_mono = 1e-6;
+  p->ransac_inlier_percentage_mono = 0.01;
+  p->max_ransac_iterations_mono = 1000;
+  p->ransac_probability_mono = 0.995;
+  p->ransac_threshold = 0.5;
+  p->max_ransac_iterations = 1000;
+  p->ransac_probability = 0.995;
+  p->geometric_verification_min_inlier_count = 5;
+  p->geometric_verification_min_inlier_percentage = 0.0;
+  p->ransac_randomize = 0;
+  p->ransac_seed = 12345u;
+  p->top_k_verify = 16;
+}
+
+int kml_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int kml_create(const kml_params* p, int device, kml_handle** out) {
+  if (!out) return KML_ERR_ARG;
+  *out = nullptr;
+  kml_handle* h = nullptr;
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      g_create_err = "no CUDA device: libkml has no CPU fallback";
+      return KML_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+      g_create_err = "bad device index";
+      return KML_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    KML_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+      g_create_err = std::string("device is sm_") + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; libkml kernels are built for sm_100a only";
+      return KML_ERR_CUDA;
+    }
+    h = new kml_handle();
+    if (p) h->prm = *p; else kml_default_params(&h->prm);
+    if (h->prm.ransac_randomize != 0) {
+      g_create_err = "ransac_randomize must be 0 (pre-drawn sample stream)";
+      delete h;
+      return KML_ERR_ARG;
+    }
+    if (h->prm.max_db_results > kBowMaxK || h->prm.max_db_results < 1) {
+      g_create_err = "max_db_results must be in [1,128]";
+      delete h;
+      return KML_ERR_ARG;
+    }
+    h->device = device;
+    KML_CUDA(cudaSetDevice(device));
+    KML_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e2 : h->ev) KML_CUDA(cudaEventCreate(&e2));
+    // pre-drawn sample stream: mt19937(seed)() >> 1  
+    const int max_it = std::max(h->prm.max_ransac_iterations_mono, h->prm.max_ransac_iterations);
+    const size_t draws = (size_t)max_it + 1 + 256;
+    h->raw_h.resize(draws * 8);
+    std::mt19937 mt(h->prm.ransac_seed);
+    for (auto& r : h->raw_h) r = (uint32_t)mt() >> 1;
+    h->d_raw.scratch(h->raw_h.size());
+    KML_CUDA(cudaMemcpy(h->d_raw.p, h->raw_h.data(), h->raw_h.size() * 4, cudaMemcpyHostToDevice));
+    *out = h;
+    return KML_OK;
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    cudaGetLastError();
+    delete h;
+    return KML_ERR_CUDA;
+  }
+}
+
+void kml_comm_destroy_internal(kml_handle* h);
+
+int kml_destroy(kml_handle* h) {
+  if (!h) return KML_ERR_ARG;
+  cudaSetDevice(h->device);
+  kml_comm_destroy_internal(h);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  delete h;
+  return KML_OK;
+}
+
+const char* kml_last_error(const kml_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int kml_get_stats(kml_handle* h, kml_stats* out) {
+  if (!h || !out) return KML_ERR_ARG;
+  *out = h->stats;
+  return KML_OK;
+}
+
+// ------------------------------------------------------------- Hamming kNN
+static void knn2_device(kml_handle* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int64_t nt,
+                        uint32_t* d_idx, uint16_t* d_dist, int reps, float* ms_avg) {
+  // split the train set into ranges (one CTA each); >= 2 CTAs per SM when large
+  int64_t range_len = (nt + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  range_len = ((range_len + 511) / 512) * 512;
+  range_len = std::max<int64_t>(512, std::min<int64_t>(range_len, 1 << 20));
+  const int nranges = nt > 0 ? (int)((nt + range_len - 1) / range_len) : 1;
+  h->d_keys.scratch((size_t)nranges * nq * 2);
+  std::vector<HamJob> jobs(nranges);
+  for (int r = 0; r < nranges; ++r) {
+    jobs[r].q = d_q;
+    jobs[r].nq = nq;
+    jobs[r].t = d_t + (size_t)r * range_len * 32;
+    jobs[r].nt = (int)std::max<int64_t>(0, std::min<int64_t>(range_len, nt - (int64_t)r * range_len));
+    jobs[r].keys = h->d_keys.p + (size_t)r * nq * 2;
+  }
+  h->d_jobs.scratch(nranges);
+  KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(HamJob) * nranges,
+                           cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  float total = 0.f;
+  for (int rep = 0; rep < reps; ++rep) {
+    KML_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    launch_hamming_jobs(h->d_jobs.p, nranges, h->stream);
+    launch_knn2_reduce(h->d_keys.p, nranges, nq, range_len, d_idx, d_dist, h->stream);
+    KML_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    KML_CUDA(cudaGetLastError());
+    KML_CUDA(cudaEventSynchronize(h->ev[1]));
+    float ms = 0;
+    KML_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    total += ms;
+    h->stats.kernel_launches += 2;
+  }
+  if (ms_avg) *ms_avg = total / std::max(reps, 1);
+}
+
+static int knn2_host(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+                     int reps, uint32_t* idx, uint16_t* dist, float* ms) {
+  if (nq < 0 || nt < 0 || (nq > 0 && !q) || (nt > 0 && !t) || !idx || !dist) {
+    h->err = "kml_hamming_knn2: bad argument";
+    return KML_ERR_ARG;
+  }
+  if (nq == 0) return KML_OK;
+  h->d_scratch.scratch((size_t)nq * 32 + 16);
+  h->d_scratch2.scratch((size_t)std::max<int64_t>(nt, 1) * 32 + 16);
+  KML_CUDA(cudaMemcpyAsync(h->d_scratch.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+  if (nt > 0)
+    KML_CUDA(cudaMemcpyAsync(h->d_scratch2.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, h->stream));
+  DevBuf<uint32_t> d_idx;
+  DevBuf<uint16_t> d_dist;
+  d_idx.scratch((size_t)nq * 2);
+  d_dist.scratch((size_t)nq * 2);
+  knn2_device(h, h->d_scratch.p, nq, h->d_scratch2.p, nt, d_idx.p, d_dist.p, reps, ms);
+  KML_CUDA(cudaMemcpyAsync(idx, d_idx.p, sizeof(uint32_t) * nq * 2, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaMemcpyAsync(dist, d_dist.p, sizeof(uint16_t) * nq * 2, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  return KML_OK;
+}
+
+int kml_hamming_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+                     uint32_t* idx, uint16_t* dist, float* ms_kernel) {
+  KML_API_BEGIN(h)
+  return knn2_host(h, q, nq, t, nt, 1, idx, dist, ms_kernel);
+  KML_API_END(h)
+}
+
+int kml_hamming_knn2_bench(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+                           int reps, uint32_t* idx, uint16_t* dist, float* ms_avg) {
+  KML_API_BEGIN(h)
+  return knn2_host(h, q, nq, t, nt, std::max(reps, 1), idx, dist, ms_avg);
+  KML_API_END(h)
+}
+
+int kml_peak_popc(kml_handle* h, double* out) {
+  KML_API_BEGIN(h)
+  if (!out) return KML_ERR_ARG;
+  *out = measure_popc_peak(h->stream);
+  h->stats.kernel_launches += 5;
+  return KML_OK;
+  KML_API_END(h)
+}
+int kml_peak_fp64(kml_handle* h, double* out) {
+  KML_API_BEGIN(h)
+  if (!out) return KML_ERR_ARG;
+  *out = measure_fp64_peak(h->stream);
+  h->stats.kernel_launches += 5;
+  return KML_OK;
+  KML_API_END(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// handle.h — kml_handle: host-side state of the LoopClosureDetector replacement.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/kml.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace kml {
+
+typedef std::pair<uint64_t, uint64_t> RobotPoseId;
+
+struct HostBow {
+  std::vector<uint32_t> ids;
+  std::vector<float> vals;
+};
+
+// One robot's DBoW2-style database: host append log + lazily rebuilt device CSR.
+struct RobotDb {
+  uint64_t robot = 0;
+  // host log (entry order == insertion order == DBoW2 EntryId)
+  std::vector<int64_t> off{0};
+  std::vector<uint32_t> ids;
+  std::vector<float> vals;
+  std::vector<uint64_t> entry_to_pose;
+  std::map<uint64_t, uint32_t> pose_to_entry;
+  // device CSR
+  bool dirty = true;
+  uint32_t W = 0;
+  DevBuf<uint32_t> row_ptr;
+  DevBuf<uint2> postings;
+  uint32_t n_entries() const { return (uint32_t)entry_to_pose.size(); }
+};
+
+struct FrameRec {
+  int64_t feat_off;  // offset into the feature arenas
+  int32_t F;
+  int32_t index;     // dense frame index
+};
+
+struct Comm;  // NCCL state (comm.cu)
+
+}  // namespace kml
+
+struct kml_handle {
+  kml_params prm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string err;
+  kml_stats stats = {};
+
+  // ---- BoW databases (one per robot, ordered: detectLoop visits ascending)
+  std::map<uint64_t, std::unique_ptr<kml::RobotDb>> dbs;
+  kml::DevBuf<kml::BowDb> d_dbs;
+  kml::DevBuf<int32_t> d_maxid;
+
+  // ---- frame store (feature arenas in HBM)
+  std::map<kml::RobotPoseId, kml::FrameRec> frames;
+  std::vector<int64_t> frame_off_h;  // per dense frame index
+  std::vector<int32_t> frame_F_h;
+  int64_t n_feat = 0;
+  kml::DevBuf<uint8_t> s_desc;     // [n_feat][32]
+  kml::DevBuf<double> s_bear;      // [n_feat][3]
+  kml::DevBuf<double> s_pts;       // [n_feat][3]
+  kml::DevBuf<int64_t> s_off;      // [n_frames]
+  bool s_off_dirty = true;
+
+  // ---- pre-drawn sample stream + k tables
+  std::vector<uint32_t> raw_h;
+  kml::DevBuf<uint32_t> d_raw;
+  int ktable_n_mono = 0, ktable_n_stereo = 0;
+  kml::DevBuf<double> d_ktable_mono, d_ktable_stereo;
+
+  // ---- batch buffers (query side)
+  int B = 0, qF = 0;
+  std::vector<uint64_t> q_robot_h, q_pose_h;
+  kml::DevBuf<int64_t> d_qoff, d_poff;
+  kml::DevBuf<uint32_t> d_qids, d_pids;
+  kml::DevBuf<float> d_qvals, d_pvals;
+  kml::DevBuf<uint8_t> d_qdesc;
+  kml::DevBuf<double> d_qbear, d_qpts;
+  // BoW outputs
+  kml::DevBuf<uint32_t> d_bow_entry;
+  kml::DevBuf<double> d_bow_score, d_nss;
+  kml::DevBuf<int32_t> d_bow_count;
+  kml::DevBuf<unsigned long long> d_postings;
+  kml::PinBuf<uint32_t> h_bow_entry;
+  kml::PinBuf<double> h_bow_score, h_nss;
+  kml::PinBuf<int32_t> h_bow_count;
+  // verification buffers
+  kml::DevBuf<kml::PairDesc> d_pairs;
+  kml::DevBuf<kml::HamJob> d_jobs;
+  kml::DevBuf<uint32_t> d_keys;
+  kml::DevBuf<int32_t> d_nq, d_M, d_N3, d_mono_ok, d_status, d_out_mono, d_out_stereo;
+  kml::DevBuf<uint16_t> d_iq, d_im, d_kq, d_km;
+  kml::DevBuf<double> d_a, d_b, d_models, d_best_mono, d_best_stereo, d_outR, d_outT;
+  kml::DevBuf<uint16_t> d_perm, d_samples;
+  kml::DevBuf<int32_t> d_valid, d_counts, d_inl_mono, d_inl_stereo;
+  kml::DevBuf<kml::SacState> d_st_mono, d_st_stereo;
+  kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
+  kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
+  kml::DevBuf<uint8_t> d_scratch, d_scratch2;
+
+  kml::Comm* comm = nullptr;
+};

@@ -1,0 +1,140 @@
+// kernels.h — host-callable launchers of the sm_100a kernels of libkml.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kml {
+
+// ------------------------------------------------------------- hamming.cu
+struct HamJob {
+  const uint8_t* q;  // query descriptors [nq][32]
+  const uint8_t* t;  // train descriptors [nt][32], nt <= 2^20
+  uint32_t* keys;    // out [nq][2] packed (dist<<20 | trainIdx), 0xFFFFFFFF = none
+  int nq, nt;
+};
+void launch_hamming_jobs(const HamJob* d_jobs, int njobs, cudaStream_t s);
+void launch_knn2_reduce(const uint32_t* partial, int nranges, int nq, int64_t range_len,
+                        uint32_t* idx, uint16_t* dist, cudaStream_t s);
+void launch_lowe_compact(const uint32_t* keys, const int* nq_arr, int key_stride, double lowe,
+                         uint16_t* iq, uint16_t* im, int* M, int P, cudaStream_t s);
+double measure_popc_peak(cudaStream_t s);
+double measure_fp64_peak(cudaStream_t s);
+
+// ----------------------------------------------------------------- bow.cu
+// Device view of one robot's inverted file (CSR over word ids).
+struct BowDb {
+  const uint32_t* row_ptr;  // [W+1]
+  const uint2* postings;    // {entry, float bits of weight}, rows ascending in entry
+  uint32_t W;               // number of word rows
+  uint32_t n_entries;
+};
+constexpr int kBowMaxWords = 1024;  // max words per BoW vector handled on device
+constexpr int kBowMaxK = 128;       // max max_results handled on device
+constexpr double kBowScale = 4611686018427387904.0;  // 2^62 fixed-point scale
+// One CTA per (query, db, entry tile).  Query BoWs in CSR form (q_off).
+// out_entry/out_score: [B][n_db][n_tiles][K]; out_count: [B][n_db][n_tiles].
+// nss (nullable): [B] L1 score between query and prev BoW.
+struct BowArgs {
+  const BowDb* dbs;
+  int n_db;
+  int B;
+  const int64_t* q_off;
+  const uint32_t* q_ids;
+  const float* q_vals;
+  const int64_t* p_off;  // previous BoW (nullable with nss == nullptr)
+  const uint32_t* p_ids;
+  const float* p_vals;
+  int K;
+  const int32_t* max_id;  // [n_db] or nullptr (-1 = no limit)
+  int tile_entries;       // entries per tile (shared-memory accumulators)
+  int n_tiles;
+  uint32_t* out_entry;
+  double* out_score;
+  int32_t* out_count;
+  double* nss;
+  unsigned long long* postings_touched;  // nullable: algorithmic postings counter
+};
+void launch_bow(const BowArgs& a, cudaStream_t s);
+
+// -------------------------------------------------------------- ransac.cu
+// Per-pair RANSAC state (opengv::sac::Ransac::computeModel locals)
+struct SacState {
+  int32_t iterations, skipped, draws, best, best_draw, done, exhausted, pad;
+  double k;
+};
+struct SacArgs {
+  int P;                 // problems
+  const double* a;       // mono: query bearings; stereo: query points   [P][stride][3]
+  const double* b;       // mono: match bearings; stereo: match points   [P][stride][3]
+  const int32_t* N;      // correspondences per problem [P]
+  int stride;            // row stride (max correspondences)
+  const uint32_t* raw;   // pre-drawn mt19937()>>1 stream
+  int raw_len;
+  uint16_t* perm;        // [P][stride] persistent shuffle state
+  uint16_t* samples;     // [P][chunk][S]
+  double* models;        // [P][chunk][12]
+  int32_t* valid;        // [P][chunk]
+  int32_t* counts;       // [P][chunk]
+  SacState* st;          // [P]
+  double* best_model;    // [P][12]
+  const double* ktable;  // [(Nmax+1)*(Nmax+1)] k as function of (N, best count)
+  int ktable_n;          // Nmax+1
+  double threshold;      // mono: 1-cos sum threshold; stereo: metres
+  double sq_crit;        // stereo: smallest s with sqrt(s) >= threshold
+  int max_iterations;
+  int full;              // evaluate every draw up to max_iterations+1 (no adaptive stop)
+  uint32_t* inlier_mask; // [P][mask_words]
+  int mask_words;
+  int32_t* n_inliers;    // [P]
+};
+constexpr int kMonoChunk = 64;
+constexpr int kStereoChunk = 128;
+void launch_sac_init(const SacArgs& a, cudaStream_t s);
+int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);    // returns #kernels launched
+int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s);
+void launch_mono_select(const SacArgs& a, cudaStream_t s);
+void launch_stereo_select(const SacArgs& a, cudaStream_t s);
+
+// gather kernels between the stages of the verification pipeline
+struct PairDesc {
+  int32_t q_slot;   // index into the batch's query frames
+  int32_t m_frame;  // index into the frame store
+};
+struct GatherArgs {
+  int P;
+  const PairDesc* pairs;
+  // query frames of the batch
+  const double* qb; const double* qp; int qF;       // bearings / points [B][qF][3]
+  // frame store
+  const double* sb; const double* sp;               // bearings / points [total_feat][3]
+  const int64_t* s_off;                             // feature offset per stored frame
+  // matches
+  const uint16_t* iq; const uint16_t* im; const int32_t* M; int stride;
+  // outputs
+  double* a; double* b;                             // [P][stride][3]
+  int32_t* N;                                       // [P]
+};
+void launch_gather_bearings(const GatherArgs& g, cudaStream_t s);
+// stereo gather: from mono inlier mask keep pairs with both 3-D norms > 1e-3;
+// also rewrites (iq, im) to the kept subset (kq, km).  Gated by mono success.
+struct StereoGatherArgs {
+  GatherArgs g;
+  const uint32_t* mono_mask; int mask_words;
+  const int32_t* mono_ok;                            // [P] 1 if mono verification passed
+  uint16_t* kq; uint16_t* km;                        // [P][stride]
+};
+void launch_gather_points(const StereoGatherArgs& g, cudaStream_t s);
+// mono acceptance gate + final record assembly
+struct FinalizeArgs {
+  int P;
+  const SacState* mono_st; const int32_t* mono_inl; const int32_t* M; const double* mono_model;
+  const SacState* st3; const int32_t* inl3; const int32_t* N3; const double* model3;
+  int min_inliers; double min_ratio_mono; double min_ratio_stereo;
+  int32_t* mono_ok;  // out (phase 1)
+  // phase 2 outputs
+  int32_t* status; int32_t* out_mono_inl; int32_t* out_stereo_inl; double* out_R; double* out_T;
+};
+void launch_mono_gate(const FinalizeArgs& f, cudaStream_t s);
+void launch_finalize(const FinalizeArgs& f, cudaStream_t s);
+
+}  // namespace kml

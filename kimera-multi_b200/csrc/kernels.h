@@ -89,7 +89,7 @@ struct SacArgs {
 };
 constexpr int kMonoChunk = 64;
 constexpr int kStereoChunk = 128;
-void launch_sac_init(const SacArgs& a, cudaStream_t s);
+void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);    // returns #kernels launched
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s);
 void launch_mono_select(const SacArgs& a, cudaStream_t s);

@@ -1,0 +1,1119 @@
+// lcd.cu — host side of the LoopClosureDetector replacement: database and
+// frame store residency in HBM, candidate selection (detectLoopWithRobot
+// post-processing), and the device verification pipeline
+// (computeMatchedIndices -> geometricVerificationNister -> recoverPose,
+// SURVEY.md A.4-A.8; call order of kimera_distributed's verifyLoopSpin,
+// /root/reference/images/kimera-multi.drawio:2638-2654).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "handle.h"
+
+using namespace kml;
+
+namespace kml {
+int comm_nranks(const kml_handle* h);
+int comm_rank(const kml_handle* h);
+int comm_allgather(kml_handle* h, const void* d_send, void* d_recv, size_t bytes);
+}  // namespace kml
+
+#define KML_API_BEGIN(h)                              \
+  if (!(h)) return KML_ERR_ARG;                       \
+  try {                                               \
+    KML_CUDA(cudaSetDevice((h)->device));
+#define KML_API_END(h)                                \
+  }                                                   \
+  catch (const kml::CudaError& e) {                   \
+    (h)->err = e.what();                              \
+    cudaGetLastError();                               \
+    return KML_ERR_CUDA;                              \
+  }                                                   \
+  catch (const std::exception& e) {                   \
+    (h)->err = e.what();                              \
+    return KML_ERR_ARG;                               \
+  }
+
+static int fail(kml_handle* h, int code, const char* msg) {
+  h->err = msg;
+  return code;
+}
+
+// ===================================================================== DB
+static RobotDb* get_db(kml_handle* h, uint64_t robot, bool create) {
+  auto it = h->dbs.find(robot);
+  if (it != h->dbs.end()) return it->second.get();
+  if (!create) return nullptr;
+  auto db = std::unique_ptr<RobotDb>(new RobotDb());
+  db->robot = robot;
+  RobotDb* p = db.get();
+  h->dbs[robot] = std::move(db);
+  return p;
+}
+
+static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_t* ids,
+                        const float* vals, int n) {
+  if (n < 0 || (n > 0 && (!ids || !vals))) return fail(h, KML_ERR_ARG, "add_bow: bad argument");
+  if (n > kBowMaxWords) return fail(h, KML_ERR_CAPACITY, "add_bow: more than 1024 words");
+  for (int i = 1; i < n; ++i)
+    if (ids[i] <= ids[i - 1]) return fail(h, KML_ERR_ARG, "add_bow: word ids must be strictly ascending");
+  if (db->pose_to_entry.count(pose)) return KML_OK;  // addBowVector: already present -> no-op
+  const uint32_t entry = db->n_entries();
+  db->pose_to_entry[pose] = entry;
+  db->entry_to_pose.push_back(pose);
+  db->ids.insert(db->ids.end(), ids, ids + n);
+  db->vals.insert(db->vals.end(), vals, vals + n);
+  db->off.push_back((int64_t)db->ids.size());
+  db->dirty = true;
+  return KML_OK;
+}
+
+// rebuild the CSR inverted file of a robot (counting sort by word id; rows
+// come out ascending in entry id because entries are visited in order)
+static void rebuild_csr(kml_handle* h, RobotDb* db) {
+  uint32_t W = 0;
+  for (uint32_t w : db->ids) W = std::max(W, w + 1);
+  std::vector<uint32_t> row_ptr((size_t)W + 1, 0);
+  for (uint32_t w : db->ids) row_ptr[w + 1]++;
+  for (uint32_t w = 0; w < W; ++w) row_ptr[w + 1] += row_ptr[w];
+  std::vector<uint2> post(db->ids.size());
+  std::vector<uint32_t> cur(row_ptr.begin(), row_ptr.end() - (W ? 1 : 0));
+  if (W == 0) cur.clear();
+  const uint32_t ne = db->n_entries();
+  for (uint32_t e = 0; e < ne; ++e)
+    for (int64_t k = db->off[e]; k < db->off[e + 1]; ++k) {
+      uint32_t bits;
+      memcpy(&bits, &db->vals[k], 4);
+      post[cur[db->ids[k]]++] = make_uint2(e, bits);
+    }
+  db->row_ptr.scratch(row_ptr.size());
+  db->postings.scratch(std::max<size_t>(post.size(), 1));
+  KML_CUDA(cudaMemcpyAsync(db->row_ptr.p, row_ptr.data(), row_ptr.size() * 4,
+                           cudaMemcpyHostToDevice, h->stream));
+  if (!post.empty())
+    KML_CUDA(cudaMemcpyAsync(db->postings.p, post.data(), post.size() * sizeof(uint2),
+                             cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  db->W = W;
+  db->dirty = false;
+}
+
+static BowDb db_view(kml_handle* h, RobotDb* db) {
+  if (db->dirty) rebuild_csr(h, db);
+  BowDb v;
+  v.row_ptr = db->row_ptr.p;
+  v.postings = db->postings.p;
+  v.W = db->W;
+  v.n_entries = db->n_entries();
+  return v;
+}
+
+// Host-visible result of one BoW launch
+struct BowOut {
+  int B = 0, n_db = 0, K = 0;
+  std::vector<uint32_t> entry;  // [B][n_db][K]
+  std::vector<double> score;
+  std::vector<int32_t> count;   // [B][n_db]
+  std::vector<double> nss;      // [B]
+};
+
+// Score B query vectors (device CSR form) against the given databases.
+static void run_bow(kml_handle* h, const std::vector<RobotDb*>& dbs, int B, const int64_t* d_qoff,
+                    const uint32_t* d_qids, const float* d_qvals, const int64_t* d_poff,
+                    const uint32_t* d_pids, const float* d_pvals, int K,
+                    const std::vector<int32_t>* max_id, BowOut* out) {
+  const int n_db = (int)dbs.size();
+  out->B = B; out->n_db = n_db; out->K = K;
+  out->entry.assign((size_t)B * n_db * K, 0);
+  out->score.assign((size_t)B * n_db * K, 0.0);
+  out->count.assign((size_t)B * n_db, 0);
+  out->nss.assign(B, 0.0);
+  if (B <= 0 || n_db <= 0) return;
+  std::vector<BowDb> views(n_db);
+  uint32_t max_entries = 1;
+  for (int i = 0; i < n_db; ++i) {
+    views[i] = db_view(h, dbs[i]);
+    max_entries = std::max(max_entries, views[i].n_entries);
+  }
+  const int tile_cap = 24576;  // 192 KB of u64 accumulators
+  int tile = (int)std::min<uint32_t>(max_entries, tile_cap);
+  tile = std::max(256, ((tile + 255) / 256) * 256);
+  const int n_tiles = (int)((max_entries + tile - 1) / tile);
+  h->d_dbs.scratch(n_db);
+  KML_CUDA(cudaMemcpyAsync(h->d_dbs.p, views.data(), sizeof(BowDb) * n_db, cudaMemcpyHostToDevice, h->stream));
+  const int32_t* d_maxid = nullptr;
+  if (max_id) {
+    h->d_maxid.scratch(n_db);
+    KML_CUDA(cudaMemcpyAsync(h->d_maxid.p, max_id->data(), sizeof(int32_t) * n_db, cudaMemcpyHostToDevice, h->stream));
+    d_maxid = h->d_maxid.p;
+  }
+  const size_t nlist = (size_t)B * n_db * n_tiles;
+  h->d_bow_entry.scratch(nlist * K);
+  h->d_bow_score.scratch(nlist * K);
+  h->d_bow_count.scratch(nlist);
+  h->d_nss.scratch(B);
+  h->d_postings.scratch(1);
+  KML_CUDA(cudaMemsetAsync(h->d_postings.p, 0, sizeof(unsigned long long), h->stream));
+  KML_CUDA(cudaMemsetAsync(h->d_nss.p, 0, sizeof(double) * B, h->stream));
+  BowArgs a;
+  a.dbs = h->d_dbs.p; a.n_db = n_db; a.B = B;
+  a.q_off = d_qoff; a.q_ids = d_qids; a.q_vals = d_qvals;
+  a.p_off = d_poff; a.p_ids = d_pids; a.p_vals = d_pvals;
+  a.K = K; a.max_id = d_maxid; a.tile_entries = tile; a.n_tiles = n_tiles;
+  a.out_entry = h->d_bow_entry.p; a.out_score = h->d_bow_score.p; a.out_count = h->d_bow_count.p;
+  a.nss = d_poff ? h->d_nss.p : nullptr;
+  a.postings_touched = h->d_postings.p;
+  KML_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  launch_bow(a, h->stream);
+  KML_CUDA(cudaGetLastError());
+  KML_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  h->stats.kernel_launches += 1;
+  h->h_bow_entry.scratch(nlist * K);
+  h->h_bow_score.scratch(nlist * K);
+  h->h_bow_count.scratch(nlist);
+  h->h_nss.scratch(B + 1);
+  KML_CUDA(cudaMemcpyAsync(h->h_bow_entry.p, h->d_bow_entry.p, nlist * K * 4, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaMemcpyAsync(h->h_bow_score.p, h->d_bow_score.p, nlist * K * 8, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaMemcpyAsync(h->h_bow_count.p, h->d_bow_count.p, nlist * 4, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaMemcpyAsync(h->h_nss.p, h->d_nss.p, B * 8, cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long postings = 0;
+  KML_CUDA(cudaMemcpyAsync(&postings, h->d_postings.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_bow, h->ev[0], h->ev[1]));
+  h->stats.bow_postings_last = postings;
+  for (int b = 0; b < B; ++b) out->nss[b] = h->h_nss.p[b];
+  // merge entry tiles (each tile's list is already sorted best-first)
+  std::vector<std::pair<double, uint32_t>> tmp;
+  for (int b = 0; b < B; ++b)
+    for (int d = 0; d < n_db; ++d) {
+      const size_t l0 = ((size_t)b * n_db + d) * n_tiles;
+      uint32_t* oe = &out->entry[((size_t)b * n_db + d) * K];
+      double* os = &out->score[((size_t)b * n_db + d) * K];
+      if (n_tiles == 1) {
+        const int c = h->h_bow_count.p[l0];
+        memcpy(oe, h->h_bow_entry.p + l0 * K, sizeof(uint32_t) * c);
+        memcpy(os, h->h_bow_score.p + l0 * K, sizeof(double) * c);
+        out->count[(size_t)b * n_db + d] = c;
+        continue;
+      }
+      tmp.clear();
+      for (int t = 0; t < n_tiles; ++t)
+        for (int i = 0; i < h->h_bow_count.p[l0 + t]; ++i)
+          tmp.emplace_back(-h->h_bow_score.p[(l0 + t) * K + i], h->h_bow_entry.p[(l0 + t) * K + i]);
+      std::sort(tmp.begin(), tmp.end());  // score desc, entry asc
+      const int c = (int)std::min<size_t>(tmp.size(), K);
+      for (int i = 0; i < c; ++i) { oe[i] = tmp[i].second; os[i] = -tmp[i].first; }
+      out->count[(size_t)b * n_db + d] = c;
+    }
+}
+
+// upload one host BoW vector (and optionally a second one) in CSR form
+static void upload_single_bow(kml_handle* h, const uint32_t* ids, const float* vals, int n,
+                              const uint32_t* pids, const float* pvals, int pn) {
+  int64_t off[2] = {0, n}, poff[2] = {0, pn};
+  h->d_qoff.scratch(2); h->d_poff.scratch(2);
+  h->d_qids.scratch(std::max(n, 1)); h->d_qvals.scratch(std::max(n, 1));
+  h->d_pids.scratch(std::max(pn, 1)); h->d_pvals.scratch(std::max(pn, 1));
+  KML_CUDA(cudaMemcpyAsync(h->d_qoff.p, off, 16, cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaMemcpyAsync(h->d_poff.p, poff, 16, cudaMemcpyHostToDevice, h->stream));
+  if (n) {
+    KML_CUDA(cudaMemcpyAsync(h->d_qids.p, ids, 4 * n, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->d_qvals.p, vals, 4 * n, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (pn) {
+    KML_CUDA(cudaMemcpyAsync(h->d_pids.p, pids, 4 * pn, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->d_pvals.p, pvals, 4 * pn, cudaMemcpyHostToDevice, h->stream));
+  }
+  KML_CUDA(cudaStreamSynchronize(h->stream));  // host arrays `off` go out of scope
+}
+
+static int check_bow(kml_handle* h, const uint32_t* ids, const float* vals, int n) {
+  if (n < 0 || (n > 0 && (!ids || !vals))) return fail(h, KML_ERR_ARG, "bad BoW vector");
+  if (n > kBowMaxWords) return fail(h, KML_ERR_CAPACITY, "BoW vector has more than 1024 words");
+  for (int i = 1; i < n; ++i)
+    if (ids[i] <= ids[i - 1]) return fail(h, KML_ERR_ARG, "BoW word ids must be strictly ascending");
+  return KML_OK;
+}
+
+// detectLoopWithRobot steps 3-7 on one (query, db) result list
+struct Cand {
+  double score;
+  uint64_t robot, pose;
+};
+static void select_candidates(const kml_handle* h, const RobotDb* db, uint64_t q_robot,
+                              uint64_t q_pose, double nss, const uint32_t* entry,
+                              const double* score, int count, std::vector<Cand>* out) {
+  const kml_params& P = h->prm;
+  if (P.inter_robot_only && q_robot == db->robot) return;
+  if (nss < P.min_nss_factor) return;
+  const double cut = P.alpha * nss;
+  for (int i = 0; i < count; ++i) {
+    if (score[i] < cut) break;  // list is best-first: lower_bound(Result::geq) + resize
+    const uint64_t pose = db->entry_to_pose[entry[i]];
+    if (q_robot == db->robot) {
+      const uint64_t d = q_pose > pose ? q_pose - pose : pose - q_pose;
+      if (d < (uint64_t)P.dist_local) continue;
+    }
+    out->push_back({score[i] / nss, db->robot, pose});
+  }
+}
+
+// ============================================================ frame store
+static int add_frames_host(kml_handle* h, uint64_t robot, const uint64_t* poses, int count,
+                           const uint8_t* desc, const double* bearings, const double* points,
+                           int F) {
+  if (count < 0 || F < 0 || F > 65535 || (count > 0 && F > 0 && (!desc || !bearings || !points)) ||
+      (count > 0 && !poses))
+    return fail(h, KML_ERR_ARG, "add_frame: bad argument (F must be < 65536)");
+  const size_t total = (size_t)count * F;
+  const int64_t base = h->n_feat;
+  h->s_desc.reserve((size_t)(base + total) * 32 + 32, (size_t)base * 32, h->stream);
+  h->s_bear.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
+  h->s_pts.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
+  if (total) {
+    KML_CUDA(cudaMemcpyAsync(h->s_desc.p + (size_t)base * 32, desc, total * 32, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->s_bear.p + (size_t)base * 3, bearings, total * 24, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->s_pts.p + (size_t)base * 3, points, total * 24, cudaMemcpyHostToDevice, h->stream));
+  }
+  for (int i = 0; i < count; ++i) {
+    const RobotPoseId id(robot, poses[i]);
+    FrameRec rec;
+    rec.feat_off = base + (int64_t)i * F;
+    rec.F = F;
+    rec.index = (int32_t)h->frame_off_h.size();
+    h->frame_off_h.push_back(rec.feat_off);
+    h->frame_F_h.push_back(F);
+    h->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
+  }
+  h->n_feat = base + (int64_t)total;
+  h->s_off_dirty = true;
+  KML_CUDA(cudaStreamSynchronize(h->stream));  // caller may free its buffers on return
+  return KML_OK;
+}
+
+static void ensure_frame_offsets(kml_handle* h) {
+  if (!h->s_off_dirty) return;
+  h->s_off.scratch(std::max<size_t>(h->frame_off_h.size(), 1));
+  if (!h->frame_off_h.empty())
+    KML_CUDA(cudaMemcpyAsync(h->s_off.p, h->frame_off_h.data(), 8 * h->frame_off_h.size(),
+                             cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  h->s_off_dirty = false;
+}
+
+// ====================================================== RANSAC host helpers
+// k as a function of (N, best inlier count): the exact expressions of
+// opengv::sac::Ransac::computeModel evaluated with the host libm, so that the
+// device replay takes the same branches as a CPU run.
+static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob, DevBuf<double>* buf,
+                          int* cur_n) {
+  const int need = Nmax + 1;
+  if (*cur_n >= need) return;
+  int n1 = std::max(need, 512);
+  std::vector<double> tab((size_t)n1 * n1, 1.0);
+  const double lnum = std::log(1.0 - prob);
+  for (int N = 1; N < n1; ++N)
+    for (int n = 0; n <= N; ++n) {
+      double w = (double)n / (double)N;
+      double p_no = 1.0 - std::pow(w, (double)sample_size);
+      p_no = std::max(DBL_EPSILON, p_no);
+      p_no = std::min(1.0 - DBL_EPSILON, p_no);
+      tab[(size_t)N * n1 + n] = lnum / std::log(p_no);
+    }
+  buf->scratch(tab.size());
+  KML_CUDA(cudaMemcpyAsync(buf->p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  *cur_n = n1;
+}
+
+static double sq_crit_of(double thr) {
+  // smallest double s with sqrt(s) >= thr  =>  (sqrt(d2) < thr) == (d2 < s)
+  if (!(thr > 0.0)) return 0.0;
+  double s = thr * thr;
+  while (std::sqrt(s) >= thr) s = std::nextafter(s, 0.0);
+  while (std::sqrt(s) < thr) s = std::nextafter(s, INFINITY);
+  return s;
+}
+
+struct SacBufs {
+  DevBuf<SacState>* st;
+  DevBuf<double>* best;
+  DevBuf<uint32_t>* mask;
+  DevBuf<int32_t>* inl;
+};
+
+// Runs one batched RANSAC (mono: S=8, stereo: S=3) over P problems whose
+// correspondences are already gathered in d_a/d_b.  Everything is enqueued on
+// the handle's stream; no host synchronisation.
+static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
+                    const int32_t* d_N, int stride, int full, SacBufs out, int mask_words) {
+  if (P <= 0) return;
+  const kml_params& prm = h->prm;
+  const int S = mono ? 8 : 3;
+  const int chunk = mono ? kMonoChunk : kStereoChunk;
+  const int max_it = mono ? prm.max_ransac_iterations_mono : prm.max_ransac_iterations;
+  if (mono)
+    ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->d_ktable_mono, &h->ktable_n_mono);
+  else
+    ensure_ktable(h, stride, 3, prm.ransac_probability, &h->d_ktable_stereo, &h->ktable_n_stereo);
+  h->d_perm.scratch((size_t)P * stride);
+  h->d_samples.scratch((size_t)P * chunk * S);
+  h->d_models.scratch((size_t)P * chunk * 12);
+  h->d_valid.scratch((size_t)P * chunk);
+  h->d_counts.scratch((size_t)P * chunk);
+  out.st->scratch(P);
+  out.best->scratch((size_t)P * 12);
+  out.mask->scratch((size_t)P * mask_words);
+  out.inl->scratch(P);
+  SacArgs a;
+  a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
+  a.raw = h->d_raw.p; a.raw_len = (int)h->raw_h.size();
+  a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
+  a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
+  a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
+  a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;
+  a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
+  a.sq_crit = sq_crit_of(prm.ransac_threshold);
+  a.max_iterations = max_it; a.full = full;
+  a.inlier_mask = out.mask->p; a.mask_words = mask_words; a.n_inliers = out.inl->p;
+  KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * P, h->stream));
+  launch_sac_init(a, S, h->stream);
+  h->stats.kernel_launches += 1;
+  // rounds needed to cover max_it+1 counted trials plus the skip reserve
+  const int total_draws = a.raw_len / S;
+  const int want = std::min(total_draws, max_it + 1 + 256);
+  const int rounds = (want + chunk - 1) / chunk;
+  for (int r = 0; r < rounds; ++r)
+    h->stats.kernel_launches += mono ? launch_mono_round(a, r, h->stream) : launch_stereo_round(a, r, h->stream);
+  if (mono) launch_mono_select(a, h->stream); else launch_stereo_select(a, h->stream);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaGetLastError());
+}
+
+// =========================================================== verification
+// Query-side frame arrays of the current verification call
+struct QuerySide {
+  const uint8_t* desc; const double* bear; const double* pts; int F;  // [slots][F][...]
+};
+
+struct VerifyOut {
+  std::vector<int32_t> status, M, mono_inl, stereo_inl;
+  std::vector<double> R, T;
+};
+
+// Full device pipeline over P pairs.  pairs[p] = {query slot, stored frame index}.
+static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, const QuerySide& qs,
+                         VerifyOut* out) {
+  const int P = (int)pairs.size();
+  out->status.assign(P, 1); out->M.assign(P, 0); out->mono_inl.assign(P, 0);
+  out->stereo_inl.assign(P, 0); out->R.assign((size_t)P * 9, 0.0); out->T.assign((size_t)P * 12, 0.0);
+  h->stats.pairs_last = P;
+  if (P == 0) return;
+  ensure_frame_offsets(h);
+  const int stride = std::max(qs.F, 8);
+  const int mask_words = (stride + 31) / 32;
+  // ---- jobs
+  std::vector<HamJob> jobs(P);
+  std::vector<int32_t> nq(P, qs.F);
+  h->d_keys.scratch((size_t)P * stride * 2);
+  for (int p = 0; p < P; ++p) {
+    jobs[p].q = qs.desc + (size_t)pairs[p].q_slot * qs.F * 32;
+    jobs[p].nq = qs.F;
+    jobs[p].t = h->s_desc.p + (size_t)h->frame_off_h[pairs[p].m_frame] * 32;
+    jobs[p].nt = h->frame_F_h[pairs[p].m_frame];
+    jobs[p].keys = h->d_keys.p + (size_t)p * stride * 2;
+  }
+  h->d_jobs.scratch(P); h->d_pairs.scratch(P); h->d_nq.scratch(P);
+  h->d_iq.scratch((size_t)P * stride); h->d_im.scratch((size_t)P * stride);
+  h->d_kq.scratch((size_t)P * stride); h->d_km.scratch((size_t)P * stride);
+  h->d_M.scratch(P); h->d_N3.scratch(P); h->d_mono_ok.scratch(P); h->d_status.scratch(P);
+  h->d_out_mono.scratch(P); h->d_out_stereo.scratch(P);
+  h->d_a.scratch((size_t)P * stride * 3); h->d_b.scratch((size_t)P * stride * 3);
+  h->d_outR.scratch((size_t)P * 9); h->d_outT.scratch((size_t)P * 12);
+  cudaStream_t s = h->stream;
+  KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(HamJob) * P, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_pairs.p, pairs.data(), sizeof(PairDesc) * P, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_nq.p, nq.data(), sizeof(int32_t) * P, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemsetAsync(h->d_outR.p, 0, sizeof(double) * 9 * P, s));
+  KML_CUDA(cudaMemsetAsync(h->d_outT.p, 0, sizeof(double) * 12 * P, s));
+  // ---- computeMatchedIndices
+  KML_CUDA(cudaEventRecord(h->ev[2], s));
+  launch_hamming_jobs(h->d_jobs.p, P, s);
+  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
+  h->stats.kernel_launches += 2;
+  KML_CUDA(cudaEventRecord(h->ev[3], s));
+  // ---- geometricVerificationNister
+  GatherArgs g;
+  g.P = P; g.pairs = h->d_pairs.p; g.qb = qs.bear; g.qp = qs.pts; g.qF = qs.F;
+  g.sb = h->s_bear.p; g.sp = h->s_pts.p; g.s_off = h->s_off.p;
+  g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
+  g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;  // N3 reused as "N" of the mono stage
+  launch_gather_bearings(g, s);
+  h->stats.kernel_launches += 1;
+  SacBufs mono{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono};
+  run_sac(h, true, P, h->d_a.p, h->d_b.p, h->d_M.p, stride, 0, mono, mask_words);
+  FinalizeArgs f;
+  f.P = P; f.mono_st = h->d_st_mono.p; f.mono_inl = h->d_inl_mono.p; f.M = h->d_M.p;
+  f.mono_model = h->d_best_mono.p;
+  f.min_inliers = h->prm.geometric_verification_min_inlier_count;
+  f.min_ratio_mono = h->prm.ransac_inlier_percentage_mono;
+  f.min_ratio_stereo = h->prm.geometric_verification_min_inlier_percentage;
+  f.mono_ok = h->d_mono_ok.p;
+  launch_mono_gate(f, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaEventRecord(h->ev[4], s));
+  // ---- recoverPose
+  StereoGatherArgs sg;
+  sg.g = g;
+  sg.mono_mask = h->d_mask_mono.p; sg.mask_words = mask_words; sg.mono_ok = h->d_mono_ok.p;
+  sg.kq = h->d_kq.p; sg.km = h->d_km.p;
+  launch_gather_points(sg, s);
+  h->stats.kernel_launches += 1;
+  SacBufs st3{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  run_sac(h, false, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, st3, mask_words);
+  f.st3 = h->d_st_stereo.p; f.inl3 = h->d_inl_stereo.p; f.N3 = h->d_N3.p; f.model3 = h->d_best_stereo.p;
+  f.status = h->d_status.p; f.out_mono_inl = h->d_out_mono.p; f.out_stereo_inl = h->d_out_stereo.p;
+  f.out_R = h->d_outR.p; f.out_T = h->d_outT.p;
+  launch_finalize(f, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaEventRecord(h->ev[5], s));
+  // ---- results back
+  std::vector<SacState> stm(P), sts(P);
+  KML_CUDA(cudaMemcpyAsync(out->status.data(), h->d_status.p, 4 * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(out->M.data(), h->d_M.p, 4 * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(out->mono_inl.data(), h->d_out_mono.p, 4 * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(out->stereo_inl.data(), h->d_out_stereo.p, 4 * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(out->R.data(), h->d_outR.p, 72 * (size_t)P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(out->T.data(), h->d_outT.p, 96 * (size_t)P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(stm.data(), h->d_st_mono.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(sts.data(), h->d_st_stereo.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaStreamSynchronize(s));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
+  uint64_t hm = 0, hs = 0, nmono_ok = 0;
+  bool exhausted = false;
+  for (int p = 0; p < P; ++p) {
+    hm += (uint64_t)stm[p].draws;
+    hs += (uint64_t)sts[p].draws;
+    exhausted |= stm[p].exhausted || sts[p].exhausted;
+    nmono_ok += out->status[p] != 1;
+  }
+  h->stats.mono_hypotheses_last = hm;
+  h->stats.stereo_hypotheses_last = hs;
+  h->stats.total_geom_verifications_mono += P;
+  h->stats.total_geometric_verifications += nmono_ok;
+  if (exhausted) throw std::runtime_error("pre-drawn sample stream exhausted (too many skipped samples)");
+}
+
+// ============================================================ batch query
+static int batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,
+                        const int64_t* bow_off, const uint32_t* ids, const float* vals,
+                        const int64_t* prev_off, const uint32_t* prev_ids, const float* prev_vals,
+                        const uint8_t* desc, const double* bearings, const double* points, int F) {
+  if (B < 0 || F < 0 || F > 65535) return fail(h, KML_ERR_ARG, "query_batch: bad B or F");
+  if (B > 0 && (!q_robot || !q_pose || !bow_off || !prev_off || !desc || !bearings || !points))
+    return fail(h, KML_ERR_ARG, "query_batch: null argument");
+  for (int b = 0; b < B; ++b) {
+    int rc = check_bow(h, ids + bow_off[b], vals + bow_off[b], (int)(bow_off[b + 1] - bow_off[b]));
+    if (rc != KML_OK) return rc;
+    rc = check_bow(h, prev_ids + prev_off[b], prev_vals + prev_off[b], (int)(prev_off[b + 1] - prev_off[b]));
+    if (rc != KML_OK) return rc;
+  }
+  h->B = B; h->qF = F;
+  h->q_robot_h.assign(q_robot, q_robot + B);
+  h->q_pose_h.assign(q_pose, q_pose + B);
+  if (B == 0) return KML_OK;
+  const size_t nw = (size_t)bow_off[B], np = (size_t)prev_off[B];
+  cudaStream_t s = h->stream;
+  h->d_qoff.scratch(B + 1); h->d_poff.scratch(B + 1);
+  h->d_qids.scratch(std::max<size_t>(nw, 1)); h->d_qvals.scratch(std::max<size_t>(nw, 1));
+  h->d_pids.scratch(std::max<size_t>(np, 1)); h->d_pvals.scratch(std::max<size_t>(np, 1));
+  h->d_qdesc.scratch((size_t)B * F * 32 + 32);
+  h->d_qbear.scratch((size_t)B * F * 3 + 3); h->d_qpts.scratch((size_t)B * F * 3 + 3);
+  KML_CUDA(cudaMemcpyAsync(h->d_qoff.p, bow_off, 8 * (B + 1), cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_poff.p, prev_off, 8 * (B + 1), cudaMemcpyHostToDevice, s));
+  if (nw) {
+    KML_CUDA(cudaMemcpyAsync(h->d_qids.p, ids, 4 * nw, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(h->d_qvals.p, vals, 4 * nw, cudaMemcpyHostToDevice, s));
+  }
+  if (np) {
+    KML_CUDA(cudaMemcpyAsync(h->d_pids.p, prev_ids, 4 * np, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(h->d_pvals.p, prev_vals, 4 * np, cudaMemcpyHostToDevice, s));
+  }
+  if (F) {
+    KML_CUDA(cudaMemcpyAsync(h->d_qdesc.p, desc, (size_t)B * F * 32, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(h->d_qbear.p, bearings, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(h->d_qpts.p, points, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
+  }
+  KML_CUDA(cudaStreamSynchronize(s));
+  return KML_OK;
+}
+
+struct BatchRecs {
+  std::vector<kml_result> recs;   // [B][cap]
+  std::vector<int32_t> counts;    // [B]
+};
+
+static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
+  const int B = h->B;
+  br->recs.assign((size_t)B * cap, kml_result{});
+  br->counts.assign(B, 0);
+  if (B == 0) return KML_OK;
+  KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
+  std::vector<RobotDb*> dbs;
+  for (auto& kv : h->dbs) dbs.push_back(kv.second.get());
+  BowOut bo;
+  run_bow(h, dbs, B, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
+          h->d_pvals.p, h->prm.max_db_results, nullptr, &bo);
+  // candidate selection (detectLoop = detectLoopWithRobot over every robot DB)
+  const int K = std::min(h->prm.top_k_verify, cap);
+  std::vector<PairDesc> pairs;
+  std::vector<int> pair_rec;  // pair -> record index
+  std::vector<Cand> cands;
+  for (int b = 0; b < B; ++b) {
+    cands.clear();
+    for (int d = 0; d < bo.n_db; ++d) {
+      const size_t l = (size_t)b * bo.n_db + d;
+      select_candidates(h, dbs[d], h->q_robot_h[b], h->q_pose_h[b], bo.nss[b],
+                        &bo.entry[l * bo.K], &bo.score[l * bo.K], bo.count[l], &cands);
+    }
+    h->stats.total_bow_matches += cands.size();
+    std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) {
+      if (x.score != y.score) return x.score > y.score;
+      if (x.robot != y.robot) return x.robot < y.robot;
+      return x.pose < y.pose;
+    });
+    const int nv = std::min<int>((int)cands.size(), K);
+    br->counts[b] = nv;
+    for (int i = 0; i < nv; ++i) {
+      kml_result& r = br->recs[(size_t)b * cap + i];
+      r.q_robot = h->q_robot_h[b]; r.q_pose = h->q_pose_h[b];
+      r.m_robot = cands[i].robot; r.m_pose = cands[i].pose;
+      r.norm_bow_score = cands[i].score;
+      auto fit = h->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
+      if (fit == h->frames.end()) { r.status = 3; continue; }
+      pairs.push_back({b, fit->second.index});
+      pair_rec.push_back(b * cap + i);
+    }
+  }
+  QuerySide qs{h->d_qdesc.p, h->d_qbear.p, h->d_qpts.p, h->qF};
+  VerifyOut vo;
+  verify_pairs(h, pairs, qs, &vo);
+  for (size_t p = 0; p < pairs.size(); ++p) {
+    kml_result& r = br->recs[pair_rec[p]];
+    r.n_matches = vo.M[p];
+    r.status = vo.status[p];
+    r.mono_inliers = vo.mono_inl[p];
+    r.stereo_inliers = vo.stereo_inl[p];
+    memcpy(r.R_mono, &vo.R[p * 9], 72);
+    memcpy(r.T, &vo.T[p * 12], 96);
+  }
+  KML_CUDA(cudaEventRecord(h->ev[7], h->stream));
+  KML_CUDA(cudaEventSynchronize(h->ev[7]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_total, h->ev[6], h->ev[7]));
+  return KML_OK;
+}
+
+static void copy_out(const BatchRecs& br, int B, int cap, kml_result* out, int32_t* counts) {
+  if (B == 0) return;
+  memcpy(out, br.recs.data(), sizeof(kml_result) * (size_t)B * cap);
+  memcpy(counts, br.counts.data(), sizeof(int32_t) * B);
+}
+
+// single stored frame as the "query side"
+static bool stored_query_side(kml_handle* h, uint64_t robot, uint64_t pose, QuerySide* qs) {
+  auto it = h->frames.find(RobotPoseId(robot, pose));
+  if (it == h->frames.end()) return false;
+  const FrameRec& r = it->second;
+  qs->desc = h->s_desc.p + (size_t)r.feat_off * 32;
+  qs->bear = h->s_bear.p + (size_t)r.feat_off * 3;
+  qs->pts = h->s_pts.p + (size_t)r.feat_off * 3;
+  qs->F = r.F;
+  return true;
+}
+
+// gather + RANSAC on caller-provided index lists for ONE stored pair
+static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint64_t mr,
+                        uint64_t mp, uint32_t* inl_q, uint32_t* inl_m, int* count, double* model12,
+                        int* n_valid_out) {
+  if (!inl_q || !inl_m || !count || *count < 0) return fail(h, KML_ERR_ARG, "bad index lists");
+  QuerySide qs;
+  if (!stored_query_side(h, qr, qp, &qs)) return KML_NO_FRAME;
+  auto mit = h->frames.find(RobotPoseId(mr, mp));
+  if (mit == h->frames.end()) return KML_NO_FRAME;
+  const int M = *count;
+  for (int i = 0; i < M; ++i)
+    if (inl_q[i] >= (uint32_t)qs.F || inl_m[i] >= (uint32_t)mit->second.F)
+      return fail(h, KML_ERR_ARG, "feature index out of range");
+  ensure_frame_offsets(h);
+  const int stride = std::max(M, 8);
+  const int mask_words = (stride + 31) / 32;
+  std::vector<uint16_t> iq(stride, 0), im(stride, 0);
+  for (int i = 0; i < M; ++i) { iq[i] = (uint16_t)inl_q[i]; im[i] = (uint16_t)inl_m[i]; }
+  PairDesc pd{0, mit->second.index};
+  int32_t one = 1;
+  cudaStream_t s = h->stream;
+  h->d_pairs.scratch(1); h->d_iq.scratch(stride); h->d_im.scratch(stride);
+  h->d_kq.scratch(stride); h->d_km.scratch(stride); h->d_M.scratch(1); h->d_N3.scratch(1);
+  h->d_mono_ok.scratch(1); h->d_a.scratch((size_t)stride * 3); h->d_b.scratch((size_t)stride * 3);
+  KML_CUDA(cudaMemcpyAsync(h->d_pairs.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_iq.p, iq.data(), 2 * stride, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_im.p, im.data(), 2 * stride, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_M.p, &M, 4, cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_mono_ok.p, &one, 4, cudaMemcpyHostToDevice, s));
+  GatherArgs g;
+  g.P = 1; g.pairs = h->d_pairs.p; g.qb = qs.bear; g.qp = qs.pts; g.qF = qs.F;
+  g.sb = h->s_bear.p; g.sp = h->s_pts.p; g.s_off = h->s_off.p;
+  g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
+  g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;
+  SacBufs bufs = mono ? SacBufs{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono}
+                      : SacBufs{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  std::vector<uint16_t> kq(stride), km(stride);
+  if (mono) {
+    launch_gather_bearings(g, s);
+  } else {
+    // recoverPose filters on the 3-D keypoints of every listed pair: all-ones mask
+    std::vector<uint32_t> ones(mask_words, 0xFFFFFFFFu);
+    h->d_mask_mono.scratch(mask_words);
+    KML_CUDA(cudaMemcpyAsync(h->d_mask_mono.p, ones.data(), 4 * mask_words, cudaMemcpyHostToDevice, s));
+    StereoGatherArgs sg;
+    sg.g = g; sg.mono_mask = h->d_mask_mono.p; sg.mask_words = mask_words;
+    sg.mono_ok = h->d_mono_ok.p; sg.kq = h->d_kq.p; sg.km = h->d_km.p;
+    launch_gather_points(sg, s);
+  }
+  h->stats.kernel_launches += 1;
+  run_sac(h, mono, 1, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, bufs, mask_words);
+  SacState st;
+  int32_t N = 0, ninl = 0;
+  std::vector<uint32_t> mask(mask_words);
+  KML_CUDA(cudaMemcpyAsync(&st, bufs.st->p, sizeof(st), cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(&N, h->d_N3.p, 4, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(&ninl, bufs.inl->p, 4, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(mask.data(), bufs.mask->p, 4 * mask_words, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(model12, bufs.best->p, 96, cudaMemcpyDeviceToHost, s));
+  if (!mono) {
+    KML_CUDA(cudaMemcpyAsync(kq.data(), h->d_kq.p, 2 * stride, cudaMemcpyDeviceToHost, s));
+    KML_CUDA(cudaMemcpyAsync(km.data(), h->d_km.p, 2 * stride, cudaMemcpyDeviceToHost, s));
+  }
+  KML_CUDA(cudaStreamSynchronize(s));
+  if (st.exhausted) return fail(h, KML_ERR_STREAM_EXHAUSTED, "pre-drawn sample stream exhausted");
+  *n_valid_out = N;
+  if (N < (mono ? 8 : 3)) return KML_TOO_FEW_POINTS;
+  if (st.best_draw < 0) return KML_RANSAC_FAIL;
+  const kml_params& P = h->prm;
+  if (ninl < P.geometric_verification_min_inlier_count) return KML_TOO_FEW_INLIERS;
+  const double ratio = mono ? P.ransac_inlier_percentage_mono : P.geometric_verification_min_inlier_percentage;
+  if ((double)ninl / (double)N < ratio) return KML_TOO_FEW_INLIERS;
+  // rewrite the index lists to the inlier subset (ascending)
+  int c = 0;
+  for (int i = 0; i < N; ++i)
+    if ((mask[i >> 5] >> (i & 31)) & 1u) {
+      const uint32_t a = mono ? (uint32_t)iq[i] : (uint32_t)kq[i];
+      const uint32_t b = mono ? (uint32_t)im[i] : (uint32_t)km[i];
+      inl_q[c] = a; inl_m[c] = b; ++c;
+    }
+  *count = c;
+  return KML_OK;
+}
+
+extern "C" {
+
+int kml_add_bow(kml_handle* h, uint64_t robot, uint64_t pose, const uint32_t* ids,
+                const float* vals, int n) {
+  KML_API_BEGIN(h)
+  return add_bow_host(h, get_db(h, robot, true), pose, ids, vals, n);
+  KML_API_END(h)
+}
+
+int kml_add_bow_bulk(kml_handle* h, uint64_t robot, const uint64_t* poses, int count,
+                     const int64_t* off, const uint32_t* ids, const float* vals) {
+  KML_API_BEGIN(h)
+  if (count < 0 || (count > 0 && (!poses || !off))) return fail(h, KML_ERR_ARG, "add_bow_bulk: bad argument");
+  RobotDb* db = get_db(h, robot, true);
+  for (int i = 0; i < count; ++i) {
+    int rc = add_bow_host(h, db, poses[i], ids + off[i], vals + off[i], (int)(off[i + 1] - off[i]));
+    if (rc != KML_OK) return rc;
+  }
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_add_frame(kml_handle* h, uint64_t robot, uint64_t pose, const uint8_t* desc,
+                  const double* bearings, const double* points, int F) {
+  KML_API_BEGIN(h)
+  return add_frames_host(h, robot, &pose, 1, desc, bearings, points, F);
+  KML_API_END(h)
+}
+
+int kml_add_frames_bulk(kml_handle* h, uint64_t robot, const uint64_t* poses, int count,
+                        const uint8_t* desc, const double* bearings, const double* points, int F) {
+  KML_API_BEGIN(h)
+  return add_frames_host(h, robot, poses, count, desc, bearings, points, F);
+  KML_API_END(h)
+}
+
+int kml_frame_exists(kml_handle* h, uint64_t robot, uint64_t pose) {
+  if (!h) return KML_ERR_ARG;
+  return h->frames.count(RobotPoseId(robot, pose)) ? 1 : 0;
+}
+int kml_bow_exists(kml_handle* h, uint64_t robot, uint64_t pose) {
+  if (!h) return KML_ERR_ARG;
+  RobotDb* db = get_db(h, robot, false);
+  return (db && db->pose_to_entry.count(pose)) ? 1 : 0;
+}
+int kml_num_bow_for_robot(kml_handle* h, uint64_t robot) {
+  if (!h) return KML_ERR_ARG;
+  RobotDb* db = get_db(h, robot, false);
+  return db ? (int)db->n_entries() : 0;
+}
+int kml_get_bow_vector(kml_handle* h, uint64_t robot, uint64_t pose, uint32_t* ids, float* vals,
+                       int cap, int* count) {
+  if (!h || !count) return KML_ERR_ARG;
+  RobotDb* db = get_db(h, robot, false);
+  if (!db) return KML_NO_DB;
+  auto it = db->pose_to_entry.find(pose);
+  if (it == db->pose_to_entry.end()) return KML_NO_PREV_BOW;
+  const int64_t o = db->off[it->second];
+  const int n = (int)(db->off[it->second + 1] - o);
+  if (n > cap) return fail(h, KML_ERR_CAPACITY, "get_bow_vector: capacity");
+  if (n) {
+    memcpy(ids, &db->ids[o], 4 * n);
+    memcpy(vals, &db->vals[o], 4 * n);
+  }
+  *count = n;
+  return KML_OK;
+}
+
+int kml_db_query(kml_handle* h, uint64_t robot, const uint32_t* ids, const float* vals, int n,
+                 int max_results, int max_id, uint32_t* out_entry, double* out_score, int cap,
+                 int* count) {
+  KML_API_BEGIN(h)
+  if (!count || !out_entry || !out_score) return fail(h, KML_ERR_ARG, "db_query: null output");
+  *count = 0;
+  int rc = check_bow(h, ids, vals, n);
+  if (rc != KML_OK) return rc;
+  RobotDb* db = get_db(h, robot, false);
+  if (!db) return KML_NO_DB;
+  if (max_results <= 0 || max_results > kBowMaxK)
+    return fail(h, KML_ERR_CAPACITY, "db_query: max_results must be in [1,128]");
+  upload_single_bow(h, ids, vals, n, nullptr, nullptr, 0);
+  BowOut bo;
+  std::vector<int32_t> mid{max_id};
+  run_bow(h, {db}, 1, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, nullptr, nullptr, nullptr,
+          max_results, &mid, &bo);
+  const int c = std::min(bo.count[0], cap);
+  memcpy(out_entry, bo.entry.data(), 4 * c);
+  memcpy(out_score, bo.score.data(), 8 * c);
+  *count = c;
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_bow_score(kml_handle* h, const uint32_t* ids1, const float* vals1, int n1,
+                  const uint32_t* ids2, const float* vals2, int n2, double* out) {
+  KML_API_BEGIN(h)
+  if (!out) return KML_ERR_ARG;
+  int rc = check_bow(h, ids1, vals1, n1);
+  if (rc != KML_OK) return rc;
+  rc = check_bow(h, ids2, vals2, n2);
+  if (rc != KML_OK) return rc;
+  // the NSS path of the scorer kernel against an empty one-entry database view
+  upload_single_bow(h, ids1, vals1, n1, ids2, vals2, n2);
+  RobotDb empty;
+  empty.robot = ~0ull;
+  BowOut bo;
+  run_bow(h, {&empty}, 1, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
+          h->d_pvals.p, 1, nullptr, &bo);
+  *out = bo.nss[0];
+  return KML_OK;
+  KML_API_END(h)
+}
+
+static int detect_impl(kml_handle* h, const std::vector<RobotDb*>& dbs, uint64_t q_robot,
+                       uint64_t q_pose, const uint32_t* ids, const float* vals, int n,
+                       uint64_t* out_robot, uint64_t* out_pose, double* out_score, int cap,
+                       int* count) {
+  *count = 0;
+  int rc = check_bow(h, ids, vals, n);
+  if (rc != KML_OK) return rc;
+  if (dbs.empty()) return KML_NO_DB;
+  // findPreviousBoWVector(query, max_nrFrames_between_queries)
+  RobotDb* own = get_db(h, q_robot, false);
+  int64_t po = 0;
+  int pn = -1;
+  if (own)
+    for (int i = 1; i <= h->prm.max_nrFrames_between_queries; ++i) {
+      if (q_pose < (uint64_t)i) break;
+      auto it = own->pose_to_entry.find(q_pose - i);
+      if (it != own->pose_to_entry.end()) {
+        po = own->off[it->second];
+        pn = (int)(own->off[it->second + 1] - po);
+        break;
+      }
+    }
+  if (pn < 0) return KML_NO_PREV_BOW;
+  upload_single_bow(h, ids, vals, n, own->ids.data() + po, own->vals.data() + po, pn);
+  BowOut bo;
+  run_bow(h, dbs, 1, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
+          h->d_pvals.p, h->prm.max_db_results, nullptr, &bo);
+  if (bo.nss[0] < h->prm.min_nss_factor) return KML_NSS_TOO_LOW;
+  std::vector<Cand> cands;
+  for (size_t d = 0; d < dbs.size(); ++d)
+    select_candidates(h, dbs[d], q_robot, q_pose, bo.nss[0], &bo.entry[d * bo.K],
+                      &bo.score[d * bo.K], bo.count[d], &cands);
+  h->stats.total_bow_matches += cands.size();
+  if ((int)cands.size() > cap) return fail(h, KML_ERR_CAPACITY, "detect_loop: output capacity");
+  for (size_t i = 0; i < cands.size(); ++i) {
+    out_robot[i] = cands[i].robot; out_pose[i] = cands[i].pose; out_score[i] = cands[i].score;
+  }
+  *count = (int)cands.size();
+  return cands.empty() ? KML_NO_MATCH : KML_OK;
+}
+
+int kml_detect_loop_with_robot(kml_handle* h, uint64_t robot, uint64_t q_robot, uint64_t q_pose,
+                               const uint32_t* ids, const float* vals, int n, uint64_t* out_robot,
+                               uint64_t* out_pose, double* out_score, int cap, int* count) {
+  KML_API_BEGIN(h)
+  if (!count || !out_robot || !out_pose || !out_score) return fail(h, KML_ERR_ARG, "null output");
+  *count = 0;
+  RobotDb* db = get_db(h, robot, false);
+  if (!db) return KML_NO_DB;
+  if (h->prm.inter_robot_only && robot == q_robot) return KML_INTER_ROBOT_ONLY;
+  return detect_impl(h, {db}, q_robot, q_pose, ids, vals, n, out_robot, out_pose, out_score, cap, count);
+  KML_API_END(h)
+}
+
+int kml_detect_loop(kml_handle* h, uint64_t q_robot, uint64_t q_pose, const uint32_t* ids,
+                    const float* vals, int n, uint64_t* out_robot, uint64_t* out_pose,
+                    double* out_score, int cap, int* count) {
+  KML_API_BEGIN(h)
+  if (!count || !out_robot || !out_pose || !out_score) return fail(h, KML_ERR_ARG, "null output");
+  std::vector<RobotDb*> dbs;
+  for (auto& kv : h->dbs) dbs.push_back(kv.second.get());
+  return detect_impl(h, dbs, q_robot, q_pose, ids, vals, n, out_robot, out_pose, out_score, cap, count);
+  KML_API_END(h)
+}
+
+int kml_compute_matched_indices(kml_handle* h, uint64_t qr, uint64_t qp, uint64_t mr, uint64_t mp,
+                                uint32_t* i_query, uint32_t* i_match, int cap, int* count) {
+  KML_API_BEGIN(h)
+  if (!count || !i_query || !i_match) return fail(h, KML_ERR_ARG, "null output");
+  *count = 0;
+  QuerySide qs;
+  if (!stored_query_side(h, qr, qp, &qs)) return KML_NO_FRAME;
+  auto mit = h->frames.find(RobotPoseId(mr, mp));
+  if (mit == h->frames.end()) return KML_NO_FRAME;
+  if (qs.F == 0) return KML_OK;
+  const int stride = qs.F;
+  cudaStream_t s = h->stream;
+  h->d_keys.scratch((size_t)stride * 2); h->d_jobs.scratch(1); h->d_nq.scratch(1);
+  h->d_iq.scratch(stride); h->d_im.scratch(stride); h->d_M.scratch(1);
+  HamJob job;
+  job.q = qs.desc; job.nq = qs.F;
+  job.t = h->s_desc.p + (size_t)mit->second.feat_off * 32; job.nt = mit->second.F;
+  job.keys = h->d_keys.p;
+  KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(h->d_nq.p, &qs.F, 4, cudaMemcpyHostToDevice, s));
+  launch_hamming_jobs(h->d_jobs.p, 1, s);
+  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->d_iq.p, h->d_im.p, h->d_M.p, 1, s);
+  h->stats.kernel_launches += 2;
+  KML_CUDA(cudaGetLastError());
+  int32_t M = 0;
+  std::vector<uint16_t> iq(stride), im(stride);
+  KML_CUDA(cudaMemcpyAsync(&M, h->d_M.p, 4, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(iq.data(), h->d_iq.p, 2 * stride, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(im.data(), h->d_im.p, 2 * stride, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaStreamSynchronize(s));
+  if (M > cap) return fail(h, KML_ERR_CAPACITY, "compute_matched_indices: output capacity");
+  for (int i = 0; i < M; ++i) { i_query[i] = iq[i]; i_match[i] = im[i]; }
+  *count = M;
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_geometric_verification_nister(kml_handle* h, uint64_t qr, uint64_t qp, uint64_t mr,
+                                      uint64_t mp, uint32_t* inl_q, uint32_t* inl_m, int* count,
+                                      double* R) {
+  KML_API_BEGIN(h)
+  if (!R) return fail(h, KML_ERR_ARG, "null output");
+  h->stats.total_geom_verifications_mono += 1;
+  double M[12];
+  int nvalid = 0;
+  int rc = sac_on_lists(h, true, qr, qp, mr, mp, inl_q, inl_m, count, M, &nvalid);
+  if (rc != KML_OK) return rc;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = M[4 * r + c];
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_recover_pose(kml_handle* h, uint64_t qr, uint64_t qp, uint64_t mr, uint64_t mp,
+                     uint32_t* inl_q, uint32_t* inl_m, int* count, const double* R_prior,
+                     double* T) {
+  KML_API_BEGIN(h)
+  (void)R_prior;  // adapter.setR12(prior) is not read by threept_arun
+  if (!T) return fail(h, KML_ERR_ARG, "null output");
+  h->stats.total_geometric_verifications += 1;
+  double M[12];
+  int nvalid = 0;
+  int rc = sac_on_lists(h, false, qr, qp, mr, mp, inl_q, inl_m, count, M, &nvalid);
+  if (rc != KML_OK) return rc;
+  memcpy(T, M, 96);
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_query_batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,
+                           const int64_t* bow_off, const uint32_t* ids, const float* vals,
+                           const int64_t* prev_off, const uint32_t* prev_ids,
+                           const float* prev_vals, const uint8_t* desc, const double* bearings,
+                           const double* points, int F) {
+  KML_API_BEGIN(h)
+  return batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
+                      desc, bearings, points, F);
+  KML_API_END(h)
+}
+
+int kml_query_batch_run(kml_handle* h, kml_result* out, int cap, int32_t* counts) {
+  KML_API_BEGIN(h)
+  if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "query_batch_run: bad output");
+  BatchRecs br;
+  int rc = batch_run(h, cap, &br);
+  if (rc != KML_OK) return rc;
+  copy_out(br, h->B, cap, out, counts);
+  return KML_OK;
+  KML_API_END(h)
+}
+
+int kml_query_batch(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,
+                    const int64_t* bow_off, const uint32_t* ids, const float* vals,
+                    const int64_t* prev_off, const uint32_t* prev_ids, const float* prev_vals,
+                    const uint8_t* desc, const double* bearings, const double* points, int F,
+                    kml_result* out, int cap, int32_t* counts) {
+  KML_API_BEGIN(h)
+  int rc = batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
+                        desc, bearings, points, F);
+  if (rc != KML_OK) return rc;
+  if (cap <= 0 || (B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "query_batch: bad output");
+  BatchRecs br;
+  rc = batch_run(h, cap, &br);
+  if (rc != KML_OK) return rc;
+  copy_out(br, B, cap, out, counts);
+  return KML_OK;
+  KML_API_END(h)
+}
+
+// Sharded query: every rank runs the (identical) uploaded batch against its
+// own robot databases, then ONE ncclAllGather merges the fixed-size record
+// blocks; every rank re-ranks the union per query and keeps the best `cap`.
+int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* counts) {
+  KML_API_BEGIN(h)
+  if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "bad output");
+  const int B = h->B;
+  BatchRecs br;
+  int rc = batch_run(h, cap, &br);
+  if (rc != KML_OK) return rc;
+  const int nr = comm_nranks(h);
+  if (nr == 1) { copy_out(br, B, cap, out, counts); return KML_OK; }
+  if (B == 0) return KML_OK;
+  const size_t rec_bytes = sizeof(kml_result) * (size_t)B * cap;
+  const size_t blk = rec_bytes + sizeof(int32_t) * (size_t)B;
+  const size_t blk_al = (blk + 255) / 256 * 256;
+  h->d_scratch.scratch(blk_al);
+  h->d_scratch2.scratch(blk_al * nr);
+  h->h_stage.scratch(blk_al * nr);
+  memcpy(h->h_stage.p, br.recs.data(), rec_bytes);
+  memcpy(h->h_stage.p + rec_bytes, br.counts.data(), sizeof(int32_t) * B);
+  KML_CUDA(cudaMemcpyAsync(h->d_scratch.p, h->h_stage.p, blk, cudaMemcpyHostToDevice, h->stream));
+  rc = comm_allgather(h, h->d_scratch.p, h->d_scratch2.p, blk_al);
+  if (rc != KML_OK) return rc;
+  KML_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_scratch2.p, blk_al * nr, cudaMemcpyDeviceToHost, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  std::vector<kml_result> all;
+  for (int b = 0; b < B; ++b) {
+    all.clear();
+    for (int r = 0; r < nr; ++r) {
+      const uint8_t* base = h->h_stage.p + blk_al * r;
+      const kml_result* recs = reinterpret_cast<const kml_result*>(base) + (size_t)b * cap;
+      const int32_t c = reinterpret_cast<const int32_t*>(base + rec_bytes)[b];
+      all.insert(all.end(), recs, recs + c);
+    }
+    std::stable_sort(all.begin(), all.end(), [](const kml_result& x, const kml_result& y) {
+      if (x.norm_bow_score != y.norm_bow_score) return x.norm_bow_score > y.norm_bow_score;
+      if (x.m_robot != y.m_robot) return x.m_robot < y.m_robot;
+      return x.m_pose < y.m_pose;
+    });
+    const int c = (int)std::min<size_t>(all.size(), cap);
+    for (int i = 0; i < c; ++i) out[(size_t)b * cap + i] = all[i];
+    counts[b] = c;
+  }
+  return KML_OK;
+  KML_API_END(h)
+}
+
+// ------------------------------------------------- batched RANSAC (C4 etc.)
+static int ransac_batch(kml_handle* h, bool mono, int P, int N, const double* a, const double* b,
+                        int full, double* models, int32_t* n_inliers, int32_t* iterations,
+                        int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
+  if (P < 0 || N < 0 || N > 65535 || (P > 0 && N > 0 && (!a || !b))) return fail(h, KML_ERR_ARG, "ransac_batch: bad argument");
+  if (P == 0) return KML_OK;
+  const int stride = std::max(N, 8);
+  const int mask_words = (stride + 31) / 32;
+  cudaStream_t s = h->stream;
+  h->d_a.scratch((size_t)P * stride * 3); h->d_b.scratch((size_t)P * stride * 3);
+  h->d_N3.scratch(P);
+  std::vector<int32_t> Ns(P, N);
+  KML_CUDA(cudaMemcpyAsync(h->d_N3.p, Ns.data(), 4 * P, cudaMemcpyHostToDevice, s));
+  if (N) {
+    KML_CUDA(cudaMemcpy2DAsync(h->d_a.p, (size_t)stride * 24, a, (size_t)N * 24, (size_t)N * 24, P, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpy2DAsync(h->d_b.p, (size_t)stride * 24, b, (size_t)N * 24, (size_t)N * 24, P, cudaMemcpyHostToDevice, s));
+  }
+  SacBufs bufs = mono ? SacBufs{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono}
+                      : SacBufs{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  KML_CUDA(cudaEventRecord(h->ev[2], s));
+  run_sac(h, mono, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, full, bufs, mask_words);
+  KML_CUDA(cudaEventRecord(h->ev[3], s));
+  std::vector<SacState> st(P);
+  std::vector<uint32_t> mask((size_t)P * mask_words);
+  KML_CUDA(cudaMemcpyAsync(st.data(), bufs.st->p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(mask.data(), bufs.mask->p, 4 * mask.size(), cudaMemcpyDeviceToHost, s));
+  if (models) KML_CUDA(cudaMemcpyAsync(models, bufs.best->p, 96 * (size_t)P, cudaMemcpyDeviceToHost, s));
+  if (n_inliers) KML_CUDA(cudaMemcpyAsync(n_inliers, bufs.inl->p, 4 * P, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  KML_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+  if (ms_kernel) *ms_kernel = ms;
+  uint64_t draws = 0;
+  const int words_out = (N + 31) / 32;
+  for (int p = 0; p < P; ++p) {
+    if (st[p].exhausted) return fail(h, KML_ERR_STREAM_EXHAUSTED, "pre-drawn sample stream exhausted");
+    if (iterations) iterations[p] = st[p].iterations;
+    if (best_draw) best_draw[p] = st[p].best_draw;
+    draws += st[p].draws;
+    if (inlier_mask)
+      for (int w = 0; w < std::max(words_out, 1); ++w)
+        inlier_mask[(size_t)p * std::max(words_out, 1) + w] = w < words_out ? mask[(size_t)p * mask_words + w] : 0u;
+  }
+  if (mono) h->stats.mono_hypotheses_last = draws; else h->stats.stereo_hypotheses_last = draws;
+  h->stats.pairs_last = P;
+  return KML_OK;
+}
+
+int kml_ransac_arun_batch(kml_handle* h, int P, int N, const double* p1, const double* p2,
+                          int full, double* models, int32_t* n_inliers, int32_t* iterations,
+                          int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
+  KML_API_BEGIN(h)
+  return ransac_batch(h, false, P, N, p1, p2, full, models, n_inliers, iterations, best_draw, inlier_mask, ms_kernel);
+  KML_API_END(h)
+}
+int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const double* f2,
+                            int full, double* models, int32_t* n_inliers, int32_t* iterations,
+                            int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
+  KML_API_BEGIN(h)
+  return ransac_batch(h, true, P, N, f1, f2, full, models, n_inliers, iterations, best_draw, inlier_mask, ms_kernel);
+  KML_API_END(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// ransac.cu — batched opengv::sac::Ransac on sm_100a (compiled -fmad=false).
+//
+// Replaces Ransac<CentralRelativePoseSacProblem>(NISTER)::computeModel as
+// called by LoopClosureDetector::geometricVerificationNister and
+// Ransac<PointCloudSacProblem>::computeModel as called by recoverPose
+// (/root/reference/images/kimera-multi.drawio:2589-2598,
+// 2646, 2654; thresholds of the same family:
+// /root/reference/params/D455/LcdParams.yaml:51-56,64-66).
+//
+// The reference loop is sequential (adaptive stop).  Here every problem
+// (candidate keyframe pair) advances in ROUNDS of `chunk` draws of the
+// pre-drawn sample stream:
+//   chunk kernel  : one CTA per problem; phase 1 one hypothesis per thread
+//                   (minimal solver), phase 2 one hypothesis per warp-pass
+//                   (lanes stride over all correspondences, ballot+popc
+//                   inlier count); correspondences live in shared memory.
+//   replay kernel : one warp per problem; lane 0 replays the reference's
+//                   serial scan over the chunk (skip rule, strict-improvement
+//                   rule, k update from a host-computed table, iteration
+//                   cap), then draws the next chunk of samples from the
+//                   persistent partial Fisher-Yates state.
+// A finished problem's CTAs exit immediately, so the host can enqueue all
+// rounds without synchronising.
+#include <limits.h>
+
+#include "common.cuh"
+#include "geom.cuh"
+#include "kernels.h"
+
+namespace kml {
+
+using geom::V3;
+
+// --------------------------------------------------------------- sampling
+// SampleConsensusProblem::drawIndexSample: for i<S swap(shuffled[i],
+// shuffled[i + rnd() % (N-i)]); rnd() = mt19937()>>1 (pre-drawn, host).
+template <int S>
+__device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict__ raw,
+                             int raw_len, int first_draw, int n_draws, uint16_t* out) {
+  for (int d = 0; d < n_draws; ++d) {
+    const int gd = first_draw + d;
+    if ((gd + 1) * S > raw_len) break;
+    for (int i = 0; i < S; ++i) {
+      const uint32_t r = raw[gd * S + i];
+      const int j = i + (int)(r % (uint32_t)(N - i));
+      const uint16_t t = perm_s[i];
+      perm_s[i] = perm_s[j];
+      perm_s[j] = t;
+    }
+    for (int i = 0; i < S; ++i) out[d * S + i] = perm_s[i];
+  }
+}
+
+template <int S, int CHUNK>
+__global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
+  extern __shared__ uint16_t perm_s[];
+  const int p = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int N = a.N[p];
+  SacState* st = &a.st[p];
+  for (int i = lane; i < N; i += 32) perm_s[i] = (uint16_t)i;
+  __syncwarp();
+  if (lane == 0) {
+    st->iterations = 0;
+    st->skipped = 0;
+    st->draws = 0;
+    st->best = -INT_MAX;
+    st->best_draw = -1;
+    st->exhausted = 0;
+    st->k = 1.0;
+    st->done = (N < S) ? 1 : 0;  // getSamples(): N < sample_size => loop exits, no model
+    if (N >= S)
+      draw_samples<S>(perm_s, N, a.raw, a.raw_len, 0, CHUNK, a.samples + (size_t)p * CHUNK * S);
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
+  if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
+}
+
+// Ransac::computeModel control flow, replayed over one chunk of results.
+template <int S, int CHUNK>
+__global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
+  extern __shared__ uint16_t perm_s[];
+  const int p = blockIdx.x;
+  const int lane = threadIdx.x;
+  SacState* st = &a.st[p];
+  if (st->done) return;
+  const int N = a.N[p];
+  for (int i = lane; i < N; i += 32) perm_s[i] = a.perm[(size_t)p * a.stride + i];
+  __syncwarp();
+  if (lane == 0) {
+    int iterations = st->iterations, skipped = st->skipped, draws = st->draws;
+    int best = st->best, best_draw = st->best_draw, done = 0, exhausted = 0;
+    double k = st->k;
+    const int max_skip = a.max_iterations * 10;
+    const int total_draws = a.raw_len / S;
+    const int32_t* valid = a.valid + (size_t)p * CHUNK;
+    const int32_t* counts = a.counts + (size_t)p * CHUNK;
+    int best_h = -1;
+    for (int h = 0; h < CHUNK; ++h) {
+      if (!((a.full || (double)iterations < k) && skipped < max_skip)) { done = 1; break; }
+      const int gd = round * CHUNK + h;
+      if (gd >= total_draws) { done = 1; exhausted = 1; break; }
+      ++draws;
+      if (!valid[h]) { ++skipped; continue; }
+      const int n = counts[h];
+      if (n > best) {
+        best = n;
+        best_draw = gd;
+        best_h = h;
+        k = a.ktable[(size_t)N * a.ktable_n + n];
+      }
+      ++iterations;
+      if (iterations > a.max_iterations) { done = 1; break; }
+    }
+    if (!done && !((a.full || (double)iterations < k) && skipped < max_skip)) done = 1;
+    if (best_h >= 0) {
+      const double* m = a.models + ((size_t)p * CHUNK + best_h) * 12;
+      for (int i = 0; i < 12; ++i) a.best_model[(size_t)p * 12 + i] = m[i];
+    }
+    st->iterations = iterations;
+    st->skipped = skipped;
+    st->draws = draws;
+    st->best = best;
+    st->best_draw = best_draw;
+    st->k = k;
+    st->exhausted = exhausted;
+    st->done = done;
+    if (!done)
+      draw_samples<S>(perm_s, N, a.raw, a.raw_len, (round + 1) * CHUNK, CHUNK,
+                      a.samples + (size_t)p * CHUNK * S);
+  }
+  __syncwarp();
+  if (!st->done)
+    for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
+}
+
+// ------------------------------------------------------------ mono chunk
+// One CTA (kMonoChunk threads) per problem.
+__global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a, int round) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int p = blockIdx.x;
+  if (a.st[p].done) return;
+  const int N = a.N[p];
+  double* s1 = smem_d;                 // [N][3] query bearings
+  double* s2 = smem_d + 3 * (size_t)N; // [N][3] match bearings
+  double* smod = s2 + 3 * (size_t)N;   // [kMonoChunk][12]
+  __shared__ int s_valid[kMonoChunk];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* ga = a.a + (size_t)p * a.stride * 3;
+  const double* gb = a.b + (size_t)p * a.stride * 3;
+  for (int i = tid; i < 3 * N; i += kMonoChunk) {
+    s1[i] = ga[i];
+    s2[i] = gb[i];
+  }
+  __syncthreads();
+  // phase 1: one hypothesis per thread
+  {
+    const int gd = round * kMonoChunk + tid;
+    int ok = 0;
+    double M[12];
+    if ((gd + 1) * 8 <= a.raw_len) {
+      const uint16_t* smp = a.samples + ((size_t)p * kMonoChunk + tid) * 8;
+      V3 f1[8], f2[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = smp[k];
+        f1[k].x = s1[3 * idx + 0]; f1[k].y = s1[3 * idx + 1]; f1[k].z = s1[3 * idx + 2];
+        f2[k].x = s2[3 * idx + 0]; f2[k].y = s2[3 * idx + 1]; f2[k].z = s2[3 * idx + 2];
+      }
+      ok = geom::mono_model(f1, f2, M) ? 1 : 0;
+    }
+    s_valid[tid] = ok;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
+    }
+  }
+  __syncthreads();
+  // phase 2: inlier counts, one hypothesis per warp pass
+  for (int h = warp; h < kMonoChunk; h += kMonoChunk / 32) {
+    int cnt = 0;
+    if (s_valid[h]) {
+      double M[12], tinv[3];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) M[i] = smod[12 * h + i];
+      geom::mono_tinv(M, tinv);
+      for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + lane;
+        bool in = false;
+        if (i < N) {
+          const V3 f1 = {s1[3 * i], s1[3 * i + 1], s1[3 * i + 2]};
+          const V3 f2 = {s2[3 * i], s2[3 * i + 1], s2[3 * i + 2]};
+          in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
+        }
+        cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+      }
+    }
+    if (lane == 0) {
+      a.valid[(size_t)p * kMonoChunk + h] = s_valid[h];
+      a.counts[(size_t)p * kMonoChunk + h] = cnt;
+    }
+  }
+  // models to global for the replay kernel
+  for (int i = tid; i < kMonoChunk * 12; i += kMonoChunk)
+    a.models[(size_t)p * kMonoChunk * 12 + i] = smod[i];
+}
+
+// ---------------------------------------------------------- stereo chunk
+__global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a, int round) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int p = blockIdx.x;
+  if (a.st[p].done) return;
+  const int N = a.N[p];
+  double* s1 = smem_d;
+  double* s2 = smem_d + 3 * (size_t)N;
+  double* smod = s2 + 3 * (size_t)N;  // [kStereoChunk][12]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* ga = a.a + (size_t)p * a.stride * 3;
+  const double* gb = a.b + (size_t)p * a.stride * 3;
+  for (int i = tid; i < 3 * N; i += kStereoChunk) {
+    s1[i] = ga[i];
+    s2[i] = gb[i];
+  }
+  __syncthreads();
+  {
+    const int gd = round * kStereoChunk + tid;
+    double M[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) M[i] = 0.0;
+    if ((gd + 1) * 3 <= a.raw_len) {
+      const uint16_t* smp = a.samples + ((size_t)p * kStereoChunk + tid) * 3;
+      const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
+      geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
+  }
+  __syncthreads();
+  for (int h = warp; h < kStereoChunk; h += kStereoChunk / 32) {
+    double M[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) M[i] = smod[12 * h + i];
+    int cnt = 0;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+      const int i = i0 + lane;
+      bool in = false;
+      if (i < N)
+        in = geom::arun_sqdist(M, s1[3 * i], s1[3 * i + 1], s1[3 * i + 2], s2[3 * i],
+                               s2[3 * i + 1], s2[3 * i + 2]) < a.sq_crit;
+      cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+    }
+    if (lane == 0) {
+      a.valid[(size_t)p * kStereoChunk + h] = 1;  // threept_arun always yields a model
+      a.counts[(size_t)p * kStereoChunk + h] = cnt;
+    }
+  }
+  for (int i = tid; i < kStereoChunk * 12; i += kStereoChunk)
+    a.models[(size_t)p * kStereoChunk * 12 + i] = smod[i];
+}
+
+// ------------------------------------------------ selectWithinDistance
+template <bool MONO>
+__global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
+  const int p = blockIdx.x;
+  const SacState st = a.st[p];
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const int N = a.N[p];
+  uint32_t* mask = a.inlier_mask + (size_t)p * a.mask_words;
+  if (st.best_draw < 0) {  // model_ empty: inliers_.clear(), return false
+    for (int w = tid; w < a.mask_words; w += 128) mask[w] = 0u;
+    if (tid == 0) a.n_inliers[p] = 0;
+    return;
+  }
+  double M[12], tinv[3];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) M[i] = a.best_model[(size_t)p * 12 + i];
+  if (MONO) geom::mono_tinv(M, tinv);
+  const double* ga = a.a + (size_t)p * a.stride * 3;
+  const double* gb = a.b + (size_t)p * a.stride * 3;
+  int cnt = 0;
+  const int nwords = (N + 31) / 32;
+  for (int w = tid >> 5; w < a.mask_words; w += 4) {
+    bool in = false;
+    const int i = w * 32 + lane;
+    if (w < nwords && i < N) {
+      if (MONO) {
+        const V3 f1 = {ga[3 * i], ga[3 * i + 1], ga[3 * i + 2]};
+        const V3 f2 = {gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]};
+        in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
+      } else {
+        in = geom::arun_sqdist(M, ga[3 * i], ga[3 * i + 1], ga[3 * i + 2], gb[3 * i],
+                               gb[3 * i + 1], gb[3 * i + 2]) < a.sq_crit;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
+    if (lane == 0) {
+      mask[w] = bal;
+      cnt += __popc(bal);
+    }
+  }
+  if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (tid == 0) a.n_inliers[p] = s_cnt;
+}
+
+// ----------------------------------------------------------------- gather
+__global__ void __launch_bounds__(128) gather_bearings_kernel(GatherArgs g) {
+  const int p = blockIdx.x;
+  const PairDesc pd = g.pairs[p];
+  const int M = g.M[p];
+  const double* qb = g.qb + (size_t)pd.q_slot * g.qF * 3;
+  const double* mb = g.sb + (size_t)g.s_off[pd.m_frame] * 3;
+  const uint16_t* iq = g.iq + (size_t)p * g.stride;
+  const uint16_t* im = g.im + (size_t)p * g.stride;
+  double* oa = g.a + (size_t)p * g.stride * 3;
+  double* ob = g.b + (size_t)p * g.stride * 3;
+  for (int i = threadIdx.x; i < M; i += 128) {
+    const int a = iq[i], b = im[i];
+    oa[3 * i + 0] = qb[3 * a + 0]; oa[3 * i + 1] = qb[3 * a + 1]; oa[3 * i + 2] = qb[3 * a + 2];
+    ob[3 * i + 0] = mb[3 * b + 0]; ob[3 * i + 1] = mb[3 * b + 1]; ob[3 * i + 2] = mb[3 * b + 2];
+  }
+  if (threadIdx.x == 0) g.N[p] = M;
+}
+
+// recoverPose() prologue: keep mono inliers whose 3-D keypoints both have
+// norm > 1e-3 (ordered compaction).  N3 = 0 when the mono gate failed.
+__global__ void __launch_bounds__(128) gather_points_kernel(StereoGatherArgs sg) {
+  const GatherArgs& g = sg.g;
+  const int p = blockIdx.x;
+  __shared__ int warp_cnt[4];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  if (!sg.mono_ok[p]) {
+    if (tid == 0) g.N[p] = 0;
+    return;
+  }
+  const PairDesc pd = g.pairs[p];
+  const int M = g.M[p];
+  const double* qp = g.qp + (size_t)pd.q_slot * g.qF * 3;
+  const double* mp = g.sp + (size_t)g.s_off[pd.m_frame] * 3;
+  const uint16_t* iq = g.iq + (size_t)p * g.stride;
+  const uint16_t* im = g.im + (size_t)p * g.stride;
+  const uint32_t* mask = sg.mono_mask + (size_t)p * sg.mask_words;
+  double* oa = g.a + (size_t)p * g.stride * 3;
+  double* ob = g.b + (size_t)p * g.stride * 3;
+  for (int i0 = 0; i0 < M; i0 += 128) {
+    const int i = i0 + tid;
+    bool keep = false;
+    int qa = 0, mb = 0;
+    double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+    if (i < M && ((mask[i >> 5] >> (i & 31)) & 1u)) {
+      qa = iq[i];
+      mb = im[i];
+      ax = qp[3 * qa]; ay = qp[3 * qa + 1]; az = qp[3 * qa + 2];
+      bx = mp[3 * mb]; by = mp[3 * mb + 1]; bz = mp[3 * mb + 2];
+      const double na = sqrt((ax * ax + ay * ay) + az * az);
+      const double nb = sqrt((bx * bx + by * by) + bz * bz);
+      keep = na > 1e-3 && nb > 1e-3;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (keep) {
+      const int pos = off + __popc(bal & ((1u << lane) - 1u));
+      oa[3 * pos] = ax; oa[3 * pos + 1] = ay; oa[3 * pos + 2] = az;
+      ob[3 * pos] = bx; ob[3 * pos + 1] = by; ob[3 * pos + 2] = bz;
+      sg.kq[(size_t)p * g.stride + pos] = (uint16_t)qa;
+      sg.km[(size_t)p * g.stride + pos] = (uint16_t)mb;
+    }
+    __syncthreads();
+    if (tid == 0) base_s += warp_cnt[0] + warp_cnt[1] + warp_cnt[2] + warp_cnt[3];
+    __syncthreads();
+  }
+  if (tid == 0) g.N[p] = base_s;
+}
+
+// acceptance gates of geometricVerificationNister / recoverPose
+__global__ void mono_gate_kernel(FinalizeArgs f) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f.P) return;
+  const int inl = f.mono_inl[p];
+  const int M = f.M[p];
+  int ok = f.mono_st[p].best_draw >= 0;
+  if (ok && inl < f.min_inliers) ok = 0;
+  if (ok && (double)inl / (double)M < f.min_ratio_mono) ok = 0;
+  f.mono_ok[p] = ok;
+}
+__global__ void finalize_kernel(FinalizeArgs f) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= f.P) return;
+  int status = 1;
+  int mono_inl = 0, stereo_inl = 0;
+  if (f.mono_ok[p]) {
+    status = 2;
+    mono_inl = f.mono_inl[p];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) f.out_R[(size_t)p * 9 + 3 * r + c] = f.mono_model[(size_t)p * 12 + 4 * r + c];
+    const int N3 = f.N3[p];
+    const int inl3 = f.inl3[p];
+    int ok = N3 >= 3 && f.st3[p].best_draw >= 0;
+    if (ok && inl3 < f.min_inliers) ok = 0;
+    if (ok && (double)inl3 / (double)N3 < f.min_ratio_stereo) ok = 0;
+    if (ok) {
+      status = 0;
+      stereo_inl = inl3;
+      for (int i = 0; i < 12; ++i) f.out_T[(size_t)p * 12 + i] = f.model3[(size_t)p * 12 + i];
+    }
+  }
+  f.status[p] = status;
+  f.out_mono_inl[p] = mono_inl;
+  f.out_stereo_inl[p] = stereo_inl;
+}
+
+// --------------------------------------------------------------- launchers
+static size_t mono_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kMonoChunk); }
+static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
+
+template <class K>
+static void ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    KML_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
+  if (a.P <= 0) return;
+  const size_t sm = sizeof(uint16_t) * (size_t)a.stride;
+  if (sample_size == 8)
+    sac_init_kernel<8, kMonoChunk><<<a.P, 32, sm, s>>>(a);
+  else
+    sac_init_kernel<3, kStereoChunk><<<a.P, 32, sm, s>>>(a);
+}
+
+int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
+  if (a.P <= 0) return 0;
+  const size_t sm = mono_smem(a.stride);
+  ensure_smem(mono_chunk_kernel, sm);
+  mono_chunk_kernel<<<a.P, kMonoChunk, sm, s>>>(a, round);
+  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  return 2;
+}
+int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
+  if (a.P <= 0) return 0;
+  const size_t sm = stereo_smem(a.stride);
+  ensure_smem(stereo_chunk_kernel, sm);
+  stereo_chunk_kernel<<<a.P, kStereoChunk, sm, s>>>(a, round);
+  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  return 2;
+}
+void launch_mono_select(const SacArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  sac_select_kernel<true><<<a.P, 128, 0, s>>>(a);
+}
+void launch_stereo_select(const SacArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  sac_select_kernel<false><<<a.P, 128, 0, s>>>(a);
+}
+void launch_gather_bearings(const GatherArgs& g, cudaStream_t s) {
+  if (g.P <= 0) return;
+  gather_bearings_kernel<<<g.P, 128, 0, s>>>(g);
+}
+void launch_gather_points(const StereoGatherArgs& g, cudaStream_t s) {
+  if (g.g.P <= 0) return;
+  gather_points_kernel<<<g.g.P, 128, 0, s>>>(g);
+}
+void launch_mono_gate(const FinalizeArgs& f, cudaStream_t s) {
+  if (f.P <= 0) return;
+  mono_gate_kernel<<<(f.P + 127) / 128, 128, 0, s>>>(f);
+}
+void launch_finalize(const FinalizeArgs& f, cudaStream_t s) {
+  if (f.P <= 0) return;
+  finalize_kernel<<<(f.P + 127) / 128, 128, 0, s>>>(f);
+}
+
+}  // namespace kml

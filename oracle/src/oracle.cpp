@@ -95,9 +95,12 @@ static int db_query(const kmo_db* db, const uint32_t* ids, const float* vals, in
 // A.4 / B.1  BFMatcher(NORM_HAMMING).knnMatch(k=2) + Lowe ratio
 // =========================================================================
 static inline int hamming256(const uint8_t* a, const uint8_t* b) {
-  int d = 0;
-  for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
-  return d;
+  // cv::hal::normHamming on 32 bytes (4 x 64-bit popcount)
+  uint64_t x[4], y[4];
+  memcpy(x, a, 32);
+  memcpy(y, b, 32);
+  return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+         __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
 }
 
 static void knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* idx,

@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — loop-closure queries/s on B200 (BASELINE.json metric).
+
+Workload (config C2): 6 robot databases x 5 000 keyframes per
+GPU (500 ORB-256 features / keyframe, synthetic k=10 L=6 vocabulary), queries
+in batches of 256, top_k_verify = 16 candidates verified per query
+(kNN + Lowe 0.9 -> mono 5-pt RANSAC -> stereo Arun RANSAC).  One "step" = one
+batch of 256 queries through the whole hot path.
+
+  value : queries/s with the batch already resident in HBM (kml_query_batch_run),
+          timed on the device with CUDA events on the library's stream.
+  e2e   : the same through kml_query_batch with HOST buffers (H2D of the
+          batch + D2H of the records inside the timed region).
+  N > 1 : one process per GPU, databases sharded by robot (each rank holds its
+          own 6 x 5 000 shard), the batch is replicated on every rank and the
+          per-shard records are merged by ONE ncclAllGather per step; value =
+          (N * 256 shard-queries) / max-over-ranks step time  ("weak").
+
+`--impl reference` times the CPU oracle (scalar C++ restatement of the
+reference algorithms, all host threads) on bounded samples of the same
+workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "kimera-multi_b200"))
+
+import numpy as np  # noqa: E402
+
+N_ROBOTS = 6
+N_KEYFRAMES = 5000
+BATCH = 256
+F = 500
+METRIC = "loop_closure_queries_per_s"
+UNIT = "queries/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_world(rank, log):
+    from kml import synth
+    t0 = time.time()
+    world = synth.World(N_KEYFRAMES // 4, F=F)
+    robots = [rank * N_ROBOTS + r for r in range(N_ROBOTS)]
+    log("world ready in %.1fs; shard robots %s" % (time.time() - t0, robots))
+    return world, robots
+
+
+def fill_detector(det, world, robots, log):
+    from kml import synth
+    t0 = time.time()
+    for ch in synth.build_database(world, robots, N_KEYFRAMES, chunk=1000):
+        det.addBowVectors(ch["robot"], ch["poses"], ch["bow_off"], ch["bow_ids"], ch["bow_vals"])
+        det.addVLCFrames(ch["robot"], ch["poses"], ch["desc"], ch["bearings"], ch["points"])
+    log("database of %d x %d keyframes resident in %.1fs" % (len(robots), N_KEYFRAMES, time.time() - t0))
+
+
+def make_batches(world, n, n_robots_total, B=BATCH):
+    from kml import synth
+    out = []
+    for k in range(n):
+        q = synth.make_queries(world, B, N_KEYFRAMES, n_robots_total, key=k)
+        fq, fp = q["frames"], q["prev"]
+        out.append((q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"],
+                    fp["bow_off"], fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"],
+                    fq["points"]))
+    return out
+
+
+def batch_bytes(b):
+    return int(sum(np.asarray(x).nbytes for x in b))
+
+
+def run_reference(args, rank, world_size, log):
+    """CPU arm: the oracle (scalar C++ port of DBoW2 + BFMatcher + OpenGV paths)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kml_oracle as ko
+    world, robots = build_world(0, log)
+    lcd = ko.LoopClosureDetector()
+    from kml import synth
+    t0 = time.time()
+    for ch in synth.build_database(world, robots, N_KEYFRAMES, chunk=1000):
+        for i, p in enumerate(ch["poses"]):
+            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
+            lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
+            lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+    log("oracle database ready in %.1fs" % (time.time() - t0))
+    threads = ko.num_threads()
+    sample = max(2 * threads, 16)
+    batches = make_batches(world, args.steps + args.warmup, N_ROBOTS, B=sample)
+    times = []
+    for i, b in enumerate(batches):
+        t0 = time.perf_counter()
+        lcd.query_batch(*b, threads=threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+        "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d-query samples of the 256-query batch, %d OpenMP threads" % (sample, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "C2: %d robot DBs x %d keyframes per GPU, %d ORB-256 features/keyframe, "
+                        "%d-query batches, top_k_verify 16, lowe 0.9, mono 5-pt + stereo Arun RANSAC "
+                        "(max 1000 it, p 0.995)" % (N_ROBOTS, N_KEYFRAMES, F, BATCH),
+            "global_batch": BATCH, "n_robots_per_gpu": N_ROBOTS, "keyframes_per_robot": N_KEYFRAMES,
+            "parallelism": "robot-sharded x%d, replicated query batch + 1 ncclAllGather/step" % n if n > 1 else "single GPU",
+            "l2": "256 MiB device memset between timed steps; distinct query batch every step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kml", choices=["kml", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    def log(msg):
+        print("[bench r%d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world_size, log)
+        return
+
+    import kml
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world_size)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    kml.build()
+    det = kml.LoopClosureDetector(device=local_rank)
+    if world_size > 1:
+        uid = [kml.LoopClosureDetector.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        det.comm_init(world_size, rank, uid[0])
+    world, robots = build_world(rank, log)
+    fill_detector(det, world, robots, log)
+    n_batches = args.steps + args.warmup
+    batches = make_batches(world, min(n_batches, 6), N_ROBOTS * world_size)
+    sharded = world_size > 1
+    popc_peak = det.peak_popc()
+    fp64_peak = det.peak_fp64()
+
+    # ---------------- resident arm: device-timed steps
+    for i in range(args.warmup):
+        det.query_batch_upload(*batches[i % len(batches)])
+        det.query_batch_run(sharded=sharded)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = det.stats().kernel_launches
+    dev_ms, wall_ms, stage = [], [], {"bow": 0.0, "match": 0.0, "mono": 0.0, "stereo": 0.0}
+    postings = hyp_m = hyp_s = pairs = 0
+    for i in range(args.steps):
+        det.query_batch_upload(*batches[(args.warmup + i) % len(batches)])
+        det.flush_l2()
+        t0 = time.perf_counter()
+        out, counts = det.query_batch_run(sharded=sharded)
+        wall_ms.append(1e3 * (time.perf_counter() - t0))
+        st = det.stats()
+        dev_ms.append(st.ms_total if not sharded else wall_ms[-1])
+        stage["bow"] += st.ms_bow; stage["match"] += st.ms_match
+        stage["mono"] += st.ms_mono; stage["stereo"] += st.ms_stereo
+        postings += st.bow_postings_last; hyp_m += st.mono_hypotheses_last
+        hyp_s += st.stereo_hypotheses_last; pairs += st.pairs_last
+    launches = det.stats().kernel_launches - l0
+    clocks = sampler.stop()
+    barrier()
+    step_ms = float(np.sum(dev_ms))
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t[0])
+    value = world_size * BATCH * args.steps / (step_ms * 1e-3)
+
+    # ---------------- e2e arm: host buffers in, records out, every step
+    for i in range(2):
+        det.query_batch(*batches[i % len(batches)]) if not sharded else None
+    barrier()
+    e2e_t = 0.0
+    for i in range(args.steps):
+        b = batches[(args.warmup + i) % len(batches)]
+        det.flush_l2()
+        t0 = time.perf_counter()
+        if sharded:
+            det.query_batch_upload(*b)
+            out, counts = det.query_batch_run(sharded=True)
+        else:
+            out, counts = det.query_batch(*b)
+        e2e_t += time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_t], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t[0])
+    e2e_value = world_size * BATCH * args.steps / e2e_t
+    h2d = batch_bytes(batches[0])
+    d2h = int(out.nbytes + counts.nbytes)
+
+    # ---------------- rooflines (algorithmic work / device time per stage)
+    hbm_peak, peak_src = load_peaks()
+    K = args.steps
+    compares = pairs * F * F
+    roof = {
+        "bow_scan": {"bound": "hbm", "achieved": postings * 8 / (stage["bow"] * 1e-3) / 1e9 if stage["bow"] else None,
+                     "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": postings * 8 / K, "ms_per_step": stage["bow"] / K},
+        "hamming_knn": {"bound": "popc", "achieved": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                        "peak": popc_peak / 1e12, "unit": "T POPC32/s", "peak_source": "measured (kml_peak_popc, same run)",
+                        "compares_per_step": compares / K, "ms_per_step": stage["match"] / K},
+        "mono_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_m / K, "ms_per_step": stage["mono"] / K,
+                        "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "peak_source": "measured (kml_peak_fp64, same run)"},
+        "stereo_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_s / K, "ms_per_step": stage["stereo"] / K,
+                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s"},
+    }
+    for k in ("bow_scan", "hamming_knn"):
+        if roof[k]["achieved"]:
+            roof[k]["frac"] = roof[k]["achieved"] / roof[k]["peak"]
+    # flop model: 5-pt hypothesis ~ 60 kflop solver + 8x4x10 scoring; residual 95 flop
+    dominant = max(("bow", "match", "mono", "stereo"), key=lambda s: stage[s])
+    dom_key = {"bow": "bow_scan", "match": "hamming_knn", "mono": "mono_ransac", "stereo": "stereo_ransac"}[dominant]
+    roofline = dict(roof[dom_key])
+    roofline["kernel"] = dom_key
+    roofline.setdefault("achieved", None)
+    roofline.setdefault("frac", None)
+    roofline["traffic"] = None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64-fixed/f64", "data": "synthetic",
+        "config": workload_config(world_size), "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": roofline, "rooflines": roof,
+        "stage_ms_per_step": {k: v / K for k, v in stage.items()},
+        "wall_ms_per_step": float(np.mean(wall_ms)),
+        "loop_closures_last_step": int((out["status"][counts[:, None] > np.arange(out.shape[1])[None]] == 0).sum()),
+    }
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(world, robots, log)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    det.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(world, robots, log):
+    """The oracle timed on this box's host cores on a bounded sample (rank 0, N=1)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kml_oracle as ko
+    from kml import synth
+    lcd = ko.LoopClosureDetector()
+    t0 = time.time()
+    for ch in synth.build_database(world, robots, N_KEYFRAMES, chunk=1000):
+        for i, p in enumerate(ch["poses"]):
+            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
+            lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
+            lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+    log("oracle database ready in %.1fs" % (time.time() - t0))
+    threads = ko.num_threads()
+    sample = max(4 * threads, 32)
+    b = make_batches(world, 1, N_ROBOTS, B=sample)[0]
+    lcd.query_batch(*b, threads=threads)  # warm-up
+    t0 = time.perf_counter()
+    lcd.query_batch(*b, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d queries of the C2 workload, %d OpenMP threads, %.2fs" % (sample, threads, dt)}
+
+
+if __name__ == "__main__":
+    main()

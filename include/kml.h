@@ -208,6 +208,9 @@ int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const
 /* microbenchmarks for the roofline denominators (ops per second) */
 int kml_peak_popc(kml_handle* h, double* popc32_per_s);
 int kml_peak_fp64(kml_handle* h, double* flop_per_s);
+/* measurement hygiene: overwrite a 256 MiB device buffer (> 126 MB L2) on the
+ * handle's stream so the next timed step starts with a cold L2 */
+int kml_flush_l2(kml_handle* h);
 
 /* ---- multi-GPU (one process per GPU; databases sharded by robot) -------- */
 #define KML_UNIQUE_ID_BYTES 128

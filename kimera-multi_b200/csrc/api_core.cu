@@ -227,6 +227,20 @@ int kml_peak_popc(kml_handle* h, double* out) {
   return KML_OK;
   KML_API_END(h)
 }
+int kml_flush_l2(kml_handle* h) {
+  KML_API_BEGIN(h)
+  static thread_local void* buf = nullptr;
+  static thread_local int buf_dev = -1;
+  const size_t bytes = 256ull << 20;
+  if (!buf || buf_dev != h->device) {
+    KML_CUDA(cudaMalloc(&buf, bytes));
+    buf_dev = h->device;
+  }
+  KML_CUDA(cudaMemsetAsync(buf, 0x5a, bytes, h->stream));
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  return KML_OK;
+  KML_API_END(h)
+}
 int kml_peak_fp64(kml_handle* h, double* out) {
   KML_API_BEGIN(h)
   if (!out) return KML_ERR_ARG;

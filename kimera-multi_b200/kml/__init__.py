@@ -320,6 +320,9 @@ class LoopClosureDetector:
         self._check(lib().kml_peak_popc(self._h, C.byref(out)))
         return out.value
 
+    def flush_l2(self):
+        self._check(lib().kml_flush_l2(self._h))
+
     def peak_fp64(self):
         out = C.c_double(0)
         self._check(lib().kml_peak_fp64(self._h, C.byref(out)))

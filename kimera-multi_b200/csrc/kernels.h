@@ -59,7 +59,9 @@ void launch_bow(const BowArgs& a, cudaStream_t s);
 // -------------------------------------------------------------- ransac.cu
 // Per-pair RANSAC state (opengv::sac::Ransac::computeModel locals)
 struct SacState {
-  int32_t iterations, skipped, draws, best, best_draw, done, exhausted, pad;
+  int32_t iterations, skipped, draws, best, best_draw, done, exhausted;
+  int32_t r_begin, r_end;  // draws [r_begin, r_end) are evaluated by the next chunk launch
+  int32_t pad;
   double k;
 };
 struct SacArgs {
@@ -71,10 +73,10 @@ struct SacArgs {
   const uint32_t* raw;   // pre-drawn mt19937()>>1 stream
   int raw_len;
   uint16_t* perm;        // [P][stride] persistent shuffle state
-  uint16_t* samples;     // [P][chunk][S]
-  double* models;        // [P][chunk][12]
-  int32_t* valid;        // [P][chunk]
-  int32_t* counts;       // [P][chunk]
+  int cap_draws;         // draws available per problem (raw_len / S)
+  uint16_t* samples;     // [P][cap_draws][S]
+  int32_t* valid;        // [P][cap_draws]
+  int32_t* counts;       // [P][cap_draws]
   SacState* st;          // [P]
   double* best_model;    // [P][12]
   const double* ktable;  // [(Nmax+1)*(Nmax+1)] k as function of (N, best count)
@@ -87,10 +89,12 @@ struct SacArgs {
   int mask_words;
   int32_t* n_inliers;    // [P]
 };
-constexpr int kMonoChunk = 64;
-constexpr int kStereoChunk = 128;
+constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
+constexpr int kStereoChunk = 128;  // hypotheses per CTA (stereo) and size of round 0
+constexpr int kSacRounds = 4;      // round 0 + up to 3 remainder rounds
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
-int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);    // returns #kernels launched
+// one round = chunk kernel over the pending draw range + replay; returns #kernels launched
+int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s);
 void launch_mono_select(const SacArgs& a, cudaStream_t s);
 void launch_stereo_select(const SacArgs& a, cudaStream_t s);

@@ -357,19 +357,21 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->d_ktable_mono, &h->ktable_n_mono);
   else
     ensure_ktable(h, stride, 3, prm.ransac_probability, &h->d_ktable_stereo, &h->ktable_n_stereo);
+  const int raw_len = (int)h->raw_h.size();
+  const int cap_draws = std::min(raw_len / S, max_it + 1 + 256);
+  (void)chunk;
   h->d_perm.scratch((size_t)P * stride);
-  h->d_samples.scratch((size_t)P * chunk * S);
-  h->d_models.scratch((size_t)P * chunk * 12);
-  h->d_valid.scratch((size_t)P * chunk);
-  h->d_counts.scratch((size_t)P * chunk);
+  h->d_samples.scratch((size_t)P * cap_draws * S);
+  h->d_valid.scratch((size_t)P * cap_draws);
+  h->d_counts.scratch((size_t)P * cap_draws);
   out.st->scratch(P);
   out.best->scratch((size_t)P * 12);
   out.mask->scratch((size_t)P * mask_words);
   out.inl->scratch(P);
   SacArgs a;
   a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
-  a.raw = h->d_raw.p; a.raw_len = (int)h->raw_h.size();
-  a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
+  a.raw = h->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
+  a.perm = h->d_perm.p; a.samples = h->d_samples.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
   a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
   a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;
@@ -380,11 +382,9 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * P, h->stream));
   launch_sac_init(a, S, h->stream);
   h->stats.kernel_launches += 1;
-  // rounds needed to cover max_it+1 counted trials plus the skip reserve
-  const int total_draws = a.raw_len / S;
-  const int want = std::min(total_draws, max_it + 1 + 256);
-  const int rounds = (want + chunk - 1) / chunk;
-  for (int r = 0; r < rounds; ++r)
+  // round 0 evaluates one chunk; each later round covers every trial the
+  // reference loop can still need (k never increases), plus a skip reserve
+  for (int r = 0; r < kSacRounds; ++r)
     h->stats.kernel_launches += mono ? launch_mono_round(a, r, h->stream) : launch_stereo_round(a, r, h->stream);
   if (mono) launch_mono_select(a, h->stream); else launch_stereo_select(a, h->stream);
   h->stats.kernel_launches += 1;

@@ -34,12 +34,11 @@ using geom::V3;
 // --------------------------------------------------------------- sampling
 // SampleConsensusProblem::drawIndexSample: for i<S swap(shuffled[i],
 // shuffled[i + rnd() % (N-i)]); rnd() = mt19937()>>1 (pre-drawn, host).
+// Draws [first, last) are appended to out[draw][S]; the shuffle state persists.
 template <int S>
-__device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict__ raw,
-                             int raw_len, int first_draw, int n_draws, uint16_t* out) {
-  for (int d = 0; d < n_draws; ++d) {
-    const int gd = first_draw + d;
-    if ((gd + 1) * S > raw_len) break;
+__device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict__ raw, int first,
+                             int last, uint16_t* out) {
+  for (int gd = first; gd < last; ++gd) {
     for (int i = 0; i < S; ++i) {
       const uint32_t r = raw[gd * S + i];
       const int j = i + (int)(r % (uint32_t)(N - i));
@@ -47,7 +46,7 @@ __device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict
       perm_s[i] = perm_s[j];
       perm_s[j] = t;
     }
-    for (int i = 0; i < S; ++i) out[d * S + i] = perm_s[i];
+    for (int i = 0; i < S; ++i) out[(size_t)gd * S + i] = perm_s[i];
   }
 }
 
@@ -69,16 +68,19 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
     st->exhausted = 0;
     st->k = 1.0;
     st->done = (N < S) ? 1 : 0;  // getSamples(): N < sample_size => loop exits, no model
-    if (N >= S)
-      draw_samples<S>(perm_s, N, a.raw, a.raw_len, 0, CHUNK, a.samples + (size_t)p * CHUNK * S);
+    st->r_begin = 0;
+    st->r_end = (N < S) ? 0 : min(CHUNK, a.cap_draws);
+    if (N >= S) draw_samples<S>(perm_s, N, a.raw, 0, st->r_end, a.samples + (size_t)p * a.cap_draws * S);
   }
   __syncwarp();
   for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
 }
 
-// Ransac::computeModel control flow, replayed over one chunk of results.
-template <int S, int CHUNK>
+// Ransac::computeModel control flow, replayed over the draws of one round.
+// k never increases, so after a round the number of trials still required is
+// known exactly (up to skipped samples): the next round covers all of them.
+template <int S>
 __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   extern __shared__ uint16_t perm_s[];
   const int p = blockIdx.x;
@@ -93,30 +95,34 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     int best = st->best, best_draw = st->best_draw, done = 0, exhausted = 0;
     double k = st->k;
     const int max_skip = a.max_iterations * 10;
-    const int total_draws = a.raw_len / S;
-    const int32_t* valid = a.valid + (size_t)p * CHUNK;
-    const int32_t* counts = a.counts + (size_t)p * CHUNK;
-    int best_h = -1;
-    for (int h = 0; h < CHUNK; ++h) {
+    const int r_begin = st->r_begin, r_end = st->r_end;
+    const int32_t* valid = a.valid + (size_t)p * a.cap_draws;
+    const int32_t* counts = a.counts + (size_t)p * a.cap_draws;
+    for (int gd = r_begin; gd < r_end; ++gd) {
       if (!((a.full || (double)iterations < k) && skipped < max_skip)) { done = 1; break; }
-      const int gd = round * CHUNK + h;
-      if (gd >= total_draws) { done = 1; exhausted = 1; break; }
       ++draws;
-      if (!valid[h]) { ++skipped; continue; }
-      const int n = counts[h];
+      if (!valid[gd]) { ++skipped; continue; }
+      const int n = counts[gd];
       if (n > best) {
         best = n;
         best_draw = gd;
-        best_h = h;
         k = a.ktable[(size_t)N * a.ktable_n + n];
       }
       ++iterations;
       if (iterations > a.max_iterations) { done = 1; break; }
     }
     if (!done && !((a.full || (double)iterations < k) && skipped < max_skip)) done = 1;
-    if (best_h >= 0) {
-      const double* m = a.models + ((size_t)p * CHUNK + best_h) * 12;
-      for (int i = 0; i < 12; ++i) a.best_model[(size_t)p * 12 + i] = m[i];
+    int nb = r_end, ne = r_end;
+    if (!done) {
+      // trials still required if no further sample is skipped
+      const int cap_it = a.max_iterations + 1;
+      int target = cap_it;
+      if (!a.full && k < (double)cap_it) target = (int)ceil(k);
+      int rem = target - iterations;
+      if (rem < 1) rem = 1;
+      const int slack = (round == 0) ? 16 : ((round == 1) ? 64 : a.cap_draws);
+      ne = min(a.cap_draws, nb + rem + slack);
+      if (round + 1 >= kSacRounds || nb >= a.cap_draws) { done = 1; exhausted = 1; }
     }
     st->iterations = iterations;
     st->skipped = skipped;
@@ -126,9 +132,9 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     st->k = k;
     st->exhausted = exhausted;
     st->done = done;
-    if (!done)
-      draw_samples<S>(perm_s, N, a.raw, a.raw_len, (round + 1) * CHUNK, CHUNK,
-                      a.samples + (size_t)p * CHUNK * S);
+    st->r_begin = nb;
+    st->r_end = ne;
+    if (!done) draw_samples<S>(perm_s, N, a.raw, nb, ne, a.samples + (size_t)p * a.cap_draws * S);
   }
   __syncwarp();
   if (!st->done)
@@ -136,11 +142,14 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 }
 
 // ------------------------------------------------------------ mono chunk
-// One CTA (kMonoChunk threads) per problem.
-__global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a, int round) {
+// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64).
+__global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
-  if (a.st[p].done) return;
+  const SacState st = a.st[p];
+  if (st.done) return;
+  const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
+  if (d0 >= st.r_end) return;
   const int N = a.N[p];
   double* s1 = smem_d;                 // [N][3] query bearings
   double* s2 = smem_d + 3 * (size_t)N; // [N][3] match bearings
@@ -154,13 +163,13 @@ __global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a, int r
     s2[i] = gb[i];
   }
   __syncthreads();
+  const int nh = min(kMonoChunk, st.r_end - d0);
   // phase 1: one hypothesis per thread
   {
-    const int gd = round * kMonoChunk + tid;
     int ok = 0;
     double M[12];
-    if ((gd + 1) * 8 <= a.raw_len) {
-      const uint16_t* smp = a.samples + ((size_t)p * kMonoChunk + tid) * 8;
+    if (tid < nh) {
+      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + tid) * 8;
       V3 f1[8], f2[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a, int r
   }
   __syncthreads();
   // phase 2: inlier counts, one hypothesis per warp pass
-  for (int h = warp; h < kMonoChunk; h += kMonoChunk / 32) {
+  for (int h = warp; h < nh; h += kMonoChunk / 32) {
     int cnt = 0;
     if (s_valid[h]) {
       double M[12], tinv[3];
@@ -197,20 +206,20 @@ __global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a, int r
       }
     }
     if (lane == 0) {
-      a.valid[(size_t)p * kMonoChunk + h] = s_valid[h];
-      a.counts[(size_t)p * kMonoChunk + h] = cnt;
+      a.valid[(size_t)p * a.cap_draws + d0 + h] = s_valid[h];
+      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
   }
-  // models to global for the replay kernel
-  for (int i = tid; i < kMonoChunk * 12; i += kMonoChunk)
-    a.models[(size_t)p * kMonoChunk * 12 + i] = smod[i];
 }
 
 // ---------------------------------------------------------- stereo chunk
-__global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a, int round) {
+__global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
-  if (a.st[p].done) return;
+  const SacState st = a.st[p];
+  if (st.done) return;
+  const int d0 = st.r_begin + blockIdx.y * kStereoChunk;
+  if (d0 >= st.r_end) return;
   const int N = a.N[p];
   double* s1 = smem_d;
   double* s2 = smem_d + 3 * (size_t)N;
@@ -223,21 +232,17 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a, i
     s2[i] = gb[i];
   }
   __syncthreads();
-  {
-    const int gd = round * kStereoChunk + tid;
+  const int nh = min(kStereoChunk, st.r_end - d0);
+  if (tid < nh) {
     double M[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) M[i] = 0.0;
-    if ((gd + 1) * 3 <= a.raw_len) {
-      const uint16_t* smp = a.samples + ((size_t)p * kStereoChunk + tid) * 3;
-      const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
-      geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
-    }
+    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + tid) * 3;
+    const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
+    geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
 #pragma unroll
     for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
   }
   __syncthreads();
-  for (int h = warp; h < kStereoChunk; h += kStereoChunk / 32) {
+  for (int h = warp; h < nh; h += kStereoChunk / 32) {
     double M[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) M[i] = smod[12 * h + i];
@@ -251,23 +256,23 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a, i
       cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
     }
     if (lane == 0) {
-      a.valid[(size_t)p * kStereoChunk + h] = 1;  // threept_arun always yields a model
-      a.counts[(size_t)p * kStereoChunk + h] = cnt;
+      a.valid[(size_t)p * a.cap_draws + d0 + h] = 1;  // threept_arun always yields a model
+      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
   }
-  for (int i = tid; i < kStereoChunk * 12; i += kStereoChunk)
-    a.models[(size_t)p * kStereoChunk * 12 + i] = smod[i];
 }
 
 // ------------------------------------------------ selectWithinDistance
+// Recomputes the winning hypothesis from its sample (same arithmetic, same
+// bits as when it was scored) and emits model_coefficients_ + inliers_.
 template <bool MONO>
 __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ int s_cnt;
+  __shared__ double s_M[12];
   if (tid == 0) s_cnt = 0;
-  __syncthreads();
   const int N = a.N[p];
   uint32_t* mask = a.inlier_mask + (size_t)p * a.mask_words;
   if (st.best_draw < 0) {  // model_ empty: inliers_.clear(), return false
@@ -275,12 +280,34 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
     if (tid == 0) a.n_inliers[p] = 0;
     return;
   }
-  double M[12], tinv[3];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) M[i] = a.best_model[(size_t)p * 12 + i];
-  if (MONO) geom::mono_tinv(M, tinv);
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
+  if (tid == 0) {
+    double M[12];
+    if (MONO) {
+      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 8;
+      V3 f1[8], f2[8];
+      for (int k = 0; k < 8; ++k) {
+        const int idx = smp[k];
+        f1[k].x = ga[3 * idx + 0]; f1[k].y = ga[3 * idx + 1]; f1[k].z = ga[3 * idx + 2];
+        f2[k].x = gb[3 * idx + 0]; f2[k].y = gb[3 * idx + 1]; f2[k].z = gb[3 * idx + 2];
+      }
+      geom::mono_model(f1, f2, M);
+    } else {
+      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 3;
+      const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
+      geom::arun3(ga + 3 * i0, ga + 3 * i1, ga + 3 * i2, gb + 3 * i0, gb + 3 * i1, gb + 3 * i2, M);
+    }
+    for (int i = 0; i < 12; ++i) {
+      s_M[i] = M[i];
+      a.best_model[(size_t)p * 12 + i] = M[i];
+    }
+  }
+  __syncthreads();
+  double M[12], tinv[3];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) M[i] = s_M[i];
+  if (MONO) geom::mono_tinv(M, tinv);
   int cnt = 0;
   const int nwords = (N + 31) / 32;
   for (int w = tid >> 5; w < a.mask_words; w += 4) {
@@ -442,16 +469,18 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem(a.stride);
   ensure_smem(mono_chunk_kernel, sm);
-  mono_chunk_kernel<<<a.P, kMonoChunk, sm, s>>>(a, round);
-  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  const int blocks = round == 0 ? 1 : (a.cap_draws + kMonoChunk - 1) / kMonoChunk;
+  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
+  sac_replay_kernel<8><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
   ensure_smem(stereo_chunk_kernel, sm);
-  stereo_chunk_kernel<<<a.P, kStereoChunk, sm, s>>>(a, round);
-  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  const int blocks = round == 0 ? 1 : (a.cap_draws + kStereoChunk - 1) / kStereoChunk;
+  stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoChunk, sm, s>>>(a);
+  sac_replay_kernel<3><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }
 void launch_mono_select(const SacArgs& a, cudaStream_t s) {

@@ -346,3 +346,6 @@ def mask_to_indices(mask_row, n):
     """inlier bitmask words -> ascending index array"""
     bits = np.unpackbits(mask_row.view(np.uint8), bitorder="little")[:n]
     return np.nonzero(bits)[0].astype(np.uint32)
+
+
+from . import logio  # noqa: E402,F401

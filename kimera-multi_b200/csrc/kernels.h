@@ -91,7 +91,11 @@ struct SacArgs {
 };
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
 constexpr int kStereoChunk = 128;  // hypotheses per CTA (stereo) and size of round 0
-constexpr int kSacRounds = 4;      // round 0 + up to 3 remainder rounds
+constexpr int kSacRounds = 6;      // 64,64,128,256,512 new draws, then everything that is left
+// upper bound of NEW draws evaluated per problem in round r (doubling schedule)
+__host__ __device__ inline int sac_round_draws(int round, int chunk) {
+  return round == 0 ? chunk : chunk << (round - 1);
+}
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
 // one round = chunk kernel over the pending draw range + replay; returns #kernels launched
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "geom.cuh"
+#include "fivept_warp.cuh"
 #include "kernels.h"
 
 namespace kml {
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
 // Ransac::computeModel control flow, replayed over the draws of one round.
 // k never increases, so after a round the number of trials still required is
 // known exactly (up to skipped samples): the next round covers all of them.
-template <int S>
+template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   extern __shared__ uint16_t perm_s[];
   const int p = blockIdx.x;
@@ -120,8 +121,13 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
       if (!a.full && k < (double)cap_it) target = (int)ceil(k);
       int rem = target - iterations;
       if (rem < 1) rem = 1;
-      const int slack = (round == 0) ? 16 : ((round == 1) ? 64 : a.cap_draws);
-      ne = min(a.cap_draws, nb + rem + slack);
+      // k is only an upper bound (it shrinks whenever a better model shows
+      // up), so the next round evaluates at most as many new draws as have
+      // been evaluated so far (doubling), except the last round, which
+      // covers everything that can still be needed plus the skip reserve.
+      const bool last = (round + 2 >= kSacRounds);
+      const int grow = last ? a.cap_draws : sac_round_draws(round + 1, CHUNK);
+      ne = min(a.cap_draws, nb + min(rem + 16, grow));
       if (round + 1 >= kSacRounds || nb >= a.cap_draws) { done = 1; exhausted = 1; }
     }
     st->iterations = iterations;
@@ -142,57 +148,52 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 }
 
 // ------------------------------------------------------------ mono chunk
-// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64).
-__global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64);
+// one hypothesis per WARP (16 warps, 4 hypotheses each): the warp solves the
+// 5-point problem cooperatively (fivept_warp.cuh), then its lanes stride over
+// all correspondences for the inlier count (ballot + popc).  The 16 warps of
+// the CTA (one CTA per SM) move through the solver phases together, so the SM
+// fetches ONE instruction stream instead of 16 unrelated ones.
+constexpr int kMonoWarps = 16;
+__global__ void __launch_bounds__(kMonoWarps * 32, 1) mono_chunk_kernel(SacArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
-  double* s1 = smem_d;                 // [N][3] query bearings
-  double* s2 = smem_d + 3 * (size_t)N; // [N][3] match bearings
-  double* smod = s2 + 3 * (size_t)N;   // [kMonoChunk][12]
-  __shared__ int s_valid[kMonoChunk];
+  geom::MonoWs* wsv = reinterpret_cast<geom::MonoWs*>(smem_raw);
+  double* s1 = reinterpret_cast<double*>(smem_raw + sizeof(geom::MonoWs) * kMonoWarps);  // [N][3]
+  double* s2 = s1 + 3 * (size_t)N;                                                          // [N][3]
+  __shared__ geom::MonoTables tables;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  geom::load_mono_tables(&tables, tid, kMonoWarps * 32);
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  for (int i = tid; i < 3 * N; i += kMonoChunk) {
+  for (int i = tid; i < 3 * N; i += kMonoWarps * 32) {
     s1[i] = ga[i];
     s2[i] = gb[i];
   }
   __syncthreads();
+  geom::MonoWs& ws = wsv[warp];
   const int nh = min(kMonoChunk, st.r_end - d0);
-  // phase 1: one hypothesis per thread
-  {
-    int ok = 0;
+#pragma unroll 1
+  for (int h0 = 0; h0 < nh; h0 += kMonoWarps) {   // CTA-uniform trip count (phase barriers inside)
+    const int hh = h0 + warp;
+    const bool live = hh < nh;
+    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? hh : h0)) * 8;
+    if (lane < 8) {
+      const int idx = smp[lane];
+      ws.f1[lane][0] = s1[3 * idx + 0]; ws.f1[lane][1] = s1[3 * idx + 1]; ws.f1[lane][2] = s1[3 * idx + 2];
+      ws.f2[lane][0] = s2[3 * idx + 0]; ws.f2[lane][1] = s2[3 * idx + 1]; ws.f2[lane][2] = s2[3 * idx + 2];
+    }
+    __syncwarp();
     double M[12];
-    if (tid < nh) {
-      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + tid) * 8;
-      V3 f1[8], f2[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int idx = smp[k];
-        f1[k].x = s1[3 * idx + 0]; f1[k].y = s1[3 * idx + 1]; f1[k].z = s1[3 * idx + 2];
-        f2[k].x = s2[3 * idx + 0]; f2[k].y = s2[3 * idx + 1]; f2[k].z = s2[3 * idx + 2];
-      }
-      ok = geom::mono_model(f1, f2, M) ? 1 : 0;
-    }
-    s_valid[tid] = ok;
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
-    }
-  }
-  __syncthreads();
-  // phase 2: inlier counts, one hypothesis per warp pass
-  for (int h = warp; h < nh; h += kMonoChunk / 32) {
+    const bool ok = geom::mono_model_warp<true>(ws, tables, lane, M) && live;
     int cnt = 0;
-    if (s_valid[h]) {
-      double M[12], tinv[3];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) M[i] = smod[12 * h + i];
+    if (ok) {
+      double tinv[3];
       geom::mono_tinv(M, tinv);
       for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + lane;
@@ -205,10 +206,11 @@ __global__ void __launch_bounds__(kMonoChunk) mono_chunk_kernel(SacArgs a) {
         cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
       }
     }
-    if (lane == 0) {
-      a.valid[(size_t)p * a.cap_draws + d0 + h] = s_valid[h];
-      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
+    if (lane == 0 && live) {
+      a.valid[(size_t)p * a.cap_draws + d0 + hh] = ok ? 1 : 0;
+      a.counts[(size_t)p * a.cap_draws + d0 + hh] = cnt;
     }
+    __syncwarp();
   }
 }
 
@@ -282,22 +284,32 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   }
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  if (tid == 0) {
-    double M[12];
-    if (MONO) {
+  if (MONO) {
+    __shared__ geom::MonoWs ws;
+    __shared__ geom::MonoTables tables;
+    geom::load_mono_tables(&tables, tid, 128);
+    __syncthreads();
+    if (tid < 32) {
       const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 8;
-      V3 f1[8], f2[8];
-      for (int k = 0; k < 8; ++k) {
-        const int idx = smp[k];
-        f1[k].x = ga[3 * idx + 0]; f1[k].y = ga[3 * idx + 1]; f1[k].z = ga[3 * idx + 2];
-        f2[k].x = gb[3 * idx + 0]; f2[k].y = gb[3 * idx + 1]; f2[k].z = gb[3 * idx + 2];
+      if (lane < 8) {
+        const int idx = smp[lane];
+        ws.f1[lane][0] = ga[3 * idx + 0]; ws.f1[lane][1] = ga[3 * idx + 1]; ws.f1[lane][2] = ga[3 * idx + 2];
+        ws.f2[lane][0] = gb[3 * idx + 0]; ws.f2[lane][1] = gb[3 * idx + 1]; ws.f2[lane][2] = gb[3 * idx + 2];
       }
-      geom::mono_model(f1, f2, M);
-    } else {
-      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 3;
-      const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
-      geom::arun3(ga + 3 * i0, ga + 3 * i1, ga + 3 * i2, gb + 3 * i0, gb + 3 * i1, gb + 3 * i2, M);
+      __syncwarp();
+      double Mw[12];
+      geom::mono_model_warp<false>(ws, tables, lane, Mw);
+      if (lane == 0)
+        for (int i = 0; i < 12; ++i) {
+          s_M[i] = Mw[i];
+          a.best_model[(size_t)p * 12 + i] = Mw[i];
+        }
     }
+  } else if (tid == 0) {
+    double M[12];
+    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 3;
+    const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
+    geom::arun3(ga + 3 * i0, ga + 3 * i1, ga + 3 * i2, gb + 3 * i0, gb + 3 * i1, gb + 3 * i2, M);
     for (int i = 0; i < 12; ++i) {
       s_M[i] = M[i];
       a.best_model[(size_t)p * 12 + i] = M[i];
@@ -447,7 +459,7 @@ __global__ void finalize_kernel(FinalizeArgs f) {
 }
 
 // --------------------------------------------------------------- launchers
-static size_t mono_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kMonoChunk); }
+static size_t mono_smem(int stride) { return sizeof(geom::MonoWs) * kMonoWarps + sizeof(double) * 6 * (size_t)stride; }
 static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
 
 template <class K>
@@ -469,18 +481,20 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem(a.stride);
   ensure_smem(mono_chunk_kernel, sm);
-  const int blocks = round == 0 ? 1 : (a.cap_draws + kMonoChunk - 1) / kMonoChunk;
-  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
-  sac_replay_kernel<8><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  const int draws = (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk);
+  const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
+  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoWarps * 32, sm, s>>>(a);
+  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
   ensure_smem(stereo_chunk_kernel, sm);
-  const int blocks = round == 0 ? 1 : (a.cap_draws + kStereoChunk - 1) / kStereoChunk;
+  const int draws = (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk);
+  const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoChunk, sm, s>>>(a);
-  sac_replay_kernel<3><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }
 void launch_mono_select(const SacArgs& a, cudaStream_t s) {

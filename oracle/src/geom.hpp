@@ -325,57 +325,57 @@ static inline int sturm_count(const Sturm* st, double x) {
   return changes;
 }
 
-static const int kRootGrid = 16;    // cells on [-1,1]
-static const int kRootDepth = 40;   // max Sturm bisection depth per cell
-static const int kRootBisect = 60;  // sign bisection steps per bracket
+static const int kRootDepth = 48;   // max Sturm bisection depth per root
+static const int kRootBisect = 10;  // sign bisection steps on the isolated bracket
+static const int kRootNewton = 8;   // bracketed Newton steps that follow
 
-// Real roots of p (degree n<=10) in (-1,1]: Sturm isolation on a 16-cell
-// grid with per-cell Sturm bisection, then 60 sign-bisection steps on p.
-// Roots are emitted in ascending order.  Returns the count (<= 10).
+// Real roots of p (degree n<=10) in (-1,1], ascending.  Root j (rank from the
+// left) is isolated on its own by bisection on the Sturm count, then refined
+// by 10 sign bisections and 8 bracket-safeguarded Newton steps on p.  Every
+// root is an independent computation (one GPU lane per root).  Returns the
+// number of roots found (<= 10); roots whose bracket shows no sign change
+// (numerically multiple roots) are dropped.
 static inline int roots_unit(const double* p, int n, double* roots) {
   Sturm st;
   sturm_build(p, n, &st);
   if (st.deg[0] < 1) return 0;
+  const int vm1 = sturm_count(&st, -1.0), vp1 = sturm_count(&st, 1.0);
+  int R = vm1 - vp1;
+  if (R > 10) R = 10;
   int nr = 0;
-  int V[kRootGrid + 1];
-  for (int i = 0; i <= kRootGrid; ++i) V[i] = sturm_count(&st, -1.0 + (double)i * (2.0 / kRootGrid));
-  for (int cell = 0; cell < kRootGrid; ++cell) {
-    // explicit stack of (lo, hi, Vlo, Vhi, depth); left half is explored first
-    double slo[kRootDepth + 2], shi[kRootDepth + 2];
-    int svlo[kRootDepth + 2], svhi[kRootDepth + 2], sd[kRootDepth + 2];
-    int sp = 0;
-    slo[0] = -1.0 + (double)cell * (2.0 / kRootGrid);
-    shi[0] = -1.0 + (double)(cell + 1) * (2.0 / kRootGrid);
-    svlo[0] = V[cell]; svhi[0] = V[cell + 1]; sd[0] = 0;
-    sp = 1;
-    while (sp > 0) {
-      --sp;
-      double lo = slo[sp], hi = shi[sp];
-      int vlo = svlo[sp], vhi = svhi[sp], d = sd[sp];
-      int r = vlo - vhi;
-      if (r <= 0) continue;
-      if (r == 1 || d >= kRootDepth) {
-        double flo = horner(st.c[0], st.deg[0], lo);
-        double fhi = horner(st.c[0], st.deg[0], hi);
-        if (fhi == 0.0) {
-          if (nr < 10) roots[nr++] = hi;
-          continue;
-        }
-        if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) continue;
-        for (int it = 0; it < kRootBisect; ++it) {
-          double mid = 0.5 * (lo + hi);
-          double fm = horner(st.c[0], st.deg[0], mid);
-          if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
-        }
-        if (nr < 10) roots[nr++] = 0.5 * (lo + hi);
-        continue;
-      }
-      double mid = 0.5 * (lo + hi);
-      int vm = sturm_count(&st, mid);
-      // push right half first so that the left half is popped first
-      slo[sp] = mid; shi[sp] = hi; svlo[sp] = vm; svhi[sp] = vhi; sd[sp] = d + 1; ++sp;
-      slo[sp] = lo; shi[sp] = mid; svlo[sp] = vlo; svhi[sp] = vm; sd[sp] = d + 1; ++sp;
+  const double* c0 = st.c[0];
+  const int d0 = st.deg[0];
+  const double* c1 = st.c[1];  // p' (unscaled)
+  const int d1 = st.deg[1];
+  for (int j = 0; j < R; ++j) {
+    double lo = -1.0, hi = 1.0;
+    int vlo = vm1, vhi = vp1, jj = j;
+    for (int depth = 0; depth < kRootDepth; ++depth) {
+      if (vlo - vhi == 1) break;
+      const double mid = 0.5 * (lo + hi);
+      const int vm = sturm_count(&st, mid);
+      const int left = vlo - vm;  // roots in (lo, mid]
+      if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
     }
+    double flo = horner(c0, d0, lo);
+    const double fhi = horner(c0, d0, hi);
+    if (fhi == 0.0) { roots[nr++] = hi; continue; }
+    if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) continue;
+    for (int it = 0; it < kRootBisect; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      const double fm = horner(c0, d0, mid);
+      if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
+    }
+    double x = 0.5 * (lo + hi);
+    for (int it = 0; it < kRootNewton; ++it) {
+      const double fx = horner(c0, d0, x);
+      const double dfx = horner(c1, d1, x);
+      if ((fx < 0.0) == (flo < 0.0)) { lo = x; flo = fx; } else { hi = x; }
+      double xn = x - fx / dfx;
+      if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
+      x = xn;
+    }
+    roots[nr++] = x;
   }
   return nr;
 }
@@ -501,7 +501,7 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
     n = roots_unit(rz, 10, r);
     for (int i = 0; i < n; ++i) {
       if (r[i] == 1.0 || r[i] == 0.0) continue;  // z=1 already covered; u=0 is z=inf
-      zr[nroots++] = 1.0 / r[i];
+      if (nroots < 10) zr[nroots++] = 1.0 / r[i];  // a degree-10 polynomial: keep the first 10
     }
   }
   int ns = 0;

@@ -679,3 +679,6 @@ int kmo_lcd_query_batch(kmo_lcd* L, int B, const uint64_t* q_robot, const uint64
 }
 
 }  // extern "C"
+
+// exposed for tests: real roots of a polynomial (ascending coefficients) in (-1,1]
+extern "C" int kmo_roots_unit(const double* p, int n, double* roots) { return roots_unit(p, n, roots); }

@@ -139,7 +139,7 @@ def run_reference(args, rank, world_size, log):
             lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
             lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
     log("oracle database ready in %.1fs" % (time.time() - t0))
-    threads = ko.num_threads()
+    threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
     sample = max(2 * threads, 16)
     batches = make_batches(world, args.steps + args.warmup, N_ROBOTS, B=sample)
     times = []
@@ -336,7 +336,7 @@ def cpu_baseline(world, robots, log):
             lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
             lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
     log("oracle database ready in %.1fs" % (time.time() - t0))
-    threads = ko.num_threads()
+    threads = len(os.sched_getaffinity(0))
     sample = max(4 * threads, 32)
     b = make_batches(world, 1, N_ROBOTS, B=sample)[0]
     lcd.query_batch(*b, threads=threads)  # warm-up

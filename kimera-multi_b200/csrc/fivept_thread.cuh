@@ -1,0 +1,381 @@
+// fivept_thread.cuh — the mono minimal solver, one RANSAC hypothesis per THREAD
+// (opengv fivept_nister + essential decomposition + 8-point disambiguation,
+// SURVEY.md A.6; /root/reference/images/kimera-multi.drawio:2589-2592, 2646).
+//
+// Why a thread and not a warp: the solver is a long chain of small dense
+// linear-algebra steps whose summation orders are fixed by the ARITHMETIC
+// CONTRACT.  Spreading one hypothesis over 32 lanes left 55 %
+// of the lanes idle and cost 25 k issued warp-instructions per hypothesis
+// (profiles/r01c); 32 independent hypotheses per warp need ~5 k.  What made the
+// very first thread-per-hypothesis build slow (5.7 KB of local memory per
+// thread thrashing L1, and an instruction footprint larger than the SM's
+// instruction cache) is handled explicitly here:
+//   * all per-hypothesis state lives in SHARED memory as S(i) = sm[i*STRIDE +
+//     thread]: consecutive threads hit consecutive 8-byte words, so any
+//     per-thread index (pivot rows, chain degrees, root counts) is
+//     bank-conflict free;  200 slots per thread, re-used phase by phase:
+//       phase 1 (null space)   A9 0..44 | Hv 45..89 | Hn 90..94 | x 95..103 | basis 104..139
+//       phase 2-3 (build, GJ)  A[10][20] 0..199
+//       phase 4+               Bz 0..44 | p1 45..52 | p2 53..60 | p3 61..67 | nz 68..78
+//                              Sturm chain (triangular) 80..145 | roots 146..155 | basis 156..191
+//       phase 7-8              sampled bearings 80..127 | best model 128..139
+//   * the 10x20 constraint build is generated straight-line code
+//     (fivept_build.inc) with the 36 null-space coefficients in registers;
+//   * division, sqrt, Horner, SVD are not inlined, and the CTA's warps pass
+//     phase barriers, so the SM fetches one compact instruction stream.
+#pragma once
+#include "geom.cuh"
+
+namespace kml {
+namespace geom {
+
+constexpr int kTphSlots = 200;
+constexpr int kTRootDepth = 48;
+constexpr int kTRootBisect = 10;
+constexpr int kTRootNewton = 8;
+
+// Horner on a strided shared-memory polynomial (ascending coefficients)
+template <int STRIDE>
+__device__ __noinline__ double horner_s(const double* c, int deg, double x) {
+  double r = c[deg * STRIDE];
+  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i * STRIDE];
+  return r;
+}
+// coefficient k of a*b, strided operands
+template <int STRIDE>
+__device__ __noinline__ double conv_s(const double* a, int da, const double* b, int db, int k) {
+  double r = 0.0;
+  const int i0 = max(0, k - db), i1 = min(da, k);
+  for (int i = i0; i <= i1; ++i) r = r + a[i * STRIDE] * b[(k - i) * STRIDE];
+  return r;
+}
+__device__ __forceinline__ int tri_off(int k) { return 80 + 11 * k - (k * (k - 1)) / 2; }
+
+// Sturm chain of the polynomial at `p` (degree <= 10, strided) into the
+// triangular chain area; degrees packed 4 bits each in `degs`; returns length.
+template <int STRIDE>
+__device__ __noinline__ int sturm_build_s(double* sm, const double* p, bool reversed, unsigned long long* degs_out) {
+#define SS(i) sm[(i) * STRIDE]
+  int n = 10;
+  while (n > 0 && p[(reversed ? 10 - n : n) * STRIDE] == 0.0) --n;
+  for (int i = 0; i <= n; ++i) SS(tri_off(0) + i) = p[(reversed ? 10 - i : i) * STRIDE];
+  unsigned long long degs = (unsigned long long)n;
+  int len = 1;
+  if (n >= 1) {
+    for (int i = 0; i < n; ++i) SS(tri_off(1) + i) = (double)(i + 1) * p[(reversed ? 10 - (i + 1) : (i + 1)) * STRIDE];
+    degs |= (unsigned long long)(n - 1) << 4;
+    len = 2;
+    while (len < 12) {
+      const int db = (int)((degs >> (4 * (len - 1))) & 15u);
+      if (db <= 0) break;
+      const int da = (int)((degs >> (4 * (len - 2))) & 15u);
+      const int oa = tri_off(len - 2), ob = tri_off(len - 1), oc = tri_off(len);
+      // remainder r[0..da] in scratch slots 0..10 (the B(z) area is dead by now)
+      for (int i = 0; i <= da; ++i) SS(i) = SS(oa + i);
+      for (int d = da; d >= db; --d) {
+        const double f = kdiv(SS(d), SS(ob + db));
+        for (int i = 0; i < db; ++i) SS(d - db + i) = SS(d - db + i) - f * SS(ob + i);
+        SS(d) = 0.0;
+      }
+      int dr = db - 1;
+      while (dr >= 0 && SS(dr) == 0.0) --dr;
+      if (dr < 0) break;  // exact gcd reached
+      const double sc = fabs(SS(dr));
+      for (int i = 0; i <= dr; ++i) SS(oc + i) = -kdiv(SS(i), sc);
+      degs |= (unsigned long long)dr << (4 * len);
+      ++len;
+    }
+  }
+  *degs_out = degs;
+  return len;
+#undef SS
+}
+
+template <int STRIDE>
+__device__ __noinline__ int sturm_count_s(const double* sm, unsigned long long degs, int len, double x) {
+  int changes = 0, last = 0;
+  for (int k = 0; k < len; ++k) {
+    const double v = horner_s<STRIDE>(sm + tri_off(k) * STRIDE, (int)((degs >> (4 * k)) & 15u), x);
+    const int s = (v > 0.0) - (v < 0.0);
+    if (s != 0) {
+      if (last != 0 && s != last) ++changes;
+      last = s;
+    }
+  }
+  return changes;
+}
+
+// Real roots in (-1,1] of the chain's first polynomial, ascending, appended to
+// roots[] (strided) starting at *nroots (cap 10 in total).  `invert`: the
+// chain is the reversed polynomial, emit z = 1/u and drop u = 1 and u = 0.
+template <int STRIDE>
+__device__ __noinline__ void roots_unit_s(double* sm, unsigned long long degs, int len, bool invert, int* nroots) {
+#define SS(i) sm[(i) * STRIDE]
+  const int d0 = (int)(degs & 15u);
+  if (d0 < 1) return;
+  const int d1 = (int)((degs >> 4) & 15u);
+  const double* c0 = sm + tri_off(0) * STRIDE;
+  const double* c1 = sm + tri_off(1) * STRIDE;
+  const int vm1 = sturm_count_s<STRIDE>(sm, degs, len, -1.0), vp1 = sturm_count_s<STRIDE>(sm, degs, len, 1.0);
+  int R = vm1 - vp1;
+  if (R > 10) R = 10;
+  for (int j = 0; j < R; ++j) {
+    double lo = -1.0, hi = 1.0;
+    int vlo = vm1, vhi = vp1, jj = j;
+    for (int depth = 0; depth < kTRootDepth; ++depth) {
+      if (vlo - vhi == 1) break;
+      const double mid = 0.5 * (lo + hi);
+      const int vm = sturm_count_s<STRIDE>(sm, degs, len, mid);
+      const int left = vlo - vm;
+      if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+    }
+    double flo = horner_s<STRIDE>(c0, d0, lo);
+    const double fhi = horner_s<STRIDE>(c0, d0, hi);
+    double root;
+    if (fhi == 0.0) {
+      root = hi;
+    } else {
+      if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) continue;
+      for (int it = 0; it < kTRootBisect; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        const double fm = horner_s<STRIDE>(c0, d0, mid);
+        if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
+      }
+      double x = 0.5 * (lo + hi);
+      for (int it = 0; it < kTRootNewton; ++it) {
+        const double fx = horner_s<STRIDE>(c0, d0, x);
+        const double dfx = horner_s<STRIDE>(c1, d1, x);
+        if ((fx < 0.0) == (flo < 0.0)) { lo = x; flo = fx; } else { hi = x; }
+        double xn = x - kdiv(fx, dfx);
+        if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
+        x = xn;
+      }
+      root = x;
+    }
+    if (invert) {
+      if (root == 1.0 || root == 0.0) continue;
+      root = kdiv(1.0, root);
+    }
+    if (*nroots < 10) {
+      SS(146 + *nroots) = root;
+      ++*nroots;
+    }
+  }
+#undef SS
+}
+
+// sm: this thread's slot 0 (slot i at sm[i*STRIDE]).  ga/gb: the problem's
+// correspondences (query / match bearings, [N][3]); smp: the 8 sample indices.
+// Returns whether a model exists; on success the model [R12|t12] is in slots
+// 128..139.  `alive` = false makes the thread a passenger (barriers only).
+template <int STRIDE, bool SYNC>
+__device__ bool mono_model_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
+                                  const uint16_t* __restrict__ smp, bool alive) {
+#define S(i) sm[(i) * STRIDE]
+#define KML_PHASE() do { if (SYNC) __syncthreads(); } while (0)
+  bool failed = !alive;
+  int sidx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sidx[k] = alive ? (int)smp[k] : 0;
+  // ------------------------------------------------ phase 1: null space
+  // A9[i][j] = Q[j][i] = f_m[j][i%3] * f_q[j][i/3]   (slots 0..44, [i*5+j])
+#pragma unroll 1
+  for (int j = 0; j < 5; ++j) {
+    const double* fq = ga + 3 * sidx[j];
+    const double* fm = gb + 3 * sidx[j];
+    const double q0 = fq[0], q1 = fq[1], q2 = fq[2], m0 = fm[0], m1 = fm[1], m2 = fm[2];
+    S(0 * 5 + j) = m0 * q0; S(1 * 5 + j) = m1 * q0; S(2 * 5 + j) = m2 * q0;
+    S(3 * 5 + j) = m0 * q1; S(4 * 5 + j) = m1 * q1; S(5 * 5 + j) = m2 * q1;
+    S(6 * 5 + j) = m0 * q2; S(7 * 5 + j) = m1 * q2; S(8 * 5 + j) = m2 * q2;
+  }
+#pragma unroll 1
+  for (int k = 0; k < 5; ++k) {
+    double s2 = 0.0;
+    for (int i = k; i < 9; ++i) s2 = s2 + S(i * 5 + k) * S(i * 5 + k);
+    const double nrm = ksqrt(s2);
+    const double alpha = (S(k * 5 + k) >= 0.0) ? -nrm : nrm;
+    for (int i = 0; i < 9; ++i) S(45 + k * 9 + i) = (i < k) ? 0.0 : S(i * 5 + k);
+    S(45 + k * 9 + k) = S(45 + k * 9 + k) - alpha;
+    double n2 = 0.0;
+    for (int i = k; i < 9; ++i) n2 = n2 + S(45 + k * 9 + i) * S(45 + k * 9 + i);
+    S(90 + k) = n2;
+    if (n2 > 0.0) {
+      for (int j = k; j < 5; ++j) {
+        double d = 0.0;
+        for (int i = k; i < 9; ++i) d = d + S(45 + k * 9 + i) * S(i * 5 + j);
+        const double f = kdiv(2.0 * d, n2);
+        for (int i = k; i < 9; ++i) S(i * 5 + j) = S(i * 5 + j) - f * S(45 + k * 9 + i);
+      }
+    }
+  }
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {
+    for (int i = 0; i < 9; ++i) S(95 + i) = (i == 5 + b) ? 1.0 : 0.0;
+    for (int k = 4; k >= 0; --k) {
+      const double n2 = S(90 + k);
+      if (!(n2 > 0.0)) continue;
+      double d = 0.0;
+      for (int i = k; i < 9; ++i) d = d + S(45 + k * 9 + i) * S(95 + i);
+      const double f = kdiv(2.0 * d, n2);
+      for (int i = k; i < 9; ++i) S(95 + i) = S(95 + i) - f * S(45 + k * 9 + i);
+    }
+    for (int i = 0; i < 9; ++i) S(104 + b * 9 + i) = S(95 + i);
+  }
+  KML_PHASE();
+  // ------------------------------------- phase 2: constraint matrix 10x20
+  {
+    double B[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) B[i] = S(104 + i);
+#define SA(i) S(i)
+#include "fivept_build.inc"
+#undef SA
+    KML_PHASE();
+    // ----------------------------------------------- phase 3: Gauss-Jordan
+    // (columns < c of every row are exact zeros / unit entries that are never
+    // read again, so the row operations start at column c: same used values)
+#pragma unroll 1
+    for (int c = 0; c < 10; ++c) {
+      int pr = c;
+      double pv = fabs(S(c * 20 + c));
+      for (int r = c + 1; r < 10; ++r) {
+        const double v = fabs(S(r * 20 + c));
+        if (v > pv) { pv = v; pr = r; }
+      }
+      if (!(pv > 0.0)) failed = true;
+      if (pr != c)
+        for (int j = c; j < 20; ++j) {
+          const double t = S(c * 20 + j);
+          S(c * 20 + j) = S(pr * 20 + j);
+          S(pr * 20 + j) = t;
+        }
+      const double piv = S(c * 20 + c);
+      for (int j = c; j < 20; ++j) S(c * 20 + j) = kdiv(S(c * 20 + j), piv);
+      for (int r = 0; r < 10; ++r) {
+        if (r == c) continue;
+        const double f = S(r * 20 + c);
+        for (int j = c; j < 20; ++j) S(r * 20 + j) = S(r * 20 + j) - f * S(c * 20 + j);
+      }
+    }
+    KML_PHASE();
+    // --------------------------------- phase 4: B(z), cofactors, n(z); stash basis
+    // Bz[r][col][m] -> slot r*15 + col*5 + m (rows 0..3 of A are dead)
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      const int e = (4 + 2 * r) * 20, f = (5 + 2 * r) * 20;
+      for (int col = 0; col < 2; ++col) {
+        const int ob = 10 + 3 * col, o = r * 15 + col * 5;
+        S(o + 0) = S(e + ob + 2);
+        S(o + 1) = S(e + ob + 1) - S(f + ob + 2);
+        S(o + 2) = S(e + ob + 0) - S(f + ob + 1);
+        S(o + 3) = -S(f + ob + 0);
+        S(o + 4) = 0.0;
+      }
+      const int o = r * 15 + 10;
+      S(o + 0) = S(e + 19);
+      S(o + 1) = S(e + 18) - S(f + 19);
+      S(o + 2) = S(e + 17) - S(f + 18);
+      S(o + 3) = S(e + 16) - S(f + 17);
+      S(o + 4) = -S(f + 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 36; ++i) S(156 + i) = B[i];  // A rows 7..9 are consumed: keep the basis for phase 7
+  }
+  {
+    const double* b00 = sm + 0 * STRIDE, *b01 = sm + 5 * STRIDE, *b02 = sm + 10 * STRIDE;
+    const double* b10 = sm + 15 * STRIDE, *b11 = sm + 20 * STRIDE, *b12 = sm + 25 * STRIDE;
+    const double* b20 = sm + 30 * STRIDE, *b21 = sm + 35 * STRIDE, *b22 = sm + 40 * STRIDE;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) S(45 + k) = conv_s<STRIDE>(b01, 3, b12, 4, k) - conv_s<STRIDE>(b02, 4, b11, 3, k);
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) S(53 + k) = conv_s<STRIDE>(b02, 4, b10, 3, k) - conv_s<STRIDE>(b00, 3, b12, 4, k);
+#pragma unroll 1
+    for (int k = 0; k < 7; ++k) S(61 + k) = conv_s<STRIDE>(b00, 3, b11, 3, k) - conv_s<STRIDE>(b01, 3, b10, 3, k);
+#pragma unroll 1
+    for (int k = 0; k < 11; ++k)
+      S(68 + k) = (conv_s<STRIDE>(sm + 45 * STRIDE, 7, b20, 3, k) + conv_s<STRIDE>(sm + 53 * STRIDE, 7, b21, 3, k)) +
+                  conv_s<STRIDE>(sm + 61 * STRIDE, 6, b22, 4, k);
+  }
+  KML_PHASE();
+  // ---------------------- phases 5-6: Sturm chains and roots (n(z), then reversed n)
+  int nroots = 0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    unsigned long long degs;
+    const int len = sturm_build_s<STRIDE>(sm, sm + 68 * STRIDE, h == 1, &degs);
+    roots_unit_s<STRIDE>(sm, degs, len, h == 1, &nroots);
+  }
+  KML_PHASE();
+  // -------- phases 7-8: per root E, SVD, four (R,t) candidates scored on the 8 sample points
+  // sampled bearings -> slots 80..127 ([k*6 + c], c<3 query, c>=3 match); the chain area is dead
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const double* fq = ga + 3 * sidx[k];
+    const double* fm = gb + 3 * sidx[k];
+    S(80 + 6 * k + 0) = fq[0]; S(80 + 6 * k + 1) = fq[1]; S(80 + 6 * k + 2) = fq[2];
+    S(80 + 6 * k + 3) = fm[0]; S(80 + 6 * k + 4) = fm[1]; S(80 + 6 * k + 5) = fm[2];
+  }
+  double best = 1000000.0;
+  bool found = false;
+#pragma unroll 1
+  for (int rt = 0; rt < nroots; ++rt) {
+    const double z = S(146 + rt);
+    const double d = horner_s<STRIDE>(sm + 61 * STRIDE, 6, z);
+    const double x = kdiv(horner_s<STRIDE>(sm + 45 * STRIDE, 7, z), d);
+    const double y = kdiv(horner_s<STRIDE>(sm + 53 * STRIDE, 7, z), d);
+    double E[9];
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const double v = ((x * S(156 + e) + y * S(156 + 9 + e)) + z * S(156 + 18 + e)) + S(156 + 27 + e);
+      if (!isfinite(v)) ok = false;
+      E[e] = v;
+    }
+    if (!ok) continue;
+    double U[9], Sv[3], V[9];
+    svd3(E, U, Sv, V);
+    double Ra[9], Rb[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double a0 = U[3 * r + 0], a1 = U[3 * r + 1], a2 = U[3 * r + 2];
+        const double b0 = V[3 * c + 0], b1 = V[3 * c + 1], b2 = V[3 * c + 2];
+        Ra[3 * r + c] = (a1 * b0 - a0 * b1) + a2 * b2;
+        Rb[3 * r + c] = (a0 * b1 - a1 * b0) + a2 * b2;
+      }
+    const double tt[3] = {Sv[0] * U[2], Sv[0] * U[5], Sv[0] * U[8]};
+#pragma unroll 1
+    for (int cand = 0; cand < 4; ++cand) {
+      const double sgn = (cand & 1) ? -1.0 : 1.0;
+      double M[12], tinv[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        M[4 * r + 0] = (cand < 2) ? Ra[3 * r + 0] : Rb[3 * r + 0];
+        M[4 * r + 1] = (cand < 2) ? Ra[3 * r + 1] : Rb[3 * r + 1];
+        M[4 * r + 2] = (cand < 2) ? Ra[3 * r + 2] : Rb[3 * r + 2];
+        M[4 * r + 3] = sgn * tt[r];
+      }
+      mono_tinv(M, tinv);
+      double q = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {
+        const V3 f1 = {S(80 + 6 * k + 0), S(80 + 6 * k + 1), S(80 + 6 * k + 2)};
+        const V3 f2 = {S(80 + 6 * k + 3), S(80 + 6 * k + 4), S(80 + 6 * k + 5)};
+        q = q + mono_residual(M, tinv, f1, f2);
+      }
+      if (q < best) {
+        best = q;
+        found = true;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) S(128 + i) = M[i];
+      }
+    }
+  }
+  return found && !failed;
+#undef KML_PHASE
+#undef S
+}
+
+}  // namespace geom
+}  // namespace kml

@@ -25,7 +25,7 @@
 
 #include "common.cuh"
 #include "geom.cuh"
-#include "fivept_warp.cuh"
+#include "fivept_thread.cuh"
 #include "kernels.h"
 
 namespace kml {
@@ -148,69 +148,53 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 }
 
 // ------------------------------------------------------------ mono chunk
-// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64);
-// one hypothesis per WARP (16 warps, 4 hypotheses each): the warp solves the
-// 5-point problem cooperatively (fivept_warp.cuh), then its lanes stride over
-// all correspondences for the inlier count (ballot + popc).  The 16 warps of
-// the CTA (one CTA per SM) move through the solver phases together, so the SM
-// fetches ONE instruction stream instead of 16 unrelated ones.
-constexpr int kMonoWarps = 16;
-__global__ void __launch_bounds__(kMonoWarps * 32, 1) mono_chunk_kernel(SacArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64).
+// Phase A: one hypothesis per THREAD (fivept_thread.cuh), all solver state in
+// shared memory as [slot][thread] (bank-conflict free for any per-thread
+// index), the CTA's two warps passing phase barriers so they share one
+// instruction stream.  Phase B: one hypothesis per warp pass — the lanes
+// stride over all correspondences, inlier count by ballot + popc.
+__global__ void __launch_bounds__(kMonoChunk, 2) mono_chunk_kernel(SacArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
-  geom::MonoWs* wsv = reinterpret_cast<geom::MonoWs*>(smem_raw);
-  double* s1 = reinterpret_cast<double*>(smem_raw + sizeof(geom::MonoWs) * kMonoWarps);  // [N][3]
-  double* s2 = s1 + 3 * (size_t)N;                                                          // [N][3]
-  __shared__ geom::MonoTables tables;
+  __shared__ int s_valid[kMonoChunk];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  geom::load_mono_tables(&tables, tid, kMonoWarps * 32);
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  for (int i = tid; i < 3 * N; i += kMonoWarps * 32) {
-    s1[i] = ga[i];
-    s2[i] = gb[i];
-  }
-  __syncthreads();
-  geom::MonoWs& ws = wsv[warp];
   const int nh = min(kMonoChunk, st.r_end - d0);
-#pragma unroll 1
-  for (int h0 = 0; h0 < nh; h0 += kMonoWarps) {   // CTA-uniform trip count (phase barriers inside)
-    const int hh = h0 + warp;
-    const bool live = hh < nh;
-    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? hh : h0)) * 8;
-    if (lane < 8) {
-      const int idx = smp[lane];
-      ws.f1[lane][0] = s1[3 * idx + 0]; ws.f1[lane][1] = s1[3 * idx + 1]; ws.f1[lane][2] = s1[3 * idx + 2];
-      ws.f2[lane][0] = s2[3 * idx + 0]; ws.f2[lane][1] = s2[3 * idx + 1]; ws.f2[lane][2] = s2[3 * idx + 2];
-    }
-    __syncwarp();
-    double M[12];
-    const bool ok = geom::mono_model_warp<true>(ws, tables, lane, M) && live;
+  const bool live = tid < nh;
+  const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? tid : 0)) * 8;
+  const bool ok = geom::mono_model_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live);
+  s_valid[tid] = ok ? 1 : 0;
+  __syncthreads();
+  for (int h = warp; h < nh; h += kMonoChunk / 32) {
     int cnt = 0;
-    if (ok) {
-      double tinv[3];
+    const int v = s_valid[h];
+    if (v) {
+      double M[12], tinv[3];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) M[i] = smem_d[(128 + i) * kMonoChunk + h];
       geom::mono_tinv(M, tinv);
       for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + lane;
         bool in = false;
         if (i < N) {
-          const V3 f1 = {s1[3 * i], s1[3 * i + 1], s1[3 * i + 2]};
-          const V3 f2 = {s2[3 * i], s2[3 * i + 1], s2[3 * i + 2]};
+          const V3 f1 = {ga[3 * i], ga[3 * i + 1], ga[3 * i + 2]};
+          const V3 f2 = {gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]};
           in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
         }
         cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
       }
     }
-    if (lane == 0 && live) {
-      a.valid[(size_t)p * a.cap_draws + d0 + hh] = ok ? 1 : 0;
-      a.counts[(size_t)p * a.cap_draws + d0 + hh] = cnt;
+    if (lane == 0) {
+      a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
+      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
-    __syncwarp();
   }
 }
 
@@ -285,25 +269,14 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
   if (MONO) {
-    __shared__ geom::MonoWs ws;
-    __shared__ geom::MonoTables tables;
-    geom::load_mono_tables(&tables, tid, 128);
-    __syncthreads();
-    if (tid < 32) {
+    __shared__ double s_ws[geom::kTphSlots];
+    if (tid == 0) {
       const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 8;
-      if (lane < 8) {
-        const int idx = smp[lane];
-        ws.f1[lane][0] = ga[3 * idx + 0]; ws.f1[lane][1] = ga[3 * idx + 1]; ws.f1[lane][2] = ga[3 * idx + 2];
-        ws.f2[lane][0] = gb[3 * idx + 0]; ws.f2[lane][1] = gb[3 * idx + 1]; ws.f2[lane][2] = gb[3 * idx + 2];
+      geom::mono_model_thread<1, false>(s_ws, ga, gb, smp, true);
+      for (int i = 0; i < 12; ++i) {
+        s_M[i] = s_ws[128 + i];
+        a.best_model[(size_t)p * 12 + i] = s_ws[128 + i];
       }
-      __syncwarp();
-      double Mw[12];
-      geom::mono_model_warp<false>(ws, tables, lane, Mw);
-      if (lane == 0)
-        for (int i = 0; i < 12; ++i) {
-          s_M[i] = Mw[i];
-          a.best_model[(size_t)p * 12 + i] = Mw[i];
-        }
     }
   } else if (tid == 0) {
     double M[12];
@@ -459,7 +432,7 @@ __global__ void finalize_kernel(FinalizeArgs f) {
 }
 
 // --------------------------------------------------------------- launchers
-static size_t mono_smem(int stride) { return sizeof(geom::MonoWs) * kMonoWarps + sizeof(double) * 6 * (size_t)stride; }
+static size_t mono_smem(int) { return sizeof(double) * geom::kTphSlots * kMonoChunk; }
 static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
 
 template <class K>
@@ -483,7 +456,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   ensure_smem(mono_chunk_kernel, sm);
   const int draws = (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk);
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
-  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoWarps * 32, sm, s>>>(a);
+  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }

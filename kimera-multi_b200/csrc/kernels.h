@@ -74,6 +74,7 @@ struct SacArgs {
   int raw_len;
   uint16_t* perm;        // [P][stride] persistent shuffle state
   int cap_draws;         // draws available per problem (raw_len / S)
+  double* models;        // [P][kRoundCap][12] models of the draws of the current round
   uint16_t* samples;     // [P][cap_draws][S]
   int32_t* valid;        // [P][cap_draws]
   int32_t* counts;       // [P][cap_draws]
@@ -92,6 +93,7 @@ struct SacArgs {
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
 constexpr int kStereoChunk = 128;  // hypotheses per CTA (stereo) and size of round 0
 constexpr int kSacRounds = 6;      // 64,64,128,256,512 new draws, then everything that is left
+constexpr int kRoundCap = 512;     // most new draws any round evaluates per problem
 // upper bound of NEW draws evaluated per problem in round r (doubling schedule)
 __host__ __device__ inline int sac_round_draws(int round, int chunk) {
   return round == 0 ? chunk : chunk << (round - 1);

@@ -359,9 +359,15 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     ensure_ktable(h, stride, 3, prm.ransac_probability, &h->d_ktable_stereo, &h->ktable_n_stereo);
   const int raw_len = (int)h->raw_h.size();
   const int cap_draws = std::min(raw_len / S, max_it + 1 + 256);
-  (void)chunk;
+  {  // the doubling round schedule must cover cap_draws with at most kRoundCap new draws per round
+    int cum = 0;
+    for (int r = 0; r + 1 < kSacRounds; ++r) cum += std::min(sac_round_draws(r, chunk), kRoundCap);
+    if (cap_draws - cum > kRoundCap)
+      throw std::runtime_error("max_ransac_iterations too large for the RANSAC round schedule (limit 1279)");
+  }
   h->d_perm.scratch((size_t)P * stride);
   h->d_samples.scratch((size_t)P * cap_draws * S);
+  h->d_models.scratch((size_t)P * kRoundCap * 12);
   h->d_valid.scratch((size_t)P * cap_draws);
   h->d_counts.scratch((size_t)P * cap_draws);
   out.st->scratch(P);
@@ -371,7 +377,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   SacArgs a;
   a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
   a.raw = h->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
-  a.perm = h->d_perm.p; a.samples = h->d_samples.p;
+  a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
   a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
   a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     const int r_begin = st->r_begin, r_end = st->r_end;
     const int32_t* valid = a.valid + (size_t)p * a.cap_draws;
     const int32_t* counts = a.counts + (size_t)p * a.cap_draws;
+    int best_slot = -1;
     for (int gd = r_begin; gd < r_end; ++gd) {
       if (!((a.full || (double)iterations < k) && skipped < max_skip)) { done = 1; break; }
       ++draws;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
       if (n > best) {
         best = n;
         best_draw = gd;
+        best_slot = gd - r_begin;
         k = a.ktable[(size_t)N * a.ktable_n + n];
       }
       ++iterations;
@@ -127,8 +129,12 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
       // covers everything that can still be needed plus the skip reserve.
       const bool last = (round + 2 >= kSacRounds);
       const int grow = last ? a.cap_draws : sac_round_draws(round + 1, CHUNK);
-      ne = min(a.cap_draws, nb + min(rem + 16, grow));
+      ne = min(a.cap_draws, nb + min(min(rem + 16, grow), kRoundCap));
       if (round + 1 >= kSacRounds || nb >= a.cap_draws) { done = 1; exhausted = 1; }
+    }
+    if (best_slot >= 0) {  // model_coefficients_ = model
+      const double* m = a.models + ((size_t)p * kRoundCap + best_slot) * 12;
+      for (int i = 0; i < 12; ++i) a.best_model[(size_t)p * 12 + i] = m[i];
     }
     st->iterations = iterations;
     st->skipped = skipped;
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_chunk_kernel(SacArgs a) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
+    if (v && lane < 12)
+      a.models[((size_t)p * kRoundCap + blockIdx.y * kMonoChunk + h) * 12 + lane] = smem_d[(128 + lane) * kMonoChunk + h];
   }
 }
 
@@ -245,12 +253,12 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = 1;  // threept_arun always yields a model
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
+    if (lane < 12) a.models[((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + h) * 12 + lane] = smod[12 * h + lane];
   }
 }
 
 // ------------------------------------------------ selectWithinDistance
-// Recomputes the winning hypothesis from its sample (same arithmetic, same
-// bits as when it was scored) and emits model_coefficients_ + inliers_.
+// selectWithinDistance(model_coefficients_, threshold, inliers_) for the winner.
 template <bool MONO>
 __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   const int p = blockIdx.x;
@@ -268,26 +276,7 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   }
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  if (MONO) {
-    __shared__ double s_ws[geom::kTphSlots];
-    if (tid == 0) {
-      const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 8;
-      geom::mono_model_thread<1, false>(s_ws, ga, gb, smp, true);
-      for (int i = 0; i < 12; ++i) {
-        s_M[i] = s_ws[128 + i];
-        a.best_model[(size_t)p * 12 + i] = s_ws[128 + i];
-      }
-    }
-  } else if (tid == 0) {
-    double M[12];
-    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + st.best_draw) * 3;
-    const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
-    geom::arun3(ga + 3 * i0, ga + 3 * i1, ga + 3 * i2, gb + 3 * i0, gb + 3 * i1, gb + 3 * i2, M);
-    for (int i = 0; i < 12; ++i) {
-      s_M[i] = M[i];
-      a.best_model[(size_t)p * 12 + i] = M[i];
-    }
-  }
+  if (tid < 12) s_M[tid] = a.best_model[(size_t)p * 12 + tid];  // copied by the replay kernel
   __syncthreads();
   double M[12], tinv[3];
 #pragma unroll
@@ -454,7 +443,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem(a.stride);
   ensure_smem(mono_chunk_kernel, sm);
-  const int draws = (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk);
+  const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   mono_chunk_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
@@ -464,7 +453,7 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
   ensure_smem(stereo_chunk_kernel, sm);
-  const int draws = (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk);
+  const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoChunk, sm, s>>>(a);
   sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);

@@ -30,6 +30,7 @@ namespace kml {
 namespace geom {
 
 constexpr int kTphSlots = 200;
+constexpr int kTRootGrid = 32;
 constexpr int kTRootDepth = 48;
 constexpr int kTRootBisect = 10;
 constexpr int kTRootNewton = 8;
@@ -119,15 +120,38 @@ __device__ __noinline__ void roots_unit_s(double* sm, unsigned long long degs, i
   const int vm1 = sturm_count_s<STRIDE>(sm, degs, len, -1.0), vp1 = sturm_count_s<STRIDE>(sm, degs, len, 1.0);
   int R = vm1 - vp1;
   if (R > 10) R = 10;
+  // grid pass: 32 sign-test cells (x_{i-1}, x_i], x_i = -1 + i/16; if the number of bracketing
+  // cells equals the Sturm count they are the isolating brackets, else bisect on the count
+  unsigned cells = 0u;
+  int nb = 0;
+  if (R > 0) {
+    double fprev = horner_s<STRIDE>(c0, d0, -1.0);
+    for (int i = 1; i <= kTRootGrid; ++i) {
+      const double fi = horner_s<STRIDE>(c0, d0, -1.0 + (double)i * (2.0 / kTRootGrid));
+      if ((fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0) {
+        cells |= 1u << (i - 1);
+        ++nb;
+      }
+      fprev = fi;
+    }
+  }
+  const bool grid_ok = (nb == R);
+  int cell = -1;
   for (int j = 0; j < R; ++j) {
     double lo = -1.0, hi = 1.0;
-    int vlo = vm1, vhi = vp1, jj = j;
-    for (int depth = 0; depth < kTRootDepth; ++depth) {
-      if (vlo - vhi == 1) break;
-      const double mid = 0.5 * (lo + hi);
-      const int vm = sturm_count_s<STRIDE>(sm, degs, len, mid);
-      const int left = vlo - vm;
-      if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+    if (grid_ok) {
+      do { ++cell; } while (!((cells >> cell) & 1u));
+      lo = -1.0 + (double)cell * (2.0 / kTRootGrid);
+      hi = -1.0 + (double)(cell + 1) * (2.0 / kTRootGrid);
+    } else {
+      int vlo = vm1, vhi = vp1, jj = j;
+      for (int depth = 0; depth < kTRootDepth; ++depth) {
+        if (vlo - vhi == 1) break;
+        const double mid = 0.5 * (lo + hi);
+        const int vm = sturm_count_s<STRIDE>(sm, degs, len, mid);
+        const int left = vlo - vm;
+        if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+      }
     }
     double flo = horner_s<STRIDE>(c0, d0, lo);
     const double fhi = horner_s<STRIDE>(c0, d0, hi);
@@ -166,11 +190,12 @@ __device__ __noinline__ void roots_unit_s(double* sm, unsigned long long degs, i
 
 // sm: this thread's slot 0 (slot i at sm[i*STRIDE]).  ga/gb: the problem's
 // correspondences (query / match bearings, [N][3]); smp: the 8 sample indices.
-// Returns whether a model exists; on success the model [R12|t12] is in slots
-// 128..139.  `alive` = false makes the thread a passenger (barriers only).
+// Returns the number of essential matrices (<= 10) written to Eout[10][9]
+// (row-major, f_q^T E f_m = 0).  `alive` = false makes the thread a passenger
+// (barriers only, returns 0).
 template <int STRIDE, bool SYNC>
-__device__ bool mono_model_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
-                                  const uint16_t* __restrict__ smp, bool alive) {
+__device__ int mono_front_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
+                                 const uint16_t* __restrict__ smp, bool alive, double* __restrict__ Eout) {
 #define S(i) sm[(i) * STRIDE]
 #define KML_PHASE() do { if (SYNC) __syncthreads(); } while (0)
   bool failed = !alive;
@@ -306,17 +331,8 @@ __device__ bool mono_model_thread(double* sm, const double* __restrict__ ga, con
     roots_unit_s<STRIDE>(sm, degs, len, h == 1, &nroots);
   }
   KML_PHASE();
-  // -------- phases 7-8: per root E, SVD, four (R,t) candidates scored on the 8 sample points
-  // sampled bearings -> slots 80..127 ([k*6 + c], c<3 query, c>=3 match); the chain area is dead
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const double* fq = ga + 3 * sidx[k];
-    const double* fm = gb + 3 * sidx[k];
-    S(80 + 6 * k + 0) = fq[0]; S(80 + 6 * k + 1) = fq[1]; S(80 + 6 * k + 2) = fq[2];
-    S(80 + 6 * k + 3) = fm[0]; S(80 + 6 * k + 4) = fm[1]; S(80 + 6 * k + 5) = fm[2];
-  }
-  double best = 1000000.0;
-  bool found = false;
+  // ------------------------------ phase 7a: one essential matrix per finite root
+  int ns = 0;
 #pragma unroll 1
   for (int rt = 0; rt < nroots; ++rt) {
     const double z = S(146 + rt);
@@ -332,49 +348,68 @@ __device__ bool mono_model_thread(double* sm, const double* __restrict__ ga, con
       E[e] = v;
     }
     if (!ok) continue;
-    double U[9], Sv[3], V[9];
-    svd3(E, U, Sv, V);
-    double Ra[9], Rb[9];
+    if (!failed) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double a0 = U[3 * r + 0], a1 = U[3 * r + 1], a2 = U[3 * r + 2];
-        const double b0 = V[3 * c + 0], b1 = V[3 * c + 1], b2 = V[3 * c + 2];
-        Ra[3 * r + c] = (a1 * b0 - a0 * b1) + a2 * b2;
-        Rb[3 * r + c] = (a0 * b1 - a1 * b0) + a2 * b2;
-      }
-    const double tt[3] = {Sv[0] * U[2], Sv[0] * U[5], Sv[0] * U[8]};
-#pragma unroll 1
-    for (int cand = 0; cand < 4; ++cand) {
-      const double sgn = (cand & 1) ? -1.0 : 1.0;
-      double M[12], tinv[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        M[4 * r + 0] = (cand < 2) ? Ra[3 * r + 0] : Rb[3 * r + 0];
-        M[4 * r + 1] = (cand < 2) ? Ra[3 * r + 1] : Rb[3 * r + 1];
-        M[4 * r + 2] = (cand < 2) ? Ra[3 * r + 2] : Rb[3 * r + 2];
-        M[4 * r + 3] = sgn * tt[r];
-      }
-      mono_tinv(M, tinv);
-      double q = 0.0;
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        const V3 f1 = {S(80 + 6 * k + 0), S(80 + 6 * k + 1), S(80 + 6 * k + 2)};
-        const V3 f2 = {S(80 + 6 * k + 3), S(80 + 6 * k + 4), S(80 + 6 * k + 5)};
-        q = q + mono_residual(M, tinv, f1, f2);
-      }
-      if (q < best) {
-        best = q;
-        found = true;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) S(128 + i) = M[i];
-      }
+      for (int e = 0; e < 9; ++e) Eout[9 * ns + e] = E[e];
     }
+    ++ns;
   }
-  return found && !failed;
+  return failed ? 0 : ns;
 #undef KML_PHASE
 #undef S
+}
+
+// Decomposition of one essential matrix: Ra = U W V^T, Rb = U W^T V^T, t = s0 u2.
+__device__ __forceinline__ void essential_candidates(const double* E, double* Ra, double* Rb, double* tt) {
+  double U[9], Sv[3], V[9];
+  svd3(E, U, Sv, V);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double a0 = U[3 * r + 0], a1 = U[3 * r + 1], a2 = U[3 * r + 2];
+      const double b0 = V[3 * c + 0], b1 = V[3 * c + 1], b2 = V[3 * c + 2];
+      Ra[3 * r + c] = (a1 * b0 - a0 * b1) + a2 * b2;
+      Rb[3 * r + c] = (a0 * b1 - a1 * b0) + a2 * b2;
+    }
+  tt[0] = Sv[0] * U[2];
+  tt[1] = Sv[0] * U[5];
+  tt[2] = Sv[0] * U[8];
+}
+// candidate `cand` of (Ra,t),(Ra,-t),(Rb,t),(Rb,-t) as [R12 | t12]
+__device__ __forceinline__ void candidate_model(const double* Ra, const double* Rb, const double* tt, int cand,
+                                                double* M) {
+  const double sgn = (cand & 1) ? -1.0 : 1.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    M[4 * r + 0] = (cand < 2) ? Ra[3 * r + 0] : Rb[3 * r + 0];
+    M[4 * r + 1] = (cand < 2) ? Ra[3 * r + 1] : Rb[3 * r + 1];
+    M[4 * r + 2] = (cand < 2) ? Ra[3 * r + 2] : Rb[3 * r + 2];
+    M[4 * r + 3] = sgn * tt[r];
+  }
+}
+// Scores the four candidates of one essential matrix on the 8 sample points
+// (sequential sum of the bearing residuals, the disambiguation of SURVEY A.6).
+__device__ __noinline__ void score_essential(const double* E, const double* __restrict__ ga,
+                                             const double* __restrict__ gb, const uint16_t* __restrict__ smp,
+                                             double* qual /*[4]*/) {
+  double Ra[9], Rb[9], tt[3];
+  essential_candidates(E, Ra, Rb, tt);
+#pragma unroll 1
+  for (int cand = 0; cand < 4; ++cand) {
+    double M[12], tinv[3];
+    candidate_model(Ra, Rb, tt, cand, M);
+    mono_tinv(M, tinv);
+    double q = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+      const int idx = smp[k];
+      const V3 f1 = {ga[3 * idx], ga[3 * idx + 1], ga[3 * idx + 2]};
+      const V3 f2 = {gb[3 * idx], gb[3 * idx + 1], gb[3 * idx + 2]};
+      q = q + mono_residual(M, tinv, f1, f2);
+    }
+    qual[cand] = q;
+  }
 }
 
 }  // namespace geom

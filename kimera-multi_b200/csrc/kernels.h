@@ -75,6 +75,8 @@ struct SacArgs {
   uint16_t* perm;        // [P][stride] persistent shuffle state
   int cap_draws;         // draws available per problem (raw_len / S)
   double* models;        // [P][kRoundCap][12] models of the draws of the current round
+  int32_t* nsol;         // mono: [P][kRoundCap] essential matrices found per draw of the round
+  double* esol;          // mono: [P][kRoundCap][10][9] those matrices
   uint16_t* samples;     // [P][cap_draws][S]
   int32_t* valid;        // [P][cap_draws]
   int32_t* counts;       // [P][cap_draws]

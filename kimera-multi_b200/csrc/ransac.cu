@@ -153,38 +153,104 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
 }
 
-// ------------------------------------------------------------ mono chunk
-// grid (P, blocks): CTA (p, blk) evaluates draws r_begin + blk*64 + [0,64).
-// Phase A: one hypothesis per THREAD (fivept_thread.cuh), all solver state in
-// shared memory as [slot][thread] (bank-conflict free for any per-thread
-// index), the CTA's two warps passing phase barriers so they share one
-// instruction stream.  Phase B: one hypothesis per warp pass — the lanes
-// stride over all correspondences, inlier count by ballot + popc.
-__global__ void __launch_bounds__(kMonoChunk, 2) mono_chunk_kernel(SacArgs a) {
+// ------------------------------------------------------------ mono round
+// Two kernels per round, both on a grid (P, blocks) where CTA (p, blk) owns the
+// 64 draws r_begin + blk*64 + [0,64) of problem p.
+//
+// mono_front_kernel — one hypothesis per THREAD (fivept_thread.cuh): null
+//   space, constraint build, Gauss-Jordan, Sturm chains, roots; emits up to 10
+//   essential matrices per draw.  All solver state lives in shared memory as
+//   [slot][thread] (bank-conflict free for any per-thread index); the CTA's two
+//   warps pass phase barriers so they share one instruction stream.
+// mono_back_kernel — (a) one (draw, essential matrix) ITEM per thread: SVD, the
+//   four (R,t) candidates scored on the 8 sample points (perfectly balanced:
+//   no thread waits for another draw's larger root count); (b) one thread per
+//   draw picks the winner in the reference's order (strict <); (c) one draw per
+//   warp pass: the lanes stride over all correspondences, inlier count by
+//   ballot + popc, stopping early once the draw cannot beat the best count the
+//   problem had before this round (such a draw can never become the model).
+__global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
-  const int N = a.N[p];
-  __shared__ int s_valid[kMonoChunk];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
   const int nh = min(kMonoChunk, st.r_end - d0);
   const bool live = tid < nh;
   const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? tid : 0)) * 8;
-  const bool ok = geom::mono_model_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live);
-  s_valid[tid] = ok ? 1 : 0;
+  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
+  const int ns = geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.esol + slot * 90);
+  a.nsol[slot] = ns;
+}
+
+constexpr int kBackThreads = 256;
+__global__ void __launch_bounds__(kBackThreads, 2) mono_back_kernel(SacArgs a) {
+  const int p = blockIdx.x;
+  const SacState st = a.st[p];
+  if (st.done) return;
+  const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
+  if (d0 >= st.r_end) return;
+  const int N = a.N[p];
+  __shared__ int s_ns[kMonoChunk], s_base[kMonoChunk + 1], s_valid[kMonoChunk];
+  __shared__ uint16_t s_item[kMonoChunk * 10];
+  __shared__ double s_q[kMonoChunk * 10 * 4];
+  __shared__ double s_mod[kMonoChunk * 12];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* ga = a.a + (size_t)p * a.stride * 3;
+  const double* gb = a.b + (size_t)p * a.stride * 3;
+  const int nh = min(kMonoChunk, st.r_end - d0);
+  const size_t slot0 = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk;
+  if (tid < kMonoChunk) s_ns[tid] = (tid < nh) ? a.nsol[slot0 + tid] : 0;
   __syncthreads();
-  for (int h = warp; h < nh; h += kMonoChunk / 32) {
+  if (tid == 0) {
+    int acc = 0;
+    for (int h = 0; h < kMonoChunk; ++h) { s_base[h] = acc; acc += s_ns[h]; }
+    s_base[kMonoChunk] = acc;
+  }
+  __syncthreads();
+  if (tid < kMonoChunk)
+    for (int r = 0; r < s_ns[tid]; ++r) s_item[s_base[tid] + r] = (uint16_t)(tid * 16 + r);
+  __syncthreads();
+  // (a) items
+  const int total = s_base[kMonoChunk];
+  for (int it = tid; it < total; it += kBackThreads) {
+    const int h = s_item[it] >> 4, r = s_item[it] & 15;
+    geom::score_essential(a.esol + (slot0 + h) * 90 + 9 * r, ga, gb,
+                          a.samples + ((size_t)p * a.cap_draws + d0 + h) * 8, &s_q[it * 4]);
+  }
+  __syncthreads();
+  // (b) winner per draw, in (solution, candidate) order with strict <
+  if (tid < nh) {
+    double best = 1000000.0;
+    int br = -1, bc = 0;
+    for (int r = 0; r < s_ns[tid]; ++r)
+      for (int c = 0; c < 4; ++c) {
+        const double q = s_q[(s_base[tid] + r) * 4 + c];
+        if (q < best) { best = q; br = r; bc = c; }
+      }
+    if (br >= 0) {
+      double Ra[9], Rb[9], tt[3], M[12];
+      geom::essential_candidates(a.esol + (slot0 + tid) * 90 + 9 * br, Ra, Rb, tt);
+      geom::candidate_model(Ra, Rb, tt, bc, M);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) s_mod[12 * tid + i] = M[i];
+    }
+    s_valid[tid] = br >= 0;
+  }
+  __syncthreads();
+  // (c) inlier counts
+  const int bound = a.full ? -INT_MAX : st.best;  // a draw matters only if its count exceeds this
+  for (int h = warp; h < nh; h += kBackThreads / 32) {
     int cnt = 0;
     const int v = s_valid[h];
     if (v) {
       double M[12], tinv[3];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) M[i] = smem_d[(128 + i) * kMonoChunk + h];
+      for (int i = 0; i < 12; ++i) M[i] = s_mod[12 * h + i];
       geom::mono_tinv(M, tinv);
       for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + lane;
@@ -195,14 +261,14 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_chunk_kernel(SacArgs a) {
           in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
         }
         cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+        if (cnt + (N - i0 - 32) <= bound) break;  // cannot become the best model any more
       }
     }
     if (lane == 0) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
-    if (v && lane < 12)
-      a.models[((size_t)p * kRoundCap + blockIdx.y * kMonoChunk + h) * 12 + lane] = smem_d[(128 + lane) * kMonoChunk + h];
+    if (v && lane < 12) a.models[(slot0 + h) * 12 + lane] = s_mod[12 * h + lane];
   }
 }
 
@@ -421,7 +487,7 @@ __global__ void finalize_kernel(FinalizeArgs f) {
 }
 
 // --------------------------------------------------------------- launchers
-static size_t mono_smem(int) { return sizeof(double) * geom::kTphSlots * kMonoChunk; }
+static size_t mono_smem() { return sizeof(double) * geom::kTphSlots * kMonoChunk; }
 static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
 
 template <class K>
@@ -441,13 +507,14 @@ void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
 
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
-  const size_t sm = mono_smem(a.stride);
-  ensure_smem(mono_chunk_kernel, sm);
+  const size_t sm = mono_smem();
+  ensure_smem(mono_front_kernel, sm);
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
-  mono_chunk_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
+  mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
+  mono_back_kernel<<<dim3(a.P, blocks), kBackThreads, 0, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
-  return 2;
+  return 3;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;

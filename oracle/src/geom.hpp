@@ -325,6 +325,7 @@ static inline int sturm_count(const Sturm* st, double x) {
   return changes;
 }
 
+static const int kRootGrid = 32;    // sign-test cells on (-1,1]
 static const int kRootDepth = 48;   // max Sturm bisection depth per root
 static const int kRootBisect = 10;  // sign bisection steps on the isolated bracket
 static const int kRootNewton = 8;   // bracketed Newton steps that follow
@@ -347,15 +348,42 @@ static inline int roots_unit(const double* p, int n, double* roots) {
   const int d0 = st.deg[0];
   const double* c1 = st.c[1];  // p' (unscaled)
   const int d1 = st.deg[1];
+  // Grid pass: signs of p on the 32 cells (x_{i-1}, x_i], x_i = -1 + i/16.  A
+  // cell brackets a root if the sign changes across it or p(x_i) == 0.  If the
+  // number of bracketing cells equals the Sturm count R, every one of them
+  // holds exactly one distinct root and no other cell holds any, so the cells
+  // ARE the isolating brackets; otherwise (two roots in one cell) each root is
+  // isolated by bisection on the Sturm count.
+  unsigned cells = 0u;
+  int nb = 0;
+  if (R > 0) {
+    double fprev = horner(c0, d0, -1.0);
+    for (int i = 1; i <= kRootGrid; ++i) {
+      const double fi = horner(c0, d0, -1.0 + (double)i * (2.0 / kRootGrid));
+      if ((fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0) {
+        cells |= 1u << (i - 1);
+        ++nb;
+      }
+      fprev = fi;
+    }
+  }
+  const bool grid_ok = (nb == R);
+  int cell = -1;
   for (int j = 0; j < R; ++j) {
     double lo = -1.0, hi = 1.0;
-    int vlo = vm1, vhi = vp1, jj = j;
-    for (int depth = 0; depth < kRootDepth; ++depth) {
-      if (vlo - vhi == 1) break;
-      const double mid = 0.5 * (lo + hi);
-      const int vm = sturm_count(&st, mid);
-      const int left = vlo - vm;  // roots in (lo, mid]
-      if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+    if (grid_ok) {
+      do { ++cell; } while (!((cells >> cell) & 1u));
+      lo = -1.0 + (double)cell * (2.0 / kRootGrid);
+      hi = -1.0 + (double)(cell + 1) * (2.0 / kRootGrid);
+    } else {
+      int vlo = vm1, vhi = vp1, jj = j;
+      for (int depth = 0; depth < kRootDepth; ++depth) {
+        if (vlo - vhi == 1) break;
+        const double mid = 0.5 * (lo + hi);
+        const int vm = sturm_count(&st, mid);
+        const int left = vlo - vm;  // roots in (lo, mid]
+        if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+      }
     }
     double flo = horner(c0, d0, lo);
     const double fhi = horner(c0, d0, hi);

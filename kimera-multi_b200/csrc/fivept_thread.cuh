@@ -1,39 +1,41 @@
-// fivept_thread.cuh — the mono minimal solver, one RANSAC hypothesis per THREAD
-// (opengv fivept_nister + essential decomposition + 8-point disambiguation,
-// SURVEY.md A.6; /root/reference/images/kimera-multi.drawio:2589-2592, 2646).
-//
-// Why a thread and not a warp: the solver is a long chain of small dense
-// linear-algebra steps whose summation orders are fixed by the ARITHMETIC
-// CONTRACT.  Spreading one hypothesis over 32 lanes left 55 %
-// of the lanes idle and cost 25 k issued warp-instructions per hypothesis
-// (profiles/r01c); 32 independent hypotheses per warp need ~5 k.  What made the
-// very first thread-per-hypothesis build slow (5.7 KB of local memory per
-// thread thrashing L1, and an instruction footprint larger than the SM's
-// instruction cache) is handled explicitly here:
-//   * all per-hypothesis state lives in SHARED memory as S(i) = sm[i*STRIDE +
-//     thread]: consecutive threads hit consecutive 8-byte words, so any
-//     per-thread index (pivot rows, chain degrees, root counts) is
-//     bank-conflict free;  200 slots per thread, re-used phase by phase:
-//       phase 1 (null space)   A9 0..44 | Hv 45..89 | Hn 90..94 | x 95..103 | basis 104..139
-//       phase 2-3 (build, GJ)  A[10][20] 0..199
-//       phase 4+               Bz 0..44 | p1 45..52 | p2 53..60 | p3 61..67 | nz 68..78
-//                              Sturm chain (triangular) 80..145 | roots 146..155 | basis 156..191
-//       phase 7-8              sampled bearings 80..127 | best model 128..139
-//   * the 10x20 constraint build is generated straight-line code
-//     (fivept_build.inc) with the 36 null-space coefficients in registers;
-//   * division, sqrt, Horner, SVD are not inlined, and the CTA's warps pass
-//     phase barriers, so the SM fetches one compact instruction stream.
+// fivept_thread.cuh — the mono minimal solver of one RANSAC round, staged for
+// the GPU (opengv fivept_nister + essential decomposition + 8-point
+// disambiguation; /root/reference/images/kimera-multi.drawio:
+// 2589-2592, 2646).  Every stage executes the operation sequence of the
+// ARITHMETIC CONTRACT; the stages only differ in what one
+// thread owns:
+//   stage 1  mono_front_thread    thread = draw.  Null space (Householder),
+//            10x20 constraint build (generated straight-line code), Gauss-
+//            Jordan, B(z) cofactors -> n(z), p1, p2, p3, basis (70 doubles).
+//            State in SHARED memory as S(i) = sm[i*STRIDE + thread]: any
+//            per-thread index (pivot row!) is bank-conflict free.  200 slots:
+//              null space   A9 0..44 | Hv 45..89 | Hn 90..94 | x 95..103 | basis 104..139
+//              build, GJ    A[10][20] 0..199
+//              cofactors    Bz 0..44 | p1 45..52 | p2 53..60 | p3 61..67 | nz 68..78
+//   stage 2  mono_isolate_thread  thread = draw.  Sturm chains of n(z) and of
+//            the reversed polynomial, root counts, 32-cell sign grid (or
+//            bisection on the Sturm count when two roots share a cell) ->
+//            one isolating bracket per real root.  88 slots:
+//              scratch 0..10 | nz 11..21 | chain (triangular) 22..87
+//   stage 3  (mono_back_kernel)   thread = (draw, root) ITEM: refine the root,
+//            E, SVD, four (R,t) candidates scored on the 8 sample points.
+// Division, sqrt, Horner and SVD are not inlined and the front CTA's warps pass
+// phase barriers: the SM fetches one compact instruction stream (the first
+// fully inlined build stalled 63 % of its warp time on instruction fetch).
 #pragma once
 #include "geom.cuh"
 
 namespace kml {
 namespace geom {
 
-constexpr int kTphSlots = 200;
+constexpr int kTphSlots = 200;    // stage 1
+constexpr int kIsoSlots = 88;     // stage 2
+constexpr int kFrontOut = 70;     // nz[11] p1[8] p2[8] p3[7] basis[36]
+constexpr int kMaxBrackets = 20;  // <= 10 per chain
 constexpr int kTRootGrid = 32;
 constexpr int kTRootDepth = 48;
-constexpr int kTRootBisect = 10;
-constexpr int kTRootNewton = 8;
+constexpr int kTRootBisect = 6;
+constexpr int kTRootNewton = 6;
 
 // Horner on a strided shared-memory polynomial (ascending coefficients)
 template <int STRIDE>
@@ -50,152 +52,15 @@ __device__ __noinline__ double conv_s(const double* a, int da, const double* b, 
   for (int i = i0; i <= i1; ++i) r = r + a[i * STRIDE] * b[(k - i) * STRIDE];
   return r;
 }
-__device__ __forceinline__ int tri_off(int k) { return 80 + 11 * k - (k * (k - 1)) / 2; }
 
-// Sturm chain of the polynomial at `p` (degree <= 10, strided) into the
-// triangular chain area; degrees packed 4 bits each in `degs`; returns length.
-template <int STRIDE>
-__device__ __noinline__ int sturm_build_s(double* sm, const double* p, bool reversed, unsigned long long* degs_out) {
-#define SS(i) sm[(i) * STRIDE]
-  int n = 10;
-  while (n > 0 && p[(reversed ? 10 - n : n) * STRIDE] == 0.0) --n;
-  for (int i = 0; i <= n; ++i) SS(tri_off(0) + i) = p[(reversed ? 10 - i : i) * STRIDE];
-  unsigned long long degs = (unsigned long long)n;
-  int len = 1;
-  if (n >= 1) {
-    for (int i = 0; i < n; ++i) SS(tri_off(1) + i) = (double)(i + 1) * p[(reversed ? 10 - (i + 1) : (i + 1)) * STRIDE];
-    degs |= (unsigned long long)(n - 1) << 4;
-    len = 2;
-    while (len < 12) {
-      const int db = (int)((degs >> (4 * (len - 1))) & 15u);
-      if (db <= 0) break;
-      const int da = (int)((degs >> (4 * (len - 2))) & 15u);
-      const int oa = tri_off(len - 2), ob = tri_off(len - 1), oc = tri_off(len);
-      // remainder r[0..da] in scratch slots 0..10 (the B(z) area is dead by now)
-      for (int i = 0; i <= da; ++i) SS(i) = SS(oa + i);
-      for (int d = da; d >= db; --d) {
-        const double f = kdiv(SS(d), SS(ob + db));
-        for (int i = 0; i < db; ++i) SS(d - db + i) = SS(d - db + i) - f * SS(ob + i);
-        SS(d) = 0.0;
-      }
-      int dr = db - 1;
-      while (dr >= 0 && SS(dr) == 0.0) --dr;
-      if (dr < 0) break;  // exact gcd reached
-      const double sc = fabs(SS(dr));
-      for (int i = 0; i <= dr; ++i) SS(oc + i) = -kdiv(SS(i), sc);
-      degs |= (unsigned long long)dr << (4 * len);
-      ++len;
-    }
-  }
-  *degs_out = degs;
-  return len;
-#undef SS
-}
-
-template <int STRIDE>
-__device__ __noinline__ int sturm_count_s(const double* sm, unsigned long long degs, int len, double x) {
-  int changes = 0, last = 0;
-  for (int k = 0; k < len; ++k) {
-    const double v = horner_s<STRIDE>(sm + tri_off(k) * STRIDE, (int)((degs >> (4 * k)) & 15u), x);
-    const int s = (v > 0.0) - (v < 0.0);
-    if (s != 0) {
-      if (last != 0 && s != last) ++changes;
-      last = s;
-    }
-  }
-  return changes;
-}
-
-// Real roots in (-1,1] of the chain's first polynomial, ascending, appended to
-// roots[] (strided) starting at *nroots (cap 10 in total).  `invert`: the
-// chain is the reversed polynomial, emit z = 1/u and drop u = 1 and u = 0.
-template <int STRIDE>
-__device__ __noinline__ void roots_unit_s(double* sm, unsigned long long degs, int len, bool invert, int* nroots) {
-#define SS(i) sm[(i) * STRIDE]
-  const int d0 = (int)(degs & 15u);
-  if (d0 < 1) return;
-  const int d1 = (int)((degs >> 4) & 15u);
-  const double* c0 = sm + tri_off(0) * STRIDE;
-  const double* c1 = sm + tri_off(1) * STRIDE;
-  const int vm1 = sturm_count_s<STRIDE>(sm, degs, len, -1.0), vp1 = sturm_count_s<STRIDE>(sm, degs, len, 1.0);
-  int R = vm1 - vp1;
-  if (R > 10) R = 10;
-  // grid pass: 32 sign-test cells (x_{i-1}, x_i], x_i = -1 + i/16; if the number of bracketing
-  // cells equals the Sturm count they are the isolating brackets, else bisect on the count
-  unsigned cells = 0u;
-  int nb = 0;
-  if (R > 0) {
-    double fprev = horner_s<STRIDE>(c0, d0, -1.0);
-    for (int i = 1; i <= kTRootGrid; ++i) {
-      const double fi = horner_s<STRIDE>(c0, d0, -1.0 + (double)i * (2.0 / kTRootGrid));
-      if ((fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0) {
-        cells |= 1u << (i - 1);
-        ++nb;
-      }
-      fprev = fi;
-    }
-  }
-  const bool grid_ok = (nb == R);
-  int cell = -1;
-  for (int j = 0; j < R; ++j) {
-    double lo = -1.0, hi = 1.0;
-    if (grid_ok) {
-      do { ++cell; } while (!((cells >> cell) & 1u));
-      lo = -1.0 + (double)cell * (2.0 / kTRootGrid);
-      hi = -1.0 + (double)(cell + 1) * (2.0 / kTRootGrid);
-    } else {
-      int vlo = vm1, vhi = vp1, jj = j;
-      for (int depth = 0; depth < kTRootDepth; ++depth) {
-        if (vlo - vhi == 1) break;
-        const double mid = 0.5 * (lo + hi);
-        const int vm = sturm_count_s<STRIDE>(sm, degs, len, mid);
-        const int left = vlo - vm;
-        if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
-      }
-    }
-    double flo = horner_s<STRIDE>(c0, d0, lo);
-    const double fhi = horner_s<STRIDE>(c0, d0, hi);
-    double root;
-    if (fhi == 0.0) {
-      root = hi;
-    } else {
-      if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) continue;
-      for (int it = 0; it < kTRootBisect; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        const double fm = horner_s<STRIDE>(c0, d0, mid);
-        if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
-      }
-      double x = 0.5 * (lo + hi);
-      for (int it = 0; it < kTRootNewton; ++it) {
-        const double fx = horner_s<STRIDE>(c0, d0, x);
-        const double dfx = horner_s<STRIDE>(c1, d1, x);
-        if ((fx < 0.0) == (flo < 0.0)) { lo = x; flo = fx; } else { hi = x; }
-        double xn = x - kdiv(fx, dfx);
-        if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
-        x = xn;
-      }
-      root = x;
-    }
-    if (invert) {
-      if (root == 1.0 || root == 0.0) continue;
-      root = kdiv(1.0, root);
-    }
-    if (*nroots < 10) {
-      SS(146 + *nroots) = root;
-      ++*nroots;
-    }
-  }
-#undef SS
-}
-
-// sm: this thread's slot 0 (slot i at sm[i*STRIDE]).  ga/gb: the problem's
-// correspondences (query / match bearings, [N][3]); smp: the 8 sample indices.
-// Returns the number of essential matrices (<= 10) written to Eout[10][9]
-// (row-major, f_q^T E f_m = 0).  `alive` = false makes the thread a passenger
-// (barriers only, returns 0).
+// ============================================================== stage 1
+// sm: this thread's slot 0.  ga/gb: the problem's correspondences (query /
+// match bearings, [N][3]); smp: the 8 sample indices.  Writes the 70 doubles
+// of kFrontOut to `out` (NaN basis if the constraint system was singular).
+// `alive` = false makes the thread a passenger (barriers only, no output).
 template <int STRIDE, bool SYNC>
-__device__ int mono_front_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
-                                 const uint16_t* __restrict__ smp, bool alive, double* __restrict__ Eout) {
+__device__ void mono_front_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
+                                  const uint16_t* __restrict__ smp, bool alive, double* __restrict__ out) {
 #define S(i) sm[(i) * STRIDE]
 #define KML_PHASE() do { if (SYNC) __syncthreads(); } while (0)
   bool failed = !alive;
@@ -303,8 +168,10 @@ __device__ int mono_front_thread(double* sm, const double* __restrict__ ga, cons
       S(o + 3) = S(e + 16) - S(f + 17);
       S(o + 4) = -S(f + 16);
     }
+    if (alive) {
 #pragma unroll
-    for (int i = 0; i < 36; ++i) S(156 + i) = B[i];  // A rows 7..9 are consumed: keep the basis for phase 7
+      for (int i = 0; i < 36; ++i) out[34 + i] = failed ? nan("") : B[i];
+    }
   }
   {
     const double* b00 = sm + 0 * STRIDE, *b01 = sm + 5 * STRIDE, *b02 = sm + 10 * STRIDE;
@@ -321,42 +188,196 @@ __device__ int mono_front_thread(double* sm, const double* __restrict__ ga, cons
       S(68 + k) = (conv_s<STRIDE>(sm + 45 * STRIDE, 7, b20, 3, k) + conv_s<STRIDE>(sm + 53 * STRIDE, 7, b21, 3, k)) +
                   conv_s<STRIDE>(sm + 61 * STRIDE, 6, b22, 4, k);
   }
-  KML_PHASE();
-  // ---------------------- phases 5-6: Sturm chains and roots (n(z), then reversed n)
-  int nroots = 0;
+  if (alive) {
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    unsigned long long degs;
-    const int len = sturm_build_s<STRIDE>(sm, sm + 68 * STRIDE, h == 1, &degs);
-    roots_unit_s<STRIDE>(sm, degs, len, h == 1, &nroots);
+    for (int k = 0; k < 34; ++k) out[k] = (k < 11) ? S(68 + k) : S(45 + (k - 11));
   }
-  KML_PHASE();
-  // ------------------------------ phase 7a: one essential matrix per finite root
-  int ns = 0;
-#pragma unroll 1
-  for (int rt = 0; rt < nroots; ++rt) {
-    const double z = S(146 + rt);
-    const double d = horner_s<STRIDE>(sm + 61 * STRIDE, 6, z);
-    const double x = kdiv(horner_s<STRIDE>(sm + 45 * STRIDE, 7, z), d);
-    const double y = kdiv(horner_s<STRIDE>(sm + 53 * STRIDE, 7, z), d);
-    double E[9];
-    bool ok = true;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      const double v = ((x * S(156 + e) + y * S(156 + 9 + e)) + z * S(156 + 18 + e)) + S(156 + 27 + e);
-      if (!isfinite(v)) ok = false;
-      E[e] = v;
-    }
-    if (!ok) continue;
-    if (!failed) {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Eout[9 * ns + e] = E[e];
-    }
-    ++ns;
-  }
-  return failed ? 0 : ns;
 #undef KML_PHASE
 #undef S
+}
+
+// ============================================================== stage 2
+__device__ __forceinline__ int tri_off(int k) { return 22 + 11 * k - (k * (k - 1)) / 2; }
+
+// Sturm chain of the polynomial in slots 11..21 (or its reversal) into the
+// triangular chain area; degrees packed 4 bits each; returns the length.
+template <int STRIDE>
+__device__ __noinline__ int sturm_build_s(double* sm, bool reversed, unsigned long long* degs_out) {
+#define SS(i) sm[(i) * STRIDE]
+  int n = 10;
+  while (n > 0 && SS(11 + (reversed ? 10 - n : n)) == 0.0) --n;
+  for (int i = 0; i <= n; ++i) SS(tri_off(0) + i) = SS(11 + (reversed ? 10 - i : i));
+  unsigned long long degs = (unsigned long long)n;
+  int len = 1;
+  if (n >= 1) {
+    for (int i = 0; i < n; ++i) SS(tri_off(1) + i) = (double)(i + 1) * SS(11 + (reversed ? 10 - (i + 1) : (i + 1)));
+    degs |= (unsigned long long)(n - 1) << 4;
+    len = 2;
+    while (len < 12) {
+      const int db = (int)((degs >> (4 * (len - 1))) & 15u);
+      if (db <= 0) break;
+      const int da = (int)((degs >> (4 * (len - 2))) & 15u);
+      const int oa = tri_off(len - 2), ob = tri_off(len - 1), oc = tri_off(len);
+      for (int i = 0; i <= da; ++i) SS(i) = SS(oa + i);  // remainder r[0..da] in scratch 0..10
+      for (int d = da; d >= db; --d) {
+        const double f = kdiv(SS(d), SS(ob + db));
+        for (int i = 0; i < db; ++i) SS(d - db + i) = SS(d - db + i) - f * SS(ob + i);
+        SS(d) = 0.0;
+      }
+      int dr = db - 1;
+      while (dr >= 0 && SS(dr) == 0.0) --dr;
+      if (dr < 0) break;  // exact gcd reached
+      const double sc = fabs(SS(dr));
+      for (int i = 0; i <= dr; ++i) SS(oc + i) = -kdiv(SS(i), sc);
+      degs |= (unsigned long long)dr << (4 * len);
+      ++len;
+    }
+  }
+  *degs_out = degs;
+  return len;
+#undef SS
+}
+
+template <int STRIDE>
+__device__ __noinline__ int sturm_count_s(const double* sm, unsigned long long degs, int len, double x) {
+  int changes = 0, last = 0;
+  for (int k = 0; k < len; ++k) {
+    const double v = horner_s<STRIDE>(sm + tri_off(k) * STRIDE, (int)((degs >> (4 * k)) & 15u), x);
+    const int s = (v > 0.0) - (v < 0.0);
+    if (s != 0) {
+      if (last != 0 && s != last) ++changes;
+      last = s;
+    }
+  }
+  return changes;
+}
+
+// Isolating brackets (lo, hi] of the real roots in (-1,1] of the chain's first
+// polynomial, ascending; returns their number R (<= 10).
+template <int STRIDE>
+__device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, int len, double* __restrict__ brk) {
+  const int d0 = (int)(degs & 15u);
+  if (d0 < 1) return 0;
+  const double* c0 = sm + tri_off(0) * STRIDE;
+  const int vm1 = sturm_count_s<STRIDE>(sm, degs, len, -1.0), vp1 = sturm_count_s<STRIDE>(sm, degs, len, 1.0);
+  int R = vm1 - vp1;
+  if (R > 10) R = 10;
+  if (R <= 0) return 0;
+  // grid pass: 32 sign-test cells (x_{i-1}, x_i], x_i = -1 + i/16; if the number of bracketing
+  // cells equals the Sturm count they are the isolating brackets, else bisect on the count
+  unsigned cells = 0u;
+  int nb = 0;
+  double fprev = horner_s<STRIDE>(c0, d0, -1.0);
+  for (int i = 1; i <= kTRootGrid; ++i) {
+    const double fi = horner_s<STRIDE>(c0, d0, -1.0 + (double)i * (2.0 / kTRootGrid));
+    if ((fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0) {
+      cells |= 1u << (i - 1);
+      ++nb;
+    }
+    fprev = fi;
+  }
+  const bool grid_ok = (nb == R);
+  int cell = -1;
+  for (int j = 0; j < R; ++j) {
+    double lo = -1.0, hi = 1.0;
+    if (grid_ok) {
+      do { ++cell; } while (!((cells >> cell) & 1u));
+      lo = -1.0 + (double)cell * (2.0 / kTRootGrid);
+      hi = -1.0 + (double)(cell + 1) * (2.0 / kTRootGrid);
+    } else {
+      int vlo = vm1, vhi = vp1, jj = j;
+      for (int depth = 0; depth < kTRootDepth; ++depth) {
+        if (vlo - vhi == 1) break;
+        const double mid = 0.5 * (lo + hi);
+        const int vm = sturm_count_s<STRIDE>(sm, degs, len, mid);
+        const int left = vlo - vm;
+        if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+      }
+    }
+    brk[2 * j] = lo;
+    brk[2 * j + 1] = hi;
+  }
+  return R;
+}
+
+// fo: this draw's stage-1 output.  Writes up to 10 + 10 brackets to brk and
+// returns R0 | R1 << 8 (0 if the draw has no usable polynomial).
+template <int STRIDE>
+__device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, double* __restrict__ brk) {
+#define S(i) sm[(i) * STRIDE]
+  if (!(fo[34] == fo[34])) return 0;  // singular constraint system (NaN basis)
+#pragma unroll 1
+  for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];
+  unsigned long long degs;
+  int len = sturm_build_s<STRIDE>(sm, false, &degs);
+  const int R0 = isolate_unit_s<STRIDE>(sm, degs, len, brk);
+  len = sturm_build_s<STRIDE>(sm, true, &degs);
+  const int R1 = isolate_unit_s<STRIDE>(sm, degs, len, brk + 2 * R0);
+  return R0 | (R1 << 8);
+#undef S
+}
+
+// ============================================================== stage 3
+__device__ __noinline__ double horner_l(const double* c, int deg, double x) {
+  double r = c[deg];
+  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i];
+  return r;
+}
+
+// Refines the root of bracket (lo, hi] of n(z) (chain 0) or of the reversed
+// polynomial (chain 1) and maps it to z.  fo = stage-1 output of the draw.
+__device__ __noinline__ bool refine_root(const double* __restrict__ fo, int chain, double lo, double hi,
+                                         double* z_out) {
+  double c0[11], c1[10];
+  int d0 = 10;
+  while (d0 > 0 && fo[chain ? 10 - d0 : d0] == 0.0) --d0;
+  for (int i = 0; i <= d0; ++i) c0[i] = fo[chain ? 10 - i : i];
+  for (int i = 0; i < d0; ++i) c1[i] = (double)(i + 1) * c0[i + 1];
+  const int d1 = d0 - 1;
+  double flo = horner_l(c0, d0, lo);
+  const double fhi = horner_l(c0, d0, hi);
+  double root;
+  if (fhi == 0.0) {
+    root = hi;
+  } else {
+    if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) return false;
+    for (int it = 0; it < kTRootBisect; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      const double fm = horner_l(c0, d0, mid);
+      if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
+    }
+    double x = 0.5 * (lo + hi);
+    for (int it = 0; it < kTRootNewton; ++it) {
+      const double fx = horner_l(c0, d0, x);
+      const double dfx = horner_l(c1, d1, x);
+      if ((fx < 0.0) == (flo < 0.0)) { lo = x; flo = fx; } else { hi = x; }
+      double xn = x - kdiv(fx, dfx);
+      if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
+      x = xn;
+    }
+    root = x;
+  }
+  if (chain) {
+    if (root == 1.0 || root == 0.0) return false;  // z = 1 belongs to chain 0; u = 0 is z = inf
+    root = kdiv(1.0, root);
+  }
+  *z_out = root;
+  return true;
+}
+
+// E(z) = x X + y Y + z Z + W with x = p1(z)/p3(z), y = p2(z)/p3(z); false if not finite.
+__device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, double z, double* E) {
+  const double d = horner_l(fo + 27, 6, z);
+  const double x = kdiv(horner_l(fo + 11, 7, z), d);
+  const double y = kdiv(horner_l(fo + 19, 7, z), d);
+  bool ok = true;
+#pragma unroll 1
+  for (int e = 0; e < 9; ++e) {
+    const double v = ((x * fo[34 + e] + y * fo[34 + 9 + e]) + z * fo[34 + 18 + e]) + fo[34 + 27 + e];
+    if (!isfinite(v)) ok = false;
+    E[e] = v;
+  }
+  return ok;
 }
 
 // Decomposition of one essential matrix: Ra = U W V^T, Rb = U W^T V^T, t = s0 u2.

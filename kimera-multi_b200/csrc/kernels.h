@@ -75,8 +75,9 @@ struct SacArgs {
   uint16_t* perm;        // [P][stride] persistent shuffle state
   int cap_draws;         // draws available per problem (raw_len / S)
   double* models;        // [P][kRoundCap][12] models of the draws of the current round
-  int32_t* nsol;         // mono: [P][kRoundCap] essential matrices found per draw of the round
-  double* esol;          // mono: [P][kRoundCap][10][9] those matrices
+  double* fsol;          // mono: [P][kRoundCap][70] stage-1 output per draw of the round
+  int32_t* nroot;        // mono: [P][kRoundCap] R0 | R1<<8 real-root counts of the two chains
+  double* brk;           // mono: [P][kRoundCap][20][2] isolating brackets
   uint16_t* samples;     // [P][cap_draws][S]
   int32_t* valid;        // [P][cap_draws]
   int32_t* counts;       // [P][cap_draws]

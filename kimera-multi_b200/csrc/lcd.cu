@@ -370,7 +370,8 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   h->d_models.scratch((size_t)P * kRoundCap * 12);
   if (mono) {
     h->d_nsol.scratch((size_t)P * kRoundCap);
-    h->d_esol.scratch((size_t)P * kRoundCap * 90);
+    h->d_esol.scratch((size_t)P * kRoundCap * 70);
+    h->d_brk.scratch((size_t)P * kRoundCap * 40);
   }
   h->d_valid.scratch((size_t)P * cap_draws);
   h->d_counts.scratch((size_t)P * cap_draws);
@@ -382,7 +383,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
   a.raw = h->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
-  a.nsol = h->d_nsol.p; a.esol = h->d_esol.p;
+  a.fsol = h->d_esol.p; a.nroot = h->d_nsol.p; a.brk = h->d_brk.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
   a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
   a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;

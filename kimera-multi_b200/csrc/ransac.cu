@@ -154,21 +154,23 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 }
 
 // ------------------------------------------------------------ mono round
-// Two kernels per round, both on a grid (P, blocks) where CTA (p, blk) owns the
-// 64 draws r_begin + blk*64 + [0,64) of problem p.
-//
-// mono_front_kernel — one hypothesis per THREAD (fivept_thread.cuh): null
-//   space, constraint build, Gauss-Jordan, Sturm chains, roots; emits up to 10
-//   essential matrices per draw.  All solver state lives in shared memory as
-//   [slot][thread] (bank-conflict free for any per-thread index); the CTA's two
-//   warps pass phase barriers so they share one instruction stream.
-// mono_back_kernel — (a) one (draw, essential matrix) ITEM per thread: SVD, the
-//   four (R,t) candidates scored on the 8 sample points (perfectly balanced:
-//   no thread waits for another draw's larger root count); (b) one thread per
-//   draw picks the winner in the reference's order (strict <); (c) one draw per
-//   warp pass: the lanes stride over all correspondences, inlier count by
-//   ballot + popc, stopping early once the draw cannot beat the best count the
-//   problem had before this round (such a draw can never become the model).
+// Three kernels per round on a grid (P, blocks); CTA (p, blk) owns the 64 draws
+// r_begin + blk*64 + [0,64) of problem p; they hand over through per-round
+// global buffers indexed by slot = p*kRoundCap + blk*64 + t.
+//   mono_front_kernel    thread = draw: null space, constraint build, Gauss-
+//                        Jordan, cofactor polynomials (fivept_thread.cuh stage 1);
+//                        200 shared-memory slots per thread -> 4 warps per SM.
+//   mono_isolate_kernel  thread = draw: Sturm chains + isolating brackets of the
+//                        real roots (stage 2); 88 slots -> 10 warps per SM.
+//   mono_back_kernel     (a) thread = (draw, root) ITEM: refine root, E, SVD, the
+//                        four (R,t) candidates scored on the 8 sample points —
+//                        every item costs the same, no thread waits for another
+//                        draw's larger root count; (b) thread = draw: winner in
+//                        the reference's order (strict <, first 10 roots);
+//                        (c) warp = draw: lanes stride over all correspondences,
+//                        inlier count by ballot + popc, stopping early once the
+//                        draw cannot beat the best count the problem had before
+//                        this round (such a draw can never become the model).
 __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
@@ -183,11 +185,26 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   const bool live = tid < nh;
   const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? tid : 0)) * 8;
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
-  const int ns = geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.esol + slot * 90);
-  a.nsol[slot] = ns;
+  geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * geom::kFrontOut);
+}
+
+__global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int p = blockIdx.x;
+  const SacState st = a.st[p];
+  if (st.done) return;
+  const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
+  if (d0 >= st.r_end) return;
+  const int tid = threadIdx.x;
+  const int nh = min(kMonoChunk, st.r_end - d0);
+  if (tid >= nh) return;
+  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
+  a.nroot[slot] = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
+                                                        a.brk + slot * 2 * geom::kMaxBrackets);
 }
 
 constexpr int kBackThreads = 256;
+constexpr int kMaxItems = kMonoChunk * geom::kMaxBrackets;
 __global__ void __launch_bounds__(kBackThreads, 2) mono_back_kernel(SacArgs a) {
   const int p = blockIdx.x;
   const SacState st = a.st[p];
@@ -195,46 +212,78 @@ __global__ void __launch_bounds__(kBackThreads, 2) mono_back_kernel(SacArgs a) {
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
-  __shared__ int s_ns[kMonoChunk], s_base[kMonoChunk + 1], s_valid[kMonoChunk];
-  __shared__ uint16_t s_item[kMonoChunk * 10];
-  __shared__ double s_q[kMonoChunk * 10 * 4];
-  __shared__ double s_mod[kMonoChunk * 12];
+  extern __shared__ __align__(16) double smem_d[];
+  double* s_q = smem_d;                        // [kMaxItems][4] candidate qualities
+  double* s_z = s_q + kMaxItems * 4;           // [kMaxItems] refined roots
+  double* s_mod = s_z + kMaxItems;             // [64][12] winning model per draw
+  int* s_nr = reinterpret_cast<int*>(s_mod + kMonoChunk * 12);  // [64]
+  int* s_base = s_nr + kMonoChunk;             // [65]
+  int* s_valid = s_base + kMonoChunk + 1;      // [64]
+  uint16_t* s_item = reinterpret_cast<uint16_t*>(s_valid + kMonoChunk);  // [kMaxItems]
+  unsigned char* s_ok = reinterpret_cast<unsigned char*>(s_item + kMaxItems);  // [kMaxItems]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
   const int nh = min(kMonoChunk, st.r_end - d0);
   const size_t slot0 = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk;
-  if (tid < kMonoChunk) s_ns[tid] = (tid < nh) ? a.nsol[slot0 + tid] : 0;
+  if (tid < kMonoChunk) s_nr[tid] = (tid < nh) ? a.nroot[slot0 + tid] : 0;
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
-    for (int h = 0; h < kMonoChunk; ++h) { s_base[h] = acc; acc += s_ns[h]; }
+    for (int h = 0; h < kMonoChunk; ++h) { s_base[h] = acc; acc += (s_nr[h] & 255) + (s_nr[h] >> 8); }
     s_base[kMonoChunk] = acc;
   }
   __syncthreads();
-  if (tid < kMonoChunk)
-    for (int r = 0; r < s_ns[tid]; ++r) s_item[s_base[tid] + r] = (uint16_t)(tid * 16 + r);
-  __syncthreads();
-  // (a) items
-  const int total = s_base[kMonoChunk];
-  for (int it = tid; it < total; it += kBackThreads) {
-    const int h = s_item[it] >> 4, r = s_item[it] & 15;
-    geom::score_essential(a.esol + (slot0 + h) * 90 + 9 * r, ga, gb,
-                          a.samples + ((size_t)p * a.cap_draws + d0 + h) * 8, &s_q[it * 4]);
+  if (tid < kMonoChunk) {
+    const int n = (s_nr[tid] & 255) + (s_nr[tid] >> 8);
+    for (int r = 0; r < n; ++r) s_item[s_base[tid] + r] = (uint16_t)(tid * 32 + r);
   }
   __syncthreads();
-  // (b) winner per draw, in (solution, candidate) order with strict <
+  // (a) items: one bracketed root each
+  const int total = s_base[kMonoChunk];
+  for (int it = tid; it < total; it += kBackThreads) {
+    const int h = s_item[it] >> 5, r = s_item[it] & 31;
+    const int R0 = s_nr[h] & 255;
+    const double* fo = a.fsol + (slot0 + h) * geom::kFrontOut;
+    const double* bk = a.brk + (slot0 + h) * 2 * geom::kMaxBrackets + 2 * r;
+    double z, E[9];
+    bool ok = geom::refine_root(fo, r >= R0 ? 1 : 0, bk[0], bk[1], &z);
+    if (ok) {
+      s_z[it] = z;
+      ok = geom::essential_from_root(fo, z, E);
+    }
+    if (ok) geom::score_essential(E, ga, gb, a.samples + ((size_t)p * a.cap_draws + d0 + h) * 8, &s_q[it * 4]);
+    s_ok[it] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  // (b) winner per draw: roots in order, at most the first 10 refined ones, strict <
   if (tid < nh) {
+    const int n = (s_nr[tid] & 255) + (s_nr[tid] >> 8);
+    const double* fo = a.fsol + (slot0 + tid) * geom::kFrontOut;
     double best = 1000000.0;
-    int br = -1, bc = 0;
-    for (int r = 0; r < s_ns[tid]; ++r)
+    int br = -1, bc = 0, refined = 0;
+    for (int r = 0; r < n && refined < 10; ++r) {
+      const int it = s_base[tid] + r;
+      // a root counts towards the 10 as soon as it is refined, even if its E is not finite
+      double z;
+      const int R0 = s_nr[tid] & 255;
+      (void)R0;
+      if (!s_ok[it]) {
+        // distinguish "not refined" from "refined, E not finite": redo the cheap test
+        const double* bk = a.brk + (slot0 + tid) * 2 * geom::kMaxBrackets + 2 * r;
+        if (geom::refine_root(fo, r >= (s_nr[tid] & 255) ? 1 : 0, bk[0], bk[1], &z)) ++refined;
+        continue;
+      }
+      ++refined;
       for (int c = 0; c < 4; ++c) {
-        const double q = s_q[(s_base[tid] + r) * 4 + c];
+        const double q = s_q[it * 4 + c];
         if (q < best) { best = q; br = r; bc = c; }
       }
+    }
     if (br >= 0) {
-      double Ra[9], Rb[9], tt[3], M[12];
-      geom::essential_candidates(a.esol + (slot0 + tid) * 90 + 9 * br, Ra, Rb, tt);
+      double E[9], Ra[9], Rb[9], tt[3], M[12];
+      geom::essential_from_root(fo, s_z[s_base[tid] + br], E);
+      geom::essential_candidates(E, Ra, Rb, tt);
       geom::candidate_model(Ra, Rb, tt, bc, M);
 #pragma unroll
       for (int i = 0; i < 12; ++i) s_mod[12 * tid + i] = M[i];
@@ -508,13 +557,18 @@ void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem();
+  const size_t sm2 = sizeof(double) * geom::kIsoSlots * kMonoChunk;
   ensure_smem(mono_front_kernel, sm);
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
-  mono_back_kernel<<<dim3(a.P, blocks), kBackThreads, 0, s>>>(a);
+  mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, sm2, s>>>(a);
+  const size_t sm3 = sizeof(double) * (kMaxItems * 5 + kMonoChunk * 12) + sizeof(int) * (3 * kMonoChunk + 1) +
+                     kMaxItems * 3 + 16;
+  ensure_smem(mono_back_kernel, sm3);
+  mono_back_kernel<<<dim3(a.P, blocks), kBackThreads, sm3, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
-  return 3;
+  return 4;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;

@@ -327,8 +327,8 @@ static inline int sturm_count(const Sturm* st, double x) {
 
 static const int kRootGrid = 32;    // sign-test cells on (-1,1]
 static const int kRootDepth = 48;   // max Sturm bisection depth per root
-static const int kRootBisect = 10;  // sign bisection steps on the isolated bracket
-static const int kRootNewton = 8;   // bracketed Newton steps that follow
+static const int kRootBisect = 6;   // sign bisection steps on the isolated bracket
+static const int kRootNewton = 6;   // bracketed Newton steps that follow
 
 // Real roots of p (degree n<=10) in (-1,1], ascending.  Root j (rank from the
 // left) is isolated on its own by bisection on the Sturm count, then refined

@@ -14,6 +14,13 @@
 namespace kml {
 
 typedef std::pair<uint64_t, uint64_t> RobotPoseId;
+struct RobotPoseHash {
+  size_t operator()(const RobotPoseId& id) const {
+    uint64_t x = id.first * 0x9E3779B97F4A7C15ull ^ (id.second + 0x7F4A7C15ull + (id.first << 6));
+    x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29;
+    return (size_t)x;
+  }
+};
 
 struct HostBow {
   std::vector<uint32_t> ids;
@@ -61,7 +68,7 @@ struct kml_handle {
   kml::DevBuf<int32_t> d_maxid;
 
   // ---- frame store (feature arenas in HBM)
-  std::map<kml::RobotPoseId, kml::FrameRec> frames;
+  std::unordered_map<kml::RobotPoseId, kml::FrameRec, kml::RobotPoseHash> frames;
   std::vector<int64_t> frame_off_h;  // per dense frame index
   std::vector<int32_t> frame_F_h;
   int64_t n_feat = 0;

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -625,6 +627,13 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
   KML_CUDA(cudaEventRecord(h->ev[7], h->stream));
   KML_CUDA(cudaEventSynchronize(h->ev[7]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_total, h->ev[6], h->ev[7]));
+  if (getenv("KML_DEBUG_TIMING")) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->ev[6], h->ev[0]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&c, h->ev[5], h->ev[7]);
+    fprintf(stderr, "[kml] gaps: before bow %.3f ms, bow->match %.3f ms, after stereo %.3f ms\n", a, b, c);
+  }
   return KML_OK;
 }
 

@@ -97,6 +97,8 @@ typedef struct kml_stats {
   float ms_bow, ms_match, ms_mono, ms_stereo, ms_total;
   uint64_t bow_postings_last; /* inverted-file postings touched by the last batch */
   uint64_t mono_hypotheses_last, stereo_hypotheses_last, pairs_last;
+  /* sum over problems of (draws consumed x correspondences): residual evaluations of the reference loop */
+  uint64_t mono_residuals_last, stereo_residuals_last;
 } kml_stats;
 
 typedef struct kml_handle kml_handle;

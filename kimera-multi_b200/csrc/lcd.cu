@@ -494,6 +494,8 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   KML_CUDA(cudaEventRecord(h->ev[5], s));
   // ---- results back
   std::vector<SacState> stm(P), sts(P);
+  std::vector<int32_t> n3(P);
+  KML_CUDA(cudaMemcpyAsync(n3.data(), h->d_N3.p, 4 * P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(out->status.data(), h->d_status.p, 4 * P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(out->M.data(), h->d_M.p, 4 * P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(out->mono_inl.data(), h->d_out_mono.p, 4 * P, cudaMemcpyDeviceToHost, s));
@@ -506,16 +508,20 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
-  uint64_t hm = 0, hs = 0, nmono_ok = 0;
+  uint64_t hm = 0, hs = 0, nmono_ok = 0, rm = 0, rs = 0;
   bool exhausted = false;
   for (int p = 0; p < P; ++p) {
     hm += (uint64_t)stm[p].draws;
     hs += (uint64_t)sts[p].draws;
+    rm += (uint64_t)stm[p].draws * (uint64_t)out->M[p];
+    rs += (uint64_t)sts[p].draws * (uint64_t)n3[p];
     exhausted |= stm[p].exhausted || sts[p].exhausted;
     nmono_ok += out->status[p] != 1;
   }
   h->stats.mono_hypotheses_last = hm;
   h->stats.stereo_hypotheses_last = hs;
+  h->stats.mono_residuals_last = rm;
+  h->stats.stereo_residuals_last = rs;
   h->stats.total_geom_verifications_mono += P;
   h->stats.total_geometric_verifications += nmono_ok;
   if (exhausted) throw std::runtime_error("pre-drawn sample stream exhausted (too many skipped samples)");
@@ -1117,7 +1123,8 @@ static int ransac_batch(kml_handle* h, bool mono, int P, int N, const double* a,
       for (int w = 0; w < std::max(words_out, 1); ++w)
         inlier_mask[(size_t)p * std::max(words_out, 1) + w] = w < words_out ? mask[(size_t)p * mask_words + w] : 0u;
   }
-  if (mono) h->stats.mono_hypotheses_last = draws; else h->stats.stereo_hypotheses_last = draws;
+  if (mono) { h->stats.mono_hypotheses_last = draws; h->stats.mono_residuals_last = draws * (uint64_t)N; }
+  else { h->stats.stereo_hypotheses_last = draws; h->stats.stereo_residuals_last = draws * (uint64_t)N; }
   h->stats.pairs_last = P;
   return KML_OK;
 }

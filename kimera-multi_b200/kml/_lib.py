@@ -62,6 +62,7 @@ class Stats(C.Structure):
         ("bow_postings_last", C.c_uint64),
         ("mono_hypotheses_last", C.c_uint64), ("stereo_hypotheses_last", C.c_uint64),
         ("pairs_last", C.c_uint64),
+        ("mono_residuals_last", C.c_uint64), ("stereo_residuals_last", C.c_uint64),
     ]
 
 

@@ -139,8 +139,8 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
           S(c * 20 + j) = S(pr * 20 + j);
           S(pr * 20 + j) = t;
         }
-      const double piv = S(c * 20 + c);
-      for (int j = c; j < 20; ++j) S(c * 20 + j) = kdiv(S(c * 20 + j), piv);
+      const double inv = kdiv(1.0, S(c * 20 + c));  // pivot row scaled by the reciprocal
+      for (int j = c; j < 20; ++j) S(c * 20 + j) = S(c * 20 + j) * inv;
       for (int r = 0; r < 10; ++r) {
         if (r == c) continue;
         const double f = S(r * 20 + c);

@@ -475,8 +475,8 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
     if (!(pv > 0.0)) return 0;  // singular constraint system
     if (pr != c)
       for (int j = 0; j < 20; ++j) { double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
-    double piv = A[c][c];
-    for (int j = 0; j < 20; ++j) A[c][j] = A[c][j] / piv;
+    const double inv = 1.0 / A[c][c];  // pivot row scaled by the reciprocal (one division per pivot)
+    for (int j = 0; j < 20; ++j) A[c][j] = A[c][j] * inv;
     for (int r = 0; r < 10; ++r) {
       if (r == c) continue;
       double f = A[r][c];

@@ -15,7 +15,7 @@ for l in sass[start + 1:]:
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m: seq[int(m.group(1), 16)] = cur
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + kernel], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split('\n')))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 hdr = rows[hi]; data = []

@@ -1,0 +1,102 @@
+"""GPU tests at BASELINE.json's sizes.  Where the oracle is too slow for a full
+comparison the checks are oracle parity on a SUBSAMPLE plus size-independent
+properties (planted exact matches, sortedness, mask/count consistency, model
+reproduces its own inlier set, determinism)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c3_hamming_sweep_one_million(oracle, gpu_lcd):
+    rng = np.random.default_rng(21)
+    nq, nt = 500, 1_000_000
+    q = rng.integers(0, 256, (nq, 32), np.uint8)
+    t = rng.integers(0, 256, (nt, 32), np.uint8)
+    plant = rng.choice(nt, nq, replace=False)
+    t[plant[:250]] = q[:250]                       # exact hits for half of the queries
+    idx, dist, ms = gpu_lcd.hamming_knn2(q, t)
+    assert (dist[:250, 0] == 0).all() and np.array_equal(idx[:250, 0], plant[:250].astype(np.uint32))
+    assert (dist[:, 0] <= dist[:, 1]).all() and (idx < nt).all()
+    assert (idx[:, 0] != idx[:, 1]).all()
+    sub = np.r_[0:8, 250:258]                      # oracle parity on 16 queries x 1M
+    i0, d0 = oracle.hamming_knn2(q[sub], t)
+    assert np.array_equal(i0, idx[sub]) and np.array_equal(d0, dist[sub])
+    idx2, dist2, _ = gpu_lcd.hamming_knn2(q, t)    # deterministic
+    assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+
+
+def _stereo_problems(P, N, rng):
+    from scipy.spatial.transform import Rotation as Rot
+    p1 = np.zeros((P, N, 3)); p2 = np.zeros((P, N, 3)); Rs = []
+    for p in range(P):
+        X = np.c_[rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(2, 12, N)]
+        R = Rot.from_rotvec(rng.normal(size=3) * 0.2).as_matrix(); t = rng.uniform(-1, 1, 3)
+        X2 = (X - t) @ R + rng.normal(size=X.shape) * 0.03
+        out = rng.random(N) < 0.35
+        X2[out] = rng.uniform(-8, 8, (int(out.sum()), 3))
+        p1[p], p2[p] = X, X2
+        Rs.append(R)
+    return p1, p2, np.array(Rs)
+
+
+def test_c4_stereo_ransac_batch_full_hypotheses(oracle, gpu_lcd):
+    """C4 shape (1 001 hypotheses x 500 correspondences, fp64) on 512 problems."""
+    from kml import mask_to_indices
+    rng = np.random.default_rng(22)
+    P, N = 512, 500
+    p1, p2, Rs = _stereo_problems(P, N, rng)
+    g = gpu_lcd.ransac_arun_batch(p1, p2, full_hypotheses=True)
+    assert (g["iterations"] == 1001).all() and (g["best_draw"] >= 0).all()
+    for p in range(0, P, 37):
+        inl = mask_to_indices(g["mask"][p], N)
+        assert len(inl) == g["n_inliers"][p] >= 250
+        M = g["models"][p]
+        res = np.linalg.norm(p1[p] - (p2[p] @ M[:, :3].T + M[:, 3]), axis=1)
+        assert set(np.nonzero(res < 0.5 - 1e-9)[0]) <= set(inl) <= set(np.nonzero(res < 0.5 + 1e-9)[0])
+        assert np.abs(M[:, :3] @ M[:, :3].T - np.eye(3)).max() < 1e-12 and np.abs(M[:, :3] - Rs[p]).max() < 0.05
+    # the adaptive run must agree with the oracle's sequential loop bit for bit (subsample)
+    ga = gpu_lcd.ransac_arun_batch(p1, p2, full_hypotheses=False)
+    for p in range(0, P, 64):
+        o = oracle.ransac_arun(p1[p], p2[p], 0.5, 0.995, 1000, 12345)
+        assert o["iterations"] == ga["iterations"][p] and o["best_draw"] == ga["best_draw"][p]
+        assert np.array_equal(o["inliers"], mask_to_indices(ga["mask"][p], N))
+        assert np.abs(o["model"] - ga["models"][p]).max() <= 1e-6
+        # the full run can only find an equal or better model than the adaptive one
+        assert g["n_inliers"][p] >= ga["n_inliers"][p]
+
+
+def test_c2_shaped_batch_against_oracle(oracle):
+    """3 robots x 2 000 keyframes, 32-query batch, every record against the oracle."""
+    import kml
+    from kml import synth
+    from conftest import fill
+    world = synth.World(500, F=500)
+    chunks = list(synth.build_database(world, range(3), 2000, chunk=1000))
+    det, ref = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    fill(det, chunks, bulk=True)
+    fill(ref, chunks)
+    q = synth.make_queries(world, 32, 2000, 3)
+    fq, fp = q["frames"], q["prev"]
+    args = (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    out1, cnt1 = det.query_batch(*args)
+    out0, cnt0 = ref.query_batch(*args)
+    assert np.array_equal(cnt0, cnt1)
+    n_lc = 0
+    for b in range(32):
+        for i in range(cnt0[b]):
+            a, g = out0[b, i], out1[b, i]
+            for k in ("m_robot", "m_pose", "n_matches", "mono_inliers", "stereo_inliers", "status"):
+                assert a[k] == g[k], (b, i, k)
+            assert abs(a["norm_bow_score"] - g["norm_bow_score"]) <= 1e-6 * abs(a["norm_bow_score"])
+            if a["status"] == 0:
+                n_lc += 1
+                assert np.abs(a["T"] - g["T"]).max() <= 1e-6
+                # the recovered pose is close to the generator's ground truth
+                ch = chunks[int(a["m_robot"]) * 2 + int(a["m_pose"]) // 1000]
+                Rgt, tgt = synth.relative_pose(fq, b, ch, int(a["m_pose"]) % 1000)
+                T = np.asarray(g["T"]).reshape(3, 4)
+                assert np.abs(T[:, :3] - Rgt).max() < 0.2 and np.abs(T[:, 3] - tgt).max() < 1.0   # 3-point model, noise-limited
+    assert n_lc >= 32 * 4
+    det.close()

@@ -207,6 +207,18 @@ int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const
                             int32_t* iterations, int32_t* best_draw, uint32_t* inlier_mask,
                             float* ms_kernel);
 
+/* ---- vocabulary transform (the step right before the path) ---
+ * DBoW2::TemplatedVocabulary with k children per node and L levels (mit_voc.yml /
+ * ORBvoc: k=10, L=6), TF-IDF weighting, L1 scoring.  node_desc[n_nodes][32] in
+ * breadth-first order (the k level-1 nodes first, then k^2, ...; the children of
+ * node i of a level are nodes i*k .. i*k+k-1 of the next); word id = index of the
+ * leaf within the last level; word_weights[k^L] = the leaves' IDF weights. */
+int kml_vocab_set(kml_handle* h, int k, int L, const uint8_t* node_desc, const double* word_weights);
+/* TemplatedVocabulary::transform(features, BowVector) for B frames of F descriptors:
+ * CSR output (out_off[B+1]; word ids ascending; L1-normalised TF-IDF values). */
+int kml_transform_batch(kml_handle* h, int B, int F, const uint8_t* desc, int64_t* out_off,
+                        uint32_t* out_ids, double* out_vals, int64_t cap, float* ms_kernel);
+
 /* microbenchmarks for the roofline denominators (ops per second) */
 int kml_peak_popc(kml_handle* h, double* popc32_per_s);
 int kml_peak_fp64(kml_handle* h, double* flop_per_s);

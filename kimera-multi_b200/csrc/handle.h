@@ -115,5 +115,11 @@ struct kml_handle {
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
   kml::DevBuf<uint8_t> d_scratch, d_scratch2;
 
+  // ---- vocabulary tree (row f1: TemplatedVocabulary::transform)
+  int voc_k = 0, voc_L = 0;
+  uint64_t voc_words = 0, voc_nodes = 0;
+  kml::DevBuf<uint8_t> d_voc_nodes;  // [nodes][32], breadth-first, level 1 first
+  kml::DevBuf<double> d_voc_w;       // [k^L] word weights (IDF)
+
   kml::Comm* comm = nullptr;
 };

@@ -320,6 +320,26 @@ class LoopClosureDetector:
         self._check(lib().kml_peak_popc(self._h, C.byref(out)))
         return out.value
 
+    # ------------------------------------------------ vocabulary (row f1)
+    def setVocabulary(self, k, L, node_desc, word_weights):
+        """OrbVocabulary: k-ary tree of L levels, nodes breadth-first, IDF weight per leaf (= word)."""
+        node_desc, word_weights = _u8(node_desc), _f64(word_weights)
+        self._check(lib().kml_vocab_set(self._h, int(k), int(L), _p(node_desc, C.c_uint8),
+                                        _p(word_weights, C.c_double)))
+
+    def transform(self, desc):
+        """TemplatedVocabulary::transform for [B, F, 32] descriptors -> (off[B+1], ids, vals, ms)."""
+        desc = _u8(desc)
+        B, F = desc.shape[0], desc.shape[1]
+        off = np.zeros(B + 1, np.int64)
+        ids = np.zeros(max(B * F, 1), np.uint32)
+        vals = np.zeros(max(B * F, 1), np.float64)
+        ms = C.c_float(0)
+        self._check(lib().kml_transform_batch(self._h, B, F, _p(desc, C.c_uint8), _p(off, C.c_int64),
+                                              _p(ids, C.c_uint32), _p(vals, C.c_double), C.c_int64(B * F),
+                                              C.byref(ms)))
+        return off, ids[:off[-1]].copy(), vals[:off[-1]].copy(), ms.value
+
     def flush_l2(self):
         self._check(lib().kml_flush_l2(self._h))
 

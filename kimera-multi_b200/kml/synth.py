@@ -166,3 +166,15 @@ def make_queries(world, B, n_keyframes, n_robots, key=0, robots=None):
     fq = world.frames(1000 + key, q_pose, places=places, key=1)
     fp = world.frames(1000 + key, q_pose - 1, places=places, key=2)
     return dict(q_robot=q_robot, q_pose=q_pose, places=places, frames=fq, prev=fp)
+
+
+def make_vocabulary(k=10, L=6, key=0):
+    """Synthetic DBoW2 vocabulary tree: random 256-bit node descriptors in
+    breadth-first order (level 1 first) and a log-uniform IDF weight in [0.5, 8] per leaf;
+    2 % of the words get weight 0 (DBoW2 drops words seen in every training image)."""
+    r = _rng(4, key)
+    n_nodes = sum(k ** l for l in range(1, L + 1))
+    nodes = r.integers(0, 256, (n_nodes, 32), dtype=np.uint8)
+    w = np.exp(r.uniform(np.log(0.5), np.log(8.0), k ** L))
+    w[r.random(k ** L) < 0.02] = 0.0
+    return nodes, w

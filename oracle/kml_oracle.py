@@ -333,5 +333,28 @@ class LoopClosureDetector:
         return out, counts
 
 
+class Vocabulary:
+    """DBoW2::TemplatedVocabulary::transform restatement (SURVEY.md A.9)."""
+
+    def __init__(self, k, L, node_desc, word_weights):
+        node_desc, word_weights = _u8(node_desc), _f64(word_weights)
+        lib().kmo_vocab_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().kmo_vocab_create(int(k), int(L), _p(node_desc, C.c_uint8),
+                                                    _p(word_weights, C.c_double)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().kmo_vocab_destroy(self._h)
+            self._h = None
+
+    def transform(self, desc):
+        desc = _u8(desc).reshape(-1, 32)
+        ids = np.zeros(max(len(desc), 1), np.uint32)
+        vals = np.zeros(max(len(desc), 1), np.float64)
+        n = lib().kmo_vocab_transform(self._h, _p(desc, C.c_uint8), len(desc), _p(ids, C.c_uint32),
+                                      _p(vals, C.c_double))
+        return ids[:n].copy(), vals[:n].copy()
+
+
 def num_threads():
     return lib().kmo_num_threads()

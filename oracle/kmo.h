@@ -121,6 +121,11 @@ void kmo_ransac_nister(const double* f1, const double* f2, int N, double thr,
 typedef struct kmo_lcd kmo_lcd;
 kmo_lcd* kmo_lcd_create(const kmo_params*);
 void kmo_lcd_destroy(kmo_lcd*);
+/* ---- A.9 TemplatedVocabulary::transform (row f1) ---- */
+typedef struct kmo_vocab kmo_vocab;
+kmo_vocab* kmo_vocab_create(int k, int L, const uint8_t* node_desc, const double* word_weights);
+void kmo_vocab_destroy(kmo_vocab*);
+int kmo_vocab_transform(const kmo_vocab*, const uint8_t* desc, int F, uint32_t* ids, double* vals);
 void kmo_lcd_add_bow(kmo_lcd*, uint64_t robot, uint64_t pose,
                      const uint32_t* ids, const float* vals, int n);
 void kmo_lcd_add_frame(kmo_lcd*, uint64_t robot, uint64_t pose,

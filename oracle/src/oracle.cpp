@@ -682,3 +682,55 @@ int kmo_lcd_query_batch(kmo_lcd* L, int B, const uint64_t* q_robot, const uint64
 
 // exposed for tests: real roots of a polynomial (ascending coefficients) in (-1,1]
 extern "C" int kmo_roots_unit(const double* p, int n, double* roots) { return roots_unit(p, n, roots); }
+
+// =========================================================================
+// A.9  TemplatedVocabulary::transform (DBoW2/include/DBoW2/TemplatedVocabulary.h,
+//      BowVector::addWeight / normalize in DBoW2/src/BowVector.cpp) — row f1
+// =========================================================================
+struct kmo_vocab {
+  int k, L;
+  std::vector<uint8_t> nodes;    // breadth-first, level 1 first
+  std::vector<double> weights;   // per leaf
+};
+extern "C" kmo_vocab* kmo_vocab_create(int k, int L, const uint8_t* node_desc, const double* w) {
+  kmo_vocab* v = new kmo_vocab();
+  v->k = k; v->L = L;
+  size_t nodes = 0, lvl = 1;
+  for (int l = 0; l < L; ++l) { lvl *= (size_t)k; nodes += lvl; }
+  v->nodes.assign(node_desc, node_desc + nodes * 32);
+  v->weights.assign(w, w + lvl);
+  return v;
+}
+extern "C" void kmo_vocab_destroy(kmo_vocab* v) { delete v; }
+extern "C" int kmo_vocab_transform(const kmo_vocab* voc, const uint8_t* desc, int F, uint32_t* ids, double* vals) {
+  std::map<uint32_t, double> v;
+  for (int f = 0; f < F; ++f) {
+    size_t idx = 0, level_off = 0, level_n = 1;
+    for (int l = 0; l < voc->L; ++l) {
+      level_n *= (size_t)voc->k;
+      const uint8_t* children = voc->nodes.data() + 32 * (level_off + idx * (size_t)voc->k);
+      int best = hamming256(desc + 32 * f, children), bc = 0;
+      for (int c = 1; c < voc->k; ++c) {
+        const int d = hamming256(desc + 32 * f, children + 32 * c);
+        if (d < best) { best = d; bc = c; }
+      }
+      idx = idx * (size_t)voc->k + (size_t)bc;
+      level_off += level_n;
+    }
+    const double w = voc->weights[idx];
+    if (w > 0) {  // BowVector::addWeight
+      auto it = v.lower_bound((uint32_t)idx);
+      if (it != v.end() && !(v.key_comp()((uint32_t)idx, it->first))) it->second += w;
+      else v.insert(it, std::make_pair((uint32_t)idx, w));
+    }
+  }
+  double norm = 0.0;  // BowVector::normalize(L1)
+  for (auto& kv : v) norm += std::fabs(kv.second);
+  int n = 0;
+  for (auto& kv : v) {
+    ids[n] = kv.first;
+    vals[n] = norm > 0.0 ? kv.second / norm : kv.second;
+    ++n;
+  }
+  return n;
+}

@@ -74,6 +74,9 @@ typedef struct kml_params {
   int32_t ransac_randomize; /* must be 0: the sample stream is pre-drawn */
   uint32_t ransac_seed;     /* 12345 = OpenGV's fixed seed */
   int32_t top_k_verify;     /* benchmark knob: candidates verified per query */
+  int32_t matcher_norm;     /* 0 = NORM_HAMMING (BASELINE.json north_star, default); 1 = NORM_L1 over the 32
+                             * descriptor bytes = what upstream's DescriptorMatcher::create(3) really selects
+                             * (kimera_multi_lcd.patch:34-35) */
 } kml_params;
 
 /* One verified candidate (VLCEdge of kimera_distributed + the counters the
@@ -187,6 +190,9 @@ int kml_query_batch_run(kml_handle* h, kml_result* out, int cap_per_query, int32
  * receives the device time of the matching kernels. */
 int kml_hamming_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
                      uint32_t* idx, uint16_t* dist, float* ms_kernel);
+/* cv::BFMatcher(NORM_L1).knnMatch(q, t, k=2) on the descriptor bytes (dist <= 8160) */
+int kml_l1_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+                uint32_t* idx, uint16_t* dist, float* ms_kernel);
 /* resident variant for roofline measurement: upload once, run `reps` times */
 int kml_hamming_knn2_bench(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t,
                            int64_t nt, int reps, uint32_t* idx, uint16_t* dist, float* ms_avg);

@@ -53,6 +53,7 @@ void kml_default_params(kml_params* p) {
   p->ransac_randomize = 0;
   p->ransac_seed = 12345u;
   p->top_k_verify = 16;
+  p->matcher_norm = 0;
 }
 
 int kml_device_count(void) {
@@ -91,6 +92,11 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
     if (p) h->prm = *p; else kml_default_params(&h->prm);
     if (h->prm.ransac_randomize != 0) {
       g_create_err = "ransac_randomize must be 0 (pre-drawn sample stream)";
+      delete h;
+      return KML_ERR_ARG;
+    }
+    if (h->prm.matcher_norm != 0 && h->prm.matcher_norm != 1) {
+      g_create_err = "matcher_norm must be 0 (HAMMING) or 1 (L1)";
       delete h;
       return KML_ERR_ARG;
     }
@@ -146,12 +152,12 @@ int kml_get_stats(kml_handle* h, kml_stats* out) {
 }
 
 // ------------------------------------------------------------- Hamming kNN
-static void knn2_device(kml_handle* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int64_t nt,
+static void knn2_device(kml_handle* h, int norm, const uint8_t* d_q, int nq, const uint8_t* d_t, int64_t nt,
                         uint32_t* d_idx, uint16_t* d_dist, int reps, float* ms_avg) {
   // split the train set into ranges (one CTA each); >= 2 CTAs per SM when large
   int64_t range_len = (nt + 2 * kNumSMs - 1) / (2 * kNumSMs);
   range_len = ((range_len + 511) / 512) * 512;
-  range_len = std::max<int64_t>(512, std::min<int64_t>(range_len, 1 << 20));
+  range_len = std::max<int64_t>(512, std::min<int64_t>(range_len, (int64_t)1 << knn_key_shift(norm)));
   const int nranges = nt > 0 ? (int)((nt + range_len - 1) / range_len) : 1;
   h->d_keys.scratch((size_t)nranges * nq * 2);
   std::vector<HamJob> jobs(nranges);
@@ -169,8 +175,8 @@ static void knn2_device(kml_handle* h, const uint8_t* d_q, int nq, const uint8_t
   float total = 0.f;
   for (int rep = 0; rep < reps; ++rep) {
     KML_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    launch_hamming_jobs(h->d_jobs.p, nranges, h->stream);
-    launch_knn2_reduce(h->d_keys.p, nranges, nq, range_len, d_idx, d_dist, h->stream);
+    launch_hamming_jobs(h->d_jobs.p, nranges, norm, h->stream);
+    launch_knn2_reduce(h->d_keys.p, nranges, nq, range_len, norm, d_idx, d_dist, h->stream);
     KML_CUDA(cudaEventRecord(h->ev[1], h->stream));
     KML_CUDA(cudaGetLastError());
     KML_CUDA(cudaEventSynchronize(h->ev[1]));
@@ -182,7 +188,7 @@ static void knn2_device(kml_handle* h, const uint8_t* d_q, int nq, const uint8_t
   if (ms_avg) *ms_avg = total / std::max(reps, 1);
 }
 
-static int knn2_host(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
+static int knn2_host(kml_handle* h, int norm, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
                      int reps, uint32_t* idx, uint16_t* dist, float* ms) {
   if (nq < 0 || nt < 0 || (nq > 0 && !q) || (nt > 0 && !t) || !idx || !dist) {
     h->err = "kml_hamming_knn2: bad argument";
@@ -198,7 +204,7 @@ static int knn2_host(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, 
   DevBuf<uint16_t> d_dist;
   d_idx.scratch((size_t)nq * 2);
   d_dist.scratch((size_t)nq * 2);
-  knn2_device(h, h->d_scratch.p, nq, h->d_scratch2.p, nt, d_idx.p, d_dist.p, reps, ms);
+  knn2_device(h, norm, h->d_scratch.p, nq, h->d_scratch2.p, nt, d_idx.p, d_dist.p, reps, ms);
   KML_CUDA(cudaMemcpyAsync(idx, d_idx.p, sizeof(uint32_t) * nq * 2, cudaMemcpyDeviceToHost, h->stream));
   KML_CUDA(cudaMemcpyAsync(dist, d_dist.p, sizeof(uint16_t) * nq * 2, cudaMemcpyDeviceToHost, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
@@ -208,14 +214,21 @@ static int knn2_host(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, 
 int kml_hamming_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
                      uint32_t* idx, uint16_t* dist, float* ms_kernel) {
   KML_API_BEGIN(h)
-  return knn2_host(h, q, nq, t, nt, 1, idx, dist, ms_kernel);
+  return knn2_host(h, 0, q, nq, t, nt, 1, idx, dist, ms_kernel);
   KML_API_END(h)
 }
 
 int kml_hamming_knn2_bench(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt,
                            int reps, uint32_t* idx, uint16_t* dist, float* ms_avg) {
   KML_API_BEGIN(h)
-  return knn2_host(h, q, nq, t, nt, std::max(reps, 1), idx, dist, ms_avg);
+  return knn2_host(h, 0, q, nq, t, nt, std::max(reps, 1), idx, dist, ms_avg);
+  KML_API_END(h)
+}
+
+int kml_l1_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64_t nt, uint32_t* idx,
+                uint16_t* dist, float* ms_kernel) {
+  KML_API_BEGIN(h)
+  return knn2_host(h, 1, q, nq, t, nt, 1, idx, dist, ms_kernel);
   KML_API_END(h)
 }
 

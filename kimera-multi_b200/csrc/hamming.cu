@@ -22,18 +22,29 @@ namespace kml {
 constexpr int kHamThreads = 512;
 constexpr int kHamTile = 512;  // train descriptors per shared-memory stage
 
+// L1 = false: NORM_HAMMING (8 x LOP3 + POPC, key = dist << 20 | idx);
+// L1 = true : NORM_L1 over the 32 bytes (8 x VABSDIFF4 sum-of-absolute-differences, dist <= 8160,
+//             key = dist << 18 | idx) — what upstream's cv::DescriptorMatcher::create(3) selects
+//             (/root/reference/docker/copy/kimera_multi_lcd.patch:34-35).
+template <bool L1>
 __device__ __forceinline__ void ham_update(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3,
                                            uint32_t q4, uint32_t q5, uint32_t q6, uint32_t q7,
                                            const uint4& a, const uint4& b, uint32_t idx,
                                            uint32_t& best, uint32_t& second) {
-  uint32_t d = __popc(q0 ^ a.x) + __popc(q1 ^ a.y) + __popc(q2 ^ a.z) + __popc(q3 ^ a.w) +
-               __popc(q4 ^ b.x) + __popc(q5 ^ b.y) + __popc(q6 ^ b.z) + __popc(q7 ^ b.w);
-  uint32_t key = (d << 20) | idx;
+  uint32_t d;
+  if (L1)
+    d = __vsadu4(q0, a.x) + __vsadu4(q1, a.y) + __vsadu4(q2, a.z) + __vsadu4(q3, a.w) +
+        __vsadu4(q4, b.x) + __vsadu4(q5, b.y) + __vsadu4(q6, b.z) + __vsadu4(q7, b.w);
+  else
+    d = __popc(q0 ^ a.x) + __popc(q1 ^ a.y) + __popc(q2 ^ a.z) + __popc(q3 ^ a.w) +
+        __popc(q4 ^ b.x) + __popc(q5 ^ b.y) + __popc(q6 ^ b.z) + __popc(q7 ^ b.w);
+  uint32_t key = (d << (L1 ? 18 : 20)) | idx;
   uint32_t mx = max(best, key);
   best = min(best, key);
   second = min(second, mx);
 }
 
+template <bool L1>
 __global__ void __launch_bounds__(kHamThreads, 2) hamming_knn2_kernel(const HamJob* __restrict__ jobs) {
   __shared__ __align__(128) uint4 tile[2][kHamTile * 2];
   __shared__ __align__(8) uint64_t full[2];
@@ -80,14 +91,14 @@ __global__ void __launch_bounds__(kHamThreads, 2) hamming_knn2_kernel(const HamJ
         uint4 a1 = tp[2 * j + 2], b1 = tp[2 * j + 3];
         uint4 a2 = tp[2 * j + 4], b2 = tp[2 * j + 5];
         uint4 a3 = tp[2 * j + 6], b3 = tp[2 * j + 7];
-        ham_update(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a0, b0, base + j + 0, best, second);
-        ham_update(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a1, b1, base + j + 1, best, second);
-        ham_update(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a2, b2, base + j + 2, best, second);
-        ham_update(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a3, b3, base + j + 3, best, second);
+        ham_update<L1>(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a0, b0, base + j + 0, best, second);
+        ham_update<L1>(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a1, b1, base + j + 1, best, second);
+        ham_update<L1>(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a2, b2, base + j + 2, best, second);
+        ham_update<L1>(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a3, b3, base + j + 3, best, second);
       }
       for (; j < n; ++j) {
         uint4 a0 = tp[2 * j + 0], b0 = tp[2 * j + 1];
-        ham_update(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a0, b0, base + j, best, second);
+        ham_update<L1>(qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w, a0, b0, base + j, best, second);
       }
       __syncthreads();  // everyone is done with this stage before it is refilled
     }
@@ -101,7 +112,7 @@ __global__ void __launch_bounds__(kHamThreads, 2) hamming_knn2_kernel(const HamJ
 // Merge per-range top-2 keys of the sweep (config C3) into BFMatcher output.
 // partial: [nranges][nq][2]; range r covers train indices [r*range_len, ...).
 __global__ void knn2_reduce_kernel(const uint32_t* __restrict__ partial, int nranges, int nq,
-                                   int64_t range_len, uint32_t* __restrict__ idx,
+                                   int64_t range_len, int shift, uint32_t* __restrict__ idx,
                                    uint16_t* __restrict__ dist) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
@@ -110,8 +121,9 @@ __global__ void knn2_reduce_kernel(const uint32_t* __restrict__ partial, int nra
     const uint32_t k0 = partial[((size_t)r * nq + qi) * 2 + 0];
     const uint32_t k1 = partial[((size_t)r * nq + qi) * 2 + 1];
     const uint64_t off = (uint64_t)r * (uint64_t)range_len;
-    uint64_t g0 = (k0 == 0xFFFFFFFFu) ? ~0ull : (((uint64_t)(k0 >> 20) << 40) | (off + (k0 & 0xFFFFFu)));
-    uint64_t g1 = (k1 == 0xFFFFFFFFu) ? ~0ull : (((uint64_t)(k1 >> 20) << 40) | (off + (k1 & 0xFFFFFu)));
+    const uint32_t im = (1u << shift) - 1u;
+    uint64_t g0 = (k0 == 0xFFFFFFFFu) ? ~0ull : (((uint64_t)(k0 >> shift) << 40) | (off + (k0 & im)));
+    uint64_t g1 = (k1 == 0xFFFFFFFFu) ? ~0ull : (((uint64_t)(k1 >> shift) << 40) | (off + (k1 & im)));
     uint64_t mx = max(best, g0);
     best = min(best, g0);
     second = min(min(second, mx), g1);
@@ -127,7 +139,7 @@ __global__ void knn2_reduce_kernel(const uint32_t* __restrict__ partial, int nra
 // One CTA per pair; output ascending in query index.
 __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __restrict__ keys,
                                                            const int* __restrict__ nq_arr,
-                                                           int key_stride, double lowe,
+                                                           int key_stride, double lowe, int shift,
                                                            uint16_t* __restrict__ iq,
                                                            uint16_t* __restrict__ im,
                                                            int* __restrict__ M) {
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __res
       k0 = kp[2 * qi];
       const uint32_t k1 = kp[2 * qi + 1];
       if (k1 != 0xFFFFFFFFu) {
-        const double d0 = (double)(float)(k0 >> 20), d1 = (double)(float)(k1 >> 20);
+        const double d0 = (double)(float)(k0 >> shift), d1 = (double)(float)(k1 >> shift);
         keep = d0 < lowe * d1;
       }
     }
@@ -161,7 +173,7 @@ __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __res
     if (keep) {
       const int pos = off + __popc(bal & ((1u << lane) - 1u));
       oq[pos] = (uint16_t)qi;
-      om[pos] = (uint16_t)(k0 & 0xFFFFFu);
+      om[pos] = (uint16_t)(k0 & ((1u << shift) - 1u));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -174,19 +186,20 @@ __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __res
   if (threadIdx.x == 0) M[p] = base_s;
 }
 
-void launch_hamming_jobs(const HamJob* d_jobs, int njobs, cudaStream_t s) {
+void launch_hamming_jobs(const HamJob* d_jobs, int njobs, int norm, cudaStream_t s) {
   if (njobs <= 0) return;
-  hamming_knn2_kernel<<<njobs, kHamThreads, 0, s>>>(d_jobs);
+  if (norm == 1) hamming_knn2_kernel<true><<<njobs, kHamThreads, 0, s>>>(d_jobs);
+  else hamming_knn2_kernel<false><<<njobs, kHamThreads, 0, s>>>(d_jobs);
 }
-void launch_knn2_reduce(const uint32_t* partial, int nranges, int nq, int64_t range_len,
+void launch_knn2_reduce(const uint32_t* partial, int nranges, int nq, int64_t range_len, int norm,
                         uint32_t* idx, uint16_t* dist, cudaStream_t s) {
   if (nq <= 0) return;
-  knn2_reduce_kernel<<<(nq + 127) / 128, 128, 0, s>>>(partial, nranges, nq, range_len, idx, dist);
+  knn2_reduce_kernel<<<(nq + 127) / 128, 128, 0, s>>>(partial, nranges, nq, range_len, knn_key_shift(norm), idx, dist);
 }
-void launch_lowe_compact(const uint32_t* keys, const int* nq_arr, int key_stride, double lowe,
+void launch_lowe_compact(const uint32_t* keys, const int* nq_arr, int key_stride, double lowe, int norm,
                          uint16_t* iq, uint16_t* im, int* M, int P, cudaStream_t s) {
   if (P <= 0) return;
-  lowe_compact_kernel<<<P, 256, 0, s>>>(keys, nq_arr, key_stride, lowe, iq, im, M);
+  lowe_compact_kernel<<<P, 256, 0, s>>>(keys, nq_arr, key_stride, lowe, knn_key_shift(norm), iq, im, M);
 }
 
 // ------------------------------------------------------------ peak probes

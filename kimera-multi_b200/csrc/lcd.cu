@@ -453,8 +453,8 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   KML_CUDA(cudaMemsetAsync(h->d_outT.p, 0, sizeof(double) * 12 * P, s));
   // ---- computeMatchedIndices
   KML_CUDA(cudaEventRecord(h->ev[2], s));
-  launch_hamming_jobs(h->d_jobs.p, P, s);
-  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
+  launch_hamming_jobs(h->d_jobs.p, P, h->prm.matcher_norm, s);
+  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
   h->stats.kernel_launches += 2;
   KML_CUDA(cudaEventRecord(h->ev[3], s));
   // ---- geometricVerificationNister
@@ -943,8 +943,8 @@ int kml_compute_matched_indices(kml_handle* h, uint64_t qr, uint64_t qp, uint64_
   job.keys = h->d_keys.p;
   KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaMemcpyAsync(h->d_nq.p, &qs.F, 4, cudaMemcpyHostToDevice, s));
-  launch_hamming_jobs(h->d_jobs.p, 1, s);
-  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->d_iq.p, h->d_im.p, h->d_M.p, 1, s);
+  launch_hamming_jobs(h->d_jobs.p, 1, h->prm.matcher_norm, s);
+  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, 1, s);
   h->stats.kernel_launches += 2;
   KML_CUDA(cudaGetLastError());
   int32_t M = 0;

@@ -293,6 +293,16 @@ class LoopClosureDetector:
                 _p(idx, C.c_uint32), _p(dist, C.c_uint16), C.byref(ms)))
         return idx, dist, ms.value
 
+    def l1_knn2(self, q, t):
+        """cv::BFMatcher(NORM_L1).knnMatch(q, t, k=2) on descriptor bytes -> idx[nq,2], dist[nq,2], ms."""
+        q, t = _u8(q).reshape(-1, 32), _u8(t).reshape(-1, 32)
+        idx = np.zeros((len(q), 2), np.uint32)
+        dist = np.zeros((len(q), 2), np.uint16)
+        ms = C.c_float(0)
+        self._check(lib().kml_l1_knn2(self._h, _p(q, C.c_uint8), len(q), _p(t, C.c_uint8), C.c_int64(len(t)),
+                                      _p(idx, C.c_uint32), _p(dist, C.c_uint16), C.byref(ms)))
+        return idx, dist, ms.value
+
     def _ransac_batch(self, fn, a, b, full):
         a, b = _f64(a), _f64(b)
         P, N = a.shape[0], a.shape[1]

@@ -42,6 +42,7 @@ class Params(C.Structure):
         ("geometric_verification_min_inlier_percentage", C.c_double),
         ("ransac_seed", C.c_uint32),
         ("top_k_verify", C.c_int32),
+        ("matcher_norm", C.c_int32),
     ]
 
 
@@ -161,6 +162,14 @@ def hamming_knn2(q, t):
     dist = np.zeros((len(q), 2), np.uint16)
     lib().kmo_hamming_knn2(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t),
                            _p(idx, C.c_uint32), _p(dist, C.c_uint16))
+    return idx, dist
+
+
+def l1_knn2(q, t):
+    q, t = _u8(q).reshape(-1, 32), _u8(t).reshape(-1, 32)
+    idx = np.zeros((len(q), 2), np.uint32)
+    dist = np.zeros((len(q), 2), np.uint16)
+    lib().kmo_l1_knn2(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), _p(idx, C.c_uint32), _p(dist, C.c_uint16))
     return idx, dist
 
 

@@ -51,6 +51,7 @@ typedef struct kmo_params {
   double geometric_verification_min_inlier_percentage;
   uint32_t ransac_seed;
   int32_t top_k_verify;
+  int32_t matcher_norm; /* 0 NORM_HAMMING, 1 NORM_L1 (upstream's create(3)) */
 } kmo_params;
 
 void kmo_default_params(kmo_params* p);
@@ -74,6 +75,7 @@ int kmo_db_query(const kmo_db*, const uint32_t* ids, const float* vals, int n,
 /* idx/dist are [nq][2]; missing neighbours are idx=0xFFFFFFFF dist=0xFFFF */
 void kmo_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt,
                       uint32_t* idx, uint16_t* dist);
+void kmo_l1_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* idx, uint16_t* dist);
 int kmo_match_lowe(const uint8_t* q, int nq, const uint8_t* t, int nt,
                    double lowe_ratio, uint32_t* i_query, uint32_t* i_match);
 

@@ -103,13 +103,19 @@ static inline int hamming256(const uint8_t* a, const uint8_t* b) {
          __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
 }
 
+static inline int l1_32(const uint8_t* a, const uint8_t* b) {  // cv::hal::normL1 on 32 bytes
+  int d = 0;
+  for (int i = 0; i < 32; ++i) d += std::abs((int)a[i] - (int)b[i]);
+  return d;
+}
+
 static void knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* idx,
-                 uint16_t* dist) {
+                 uint16_t* dist, int norm = 0) {
   for (int i = 0; i < nq; ++i) {
     int d0 = INT_MAX, d1 = INT_MAX;
     uint32_t i0 = 0xFFFFFFFFu, i1 = 0xFFFFFFFFu;
     for (int j = 0; j < nt; ++j) {
-      int d = hamming256(q + 32 * i, t + 32 * j);
+      int d = norm == 1 ? l1_32(q + 32 * i, t + 32 * j) : hamming256(q + 32 * i, t + 32 * j);
       if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = (uint32_t)j; }
       else if (d < d1) { d1 = d; i1 = (uint32_t)j; }
     }
@@ -120,10 +126,10 @@ static void knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* i
 }
 
 static int match_lowe(const uint8_t* q, int nq, const uint8_t* t, int nt, double lowe,
-                      uint32_t* iq, uint32_t* im) {
+                      uint32_t* iq, uint32_t* im, int norm = 0) {
   std::vector<uint32_t> idx(2 * (size_t)std::max(nq, 1));
   std::vector<uint16_t> dist(2 * (size_t)std::max(nq, 1));
-  knn2(q, nq, t, nt, idx.data(), dist.data());
+  knn2(q, nq, t, nt, idx.data(), dist.data(), norm);
   int cnt = 0;
   for (int i = 0; i < nq; ++i) {
     if (idx[2 * i + 1] == 0xFFFFFFFFu) continue;  // fewer than 2 neighbours
@@ -316,7 +322,7 @@ static int verify_pair(const kmo_lcd* L, const Frame& fq, const Frame& fm, kmo_r
   const kmo_params& P = L->prm;
   // computeMatchedIndices (A.4)
   iq.resize(std::max(fq.F, 1)); im.resize(std::max(fq.F, 1));
-  int M = match_lowe(fq.desc.data(), fq.F, fm.desc.data(), fm.F, P.lowe_ratio, iq.data(), im.data());
+  int M = match_lowe(fq.desc.data(), fq.F, fm.desc.data(), fm.F, P.lowe_ratio, iq.data(), im.data(), P.matcher_norm);
   r->n_matches = M;
   r->mono_inliers = 0; r->stereo_inliers = 0; r->status = 1;
   // geometricVerificationNister (A.6)
@@ -427,6 +433,7 @@ void kmo_default_params(kmo_params* p) {
   p->geometric_verification_min_inlier_percentage = 0.0;
   p->ransac_seed = 12345u;
   p->top_k_verify = 16;
+  p->matcher_norm = 0;
 }
 
 double kmo_bow_score(const uint32_t* ids1, const float* vals1, int n1, const uint32_t* ids2,
@@ -559,7 +566,7 @@ int kmo_lcd_compute_matched_indices(kmo_lcd* L, uint64_t qr, uint64_t qp, uint64
   if (q == L->vlc_frames_.end() || m == L->vlc_frames_.end()) return 0;
   std::vector<uint32_t> iq(std::max(q->second.F, 1)), im(std::max(q->second.F, 1));
   int M = match_lowe(q->second.desc.data(), q->second.F, m->second.desc.data(), m->second.F,
-                     L->prm.lowe_ratio, iq.data(), im.data());
+                     L->prm.lowe_ratio, iq.data(), im.data(), L->prm.matcher_norm);
   M = std::min(M, cap);
   memcpy(i_query, iq.data(), sizeof(uint32_t) * M);
   memcpy(i_match, im.data(), sizeof(uint32_t) * M);
@@ -733,4 +740,8 @@ extern "C" int kmo_vocab_transform(const kmo_vocab* voc, const uint8_t* desc, in
     ++n;
   }
   return n;
+}
+
+extern "C" void kmo_l1_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* idx, uint16_t* dist) {
+  knn2(q, nq, t, nt, idx, dist, 1);
 }

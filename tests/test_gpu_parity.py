@@ -218,3 +218,41 @@ def test_ransac_batches(oracle, gpu_lcd):
     # too few correspondences: no model
     g = gpu_lcd.ransac_nister_batch(f1[:, :5], f2[:, :5])
     assert (g["best_draw"] == -1).all() and (g["n_inliers"] == 0).all()
+
+
+def test_l1_matcher_variant(oracle, small_world):
+    """matcher_norm = 1: byte-wise L1, what upstream's DescriptorMatcher::create(3) selects
+    (kimera_multi_lcd.patch:34-35) — bit-exact vs cv2.BFMatcher(NORM_L1) and the oracle."""
+    import cv2
+    import kml
+    from conftest import fill
+    world, chunks, queries = small_world
+    prm = kml.default_params()
+    prm.matcher_norm = 1
+    det = kml.LoopClosureDetector(prm)
+    rng = np.random.default_rng(17)
+    for nq, nt in [(500, 500), (64, 3000), (5, 1), (9, 0)]:
+        q = rng.integers(0, 256, (nq, 32), np.uint8)
+        t = rng.integers(0, 256, (nt, 32), np.uint8)
+        if nt > 8:
+            t[5] = t[3]
+            q[0] = t[3]
+        i1, d1, _ = det.l1_knn2(q, t)
+        i0, d0 = oracle.l1_knn2(q, t)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+        if nt >= 2:
+            m = cv2.BFMatcher(cv2.NORM_L1).knnMatch(q, t, 2)
+            ci = np.array([[x.trainIdx for x in row] for row in m], np.uint32)
+            cd = np.array([[int(x.distance) for x in row] for row in m], np.uint16)
+            assert np.array_equal(ci, i1) and np.array_equal(cd, d1)
+    oprm = oracle.default_params()
+    oprm.matcher_norm = 1
+    ref = oracle.LoopClosureDetector(oprm)
+    fill(det, chunks[:1], bulk=True)
+    fill(ref, chunks[:1])
+    for (qp, mp) in [(5, 105), (7, 40), (3, 203)]:
+        iq0, im0 = ref.computeMatchedIndices(0, qp, 0, mp)
+        iq1, im1 = det.computeMatchedIndices(0, qp, 0, mp)
+        assert np.array_equal(iq0, iq1) and np.array_equal(im0, im1)
+    assert len(iq0) > 50   # same place (3, 203): matches survive under L1 as well
+    det.close()

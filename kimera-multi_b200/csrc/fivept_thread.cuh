@@ -254,8 +254,12 @@ __device__ __noinline__ int sturm_count_s(const double* sm, unsigned long long d
 
 // Isolating brackets (lo, hi] of the real roots in (-1,1] of the chain's first
 // polynomial, ascending; returns their number R (<= 10).
+// mode 0: grid pass only — if the grid does not isolate the roots, *deferred is set and no
+// bracket is written (the rare, expensive Sturm bisection runs in a separate, compacted launch
+// so that it does not stall the other 31 lanes of every warp); mode 1: bisection on the count.
 template <int STRIDE>
-__device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, int len, double* __restrict__ brk) {
+__device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, int len, double* __restrict__ brk,
+                                           int mode, bool* deferred) {
   const int d0 = (int)(degs & 15u);
   if (d0 < 1) return 0;
   const double* c0 = sm + tri_off(0) * STRIDE;
@@ -277,6 +281,11 @@ __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, 
     fprev = fi;
   }
   const bool grid_ok = (nb == R);
+  if (mode == 0 && !grid_ok) {
+    *deferred = true;
+    return R;
+  }
+  if (mode == 1 && grid_ok) return R;  // already bracketed by the grid pass
   int cell = -1;
   for (int j = 0; j < R; ++j) {
     double lo = -1.0, hi = 1.0;
@@ -301,7 +310,8 @@ __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, 
 }
 
 // fo: this draw's stage-1 output.  Writes up to 10 + 10 brackets to brk and
-// returns R0 | R1 << 8 (0 if the draw has no usable polynomial).
+// returns R0 | R1 << 8 | deferred0 << 16 | deferred1 << 17 (0 if the draw has
+// no usable polynomial).
 template <int STRIDE>
 __device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, double* __restrict__ brk) {
 #define S(i) sm[(i) * STRIDE]
@@ -309,11 +319,25 @@ __device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, do
 #pragma unroll 1
   for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];
   unsigned long long degs;
+  bool def0 = false, def1 = false;
   int len = sturm_build_s<STRIDE>(sm, false, &degs);
-  const int R0 = isolate_unit_s<STRIDE>(sm, degs, len, brk);
+  const int R0 = isolate_unit_s<STRIDE>(sm, degs, len, brk, 0, &def0);
   len = sturm_build_s<STRIDE>(sm, true, &degs);
-  const int R1 = isolate_unit_s<STRIDE>(sm, degs, len, brk + 2 * R0);
-  return R0 | (R1 << 8);
+  const int R1 = isolate_unit_s<STRIDE>(sm, degs, len, brk + 2 * R0, 0, &def1);
+  return R0 | (R1 << 8) | ((int)def0 << 16) | ((int)def1 << 17);
+#undef S
+}
+// the deferred case of one (draw, chain): brackets by bisection on the Sturm count
+template <int STRIDE>
+__device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain,
+                                             double* __restrict__ brk) {
+#define S(i) sm[(i) * STRIDE]
+#pragma unroll 1
+  for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];
+  unsigned long long degs;
+  bool dummy = false;
+  const int len = sturm_build_s<STRIDE>(sm, chain != 0, &degs);
+  isolate_unit_s<STRIDE>(sm, degs, len, brk, 1, &dummy);
 #undef S
 }
 

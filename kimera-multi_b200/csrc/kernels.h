@@ -80,6 +80,8 @@ struct SacArgs {
   double* fsol;          // mono: [P][kRoundCap][70] stage-1 output per draw of the round
   int32_t* nroot;        // mono: [P][kRoundCap] R0 | R1<<8 real-root counts of the two chains
   double* brk;           // mono: [P][kRoundCap][20][2] isolating brackets
+  uint32_t* fb_list;     // mono: deferred root isolations of the round, slot*2 + chain
+  unsigned int* fb_count;
   uint16_t* samples;     // [P][cap_draws][S]
   int32_t* valid;        // [P][cap_draws]
   int32_t* counts;       // [P][cap_draws]

@@ -374,6 +374,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     h->d_nsol.scratch((size_t)P * kRoundCap);
     h->d_esol.scratch((size_t)P * kRoundCap * 70);
     h->d_brk.scratch((size_t)P * kRoundCap * 40);
+    h->d_fb_list.scratch((size_t)P * kRoundCap * 2 + 1);
   }
   h->d_valid.scratch((size_t)P * cap_draws);
   h->d_counts.scratch((size_t)P * cap_draws);
@@ -386,6 +387,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.raw = h->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
   a.fsol = h->d_esol.p; a.nroot = h->d_nsol.p; a.brk = h->d_brk.p;
+  a.fb_list = h->d_fb_list.p + 1; a.fb_count = h->d_fb_list.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
   a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
   a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;

@@ -199,8 +199,26 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
   const int nh = min(kMonoChunk, st.r_end - d0);
   if (tid >= nh) return;
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
-  a.nroot[slot] = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
-                                                        a.brk + slot * 2 * geom::kMaxBrackets);
+  const int nr = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
+                                                       a.brk + slot * 2 * geom::kMaxBrackets);
+  a.nroot[slot] = nr & 0xFFFF;
+  for (int chain = 0; chain < 2; ++chain)
+    if ((nr >> (16 + chain)) & 1) a.fb_list[atomicAdd(a.fb_count, 1u)] = (uint32_t)(slot * 2 + chain);
+}
+
+// Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
+// separate the roots, ~8 % of the chains): compacted work list, one item per thread.
+__global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
+  const unsigned n = *a.fb_count;
+  for (unsigned it = blockIdx.x * kMonoChunk + threadIdx.x; it < n; it += gridDim.x * kMonoChunk) {
+    const uint32_t item = a.fb_list[it];
+    const size_t slot = item >> 1;
+    const int chain = item & 1;
+    const int R0 = a.nroot[slot] & 255;
+    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * geom::kFrontOut, chain,
+                                                   a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
+  }
 }
 
 constexpr int kBackThreads = 256;
@@ -562,13 +580,15 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
+  KML_CUDA(cudaMemsetAsync(a.fb_count, 0, sizeof(unsigned int), s));
   mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, sm2, s>>>(a);
+  mono_isolate_deferred_kernel<<<kNumSMs * 4, kMonoChunk, sm2, s>>>(a);
   const size_t sm3 = sizeof(double) * (kMaxItems * 5 + kMonoChunk * 12) + sizeof(int) * (3 * kMonoChunk + 1) +
                      kMaxItems * 3 + 16;
   ensure_smem(mono_back_kernel, sm3);
   mono_back_kernel<<<dim3(a.P, blocks), kBackThreads, sm3, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
-  return 4;
+  return 5;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;

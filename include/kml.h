@@ -110,6 +110,11 @@ void kml_default_params(kml_params* p);
 /* loadAndInitialize(params) on CUDA device `device` */
 int kml_create(const kml_params* p, int device, kml_handle** out);
 int kml_destroy(kml_handle* h);
+/* A query lane: a second handle that shares `parent`'s databases, frame store and vocabulary
+ * (read-only while queries run) but owns its stream and batch buffers, so that two host threads
+ * can keep two query batches in flight on one GPU (the tail rounds of one batch's RANSAC overlap
+ * the bulk of the other's).  add* / vocab_set on any of them must not overlap queries. */
+int kml_create_lane(kml_handle* parent, kml_handle** out);
 const char* kml_last_error(const kml_handle* h); /* h may be NULL: last create error */
 int kml_get_stats(kml_handle* h, kml_stats* out);
 int kml_device_count(void);
@@ -228,6 +233,10 @@ int kml_transform_batch(kml_handle* h, int B, int F, const uint8_t* desc, int64_
 /* microbenchmarks for the roofline denominators (ops per second) */
 int kml_peak_popc(kml_handle* h, double* popc32_per_s);
 int kml_peak_fp64(kml_handle* h, double* flop_per_s);
+/* device-side stopwatch across lanes (CUDA events): begin on h's stream; end waits for all
+ * work enqueued on the listed lanes, returns elapsed device milliseconds */
+int kml_timer_begin(kml_handle* h);
+int kml_timer_end(kml_handle* h, kml_handle** lanes, int n_lanes, float* ms);
 /* measurement hygiene: overwrite a 256 MiB device buffer (> 126 MB L2) on the
  * handle's stream so the next timed step starts with a cold L2 */
 int kml_flush_l2(kml_handle* h);

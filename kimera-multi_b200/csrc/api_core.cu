@@ -89,6 +89,7 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
       return KML_ERR_CUDA;
     }
     h = new kml_handle();
+    h->sh = std::make_shared<kml_shared>();
     if (p) h->prm = *p; else kml_default_params(&h->prm);
     if (h->prm.ransac_randomize != 0) {
       g_create_err = "ransac_randomize must be 0 (pre-drawn sample stream)";
@@ -112,11 +113,11 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
     // pre-drawn sample stream: mt19937(seed)() >> 1  
     const int max_it = std::max(h->prm.max_ransac_iterations_mono, h->prm.max_ransac_iterations);
     const size_t draws = (size_t)max_it + 1 + 256;
-    h->raw_h.resize(draws * 8);
+    h->sh->raw_h.resize(draws * 8);
     std::mt19937 mt(h->prm.ransac_seed);
-    for (auto& r : h->raw_h) r = (uint32_t)mt() >> 1;
-    h->d_raw.scratch(h->raw_h.size());
-    KML_CUDA(cudaMemcpy(h->d_raw.p, h->raw_h.data(), h->raw_h.size() * 4, cudaMemcpyHostToDevice));
+    for (auto& r : h->sh->raw_h) r = (uint32_t)mt() >> 1;
+    h->sh->d_raw.scratch(h->sh->raw_h.size());
+    KML_CUDA(cudaMemcpy(h->sh->d_raw.p, h->sh->raw_h.data(), h->sh->raw_h.size() * 4, cudaMemcpyHostToDevice));
     *out = h;
     return KML_OK;
   } catch (const std::exception& e) {
@@ -129,6 +130,31 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
 
 void kml_comm_destroy_internal(kml_handle* h);
 
+// A query lane: a second handle that SHARES the parent's databases, frame store, RANSAC
+// constants and vocabulary (read-only while queries run) but owns its stream, events and
+// batch buffers, so two host threads can keep two batches in flight on one GPU.
+int kml_create_lane(kml_handle* parent, kml_handle** out) {
+  if (!parent || !out) return KML_ERR_ARG;
+  *out = nullptr;
+  kml_handle* h = nullptr;
+  try {
+    KML_CUDA(cudaSetDevice(parent->device));
+    h = new kml_handle();
+    h->sh = parent->sh;
+    h->prm = parent->prm;
+    h->device = parent->device;
+    KML_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e2 : h->ev) KML_CUDA(cudaEventCreate(&e2));
+    *out = h;
+    return KML_OK;
+  } catch (const std::exception& e) {
+    parent->err = e.what();
+    cudaGetLastError();
+    delete h;
+    return KML_ERR_CUDA;
+  }
+}
+
 int kml_destroy(kml_handle* h) {
   if (!h) return KML_ERR_ARG;
   cudaSetDevice(h->device);
@@ -139,6 +165,7 @@ int kml_destroy(kml_handle* h) {
   }
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_t0) { cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_lane); }
   delete h;
   return KML_OK;
 }
@@ -229,6 +256,36 @@ int kml_l1_knn2(kml_handle* h, const uint8_t* q, int nq, const uint8_t* t, int64
                 uint16_t* dist, float* ms_kernel) {
   KML_API_BEGIN(h)
   return knn2_host(h, 1, q, nq, t, nt, 1, idx, dist, ms_kernel);
+  KML_API_END(h)
+}
+
+// Device-side stopwatch over several lanes: begin records an event on h's stream; end makes
+// h's stream wait for everything enqueued so far on the listed lanes, records the end event,
+// synchronises and returns the elapsed device time.
+int kml_timer_begin(kml_handle* h) {
+  KML_API_BEGIN(h)
+  if (!h->ev_t0) {
+    KML_CUDA(cudaEventCreate(&h->ev_t0));
+    KML_CUDA(cudaEventCreate(&h->ev_t1));
+    KML_CUDA(cudaEventCreateWithFlags(&h->ev_lane, cudaEventDisableTiming));
+  }
+  KML_CUDA(cudaStreamSynchronize(h->stream));
+  KML_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+  return KML_OK;
+  KML_API_END(h)
+}
+int kml_timer_end(kml_handle* h, kml_handle** lanes, int n_lanes, float* ms) {
+  KML_API_BEGIN(h)
+  if (!h->ev_t0 || !ms || n_lanes < 0 || (n_lanes > 0 && !lanes)) return KML_ERR_ARG;
+  for (int i = 0; i < n_lanes; ++i) {
+    if (!lanes[i] || lanes[i] == h) continue;
+    KML_CUDA(cudaEventRecord(h->ev_lane, lanes[i]->stream));
+    KML_CUDA(cudaStreamWaitEvent(h->stream, h->ev_lane, 0));
+  }
+  KML_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+  KML_CUDA(cudaEventSynchronize(h->ev_t1));
+  KML_CUDA(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return KML_OK;
   KML_API_END(h)
 }
 

@@ -1,6 +1,7 @@
 // handle.h — kml_handle: host-side state of the LoopClosureDetector replacement.
 #pragma once
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -54,18 +55,17 @@ struct Comm;  // NCCL state (comm.cu)
 
 }  // namespace kml
 
-struct kml_handle {
-  kml_params prm;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
-  std::string err;
-  kml_stats stats = {};
-
+// Database, frame store, RANSAC constants and vocabulary: owned jointly by a handle and the
+// query lanes cloned from it.  Lazily prepared device copies (CSR rebuild, k tables, frame
+// offsets) are guarded by `mu`; mutating calls (add*, vocab_set) must not overlap queries.
+struct kml_shared {
+  std::mutex mu;
+  std::vector<void*> retired;  // device tables replaced while another lane may still read them
+  ~kml_shared() {
+    for (void* p : retired) cudaFree(p);
+  }
   // ---- BoW databases (one per robot, ordered: detectLoop visits ascending)
   std::map<uint64_t, std::unique_ptr<kml::RobotDb>> dbs;
-  kml::DevBuf<kml::BowDb> d_dbs;
-  kml::DevBuf<int32_t> d_maxid;
 
   // ---- frame store (feature arenas in HBM)
   std::unordered_map<kml::RobotPoseId, kml::FrameRec, kml::RobotPoseHash> frames;
@@ -83,6 +83,28 @@ struct kml_handle {
   kml::DevBuf<uint32_t> d_raw;
   int ktable_n_mono = 0, ktable_n_stereo = 0;
   kml::DevBuf<double> d_ktable_mono, d_ktable_stereo;
+
+  // ---- vocabulary tree (row f1: TemplatedVocabulary::transform)
+  int voc_k = 0, voc_L = 0;
+  uint64_t voc_words = 0, voc_nodes = 0;
+  kml::DevBuf<uint8_t> d_voc_nodes;  // [nodes][32], breadth-first, level 1 first
+  kml::DevBuf<double> d_voc_w;       // [k^L] word weights (IDF)
+
+};
+
+struct kml_handle {
+  kml_params prm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane = nullptr;  // kml_timer_begin / kml_timer_end
+  std::string err;
+  kml_stats stats = {};
+
+  // ---- state shared by a handle and the query lanes cloned from it (kml_create_lane)
+  std::shared_ptr<kml_shared> sh;
+  kml::DevBuf<kml::BowDb> d_dbs;
+  kml::DevBuf<int32_t> d_maxid;
 
   // ---- batch buffers (query side)
   int B = 0, qF = 0;
@@ -115,12 +137,6 @@ struct kml_handle {
   kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
   kml::DevBuf<uint8_t> d_scratch, d_scratch2;
-
-  // ---- vocabulary tree (row f1: TemplatedVocabulary::transform)
-  int voc_k = 0, voc_L = 0;
-  uint64_t voc_words = 0, voc_nodes = 0;
-  kml::DevBuf<uint8_t> d_voc_nodes;  // [nodes][32], breadth-first, level 1 first
-  kml::DevBuf<double> d_voc_w;       // [k^L] word weights (IDF)
 
   kml::Comm* comm = nullptr;
 };

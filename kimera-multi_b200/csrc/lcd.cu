@@ -44,13 +44,13 @@ static int fail(kml_handle* h, int code, const char* msg) {
 
 // ===================================================================== DB
 static RobotDb* get_db(kml_handle* h, uint64_t robot, bool create) {
-  auto it = h->dbs.find(robot);
-  if (it != h->dbs.end()) return it->second.get();
+  auto it = h->sh->dbs.find(robot);
+  if (it != h->sh->dbs.end()) return it->second.get();
   if (!create) return nullptr;
   auto db = std::unique_ptr<RobotDb>(new RobotDb());
   db->robot = robot;
   RobotDb* p = db.get();
-  h->dbs[robot] = std::move(db);
+  h->sh->dbs[robot] = std::move(db);
   return p;
 }
 
@@ -102,7 +102,10 @@ static void rebuild_csr(kml_handle* h, RobotDb* db) {
 }
 
 static BowDb db_view(kml_handle* h, RobotDb* db) {
-  if (db->dirty) rebuild_csr(h, db);
+  {
+    std::lock_guard<std::mutex> lk(h->sh->mu);
+    if (db->dirty) rebuild_csr(h, db);
+  }
   BowDb v;
   v.row_ptr = db->row_ptr.p;
   v.postings = db->postings.p;
@@ -269,39 +272,40 @@ static int add_frames_host(kml_handle* h, uint64_t robot, const uint64_t* poses,
       (count > 0 && !poses))
     return fail(h, KML_ERR_ARG, "add_frame: bad argument (F must be < 65536)");
   const size_t total = (size_t)count * F;
-  const int64_t base = h->n_feat;
-  h->s_desc.reserve((size_t)(base + total) * 32 + 32, (size_t)base * 32, h->stream);
-  h->s_bear.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
-  h->s_pts.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
+  const int64_t base = h->sh->n_feat;
+  h->sh->s_desc.reserve((size_t)(base + total) * 32 + 32, (size_t)base * 32, h->stream);
+  h->sh->s_bear.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
+  h->sh->s_pts.reserve((size_t)(base + total) * 3 + 3, (size_t)base * 3, h->stream);
   if (total) {
-    KML_CUDA(cudaMemcpyAsync(h->s_desc.p + (size_t)base * 32, desc, total * 32, cudaMemcpyHostToDevice, h->stream));
-    KML_CUDA(cudaMemcpyAsync(h->s_bear.p + (size_t)base * 3, bearings, total * 24, cudaMemcpyHostToDevice, h->stream));
-    KML_CUDA(cudaMemcpyAsync(h->s_pts.p + (size_t)base * 3, points, total * 24, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->sh->s_desc.p + (size_t)base * 32, desc, total * 32, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->sh->s_bear.p + (size_t)base * 3, bearings, total * 24, cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaMemcpyAsync(h->sh->s_pts.p + (size_t)base * 3, points, total * 24, cudaMemcpyHostToDevice, h->stream));
   }
   for (int i = 0; i < count; ++i) {
     const RobotPoseId id(robot, poses[i]);
     FrameRec rec;
     rec.feat_off = base + (int64_t)i * F;
     rec.F = F;
-    rec.index = (int32_t)h->frame_off_h.size();
-    h->frame_off_h.push_back(rec.feat_off);
-    h->frame_F_h.push_back(F);
-    h->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
+    rec.index = (int32_t)h->sh->frame_off_h.size();
+    h->sh->frame_off_h.push_back(rec.feat_off);
+    h->sh->frame_F_h.push_back(F);
+    h->sh->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
   }
-  h->n_feat = base + (int64_t)total;
-  h->s_off_dirty = true;
+  h->sh->n_feat = base + (int64_t)total;
+  h->sh->s_off_dirty = true;
   KML_CUDA(cudaStreamSynchronize(h->stream));  // caller may free its buffers on return
   return KML_OK;
 }
 
 static void ensure_frame_offsets(kml_handle* h) {
-  if (!h->s_off_dirty) return;
-  h->s_off.scratch(std::max<size_t>(h->frame_off_h.size(), 1));
-  if (!h->frame_off_h.empty())
-    KML_CUDA(cudaMemcpyAsync(h->s_off.p, h->frame_off_h.data(), 8 * h->frame_off_h.size(),
+  std::lock_guard<std::mutex> lk(h->sh->mu);
+  if (!h->sh->s_off_dirty) return;
+  h->sh->s_off.scratch(std::max<size_t>(h->sh->frame_off_h.size(), 1));
+  if (!h->sh->frame_off_h.empty())
+    KML_CUDA(cudaMemcpyAsync(h->sh->s_off.p, h->sh->frame_off_h.data(), 8 * h->sh->frame_off_h.size(),
                              cudaMemcpyHostToDevice, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
-  h->s_off_dirty = false;
+  h->sh->s_off_dirty = false;
 }
 
 // ====================================================== RANSAC host helpers
@@ -310,6 +314,7 @@ static void ensure_frame_offsets(kml_handle* h) {
 // device replay takes the same branches as a CPU run.
 static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob, DevBuf<double>* buf,
                           int* cur_n) {
+  std::lock_guard<std::mutex> lk(h->sh->mu);
   const int need = Nmax + 1;
   if (*cur_n >= need) return;
   int n1 = std::max(need, 512);
@@ -323,6 +328,11 @@ static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob,
       p_no = std::min(1.0 - DBL_EPSILON, p_no);
       tab[(size_t)N * n1 + n] = lnum / std::log(p_no);
     }
+  if (buf->p) {  // another lane's kernels may still read the old table: retire it instead of freeing
+    h->sh->retired.push_back(buf->p);
+    buf->p = nullptr;
+    buf->cap = 0;
+  }
   buf->scratch(tab.size());
   KML_CUDA(cudaMemcpyAsync(buf->p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
@@ -356,10 +366,10 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   const int chunk = mono ? kMonoChunk : kStereoChunk;
   const int max_it = mono ? prm.max_ransac_iterations_mono : prm.max_ransac_iterations;
   if (mono)
-    ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->d_ktable_mono, &h->ktable_n_mono);
+    ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->sh->d_ktable_mono, &h->sh->ktable_n_mono);
   else
-    ensure_ktable(h, stride, 3, prm.ransac_probability, &h->d_ktable_stereo, &h->ktable_n_stereo);
-  const int raw_len = (int)h->raw_h.size();
+    ensure_ktable(h, stride, 3, prm.ransac_probability, &h->sh->d_ktable_stereo, &h->sh->ktable_n_stereo);
+  const int raw_len = (int)h->sh->raw_h.size();
   const int cap_draws = std::min(raw_len / S, max_it + 1 + 256);
   {  // the doubling round schedule must cover cap_draws with at most kRoundCap new draws per round
     int cum = 0;
@@ -384,13 +394,13 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   out.inl->scratch(P);
   SacArgs a;
   a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
-  a.raw = h->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
+  a.raw = h->sh->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
   a.fsol = h->d_esol.p; a.nroot = h->d_nsol.p; a.brk = h->d_brk.p;
   a.fb_list = h->d_fb_list.p + 1; a.fb_count = h->d_fb_list.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
-  a.ktable = mono ? h->d_ktable_mono.p : h->d_ktable_stereo.p;
-  a.ktable_n = mono ? h->ktable_n_mono : h->ktable_n_stereo;
+  a.ktable = mono ? h->sh->d_ktable_mono.p : h->sh->d_ktable_stereo.p;
+  a.ktable_n = mono ? h->sh->ktable_n_mono : h->sh->ktable_n_stereo;
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
   a.sq_crit = sq_crit_of(prm.ransac_threshold);
   a.max_iterations = max_it; a.full = full;
@@ -436,8 +446,8 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   for (int p = 0; p < P; ++p) {
     jobs[p].q = qs.desc + (size_t)pairs[p].q_slot * qs.F * 32;
     jobs[p].nq = qs.F;
-    jobs[p].t = h->s_desc.p + (size_t)h->frame_off_h[pairs[p].m_frame] * 32;
-    jobs[p].nt = h->frame_F_h[pairs[p].m_frame];
+    jobs[p].t = h->sh->s_desc.p + (size_t)h->sh->frame_off_h[pairs[p].m_frame] * 32;
+    jobs[p].nt = h->sh->frame_F_h[pairs[p].m_frame];
     jobs[p].keys = h->d_keys.p + (size_t)p * stride * 2;
   }
   h->d_jobs.scratch(P); h->d_pairs.scratch(P); h->d_nq.scratch(P);
@@ -462,7 +472,7 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   // ---- geometricVerificationNister
   GatherArgs g;
   g.P = P; g.pairs = h->d_pairs.p; g.qb = qs.bear; g.qp = qs.pts; g.qF = qs.F;
-  g.sb = h->s_bear.p; g.sp = h->s_pts.p; g.s_off = h->s_off.p;
+  g.sb = h->sh->s_bear.p; g.sp = h->sh->s_pts.p; g.s_off = h->sh->s_off.p;
   g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
   g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;  // N3 reused as "N" of the mono stage
   launch_gather_bearings(g, s);
@@ -585,7 +595,7 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
   if (B == 0) return KML_OK;
   KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
   std::vector<RobotDb*> dbs;
-  for (auto& kv : h->dbs) dbs.push_back(kv.second.get());
+  for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
   BowOut bo;
   run_bow(h, dbs, B, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
           h->d_pvals.p, h->prm.max_db_results, nullptr, &bo);
@@ -614,8 +624,8 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
       r.q_robot = h->q_robot_h[b]; r.q_pose = h->q_pose_h[b];
       r.m_robot = cands[i].robot; r.m_pose = cands[i].pose;
       r.norm_bow_score = cands[i].score;
-      auto fit = h->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
-      if (fit == h->frames.end()) { r.status = 3; continue; }
+      auto fit = h->sh->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
+      if (fit == h->sh->frames.end()) { r.status = 3; continue; }
       pairs.push_back({b, fit->second.index});
       pair_rec.push_back(b * cap + i);
     }
@@ -653,12 +663,12 @@ static void copy_out(const BatchRecs& br, int B, int cap, kml_result* out, int32
 
 // single stored frame as the "query side"
 static bool stored_query_side(kml_handle* h, uint64_t robot, uint64_t pose, QuerySide* qs) {
-  auto it = h->frames.find(RobotPoseId(robot, pose));
-  if (it == h->frames.end()) return false;
+  auto it = h->sh->frames.find(RobotPoseId(robot, pose));
+  if (it == h->sh->frames.end()) return false;
   const FrameRec& r = it->second;
-  qs->desc = h->s_desc.p + (size_t)r.feat_off * 32;
-  qs->bear = h->s_bear.p + (size_t)r.feat_off * 3;
-  qs->pts = h->s_pts.p + (size_t)r.feat_off * 3;
+  qs->desc = h->sh->s_desc.p + (size_t)r.feat_off * 32;
+  qs->bear = h->sh->s_bear.p + (size_t)r.feat_off * 3;
+  qs->pts = h->sh->s_pts.p + (size_t)r.feat_off * 3;
   qs->F = r.F;
   return true;
 }
@@ -670,8 +680,8 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
   if (!inl_q || !inl_m || !count || *count < 0) return fail(h, KML_ERR_ARG, "bad index lists");
   QuerySide qs;
   if (!stored_query_side(h, qr, qp, &qs)) return KML_NO_FRAME;
-  auto mit = h->frames.find(RobotPoseId(mr, mp));
-  if (mit == h->frames.end()) return KML_NO_FRAME;
+  auto mit = h->sh->frames.find(RobotPoseId(mr, mp));
+  if (mit == h->sh->frames.end()) return KML_NO_FRAME;
   const int M = *count;
   for (int i = 0; i < M; ++i)
     if (inl_q[i] >= (uint32_t)qs.F || inl_m[i] >= (uint32_t)mit->second.F)
@@ -694,7 +704,7 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
   KML_CUDA(cudaMemcpyAsync(h->d_mono_ok.p, &one, 4, cudaMemcpyHostToDevice, s));
   GatherArgs g;
   g.P = 1; g.pairs = h->d_pairs.p; g.qb = qs.bear; g.qp = qs.pts; g.qF = qs.F;
-  g.sb = h->s_bear.p; g.sp = h->s_pts.p; g.s_off = h->s_off.p;
+  g.sb = h->sh->s_bear.p; g.sp = h->sh->s_pts.p; g.s_off = h->sh->s_off.p;
   g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
   g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;
   SacBufs bufs = mono ? SacBufs{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono}
@@ -785,7 +795,7 @@ int kml_add_frames_bulk(kml_handle* h, uint64_t robot, const uint64_t* poses, in
 
 int kml_frame_exists(kml_handle* h, uint64_t robot, uint64_t pose) {
   if (!h) return KML_ERR_ARG;
-  return h->frames.count(RobotPoseId(robot, pose)) ? 1 : 0;
+  return h->sh->frames.count(RobotPoseId(robot, pose)) ? 1 : 0;
 }
 int kml_bow_exists(kml_handle* h, uint64_t robot, uint64_t pose) {
   if (!h) return KML_ERR_ARG;
@@ -920,7 +930,7 @@ int kml_detect_loop(kml_handle* h, uint64_t q_robot, uint64_t q_pose, const uint
   KML_API_BEGIN(h)
   if (!count || !out_robot || !out_pose || !out_score) return fail(h, KML_ERR_ARG, "null output");
   std::vector<RobotDb*> dbs;
-  for (auto& kv : h->dbs) dbs.push_back(kv.second.get());
+  for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
   return detect_impl(h, dbs, q_robot, q_pose, ids, vals, n, out_robot, out_pose, out_score, cap, count);
   KML_API_END(h)
 }
@@ -932,8 +942,8 @@ int kml_compute_matched_indices(kml_handle* h, uint64_t qr, uint64_t qp, uint64_
   *count = 0;
   QuerySide qs;
   if (!stored_query_side(h, qr, qp, &qs)) return KML_NO_FRAME;
-  auto mit = h->frames.find(RobotPoseId(mr, mp));
-  if (mit == h->frames.end()) return KML_NO_FRAME;
+  auto mit = h->sh->frames.find(RobotPoseId(mr, mp));
+  if (mit == h->sh->frames.end()) return KML_NO_FRAME;
   if (qs.F == 0) return KML_OK;
   const int stride = qs.F;
   cudaStream_t s = h->stream;
@@ -941,7 +951,7 @@ int kml_compute_matched_indices(kml_handle* h, uint64_t qr, uint64_t qp, uint64_
   h->d_iq.scratch(stride); h->d_im.scratch(stride); h->d_M.scratch(1);
   HamJob job;
   job.q = qs.desc; job.nq = qs.F;
-  job.t = h->s_desc.p + (size_t)mit->second.feat_off * 32; job.nt = mit->second.F;
+  job.t = h->sh->s_desc.p + (size_t)mit->second.feat_off * 32; job.nt = mit->second.F;
   job.keys = h->d_keys.p;
   KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaMemcpyAsync(h->d_nq.p, &qs.F, 4, cudaMemcpyHostToDevice, s));

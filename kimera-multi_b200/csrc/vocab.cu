@@ -143,11 +143,11 @@ int kml_vocab_set(kml_handle* h, int k, int L, const uint8_t* node_desc, const d
     nodes += lvl;
     if (lvl > (1ull << 31)) { h->err = "vocab_set: more than 2^31 words"; return KML_ERR_CAPACITY; }
   }
-  h->voc_k = k; h->voc_L = L; h->voc_words = lvl; h->voc_nodes = nodes;
-  h->d_voc_nodes.scratch(nodes * 32 + 32);
-  h->d_voc_w.scratch(lvl);
-  KML_CUDA(cudaMemcpyAsync(h->d_voc_nodes.p, node_desc, nodes * 32, cudaMemcpyHostToDevice, h->stream));
-  KML_CUDA(cudaMemcpyAsync(h->d_voc_w.p, word_weights, lvl * 8, cudaMemcpyHostToDevice, h->stream));
+  h->sh->voc_k = k; h->sh->voc_L = L; h->sh->voc_words = lvl; h->sh->voc_nodes = nodes;
+  h->sh->d_voc_nodes.scratch(nodes * 32 + 32);
+  h->sh->d_voc_w.scratch(lvl);
+  KML_CUDA(cudaMemcpyAsync(h->sh->d_voc_nodes.p, node_desc, nodes * 32, cudaMemcpyHostToDevice, h->stream));
+  KML_CUDA(cudaMemcpyAsync(h->sh->d_voc_w.p, word_weights, lvl * 8, cudaMemcpyHostToDevice, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
   return KML_OK;
   KML_API_END(h)
@@ -156,7 +156,7 @@ int kml_vocab_set(kml_handle* h, int k, int L, const uint8_t* node_desc, const d
 int kml_transform_batch(kml_handle* h, int B, int F, const uint8_t* desc, int64_t* out_off, uint32_t* out_ids,
                         double* out_vals, int64_t cap, float* ms_kernel) {
   KML_API_BEGIN(h)
-  if (h->voc_nodes == 0) { h->err = "transform: no vocabulary (kml_vocab_set)"; return KML_ERR_ARG; }
+  if (h->sh->voc_nodes == 0) { h->err = "transform: no vocabulary (kml_vocab_set)"; return KML_ERR_ARG; }
   if (B < 0 || F < 0 || F > kAsmMaxF || !out_off || (B > 0 && F > 0 && (!desc || !out_ids || !out_vals))) {
     h->err = "transform: bad argument (F <= 1024)";
     return KML_ERR_ARG;
@@ -175,9 +175,9 @@ int kml_transform_batch(kml_handle* h, int B, int F, const uint8_t* desc, int64_
   d_words.scratch(n); d_ids.scratch(n); d_vals.scratch(n); d_cnt.scratch(B);
   KML_CUDA(cudaMemcpyAsync(h->d_scratch.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaEventRecord(h->ev[0], s));
-  vocab_descend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_scratch.p, n, h->d_voc_nodes.p, h->voc_k,
-                                                                  h->voc_L, d_words.p);
-  bow_assemble_kernel<<<B, kAsmThreads, 0, s>>>(d_words.p, F, h->d_voc_w.p, d_ids.p, d_vals.p, d_cnt.p);
+  vocab_descend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_scratch.p, n, h->sh->d_voc_nodes.p, h->sh->voc_k,
+                                                                  h->sh->voc_L, d_words.p);
+  bow_assemble_kernel<<<B, kAsmThreads, 0, s>>>(d_words.p, F, h->sh->d_voc_w.p, d_ids.p, d_vals.p, d_cnt.p);
   KML_CUDA(cudaEventRecord(h->ev[1], s));
   KML_CUDA(cudaGetLastError());
   h->stats.kernel_launches += 2;

@@ -81,6 +81,16 @@ class LoopClosureDetector:
         self.params = params
         self.device = device
 
+    def create_lane(self):
+        """Second query context on the same GPU sharing this detector's databases (kml_create_lane)."""
+        lane = LoopClosureDetector.__new__(LoopClosureDetector)
+        lane._h = C.c_void_p()
+        lane.params, lane.device = self.params, self.device
+        rc = lib().kml_create_lane(self._h, C.byref(lane._h))
+        if rc != KML_OK:
+            raise KmlError(rc, (lib().kml_last_error(self._h) or b"").decode())
+        return lane
+
     def close(self):
         if getattr(self, "_h", None):
             lib().kml_destroy(self._h)
@@ -349,6 +359,15 @@ class LoopClosureDetector:
                                               _p(ids, C.c_uint32), _p(vals, C.c_double), C.c_int64(B * F),
                                               C.byref(ms)))
         return off, ids[:off[-1]].copy(), vals[:off[-1]].copy(), ms.value
+
+    def timer_begin(self):
+        self._check(lib().kml_timer_begin(self._h))
+
+    def timer_end(self, lanes=()):
+        arr = (C.c_void_p * max(len(lanes), 1))(*[l._h for l in lanes])
+        ms = C.c_float(0)
+        self._check(lib().kml_timer_end(self._h, arr, len(lanes), C.byref(ms)))
+        return ms.value
 
     def flush_l2(self):
         self._check(lib().kml_flush_l2(self._h))

@@ -81,14 +81,14 @@ class Result(C.Structure):
 
 # every symbol include/kml.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "kml_default_params", "kml_create", "kml_destroy", "kml_last_error", "kml_get_stats",
+    "kml_default_params", "kml_create", "kml_create_lane", "kml_destroy", "kml_last_error", "kml_get_stats",
     "kml_device_count", "kml_add_bow", "kml_add_bow_bulk", "kml_add_frame",
     "kml_add_frames_bulk", "kml_frame_exists", "kml_bow_exists", "kml_num_bow_for_robot",
     "kml_get_bow_vector", "kml_db_query", "kml_bow_score", "kml_detect_loop_with_robot",
     "kml_detect_loop", "kml_compute_matched_indices", "kml_geometric_verification_nister",
     "kml_recover_pose", "kml_query_batch", "kml_query_batch_upload", "kml_query_batch_run",
     "kml_hamming_knn2", "kml_l1_knn2", "kml_hamming_knn2_bench", "kml_ransac_arun_batch",
-    "kml_ransac_nister_batch", "kml_vocab_set", "kml_transform_batch", "kml_peak_popc", "kml_peak_fp64", "kml_flush_l2", "kml_comm_unique_id",
+    "kml_ransac_nister_batch", "kml_vocab_set", "kml_transform_batch", "kml_peak_popc", "kml_peak_fp64", "kml_timer_begin", "kml_timer_end", "kml_flush_l2", "kml_comm_unique_id",
     "kml_comm_init", "kml_query_batch_sharded",
 ]
 

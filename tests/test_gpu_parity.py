@@ -176,6 +176,42 @@ def test_query_batch(oracle_lcd, gpu_lcd, small_world):
     assert len(cnt3) == 0
 
 
+def test_query_lanes_concurrent(gpu_lcd, small_world):
+    """Two lanes (kml_create_lane) sharing one database, driven from two host
+    threads at once, return byte-identical records to the parent handle."""
+    import threading
+    world, chunks, q = small_world
+    fq, fp = q["frames"], q["prev"]
+    args = (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    ref, cnt = gpu_lcd.query_batch(*args)
+    lanes = [gpu_lcd.create_lane(), gpu_lcd.create_lane()]
+    got, errs = {}, []
+
+    def work(i):
+        try:
+            for rep in range(4):
+                got[(i, rep)] = lanes[i].query_batch(*args)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert len(got) == 8
+    for out, c in got.values():
+        assert np.array_equal(c, cnt) and out.tobytes() == ref.tobytes()
+    # the parent still sees frames added through a lane (shared store)
+    ch = chunks[0]
+    lanes[0].addVLCFrame(7, 1, ch["desc"][0], ch["bearings"][0], ch["points"][0])
+    assert gpu_lcd.frameExists(7, 1) and lanes[1].frameExists(7, 1)
+    for ln in lanes:
+        ln.close()
+    out2, cnt2 = gpu_lcd.query_batch(*args)
+    assert out2.tobytes() == ref.tobytes()
+
+
 def test_ransac_batches(oracle, gpu_lcd):
     """Batched RANSAC entry points against the oracle's sequential loop:
     inlier sets, iteration counts and winning draws bit-exact."""

@@ -433,28 +433,80 @@ __device__ __forceinline__ void candidate_model(const double* Ra, const double* 
     M[4 * r + 3] = sgn * tt[r];
   }
 }
-// Scores the four candidates of one essential matrix on the 8 sample points
-// (sequential sum of the bearing residuals, the disambiguation of SURVEY A.6).
-__device__ __noinline__ void score_essential(const double* E, const double* __restrict__ ga,
-                                             const double* __restrict__ gb, const uint16_t* __restrict__ smp,
-                                             double* qual /*[4]*/) {
+// Residuals of the candidate pair (R, t) and (R, -t) for one correspondence.
+// Negating t negates b0, b1, l0, l1, p, tinv and q exactly (every IEEE operation is
+// sign-symmetric), so with x1 = f1.p/|p| and x2 = f2.q/|q| of the +t candidate the -t
+// candidate's residual is (1 + x1) + (1 + x2): two candidates for one evaluation, bit
+// for bit what mono_residual returns for each of them.
+__device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, const V3& t, const double* tinv,
+                                                   const V3& f1, const V3& f2, double* r_pos, double* r_neg) {
+  V3 f2u;
+  f2u.x = (R[0] * f2.x + R[1] * f2.y) + R[2] * f2.z;
+  f2u.y = (R[3] * f2.x + R[4] * f2.y) + R[5] * f2.z;
+  f2u.z = (R[6] * f2.x + R[7] * f2.y) + R[8] * f2.z;
+  const double b0 = dot(t, f1), b1 = dot(t, f2u);
+  const double d12 = dot(f1, f2u);
+  const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
+  const double det = A00 * A11 - A01 * A10;
+  const double l0 = kdiv(A11 * b0 - A01 * b1, det);
+  const double l1 = kdiv(A00 * b1 - A10 * b0, det);
+  V3 p, q;
+  p.x = 0.5 * (l0 * f1.x + (t.x + l1 * f2u.x));
+  p.y = 0.5 * (l0 * f1.y + (t.y + l1 * f2u.y));
+  p.z = 0.5 * (l0 * f1.z + (t.z + l1 * f2u.z));
+  q.x = ((R[0] * p.x + R[3] * p.y) + R[6] * p.z) + tinv[0];
+  q.y = ((R[1] * p.x + R[4] * p.y) + R[7] * p.z) + tinv[1];
+  q.z = ((R[2] * p.x + R[5] * p.y) + R[8] * p.z) + tinv[2];
+  const double np = ksqrt(dot(p, p)), nq = ksqrt(dot(q, q));
+  const double x1 = kdiv(dot(f1, p), np);
+  const double x2 = kdiv(dot(f2, q), nq);
+  *r_pos = (1.0 - x1) + (1.0 - x2);
+  *r_neg = (1.0 + x1) + (1.0 + x2);
+}
+
+// One (draw, root) item: refine the bracketed root, build E, decompose it, score the four
+// (R, t) candidates on the 8 sample points (sequential sums) and keep the first
+// smallest one below the reference's initial quality 1e6.
+// returns 0 root not refined, 1 refined but nothing usable, 2 *q_out / M_out written
+__device__ __forceinline__ int mono_item(const double* __restrict__ fo, int chain, double lo, double hi,
+                                         const double* __restrict__ ga, const double* __restrict__ gb,
+                                         const uint16_t* __restrict__ smp, double* q_out, double* M_out) {
+  double z, E[9];
+  if (!refine_root(fo, chain, lo, hi, &z)) return 0;
+  if (!essential_from_root(fo, z, E)) return 1;
   double Ra[9], Rb[9], tt[3];
   essential_candidates(E, Ra, Rb, tt);
-#pragma unroll 1
-  for (int cand = 0; cand < 4; ++cand) {
-    double M[12], tinv[3];
-    candidate_model(Ra, Rb, tt, cand, M);
-    mono_tinv(M, tinv);
-    double q = 0.0;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-      const int idx = smp[k];
-      const V3 f1 = {ga[3 * idx], ga[3 * idx + 1], ga[3 * idx + 2]};
-      const V3 f2 = {gb[3 * idx], gb[3 * idx + 1], gb[3 * idx + 2]};
-      q = q + mono_residual(M, tinv, f1, f2);
-    }
-    qual[cand] = q;
+  const V3 t = {tt[0], tt[1], tt[2]};
+  double ta[3], tb[3];  // -R^T t of the +t candidates (mono_tinv)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ta[c] = -((Ra[c] * tt[0] + Ra[3 + c] * tt[1]) + Ra[6 + c] * tt[2]);
+    tb[c] = -((Rb[c] * tt[0] + Rb[3 + c] * tt[1]) + Rb[6 + c] * tt[2]);
   }
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const int idx = smp[k];
+    const V3 f1 = {ga[3 * idx], ga[3 * idx + 1], ga[3 * idx + 2]};
+    const V3 f2 = {gb[3 * idx], gb[3 * idx + 1], gb[3 * idx + 2]};
+    double rp, rn;
+    mono_residual_pair(Ra, t, ta, f1, f2, &rp, &rn);
+    q0 = q0 + rp;
+    q1 = q1 + rn;
+    mono_residual_pair(Rb, t, tb, f1, f2, &rp, &rn);
+    q2 = q2 + rp;
+    q3 = q3 + rn;
+  }
+  double best = 1000000.0;
+  int bc = -1;
+  if (q0 < best) { best = q0; bc = 0; }
+  if (q1 < best) { best = q1; bc = 1; }
+  if (q2 < best) { best = q2; bc = 2; }
+  if (q3 < best) { best = q3; bc = 3; }
+  if (bc < 0) return 1;
+  *q_out = best;
+  candidate_model(Ra, Rb, tt, bc, M_out);
+  return 2;
 }
 
 }  // namespace geom

@@ -206,5 +206,84 @@ KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, c
   return e1 + e2;
 }
 
+// ----------------------------------------------- inlier test, fast filter
+// Decides `mono_residual(...) < thr` WITHOUT the six IEEE divisions / square roots
+// for all but the correspondences whose residual lies within a rigorous error margin
+// of the threshold (those, and every badly conditioned triangulation, return -1 and
+// are re-evaluated with mono_residual, so the decision is always the exact one).
+// Preconditions: unit bearings (SacState::unit_bearings).
+// Error budget (e~ = filter value, e = value of mono_residual): the two evaluations differ
+// by FMA contraction and <= 2 ulp reciprocal / rsqrt, i.e. absolute differences of a few
+// ulp in det and the numerators.  With |det| >= 1e-4 that is <= 4e-12 (|l0|+|l1|+|t|) in p;
+// guard kp bounds the cancellation in p (|p| >= 0.01 of its terms) and guard kq the one in
+// q = R^T p - R^T t, so the direction of p moves by <= 4e-10 rad and that of q by <= 4e-8 rad.
+// d(1-cos x) = sin x dx <= 4e-8 everywhere, and <= sqrt(2 (thr + 1e-6)) * 4e-8 for
+// e <= thr + 1e-6.  The margins used below are 10x these bounds.
+KML_DI double rcp_fast(double d, bool* ok) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  e = __fma_rn(-d, x, 1.0);
+  *ok = fabs(e) < 1e-8;  // remaining relative error e^2 < 1e-16
+  return __fma_rn(x, e, x);
+}
+KML_DI double rsqrt_fast(double a, bool* ok) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = __fma_rn(-(a * y), y, 1.0);
+  y = __fma_rn(0.5 * y, e, y);
+  e = __fma_rn(-(a * y), y, 1.0);
+  *ok = fabs(e) < 1e-8;
+  return __fma_rn(0.5 * y, e, y);
+}
+KML_DI double dotf(const V3& a, const V3& b) { return __fma_rn(a.z, b.z, __fma_rn(a.y, b.y, a.x * b.x)); }
+struct InlierMargins {
+  double lo, hi, far;  // in if e~ < lo; out if e~ > hi (near band) or e~ > far
+};
+KML_DI InlierMargins inlier_margins(double thr) {
+  InlierMargins m;
+  const double near = ksqrt(2.0 * (thr + 1e-6)) * 4e-7 + 1e-12;
+  m.lo = thr - near;
+  m.hi = thr + near;
+  m.far = thr + 1e-6;
+  return m;
+}
+// 1 = inlier, 0 = outlier, -1 = undecided (caller evaluates mono_residual)
+KML_DI int mono_inlier_fast(const double* M, const double* tinv, const V3& f1, const V3& f2,
+                            const InlierMargins& mg) {
+  const V3 t = {M[3], M[7], M[11]};
+  V3 f2u;
+  f2u.x = __fma_rn(M[2], f2.z, __fma_rn(M[1], f2.y, M[0] * f2.x));
+  f2u.y = __fma_rn(M[6], f2.z, __fma_rn(M[5], f2.y, M[4] * f2.x));
+  f2u.z = __fma_rn(M[10], f2.z, __fma_rn(M[9], f2.y, M[8] * f2.x));
+  const double b0 = dotf(t, f1), b1 = dotf(t, f2u), d12 = dotf(f1, f2u);
+  const double A00 = dotf(f1, f1), n2 = dotf(f2u, f2u);
+  const double det = __fma_rn(d12, d12, -(A00 * n2));
+  bool ok0, ok1, ok2;
+  const double r = rcp_fast(det, &ok0);
+  const double l0 = __fma_rn(d12, b1, -(n2 * b0)) * r;
+  const double l1 = __fma_rn(A00, b1, -(d12 * b0)) * r;
+  V3 p, q;
+  p.x = 0.5 * __fma_rn(l0, f1.x, __fma_rn(l1, f2u.x, t.x));
+  p.y = 0.5 * __fma_rn(l0, f1.y, __fma_rn(l1, f2u.y, t.y));
+  p.z = 0.5 * __fma_rn(l0, f1.z, __fma_rn(l1, f2u.z, t.z));
+  q.x = __fma_rn(M[8], p.z, __fma_rn(M[4], p.y, __fma_rn(M[0], p.x, tinv[0])));
+  q.y = __fma_rn(M[9], p.z, __fma_rn(M[5], p.y, __fma_rn(M[1], p.x, tinv[1])));
+  q.z = __fma_rn(M[10], p.z, __fma_rn(M[6], p.y, __fma_rn(M[2], p.x, tinv[2])));
+  const double pp = dotf(p, p), qq = dotf(q, q);
+  const double s1 = (fabs(l0) + fabs(l1)) + ((fabs(t.x) + fabs(t.y)) + fabs(t.z));
+  const double s2 = ((fabs(p.x) + fabs(p.y)) + fabs(p.z)) + ((fabs(tinv[0]) + fabs(tinv[1])) + fabs(tinv[2]));
+  const double y1 = rsqrt_fast(pp, &ok1), y2 = rsqrt_fast(qq, &ok2);
+  const double e = 2.0 - __fma_rn(dotf(f1, p), y1, dotf(f2, q) * y2);
+  // conditioning guards (all false on NaN): |det| >= 1e-4, |f2u| sane, kp, kq <= 100
+  const bool sane = ok0 && ok1 && ok2 && fabs(det) >= 1e-4 && n2 > 0.5 && n2 < 2.0 && pp >= 1e-4 * (s1 * s1) &&
+                    qq >= 1e-4 * (s2 * s2) && pp < 1e280 && qq < 1e280;
+  if (!sane) return -1;
+  if (e < mg.lo) return 1;
+  if (e > mg.far || e > mg.hi) return 0;
+  return -1;
+}
+
 }  // namespace geom
 }  // namespace kml

@@ -132,7 +132,10 @@ struct kml_handle {
   kml::DevBuf<uint16_t> d_perm, d_samples;
   kml::DevBuf<int32_t> d_valid, d_counts, d_inl_mono, d_inl_stereo, d_nsol;
   kml::DevBuf<double> d_esol, d_brk;
-  kml::DevBuf<uint32_t> d_fb_list;  // [0] = counter, [1..] = deferred (slot, chain) items
+  kml::DevBuf<uint32_t> d_fb_list;  // [0] = deferred counter, [1] = item counter, [2..] = deferred (slot, chain) list
+  kml::DevBuf<uint32_t> d_item_base, d_item_list;  // (draw, root) items of a mono round (kernels.h SacArgs)
+  kml::DevBuf<double> d_item_q, d_item_model;
+  kml::DevBuf<uint8_t> d_item_status;
   kml::DevBuf<kml::SacState> d_st_mono, d_st_stereo;
   kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging

@@ -63,7 +63,7 @@ void launch_bow(const BowArgs& a, cudaStream_t s);
 struct SacState {
   int32_t iterations, skipped, draws, best, best_draw, done, exhausted;
   int32_t r_begin, r_end;  // draws [r_begin, r_end) are evaluated by the next chunk launch
-  int32_t pad;
+  int32_t unit_bearings;   // mono: every bearing of the problem has | |f|^2 - 1 | <= 1e-12 (set by sac_init)
   double k;
 };
 struct SacArgs {
@@ -82,6 +82,14 @@ struct SacArgs {
   double* brk;           // mono: [P][kRoundCap][20][2] isolating brackets
   uint32_t* fb_list;     // mono: deferred root isolations of the round, slot*2 + chain
   unsigned int* fb_count;
+  // mono: (draw, root) items of the round — one bracketed real root each.  A draw owns the
+  // contiguous range item_base[slot] + [0, R0+R1) of the item arrays.
+  unsigned int* item_count;
+  uint32_t* item_base;   // [P][kRoundCap]
+  uint32_t* item_list;   // [items] slot*32 + root
+  double* item_q;        // [items] smallest candidate quality of the item (< 1e6), if status == 2
+  double* item_model;    // [items][12] the candidate that attains it
+  uint8_t* item_status;  // [items] 0 root not refined, 1 refined without usable candidate, 2 scored
   uint16_t* samples;     // [P][cap_draws][S]
   int32_t* valid;        // [P][cap_draws]
   int32_t* counts;       // [P][cap_draws]

@@ -384,7 +384,14 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     h->d_nsol.scratch((size_t)P * kRoundCap);
     h->d_esol.scratch((size_t)P * kRoundCap * 70);
     h->d_brk.scratch((size_t)P * kRoundCap * 40);
-    h->d_fb_list.scratch((size_t)P * kRoundCap * 2 + 1);
+    h->d_fb_list.scratch((size_t)P * kRoundCap * 2 + 2);
+    // (draw, root) items of a round: up to 20 brackets per draw (both Sturm chains)
+    const size_t max_items = (size_t)P * kRoundCap * 20;
+    h->d_item_base.scratch((size_t)P * kRoundCap);
+    h->d_item_list.scratch(max_items);
+    h->d_item_q.scratch(max_items);
+    h->d_item_model.scratch(max_items * 12);
+    h->d_item_status.scratch(max_items);
   }
   h->d_valid.scratch((size_t)P * cap_draws);
   h->d_counts.scratch((size_t)P * cap_draws);
@@ -397,7 +404,9 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.raw = h->sh->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
   a.fsol = h->d_esol.p; a.nroot = h->d_nsol.p; a.brk = h->d_brk.p;
-  a.fb_list = h->d_fb_list.p + 1; a.fb_count = h->d_fb_list.p;
+  a.fb_list = h->d_fb_list.p + 2; a.fb_count = h->d_fb_list.p; a.item_count = h->d_fb_list.p + 1;
+  a.item_base = h->d_item_base.p; a.item_list = h->d_item_list.p; a.item_q = h->d_item_q.p;
+  a.item_model = h->d_item_model.p; a.item_status = h->d_item_status.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
   a.ktable = mono ? h->sh->d_ktable_mono.p : h->sh->d_ktable_stereo.p;
   a.ktable_n = mono ? h->sh->ktable_n_mono : h->sh->ktable_n_stereo;

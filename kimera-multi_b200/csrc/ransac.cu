@@ -59,8 +59,20 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
   const int N = a.N[p];
   SacState* st = &a.st[p];
   for (int i = lane; i < N; i += 32) perm_s[i] = (uint16_t)i;
+  bool unit = true;
+  if (S == 8) {  // unit bearings are the precondition of the fast inlier filter (geom::mono_inlier_fast)
+    const double* ga = a.a + (size_t)p * a.stride * 3;
+    const double* gb = a.b + (size_t)p * a.stride * 3;
+    for (int i = lane; i < N; i += 32) {
+      const double na = (ga[3 * i] * ga[3 * i] + ga[3 * i + 1] * ga[3 * i + 1]) + ga[3 * i + 2] * ga[3 * i + 2];
+      const double nb = (gb[3 * i] * gb[3 * i] + gb[3 * i + 1] * gb[3 * i + 1]) + gb[3 * i + 2] * gb[3 * i + 2];
+      unit = unit && fabs(na - 1.0) <= 1e-12 && fabs(nb - 1.0) <= 1e-12;
+    }
+  }
+  unit = __all_sync(0xFFFFFFFFu, unit);
   __syncwarp();
   if (lane == 0) {
+    st->unit_bearings = unit ? 1 : 0;
     st->iterations = 0;
     st->skipped = 0;
     st->draws = 0;
@@ -195,15 +207,33 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nh = min(kMonoChunk, st.r_end - d0);
-  if (tid >= nh) return;
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
-  const int nr = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
-                                                       a.brk + slot * 2 * geom::kMaxBrackets);
-  a.nroot[slot] = nr & 0xFFFF;
-  for (int chain = 0; chain < 2; ++chain)
-    if ((nr >> (16 + chain)) & 1) a.fb_list[atomicAdd(a.fb_count, 1u)] = (uint32_t)(slot * 2 + chain);
+  int nr = 0;
+  if (tid < nh) {
+    nr = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
+                                               a.brk + slot * 2 * geom::kMaxBrackets);
+    a.nroot[slot] = nr & 0xFFFF;
+    for (int chain = 0; chain < 2; ++chain)
+      if ((nr >> (16 + chain)) & 1) a.fb_list[atomicAdd(a.fb_count, 1u)] = (uint32_t)(slot * 2 + chain);
+  }
+  // item ranges: one reservation per warp, lanes take consecutive sub-ranges
+  const int n = (nr & 255) + ((nr >> 8) & 255);
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  unsigned base = 0;
+  if (lane == 0 && total > 0) base = atomicAdd(a.item_count, (unsigned)total);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0) + (unsigned)(incl - n);
+  if (tid < nh) {
+    a.item_base[slot] = base;
+    for (int r = 0; r < n; ++r) a.item_list[base + r] = (uint32_t)(slot * 32 + r);
+  }
 }
 
 // Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
@@ -221,103 +251,93 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacAr
   }
 }
 
-constexpr int kBackThreads = 256;
-constexpr int kMaxItems = kMonoChunk * geom::kMaxBrackets;
-__global__ void __launch_bounds__(kBackThreads, 2) mono_back_kernel(SacArgs a) {
+// thread = (draw, root) item over the whole round (grid-stride over the compacted list)
+constexpr int kItemThreads = 128;
+__global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
+  const unsigned n = *a.item_count;
+  for (unsigned it = blockIdx.x * kItemThreads + threadIdx.x; it < n; it += gridDim.x * kItemThreads) {
+    const uint32_t code = a.item_list[it];
+    const size_t slot = code >> 5;
+    const int r = code & 31;
+    const int p = (int)(slot / kRoundCap), j = (int)(slot % kRoundCap);
+    const int R0 = a.nroot[slot] & 255;
+    const double* fo = a.fsol + slot * geom::kFrontOut;
+    const double* bk = a.brk + slot * 2 * geom::kMaxBrackets + 2 * r;
+    const double* ga = a.a + (size_t)p * a.stride * 3;
+    const double* gb = a.b + (size_t)p * a.stride * 3;
+    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + a.st[p].r_begin + j) * 8;
+    double q = 0.0, M[12];
+    const int status = geom::mono_item(fo, r >= R0 ? 1 : 0, bk[0], bk[1], ga, gb, smp, &q, M);
+    a.item_status[it] = (uint8_t)status;
+    if (status == 2) {
+      a.item_q[it] = q;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) a.item_model[(size_t)it * 12 + i] = M[i];
+    }
+  }
+}
+
+// warp = draw: winner among the draw's items in the reference's order (roots in order, at
+// most the first 10 refined ones, strict <), then the inlier count of the winning model.
+constexpr int kCountThreads = 256;
+constexpr int kCountWarps = kCountThreads / 32;
+__global__ void __launch_bounds__(kCountThreads) mono_count_kernel(SacArgs a) {
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
-  extern __shared__ __align__(16) double smem_d[];
-  double* s_q = smem_d;                        // [kMaxItems][4] candidate qualities
-  double* s_z = s_q + kMaxItems * 4;           // [kMaxItems] refined roots
-  double* s_mod = s_z + kMaxItems;             // [64][12] winning model per draw
-  int* s_nr = reinterpret_cast<int*>(s_mod + kMonoChunk * 12);  // [64]
-  int* s_base = s_nr + kMonoChunk;             // [65]
-  int* s_valid = s_base + kMonoChunk + 1;      // [64]
-  uint16_t* s_item = reinterpret_cast<uint16_t*>(s_valid + kMonoChunk);  // [kMaxItems]
-  unsigned char* s_ok = reinterpret_cast<unsigned char*>(s_item + kMaxItems);  // [kMaxItems]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
   const int nh = min(kMonoChunk, st.r_end - d0);
   const size_t slot0 = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk;
-  if (tid < kMonoChunk) s_nr[tid] = (tid < nh) ? a.nroot[slot0 + tid] : 0;
+  // A draw changes the outcome of the reference loop only if its count exceeds the best count
+  // of every EARLIER draw, so counting stops as soon as that is impossible: the bound starts at
+  // the best count before this round and rises with the counts of the earlier groups of
+  // kCountWarps draws of this chunk (s_cum[g], read as the warps go).
+  constexpr int kGroups = kMonoChunk / kCountWarps;
+  __shared__ int s_cum[kGroups];
+  __shared__ double s_mod[kCountWarps][12];
+  const int bound0 = a.full ? -INT_MAX : st.best;
+  if (tid < kGroups) s_cum[tid] = bound0;
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int h = 0; h < kMonoChunk; ++h) { s_base[h] = acc; acc += (s_nr[h] & 255) + (s_nr[h] >> 8); }
-    s_base[kMonoChunk] = acc;
-  }
-  __syncthreads();
-  if (tid < kMonoChunk) {
-    const int n = (s_nr[tid] & 255) + (s_nr[tid] >> 8);
-    for (int r = 0; r < n; ++r) s_item[s_base[tid] + r] = (uint16_t)(tid * 32 + r);
-  }
-  __syncthreads();
-  // (a) items: one bracketed root each
-  const int total = s_base[kMonoChunk];
-  for (int it = tid; it < total; it += kBackThreads) {
-    const int h = s_item[it] >> 5, r = s_item[it] & 31;
-    const int R0 = s_nr[h] & 255;
-    const double* fo = a.fsol + (slot0 + h) * geom::kFrontOut;
-    const double* bk = a.brk + (slot0 + h) * 2 * geom::kMaxBrackets + 2 * r;
-    double z, E[9];
-    bool ok = geom::refine_root(fo, r >= R0 ? 1 : 0, bk[0], bk[1], &z);
-    if (ok) {
-      s_z[it] = z;
-      ok = geom::essential_from_root(fo, z, E);
+  const bool filter = st.unit_bearings != 0;
+  const geom::InlierMargins mg = geom::inlier_margins(a.threshold);
+  for (int h = warp; h < nh; h += kCountWarps) {
+    const int g = h / kCountWarps;
+    const size_t slot = slot0 + h;
+    const int nr = a.nroot[slot];
+    const int n = (nr & 255) + (nr >> 8);
+    const unsigned base = a.item_base[slot];
+    // ---- winner
+    int status = 0;
+    double q = 0.0;
+    if (lane < n) {
+      status = a.item_status[base + lane];
+      if (status == 2) q = a.item_q[base + lane];
     }
-    if (ok) geom::score_essential(E, ga, gb, a.samples + ((size_t)p * a.cap_draws + d0 + h) * 8, &s_q[it * 4]);
-    s_ok[it] = ok ? 1 : 0;
-  }
-  __syncthreads();
-  // (b) winner per draw: roots in order, at most the first 10 refined ones, strict <
-  if (tid < nh) {
-    const int n = (s_nr[tid] & 255) + (s_nr[tid] >> 8);
-    const double* fo = a.fsol + (slot0 + tid) * geom::kFrontOut;
-    double best = 1000000.0;
-    int br = -1, bc = 0, refined = 0;
-    for (int r = 0; r < n && refined < 10; ++r) {
-      const int it = s_base[tid] + r;
-      // a root counts towards the 10 as soon as it is refined, even if its E is not finite
-      double z;
-      const int R0 = s_nr[tid] & 255;
-      (void)R0;
-      if (!s_ok[it]) {
-        // distinguish "not refined" from "refined, E not finite": redo the cheap test
-        const double* bk = a.brk + (slot0 + tid) * 2 * geom::kMaxBrackets + 2 * r;
-        if (geom::refine_root(fo, r >= (s_nr[tid] & 255) ? 1 : 0, bk[0], bk[1], &z)) ++refined;
-        continue;
-      }
-      ++refined;
-      for (int c = 0; c < 4; ++c) {
-        const double q = s_q[it * 4 + c];
-        if (q < best) { best = q; br = r; bc = c; }
-      }
-    }
-    if (br >= 0) {
-      double E[9], Ra[9], Rb[9], tt[3], M[12];
-      geom::essential_from_root(fo, s_z[s_base[tid] + br], E);
-      geom::essential_candidates(E, Ra, Rb, tt);
-      geom::candidate_model(Ra, Rb, tt, bc, M);
+    const unsigned refined = __ballot_sync(0xFFFFFFFFu, status >= 1);
+    const bool eligible = status == 2 && __popc(refined & ((1u << lane) - 1u)) < 10;
+    double bq = eligible ? q : 2000000.0;   // every stored quality is < 1e6
+    int br = eligible ? lane : 64;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) s_mod[12 * tid + i] = M[i];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oq = __shfl_xor_sync(0xFFFFFFFFu, bq, o);
+      const int orr = __shfl_xor_sync(0xFFFFFFFFu, br, o);
+      if (oq < bq || (oq == bq && orr < br)) { bq = oq; br = orr; }
     }
-    s_valid[tid] = br >= 0;
-  }
-  __syncthreads();
-  // (c) inlier counts
-  const int bound = a.full ? -INT_MAX : st.best;  // a draw matters only if its count exceeds this
-  for (int h = warp; h < nh; h += kBackThreads / 32) {
+    const int v = br < 64;
+    __syncwarp();
+    if (v && lane < 12) s_mod[warp][lane] = a.item_model[(size_t)(base + br) * 12 + lane];
+    __syncwarp();
+    // ---- inlier count
     int cnt = 0;
-    const int v = s_valid[h];
     if (v) {
       double M[12], tinv[3];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) M[i] = s_mod[12 * h + i];
+      for (int i = 0; i < 12; ++i) M[i] = s_mod[warp][i];
       geom::mono_tinv(M, tinv);
       for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + lane;
@@ -325,17 +345,23 @@ __global__ void __launch_bounds__(kBackThreads, 2) mono_back_kernel(SacArgs a) {
         if (i < N) {
           const V3 f1 = {ga[3 * i], ga[3 * i + 1], ga[3 * i + 2]};
           const V3 f2 = {gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]};
-          in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
+          const int fast = filter ? geom::mono_inlier_fast(M, tinv, f1, f2, mg) : -1;
+          in = fast > 0;
+          if (fast < 0) in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
         }
         cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+        const int bound = __shfl_sync(0xFFFFFFFFu, *reinterpret_cast<volatile int*>(&s_cum[g]), 0);
         if (cnt + (N - i0 - 32) <= bound) break;  // cannot become the best model any more
       }
+      // a (possibly partial) count is a lower bound of the true one: valid bound for later groups
+      if (!a.full && lane == 0)
+        for (int g2 = g + 1; g2 < kGroups; ++g2) atomicMax(&s_cum[g2], cnt);
     }
     if (lane == 0) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
-    if (v && lane < 12) a.models[(slot0 + h) * 12 + lane] = s_mod[12 * h + lane];
+    if (v && lane < 12) a.models[slot * 12 + lane] = s_mod[warp][lane];
   }
 }
 
@@ -580,15 +606,13 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
-  KML_CUDA(cudaMemsetAsync(a.fb_count, 0, sizeof(unsigned int), s));
+  KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, sm2, s>>>(a);
   mono_isolate_deferred_kernel<<<kNumSMs * 4, kMonoChunk, sm2, s>>>(a);
-  const size_t sm3 = sizeof(double) * (kMaxItems * 5 + kMonoChunk * 12) + sizeof(int) * (3 * kMonoChunk + 1) +
-                     kMaxItems * 3 + 16;
-  ensure_smem(mono_back_kernel, sm3);
-  mono_back_kernel<<<dim3(a.P, blocks), kBackThreads, sm3, s>>>(a);
+  mono_item_kernel<<<kNumSMs * 16, kItemThreads, 0, s>>>(a);
+  mono_count_kernel<<<dim3(a.P, blocks), kCountThreads, 0, s>>>(a);
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
-  return 5;
+  return 6;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;

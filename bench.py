@@ -171,7 +171,7 @@ def workload_config(n):
             "global_batch": BATCH, "n_robots_per_gpu": N_ROBOTS, "keyframes_per_robot": N_KEYFRAMES,
             "parallelism": "robot-sharded x%d, replicated query batch + 1 ncclAllGather/step" % n if n > 1 else "single GPU",
             "l2": "256 MiB device memset before the timed region; each step re-reads ~200 MB (touched postings, 4 096 candidate "
-                  "frames, the batch) per lane, two lanes interleaved, against a 126 MB L2; the e2e arm uses a distinct batch every step"}
+                  "frames, the batch) per lane, the query lanes interleaved, against a 126 MB L2; the e2e arm uses a distinct batch every step"}
 
 
 def main():
@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kml", choices=["kml", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="query batches kept in flight per GPU")
+    ap.add_argument("--lanes", type=int, default=3, help="query batches kept in flight per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -53,6 +53,17 @@ __device__ __noinline__ double conv_s(const double* a, int da, const double* b, 
   return r;
 }
 
+// coefficient k of a*b for register polynomials of degrees DA, DB; with k a compile-time
+// constant after unrolling the guards fold away (terms in ascending i, like conv_s)
+template <int DA, int DB>
+__device__ __forceinline__ double conv_r(const double* a, const double* b, int k) {
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i <= DA; ++i)
+    if (i >= k - DB && i <= k) r = r + a[i] * b[k - i];
+  return r;
+}
+
 // ============================================================== stage 1
 // sm: this thread's slot 0.  ga/gb: the problem's correspondences (query /
 // match bearings, [N][3]); smp: the 8 sample indices.  Writes the 70 doubles
@@ -140,57 +151,63 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
           S(pr * 20 + j) = t;
         }
       const double inv = kdiv(1.0, S(c * 20 + c));  // pivot row scaled by the reciprocal
-      for (int j = c; j < 20; ++j) S(c * 20 + j) = S(c * 20 + j) * inv;
-      for (int r = 0; r < 10; ++r) {
+      // Column c itself is never read again, and rows 0..3 are neither pivot candidates nor
+      // outputs once c >= 4 (only rows 4..9 feed B(z)): their updates are skipped, every
+      // value that is used later is computed by the same operations as in the full sweep.
+      for (int j = c + 1; j < 20; ++j) S(c * 20 + j) = S(c * 20 + j) * inv;
+      for (int r = (c >= 4 ? 4 : 0); r < 10; ++r) {
         if (r == c) continue;
         const double f = S(r * 20 + c);
-        for (int j = c; j < 20; ++j) S(r * 20 + j) = S(r * 20 + j) - f * S(c * 20 + j);
+        for (int j = c + 1; j < 20; ++j) S(r * 20 + j) = S(r * 20 + j) - f * S(c * 20 + j);
       }
     }
     KML_PHASE();
     // --------------------------------- phase 4: B(z), cofactors, n(z); stash basis
-    // Bz[r][col][m] -> slot r*15 + col*5 + m (rows 0..3 of A are dead)
-#pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-      const int e = (4 + 2 * r) * 20, f = (5 + 2 * r) * 20;
-      for (int col = 0; col < 2; ++col) {
-        const int ob = 10 + 3 * col, o = r * 15 + col * 5;
-        S(o + 0) = S(e + ob + 2);
-        S(o + 1) = S(e + ob + 1) - S(f + ob + 2);
-        S(o + 2) = S(e + ob + 0) - S(f + ob + 1);
-        S(o + 3) = -S(f + ob + 0);
-        S(o + 4) = 0.0;
-      }
-      const int o = r * 15 + 10;
-      S(o + 0) = S(e + 19);
-      S(o + 1) = S(e + 18) - S(f + 19);
-      S(o + 2) = S(e + 17) - S(f + 18);
-      S(o + 3) = S(e + 16) - S(f + 17);
-      S(o + 4) = -S(f + 16);
-    }
     if (alive) {
 #pragma unroll
       for (int i = 0; i < 36; ++i) out[34 + i] = failed ? nan("") : B[i];
     }
   }
   {
-    const double* b00 = sm + 0 * STRIDE, *b01 = sm + 5 * STRIDE, *b02 = sm + 10 * STRIDE;
-    const double* b10 = sm + 15 * STRIDE, *b11 = sm + 20 * STRIDE, *b12 = sm + 25 * STRIDE;
-    const double* b20 = sm + 30 * STRIDE, *b21 = sm + 35 * STRIDE, *b22 = sm + 40 * STRIDE;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) S(45 + k) = conv_s<STRIDE>(b01, 3, b12, 4, k) - conv_s<STRIDE>(b02, 4, b11, 3, k);
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) S(53 + k) = conv_s<STRIDE>(b02, 4, b10, 3, k) - conv_s<STRIDE>(b00, 3, b12, 4, k);
-#pragma unroll 1
-    for (int k = 0; k < 7; ++k) S(61 + k) = conv_s<STRIDE>(b00, 3, b11, 3, k) - conv_s<STRIDE>(b01, 3, b10, 3, k);
-#pragma unroll 1
-    for (int k = 0; k < 11; ++k)
-      S(68 + k) = (conv_s<STRIDE>(sm + 45 * STRIDE, 7, b20, 3, k) + conv_s<STRIDE>(sm + 53 * STRIDE, 7, b21, 3, k)) +
-                  conv_s<STRIDE>(sm + 61 * STRIDE, 6, b22, 4, k);
-  }
-  if (alive) {
-#pragma unroll 1
-    for (int k = 0; k < 34; ++k) out[k] = (k < 11) ? S(68 + k) : S(45 + (k - 11));
+    // B(z) entries as polynomials in z (ascending), rows 4..9 of the reduced system:
+    // c0[r], c1[r] of degree 3, c2[r] of degree 4 (rows 0..3 of A are dead)
+    double c0[3][4], c1[3][4], c2[3][5];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int e = (4 + 2 * r) * 20, f = (5 + 2 * r) * 20;
+      c0[r][0] = S(e + 12);
+      c0[r][1] = S(e + 11) - S(f + 12);
+      c0[r][2] = S(e + 10) - S(f + 11);
+      c0[r][3] = -S(f + 10);
+      c1[r][0] = S(e + 15);
+      c1[r][1] = S(e + 14) - S(f + 15);
+      c1[r][2] = S(e + 13) - S(f + 14);
+      c1[r][3] = -S(f + 13);
+      c2[r][0] = S(e + 19);
+      c2[r][1] = S(e + 18) - S(f + 19);
+      c2[r][2] = S(e + 17) - S(f + 18);
+      c2[r][3] = S(e + 16) - S(f + 17);
+      c2[r][4] = -S(f + 16);
+    }
+    // cofactors of the third row and n(z) = det B(z); the sums keep the ascending term order
+    double p1[8], p2[8], p3[7];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p1[k] = conv_r<3, 4>(c1[0], c2[1], k) - conv_r<4, 3>(c2[0], c1[1], k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p2[k] = conv_r<4, 3>(c2[0], c0[1], k) - conv_r<3, 4>(c0[0], c2[1], k);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) p3[k] = conv_r<3, 3>(c0[0], c1[1], k) - conv_r<3, 3>(c1[0], c0[1], k);
+    if (alive) {
+#pragma unroll
+      for (int k = 0; k < 11; ++k)
+        out[k] = (conv_r<7, 3>(p1, c0[2], k) + conv_r<7, 3>(p2, c1[2], k)) + conv_r<6, 4>(p3, c2[2], k);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[11 + k] = p1[k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[19 + k] = p2[k];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) out[27 + k] = p3[k];
+    }
   }
 #undef KML_PHASE
 #undef S

@@ -198,6 +198,8 @@ def main():
     import kml
     dist = None
     if world_size > 1:
+        # NCCL prints its version / debug lines on stdout by default: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("gloo", rank=rank, world_size=world_size)
@@ -208,10 +210,15 @@ def main():
 
     kml.build()
     det = kml.LoopClosureDetector(device=local_rank)
+    n_lanes = max(1, args.lanes)
+    lanes = [det] + [det.create_lane() for _ in range(n_lanes - 1)]
     if world_size > 1:
-        uid = [kml.LoopClosureDetector.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        det.comm_init(world_size, rank, uid[0])
+        # one communicator per lane: lane i of every rank forms its own all-gather group, so the
+        # lanes' collectives never have to be ordered against each other
+        uids = [[kml.LoopClosureDetector.comm_unique_id() for _ in lanes] if rank == 0 else None]
+        dist.broadcast_object_list(uids, src=0)
+        for ln, uid in zip(lanes, uids[0]):
+            ln.comm_init(world_size, rank, uid)
     world, robots = build_world(rank, log)
     fill_detector(det, world, robots, log)
     n_batches = args.steps + args.warmup
@@ -223,9 +230,6 @@ def main():
     # ---------------- resident arm: device-timed steps
     # Two query lanes (kml_create_lane) keep two batches in flight on the GPU: the tail rounds
     # of one batch's RANSAC and the host-side candidate selection overlap the other batch.
-    # (The sharded N>1 path stays single-lane: one communicator, one collective order.)
-    n_lanes = 1 if sharded else max(1, args.lanes)
-    lanes = [det] + [det.create_lane() for _ in range(n_lanes - 1)]
     for li, ln in enumerate(lanes):
         for i in range(args.warmup):
             ln.query_batch_upload(*batches[(li + i) % len(batches)])

@@ -539,6 +539,20 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
     exhausted |= stm[p].exhausted || sts[p].exhausted;
     nmono_ok += out->status[p] != 1;
   }
+  if (getenv("KML_DEBUG_TIMING")) {  // consumed vs evaluated draws (SacState::r_begin ends at the last evaluated draw)
+    uint64_t em = 0, es = 0;
+    int hist[8] = {0};
+    for (int p = 0; p < P; ++p) {
+      em += (uint64_t)stm[p].r_begin;
+      es += (uint64_t)sts[p].r_begin;
+      const int d = stm[p].draws;
+      ++hist[d <= 16 ? 0 : d <= 32 ? 1 : d <= 64 ? 2 : d <= 128 ? 3 : d <= 256 ? 4 : d <= 512 ? 5 : d <= 1000 ? 6 : 7];
+    }
+    fprintf(stderr, "[kml] mono draws consumed %llu evaluated %llu; stereo consumed %llu evaluated %llu; "
+            "mono consumed histogram <=16:%d <=32:%d <=64:%d <=128:%d <=256:%d <=512:%d <=1000:%d more:%d\n",
+            (unsigned long long)hm, (unsigned long long)em, (unsigned long long)hs, (unsigned long long)es,
+            hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
+  }
   h->stats.mono_hypotheses_last = hm;
   h->stats.stereo_hypotheses_last = hs;
   h->stats.mono_residuals_last = rm;

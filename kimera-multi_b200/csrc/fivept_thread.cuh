@@ -64,6 +64,50 @@ __device__ __forceinline__ double conv_r(const double* a, const double* b, int k
   return r;
 }
 
+// One Gauss-Jordan pivot step (column C) of the 10x20 constraint matrix in strided shared
+// memory, partial pivoting.  C is a compile-time constant: the scaled pivot row sits in
+// registers and every row update is a straight line of loads / stores at immediate offsets.
+// Column C itself is never read again, and rows 0..3 are neither pivot candidates nor
+// outputs once C >= 4 (only rows 4..9 feed B(z)): those updates are skipped; every value
+// that is used later is produced by the same operations as in a full sweep.
+template <int STRIDE, int C>
+__device__ __forceinline__ void gj_step(double* sm, bool& failed) {
+#define S(i) sm[(i) * STRIDE]
+  int pr = C;
+  double pv = fabs(S(C * 20 + C));
+#pragma unroll
+  for (int r = C + 1; r < 10; ++r) {
+    const double v = fabs(S(r * 20 + C));
+    if (v > pv) { pv = v; pr = r; }
+  }
+  if (!(pv > 0.0)) failed = true;
+  if (pr != C) {
+    double* rowp = sm + pr * 20 * STRIDE;
+#pragma unroll
+    for (int j = C; j < 20; ++j) {
+      const double t = S(C * 20 + j);
+      S(C * 20 + j) = rowp[j * STRIDE];
+      rowp[j * STRIDE] = t;
+    }
+  }
+  const double inv = kdiv(1.0, S(C * 20 + C));  // pivot row scaled by the reciprocal
+  double prow[20];
+#pragma unroll
+  for (int j = C + 1; j < 20; ++j) {
+    prow[j] = S(C * 20 + j) * inv;
+    S(C * 20 + j) = prow[j];
+  }
+#pragma unroll 1
+  for (int r = (C >= 4 ? 4 : 0); r < 10; ++r) {
+    if (r == C) continue;
+    double* row = sm + r * 20 * STRIDE;
+    const double f = row[C * STRIDE];
+#pragma unroll
+    for (int j = C + 1; j < 20; ++j) row[j * STRIDE] = row[j * STRIDE] - f * prow[j];
+  }
+#undef S
+}
+
 // ============================================================== stage 1
 // sm: this thread's slot 0.  ga/gb: the problem's correspondences (query /
 // match bearings, [N][3]); smp: the 8 sample indices.  Writes the 70 doubles
@@ -79,96 +123,92 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
 #pragma unroll
   for (int k = 0; k < 8; ++k) sidx[k] = alive ? (int)smp[k] : 0;
   // ------------------------------------------------ phase 1: null space
-  // A9[i][j] = Q[j][i] = f_m[j][i%3] * f_q[j][i/3]   (slots 0..44, [i*5+j])
-#pragma unroll 1
-  for (int j = 0; j < 5; ++j) {
-    const double* fq = ga + 3 * sidx[j];
-    const double* fm = gb + 3 * sidx[j];
-    const double q0 = fq[0], q1 = fq[1], q2 = fq[2], m0 = fm[0], m1 = fm[1], m2 = fm[2];
-    S(0 * 5 + j) = m0 * q0; S(1 * 5 + j) = m1 * q0; S(2 * 5 + j) = m2 * q0;
-    S(3 * 5 + j) = m0 * q1; S(4 * 5 + j) = m1 * q1; S(5 * 5 + j) = m2 * q1;
-    S(6 * 5 + j) = m0 * q2; S(7 * 5 + j) = m1 * q2; S(8 * 5 + j) = m2 * q2;
-  }
-#pragma unroll 1
-  for (int k = 0; k < 5; ++k) {
-    double s2 = 0.0;
-    for (int i = k; i < 9; ++i) s2 = s2 + S(i * 5 + k) * S(i * 5 + k);
-    const double nrm = ksqrt(s2);
-    const double alpha = (S(k * 5 + k) >= 0.0) ? -nrm : nrm;
-    for (int i = 0; i < 9; ++i) S(45 + k * 9 + i) = (i < k) ? 0.0 : S(i * 5 + k);
-    S(45 + k * 9 + k) = S(45 + k * 9 + k) - alpha;
-    double n2 = 0.0;
-    for (int i = k; i < 9; ++i) n2 = n2 + S(45 + k * 9 + i) * S(45 + k * 9 + i);
-    S(90 + k) = n2;
-    if (n2 > 0.0) {
-      for (int j = k; j < 5; ++j) {
-        double d = 0.0;
-        for (int i = k; i < 9; ++i) d = d + S(45 + k * 9 + i) * S(i * 5 + j);
-        const double f = kdiv(2.0 * d, n2);
-        for (int i = k; i < 9; ++i) S(i * 5 + j) = S(i * 5 + j) - f * S(45 + k * 9 + i);
+  // A9[i][j] = Q[j][i] = f_m[j][i%3] * f_q[j][i/3]; five Householder reflections, then the last
+  // four columns of Q are the basis.  Everything is unrolled with static indices, so the 9x5
+  // matrix, the reflectors and the basis live in registers.
+  double B[36];
+  {
+    double A[45], V[45], N2[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const double* fq = ga + 3 * sidx[j];
+      const double* fm = gb + 3 * sidx[j];
+      const double q0 = fq[0], q1 = fq[1], q2 = fq[2], m0 = fm[0], m1 = fm[1], m2 = fm[2];
+      A[0 * 5 + j] = m0 * q0; A[1 * 5 + j] = m1 * q0; A[2 * 5 + j] = m2 * q0;
+      A[3 * 5 + j] = m0 * q1; A[4 * 5 + j] = m1 * q1; A[5 * 5 + j] = m2 * q1;
+      A[6 * 5 + j] = m0 * q2; A[7 * 5 + j] = m1 * q2; A[8 * 5 + j] = m2 * q2;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int i = k; i < 9; ++i) s2 = s2 + A[i * 5 + k] * A[i * 5 + k];
+      const double nrm = ksqrt(s2);
+      const double alpha = (A[k * 5 + k] >= 0.0) ? -nrm : nrm;
+#pragma unroll
+      for (int i = k; i < 9; ++i) V[k * 9 + i] = A[i * 5 + k];
+      V[k * 9 + k] = V[k * 9 + k] - alpha;
+      double n2 = 0.0;
+#pragma unroll
+      for (int i = k; i < 9; ++i) n2 = n2 + V[k * 9 + i] * V[k * 9 + i];
+      N2[k] = n2;
+      if (n2 > 0.0) {
+#pragma unroll
+        for (int j = k; j < 5; ++j) {
+          double d = 0.0;
+#pragma unroll
+          for (int i = k; i < 9; ++i) d = d + V[k * 9 + i] * A[i * 5 + j];
+          const double f = kdiv(2.0 * d, n2);
+#pragma unroll
+          for (int i = k; i < 9; ++i) A[i * 5 + j] = A[i * 5 + j] - f * V[k * 9 + i];
+        }
       }
     }
-  }
-#pragma unroll 1
-  for (int b = 0; b < 4; ++b) {
-    for (int i = 0; i < 9; ++i) S(95 + i) = (i == 5 + b) ? 1.0 : 0.0;
-    for (int k = 4; k >= 0; --k) {
-      const double n2 = S(90 + k);
-      if (!(n2 > 0.0)) continue;
-      double d = 0.0;
-      for (int i = k; i < 9; ++i) d = d + S(45 + k * 9 + i) * S(95 + i);
-      const double f = kdiv(2.0 * d, n2);
-      for (int i = k; i < 9; ++i) S(95 + i) = S(95 + i) - f * S(45 + k * 9 + i);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double e[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) e[i] = (i == 5 + b) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 4; k >= 0; --k) {
+        const double n2 = N2[k];
+        if (!(n2 > 0.0)) continue;
+        double d = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) d = d + V[k * 9 + i] * e[i];
+        const double f = kdiv(2.0 * d, n2);
+#pragma unroll
+        for (int i = k; i < 9; ++i) e[i] = e[i] - f * V[k * 9 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) B[b * 9 + i] = e[i];
     }
-    for (int i = 0; i < 9; ++i) S(104 + b * 9 + i) = S(95 + i);
   }
-  KML_PHASE();
+  // the basis goes out now (E(z) is rebuilt from it downstream); a singular constraint system,
+  // known only after the elimination, overwrites it with NaN
+  if (alive) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) out[34 + i] = B[i];
+  }
   // ------------------------------------- phase 2: constraint matrix 10x20
   {
-    double B[36];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) B[i] = S(104 + i);
 #define SA(i) S(i)
 #include "fivept_build.inc"
 #undef SA
-    KML_PHASE();
-    // ----------------------------------------------- phase 3: Gauss-Jordan
-    // (columns < c of every row are exact zeros / unit entries that are never
-    // read again, so the row operations start at column c: same used values)
+  }
+  KML_PHASE();
+  // ----------------------------------------------- phase 3: Gauss-Jordan
+  gj_step<STRIDE, 0>(sm, failed); gj_step<STRIDE, 1>(sm, failed); gj_step<STRIDE, 2>(sm, failed);
+  gj_step<STRIDE, 3>(sm, failed); gj_step<STRIDE, 4>(sm, failed); gj_step<STRIDE, 5>(sm, failed);
+  gj_step<STRIDE, 6>(sm, failed); gj_step<STRIDE, 7>(sm, failed); gj_step<STRIDE, 8>(sm, failed);
+  gj_step<STRIDE, 9>(sm, failed);
+  KML_PHASE();
+  if (alive && failed) {
 #pragma unroll 1
-    for (int c = 0; c < 10; ++c) {
-      int pr = c;
-      double pv = fabs(S(c * 20 + c));
-      for (int r = c + 1; r < 10; ++r) {
-        const double v = fabs(S(r * 20 + c));
-        if (v > pv) { pv = v; pr = r; }
-      }
-      if (!(pv > 0.0)) failed = true;
-      if (pr != c)
-        for (int j = c; j < 20; ++j) {
-          const double t = S(c * 20 + j);
-          S(c * 20 + j) = S(pr * 20 + j);
-          S(pr * 20 + j) = t;
-        }
-      const double inv = kdiv(1.0, S(c * 20 + c));  // pivot row scaled by the reciprocal
-      // Column c itself is never read again, and rows 0..3 are neither pivot candidates nor
-      // outputs once c >= 4 (only rows 4..9 feed B(z)): their updates are skipped, every
-      // value that is used later is computed by the same operations as in the full sweep.
-      for (int j = c + 1; j < 20; ++j) S(c * 20 + j) = S(c * 20 + j) * inv;
-      for (int r = (c >= 4 ? 4 : 0); r < 10; ++r) {
-        if (r == c) continue;
-        const double f = S(r * 20 + c);
-        for (int j = c + 1; j < 20; ++j) S(r * 20 + j) = S(r * 20 + j) - f * S(c * 20 + j);
-      }
-    }
-    KML_PHASE();
-    // --------------------------------- phase 4: B(z), cofactors, n(z); stash basis
-    if (alive) {
-#pragma unroll
-      for (int i = 0; i < 36; ++i) out[34 + i] = failed ? nan("") : B[i];
-    }
+    for (int i = 0; i < 36; ++i) out[34 + i] = nan("");
   }
   {
+    // --------------------------------- phase 4: B(z), cofactors, n(z)
     // B(z) entries as polynomials in z (ascending), rows 4..9 of the reduced system:
     // c0[r], c1[r] of degree 3, c2[r] of degree 4 (rows 0..3 of A are dead)
     double c0[3][4], c1[3][4], c2[3][5];

@@ -316,7 +316,7 @@ __device__ __noinline__ int sturm_count_s(const double* sm, unsigned long long d
 // so that it does not stall the other 31 lanes of every warp); mode 1: bisection on the count.
 template <int STRIDE>
 __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, int len, double* __restrict__ brk,
-                                           int mode, bool* deferred) {
+                                           int mode, bool* deferred, int only_j = -1) {
   const int d0 = (int)(degs & 15u);
   if (d0 < 1) return 0;
   const double* c0 = sm + tri_off(0) * STRIDE;
@@ -328,23 +328,38 @@ __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, 
   // cells equals the Sturm count they are the isolating brackets, else bisect on the count
   unsigned cells = 0u;
   int nb = 0;
-  double fprev = horner_s<STRIDE>(c0, d0, -1.0);
-  for (int i = 1; i <= kTRootGrid; ++i) {
-    const double fi = horner_s<STRIDE>(c0, d0, -1.0 + (double)i * (2.0 / kTRootGrid));
-    if ((fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0) {
-      cells |= 1u << (i - 1);
-      ++nb;
+  // (mode 1 is only entered for chains the grid pass could not separate: no need to repeat it)
+  if (mode == 0) {
+    // The polynomial goes to registers, zero-padded to degree 10: a Horner recurrence that
+    // starts from padding zeros reaches c[d0] exactly (0*x + c = c for finite x), so the
+    // values equal those of the degree-d0 recurrence up to the sign of a zero, which the
+    // comparisons below do not see.  Sign bits of the 33 grid values, then the cells.
+    double cr[11];
+#pragma unroll
+    for (int i = 0; i <= 10; ++i) cr[i] = (i <= d0) ? c0[i * STRIDE] : 0.0;
+    unsigned long long neg = 0ull, pos = 0ull, zer = 0ull;
+#pragma unroll 3
+    for (int i = 0; i <= kTRootGrid; ++i) {
+      const double x = -1.0 + (double)i * (2.0 / kTRootGrid);
+      double r = cr[10];
+#pragma unroll
+      for (int k = 9; k >= 0; --k) r = r * x + cr[k];
+      neg |= (unsigned long long)(r < 0.0) << i;
+      pos |= (unsigned long long)(r > 0.0) << i;
+      zer |= (unsigned long long)(r == 0.0) << i;
     }
-    fprev = fi;
+    // cell i-1 = (x_{i-1}, x_i] brackets a root: sign change across it, or f(x_i) == 0
+    cells = (unsigned)((((neg << 1) & pos) | ((pos << 1) & neg) | zer) >> 1);
+    nb = __popc(cells);
   }
-  const bool grid_ok = (nb == R);
+  const bool grid_ok = (mode == 0) && (nb == R);
   if (mode == 0 && !grid_ok) {
     *deferred = true;
     return R;
   }
-  if (mode == 1 && grid_ok) return R;  // already bracketed by the grid pass
   int cell = -1;
-  for (int j = 0; j < R; ++j) {
+  // mode 1: the bisections of the R roots are independent, the caller asks for one of them
+  for (int j = (mode == 1 ? only_j : 0); j < (mode == 1 ? min(only_j + 1, R) : R); ++j) {
     double lo = -1.0, hi = 1.0;
     if (grid_ok) {
       do { ++cell; } while (!((cells >> cell) & 1u));
@@ -386,7 +401,7 @@ __device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, do
 }
 // the deferred case of one (draw, chain): brackets by bisection on the Sturm count
 template <int STRIDE>
-__device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain,
+__device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain, int root,
                                              double* __restrict__ brk) {
 #define S(i) sm[(i) * STRIDE]
 #pragma unroll 1
@@ -394,7 +409,7 @@ __device__ void mono_isolate_deferred_thread(double* sm, const double* __restric
   unsigned long long degs;
   bool dummy = false;
   const int len = sturm_build_s<STRIDE>(sm, chain != 0, &degs);
-  isolate_unit_s<STRIDE>(sm, degs, len, brk, 1, &dummy);
+  isolate_unit_s<STRIDE>(sm, degs, len, brk, 1, &dummy, root);
 #undef S
 }
 

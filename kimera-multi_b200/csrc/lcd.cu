@@ -384,7 +384,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     h->d_nsol.scratch((size_t)P * kRoundCap);
     h->d_esol.scratch((size_t)P * kRoundCap * 70);
     h->d_brk.scratch((size_t)P * kRoundCap * 40);
-    h->d_fb_list.scratch((size_t)P * kRoundCap * 2 + 2);
+    h->d_fb_list.scratch((size_t)P * kRoundCap * 20 + 2);
     // (draw, root) items of a round: up to 20 brackets per draw (both Sturm chains)
     const size_t max_items = (size_t)P * kRoundCap * 20;
     h->d_item_base.scratch((size_t)P * kRoundCap);

@@ -216,7 +216,11 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
                                                a.brk + slot * 2 * geom::kMaxBrackets);
     a.nroot[slot] = nr & 0xFFFF;
     for (int chain = 0; chain < 2; ++chain)
-      if ((nr >> (16 + chain)) & 1) a.fb_list[atomicAdd(a.fb_count, 1u)] = (uint32_t)(slot * 2 + chain);
+      if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
+        const int R = chain ? ((nr >> 8) & 255) : (nr & 255);
+        const unsigned at = atomicAdd(a.fb_count, (unsigned)R);
+        for (int j = 0; j < R; ++j) a.fb_list[at + j] = (uint32_t)(((slot * 2 + chain) << 4) | j);
+      }
   }
   // item ranges: one reservation per warp, lanes take consecutive sub-ranges
   const int n = (nr & 255) + ((nr >> 8) & 255);
@@ -237,16 +241,17 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
 }
 
 // Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
-// separate the roots, ~8 % of the chains): compacted work list, one item per thread.
+// separate the roots, ~8 % of the chains): compacted work list, one (draw, chain, root)
+// bisection per thread.
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const unsigned n = *a.fb_count;
   for (unsigned it = blockIdx.x * kMonoChunk + threadIdx.x; it < n; it += gridDim.x * kMonoChunk) {
     const uint32_t item = a.fb_list[it];
-    const size_t slot = item >> 1;
-    const int chain = item & 1;
+    const size_t slot = item >> 5;
+    const int chain = (item >> 4) & 1, root = item & 15;
     const int R0 = a.nroot[slot] & 255;
-    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * geom::kFrontOut, chain,
+    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * geom::kFrontOut, chain, root,
                                                    a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
   }
 }

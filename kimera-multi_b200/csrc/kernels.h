@@ -106,7 +106,8 @@ struct SacArgs {
   int32_t* n_inliers;    // [P]
 };
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
-constexpr int kStereoChunk = 128;  // hypotheses per CTA (stereo) and size of round 0
+constexpr int kStereoChunk = 64;    // hypotheses per CTA (stereo) and size of round 0
+constexpr int kStereoThreads = 128; // threads of a stereo CTA (4 counting warps)
 constexpr int kSacRounds = 6;      // 64,64,128,256,512 new draws, then everything that is left
 constexpr int kRoundCap = 512;     // most new draws any round evaluates per problem
 // upper bound of NEW draws evaluated per problem in round r (doubling schedule)

@@ -282,11 +282,15 @@ __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
   }
 }
 
-// warp = draw: winner among the draw's items in the reference's order (roots in order, at
-// most the first 10 refined ones, strict <), then the inlier count of the winning model.
+// CTA = 64 draws of one problem.  (1) thread = draw: winner among the draw's items in the
+// reference's order (roots in order, at most the first 10 refined ones, strict <); the item
+// records are fetched as two batches of independent loads.  (2) warp = draw: inlier count of
+// the winning model over the problem's correspondences, staged once per CTA in shared memory.
 constexpr int kCountThreads = 256;
 constexpr int kCountWarps = kCountThreads / 32;
-__global__ void __launch_bounds__(kCountThreads) mono_count_kernel(SacArgs a) {
+template <bool STAGED>  // STAGED: the problem's bearings fit in shared memory (else read through L1)
+__global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
@@ -294,8 +298,6 @@ __global__ void __launch_bounds__(kCountThreads) mono_count_kernel(SacArgs a) {
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* ga = a.a + (size_t)p * a.stride * 3;
-  const double* gb = a.b + (size_t)p * a.stride * 3;
   const int nh = min(kMonoChunk, st.r_end - d0);
   const size_t slot0 = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk;
   // A draw changes the outcome of the reference loop only if its count exceeds the best count
@@ -304,52 +306,76 @@ __global__ void __launch_bounds__(kCountThreads) mono_count_kernel(SacArgs a) {
   // kCountWarps draws of this chunk (s_cum[g], read as the warps go).
   constexpr int kGroups = kMonoChunk / kCountWarps;
   __shared__ int s_cum[kGroups];
-  __shared__ double s_mod[kCountWarps][12];
+  __shared__ int s_valid[kMonoChunk];
+  __shared__ double s_mod[kMonoChunk][12];
+  double* s_f = smem_d;  // [6][NP] structure-of-arrays copy of the bearings: f1.xyz, f2.xyz
+  const int NP = (N + 31) & ~31;
+  const double* ga = a.a + (size_t)p * a.stride * 3;
+  const double* gb = a.b + (size_t)p * a.stride * 3;
+  if (STAGED) {
+    for (int f = tid; f < 3 * N; f += kCountThreads) {
+      const int i = f / 3, c = f - 3 * i;
+      s_f[c * NP + i] = ga[f];
+      s_f[(3 + c) * NP + i] = gb[f];
+    }
+  }
   const int bound0 = a.full ? -INT_MAX : st.best;
   if (tid < kGroups) s_cum[tid] = bound0;
+  if (tid < kMonoChunk) {
+    int v = 0;
+    if (tid < nh) {
+      const size_t slot = slot0 + tid;
+      const int nr = a.nroot[slot];
+      const int n = (nr & 255) + (nr >> 8);
+      const unsigned base = a.item_base[slot];
+      int status[geom::kMaxBrackets];
+      double q[geom::kMaxBrackets];
+#pragma unroll
+      for (int r = 0; r < geom::kMaxBrackets; ++r) status[r] = (r < n) ? (int)a.item_status[base + r] : 0;
+#pragma unroll
+      for (int r = 0; r < geom::kMaxBrackets; ++r) q[r] = (status[r] == 2) ? a.item_q[base + r] : 0.0;
+      double best = 1000000.0;
+      int br = -1, refined = 0;
+#pragma unroll
+      for (int r = 0; r < geom::kMaxBrackets; ++r) {
+        if (status[r] >= 1 && refined < 10) {
+          if (status[r] == 2 && q[r] < best) { best = q[r]; br = r; }
+        }
+        refined += status[r] >= 1;
+      }
+      if (br >= 0) {
+        v = 1;
+        const double* m = a.item_model + (size_t)(base + br) * 12;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s_mod[tid][i] = m[i];
+      }
+    }
+    s_valid[tid] = v;
+  }
   __syncthreads();
   const bool filter = st.unit_bearings != 0;
   const geom::InlierMargins mg = geom::inlier_margins(a.threshold);
   for (int h = warp; h < nh; h += kCountWarps) {
     const int g = h / kCountWarps;
-    const size_t slot = slot0 + h;
-    const int nr = a.nroot[slot];
-    const int n = (nr & 255) + (nr >> 8);
-    const unsigned base = a.item_base[slot];
-    // ---- winner
-    int status = 0;
-    double q = 0.0;
-    if (lane < n) {
-      status = a.item_status[base + lane];
-      if (status == 2) q = a.item_q[base + lane];
-    }
-    const unsigned refined = __ballot_sync(0xFFFFFFFFu, status >= 1);
-    const bool eligible = status == 2 && __popc(refined & ((1u << lane) - 1u)) < 10;
-    double bq = eligible ? q : 2000000.0;   // every stored quality is < 1e6
-    int br = eligible ? lane : 64;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double oq = __shfl_xor_sync(0xFFFFFFFFu, bq, o);
-      const int orr = __shfl_xor_sync(0xFFFFFFFFu, br, o);
-      if (oq < bq || (oq == bq && orr < br)) { bq = oq; br = orr; }
-    }
-    const int v = br < 64;
-    __syncwarp();
-    if (v && lane < 12) s_mod[warp][lane] = a.item_model[(size_t)(base + br) * 12 + lane];
-    __syncwarp();
-    // ---- inlier count
+    const int v = s_valid[h];
     int cnt = 0;
     if (v) {
       double M[12], tinv[3];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) M[i] = s_mod[warp][i];
+      for (int i = 0; i < 12; ++i) M[i] = s_mod[h][i];
       geom::mono_tinv(M, tinv);
       for (int i0 = 0; i0 < N; i0 += 32) {
         const int i = i0 + lane;
         bool in = false;
         if (i < N) {
-          const V3 f1 = {ga[3 * i], ga[3 * i + 1], ga[3 * i + 2]};
-          const V3 f2 = {gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]};
+          V3 f1, f2;
+          if (STAGED) {
+            f1 = {s_f[i], s_f[NP + i], s_f[2 * NP + i]};
+            f2 = {s_f[3 * NP + i], s_f[4 * NP + i], s_f[5 * NP + i]};
+          } else {
+            f1 = {ga[3 * i], ga[3 * i + 1], ga[3 * i + 2]};
+            f2 = {gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]};
+          }
           const int fast = filter ? geom::mono_inlier_fast(M, tinv, f1, f2, mg) : -1;
           in = fast > 0;
           if (fast < 0) in = geom::mono_residual(M, tinv, f1, f2) < a.threshold;
@@ -366,12 +392,12 @@ __global__ void __launch_bounds__(kCountThreads) mono_count_kernel(SacArgs a) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
     }
-    if (v && lane < 12) a.models[slot * 12 + lane] = s_mod[warp][lane];
+    if (v && lane < 12) a.models[(slot0 + h) * 12 + lane] = s_mod[h][lane];
   }
 }
 
 // ---------------------------------------------------------- stereo chunk
-__global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
+__global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
   const SacState st = a.st[p];
@@ -385,7 +411,7 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  for (int i = tid; i < 3 * N; i += kStereoChunk) {
+  for (int i = tid; i < 3 * N; i += kStereoThreads) {
     s1[i] = ga[i];
     s2[i] = gb[i];
   }
@@ -400,7 +426,14 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
     for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
   }
   __syncthreads();
-  for (int h = warp; h < nh; h += kStereoChunk / 32) {
+  // running bound as in mono_count_kernel: a draw matters only if it beats every earlier one
+  constexpr int kWarps = kStereoThreads / 32, kGroups = kStereoChunk / kWarps;
+  __shared__ int s_cum[kGroups];
+  const int bound0 = a.full ? -INT_MAX : st.best;
+  if (tid < kGroups) s_cum[tid] = bound0;
+  __syncthreads();
+  for (int h = warp; h < nh; h += kWarps) {
+    const int g = h / kWarps;
     double M[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) M[i] = smod[12 * h + i];
@@ -412,7 +445,11 @@ __global__ void __launch_bounds__(kStereoChunk) stereo_chunk_kernel(SacArgs a) {
         in = geom::arun_sqdist(M, s1[3 * i], s1[3 * i + 1], s1[3 * i + 2], s2[3 * i],
                                s2[3 * i + 1], s2[3 * i + 2]) < a.sq_crit;
       cnt += __popc(__ballot_sync(0xFFFFFFFFu, in));
+      const int bound = __shfl_sync(0xFFFFFFFFu, *reinterpret_cast<volatile int*>(&s_cum[g]), 0);
+      if (cnt + (N - i0 - 32) <= bound) break;
     }
+    if (!a.full && lane == 0)
+      for (int g2 = g + 1; g2 < kGroups; ++g2) atomicMax(&s_cum[g2], cnt);
     if (lane == 0) {
       a.valid[(size_t)p * a.cap_draws + d0 + h] = 1;  // threept_arun always yields a model
       a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
@@ -615,7 +652,13 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, sm2, s>>>(a);
   mono_isolate_deferred_kernel<<<kNumSMs * 4, kMonoChunk, sm2, s>>>(a);
   mono_item_kernel<<<kNumSMs * 16, kItemThreads, 0, s>>>(a);
-  mono_count_kernel<<<dim3(a.P, blocks), kCountThreads, 0, s>>>(a);
+  const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);
+  if (sm4 <= 96 * 1024) {
+    ensure_smem(mono_count_kernel<true>, sm4);
+    mono_count_kernel<true><<<dim3(a.P, blocks), kCountThreads, sm4, s>>>(a);
+  } else {
+    mono_count_kernel<false><<<dim3(a.P, blocks), kCountThreads, 0, s>>>(a);
+  }
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 6;
 }
@@ -625,7 +668,7 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   ensure_smem(stereo_chunk_kernel, sm);
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
-  stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoChunk, sm, s>>>(a);
+  stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoThreads, sm, s>>>(a);
   sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }

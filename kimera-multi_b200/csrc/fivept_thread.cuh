@@ -414,9 +414,16 @@ __device__ void mono_isolate_deferred_thread(double* sm, const double* __restric
 }
 
 // ============================================================== stage 3
-__device__ __noinline__ double horner_l(const double* c, int deg, double x) {
-  double r = c[deg];
-  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i];
+
+// Fixed-degree Horner on register coefficients.  Callers pad with the polynomial's own
+// zero leading coefficients: the recurrence then reaches the true leading coefficient
+// exactly (0*x + c = c for finite x), so the value equals the variable-degree recurrence
+// up to the sign of a zero, which none of the uses below can see.
+template <int DEG>
+__device__ __forceinline__ double horner_r(const double* c, double x) {
+  double r = c[DEG];
+#pragma unroll
+  for (int i = DEG - 1; i >= 0; --i) r = r * x + c[i];
   return r;
 }
 
@@ -425,27 +432,28 @@ __device__ __noinline__ double horner_l(const double* c, int deg, double x) {
 __device__ __noinline__ bool refine_root(const double* __restrict__ fo, int chain, double lo, double hi,
                                          double* z_out) {
   double c0[11], c1[10];
-  int d0 = 10;
-  while (d0 > 0 && fo[chain ? 10 - d0 : d0] == 0.0) --d0;
-  for (int i = 0; i <= d0; ++i) c0[i] = fo[chain ? 10 - i : i];
-  for (int i = 0; i < d0; ++i) c1[i] = (double)(i + 1) * c0[i + 1];
-  const int d1 = d0 - 1;
-  double flo = horner_l(c0, d0, lo);
-  const double fhi = horner_l(c0, d0, hi);
+#pragma unroll
+  for (int i = 0; i <= 10; ++i) c0[i] = chain ? fo[10 - i] : fo[i];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) c1[i] = (double)(i + 1) * c0[i + 1];
+  double flo = horner_r<10>(c0, lo);
+  const double fhi = horner_r<10>(c0, hi);
   double root;
   if (fhi == 0.0) {
     root = hi;
   } else {
     if (!((flo < 0.0 && fhi > 0.0) || (flo > 0.0 && fhi < 0.0))) return false;
+#pragma unroll 1
     for (int it = 0; it < kTRootBisect; ++it) {
       const double mid = 0.5 * (lo + hi);
-      const double fm = horner_l(c0, d0, mid);
+      const double fm = horner_r<10>(c0, mid);
       if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else { hi = mid; }
     }
     double x = 0.5 * (lo + hi);
+#pragma unroll 1
     for (int it = 0; it < kTRootNewton; ++it) {
-      const double fx = horner_l(c0, d0, x);
-      const double dfx = horner_l(c1, d1, x);
+      const double fx = horner_r<10>(c0, x);
+      const double dfx = horner_r<9>(c1, x);
       if ((fx < 0.0) == (flo < 0.0)) { lo = x; flo = fx; } else { hi = x; }
       double xn = x - kdiv(fx, dfx);
       if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
@@ -463,9 +471,16 @@ __device__ __noinline__ bool refine_root(const double* __restrict__ fo, int chai
 
 // E(z) = x X + y Y + z Z + W with x = p1(z)/p3(z), y = p2(z)/p3(z); false if not finite.
 __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, double z, double* E) {
-  const double d = horner_l(fo + 27, 6, z);
-  const double x = kdiv(horner_l(fo + 11, 7, z), d);
-  const double y = kdiv(horner_l(fo + 19, 7, z), d);
+  double c[8];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) c[i] = fo[27 + i];
+  const double d = horner_r<6>(c, z);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i] = fo[11 + i];
+  const double x = kdiv(horner_r<7>(c, z), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i] = fo[19 + i];
+  const double y = kdiv(horner_r<7>(c, z), d);
   bool ok = true;
 #pragma unroll 1
   for (int e = 0; e < 9; ++e) {

@@ -217,8 +217,18 @@ def main():
         # lanes' collectives never have to be ordered against each other
         uids = [[kml.LoopClosureDetector.comm_unique_id() for _ in lanes] if rank == 0 else None]
         dist.broadcast_object_list(uids, src=0)
-        for ln, uid in zip(lanes, uids[0]):
-            ln.comm_init(world_size, rank, uid)
+        # NCCL prints its version line on stdout while a communicator is created: point fd 1 at
+        # stderr for the duration so that stdout carries nothing but the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            for ln, uid in zip(lanes, uids[0]):
+                ln.comm_init(world_size, rank, uid)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     world, robots = build_world(rank, log)
     fill_detector(det, world, robots, log)
     n_batches = args.steps + args.warmup

@@ -256,6 +256,65 @@ def test_ransac_batches(oracle, gpu_lcd):
     assert (g["best_draw"] == -1).all() and (g["n_inliers"] == 0).all()
 
 
+def _nister_case(rng, N, kind):
+    """Synthetic two-view problem [N,3] bearings; `kind` picks the numerically awkward variant."""
+    from scipy.spatial.transform import Rotation as Rot
+    X = np.c_[rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(2, 12, N)]
+    R = Rot.from_rotvec(rng.normal(size=3) * 0.15).as_matrix()
+    t = rng.uniform(-1, 1, 3)
+    if kind == "low_parallax":          # baseline tiny against depth: |det| of the triangulation ~ 1e-6
+        t = t * 1e-3
+    if kind == "far_points":            # a third of the structure at 1e4 baselines
+        X[: N // 3] *= 2e3
+    if kind == "near_centres":          # structure around both camera centres (tiny |p|, |q|)
+        X[: N // 4] = rng.normal(size=(N // 4, 3)) * 1e-3
+        X[N // 4: N // 2] = t + rng.normal(size=(N // 2 - N // 4, 3)) * 1e-3
+    X2 = (X - t) @ R
+    a = X + rng.normal(size=X.shape) * 1e-3 * np.linalg.norm(X, axis=1, keepdims=True)
+    b = X2 + rng.normal(size=X.shape) * 1e-3 * np.linalg.norm(X2, axis=1, keepdims=True)
+    out = rng.random(N) < 0.3
+    b[out] = rng.normal(size=(out.sum(), 3))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    if kind == "non_unit":              # bearings that are not unit vectors: filter must switch itself off
+        a *= rng.uniform(0.5, 2.0, (N, 1))
+        b *= rng.uniform(0.5, 2.0, (N, 1))
+    if kind == "duplicates":            # repeated correspondences (degenerate samples)
+        a[N // 2:] = a[: N - N // 2]
+        b[N // 2:] = b[: N - N // 2]
+    return a, b
+
+
+def test_mono_ransac_corner_cases(oracle):
+    """The counting kernel decides most inliers with an approximate filter and falls back to the
+    exact residual near the threshold or when the triangulation is badly conditioned.  Inlier sets,
+    iteration counts, winning draws and models must stay bit-identical to the oracle on inputs built
+    to hit every guard, and across thresholds from far below to far above the noise level."""
+    import kml
+    from kml import mask_to_indices
+    rng = np.random.default_rng(2024)
+    kinds = ["plain", "low_parallax", "far_points", "near_centres", "non_unit", "duplicates"]
+    for thr in (1e-6, 1e-9, 1e-4, 5e-8):
+        p = kml.default_params()
+        p.ransac_threshold_mono = thr
+        det = kml.LoopClosureDetector(params=p)
+        for N in (8, 9, 33, 200):
+            f1 = np.zeros((len(kinds), N, 3)); f2 = np.zeros((len(kinds), N, 3))
+            for i, kind in enumerate(kinds):
+                f1[i], f2[i] = _nister_case(rng, N, kind)
+            g = det.ransac_nister_batch(f1, f2)
+            for i, kind in enumerate(kinds):
+                o = oracle.ransac_nister(f1[i], f2[i], thr, 0.995, 1000, 12345)
+                tag = (thr, N, kind)
+                assert o["iterations"] == g["iterations"][i], tag
+                assert o["best_draw"] == g["best_draw"][i], tag
+                assert o["n_inliers"] == g["n_inliers"][i], tag
+                assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][i], N)), tag
+                if o["best_draw"] >= 0:
+                    assert np.array_equal(o["model"], g["models"][i]), tag
+        det.close()
+
+
 def test_l1_matcher_variant(oracle, small_world):
     """matcher_norm = 1: byte-wise L1, what upstream's DescriptorMatcher::create(3) selects
     (kimera_multi_lcd.patch:34-35) — bit-exact vs cv2.BFMatcher(NORM_L1) and the oracle."""

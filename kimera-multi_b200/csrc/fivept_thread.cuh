@@ -535,8 +535,8 @@ __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, cons
   const double d12 = dot(f1, f2u);
   const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
   const double det = A00 * A11 - A01 * A10;
-  const double l0 = kdiv(A11 * b0 - A01 * b1, det);
-  const double l1 = kdiv(A00 * b1 - A10 * b0, det);
+  const double l0 = (A11 * b0 - A01 * b1) / det;
+  const double l1 = (A00 * b1 - A10 * b0) / det;
   V3 p, q;
   p.x = 0.5 * (l0 * f1.x + (t.x + l1 * f2u.x));
   p.y = 0.5 * (l0 * f1.y + (t.y + l1 * f2u.y));
@@ -544,9 +544,9 @@ __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, cons
   q.x = ((R[0] * p.x + R[3] * p.y) + R[6] * p.z) + tinv[0];
   q.y = ((R[1] * p.x + R[4] * p.y) + R[7] * p.z) + tinv[1];
   q.z = ((R[2] * p.x + R[5] * p.y) + R[8] * p.z) + tinv[2];
-  const double np = ksqrt(dot(p, p)), nq = ksqrt(dot(q, q));
-  const double x1 = kdiv(dot(f1, p), np);
-  const double x2 = kdiv(dot(f2, q), nq);
+  const double np = sqrt(dot(p, p)), nq = sqrt(dot(q, q));
+  const double x1 = dot(f1, p) / np;
+  const double x2 = dot(f2, q) / nq;
   *r_pos = (1.0 - x1) + (1.0 - x2);
   *r_neg = (1.0 + x1) + (1.0 + x2);
 }

@@ -18,7 +18,8 @@
  *   - 5-pt solver  ⊇ cv2.findEssentialMat solution set, invariants
  *   - Arun         == numpy SVD Kabsch (1e-12)
  *   - BoW L1       == dense numpy 1 - 0.5*|v-w|_1 (1e-12)
- * (see tests/test_oracle_*.py).
+ * (see tests/test_oracle.py; the same external implementations wrote the
+ * committed fixture tests/golden/golden_v1.npz checked by tests/test_golden.py).
  *
  * All fp64 arithmetic is compiled with -ffp-contract=off (no FMA) so that
  * the operation order written in the sources is the operation order executed.

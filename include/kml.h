@@ -241,6 +241,50 @@ int kml_timer_end(kml_handle* h, kml_handle** lanes, int n_lanes, float* ms);
  * handle's stream so the next timed step starts with a cold L2 */
 int kml_flush_l2(kml_handle* h);
 
+/* ---- row f3: post filters and wire layout around the path (host logic) ----
+ * Kimera-VIO's detection flow "2 computeIslands() 3 checkTemporalConstraint()"
+ * (/root/reference/images/kimera-multi.drawio:1565) with the
+ * thresholds of /root/reference/params/D455/LcdParams.yaml:5,9-12. */
+typedef struct kml_island {
+  uint64_t start_id, end_id; /* first / last result id of the group */
+  uint64_t best_id;          /* id with the largest score in the group */
+  double island_score;       /* sum of the group's scores */
+  double best_score;
+} kml_island;
+typedef struct kml_temporal_state { /* zero-initialise; one per (querying robot, database) */
+  int32_t temporal_entries;
+  int32_t pad;
+  uint64_t latest_query_id;
+  kml_island latest_island;
+} kml_temporal_state;
+/* LCDStatus values written to output_lcd_status.csv (/root/reference/evaluation/lc_result.py:143-162) */
+#define KML_LCD_LOOP_DETECTED 0
+#define KML_LCD_NO_MATCHES 1
+#define KML_LCD_LOW_NSS_FACTOR 2
+#define KML_LCD_LOW_SCORE 3
+#define KML_LCD_NO_GROUPS 4
+#define KML_LCD_FAILED_TEMPORAL_CONSTRAINT 5
+#define KML_LCD_FAILED_GEOM_VERIFICATION 6
+#define KML_LCD_FAILED_POSE_RECOVERY 7
+/* LcdThirdPartyWrapper::computeIslands: ids/scores = surviving results of one database */
+int kml_compute_islands(const uint64_t* ids, const double* scores, int n, int max_intraisland_gap,
+                        int min_matches_per_island, kml_island* out, int cap, int* count);
+/* LcdThirdPartyWrapper::checkTemporalConstraint: 1 = passes, 0 = fails, <0 error */
+int kml_check_temporal_constraint(kml_temporal_state* st, uint64_t query_id, const kml_island* island,
+                                  int max_nrFrames_between_queries, int max_nrFrames_between_islands,
+                                  int min_temporal_matches);
+/* detectLoopWithRobot + islands + temporal check: KML_OK and the best island's best entry,
+ * or KML_NO_MATCH / KML_NSS_TOO_LOW with *lcd_status saying why */
+int kml_detect_loop_islands(kml_handle* h, uint64_t robot, uint64_t q_robot, uint64_t q_pose,
+                            const uint32_t* ids, const float* vals, int n, int max_intraisland_gap,
+                            int min_matches_per_island, int max_nrFrames_between_islands,
+                            int min_temporal_matches, kml_temporal_state* st, uint64_t* match_pose,
+                            double* match_score, kml_island* best_island, int* lcd_status);
+/* addVLCFrame from the VLCFrameMsg layout: float32 xyz clouds for versors and keypoints
+ * (/root/reference/images/kimera-multi.drawio:385-414) */
+int kml_add_frame_msg(kml_handle* h, uint64_t robot, uint64_t pose, const uint8_t* desc,
+                      const float* versors_xyz, const float* keypoints_xyz, int F);
+
 /* ---- multi-GPU (one process per GPU; databases sharded by robot) -------- */
 #define KML_UNIQUE_ID_BYTES 128
 int kml_comm_unique_id(void* id_out /* KML_UNIQUE_ID_BYTES */);

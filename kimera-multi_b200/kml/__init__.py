@@ -14,7 +14,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (KML_OK, KmlError, Params, Result, Stats, EXPORTS, build, lib)  # noqa: F401
+from ._lib import (KML_OK, KmlError, Params, Result, Stats, EXPORTS, build, lib,  # noqa: F401
+                   Island, TemporalState, LCD_STATUS)
 
 RESULT_DTYPE = np.dtype([
     ("q_robot", "<u8"), ("q_pose", "<u8"), ("m_robot", "<u8"), ("m_pose", "<u8"),
@@ -386,9 +387,63 @@ class LoopClosureDetector:
             raise KmlError(rc, "kml_comm_unique_id failed")
         return bytes(buf)
 
+    # ------------------------------------------------ row f3: post filters, wire layout
+    def addVLCFrameMsg(self, robot, pose, desc, versors_f32, keypoints_f32):
+        """addVLCFrame from the VLCFrameMsg layout (float32 xyz clouds)."""
+        desc = _u8(desc)
+        v = np.ascontiguousarray(versors_f32, np.float32)
+        k = np.ascontiguousarray(keypoints_f32, np.float32)
+        self._check(lib().kml_add_frame_msg(self._h, C.c_uint64(int(robot)), C.c_uint64(int(pose)),
+                                            _p(desc, C.c_uint8), _p(v, C.c_float), _p(k, C.c_float),
+                                            int(desc.shape[0])))
+
+    def detectLoopIslands(self, robot, q_robot, q_pose, ids, vals, state, max_intraisland_gap=3,
+                          min_matches_per_island=1, max_nrFrames_between_islands=3, min_temporal_matches=1):
+        """detectLoopWithRobot + computeIslands + checkTemporalConstraint (Kimera-VIO flow).
+        Returns (lcd_status string, match_pose, match_score, island tuple or None)."""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        vals = np.ascontiguousarray(vals, np.float32)
+        mp, ms, isl, st = C.c_uint64(0), C.c_double(0), Island(), C.c_int(1)
+        rc = lib().kml_detect_loop_islands(self._h, C.c_uint64(int(robot)), C.c_uint64(int(q_robot)),
+                                           C.c_uint64(int(q_pose)), _p(ids, C.c_uint32), _p(vals, C.c_float),
+                                           len(ids), int(max_intraisland_gap), int(min_matches_per_island),
+                                           int(max_nrFrames_between_islands), int(min_temporal_matches),
+                                           C.byref(state), C.byref(mp), C.byref(ms), C.byref(isl), C.byref(st))
+        if rc < 0:
+            self._check(rc)
+        status = LCD_STATUS[st.value]
+        has_island = status in ("LOOP_DETECTED", "FAILED_TEMPORAL_CONSTRAINT")
+        return status, int(mp.value), float(ms.value), (isl.astuple() if has_island else None)
+
     def comm_init(self, nranks, rank, unique_id):
         buf = (C.c_uint8 * _lib.KML_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._check(lib().kml_comm_init(self._h, int(nranks), int(rank), buf))
+
+
+def compute_islands(ids, scores, max_intraisland_gap=3, min_matches_per_island=1):
+    """LcdThirdPartyWrapper::computeIslands on one database's surviving results -> list of
+    (start_id, end_id, best_id, island_score, best_score), ascending start id."""
+    ids = np.ascontiguousarray(ids, np.uint64)
+    scores = np.ascontiguousarray(scores, np.float64)
+    out = (Island * max(len(ids), 1))()
+    cnt = C.c_int(0)
+    rc = lib().kml_compute_islands(_p(ids, C.c_uint64), _p(scores, C.c_double), len(ids), int(max_intraisland_gap),
+                                   int(min_matches_per_island), out, len(out), C.byref(cnt))
+    if rc != KML_OK:
+        raise KmlError(rc, "kml_compute_islands")
+    return [out[i].astuple() for i in range(cnt.value)]
+
+
+def check_temporal_constraint(state, query_id, island, max_nrFrames_between_queries=2,
+                              max_nrFrames_between_islands=3, min_temporal_matches=1):
+    """LcdThirdPartyWrapper::checkTemporalConstraint; `state` is a kml.TemporalState()."""
+    isl = Island(*island)
+    rc = lib().kml_check_temporal_constraint(C.byref(state), C.c_uint64(int(query_id)), C.byref(isl),
+                                             int(max_nrFrames_between_queries), int(max_nrFrames_between_islands),
+                                             int(min_temporal_matches))
+    if rc < 0:
+        raise KmlError(rc, "kml_check_temporal_constraint")
+    return bool(rc)
 
 
 def mask_to_indices(mask_row, n):

@@ -80,6 +80,24 @@ class Result(C.Structure):
 
 
 # every symbol include/kml.h declares (checked by tests/test_abi.py)
+class Island(C.Structure):
+    """kml_island"""
+    _fields_ = [("start_id", C.c_uint64), ("end_id", C.c_uint64), ("best_id", C.c_uint64),
+                ("island_score", C.c_double), ("best_score", C.c_double)]
+
+    def astuple(self):
+        return (self.start_id, self.end_id, self.best_id, self.island_score, self.best_score)
+
+
+class TemporalState(C.Structure):
+    """kml_temporal_state (zero-initialised = no history)"""
+    _fields_ = [("temporal_entries", C.c_int32), ("pad", C.c_int32), ("latest_query_id", C.c_uint64),
+                ("latest_island", Island)]
+
+
+LCD_STATUS = ["LOOP_DETECTED", "NO_MATCHES", "LOW_NSS_FACTOR", "LOW_SCORE", "NO_GROUPS",
+              "FAILED_TEMPORAL_CONSTRAINT", "FAILED_GEOM_VERIFICATION", "FAILED_POSE_RECOVERY"]
+
 EXPORTS = [
     "kml_default_params", "kml_create", "kml_create_lane", "kml_destroy", "kml_last_error", "kml_get_stats",
     "kml_device_count", "kml_add_bow", "kml_add_bow_bulk", "kml_add_frame",
@@ -90,6 +108,7 @@ EXPORTS = [
     "kml_hamming_knn2", "kml_l1_knn2", "kml_hamming_knn2_bench", "kml_ransac_arun_batch",
     "kml_ransac_nister_batch", "kml_vocab_set", "kml_transform_batch", "kml_peak_popc", "kml_peak_fp64", "kml_timer_begin", "kml_timer_end", "kml_flush_l2", "kml_comm_unique_id",
     "kml_comm_init", "kml_query_batch_sharded",
+    "kml_compute_islands", "kml_check_temporal_constraint", "kml_detect_loop_islands", "kml_add_frame_msg",
 ]
 
 _lib = None

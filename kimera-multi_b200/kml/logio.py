@@ -58,3 +58,23 @@ def write_loop_closures_csv(path, records, counts, stamps_ns=None, append=False)
                             int(r["stereo_inliers"]), stamp])
                 n += 1
     return n
+
+
+STATUS_HEADER = ["timestamp_kf", "lcd_status", "query_id", "match_id", "mono_input_size", "mono_inliers",
+                 "mono_iters", "stereo_input_size", "stereo_inliers", "stereo_iters"]
+
+
+def write_lcd_status_csv(path, rows, append=False):
+    """`output_lcd_status.csv` of the intra-robot detector, read by
+    /root/reference/evaluation/lc_result.py:143-162 through csv.DictReader (columns used:
+    lcd_status, query_id, match_id, mono_inliers, stereo_inliers).  rows = iterable of dicts with
+    those keys; lcd_status is one of kml.LCD_STATUS; missing keys are written as 0."""
+    n = 0
+    with open(path, "a" if append else "w", newline="") as f:
+        w = csv.writer(f)
+        if not append:
+            w.writerow(STATUS_HEADER)
+        for r in rows:
+            w.writerow([r.get(k, 0) for k in STATUS_HEADER])
+            n += 1
+    return n

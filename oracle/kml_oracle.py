@@ -367,3 +367,36 @@ class Vocabulary:
 
 def num_threads():
     return lib().kmo_num_threads()
+
+
+# ---------------------------------------------------------------- row f3
+class Island(C.Structure):
+    _fields_ = [("start_id", C.c_uint64), ("end_id", C.c_uint64), ("best_id", C.c_uint64),
+                ("island_score", C.c_double), ("best_score", C.c_double)]
+
+    def astuple(self):
+        return (self.start_id, self.end_id, self.best_id, self.island_score, self.best_score)
+
+
+class TemporalState(C.Structure):
+    _fields_ = [("temporal_entries", C.c_int32), ("pad", C.c_int32), ("latest_query_id", C.c_uint64),
+                ("latest_island", Island)]
+
+
+def compute_islands(ids, scores, max_gap, min_len):
+    ids = np.ascontiguousarray(ids, np.uint64)
+    scores = _f64(scores)
+    out = (Island * max(len(ids), 1))()
+    lib().kmo_compute_islands.restype = C.c_int
+    n = lib().kmo_compute_islands(_p(ids, C.c_uint64), _p(scores, C.c_double), len(ids), int(max_gap),
+                                  int(min_len), out, len(out))
+    return [out[i].astuple() for i in range(n)]
+
+
+def check_temporal_constraint(state, query_id, island, max_between_queries, max_between_islands,
+                              min_temporal_matches):
+    isl = Island(*island)
+    lib().kmo_check_temporal_constraint.restype = C.c_int
+    return bool(lib().kmo_check_temporal_constraint(C.byref(state), C.c_uint64(int(query_id)), C.byref(isl),
+                                                    int(max_between_queries), int(max_between_islands),
+                                                    int(min_temporal_matches)))

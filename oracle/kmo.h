@@ -185,6 +185,24 @@ int kmo_lcd_query_batch(kmo_lcd*, int B, const uint64_t* q_robot,
                         int threads);
 int kmo_num_threads(void);
 
+/* ---- row f3: islands / temporal constraint ---- */
+typedef struct kmo_island {
+  uint64_t start_id, end_id, best_id;
+  double island_score, best_score;
+} kmo_island;
+typedef struct kmo_temporal_state {
+  int32_t temporal_entries;
+  int32_t pad;
+  uint64_t latest_query_id;
+  kmo_island latest_island;
+} kmo_temporal_state;
+/* returns the number of islands (may exceed cap; only cap are written) */
+int kmo_compute_islands(const uint64_t* ids, const double* scores, int n, int max_gap, int min_len,
+                        kmo_island* out, int cap);
+int kmo_check_temporal_constraint(kmo_temporal_state* st, uint64_t id, const kmo_island* island,
+                                  int max_between_queries, int max_between_islands,
+                                  int min_temporal_matches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -745,3 +745,72 @@ extern "C" int kmo_vocab_transform(const kmo_vocab* voc, const uint8_t* desc, in
 extern "C" void kmo_l1_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, uint32_t* idx, uint16_t* dist) {
   knn2(q, nq, t, nt, idx, dist, 1);
 }
+
+// ===================================================== row f3 post filters
+// LcdThirdPartyWrapper::computeIslands / checkTemporalConstraint as Kimera-VIO runs them after the
+// alpha*nss cut.  Walks the results by ascending id exactly like the
+// upstream loop: first/last entry of the running island, best score so far, island closed when
+// the next id is max_intraisland_gap or more away.
+extern "C" int kmo_compute_islands(const uint64_t* ids, const double* scores, int n, int max_gap,
+                                   int min_len, kmo_island* out, int cap) {
+  struct Res { uint64_t id; double score; };
+  std::vector<Res> q(n);
+  for (int i = 0; i < n; ++i) q[i] = Res{ids[i], scores[i]};
+  std::vector<kmo_island> islands;
+  if (q.size() == 1) {
+    islands.push_back(kmo_island{q[0].id, q[0].id, q[0].id, q[0].score, q[0].score});
+  } else if (!q.empty()) {
+    std::sort(q.begin(), q.end(), [](const Res& a, const Res& b) { return a.id < b.id; });
+    long long first_entry = (long long)q[0].id, last_entry = (long long)q[0].id;
+    size_t i_first = 0, i_last = 0;
+    double best_score = q[0].score;
+    uint64_t best_entry = q[0].id;
+    auto island_score = [&](size_t a, size_t b) {
+      double sum = 0.0;
+      for (size_t i = a; i <= b; ++i) sum += q[i].score;
+      return sum;
+    };
+    for (size_t idx = 1; idx < q.size(); ++idx) {
+      if ((long long)q[idx].id - last_entry < (long long)max_gap) {
+        last_entry = (long long)q[idx].id;
+        i_last = idx;
+        if (q[idx].score > best_score) { best_score = q[idx].score; best_entry = q[idx].id; }
+      } else {
+        if (last_entry - first_entry + 1 >= (long long)min_len)
+          islands.push_back(kmo_island{(uint64_t)first_entry, (uint64_t)last_entry, best_entry,
+                                       island_score(i_first, i_last), best_score});
+        first_entry = last_entry = (long long)q[idx].id;
+        i_first = i_last = idx;
+        best_score = q[idx].score;
+        best_entry = q[idx].id;
+      }
+    }
+    if (last_entry - first_entry + 1 >= (long long)min_len)
+      islands.push_back(kmo_island{(uint64_t)first_entry, (uint64_t)last_entry, best_entry,
+                                   island_score(i_first, i_last), best_score});
+  }
+  const int m = std::min<int>((int)islands.size(), cap);
+  for (int i = 0; i < m; ++i) out[i] = islands[i];
+  return (int)islands.size();
+}
+
+extern "C" int kmo_check_temporal_constraint(kmo_temporal_state* st, uint64_t id, const kmo_island* island,
+                                             int max_between_queries, int max_between_islands,
+                                             int min_temporal_matches) {
+  if (st->temporal_entries == 0 || (long long)id - (long long)st->latest_query_id > (long long)max_between_queries) {
+    st->temporal_entries = 1;
+  } else {
+    const long long a1 = (long long)st->latest_island.start_id, a2 = (long long)st->latest_island.end_id;
+    const long long b1 = (long long)island->start_id, b2 = (long long)island->end_id;
+    const bool overlap = (b1 <= a1 && a1 <= b2) || (a1 <= b1 && b1 <= a2);
+    bool gap_is_small = false;
+    if (!overlap) {
+      const long long d = (a1 > b2) ? a1 - b2 : b1 - a2;
+      gap_is_small = d <= (long long)max_between_islands;
+    }
+    if (overlap || gap_is_small) st->temporal_entries++; else st->temporal_entries = 1;
+  }
+  st->latest_island = *island;
+  st->latest_query_id = id;
+  return st->temporal_entries > min_temporal_matches;
+}

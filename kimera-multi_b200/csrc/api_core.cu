@@ -166,7 +166,6 @@ int kml_destroy(kml_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ev_t0) { cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_lane); }
-  if (h->ev_block) cudaEventDestroy(h->ev_block);
   delete h;
   return KML_OK;
 }

@@ -98,16 +98,6 @@ struct kml_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane = nullptr;  // kml_timer_begin / kml_timer_end
-  // Host waits of the batch path yield the CPU (blocking-sync event) instead of spinning: with
-  // several lanes per GPU and several GPUs per box the waiting threads outnumber the cores.
-  cudaEvent_t ev_block = nullptr;
-  bool blocking_wait = false;  // set for the duration of a batch of >= 16 queries
-  void wait_stream() {
-    if (!blocking_wait) { KML_CUDA(cudaStreamSynchronize(stream)); return; }
-    if (!ev_block) KML_CUDA(cudaEventCreateWithFlags(&ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
-    KML_CUDA(cudaEventRecord(ev_block, stream));
-    KML_CUDA(cudaEventSynchronize(ev_block));
-  }
   std::string err;
   kml_stats stats = {};
 

@@ -184,7 +184,7 @@ static void run_bow(kml_handle* h, const std::vector<RobotDb*>& dbs, int B, cons
   KML_CUDA(cudaMemcpyAsync(h->h_nss.p, h->d_nss.p, B * 8, cudaMemcpyDeviceToHost, h->stream));
   unsigned long long postings = 0;
   KML_CUDA(cudaMemcpyAsync(&postings, h->d_postings.p, 8, cudaMemcpyDeviceToHost, h->stream));
-  h->wait_stream();
+  KML_CUDA(cudaStreamSynchronize(h->stream));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_bow, h->ev[0], h->ev[1]));
   h->stats.bow_postings_last = postings;
   for (int b = 0; b < B; ++b) out->nss[b] = h->h_nss.p[b];
@@ -525,7 +525,7 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   KML_CUDA(cudaMemcpyAsync(out->T.data(), h->d_outT.p, 96 * (size_t)P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(stm.data(), h->d_st_mono.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(sts.data(), h->d_st_stereo.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
-  h->wait_stream();
+  KML_CUDA(cudaStreamSynchronize(s));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
@@ -602,9 +602,7 @@ static int batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uin
     KML_CUDA(cudaMemcpyAsync(h->d_qbear.p, bearings, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
     KML_CUDA(cudaMemcpyAsync(h->d_qpts.p, points, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
   }
-  h->blocking_wait = B >= 16;
-  h->wait_stream();
-  h->blocking_wait = false;
+  KML_CUDA(cudaStreamSynchronize(s));
   return KML_OK;
 }
 
@@ -618,11 +616,6 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
   br->recs.assign((size_t)B * cap, kml_result{});
   br->counts.assign(B, 0);
   if (B == 0) return KML_OK;
-  struct BlockingScope {  // batches wait without spinning; single queries keep the low-latency spin
-    kml_handle* h;
-    BlockingScope(kml_handle* hh, bool on) : h(hh) { h->blocking_wait = on; }
-    ~BlockingScope() { h->blocking_wait = false; }
-  } scope(h, B >= 16);
   KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
   std::vector<RobotDb*> dbs;
   for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
@@ -673,7 +666,7 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
     memcpy(r.T, &vo.T[p * 12], 96);
   }
   KML_CUDA(cudaEventRecord(h->ev[7], h->stream));
-  h->wait_stream();
+  KML_CUDA(cudaEventSynchronize(h->ev[7]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_total, h->ev[6], h->ev[7]));
   if (getenv("KML_DEBUG_TIMING")) {
     float a = 0, b = 0, c = 0;
@@ -1099,9 +1092,7 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* co
   rc = comm_allgather(h, h->d_scratch.p, h->d_scratch2.p, blk_al);
   if (rc != KML_OK) return rc;
   KML_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_scratch2.p, blk_al * nr, cudaMemcpyDeviceToHost, h->stream));
-  h->blocking_wait = B >= 16;
-  h->wait_stream();
-  h->blocking_wait = false;
+  KML_CUDA(cudaStreamSynchronize(h->stream));
   std::vector<kml_result> all;
   for (int b = 0; b < B; ++b) {
     all.clear();

@@ -341,7 +341,11 @@ def main():
         "bow_scan": {"bound": "hbm", "achieved": postings * 8 / (stage["bow"] * 1e-3) / 1e9 if stage["bow"] else None,
                      "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
                      "algorithmic_bytes_per_step": postings * 8 / K, "ms_per_step": stage["bow"] / K},
+        # algorithmic: 8 POPC32 per 256-bit compare; the kernel executes 5 (three carry-save adders fold
+        # seven XOR words into two weight-1 and three weight-2 words first), so `achieved` can exceed
+        # the pipe's peak; `frac` is the utilisation of the POPC pipe by what is actually executed
         "hamming_knn": {"bound": "popc", "achieved": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                        "executed": compares * 5 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
                         "peak": popc_peak / 1e12, "unit": "T POPC32/s", "peak_source": "measured (kml_peak_popc, same run)",
                         "compares_per_step": compares / K, "ms_per_step": stage["match"] / K},
         # algorithmic flops of the reference loop: per consumed hypothesis the minimal
@@ -358,6 +362,9 @@ def main():
     for k in ("bow_scan", "hamming_knn", "mono_ransac", "stereo_ransac"):
         if roof[k]["achieved"]:
             roof[k]["frac"] = roof[k]["achieved"] / roof[k]["peak"]
+    if roof["hamming_knn"].get("executed"):
+        roof["hamming_knn"]["frac_algorithmic"] = roof["hamming_knn"]["frac"]
+        roof["hamming_knn"]["frac"] = roof["hamming_knn"]["executed"] / roof["hamming_knn"]["peak"]
     # flop model: 5-pt hypothesis ~ 60 kflop solver + 8x4x10 scoring; residual 95 flop
     dominant = max(("bow", "match", "mono", "stereo"), key=lambda s: stage[s])
     dom_key = {"bow": "bow_scan", "match": "hamming_knn", "mono": "mono_ransac", "stereo": "stereo_ransac"}[dominant]

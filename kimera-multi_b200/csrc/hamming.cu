@@ -13,7 +13,8 @@
 // second best are kept as packed keys (dist << 20 | trainIdx) so that the
 // update is three integer min/max and ties resolve to the lowest trainIdx,
 // which is BFMatcher's observed order (distance asc, trainIdx asc).
-// Bound: POPC pipe (8 POPC32 per compare), see DESIGN.md §5.2.
+// Bound: POPC pipe (8 POPC32 per compare algorithmically, 5 executed after a carry-save
+// reduction on the LOP3 pipe), see DESIGN.md §5.2.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -22,10 +23,21 @@ namespace kml {
 constexpr int kHamThreads = 512;
 constexpr int kHamTile = 512;  // train descriptors per shared-memory stage
 
-// L1 = false: NORM_HAMMING (8 x LOP3 + POPC, key = dist << 20 | idx);
+// L1 = false: NORM_HAMMING (8 XOR + 6 carry-save LOP3 + 5 POPC, key = dist << 20 | idx);
 // L1 = true : NORM_L1 over the 32 bytes (8 x VABSDIFF4 sum-of-absolute-differences, dist <= 8160,
 //             key = dist << 18 | idx) — what upstream's cv::DescriptorMatcher::create(3) selects
 //             (/root/reference/docker/copy/kimera_multi_lcd.patch:34-35).
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 template <bool L1>
 __device__ __forceinline__ void ham_update(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3,
                                            uint32_t q4, uint32_t q5, uint32_t q6, uint32_t q7,
@@ -35,10 +47,18 @@ __device__ __forceinline__ void ham_update(uint32_t q0, uint32_t q1, uint32_t q2
   if (L1)
     d = __vsadu4(q0, a.x) + __vsadu4(q1, a.y) + __vsadu4(q2, a.z) + __vsadu4(q3, a.w) +
         __vsadu4(q4, b.x) + __vsadu4(q5, b.y) + __vsadu4(q6, b.z) + __vsadu4(q7, b.w);
-  else
-    d = __popc(q0 ^ a.x) + __popc(q1 ^ a.y) + __popc(q2 ^ a.z) + __popc(q3 ^ a.w) +
-        __popc(q4 ^ b.x) + __popc(q5 ^ b.y) + __popc(q6 ^ b.z) + __popc(q7 ^ b.w);
-  uint32_t key = (d << (L1 ? 18 : 20)) | idx;
+  else {
+    // The POPC pipe (16 lanes/clk/SM, a quarter of the LOP3 rate) is the bound, so three
+    // carry-save adders fold seven of the eight XOR words into two weight-1 and three weight-2
+    // words first: 5 POPC + 14 LOP3 per compare instead of 8 POPC + 8 LOP3, same integer.
+    const uint32_t x0 = q0 ^ a.x, x1 = q1 ^ a.y, x2 = q2 ^ a.z, x3 = q3 ^ a.w;
+    const uint32_t x4 = q4 ^ b.x, x5 = q5 ^ b.y, x6 = q6 ^ b.z, x7 = q7 ^ b.w;
+    const uint32_t s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+    const uint32_t s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+    const uint32_t s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+    d = (__popc(s3) + __popc(x7)) + 2u * (__popc(c1) + __popc(c2) + __popc(c3));
+  }
+  uint32_t key = d * (L1 ? (1u << 18) : (1u << 20)) + idx;  // = (d << shift) | idx, idx < 2^shift: one IMAD off the LOP3 pipe
   uint32_t mx = max(best, key);
   best = min(best, key);
   second = min(second, mx);

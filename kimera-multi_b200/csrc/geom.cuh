@@ -23,6 +23,9 @@
 namespace kml {
 namespace geom {
 
+#ifdef KML_FILTER_STATS
+__device__ unsigned long long g_fstats[12];
+#endif
 KML_DN double kdiv(double a, double b) { return a / b; }
 KML_DN double ksqrt(double a) { return sqrt(a); }
 
@@ -212,13 +215,19 @@ KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, c
 // of the threshold (those, and every badly conditioned triangulation, return -1 and
 // are re-evaluated with mono_residual, so the decision is always the exact one).
 // Preconditions: unit bearings (SacState::unit_bearings).
-// Error budget (e~ = filter value, e = value of mono_residual): the two evaluations differ
-// by FMA contraction and <= 2 ulp reciprocal / rsqrt, i.e. absolute differences of a few
-// ulp in det and the numerators.  With |det| >= 1e-4 that is <= 4e-12 (|l0|+|l1|+|t|) in p;
-// guard kp bounds the cancellation in p (|p| >= 0.01 of its terms) and guard kq the one in
-// q = R^T p - R^T t, so the direction of p moves by <= 4e-10 rad and that of q by <= 4e-8 rad.
-// d(1-cos x) = sin x dx <= 4e-8 everywhere, and <= sqrt(2 (thr + 1e-6)) * 4e-8 for
-// e <= thr + 1e-6.  The margins used below are 10x these bounds.
+// Error budget (e~ = filter value, e = value of mono_residual; eps = 2.2e-16, r = 1/det,
+// |det| = sin^2(a) with a the angle between f1 and R f2, S = |l0| + |l1| + |t|_1).  The two
+// evaluations differ by FMA contraction and <= 2 ulp reciprocal / rsqrt: |num~ - num| <= 8 eps |t|,
+// |det~ - det| <= 4 eps, hence |dl0|, |dl1| <= 8 eps S |r|.  They move p along f1 and R f2, which
+// are a apart: the component across the direction of p is <= eps S (4 sqrt|r| + 8 sin(x) |r|),
+// x the TRUE angle between f1 and p.  With the guards |p|, |q| >= S / 1000 the direction of p (and
+// of q, by the same argument with the cameras swapped) moves by dx <= 1000 eps (4 sqrt|r| + 8 sin(x) |r|),
+// and e = (1 - cos x1) + (1 - cos x2) gives sin x_i <= u := sqrt(2 e), so
+//     |e~ - e| <= g(e) := 2000 eps u (4 sqrt|r| + 8 u |r|).
+// |r| is capped at min(1e6, 6000 / c), c := sqrt(2 (thr + 2e-6)).  Then g(e) <= 4e-8 c for every
+// e <= thr + 2e-6, and dg/de < 1e-2 beyond, so with the margin m := 4e-7 c (10x):
+//   true e <  thr  =>  e~ < thr + m            (never reported as outlier, which needs e~ > thr + m)
+//   true e >= thr  =>  e~ >= e - g(e) > thr - m (never reported as inlier, which needs e~ < thr - m)
 KML_DI double rcp_fast(double d, bool* ok) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
@@ -239,14 +248,15 @@ KML_DI double rsqrt_fast(double a, bool* ok) {
 }
 KML_DI double dotf(const V3& a, const V3& b) { return __fma_rn(a.z, b.z, __fma_rn(a.y, b.y, a.x * b.x)); }
 struct InlierMargins {
-  double lo, hi, far;  // in if e~ < lo; out if e~ > hi (near band) or e~ > far
+  double lo, hi, det_min;  // inlier if e~ < lo, outlier if e~ > hi, else (or |det| < det_min) undecided
 };
 KML_DI InlierMargins inlier_margins(double thr) {
   InlierMargins m;
-  const double near = ksqrt(2.0 * (thr + 1e-6)) * 4e-7 + 1e-12;
+  const double c = ksqrt(2.0 * (thr + 2e-6));
+  const double near = c * 4e-7 + 1e-12;
   m.lo = thr - near;
   m.hi = thr + near;
-  m.far = thr + 1e-6;
+  m.det_min = fmax(1e-6, kdiv(c, 6000.0));  // |r| <= min(1e6, 6000 / c)
   return m;
 }
 // 1 = inlier, 0 = outlier, -1 = undecided (caller evaluates mono_residual)
@@ -273,15 +283,28 @@ KML_DI int mono_inlier_fast(const double* M, const double* tinv, const V3& f1, c
   q.z = __fma_rn(M[10], p.z, __fma_rn(M[6], p.y, __fma_rn(M[2], p.x, tinv[2])));
   const double pp = dotf(p, p), qq = dotf(q, q);
   const double s1 = (fabs(l0) + fabs(l1)) + ((fabs(t.x) + fabs(t.y)) + fabs(t.z));
-  const double s2 = ((fabs(p.x) + fabs(p.y)) + fabs(p.z)) + ((fabs(tinv[0]) + fabs(tinv[1])) + fabs(tinv[2]));
   const double y1 = rsqrt_fast(pp, &ok1), y2 = rsqrt_fast(qq, &ok2);
   const double e = 2.0 - __fma_rn(dotf(f1, p), y1, dotf(f2, q) * y2);
-  // conditioning guards (all false on NaN): |det| >= 1e-4, |f2u| sane, kp, kq <= 100
-  const bool sane = ok0 && ok1 && ok2 && fabs(det) >= 1e-4 && n2 > 0.5 && n2 < 2.0 && pp >= 1e-4 * (s1 * s1) &&
-                    qq >= 1e-4 * (s2 * s2) && pp < 1e280 && qq < 1e280;
+  // conditioning guards (all false on NaN): |det| floor, |f2u| sane, |p|, |q| >= S / 1000
+  const double floor2 = 1e-6 * (s1 * s1);
+  const bool sane = ok0 & ok1 & ok2 & (fabs(det) >= mg.det_min) & (n2 > 0.5) & (n2 < 2.0) & (pp >= floor2) &
+                    (qq >= floor2) & (pp < 1e280) & (qq < 1e280);
+#ifdef KML_FILTER_STATS
+  {
+    atomicAdd(&g_fstats[0], 1ull);
+    if (!ok0) atomicAdd(&g_fstats[1], 1ull);
+    if (!(ok1 & ok2)) atomicAdd(&g_fstats[2], 1ull);
+    if (!(fabs(det) >= mg.det_min)) atomicAdd(&g_fstats[3], 1ull);
+    if (!((n2 > 0.5) & (n2 < 2.0))) atomicAdd(&g_fstats[4], 1ull);
+    if (!(pp >= floor2)) atomicAdd(&g_fstats[5], 1ull);
+    if (!(qq >= floor2)) atomicAdd(&g_fstats[6], 1ull);
+    if (sane && !(e < mg.lo) && !(e > mg.hi)) atomicAdd(&g_fstats[7], 1ull);
+    if (!sane) atomicAdd(&g_fstats[8], 1ull);
+  }
+#endif
   if (!sane) return -1;
   if (e < mg.lo) return 1;
-  if (e > mg.far || e > mg.hi) return 0;
+  if (e > mg.hi) return 0;
   return -1;
 }
 

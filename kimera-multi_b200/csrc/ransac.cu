@@ -282,6 +282,13 @@ __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
   }
 }
 
+#ifdef KML_FILTER_STATS
+using geom::g_fstats;
+__global__ void fstats_print_kernel() {
+  printf("filter: evals %llu rcp_bad %llu rsqrt_bad %llu det %llu n2 %llu pfloor %llu qfloor %llu band %llu insane %llu\n",
+         g_fstats[0], g_fstats[1], g_fstats[2], g_fstats[3], g_fstats[4], g_fstats[5], g_fstats[6], g_fstats[7], g_fstats[8]);
+}
+#endif
 // CTA = 64 draws of one problem.  (1) thread = draw: winner among the draw's items in the
 // reference's order (roots in order, at most the first 10 refined ones, strict <); the item
 // records are fetched as two batches of independent loads.  (2) warp = draw: inlier count of
@@ -659,6 +666,9 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   } else {
     mono_count_kernel<false><<<dim3(a.P, blocks), kCountThreads, 0, s>>>(a);
   }
+#ifdef KML_FILTER_STATS
+  if (round == kSacRounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
+#endif
   sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 6;
 }

@@ -253,6 +253,18 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
 #undef S
 }
 
+// Fixed-degree Horner on register coefficients.  Callers pad with the polynomial's own
+// zero leading coefficients: the recurrence then reaches the true leading coefficient
+// exactly (0*x + c = c for finite x), so the value equals the variable-degree recurrence
+// up to the sign of a zero, which none of the uses below can see.
+template <int DEG>
+__device__ __forceinline__ double horner_r(const double* c, double x) {
+  double r = c[DEG];
+#pragma unroll
+  for (int i = DEG - 1; i >= 0; --i) r = r * x + c[i];
+  return r;
+}
+
 // ============================================================== stage 2
 __device__ __forceinline__ int tri_off(int k) { return 22 + 11 * k - (k * (k - 1)) / 2; }
 
@@ -381,6 +393,87 @@ __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, 
   return R;
 }
 
+// ---- generic-position fast path of stage 2, all in registers ----------------------------
+// For a polynomial in generic position every Sturm remainder loses exactly one degree
+// (10, 9, ..., 0).  Then the chain can be built with compile-time degrees, only the last two
+// members are alive at any time, and the signs at -1 and +1 are taken as each member appears:
+// the same divisions, products and sums in the same order as sturm_build_s / sturm_count_s.
+// Any exact zero where a leading coefficient is expected hands the draw to the generic code.
+struct SturmSigns {
+  int last_m = 0, last_p = 0, ch_m = 0, ch_p = 0;
+  __device__ __forceinline__ void add(double vm, double vp) {
+    const int sm_ = (vm > 0.0) - (vm < 0.0), sp_ = (vp > 0.0) - (vp < 0.0);
+    if (sm_ != 0) { if (last_m != 0 && sm_ != last_m) ++ch_m; last_m = sm_; }
+    if (sp_ != 0) { if (last_p != 0 && sp_ != last_p) ++ch_p; last_p = sp_; }
+  }
+};
+// remainder of pa (degree DB+1) by pb (degree DB), negated and scaled by 1/|leading|: degree DB-1
+template <int DB>
+__device__ __forceinline__ bool sturm_step(const double* pa, const double* pb, double* pc) {
+  double r[DB + 2];
+#pragma unroll
+  for (int i = 0; i <= DB + 1; ++i) r[i] = pa[i];
+  {
+    const double f = kdiv(r[DB + 1], pb[DB]);
+#pragma unroll
+    for (int i = 0; i < DB; ++i) r[1 + i] = r[1 + i] - f * pb[i];
+  }
+  {
+    const double f = kdiv(r[DB], pb[DB]);
+#pragma unroll
+    for (int i = 0; i < DB; ++i) r[i] = r[i] - f * pb[i];
+  }
+  if (r[DB - 1] == 0.0) return false;  // the degree drops by more than one
+  const double sc = fabs(r[DB - 1]);
+#pragma unroll
+  for (int i = 0; i <= DB - 1; ++i) pc[i] = -kdiv(r[i], sc);
+  return true;
+}
+template <int DB>
+__device__ __forceinline__ bool sturm_tail(const double* pa, const double* pb, SturmSigns& sg) {
+  double pc[DB];
+  if (!sturm_step<DB>(pa, pb, pc)) return false;
+  sg.add(horner_r<DB - 1>(pc, -1.0), horner_r<DB - 1>(pc, 1.0));
+  if constexpr (DB - 1 >= 1) return sturm_tail<DB - 1>(pb, pc, sg);
+  return true;
+}
+constexpr int kTRootGridFast = 32;  // = kTRootGrid (defined above)
+// a[0..10]: the chain's first polynomial.  Returns the root count R in (-1, 1]; brackets are
+// written when the sign grid separates the roots, else *deferred is set (the bisection runs in
+// mono_isolate_deferred_kernel); *degenerate asks for the generic path.
+__device__ __forceinline__ int isolate_chain_fast(const double* a, double* __restrict__ brk, bool* deferred,
+                                                  bool* degenerate) {
+  if (a[10] == 0.0) { *degenerate = true; return 0; }
+  double p1[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) p1[i] = (double)(i + 1) * a[i + 1];
+  SturmSigns sg;
+  sg.add(horner_r<10>(a, -1.0), horner_r<10>(a, 1.0));
+  sg.add(horner_r<9>(p1, -1.0), horner_r<9>(p1, 1.0));
+  if (!sturm_tail<9>(a, p1, sg)) { *degenerate = true; return 0; }
+  int R = sg.ch_m - sg.ch_p;
+  if (R > 10) R = 10;
+  if (R <= 0) return 0;
+  unsigned long long neg = 0ull, pos = 0ull, zer = 0ull;
+#pragma unroll 3
+  for (int i = 0; i <= kTRootGridFast; ++i) {
+    const double x = -1.0 + (double)i * (2.0 / kTRootGridFast);
+    const double r = horner_r<10>(a, x);
+    neg |= (unsigned long long)(r < 0.0) << i;
+    pos |= (unsigned long long)(r > 0.0) << i;
+    zer |= (unsigned long long)(r == 0.0) << i;
+  }
+  unsigned cells = (unsigned)((((neg << 1) & pos) | ((pos << 1) & neg) | zer) >> 1);
+  if (__popc(cells) != R) { *deferred = true; return R; }
+  for (int j = 0; j < R; ++j) {
+    const int cell = __ffs(cells) - 1;
+    cells &= cells - 1u;
+    brk[2 * j] = -1.0 + (double)cell * (2.0 / kTRootGridFast);
+    brk[2 * j + 1] = -1.0 + (double)(cell + 1) * (2.0 / kTRootGridFast);
+  }
+  return R;
+}
+
 // fo: this draw's stage-1 output.  Writes up to 10 + 10 brackets to brk and
 // returns R0 | R1 << 8 | deferred0 << 16 | deferred1 << 17 (0 if the draw has
 // no usable polynomial).
@@ -388,10 +481,25 @@ template <int STRIDE>
 __device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, double* __restrict__ brk) {
 #define S(i) sm[(i) * STRIDE]
   if (!(fo[34] == fo[34])) return 0;  // singular constraint system (NaN basis)
+  bool def0 = false, def1 = false;
+  {
+    double a[11];
+    bool degenerate = false;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a[k] = fo[k];
+    const int R0f = isolate_chain_fast(a, brk, &def0, &degenerate);
+    if (!degenerate) {
+#pragma unroll
+      for (int k = 0; k < 11; ++k) a[k] = fo[10 - k];
+      const int R1f = isolate_chain_fast(a, brk + 2 * R0f, &def1, &degenerate);
+      if (!degenerate) return R0f | (R1f << 8) | ((int)def0 << 16) | ((int)def1 << 17);
+    }
+    def0 = def1 = false;
+  }
+  // generic path (a leading coefficient or a remainder's leading term is exactly zero)
 #pragma unroll 1
   for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];
   unsigned long long degs;
-  bool def0 = false, def1 = false;
   int len = sturm_build_s<STRIDE>(sm, false, &degs);
   const int R0 = isolate_unit_s<STRIDE>(sm, degs, len, brk, 0, &def0);
   len = sturm_build_s<STRIDE>(sm, true, &degs);
@@ -414,18 +522,6 @@ __device__ void mono_isolate_deferred_thread(double* sm, const double* __restric
 }
 
 // ============================================================== stage 3
-
-// Fixed-degree Horner on register coefficients.  Callers pad with the polynomial's own
-// zero leading coefficients: the recurrence then reaches the true leading coefficient
-// exactly (0*x + c = c for finite x), so the value equals the variable-degree recurrence
-// up to the sign of a zero, which none of the uses below can see.
-template <int DEG>
-__device__ __forceinline__ double horner_r(const double* c, double x) {
-  double r = c[DEG];
-#pragma unroll
-  for (int i = DEG - 1; i >= 0; --i) r = r * x + c[i];
-  return r;
-}
 
 // Refines the root of bracket (lo, hi] of n(z) (chain 0) or of the reversed
 // polynomial (chain 1) and maps it to z.  fo = stage-1 output of the draw.

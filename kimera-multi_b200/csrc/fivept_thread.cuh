@@ -477,12 +477,14 @@ __device__ __forceinline__ int isolate_chain_fast(const double* a, double* __res
 // fo: this draw's stage-1 output.  Writes up to 10 + 10 brackets to brk and
 // returns R0 | R1 << 8 | deferred0 << 16 | deferred1 << 17 (0 if the draw has
 // no usable polynomial).
-template <int STRIDE>
-__device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, double* __restrict__ brk) {
-#define S(i) sm[(i) * STRIDE]
+// (the rare generic path keeps its 88 scratch slots in local memory: no shared memory, so the
+// kernel's occupancy is set by registers alone)
+__device__ __noinline__ int mono_isolate_generic(const double* __restrict__ fo, double* __restrict__ brk);
+__device__ __forceinline__ int mono_isolate_thread(const double* __restrict__ fo, double* __restrict__ brk,
+                                                   bool force_generic) {
   if (!(fo[34] == fo[34])) return 0;  // singular constraint system (NaN basis)
   bool def0 = false, def1 = false;
-  {
+  if (!force_generic) {
     double a[11];
     bool degenerate = false;
 #pragma unroll
@@ -494,16 +496,21 @@ __device__ int mono_isolate_thread(double* sm, const double* __restrict__ fo, do
       const int R1f = isolate_chain_fast(a, brk + 2 * R0f, &def1, &degenerate);
       if (!degenerate) return R0f | (R1f << 8) | ((int)def0 << 16) | ((int)def1 << 17);
     }
-    def0 = def1 = false;
   }
-  // generic path (a leading coefficient or a remainder's leading term is exactly zero)
+  // a leading coefficient or a remainder's leading term is exactly zero
+  return mono_isolate_generic(fo, brk);
+}
+__device__ __noinline__ int mono_isolate_generic(const double* __restrict__ fo, double* __restrict__ brk) {
+  double sm[kIsoSlots];
+#define S(i) sm[(i)]
 #pragma unroll 1
   for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];
   unsigned long long degs;
-  int len = sturm_build_s<STRIDE>(sm, false, &degs);
-  const int R0 = isolate_unit_s<STRIDE>(sm, degs, len, brk, 0, &def0);
-  len = sturm_build_s<STRIDE>(sm, true, &degs);
-  const int R1 = isolate_unit_s<STRIDE>(sm, degs, len, brk + 2 * R0, 0, &def1);
+  bool def0 = false, def1 = false;
+  int len = sturm_build_s<1>(sm, false, &degs);
+  const int R0 = isolate_unit_s<1>(sm, degs, len, brk, 0, &def0);
+  len = sturm_build_s<1>(sm, true, &degs);
+  const int R1 = isolate_unit_s<1>(sm, degs, len, brk + 2 * R0, 0, &def1);
   return R0 | (R1 << 8) | ((int)def0 << 16) | ((int)def1 << 17);
 #undef S
 }

@@ -101,6 +101,7 @@ struct SacArgs {
   double sq_crit;        // stereo: smallest s with sqrt(s) >= threshold
   int max_iterations;
   int full;              // evaluate every draw up to max_iterations+1 (no adaptive stop)
+  int force_generic;     // test hook (env KML_FORCE_GENERIC_ISOLATE): skip the register fast path of stage 2
   uint32_t* inlier_mask; // [P][mask_words]
   int mask_words;
   int32_t* n_inliers;    // [P]

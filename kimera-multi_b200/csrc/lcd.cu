@@ -413,6 +413,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
   a.sq_crit = sq_crit_of(prm.ransac_threshold);
   a.max_iterations = max_it; a.full = full;
+  a.force_generic = getenv("KML_FORCE_GENERIC_ISOLATE") ? 1 : 0;
   a.inlier_mask = out.mask->p; a.mask_words = mask_words; a.n_inliers = out.inl->p;
   KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * P, h->stream));
   launch_sac_init(a, S, h->stream);

@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
   int nr = 0;
   if (tid < nh) {
-    nr = geom::mono_isolate_thread<kMonoChunk>(smem_d + tid, a.fsol + slot * geom::kFrontOut,
-                                               a.brk + slot * 2 * geom::kMaxBrackets);
+    nr = geom::mono_isolate_thread(a.fsol + slot * geom::kFrontOut, a.brk + slot * 2 * geom::kMaxBrackets,
+                                   a.force_generic != 0);
     a.nroot[slot] = nr & 0xFFFF;
     for (int chain = 0; chain < 2; ++chain)
       if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
@@ -656,7 +656,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
-  mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, sm2, s>>>(a);
+  mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, 0, s>>>(a);
   mono_isolate_deferred_kernel<<<kNumSMs * 4, kMonoChunk, sm2, s>>>(a);
   mono_item_kernel<<<kNumSMs * 16, kItemThreads, 0, s>>>(a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);

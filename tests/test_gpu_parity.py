@@ -315,6 +315,28 @@ def test_mono_ransac_corner_cases(oracle):
         det.close()
 
 
+def test_mono_generic_isolation_path(oracle, monkeypatch):
+    """Stage 2 has a register fast path for polynomials in generic position and a generic path for
+    exact-zero leading terms, which random data never reaches: force it and compare with the oracle."""
+    import kml
+    from kml import mask_to_indices
+    monkeypatch.setenv("KML_FORCE_GENERIC_ISOLATE", "1")
+    rng = np.random.default_rng(77)
+    det = kml.LoopClosureDetector()
+    N = 120
+    f1 = np.zeros((4, N, 3)); f2 = np.zeros((4, N, 3))
+    for i, kind in enumerate(["plain", "far_points", "low_parallax", "duplicates"]):
+        f1[i], f2[i] = _nister_case(rng, N, kind)
+    g = det.ransac_nister_batch(f1, f2)
+    for i in range(4):
+        o = oracle.ransac_nister(f1[i], f2[i], 1e-6, 0.995, 1000, 12345)
+        assert o["iterations"] == g["iterations"][i] and o["best_draw"] == g["best_draw"][i]
+        assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][i], N))
+        if o["best_draw"] >= 0:
+            assert np.array_equal(o["model"], g["models"][i])
+    det.close()
+
+
 def test_l1_matcher_variant(oracle, small_world):
     """matcher_norm = 1: byte-wise L1, what upstream's DescriptorMatcher::create(3) selects
     (kimera_multi_lcd.patch:34-35) — bit-exact vs cv2.BFMatcher(NORM_L1) and the oracle."""

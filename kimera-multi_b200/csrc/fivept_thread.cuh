@@ -597,7 +597,7 @@ __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, 
 // Decomposition of one essential matrix: Ra = U W V^T, Rb = U W^T V^T, t = s0 u2.
 __device__ __forceinline__ void essential_candidates(const double* E, double* Ra, double* Rb, double* tt) {
   double U[9], Sv[3], V[9];
-  svd3(E, U, Sv, V);
+  svd3_r(E, U, Sv, V);
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll

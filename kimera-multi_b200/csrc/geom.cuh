@@ -125,6 +125,91 @@ KML_DN void svd3(const double* A, double* U, double* S, double* V) {
   V[6] = v0.z; V[7] = v1.z; V[8] = v2.z;
 }
 
+// Register version of svd3 for kernels small enough to inline it (same operations in the same
+// order as svd3 above; column pairs are template parameters so G and W never leave registers).
+template <int P, int Q>
+KML_DI bool jacobi_pair_r(double (&G)[9], double (&W)[9]) {
+  const double a = (G[P] * G[P] + G[3 + P] * G[3 + P]) + G[6 + P] * G[6 + P];
+  const double b = (G[Q] * G[Q] + G[3 + Q] * G[3 + Q]) + G[6 + Q] * G[6 + Q];
+  const double g = (G[P] * G[Q] + G[3 + P] * G[3 + Q]) + G[6 + P] * G[6 + Q];
+  if (g * g <= 1e-30 * a * b) return false;
+  const double zeta = kdiv(b - a, 2.0 * g);
+  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(1.0 + zeta * zeta));
+  const double c = kdiv(1.0, ksqrt(1.0 + t * t));
+  const double s = c * t;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double gp = G[3 * i + P], gq = G[3 * i + Q];
+    G[3 * i + P] = c * gp - s * gq;
+    G[3 * i + Q] = s * gp + c * gq;
+    const double wp = W[3 * i + P], wq = W[3 * i + Q];
+    W[3 * i + P] = c * wp - s * wq;
+    W[3 * i + Q] = s * wp + c * wq;
+  }
+  return true;
+}
+KML_DI V3 column_of(const double (&M)[9], int j) {  // column j of a row-major 3x3, j in registers
+  V3 v;
+  v.x = j == 0 ? M[0] : (j == 1 ? M[1] : M[2]);
+  v.y = j == 0 ? M[3] : (j == 1 ? M[4] : M[5]);
+  v.z = j == 0 ? M[6] : (j == 1 ? M[7] : M[8]);
+  return v;
+}
+KML_DI void svd3_r(const double* A, double* U, double* S, double* V) {
+  double G[9], W[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    G[i] = A[i];
+    W[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    bool rotated = jacobi_pair_r<0, 1>(G, W);
+    rotated = jacobi_pair_r<0, 2>(G, W) || rotated;
+    rotated = jacobi_pair_r<1, 2>(G, W) || rotated;
+    if (!rotated) break;
+  }
+  double n[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) n[j] = ksqrt((G[j] * G[j] + G[3 + j] * G[3 + j]) + G[6 + j] * G[6 + j]);
+  // stable descending order of the three column norms
+  int i0 = 0, i1 = 1, i2 = 2;
+  double n0 = n[0], n1 = n[1], n2 = n[2];
+  if (n1 > n0) { const int t = i0; i0 = i1; i1 = t; const double d = n0; n0 = n1; n1 = d; }
+  if (n2 > n1) { const int t = i1; i1 = i2; i2 = t; const double d = n1; n1 = n2; n2 = d; }
+  if (n1 > n0) { const int t = i0; i0 = i1; i1 = t; const double d = n0; n0 = n1; n1 = d; }
+  S[0] = n0; S[1] = n1; S[2] = n2;
+  V3 u0, u1;
+  if (n0 > 0.0) {
+    const V3 g0 = column_of(G, i0);
+    u0.x = kdiv(g0.x, n0); u0.y = kdiv(g0.y, n0); u0.z = kdiv(g0.z, n0);
+  } else {
+    u0.x = 1.0; u0.y = 0.0; u0.z = 0.0;
+  }
+  if (n1 > 0.0) {
+    const V3 g1 = column_of(G, i1);
+    u1.x = kdiv(g1.x, n1); u1.y = kdiv(g1.y, n1); u1.z = kdiv(g1.z, n1);
+  } else {
+    int k = 0;
+    double m = fabs(u0.x);
+    if (fabs(u0.y) < m) { k = 1; m = fabs(u0.y); }
+    if (fabs(u0.z) < m) { k = 2; }
+    const V3 e = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+    const V3 c = cross(u0, e);
+    const double nn = ksqrt(dot(c, c));
+    u1.x = kdiv(c.x, nn); u1.y = kdiv(c.y, nn); u1.z = kdiv(c.z, nn);
+  }
+  const V3 u2 = cross(u0, u1);
+  const V3 v0 = column_of(W, i0), v1 = column_of(W, i1);
+  const V3 v2 = cross(v0, v1);
+  U[0] = u0.x; U[1] = u1.x; U[2] = u2.x;
+  U[3] = u0.y; U[4] = u1.y; U[5] = u2.y;
+  U[6] = u0.z; U[7] = u1.z; U[8] = u2.z;
+  V[0] = v0.x; V[1] = v1.x; V[2] = v2.x;
+  V[3] = v0.y; V[4] = v1.y; V[5] = v2.y;
+  V[6] = v0.z; V[7] = v1.z; V[8] = v2.z;
+}
+
 // ------------------------------------------------------------------ Arun
 // p1 = R p2 + t from three correspondences; M = [R|t] row-major 3x4.
 KML_DN void arun3(const double* a1, const double* b1, const double* c1, const double* a2,

@@ -239,7 +239,7 @@ KML_DN void arun3(const double* a1, const double* b1, const double* c1, const do
       for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + d2[r] * d1[c];
   }
   double U[9], S[3], V[9];
-  svd3(H, U, S, V);
+  svd3_r(H, U, S, V);
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll

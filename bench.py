@@ -247,8 +247,11 @@ def main():
             ln.query_batch_run(sharded=sharded)
         ln.query_batch_upload(*batches[li % len(batches)])     # this lane's resident batch
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # clocks / throttle reasons are sampled on rank 0's GPU only: eight nvidia-smi pollers on one
+    # box compete with the lane threads for the host cores
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     l0 = sum(ln.stats().kernel_launches for ln in lanes)
     last = {}
     lock = threading.Lock()
@@ -271,7 +274,7 @@ def main():
     step_ms = det.timer_end(lanes)            # CUDA events: begin on lane 0, end after every lane's last kernel
     wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = sum(ln.stats().kernel_launches for ln in lanes) - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     barrier()
     out, counts = last["out"], last["counts"]
     if dist is not None:

@@ -241,6 +241,10 @@ int kml_timer_end(kml_handle* h, kml_handle** lanes, int n_lanes, float* ms);
  * handle's stream so the next timed step starts with a cold L2 */
 int kml_flush_l2(kml_handle* h);
 
+/* the merge rule alone, on host blocks: nranks x { kml_result[B][cap_in]; int32 counts[B] } */
+int kml_merge_shard_records(const void* blocks, int nranks, int B, int cap_in, int cap, kml_result* out,
+                            int32_t* counts);
+
 /* ---- row f3: post filters and wire layout around the path (host logic) ----
  * Kimera-VIO's detection flow "2 computeIslands() 3 checkTemporalConstraint()"
  * (/root/reference/images/kimera-multi.drawio:1565) with the

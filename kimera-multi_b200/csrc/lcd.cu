@@ -1068,6 +1068,46 @@ int kml_query_batch(kml_handle* h, int B, const uint64_t* q_robot, const uint64_
   KML_API_END(h)
 }
 
+// Merge rule of the sharded query: per query, the union of every rank's records re-ranked by
+// (score desc, match robot asc, match pose asc), best `cap` kept.  Block r starts at
+// base + r*blk_stride: [B][cap_in] records, then (at rec_bytes) B int32 counts.  Pointers are
+// sorted, not the 200-byte records, and nothing is allocated per query.
+static void merge_rank_blocks(const uint8_t* base, size_t blk_stride, size_t rec_bytes, int nr, int B,
+                              int cap_in, int cap, kml_result* out, int32_t* counts) {
+  std::vector<const kml_result*> ptr;
+  ptr.reserve((size_t)nr * cap_in);
+  for (int b = 0; b < B; ++b) {
+    ptr.clear();
+    for (int r = 0; r < nr; ++r) {
+      const uint8_t* blk = base + blk_stride * r;
+      const kml_result* recs = reinterpret_cast<const kml_result*>(blk) + (size_t)b * cap_in;
+      const int32_t c = reinterpret_cast<const int32_t*>(blk + rec_bytes)[b];
+      for (int i = 0; i < c; ++i) ptr.push_back(recs + i);
+    }
+    // (rank, position) breaks exact ties of the key, which keeps the order of a stable sort
+    std::sort(ptr.begin(), ptr.end(), [](const kml_result* x, const kml_result* y) {
+      if (x->norm_bow_score != y->norm_bow_score) return x->norm_bow_score > y->norm_bow_score;
+      if (x->m_robot != y->m_robot) return x->m_robot < y->m_robot;
+      if (x->m_pose != y->m_pose) return x->m_pose < y->m_pose;
+      return x < y;
+    });
+    const int c = (int)std::min<size_t>(ptr.size(), (size_t)cap);
+    for (int i = 0; i < c; ++i) out[(size_t)b * cap + i] = *ptr[i];
+    counts[b] = c;
+  }
+}
+
+// Host-side entry to the same merge (tests, callers that move the blocks themselves): `blocks`
+// holds nranks consecutive blocks of [B][cap_in] records followed by B int32 counts each.
+int kml_merge_shard_records(const void* blocks, int nranks, int B, int cap_in, int cap, kml_result* out,
+                            int32_t* counts) {
+  if (!blocks || nranks < 1 || B < 0 || cap_in < 1 || cap < 1 || (B > 0 && (!out || !counts))) return KML_ERR_ARG;
+  const size_t rec_bytes = sizeof(kml_result) * (size_t)B * cap_in;
+  const size_t blk = rec_bytes + sizeof(int32_t) * (size_t)B;
+  merge_rank_blocks(static_cast<const uint8_t*>(blocks), blk, rec_bytes, nranks, B, cap_in, cap, out, counts);
+  return KML_OK;
+}
+
 // Sharded query: every rank runs the (identical) uploaded batch against its
 // own robot databases, then ONE ncclAllGather merges the fixed-size record
 // blocks; every rank re-ranks the union per query and keeps the best `cap`.
@@ -1094,24 +1134,7 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* co
   if (rc != KML_OK) return rc;
   KML_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_scratch2.p, blk_al * nr, cudaMemcpyDeviceToHost, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
-  std::vector<kml_result> all;
-  for (int b = 0; b < B; ++b) {
-    all.clear();
-    for (int r = 0; r < nr; ++r) {
-      const uint8_t* base = h->h_stage.p + blk_al * r;
-      const kml_result* recs = reinterpret_cast<const kml_result*>(base) + (size_t)b * cap;
-      const int32_t c = reinterpret_cast<const int32_t*>(base + rec_bytes)[b];
-      all.insert(all.end(), recs, recs + c);
-    }
-    std::stable_sort(all.begin(), all.end(), [](const kml_result& x, const kml_result& y) {
-      if (x.norm_bow_score != y.norm_bow_score) return x.norm_bow_score > y.norm_bow_score;
-      if (x.m_robot != y.m_robot) return x.m_robot < y.m_robot;
-      return x.m_pose < y.m_pose;
-    });
-    const int c = (int)std::min<size_t>(all.size(), cap);
-    for (int i = 0; i < c; ++i) out[(size_t)b * cap + i] = all[i];
-    counts[b] = c;
-  }
+  merge_rank_blocks(h->h_stage.p, blk_al, rec_bytes, nr, B, cap, cap, out, counts);
   return KML_OK;
   KML_API_END(h)
 }

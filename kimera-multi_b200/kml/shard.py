@@ -30,3 +30,21 @@ def merge_records(blocks, cap):
             out[b, i] = rows[i]
         counts[b] = n
     return out, counts
+
+
+def merge_records_native(blocks, cap):
+    """The same merge through libkml.so (kml_merge_shard_records) — what kml_query_batch_sharded
+    applies to the all-gathered blocks."""
+    import ctypes as C
+    from . import _lib
+    B = len(blocks[0][1])
+    cap_in = blocks[0][0].shape[1]
+    buf = b"".join(np.ascontiguousarray(rec).tobytes() + np.ascontiguousarray(cnt, np.int32).tobytes()
+                   for rec, cnt in blocks)
+    out = np.zeros((B, cap), blocks[0][0].dtype)
+    counts = np.zeros(B, np.int32)
+    rc = _lib.lib().kml_merge_shard_records(buf, len(blocks), B, cap_in, cap,
+                                           out.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("kml_merge_shard_records: %d" % rc)
+    return out, counts

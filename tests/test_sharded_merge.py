@@ -95,3 +95,26 @@ def test_merge_rule_orders_and_caps():
     assert out["norm_bow_score"][0].tolist() == [0.9, 0.9, 0.7, 0.5]
     assert out["m_robot"][0].tolist() == [0, 1, 1, 0]          # exact score tie -> lower robot id first
     assert shard.owner_rank(13, 6) == 2 and shard.robots_of_rank(1, 6) == [6, 7, 8, 9, 10, 11]
+    # the library's merge (what kml_query_batch_sharded applies after the all-gather) follows the same rule
+    out2, cnt2 = shard.merge_records_native([(a, np.array([2])), (b, np.array([3]))], 4)
+    assert np.array_equal(cnt, cnt2) and out.tobytes() == out2.tobytes()
+    rng = np.random.default_rng(5)
+    blocks = []
+    for r in range(8):
+        rec = np.zeros((16, 6), kml.RESULT_DTYPE)
+        cntr = rng.integers(0, 7, 16).astype(np.int32)
+        rec["norm_bow_score"] = rng.integers(0, 5, (16, 6)) / 4.0     # many exact ties
+        rec["m_robot"] = r
+        rec["m_pose"] = rng.integers(0, 50, (16, 6))
+        rec["mono_inliers"] = rng.integers(0, 99, (16, 6))
+        for b_ in range(16):                                          # per-rank lists arrive sorted, as the library emits them
+            o = np.lexsort((rec["m_pose"][b_, :cntr[b_]], -rec["norm_bow_score"][b_, :cntr[b_]]))
+            rec[b_, :cntr[b_]] = rec[b_, :cntr[b_]][o]
+        blocks.append((rec, cntr))
+    o1, c1 = shard.merge_records(blocks, 10)
+    o2, c2 = shard.merge_records_native(blocks, 10)
+    assert np.array_equal(c1, c2)
+    for b_ in range(16):
+        k1 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o1[b_, :c1[b_]]]
+        k2 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o2[b_, :c2[b_]]]
+        assert k1 == k2

@@ -1,5 +1,7 @@
 // handle.h — kml_handle: host-side state of the LoopClosureDetector replacement.
 #pragma once
+#include <time.h>
+
 #include <map>
 #include <mutex>
 #include <memory>
@@ -98,6 +100,21 @@ struct kml_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_lane = nullptr;  // kml_timer_begin / kml_timer_end
+  // Host waits of the batch path: several lanes per GPU and several GPUs per box put more waiting
+  // threads on the host than it has cores, so a batch wait polls the stream and sleeps 20 us between
+  // polls instead of spinning (a blocking-sync event was tried and doubled the 8-GPU step time);
+  // single queries keep the low-latency spin of cudaStreamSynchronize.
+  bool polite_wait = false;  // set for the duration of a batch of >= 16 queries
+  void wait_stream() {
+    if (!polite_wait) { KML_CUDA(cudaStreamSynchronize(stream)); return; }
+    for (;;) {
+      const cudaError_t e = cudaStreamQuery(stream);
+      if (e == cudaSuccess) return;
+      if (e != cudaErrorNotReady) KML_CUDA(e);
+      struct timespec ts = {0, 20000};
+      nanosleep(&ts, nullptr);
+    }
+  }
   std::string err;
   kml_stats stats = {};
 

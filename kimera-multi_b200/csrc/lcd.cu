@@ -5,6 +5,7 @@
 // SURVEY.md A.4-A.8; call order of kimera_distributed's verifyLoopSpin,
 // /root/reference/images/kimera-multi.drawio:2638-2654).
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -184,7 +185,7 @@ static void run_bow(kml_handle* h, const std::vector<RobotDb*>& dbs, int B, cons
   KML_CUDA(cudaMemcpyAsync(h->h_nss.p, h->d_nss.p, B * 8, cudaMemcpyDeviceToHost, h->stream));
   unsigned long long postings = 0;
   KML_CUDA(cudaMemcpyAsync(&postings, h->d_postings.p, 8, cudaMemcpyDeviceToHost, h->stream));
-  KML_CUDA(cudaStreamSynchronize(h->stream));
+  h->wait_stream();
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_bow, h->ev[0], h->ev[1]));
   h->stats.bow_postings_last = postings;
   for (int b = 0; b < B; ++b) out->nss[b] = h->h_nss.p[b];
@@ -526,7 +527,7 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   KML_CUDA(cudaMemcpyAsync(out->T.data(), h->d_outT.p, 96 * (size_t)P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(stm.data(), h->d_st_mono.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
   KML_CUDA(cudaMemcpyAsync(sts.data(), h->d_st_stereo.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaStreamSynchronize(s));
+  h->wait_stream();
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
@@ -617,6 +618,11 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
   br->recs.assign((size_t)B * cap, kml_result{});
   br->counts.assign(B, 0);
   if (B == 0) return KML_OK;
+  struct PoliteScope {  // batches wait without spinning; single queries keep the low-latency spin
+    kml_handle* h;
+    PoliteScope(kml_handle* hh, bool on) : h(hh) { h->polite_wait = on; }
+    ~PoliteScope() { h->polite_wait = false; }
+  } scope(h, B >= 16);
   KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
   std::vector<RobotDb*> dbs;
   for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
@@ -667,7 +673,7 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
     memcpy(r.T, &vo.T[p * 12], 96);
   }
   KML_CUDA(cudaEventRecord(h->ev[7], h->stream));
-  KML_CUDA(cudaEventSynchronize(h->ev[7]));
+  h->wait_stream();
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_total, h->ev[6], h->ev[7]));
   if (getenv("KML_DEBUG_TIMING")) {
     float a = 0, b = 0, c = 0;
@@ -1072,27 +1078,49 @@ int kml_query_batch(kml_handle* h, int B, const uint64_t* q_robot, const uint64_
 // (score desc, match robot asc, match pose asc), best `cap` kept.  Block r starts at
 // base + r*blk_stride: [B][cap_in] records, then (at rec_bytes) B int32 counts.  Pointers are
 // sorted, not the 200-byte records, and nothing is allocated per query.
+static inline bool rec_before(const kml_result* x, const kml_result* y) {
+  if (x->norm_bow_score != y->norm_bow_score) return x->norm_bow_score > y->norm_bow_score;
+  if (x->m_robot != y->m_robot) return x->m_robot < y->m_robot;
+  return x->m_pose < y->m_pose;
+}
 static void merge_rank_blocks(const uint8_t* base, size_t blk_stride, size_t rec_bytes, int nr, int B,
                               int cap_in, int cap, kml_result* out, int32_t* counts) {
-  std::vector<const kml_result*> ptr;
+  std::vector<const kml_result*> ptr, head(nr), end(nr);
   ptr.reserve((size_t)nr * cap_in);
   for (int b = 0; b < B; ++b) {
-    ptr.clear();
+    // every rank emits its list already ranked by the same key: a k-way merge of the heads needs
+    // cap * nranks comparisons; a list found out of order sends the query to the full sort
+    bool sorted = true;
     for (int r = 0; r < nr; ++r) {
       const uint8_t* blk = base + blk_stride * r;
       const kml_result* recs = reinterpret_cast<const kml_result*>(blk) + (size_t)b * cap_in;
       const int32_t c = reinterpret_cast<const int32_t*>(blk + rec_bytes)[b];
-      for (int i = 0; i < c; ++i) ptr.push_back(recs + i);
+      head[r] = recs;
+      end[r] = recs + c;
+      for (int i = 1; i < c && sorted; ++i) sorted = !rec_before(recs + i, recs + i - 1);
     }
-    // (rank, position) breaks exact ties of the key, which keeps the order of a stable sort
-    std::sort(ptr.begin(), ptr.end(), [](const kml_result* x, const kml_result* y) {
-      if (x->norm_bow_score != y->norm_bow_score) return x->norm_bow_score > y->norm_bow_score;
-      if (x->m_robot != y->m_robot) return x->m_robot < y->m_robot;
-      if (x->m_pose != y->m_pose) return x->m_pose < y->m_pose;
-      return x < y;
-    });
-    const int c = (int)std::min<size_t>(ptr.size(), (size_t)cap);
-    for (int i = 0; i < c; ++i) out[(size_t)b * cap + i] = *ptr[i];
+    int c = 0;
+    if (sorted) {
+      while (c < cap) {
+        int br = -1;
+        for (int r = 0; r < nr; ++r)  // strict "before" keeps the lower rank on exact ties
+          if (head[r] != end[r] && (br < 0 || rec_before(head[r], head[br]))) br = r;
+        if (br < 0) break;
+        out[(size_t)b * cap + c++] = *head[br]++;
+      }
+    } else {
+      ptr.clear();
+      for (int r = 0; r < nr; ++r)
+        for (const kml_result* p = head[r]; p != end[r]; ++p) ptr.push_back(p);
+      // (rank, position) breaks exact ties of the key, which keeps the order of a stable sort
+      std::sort(ptr.begin(), ptr.end(), [](const kml_result* x, const kml_result* y) {
+        if (rec_before(x, y)) return true;
+        if (rec_before(y, x)) return false;
+        return x < y;
+      });
+      c = (int)std::min<size_t>(ptr.size(), (size_t)cap);
+      for (int i = 0; i < c; ++i) out[(size_t)b * cap + i] = *ptr[i];
+    }
     counts[b] = c;
   }
 }
@@ -1116,8 +1144,11 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* co
   if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "bad output");
   const int B = h->B;
   BatchRecs br;
+  const bool dbg = getenv("KML_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = batch_run(h, cap, &br);
   if (rc != KML_OK) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   const int nr = comm_nranks(h);
   if (nr == 1) { copy_out(br, B, cap, out, counts); return KML_OK; }
   if (B == 0) return KML_OK;
@@ -1133,8 +1164,19 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* co
   rc = comm_allgather(h, h->d_scratch.p, h->d_scratch2.p, blk_al);
   if (rc != KML_OK) return rc;
   KML_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_scratch2.p, blk_al * nr, cudaMemcpyDeviceToHost, h->stream));
-  KML_CUDA(cudaStreamSynchronize(h->stream));
+  h->polite_wait = B >= 16;
+  h->wait_stream();
+  h->polite_wait = false;
+  const auto t2 = std::chrono::steady_clock::now();
   merge_rank_blocks(h->h_stage.p, blk_al, rec_bytes, nr, B, cap, cap, out, counts);
+  if (dbg) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[kml r%d] sharded batch: local query %.3f ms, all-gather + copies %.3f ms, merge %.3f ms\n",
+            comm_rank(h), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
   return KML_OK;
   KML_API_END(h)
 }

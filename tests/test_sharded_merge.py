@@ -118,3 +118,14 @@ def test_merge_rule_orders_and_caps():
         k1 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o1[b_, :c1[b_]]]
         k2 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o2[b_, :c2[b_]]]
         assert k1 == k2
+    # a rank whose list is not in rank order (never produced by the library) takes the full-sort path
+    rec0, cnt0 = blocks[0]
+    for b_ in range(16):
+        rec0[b_, :cnt0[b_]] = rec0[b_, :cnt0[b_]][::-1]
+    o1, c1 = shard.merge_records(blocks, 10)
+    o2, c2 = shard.merge_records_native(blocks, 10)
+    assert np.array_equal(c1, c2)
+    for b_ in range(16):
+        k1 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o1[b_, :c1[b_]]]
+        k2 = [(float(x["norm_bow_score"]), int(x["m_robot"]), int(x["m_pose"])) for x in o2[b_, :c2[b_]]]
+        assert k1 == k2

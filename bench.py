@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--impl", default="kml", choices=["kml", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0,
-                    help="query batches kept in flight per GPU (0 = 4 on one GPU, 3 per GPU in the sharded run)")
+                    help="query batches kept in flight per GPU (0 = default, 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +211,7 @@ def main():
 
     kml.build()
     det = kml.LoopClosureDetector(device=local_rank)
-    n_lanes = args.lanes if args.lanes > 0 else (4 if world_size == 1 else 3)
+    n_lanes = args.lanes if args.lanes > 0 else 4
     lanes = [det] + [det.create_lane() for _ in range(n_lanes - 1)]
     if world_size > 1:
         # one communicator per lane: lane i of every rank forms its own all-gather group, so the

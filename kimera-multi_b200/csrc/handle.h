@@ -38,6 +38,10 @@ struct RobotDb {
   std::vector<uint32_t> ids;
   std::vector<float> vals;
   std::vector<uint64_t> entry_to_pose;
+  // dense frame index of the entry's keyframe, -1 = not looked up yet / frame not stored yet.
+  // Filled lazily by the batch query (relaxed atomic int stores of a value that never changes
+  // once set: frames are only ever added), sized by addBowVector.
+  std::vector<int32_t> entry_to_frame;
   std::map<uint64_t, uint32_t> pose_to_entry;
   // device CSR
   bool dirty = true;

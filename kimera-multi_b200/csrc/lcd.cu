@@ -65,6 +65,7 @@ static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_
   const uint32_t entry = db->n_entries();
   db->pose_to_entry[pose] = entry;
   db->entry_to_pose.push_back(pose);
+  db->entry_to_frame.push_back(-1);
   db->ids.insert(db->ids.end(), ids, ids + n);
   db->vals.insert(db->vals.end(), vals, vals + n);
   db->off.push_back((int64_t)db->ids.size());
@@ -246,6 +247,8 @@ static int check_bow(kml_handle* h, const uint32_t* ids, const float* vals, int 
 struct Cand {
   double score;
   uint64_t robot, pose;
+  RobotDb* db;
+  uint32_t entry;
 };
 static void select_candidates(const kml_handle* h, const RobotDb* db, uint64_t q_robot,
                               uint64_t q_pose, double nss, const uint32_t* entry,
@@ -261,7 +264,7 @@ static void select_candidates(const kml_handle* h, const RobotDb* db, uint64_t q
       const uint64_t d = q_pose > pose ? q_pose - pose : pose - q_pose;
       if (d < (uint64_t)P.dist_local) continue;
     }
-    out->push_back({score[i] / nss, db->robot, pose});
+    out->push_back({score[i] / nss, db->robot, pose, const_cast<RobotDb*>(db), entry[i]});
   }
 }
 
@@ -290,6 +293,14 @@ static int add_frames_host(kml_handle* h, uint64_t robot, const uint64_t* poses,
     rec.index = (int32_t)h->sh->frame_off_h.size();
     h->sh->frame_off_h.push_back(rec.feat_off);
     h->sh->frame_F_h.push_back(F);
+    auto prev = h->sh->frames.find(id);
+    if (prev != h->sh->frames.end()) {  // overwritten frame: drop the cached index of its BoW entry
+      auto dit = h->sh->dbs.find(robot);
+      if (dit != h->sh->dbs.end()) {
+        auto eit = dit->second->pose_to_entry.find(poses[i]);
+        if (eit != dit->second->pose_to_entry.end()) dit->second->entry_to_frame[eit->second] = -1;
+      }
+    }
     h->sh->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
   }
   h->sh->n_feat = base + (int64_t)total;
@@ -627,42 +638,65 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
   std::vector<RobotDb*> dbs;
   for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
   BowOut bo;
+  const auto tb0 = std::chrono::steady_clock::now();
   run_bow(h, dbs, B, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
           h->d_pvals.p, h->prm.max_db_results, nullptr, &bo);
+  const auto tb1 = std::chrono::steady_clock::now();
   // candidate selection (detectLoop = detectLoopWithRobot over every robot DB)
   const int K = std::min(h->prm.top_k_verify, cap);
   std::vector<PairDesc> pairs;
   std::vector<int> pair_rec;  // pair -> record index
   std::vector<Cand> cands;
+  auto before = [](const Cand& x, const Cand& y) {  // (robot, pose) is unique: a total order
+    if (x.score != y.score) return x.score > y.score;
+    if (x.robot != y.robot) return x.robot < y.robot;
+    return x.pose < y.pose;
+  };
+  std::vector<Cand> found;
   for (int b = 0; b < B; ++b) {
+    // the K best survivors of every database, kept as a sorted insertion list: most of the
+    // up to n_db * max_db_results survivors lose against the current K-th with one comparison
     cands.clear();
+    size_t survivors = 0;
     for (int d = 0; d < bo.n_db; ++d) {
       const size_t l = (size_t)b * bo.n_db + d;
+      found.clear();
       select_candidates(h, dbs[d], h->q_robot_h[b], h->q_pose_h[b], bo.nss[b],
-                        &bo.entry[l * bo.K], &bo.score[l * bo.K], bo.count[l], &cands);
+                        &bo.entry[l * bo.K], &bo.score[l * bo.K], bo.count[l], &found);
+      survivors += found.size();
+      for (const Cand& c : found) {
+        if (K <= 0 || ((int)cands.size() == K && !before(c, cands.back()))) continue;
+        size_t pos = cands.size();
+        if ((int)cands.size() < K) cands.push_back(c); else pos = cands.size() - 1;
+        while (pos > 0 && before(c, cands[pos - 1])) { cands[pos] = cands[pos - 1]; --pos; }
+        cands[pos] = c;
+      }
     }
-    h->stats.total_bow_matches += cands.size();
-    std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) {
-      if (x.score != y.score) return x.score > y.score;
-      if (x.robot != y.robot) return x.robot < y.robot;
-      return x.pose < y.pose;
-    });
-    const int nv = std::min<int>((int)cands.size(), K);
+    h->stats.total_bow_matches += survivors;
+    const int nv = (int)cands.size();
     br->counts[b] = nv;
     for (int i = 0; i < nv; ++i) {
       kml_result& r = br->recs[(size_t)b * cap + i];
       r.q_robot = h->q_robot_h[b]; r.q_pose = h->q_pose_h[b];
       r.m_robot = cands[i].robot; r.m_pose = cands[i].pose;
       r.norm_bow_score = cands[i].score;
-      auto fit = h->sh->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
-      if (fit == h->sh->frames.end()) { r.status = 3; continue; }
-      pairs.push_back({b, fit->second.index});
+      int32_t* slot = &cands[i].db->entry_to_frame[cands[i].entry];
+      int32_t fidx = __atomic_load_n(slot, __ATOMIC_RELAXED);
+      if (fidx < 0) {
+        auto fit = h->sh->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
+        if (fit == h->sh->frames.end()) { r.status = 3; continue; }
+        fidx = fit->second.index;
+        __atomic_store_n(slot, fidx, __ATOMIC_RELAXED);
+      }
+      pairs.push_back({b, fidx});
       pair_rec.push_back(b * cap + i);
     }
   }
   QuerySide qs{h->d_qdesc.p, h->d_qbear.p, h->d_qpts.p, h->qF};
   VerifyOut vo;
+  const auto tb2 = std::chrono::steady_clock::now();
   verify_pairs(h, pairs, qs, &vo);
+  const auto tb3 = std::chrono::steady_clock::now();
   for (size_t p = 0; p < pairs.size(); ++p) {
     kml_result& r = br->recs[pair_rec[p]];
     r.n_matches = vo.M[p];
@@ -681,6 +715,12 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
     cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&c, h->ev[5], h->ev[7]);
     fprintf(stderr, "[kml] gaps: before bow %.3f ms, bow->match %.3f ms, after stereo %.3f ms\n", a, b, c);
+    auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
+      return std::chrono::duration<double, std::milli>(y - x).count();
+    };
+    fprintf(stderr, "[kml] host: run_bow (launch + wait + copy-out) %.3f ms, candidate selection %.3f ms, "
+            "verify_pairs (setup + launches + wait + copy-out) %.3f ms, record assembly %.3f ms\n",
+            ms(tb0, tb1), ms(tb1, tb2), ms(tb2, tb3), ms(tb3, std::chrono::steady_clock::now()));
   }
   return KML_OK;
 }

@@ -315,6 +315,33 @@ def test_mono_ransac_corner_cases(oracle):
         det.close()
 
 
+def test_frame_overwrite_is_seen_by_the_batch_query(oracle, small_world):
+    """addVLCFrame on an existing id keeps the newest copy (vlc_frames_[id] = frame); the batch query
+    caches entry -> frame indices, so an overwrite after a query must invalidate that cache."""
+    import kml
+    from conftest import fill
+    world, chunks, q = small_world
+    fq, fp = q["frames"], q["prev"]
+    args = (q["q_robot"][:4], q["q_pose"][:4], fq["bow_off"][:5], fq["bow_ids"], fq["bow_vals"], fp["bow_off"][:5],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"][:4], fq["bearings"][:4], fq["points"][:4])
+    det, orc = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    fill(det, chunks, bulk=True)
+    fill(orc, chunks)
+    out0, cnt0 = det.query_batch(*args)                      # fills the cache
+    ref0, rc0 = orc.query_batch(*args)
+    _check_records(ref0, rc0, out0, cnt0)
+    # overwrite the best match of query 0 with an unrelated frame: the pair must now fail verification
+    mr, mp = int(out0[0, 0]["m_robot"]), int(out0[0, 0]["m_pose"])
+    ch = [c for c in chunks if c["robot"] != mr][0]
+    for d_ in (det, orc):
+        d_.addVLCFrame(mr, mp, ch["desc"][7], ch["bearings"][7], ch["points"][7])
+    out1, cnt1 = det.query_batch(*args)
+    ref1, rc1 = orc.query_batch(*args)
+    _check_records(ref1, rc1, out1, cnt1)
+    assert out1[0, 0]["n_matches"] != out0[0, 0]["n_matches"]
+    det.close()
+
+
 def test_mono_generic_isolation_path(oracle, monkeypatch):
     """Stage 2 has a register fast path for polynomials in generic position and a generic path for
     exact-zero leading terms, which random data never reaches: force it and compare with the oracle."""

@@ -241,6 +241,15 @@ int kml_timer_end(kml_handle* h, kml_handle** lanes, int n_lanes, float* ms);
  * handle's stream so the next timed step starts with a cold L2 */
 int kml_flush_l2(kml_handle* h);
 
+/* ---- row f4 (part): shard persistence --------------------------------------
+ * Everything addBowVector / addVLCFrame stored for this handle's robots (BoW vectors in
+ * DBoW2 EntryId order, live frames with descriptors / bearings / points) to one file, and
+ * back into an empty detector through the same add paths: queries after a reload return the
+ * same records.  (The reference front end has no persistence; DBoW2's save()/load() cover
+ * the database only.) */
+int kml_save_shard(kml_handle* h, const char* path);
+int kml_load_shard(kml_handle* h, const char* path);
+
 /* the merge rule alone, on host blocks: nranks x { kml_result[B][cap_in]; int32 counts[B] } */
 int kml_merge_shard_records(const void* blocks, int nranks, int B, int cap_in, int cap, kml_result* out,
                             int32_t* counts);

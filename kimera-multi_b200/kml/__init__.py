@@ -387,6 +387,15 @@ class LoopClosureDetector:
             raise KmlError(rc, "kml_comm_unique_id failed")
         return bytes(buf)
 
+    # ------------------------------------------------ row f4: shard persistence
+    def save(self, path):
+        """Write this detector's BoW databases and frames to one file (kml_save_shard)."""
+        self._check(lib().kml_save_shard(self._h, str(path).encode()))
+
+    def load(self, path):
+        """Replay a saved shard into this (empty) detector (kml_load_shard)."""
+        self._check(lib().kml_load_shard(self._h, str(path).encode()))
+
     # ------------------------------------------------ row f3: post filters, wire layout
     def addVLCFrameMsg(self, robot, pose, desc, versors_f32, keypoints_f32):
         """addVLCFrame from the VLCFrameMsg layout (float32 xyz clouds)."""

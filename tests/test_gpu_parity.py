@@ -342,6 +342,41 @@ def test_frame_overwrite_is_seen_by_the_batch_query(oracle, small_world):
     det.close()
 
 
+def test_shard_save_load_roundtrip(small_world, tmp_path):
+    """kml_save_shard / kml_load_shard: a detector rebuilt from the file answers the batch query with
+    byte-identical records (entry order, frame order and overwritten frames survive), and bad files
+    are refused."""
+    import kml
+    from conftest import fill
+    world, chunks, q = small_world
+    fq, fp = q["frames"], q["prev"]
+    args = (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    det = kml.LoopClosureDetector()
+    fill(det, chunks, bulk=True)
+    ch = chunks[1]
+    det.addVLCFrame(ch["robot"], int(ch["poses"][5]), ch["desc"][9], ch["bearings"][9], ch["points"][9])  # overwrite
+    ref, cnt = det.query_batch(*args)
+    path = tmp_path / "shard.kml"
+    det.save(path)
+    det2 = kml.LoopClosureDetector()
+    det2.load(path)
+    assert det2.numBoWForRobot(0) == det.numBoWForRobot(0) and det2.frameExists(1, int(chunks[1]["poses"][5]))
+    out, c2 = det2.query_batch(*args)
+    assert np.array_equal(cnt, c2) and out.tobytes() == ref.tobytes()
+    bad = tmp_path / "bad.kml"
+    bad.write_bytes(b"not a shard")
+    with pytest.raises(kml.KmlError):
+        kml.LoopClosureDetector().load(bad)
+    with pytest.raises(kml.KmlError):
+        kml.LoopClosureDetector().load(tmp_path / "missing.kml")
+    raw = path.read_bytes()
+    (tmp_path / "cut.kml").write_bytes(raw[: len(raw) // 2])
+    with pytest.raises(kml.KmlError):
+        kml.LoopClosureDetector().load(tmp_path / "cut.kml")
+    det.close(); det2.close()
+
+
 def test_mono_generic_isolation_path(oracle, monkeypatch):
     """Stage 2 has a register fast path for polynomials in generic position and a generic path for
     exact-zero leading terms, which random data never reaches: force it and compare with the oracle."""

@@ -4,23 +4,23 @@
 // 2589-2592, 2646).  Every stage executes the operation sequence of the
 // ARITHMETIC CONTRACT; the stages only differ in what one
 // thread owns:
-//   stage 1  mono_front_thread    thread = draw.  Null space (Householder),
-//            10x20 constraint build (generated straight-line code), Gauss-
-//            Jordan, B(z) cofactors -> n(z), p1, p2, p3, basis (70 doubles).
-//            State in SHARED memory as S(i) = sm[i*STRIDE + thread]: any
-//            per-thread index (pivot row!) is bank-conflict free.  200 slots:
-//              null space   A9 0..44 | Hv 45..89 | Hn 90..94 | x 95..103 | basis 104..139
-//              build, GJ    A[10][20] 0..199
-//              cofactors    Bz 0..44 | p1 45..52 | p2 53..60 | p3 61..67 | nz 68..78
+//   stage 1  mono_front_thread    thread = draw.  Null space (Householder, in
+//            registers), 10x20 constraint build (generated straight-line code),
+//            Gauss-Jordan (one templated step per pivot column), B(z) cofactors in
+//            registers -> n(z), p1, p2, p3, basis (70 doubles).  Only the 10x20
+//            system lives in SHARED memory, as S(i) = sm[i*STRIDE + thread]: any
+//            per-thread index (pivot row!) is bank-conflict free.  200 slots.
 //   stage 2  mono_isolate_thread  thread = draw.  Sturm chains of n(z) and of
 //            the reversed polynomial, root counts, 32-cell sign grid (or
-//            bisection on the Sturm count when two roots share a cell) ->
-//            one isolating bracket per real root.  88 slots:
+//            bisection on the Sturm count when two roots share a cell, deferred
+//            to its own compacted launch) -> one isolating bracket per real
+//            root.  Generic-position fast path in registers; the generic
+//            variable-degree code keeps 88 scratch slots:
 //              scratch 0..10 | nz 11..21 | chain (triangular) 22..87
-//   stage 3  (mono_back_kernel)   thread = (draw, root) ITEM: refine the root,
+//   stage 3  mono_item            thread = (draw, root) ITEM: refine the root,
 //            E, SVD, four (R,t) candidates scored on the 8 sample points.
-// Division, sqrt, Horner and SVD are not inlined and the front CTA's warps pass
-// phase barriers: the SM fetches one compact instruction stream (the first
+// Division and sqrt are not inlined in the big kernels and the front CTA's warps
+// pass phase barriers: the SM fetches one compact instruction stream (the first
 // fully inlined build stalled 63 % of its warp time on instruction fetch).
 #pragma once
 #include "geom.cuh"

@@ -166,23 +166,27 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 }
 
 // ------------------------------------------------------------ mono round
-// Three kernels per round on a grid (P, blocks); CTA (p, blk) owns the 64 draws
+// Six kernels per round.  CTA (p, blk) of the grid kernels owns the 64 draws
 // r_begin + blk*64 + [0,64) of problem p; they hand over through per-round
 // global buffers indexed by slot = p*kRoundCap + blk*64 + t.
 //   mono_front_kernel    thread = draw: null space, constraint build, Gauss-
 //                        Jordan, cofactor polynomials (fivept_thread.cuh stage 1);
 //                        200 shared-memory slots per thread -> 4 warps per SM.
 //   mono_isolate_kernel  thread = draw: Sturm chains + isolating brackets of the
-//                        real roots (stage 2); 88 slots -> 10 warps per SM.
-//   mono_back_kernel     (a) thread = (draw, root) ITEM: refine root, E, SVD, the
-//                        four (R,t) candidates scored on the 8 sample points —
-//                        every item costs the same, no thread waits for another
-//                        draw's larger root count; (b) thread = draw: winner in
-//                        the reference's order (strict <, first 10 roots);
-//                        (c) warp = draw: lanes stride over all correspondences,
-//                        inlier count by ballot + popc, stopping early once the
-//                        draw cannot beat the best count the problem had before
-//                        this round (such a draw can never become the model).
+//                        real roots (stage 2, registers only); reserves the
+//                        draw's range in the round's item list.
+//   mono_isolate_deferred_kernel  thread = (draw, chain, root) of the compacted
+//                        list of chains whose sign grid did not separate the roots.
+//   mono_item_kernel     thread = (draw, root) ITEM, grid-stride over the whole
+//                        round's list: refine root, E, SVD, the four (R,t)
+//                        candidates scored on the 8 sample points — every item
+//                        costs the same, no barrier, no tail.
+//   mono_count_kernel    thread = draw: winner in the reference's order (strict <,
+//                        first 10 refined roots); warp = draw: lanes stride over
+//                        the correspondences, inlier count by ballot + popc with
+//                        the fast inlier filter, stopping once the draw cannot
+//                        beat the best count of the draws before it.
+//   sac_replay_kernel    lane 0 per problem replays Ransac::computeModel.
 __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;

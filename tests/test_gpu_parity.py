@@ -342,6 +342,51 @@ def test_frame_overwrite_is_seen_by_the_batch_query(oracle, small_world):
     det.close()
 
 
+def test_ragged_and_large_frames(oracle, small_world):
+    """Stored frames of different sizes in one database: truncated (F = 37, 300), empty (F = 0) and
+    full (F = 500) keyframes answer the same batch query as the oracle; and a 2 500-feature pair goes
+    through the per-call API (beyond the count kernel's shared-memory staging limit)."""
+    import kml
+    from kml import synth
+    world, chunks, q = small_world
+    det, orc = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    sizes = [500, 37, 300, 0]
+    for ch in chunks:
+        for i, p in enumerate(ch["poses"]):
+            F = sizes[(int(p) + ch["robot"]) % 4]
+            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
+            for d_ in (det, orc):
+                d_.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
+                d_.addVLCFrame(ch["robot"], int(p), ch["desc"][i][:F], ch["bearings"][i][:F], ch["points"][i][:F])
+    fq, fp = q["frames"], q["prev"]
+    args = (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    out0, cnt0 = orc.query_batch(*args)
+    out1, cnt1 = det.query_batch(*args)
+    _check_records(out0, cnt0, out1, cnt1)
+    assert set(np.unique(out1["n_matches"][out1["status"] != 3])) != {0}
+    det.close()
+    # a pair of 2 500-feature frames of one place
+    big = synth.World(4, F=2500)
+    fa = big.frames(0, [10], places=[1], key=5)
+    fb = big.frames(1, [20], places=[1], key=6)
+    det, orc = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    for d_ in (det, orc):
+        d_.addVLCFrame(0, 10, fa["desc"][0], fa["bearings"][0], fa["points"][0])
+        d_.addVLCFrame(1, 20, fb["desc"][0], fb["bearings"][0], fb["points"][0])
+    iq0, im0 = orc.computeMatchedIndices(0, 10, 1, 20)
+    iq1, im1 = det.computeMatchedIndices(0, 10, 1, 20)
+    assert len(iq0) > 600 and np.array_equal(iq0, iq1) and np.array_equal(im0, im1)
+    ok0, jq0, jm0, R0 = orc.geometricVerificationNister(0, 10, 1, 20, iq0, im0)
+    ok1, jq1, jm1, R1 = det.geometricVerificationNister(0, 10, 1, 20, iq1, im1)
+    assert ok0 and ok1 and np.array_equal(jq0, jq1) and np.array_equal(jm0, jm1)
+    assert np.abs(R0 - R1).max() <= POSE_TOL
+    ok0, kq0, km0, T0 = orc.recoverPose(0, 10, 1, 20, jq0, jm0)
+    ok1, kq1, km1, T1 = det.recoverPose(0, 10, 1, 20, jq1, jm1, R_prior=R1)
+    assert ok0 and ok1 and np.array_equal(kq0, kq1) and np.abs(T0 - T1).max() <= POSE_TOL
+    det.close()
+
+
 def test_shard_save_load_roundtrip(small_world, tmp_path):
     """kml_save_shard / kml_load_shard: a detector rebuilt from the file answers the batch query with
     byte-identical records (entry order, frame order and overwritten frames survive), and bad files

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a)
 }
 
 // ---------------------------------------------------------- stereo chunk
+template <bool STAGED>  // STAGED: the problem's point pairs fit in shared memory (else read through L1)
 __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   const int p = blockIdx.x;
@@ -416,15 +417,21 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
   const int d0 = st.r_begin + blockIdx.y * kStereoChunk;
   if (d0 >= st.r_end) return;
   const int N = a.N[p];
-  double* s1 = smem_d;
-  double* s2 = smem_d + 3 * (size_t)N;
-  double* smod = s2 + 3 * (size_t)N;  // [kStereoChunk][12]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  for (int i = tid; i < 3 * N; i += kStereoThreads) {
-    s1[i] = ga[i];
-    s2[i] = gb[i];
+  double* smod = smem_d;  // [kStereoChunk][12]
+  const double* s1 = ga;
+  const double* s2 = gb;
+  if (STAGED) {
+    double* w1 = smem_d + 12 * kStereoChunk;
+    double* w2 = w1 + 3 * (size_t)N;
+    for (int i = tid; i < 3 * N; i += kStereoThreads) {
+      w1[i] = ga[i];
+      w2[i] = gb[i];
+    }
+    s1 = w1;
+    s2 = w2;
   }
   __syncthreads();
   const int nh = min(kStereoChunk, st.r_end - d0);
@@ -645,10 +652,15 @@ static void ensure_smem(K kernel, size_t bytes) {
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (a.P <= 0) return;
   const size_t sm = sizeof(uint16_t) * (size_t)a.stride;
-  if (sample_size == 8)
+  if (sample_size == 8) {
+    ensure_smem(sac_init_kernel<8, kMonoChunk>, sm);
+    ensure_smem(sac_replay_kernel<8, kMonoChunk>, sm);
     sac_init_kernel<8, kMonoChunk><<<a.P, 32, sm, s>>>(a);
-  else
+  } else {
+    ensure_smem(sac_init_kernel<3, kStereoChunk>, sm);
+    ensure_smem(sac_replay_kernel<3, kStereoChunk>, sm);
     sac_init_kernel<3, kStereoChunk><<<a.P, 32, sm, s>>>(a);
+  }
 }
 
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
@@ -679,10 +691,14 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
-  ensure_smem(stereo_chunk_kernel, sm);
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
-  stereo_chunk_kernel<<<dim3(a.P, blocks), kStereoThreads, sm, s>>>(a);
+  if (sm <= 96 * 1024) {
+    ensure_smem(stereo_chunk_kernel<true>, sm);
+    stereo_chunk_kernel<true><<<dim3(a.P, blocks), kStereoThreads, sm, s>>>(a);
+  } else {
+    stereo_chunk_kernel<false><<<dim3(a.P, blocks), kStereoThreads, sizeof(double) * 12 * kStereoChunk, s>>>(a);
+  }
   sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
   return 2;
 }

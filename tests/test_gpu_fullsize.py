@@ -100,3 +100,36 @@ def test_c2_shaped_batch_against_oracle(oracle):
                 assert np.abs(T[:, :3] - Rgt).max() < 0.2 and np.abs(T[:, 3] - tgt).max() < 1.0   # 3-point model, noise-limited
     assert n_lc >= 32 * 4
     det.close()
+
+
+def test_ransac_batches_with_many_correspondences(oracle):
+    """Maximum sizes of the batched RANSAC entry points: 30 000 point pairs (stereo) and 6 000
+    bearing pairs (mono) per problem — beyond what fits the kernels' shared-memory staging, so the
+    unstaged variants run — bit-identical inlier sets against the oracle."""
+    import kml
+    from kml import mask_to_indices
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(99)
+    det = kml.LoopClosureDetector()
+    N = 30000
+    X = np.c_[rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(2, 12, N)]
+    R = Rot.from_rotvec(rng.normal(size=3) * 0.2).as_matrix(); t = rng.uniform(-1, 1, 3)
+    X2 = (X - t) @ R + rng.normal(size=X.shape) * 0.02
+    out = rng.random(N) < 0.3
+    X2[out] = rng.uniform(-8, 8, (out.sum(), 3))
+    g = det.ransac_arun_batch(X[None], X2[None])
+    o = oracle.ransac_arun(X, X2, 0.5, 0.995, 1000, 12345)
+    assert o["iterations"] == g["iterations"][0] and o["best_draw"] == g["best_draw"][0]
+    assert o["n_inliers"] == g["n_inliers"][0] and o["n_inliers"] > 0.6 * N
+    assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][0], N))
+    N = 6000
+    a = X[:N] / np.linalg.norm(X[:N], axis=1, keepdims=True)
+    b = (X[:N] - t) @ R + rng.normal(size=(N, 3)) * 2e-3
+    b[out[:N]] = rng.normal(size=(out[:N].sum(), 3))
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    g = det.ransac_nister_batch(a[None], b[None])
+    o = oracle.ransac_nister(a, b, 1e-6, 0.995, 1000, 12345)
+    assert o["iterations"] == g["iterations"][0] and o["best_draw"] == g["best_draw"][0]
+    assert o["n_inliers"] == g["n_inliers"][0]
+    assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][0], N))
+    det.close()

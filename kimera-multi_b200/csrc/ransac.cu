@@ -51,9 +51,42 @@ __device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict
   }
 }
 
+// Warp version: the modulo of every (draw, i) is independent of the shuffle state, so all lanes
+// compute them (jrel_s, at most kRoundCap*S entries) and lane 0 is left with the swaps.
+template <int S>
+__device__ void draw_samples_warp(uint16_t* perm_s, uint16_t* jrel_s, int N, const uint32_t* __restrict__ raw,
+                                  int first, int last, uint16_t* out, int lane) {
+  const int n = (last - first) * S;
+  for (int idx = lane; idx < n; idx += 32) {
+    const int i = idx % S;
+    jrel_s[idx] = (uint16_t)(raw[first * S + idx] % (uint32_t)(N - i));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int d = 0; d < last - first; ++d) {
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const int j = i + (int)jrel_s[d * S + i];
+        const uint16_t t = perm_s[i];
+        perm_s[i] = perm_s[j];
+        perm_s[j] = t;
+      }
+#pragma unroll
+      for (int i = 0; i < S; ++i) out[(size_t)(first + d) * S + i] = perm_s[i];
+    }
+  }
+  __syncwarp();
+}
+// dynamic shared memory of sac_init / sac_replay: perm[stride] u16 | vc[kRoundCap] i32 | jrel[kRoundCap*S] u16
+__host__ __device__ inline size_t sac_perm_bytes(int stride) { return ((size_t)stride * 2 + 15) / 16 * 16; }
+template <int S>
+__host__ __device__ inline size_t sac_warp_smem(int stride) {
+  return sac_perm_bytes(stride) + sizeof(int32_t) * kRoundCap + sizeof(uint16_t) * kRoundCap * S;
+}
+
 template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
-  extern __shared__ uint16_t perm_s[];
+  extern __shared__ __align__(16) uint16_t perm_s[];
   const int p = blockIdx.x;
   const int lane = threadIdx.x;
   const int N = a.N[p];
@@ -83,9 +116,13 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
     st->done = (N < S) ? 1 : 0;  // getSamples(): N < sample_size => loop exits, no model
     st->r_begin = 0;
     st->r_end = (N < S) ? 0 : min(CHUNK, a.cap_draws);
-    if (N >= S) draw_samples<S>(perm_s, N, a.raw, 0, st->r_end, a.samples + (size_t)p * a.cap_draws * S);
   }
   __syncwarp();
+  if (N >= S) {
+    uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
+                                                   sizeof(int32_t) * kRoundCap);
+    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * a.cap_draws * S, lane);
+  }
   for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
 }
@@ -95,28 +132,35 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
 // known exactly (up to skipped samples): the next round covers all of them.
 template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
-  extern __shared__ uint16_t perm_s[];
+  extern __shared__ __align__(16) uint16_t perm_s[];
   const int p = blockIdx.x;
   const int lane = threadIdx.x;
   SacState* st = &a.st[p];
   if (st->done) return;
   const int N = a.N[p];
+  int32_t* vc_s = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride));
+  uint16_t* jrel_s = reinterpret_cast<uint16_t*>(vc_s + kRoundCap);
   for (int i = lane; i < N; i += 32) perm_s[i] = a.perm[(size_t)p * a.stride + i];
+  {  // the round's (valid, count) results, fetched by the whole warp: count, or -1 for "no model"
+    const int rb = st->r_begin, re = st->r_end;
+    const int32_t* gv = a.valid + (size_t)p * a.cap_draws;
+    const int32_t* gc = a.counts + (size_t)p * a.cap_draws;
+    for (int i = rb + lane; i < re; i += 32) vc_s[i - rb] = gv[i] ? gc[i] : -1;
+  }
   __syncwarp();
+  int nb_w = 0, ne_w = 0, done_w = 1;
   if (lane == 0) {
     int iterations = st->iterations, skipped = st->skipped, draws = st->draws;
     int best = st->best, best_draw = st->best_draw, done = 0, exhausted = 0;
     double k = st->k;
     const int max_skip = a.max_iterations * 10;
     const int r_begin = st->r_begin, r_end = st->r_end;
-    const int32_t* valid = a.valid + (size_t)p * a.cap_draws;
-    const int32_t* counts = a.counts + (size_t)p * a.cap_draws;
     int best_slot = -1;
     for (int gd = r_begin; gd < r_end; ++gd) {
       if (!((a.full || (double)iterations < k) && skipped < max_skip)) { done = 1; break; }
       ++draws;
-      if (!valid[gd]) { ++skipped; continue; }
-      const int n = counts[gd];
+      const int n = vc_s[gd - r_begin];
+      if (n < 0) { ++skipped; continue; }
       if (n > best) {
         best = n;
         best_draw = gd;
@@ -158,11 +202,15 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     st->done = done;
     st->r_begin = nb;
     st->r_end = ne;
-    if (!done) draw_samples<S>(perm_s, N, a.raw, nb, ne, a.samples + (size_t)p * a.cap_draws * S);
+    nb_w = nb; ne_w = ne; done_w = done;
   }
-  __syncwarp();
-  if (!st->done)
+  nb_w = __shfl_sync(0xFFFFFFFFu, nb_w, 0);
+  ne_w = __shfl_sync(0xFFFFFFFFu, ne_w, 0);
+  done_w = __shfl_sync(0xFFFFFFFFu, done_w, 0);
+  if (!done_w) {
+    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, nb_w, ne_w, a.samples + (size_t)p * a.cap_draws * S, lane);
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
+  }
 }
 
 // ------------------------------------------------------------ mono round
@@ -651,7 +699,7 @@ static void ensure_smem(K kernel, size_t bytes) {
 
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (a.P <= 0) return;
-  const size_t sm = sizeof(uint16_t) * (size_t)a.stride;
+  const size_t sm = sample_size == 8 ? sac_warp_smem<8>(a.stride) : sac_warp_smem<3>(a.stride);
   if (sample_size == 8) {
     ensure_smem(sac_init_kernel<8, kMonoChunk>, sm);
     ensure_smem(sac_replay_kernel<8, kMonoChunk>, sm);
@@ -685,7 +733,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
 #ifdef KML_FILTER_STATS
   if (round == kSacRounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
 #endif
-  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sac_warp_smem<8>(a.stride), s>>>(a, round);
   return 6;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
@@ -699,7 +747,7 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   } else {
     stereo_chunk_kernel<false><<<dim3(a.P, blocks), kStereoThreads, sizeof(double) * 12 * kStereoChunk, s>>>(a);
   }
-  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sizeof(uint16_t) * (size_t)a.stride, s>>>(a, round);
+  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sac_warp_smem<3>(a.stride), s>>>(a, round);
   return 2;
 }
 void launch_mono_select(const SacArgs& a, cudaStream_t s) {

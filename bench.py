@@ -21,6 +21,7 @@ reference algorithms, all host threads) on bounded samples of the same
 workload.
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -33,9 +34,10 @@ sys.path.insert(0, os.path.join(ROOT, "kimera-multi_b200"))
 
 import numpy as np  # noqa: E402
 
-N_ROBOTS = 6
+N_ROBOTS = 6          # per GPU; --workload c5 sets 1 x 50 000 (BASELINE.json configs[4])
 N_KEYFRAMES = 5000
 BATCH = 256
+WORKLOAD = "C2"
 F = 500
 METRIC = "loop_closure_queries_per_s"
 UNIT = "queries/s"
@@ -165,9 +167,9 @@ def run_reference(args, rank, world_size, log):
 
 
 def workload_config(n):
-    return {"workload": "C2: %d robot DBs x %d keyframes per GPU, %d ORB-256 features/keyframe, "
+    return {"workload": "%s: %d robot DBs x %d keyframes per GPU, %d ORB-256 features/keyframe, "
                         "%d-query batches, top_k_verify 16, lowe 0.9, mono 5-pt + stereo Arun RANSAC "
-                        "(max 1000 it, p 0.995)" % (N_ROBOTS, N_KEYFRAMES, F, BATCH),
+                        "(max 1000 it, p 0.995)" % (WORKLOAD, N_ROBOTS, N_KEYFRAMES, F, BATCH),
             "global_batch": BATCH, "n_robots_per_gpu": N_ROBOTS, "keyframes_per_robot": N_KEYFRAMES,
             "parallelism": "robot-sharded x%d, replicated query batch + 1 ncclAllGather/step" % n if n > 1 else "single GPU",
             "l2": "256 MiB device memset before the timed region; each step re-reads ~200 MB (touched postings, 4 096 candidate "
@@ -175,6 +177,7 @@ def workload_config(n):
 
 
 def main():
+    global N_ROBOTS, N_KEYFRAMES, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -183,11 +186,28 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0,
                     help="query batches kept in flight per GPU (0 = default, 4)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: 6 robot DBs x 5 000 keyframes per GPU (the headline config); "
+                         "c5: one robot DB of 50 000 keyframes per GPU (BASELINE.json configs[4])")
+    ap.add_argument("--watchdog-s", type=int, default=1500,
+                    help="dump every thread's stack and exit if the run has not finished by then (0 = off)")
     args = ap.parse_args()
+    if args.watchdog_s > 0:
+        # a wedged collective or lane thread must end the process, not hold the GPU box
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
+    if args.workload == "c5":
+        N_ROBOTS, N_KEYFRAMES, WORKLOAD = 1, 50000, "C5"
     args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size > 1 and args.lanes > 4:
+        # every lane launches its all-gather on its own stream in its own order; with more streams
+        # than hardware queues (8 by default) two lanes can share a queue, and a rank whose lane-0
+        # collective sits behind its lane-5 collective then waits on a peer that queued them the
+        # other way round (8 GPUs x 6 lanes did not finish in 200 s; <= 4 lanes never stalled).
+        # The driver reads this when the CUDA context is created.
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
     def log(msg):
         print("[bench r%d] %s" % (rank, msg), file=sys.stderr, flush=True)

@@ -596,8 +596,13 @@ static int batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uin
   const size_t nw = (size_t)bow_off[B], np = (size_t)prev_off[B];
   cudaStream_t s = h->stream;
   h->d_qoff.scratch(B + 1); h->d_poff.scratch(B + 1);
-  h->d_qids.scratch(std::max<size_t>(nw, 1)); h->d_qvals.scratch(std::max<size_t>(nw, 1));
-  h->d_pids.scratch(std::max<size_t>(np, 1)); h->d_pvals.scratch(std::max<size_t>(np, 1));
+  // word buffers are sized for the largest batch of this shape (check_bow caps a vector at
+  // kBowMaxWords), not for this batch's word count: a steady stream of B-query batches then never
+  // reallocates.  cudaFree waits for the whole device, and with several lanes in a sharded run a
+  // lane stuck there behind another lane's pending all-gather can close a wait cycle across ranks.
+  const size_t w_cap = (size_t)B * kBowMaxWords;
+  h->d_qids.scratch(w_cap); h->d_qvals.scratch(w_cap);
+  h->d_pids.scratch(w_cap); h->d_pvals.scratch(w_cap);
   h->d_qdesc.scratch((size_t)B * F * 32 + 32);
   h->d_qbear.scratch((size_t)B * F * 3 + 3); h->d_qpts.scratch((size_t)B * F * 3 + 3);
   KML_CUDA(cudaMemcpyAsync(h->d_qoff.p, bow_off, 8 * (B + 1), cudaMemcpyHostToDevice, s));

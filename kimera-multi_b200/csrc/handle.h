@@ -119,6 +119,11 @@ struct kml_handle {
       nanosleep(&ts, nullptr);
     }
   }
+  // While a batch runs: B * top_k_verify, the most candidate pairs the batch can yield.  The
+  // verification scratch is allocated for that many pairs, not for the pairs this batch happened
+  // to produce, so equal-shaped batches never reallocate (cudaFree waits for the whole device,
+  // i.e. for every other lane's kernels and pending collectives).  0 = size by the actual count.
+  int pair_cap = 0;
   std::string err;
   kml_stats stats = {};
 

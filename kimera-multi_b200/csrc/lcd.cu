@@ -373,6 +373,7 @@ struct SacBufs {
 static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
                     const int32_t* d_N, int stride, int full, SacBufs out, int mask_words) {
   if (P <= 0) return;
+  const size_t Pa = std::max<size_t>((size_t)P, (size_t)h->pair_cap);  // allocation size, see kml_handle::pair_cap
   const kml_params& prm = h->prm;
   const int S = mono ? 8 : 3;
   const int chunk = mono ? kMonoChunk : kStereoChunk;
@@ -389,28 +390,28 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     if (cap_draws - cum > kRoundCap)
       throw std::runtime_error("max_ransac_iterations too large for the RANSAC round schedule (limit 1279)");
   }
-  h->d_perm.scratch((size_t)P * stride);
-  h->d_samples.scratch((size_t)P * cap_draws * S);
-  h->d_models.scratch((size_t)P * kRoundCap * 12);
+  h->d_perm.scratch(Pa * stride);
+  h->d_samples.scratch(Pa * cap_draws * S);
+  h->d_models.scratch(Pa * kRoundCap * 12);
   if (mono) {
-    h->d_nsol.scratch((size_t)P * kRoundCap);
-    h->d_esol.scratch((size_t)P * kRoundCap * 70);
-    h->d_brk.scratch((size_t)P * kRoundCap * 40);
-    h->d_fb_list.scratch((size_t)P * kRoundCap * 20 + 2);
+    h->d_nsol.scratch(Pa * kRoundCap);
+    h->d_esol.scratch(Pa * kRoundCap * 70);
+    h->d_brk.scratch(Pa * kRoundCap * 40);
+    h->d_fb_list.scratch(Pa * kRoundCap * 20 + 2);
     // (draw, root) items of a round: up to 20 brackets per draw (both Sturm chains)
-    const size_t max_items = (size_t)P * kRoundCap * 20;
-    h->d_item_base.scratch((size_t)P * kRoundCap);
+    const size_t max_items = Pa * kRoundCap * 20;
+    h->d_item_base.scratch(Pa * kRoundCap);
     h->d_item_list.scratch(max_items);
     h->d_item_q.scratch(max_items);
     h->d_item_model.scratch(max_items * 12);
     h->d_item_status.scratch(max_items);
   }
-  h->d_valid.scratch((size_t)P * cap_draws);
-  h->d_counts.scratch((size_t)P * cap_draws);
-  out.st->scratch(P);
-  out.best->scratch((size_t)P * 12);
-  out.mask->scratch((size_t)P * mask_words);
-  out.inl->scratch(P);
+  h->d_valid.scratch(Pa * cap_draws);
+  h->d_counts.scratch(Pa * cap_draws);
+  out.st->scratch(Pa);
+  out.best->scratch(Pa * 12);
+  out.mask->scratch(Pa * mask_words);
+  out.inl->scratch(Pa);
   SacArgs a;
   a.P = P; a.a = d_a; a.b = d_b; a.N = d_N; a.stride = stride;
   a.raw = h->sh->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
@@ -459,12 +460,13 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
   h->stats.pairs_last = P;
   if (P == 0) return;
   ensure_frame_offsets(h);
+  const size_t Pa = std::max<size_t>((size_t)P, (size_t)h->pair_cap);  // allocation size, see kml_handle::pair_cap
   const int stride = std::max(qs.F, 8);
   const int mask_words = (stride + 31) / 32;
   // ---- jobs
   std::vector<HamJob> jobs(P);
   std::vector<int32_t> nq(P, qs.F);
-  h->d_keys.scratch((size_t)P * stride * 2);
+  h->d_keys.scratch(Pa * stride * 2);
   for (int p = 0; p < P; ++p) {
     jobs[p].q = qs.desc + (size_t)pairs[p].q_slot * qs.F * 32;
     jobs[p].nq = qs.F;
@@ -472,13 +474,13 @@ static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, cons
     jobs[p].nt = h->sh->frame_F_h[pairs[p].m_frame];
     jobs[p].keys = h->d_keys.p + (size_t)p * stride * 2;
   }
-  h->d_jobs.scratch(P); h->d_pairs.scratch(P); h->d_nq.scratch(P);
-  h->d_iq.scratch((size_t)P * stride); h->d_im.scratch((size_t)P * stride);
-  h->d_kq.scratch((size_t)P * stride); h->d_km.scratch((size_t)P * stride);
-  h->d_M.scratch(P); h->d_N3.scratch(P); h->d_mono_ok.scratch(P); h->d_status.scratch(P);
-  h->d_out_mono.scratch(P); h->d_out_stereo.scratch(P);
-  h->d_a.scratch((size_t)P * stride * 3); h->d_b.scratch((size_t)P * stride * 3);
-  h->d_outR.scratch((size_t)P * 9); h->d_outT.scratch((size_t)P * 12);
+  h->d_jobs.scratch(Pa); h->d_pairs.scratch(Pa); h->d_nq.scratch(Pa);
+  h->d_iq.scratch(Pa * stride); h->d_im.scratch(Pa * stride);
+  h->d_kq.scratch(Pa * stride); h->d_km.scratch(Pa * stride);
+  h->d_M.scratch(Pa); h->d_N3.scratch(Pa); h->d_mono_ok.scratch(Pa); h->d_status.scratch(Pa);
+  h->d_out_mono.scratch(Pa); h->d_out_stereo.scratch(Pa);
+  h->d_a.scratch(Pa * stride * 3); h->d_b.scratch(Pa * stride * 3);
+  h->d_outR.scratch(Pa * 9); h->d_outT.scratch(Pa * 12);
   cudaStream_t s = h->stream;
   KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(HamJob) * P, cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaMemcpyAsync(h->d_pairs.p, pairs.data(), sizeof(PairDesc) * P, cudaMemcpyHostToDevice, s));
@@ -639,6 +641,11 @@ static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
     PoliteScope(kml_handle* hh, bool on) : h(hh) { h->polite_wait = on; }
     ~PoliteScope() { h->polite_wait = false; }
   } scope(h, B >= 16);
+  struct PairCapScope {  // verification scratch sized for the most pairs a batch of this shape can yield
+    kml_handle* h;
+    PairCapScope(kml_handle* hh, int n) : h(hh) { h->pair_cap = n; }
+    ~PairCapScope() { h->pair_cap = 0; }
+  } cap_scope(h, B * std::max(0, std::min(h->prm.top_k_verify, cap)));
   KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
   std::vector<RobotDb*> dbs;
   for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());

@@ -142,7 +142,7 @@ def run_reference(args, rank, world_size, log):
             lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
     log("oracle database ready in %.1fs" % (time.time() - t0))
     threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
-    sample = max(2 * threads, 16)
+    sample = BATCH if threads >= 4 else 64  # a step = the whole 256-query batch of the GPU arm
     batches = make_batches(world, args.steps + args.warmup, N_ROBOTS, B=sample)
     times = []
     for i, b in enumerate(batches):
@@ -160,7 +160,7 @@ def run_reference(args, rank, world_size, log):
         "data": "synthetic",
         "config": workload_config(1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d-query samples of the 256-query batch, %d OpenMP threads" % (sample, threads)},
+                         "sample": "%d-query batches of the %s workload per step, %d OpenMP threads" % (sample, WORKLOAD, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -432,14 +432,14 @@ def cpu_baseline(world, robots, log):
             lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
     log("oracle database ready in %.1fs" % (time.time() - t0))
     threads = len(os.sched_getaffinity(0))
-    sample = max(4 * threads, 32)
+    sample = BATCH if threads >= 4 else 64  # the whole 256-query batch: ~15-20 core-seconds
     b = make_batches(world, 1, N_ROBOTS, B=sample)[0]
     lcd.query_batch(*b, threads=threads)  # warm-up
     t0 = time.perf_counter()
     lcd.query_batch(*b, threads=threads)
     dt = time.perf_counter() - t0
     return {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d queries of the C2 workload, %d OpenMP threads, %.2fs" % (sample, threads, dt)}
+            "sample": "%d queries (one batch) of the %s workload, %d OpenMP threads, %.2fs" % (sample, WORKLOAD, threads, dt)}
 
 
 if __name__ == "__main__":

@@ -78,3 +78,41 @@ def write_lcd_status_csv(path, rows, append=False):
             w.writerow([r.get(k, 0) for k in STATUS_HEADER])
             n += 1
     return n
+
+
+RESULT_HEADER = ["timestamp_kf", "timestamp_query", "timestamp_match", "isLoop", "matchKfId", "queryKfId",
+                 "x", "y", "z", "qw", "qx", "qy", "qz"]
+
+
+def write_lcd_result_csv(path, rows, append=False):
+    """`output_lcd_result.csv` of the intra-robot detector: one row per processed keyframe, the
+    third file /root/reference/evaluation/lc_result.py:165-183 reads (columns used: isLoop,
+    queryKfId, matchKfId, timestamp_query, timestamp_match, x, y, z, qx, qy, qz, qw).  That reader
+    walks the isLoop == 1 rows in file order and asserts that the k-th of them names the same
+    (query, match) pair as the k-th LOOP_DETECTED row of output_lcd_status.csv, so both files must
+    be written from the same sequence of detections.  rows = iterable of dicts: timestamp_kf,
+    timestamp_query, timestamp_match, isLoop, matchKfId, queryKfId and either T (3x4 row-major
+    T_match_query, as kml.RESULT_DTYPE holds it) or x, y, z, qx, qy, qz, qw; a row without a loop
+    (isLoop 0) is written with the identity pose."""
+    n = 0
+    with open(path, "a" if append else "w", newline="") as f:
+        w = csv.writer(f)
+        if not append:
+            w.writerow(RESULT_HEADER)
+        for r in rows:
+            r = dict(r)
+            if "T" in r and r["T"] is not None:
+                T = np.asarray(r["T"], dtype=np.float64).reshape(3, 4)
+                q = rot_to_quat(T[:, :3])
+                r.update(x=float(T[0, 3]), y=float(T[1, 3]), z=float(T[2, 3]),
+                         qx=float(q[0]), qy=float(q[1]), qz=float(q[2]), qw=float(q[3]))
+            elif not int(r.get("isLoop", 0)):
+                for k, v in (("x", 0.0), ("y", 0.0), ("z", 0.0), ("qx", 0.0), ("qy", 0.0), ("qz", 0.0), ("qw", 1.0)):
+                    r.setdefault(k, v)
+            out = []
+            for k in RESULT_HEADER:
+                v = r.get(k, 0)
+                out.append(repr(float(v)) if k in ("x", "y", "z", "qw", "qx", "qy", "qz") else int(v))
+            w.writerow(out)
+            n += 1
+    return n

@@ -52,3 +52,30 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pkg, "libkml.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "torch" not in out
+
+
+def run_c_client(tmp_path):
+    """Compile tests/abi_client.c as strict C99 against include/kml.h, link it to libkml.so and run it."""
+    import subprocess
+    import kml
+    kml.build()
+    pkg = os.path.join(ROOT, "kimera-multi_b200")
+    exe = str(tmp_path / "abi_client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_client.c"), "-o", exe, "-L", pkg, "-lkml",
+                    "-Wl,-rpath," + pkg], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/kml.h under gcc -std=c99 -pedantic -Werror (and as C++11); a C program with no Python
+    or torch in the process links libkml.so and, on a box without a GPU, is refused loudly."""
+    import subprocess
+    import kml
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++",
+                    os.path.join(ROOT, "include", "kml.h")], check=True)
+    out = run_c_client(tmp_path)
+    if kml.device_count() == 0:
+        assert "no device, create refused" in out and "no CPU fallback" in out

@@ -315,7 +315,11 @@ KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, c
 //   true e >= thr  =>  e~ >= e - g(e) > thr - m (never reported as inlier, which needs e~ < thr - m)
 KML_DI double rcp_fast(double d, bool* ok) {
   double x;
+#ifndef KML_HOST_EMULATION
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+#else  // tests/device_math_host.cpp: any start value within the Newton steps' basin gives the same decisions
+  x = (double)(float)(1.0 / d);
+#endif
   double e = __fma_rn(-d, x, 1.0);
   x = __fma_rn(x, e, x);
   e = __fma_rn(-d, x, 1.0);
@@ -324,7 +328,11 @@ KML_DI double rcp_fast(double d, bool* ok) {
 }
 KML_DI double rsqrt_fast(double a, bool* ok) {
   double y;
+#ifndef KML_HOST_EMULATION
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+#else
+  y = (double)(float)(1.0 / sqrt(a));
+#endif
   double e = __fma_rn(-(a * y), y, 1.0);
   y = __fma_rn(0.5 * y, e, y);
   e = __fma_rn(-(a * y), y, 1.0);

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "handle.h"
+#include "bow_merge.h"
 
 using namespace kml;
 
@@ -76,21 +77,10 @@ static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_
 // rebuild the CSR inverted file of a robot (counting sort by word id; rows
 // come out ascending in entry id because entries are visited in order)
 static void rebuild_csr(kml_handle* h, RobotDb* db) {
-  uint32_t W = 0;
-  for (uint32_t w : db->ids) W = std::max(W, w + 1);
-  std::vector<uint32_t> row_ptr((size_t)W + 1, 0);
-  for (uint32_t w : db->ids) row_ptr[w + 1]++;
-  for (uint32_t w = 0; w < W; ++w) row_ptr[w + 1] += row_ptr[w];
-  std::vector<uint2> post(db->ids.size());
-  std::vector<uint32_t> cur(row_ptr.begin(), row_ptr.end() - (W ? 1 : 0));
-  if (W == 0) cur.clear();
-  const uint32_t ne = db->n_entries();
-  for (uint32_t e = 0; e < ne; ++e)
-    for (int64_t k = db->off[e]; k < db->off[e + 1]; ++k) {
-      uint32_t bits;
-      memcpy(&bits, &db->vals[k], 4);
-      post[cur[db->ids[k]]++] = make_uint2(e, bits);
-    }
+  static_assert(sizeof(BowPosting) == sizeof(uint2), "posting layout");
+  std::vector<uint32_t> row_ptr;
+  std::vector<BowPosting> post;
+  const uint32_t W = build_bow_csr(db->off, db->ids, db->vals, db->n_entries(), &row_ptr, &post);
   db->row_ptr.scratch(row_ptr.size());
   db->postings.scratch(std::max<size_t>(post.size(), 1));
   KML_CUDA(cudaMemcpyAsync(db->row_ptr.p, row_ptr.data(), row_ptr.size() * 4,
@@ -143,10 +133,8 @@ static void run_bow(kml_handle* h, const std::vector<RobotDb*>& dbs, int B, cons
     views[i] = db_view(h, dbs[i]);
     max_entries = std::max(max_entries, views[i].n_entries);
   }
-  const int tile_cap = 24576;  // 192 KB of u64 accumulators
-  int tile = (int)std::min<uint32_t>(max_entries, tile_cap);
-  tile = std::max(256, ((tile + 255) / 256) * 256);
-  const int n_tiles = (int)((max_entries + tile - 1) / tile);
+  int tile = 0, n_tiles = 0;
+  bow_tiling(max_entries, &tile, &n_tiles);
   h->d_dbs.scratch(n_db);
   KML_CUDA(cudaMemcpyAsync(h->d_dbs.p, views.data(), sizeof(BowDb) * n_db, cudaMemcpyHostToDevice, h->stream));
   const int32_t* d_maxid = nullptr;
@@ -191,28 +179,8 @@ static void run_bow(kml_handle* h, const std::vector<RobotDb*>& dbs, int B, cons
   h->stats.bow_postings_last = postings;
   for (int b = 0; b < B; ++b) out->nss[b] = h->h_nss.p[b];
   // merge entry tiles (each tile's list is already sorted best-first)
-  std::vector<std::pair<double, uint32_t>> tmp;
-  for (int b = 0; b < B; ++b)
-    for (int d = 0; d < n_db; ++d) {
-      const size_t l0 = ((size_t)b * n_db + d) * n_tiles;
-      uint32_t* oe = &out->entry[((size_t)b * n_db + d) * K];
-      double* os = &out->score[((size_t)b * n_db + d) * K];
-      if (n_tiles == 1) {
-        const int c = h->h_bow_count.p[l0];
-        memcpy(oe, h->h_bow_entry.p + l0 * K, sizeof(uint32_t) * c);
-        memcpy(os, h->h_bow_score.p + l0 * K, sizeof(double) * c);
-        out->count[(size_t)b * n_db + d] = c;
-        continue;
-      }
-      tmp.clear();
-      for (int t = 0; t < n_tiles; ++t)
-        for (int i = 0; i < h->h_bow_count.p[l0 + t]; ++i)
-          tmp.emplace_back(-h->h_bow_score.p[(l0 + t) * K + i], h->h_bow_entry.p[(l0 + t) * K + i]);
-      std::sort(tmp.begin(), tmp.end());  // score desc, entry asc
-      const int c = (int)std::min<size_t>(tmp.size(), K);
-      for (int i = 0; i < c; ++i) { oe[i] = tmp[i].second; os[i] = -tmp[i].first; }
-      out->count[(size_t)b * n_db + d] = c;
-    }
+  merge_bow_tiles(h->h_bow_entry.p, h->h_bow_score.p, h->h_bow_count.p, B, n_db, n_tiles, K,
+                  out->entry.data(), out->score.data(), out->count.data());
 }
 
 // upload one host BoW vector (and optionally a second one) in CSR form

@@ -1,0 +1,198 @@
+// cuda_emu.h — a small SIMT emulator for the CPU test suite (test infrastructure only).
+//
+// Runs a __global__ function of this repo on the host, one CTA at a time, every CUDA thread of
+// the CTA as a cooperative fibre (ucontext) on ONE OS thread: __syncthreads / __syncwarp /
+// shuffles / ballots are rendezvous points at which a fibre yields until its CTA / warp has
+// arrived; between them a fibre runs uninterrupted, so shared-memory atomics are plain
+// read-modify-writes.  __shared__ variables become function statics (one CTA runs at a time),
+// dynamic shared memory is a host buffer.  It models the semantics the kernels rely on
+// (barriers, full-mask warp collectives, atomics), not timing, memory spaces or divergence
+// rules: full-mask collectives must be reached by every live lane of the warp.
+//
+// Use: #include "cuda_emu.h", then #include the .cu file (with KML_HOST_EMULATION defined the
+// kernels' sources skip their launchers and CUDA-runtime helpers), then
+//   kml_emu::launch(grid, block, dyn_smem_bytes, [&] { my_kernel(args); });
+#pragma once
+#include <cuda_runtime.h>  // host-side types only: uint2, dim3, cudaStream_t
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <functional>
+#include <stdexcept>
+#include <vector>
+
+#define KML_HOST_EMULATION 1
+#undef __device__
+#undef __global__
+#undef __shared__
+#undef __host__
+#undef __forceinline__
+#undef __noinline__
+#undef __launch_bounds__
+#define __device__
+#define __global__
+#define __host__
+#define __shared__ static
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+
+namespace kml_emu {
+
+struct Idx3 { unsigned x = 0, y = 0, z = 0; };
+struct State {
+  Idx3 tid, bid, bdim, gdim;       // of the fibre that is running
+  int n = 0, cur = 0;              // threads per CTA, running fibre
+  std::vector<ucontext_t> ctx;
+  std::vector<char> done;
+  std::vector<char*> stacks;
+  ucontext_t sched;
+  int alive = 0, bar_arrived = 0;
+  unsigned bar_gen = 0;
+  int w_alive[32] = {0}, w_arrived[32] = {0};
+  unsigned w_gen[32] = {0};
+  uint64_t xchg[32][32];           // [warp][lane] exchange slots of the warp collectives
+  std::vector<unsigned char> dyn;  // dynamic shared memory of the running CTA
+  const std::function<void()>* body = nullptr;
+};
+inline State& S() { static State s; return s; }
+
+inline void yield_() { State& s = S(); swapcontext(&s.ctx[s.cur], &s.sched); }
+inline void block_barrier() {
+  State& s = S();
+  const unsigned gen = s.bar_gen;
+  if (++s.bar_arrived >= s.alive) { s.bar_arrived = 0; ++s.bar_gen; return; }
+  while (s.bar_gen == gen) yield_();
+}
+inline void warp_barrier() {
+  State& s = S();
+  const int w = s.cur >> 5;
+  const unsigned gen = s.w_gen[w];
+  if (++s.w_arrived[w] >= s.w_alive[w]) { s.w_arrived[w] = 0; ++s.w_gen[w]; return; }
+  while (s.w_gen[w] == gen) yield_();
+}
+template <class T>
+inline T exchange(T v, int src_lane, bool valid) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  State& s = S();
+  const int w = s.cur >> 5, lane = s.cur & 31;
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  s.xchg[w][lane] = bits;
+  warp_barrier();
+  T r = v;
+  if (valid) memcpy(&r, &s.xchg[w][src_lane & 31], sizeof(T));
+  warp_barrier();
+  return r;
+}
+inline void fibre_entry() {
+  State& s = S();
+  (*s.body)();
+  const int t = s.cur;
+  s.done[t] = 1;
+  --s.alive;
+  --s.w_alive[t >> 5];
+  // a thread that leaves releases barriers the rest of its CTA / warp is already waiting at
+  if (s.alive > 0 && s.bar_arrived >= s.alive) { s.bar_arrived = 0; ++s.bar_gen; }
+  const int w = t >> 5;
+  if (s.w_alive[w] > 0 && s.w_arrived[w] >= s.w_alive[w]) { s.w_arrived[w] = 0; ++s.w_gen[w]; }
+  swapcontext(&s.ctx[t], &s.sched);
+}
+
+// Runs body() once per CUDA thread of a grid x block launch (1-D block, 1- or 2-D grid).
+inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::function<void()>& body) {
+  State& s = S();
+  constexpr size_t kStack = 512 * 1024;
+  if (block_threads < 1 || block_threads > 1024) throw std::runtime_error("kml_emu: bad block size");
+  s.n = block_threads;
+  s.ctx.resize(block_threads);
+  s.done.assign(block_threads, 0);
+  while ((int)s.stacks.size() < block_threads) s.stacks.push_back((char*)malloc(kStack));
+  s.dyn.assign(dyn_smem + 16, 0xCD);  // uninitialised on a GPU: poison it
+  s.body = &body;
+  s.bdim.x = block_threads; s.bdim.y = s.bdim.z = 1;
+  s.gdim = grid;
+  if (s.gdim.y == 0) s.gdim.y = 1;
+  s.gdim.z = 1;
+  for (unsigned by = 0; by < s.gdim.y; ++by)
+    for (unsigned bx = 0; bx < s.gdim.x; ++bx) {
+      s.bid.x = bx; s.bid.y = by; s.bid.z = 0;
+      s.alive = block_threads; s.bar_arrived = 0;
+      for (int w = 0; w < 32; ++w) { s.w_arrived[w] = 0; s.w_alive[w] = std::max(0, std::min(32, block_threads - 32 * w)); }
+      std::fill(s.done.begin(), s.done.end(), 0);
+      for (int t = 0; t < block_threads; ++t) {
+        getcontext(&s.ctx[t]);
+        s.ctx[t].uc_stack.ss_sp = s.stacks[t];
+        s.ctx[t].uc_stack.ss_size = kStack;
+        s.ctx[t].uc_link = &s.sched;
+        makecontext(&s.ctx[t], (void (*)())fibre_entry, 0);
+      }
+      int guard = 0;
+      while (s.alive > 0) {
+        const int before = s.alive;
+        const unsigned g0 = s.bar_gen;
+        for (int t = 0; t < block_threads; ++t) {
+          if (s.done[t]) continue;
+          s.cur = t;
+          s.tid.x = t; s.tid.y = s.tid.z = 0;
+          swapcontext(&s.sched, &s.ctx[t]);
+        }
+        // every pass must retire a thread or pass a barrier eventually; 1e6 idle passes = deadlock
+        guard = (s.alive == before && s.bar_gen == g0) ? guard + 1 : 0;
+        if (guard > 1000000) throw std::runtime_error("kml_emu: CTA deadlocked at a barrier");
+      }
+    }
+}
+inline unsigned char* dynamic_smem() {
+  State& s = S();
+  return (unsigned char*)(((uintptr_t)s.dyn.data() + 15) & ~(uintptr_t)15);
+}
+
+}  // namespace kml_emu
+
+#define threadIdx (kml_emu::S().tid)
+#define blockIdx (kml_emu::S().bid)
+#define blockDim (kml_emu::S().bdim)
+#define gridDim (kml_emu::S().gdim)
+
+static inline void __syncthreads() { kml_emu::block_barrier(); }
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { kml_emu::warp_barrier(); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return kml_emu::exchange(v, src, true); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
+  return kml_emu::exchange(v, (kml_emu::S().cur & 31) ^ m, true);
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = kml_emu::S().cur & 31;
+  return kml_emu::exchange(v, lane - d, lane - d >= 0);
+}
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
+  const int lane = kml_emu::S().cur & 31;
+  return kml_emu::exchange(v, lane + d, lane + d < 32);
+}
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+  kml_emu::State& s = kml_emu::S();
+  const int w = s.cur >> 5, lane = s.cur & 31;
+  s.xchg[w][lane] = pred ? 1u : 0u;
+  kml_emu::warp_barrier();
+  unsigned r = 0;
+  for (int l = 0; l < s.w_alive[w] && l < 32; ++l) r |= (unsigned)(s.xchg[w][l] & 1u) << l;
+  kml_emu::warp_barrier();
+  return r;
+}
+template <class T, class V> static inline T atomicAdd(T* p, V v) { const T old = *p; *p = (T)(old + (T)v); return old; }
+template <class T, class V> static inline T atomicMin(T* p, V v) { const T old = *p; if ((T)v < old) *p = (T)v; return old; }
+template <class T, class V> static inline T atomicMax(T* p, V v) { const T old = *p; if ((T)v > old) *p = (T)v; return old; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+using std::max;
+using std::min;

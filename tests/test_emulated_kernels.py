@@ -1,0 +1,167 @@
+"""CUDA kernels of libkml run on the CPU: tests/emu/cuda_emu.h executes a __global__ function of
+this repo — the source nvcc compiles, not a restatement — one CTA at a time with every CUDA thread
+as a cooperative fibre (barriers, full-mask shuffles / ballots, shared-memory atomics), behind
+the product's own host code for that kernel.  No GPU needed: this is where a change to a kernel's
+logic fails first.  It models semantics, not timing or the memory system; the GPU tests remain
+the parity tests proper.
+
+Covered here: bow_score_kernel + the CSR build, tiling and tile merge of csrc/bow_merge.h,
+including databases wider than one accumulator tile (BASELINE.json configs[4], 50 000 keyframes
+per database), which no GPU run of round 1 reached."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BOW_RTOL = 1e-6
+
+
+def _P(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+@pytest.fixture(scope="module")
+def bowemu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libbowemu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
+                    "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
+                    "-I", os.path.join(ROOT, "tests", "emu"),
+                    os.path.join(ROOT, "tests", "emu", "bow_emu.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.bowemu_db_create.restype = C.c_void_p
+    return lib
+
+
+class EmuDb:
+    def __init__(self, lib):
+        self.lib, self.h = lib, C.c_void_p(lib.bowemu_db_create())
+
+    def add_bulk(self, off, ids, vals):
+        off, ids = np.ascontiguousarray(off, np.int64), np.ascontiguousarray(ids, np.uint32)
+        vals = np.ascontiguousarray(vals, np.float32)
+        self.lib.bowemu_db_add(self.h, len(off) - 1, _P(off, C.c_int64), _P(ids, C.c_uint32), _P(vals, C.c_float))
+
+    def close(self):
+        self.lib.bowemu_db_destroy(self.h)
+
+
+def _csr(vecs):
+    off = np.zeros(len(vecs) + 1, np.int64)
+    off[1:] = np.cumsum([len(v[0]) for v in vecs])
+    ids = np.concatenate([v[0] for v in vecs] + [np.zeros(0, np.uint32)]).astype(np.uint32)
+    vals = np.concatenate([v[1] for v in vecs] + [np.zeros(0, np.float32)]).astype(np.float32)
+    return off, ids, vals
+
+
+def emu_query(lib, dbs, queries, K, max_id=None, prev=None, tile_cap=0):
+    """run_bow (lcd.cu) with the kernel emulated: returns entries [B][n_db][K], scores, counts, nss, tiles."""
+    B, n_db = len(queries), len(dbs)
+    off, ids, vals = _csr(queries)
+    arr = (C.c_void_p * n_db)(*[d.h for d in dbs])
+    oe, osc = np.zeros((B, n_db, K), np.uint32), np.zeros((B, n_db, K))
+    oc, nss = np.zeros((B, n_db), np.int32), np.zeros(B)
+    mid = None if max_id is None else np.ascontiguousarray(max_id, np.int32)
+    pa = (None, None, None)
+    if prev is not None:
+        poff, pids, pvals = _csr(prev)
+        pa = (_P(poff, C.c_int64), _P(pids, C.c_uint32), _P(pvals, C.c_float))
+    touched = C.c_ulonglong(0)
+    nt = lib.bowemu_query(arr, n_db, B, _P(off, C.c_int64), _P(ids, C.c_uint32), _P(vals, C.c_float), *pa, K,
+                          None if mid is None else _P(mid, C.c_int32), tile_cap, _P(oe, C.c_uint32),
+                          _P(osc, C.c_double), _P(oc, C.c_int32), _P(nss, C.c_double), C.byref(touched))
+    return oe, osc, oc, nss, nt, touched.value
+
+
+def _check_against_oracle(db, qi, qv, K, max_id, e1, s1):
+    from test_gpu_parity import _same_order_modulo_ties
+    e0, s0 = db.query(qi, qv, K, max_id)
+    assert len(e0) == len(e1), (len(e0), len(e1))
+    np.testing.assert_allclose(s1, s0, rtol=BOW_RTOL, atol=0)
+    assert _same_order_modulo_ties(e0, s0, e1, s1)
+    return len(e0)
+
+
+def test_bow_kernel_database_spanning_several_entry_tiles(oracle, bowemu):
+    """The scenario of tests/test_wide_database.py (one database of 60 000 entries = three
+    24 576-entry tiles, exact duplicates on both sides of every tile boundary, max_id cuts inside
+    the first and the last tile) through the emulated kernel and the product's tile merge."""
+    rng = np.random.default_rng(77)
+    n, words, vocab = 60000, 40, 3000
+    base = rng.integers(0, vocab // words, (n, words))
+    ids = (np.arange(words)[None, :] * (vocab // words) + base).astype(np.uint32)
+    vals = rng.random((n, words)).astype(np.float32) + np.float32(0.01)
+    vals = (vals / vals.sum(axis=1, keepdims=True)).astype(np.float32)
+    dup = [5, 24575, 24576, 49151, 49152, 59999]
+    for e in dup[1:]:
+        ids[e], vals[e] = ids[dup[0]], vals[dup[0]]
+    det = EmuDb(bowemu)
+    det.add_bulk(np.arange(n + 1) * words, ids.reshape(-1), vals.reshape(-1))
+    db = oracle.Database()
+    for i in range(n):
+        db.add(ids[i], vals[i])
+    queries = [(ids[dup[0]], vals[dup[0]])]
+    for k in range(3):
+        qv = rng.random(words).astype(np.float32)
+        queries.append((ids[1000 + 19000 * k].copy(), (qv / qv.sum()).astype(np.float32)))
+    for K, max_id in [(50, -1), (128, -1), (1, -1), (50, 30000), (50, 100), (50, 59000)]:
+        oe, osc, oc, _, nt, touched = emu_query(bowemu, [det], queries, K, [max_id])
+        assert nt == 3
+        assert touched == sum(int(np.isin(ids, q[0]).sum()) for q in queries)   # algorithmic postings, counted once
+        for b, (qi, qv) in enumerate(queries):
+            c = oc[b, 0]
+            assert _check_against_oracle(db, qi, qv, K, max_id, oe[b, 0, :c], osc[b, 0, :c]) > 0
+    oe, osc, oc, _, _, _ = emu_query(bowemu, [det], queries[:1], 50, [-1])
+    assert list(oe[0, 0, :len(dup)]) == dup and np.all(np.abs(osc[0, 0, :len(dup)] - 1.0) < 1e-6)
+    det.close()
+
+
+def test_bow_kernel_ragged_databases_small_tiles_and_nss(oracle, bowemu):
+    """Several databases of different sizes in one launch (empty, smaller than a tile, many tiles —
+    the tile is shrunk to 256 entries), per-database max_id, the NSS factor of the batch, empty
+    and 1 024-word query vectors; single-tile launch of the same data for comparison."""
+    rng = np.random.default_rng(3)
+    vocab = 5000
+
+    def vec(nw):
+        i = np.sort(rng.choice(vocab, nw, replace=False)).astype(np.uint32)
+        v = rng.random(nw).astype(np.float32) + np.float32(1e-3)
+        return i, (v / v.sum()).astype(np.float32)
+
+    sizes = [0, 100, 700, 1500]
+    dbs, refs = [], []
+    for n in sizes:
+        d, r = EmuDb(bowemu), oracle.Database()
+        vecs = [vec(int(rng.integers(1, 60))) for _ in range(n)]
+        if n:
+            d.add_bulk(*_csr(vecs))
+        for v in vecs:
+            r.add(*v)
+        dbs.append(d)
+        refs.append(r)
+    queries = [vec(50), vec(1024), (np.zeros(0, np.uint32), np.zeros(0, np.float32)), vec(1), vec(300)]
+    prev = [vec(40), queries[1], vec(10), (np.zeros(0, np.uint32), np.zeros(0, np.float32)), vec(300)]
+    prev[4] = (queries[4][0].copy(), prev[4][1])                      # same words, other weights
+    max_id = [-1, 37, 650, -1]
+    for K in (50, 7):
+        outs = []
+        for tile_cap in (256, 0):
+            oe, osc, oc, nss, nt, _ = emu_query(bowemu, dbs, queries, K, max_id, prev, tile_cap)
+            assert nt == (6 if tile_cap else 1)
+            outs.append((oe.copy(), osc.copy(), oc.copy(), nss.copy()))
+            for b, (qi, qv) in enumerate(queries):
+                assert nss[b] == pytest.approx(oracle.bow_score(qi, qv, *prev[b]), rel=BOW_RTOL, abs=0)
+                for d in range(len(dbs)):
+                    c = oc[b, d]
+                    if sizes[d] == 0 or len(qi) == 0:
+                        assert c == 0
+                        continue
+                    _check_against_oracle(refs[d], qi, qv, K, max_id[d], oe[b, d, :c], osc[b, d, :c])
+        # fixed-point accumulation: the tiled and the single-tile launch agree bit for bit
+        for x, y in zip(outs[0], outs[1]):
+            assert np.array_equal(x, y)
+    assert outs[0][3][1] == pytest.approx(1.0, abs=1e-6)              # a vector against itself
+    for d in dbs:
+        d.close()

@@ -15,7 +15,9 @@
 // which is BFMatcher's observed order (distance asc, trainIdx asc).
 // Bound: POPC pipe (8 POPC32 per compare algorithmically, 5 executed after a carry-save
 // reduction on the LOP3 pipe), see DESIGN.md §5.2.
+#ifndef KML_HOST_EMULATION  // tests/emu/: the kernels below are also run on the host by the CPU suite
 #include "common.cuh"
+#endif
 #include "kernels.h"
 
 namespace kml {
@@ -28,14 +30,22 @@ constexpr int kHamTile = 512;  // train descriptors per shared-memory stage
 //             key = dist << 18 | idx) — what upstream's cv::DescriptorMatcher::create(3) selects
 //             (/root/reference/docker/copy/kimera_multi_lcd.patch:34-35).
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef KML_HOST_EMULATION
+  return a ^ b ^ c;
+#else
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
+#endif
 }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef KML_HOST_EMULATION
+  return (a & b) | (a & c) | (b & c);
+#else
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
+#endif
 }
 
 template <bool L1>
@@ -206,6 +216,7 @@ __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __res
   if (threadIdx.x == 0) M[p] = base_s;
 }
 
+#ifndef KML_HOST_EMULATION
 void launch_hamming_jobs(const HamJob* d_jobs, int njobs, int norm, cudaStream_t s) {
   if (njobs <= 0) return;
   if (norm == 1) hamming_knn2_kernel<true><<<njobs, kHamThreads, 0, s>>>(d_jobs);
@@ -297,5 +308,7 @@ double measure_fp64_peak(cudaStream_t s) {
   cudaFree(d);
   return best;
 }
+
+#endif  // KML_HOST_EMULATION
 
 }  // namespace kml

@@ -194,5 +194,51 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline unsigned __vsadu4(unsigned a, unsigned b) {  // sum of absolute differences of the four bytes
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int x = (a >> (8 * i)) & 255, y = (b >> (8 * i)) & 255;
+    r += (unsigned)(x > y ? x - y : y - x);
+  }
+  return r;
+}
 using std::max;
 using std::min;
+
+// ---- mbarrier + bulk copy (common.cuh), modelled in the 64-bit barrier word: pending
+// transaction bytes, pending arrivals, the arrival count it is re-armed with, phase parity.
+namespace kml {
+struct EmuMbar { uint32_t tx; uint16_t pending; uint8_t count, phase; };
+static_assert(sizeof(EmuMbar) == 8, "mbarrier word");
+inline void emu_mbar_try_complete(EmuMbar* b) {
+  if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->count; }
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->tx = 0; b->pending = (uint16_t)count; b->count = (uint8_t)count; b->phase = 0;
+}
+inline void fence_mbar_init() {}
+// arrive + expect: the phase cannot complete before `bytes` have landed
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  if (b->pending == 0) throw std::runtime_error("kml_emu: mbarrier arrival beyond its count");
+  b->tx += bytes;
+  b->pending--;
+}
+// the copy is performed at once (an early read is not caught); a wait on the wrong parity, a
+// byte count that does not match the expectation or a misaligned copy is
+inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  if ((bytes & 15u) || ((uintptr_t)dst_smem & 15u) || ((uintptr_t)src_gmem & 15u))
+    throw std::runtime_error("kml_emu: cp.async.bulk needs 16-byte aligned addresses and size");
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  if (b->tx < bytes) throw std::runtime_error("kml_emu: bulk copy larger than the expected transaction bytes");
+  memcpy(dst_smem, src_gmem, bytes);
+  b->tx -= bytes;
+  emu_mbar_try_complete(b);
+}
+// returns once the phase with parity `parity` has completed
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  while ((uint32_t)(b->phase & 1) == (parity & 1u)) kml_emu::yield_();
+}
+}  // namespace kml

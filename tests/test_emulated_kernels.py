@@ -165,3 +165,87 @@ def test_bow_kernel_ragged_databases_small_tiles_and_nss(oracle, bowemu):
     assert outs[0][3][1] == pytest.approx(1.0, abs=1e-6)              # a vector against itself
     for d in dbs:
         d.close()
+
+
+# ---------------------------------------------------------------------------------- matcher
+@pytest.fixture(scope="module")
+def hamemu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libhamemu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
+                    "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
+                    "-I", os.path.join(ROOT, "tests", "emu"),
+                    os.path.join(ROOT, "tests", "emu", "hamming_emu.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+def emu_knn2(lib, q, t, norm=0, range_len=1 << 20):
+    q, t = np.ascontiguousarray(q, np.uint8).reshape(-1, 32), np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx, dist = np.zeros((len(q), 2), np.uint32), np.zeros((len(q), 2), np.uint16)
+    lib.hamemu_knn2(_P(q, C.c_uint8), len(q), _P(t, C.c_uint8), len(t), norm, range_len,
+                    _P(idx, C.c_uint32), _P(dist, C.c_uint16))
+    return idx, dist
+
+
+def emu_match_lowe(lib, q, t, lowe, norm=0):
+    """q: [P][nq][32], t: [P][nt][32] -> list of (iq, im) per pair"""
+    q, t = np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(t, np.uint8)
+    Pn, nq, nt = q.shape[0], q.shape[1], t.shape[1]
+    iq, im = np.zeros((Pn, max(nq, 1)), np.uint16), np.zeros((Pn, max(nq, 1)), np.uint16)
+    M = np.zeros(Pn, np.int32)
+    lib.hamemu_match_lowe(_P(q, C.c_uint8), nq, _P(t, C.c_uint8), nt, Pn, norm, C.c_double(lowe),
+                          _P(iq, C.c_uint16), _P(im, C.c_uint16), _P(M, C.c_int32))
+    return [(iq[p, :M[p]].astype(np.uint32), im[p, :M[p]].astype(np.uint32)) for p in range(Pn)]
+
+
+def test_matcher_kernels_against_the_bfmatcher_golden_vectors(hamemu):
+    """hamming_knn2_kernel (Hamming and byte-wise L1) + knn2_reduce_kernel + lowe_compact_kernel,
+    emulated, against the fixture OpenCV's BFMatcher wrote (tests/golden): the same vectors the
+    GPU test holds the compiled kernels to."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    for range_len in (1 << 20, 64):                 # one CTA, and many ranges merged by the reduce kernel
+        idx, dist = emu_knn2(hamemu, G["knn_q"], G["knn_t"], 0, range_len)
+        assert np.array_equal(idx, G["ham_idx"]) and np.array_equal(dist, G["ham_dist"])
+        idx, dist = emu_knn2(hamemu, G["knn_q"], G["knn_t"], 1, range_len)
+        assert np.array_equal(idx, G["l1_idx"]) and np.array_equal(dist, G["l1_dist"])
+    (iq, im), = emu_match_lowe(hamemu, G["knn_q"][None], G["knn_t"][None], 0.8)
+    assert np.array_equal(np.c_[iq, im], G["lowe08_pairs"])
+
+
+def test_matcher_kernels_edge_cases_against_the_oracle(oracle, hamemu):
+    """Sizes around the kernel's tiling (512 queries per pass, 512-descriptor TMA stages, the 4-way
+    unrolled inner loop), duplicates and exact hits (ties -> lowest train index), k > nTrain, an
+    empty train set, and the Lowe compaction over several 256-query passes for several pairs."""
+    rng = np.random.default_rng(12)
+    for nq, nt in [(1, 1), (3, 2), (5, 7), (500, 500), (513, 511), (37, 1030), (1025, 3), (4, 0), (0, 5)]:
+        q = rng.integers(0, 256, (nq, 32), np.uint8)
+        t = rng.integers(0, 256, (nt, 32), np.uint8)
+        if nt >= 6 and nq:
+            t[4] = t[1]; t[5] = t[1]; q[0] = t[1]
+        for norm, ref in ((0, oracle.hamming_knn2), (1, oracle.l1_knn2)):
+            if nq == 0:
+                emu_knn2(hamemu, q, t, norm)          # nothing to do, must not hang
+                continue
+            i0, d0 = ref(q, t)
+            for range_len in (1 << 20, 200):
+                i1, d1 = emu_knn2(hamemu, q, t, norm, range_len)
+                assert np.array_equal(i0, i1) and np.array_equal(d0, d1), (nq, nt, norm, range_len)
+    # Lowe + compaction: related frames so that a good share of the queries survive
+    Pn, nq, nt = 3, 700, 650
+    t = rng.integers(0, 256, (Pn, nt, 32), np.uint8)
+    q = rng.integers(0, 256, (Pn, nq, 32), np.uint8)
+    for p in range(Pn):
+        sel = rng.permutation(nq)[:400]
+        src = rng.integers(0, nt, 400)
+        q[p, sel] = t[p, src] ^ (rng.random((400, 32)) < 0.03).astype(np.uint8)   # a few flipped bits
+    for norm in (0, 1):
+        for lowe in (0.9, 0.5):
+            got = emu_match_lowe(hamemu, q, t, lowe, norm)
+            for p in range(Pn):
+                if norm == 0:
+                    iq0, im0 = oracle.match_lowe(q[p], t[p], lowe)
+                else:                                   # the oracle's Lowe helper is Hamming: restate it on l1_knn2
+                    i0, d0 = oracle.l1_knn2(q[p], t[p])
+                    keep = d0[:, 0].astype(np.float64) < lowe * d0[:, 1].astype(np.float64)
+                    iq0, im0 = np.nonzero(keep)[0], i0[keep, 0]
+                assert len(iq0) > 100
+                assert np.array_equal(got[p][0], iq0) and np.array_equal(got[p][1], im0), (norm, lowe, p)

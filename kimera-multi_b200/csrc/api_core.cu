@@ -4,6 +4,7 @@
 #include <random>
 
 #include "handle.h"
+#include "sac_host.h"
 
 using namespace kml;
 
@@ -112,10 +113,7 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
     for (auto& e2 : h->ev) KML_CUDA(cudaEventCreate(&e2));
     // pre-drawn sample stream: mt19937(seed)() >> 1  
     const int max_it = std::max(h->prm.max_ransac_iterations_mono, h->prm.max_ransac_iterations);
-    const size_t draws = (size_t)max_it + 1 + 256;
-    h->sh->raw_h.resize(draws * 8);
-    std::mt19937 mt(h->prm.ransac_seed);
-    for (auto& r : h->sh->raw_h) r = (uint32_t)mt() >> 1;
+    fill_raw_stream((uint32_t)h->prm.ransac_seed, max_it, &h->sh->raw_h);
     h->sh->d_raw.scratch(h->sh->raw_h.size());
     KML_CUDA(cudaMemcpy(h->sh->d_raw.p, h->sh->raw_h.data(), h->sh->raw_h.size() * 4, cudaMemcpyHostToDevice));
     *out = h;

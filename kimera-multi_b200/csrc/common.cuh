@@ -26,6 +26,17 @@ struct CudaError : std::runtime_error {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Kernel launch and dynamic shared memory as macros, so that the CPU test suite can compile the
+// same .cu text for the host and run the kernels under tests/emu/cuda_emu.h (which defines its own
+// versions and KML_HOST_EMULATION).  A kernel name is passed in parentheses (template arguments
+// may contain commas):  KML_LAUNCH((k<8, 64>), grid, block, smem, stream, args...);
+#ifndef KML_HOST_EMULATION
+#define KML_UNPAREN(...) __VA_ARGS__
+#define KML_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  KML_UNPAREN kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define KML_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
+
 // growable device buffer (doubling); contents preserved on growth
 template <class T>
 struct DevBuf {

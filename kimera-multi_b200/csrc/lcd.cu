@@ -14,6 +14,7 @@
 
 #include "handle.h"
 #include "bow_merge.h"
+#include "sac_host.h"
 
 using namespace kml;
 
@@ -298,16 +299,8 @@ static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob,
   const int need = Nmax + 1;
   if (*cur_n >= need) return;
   int n1 = std::max(need, 512);
-  std::vector<double> tab((size_t)n1 * n1, 1.0);
-  const double lnum = std::log(1.0 - prob);
-  for (int N = 1; N < n1; ++N)
-    for (int n = 0; n <= N; ++n) {
-      double w = (double)n / (double)N;
-      double p_no = 1.0 - std::pow(w, (double)sample_size);
-      p_no = std::max(DBL_EPSILON, p_no);
-      p_no = std::min(1.0 - DBL_EPSILON, p_no);
-      tab[(size_t)N * n1 + n] = lnum / std::log(p_no);
-    }
+  std::vector<double> tab;
+  fill_ktable(n1, sample_size, prob, &tab);
   if (buf->p) {  // another lane's kernels may still read the old table: retire it instead of freeing
     h->sh->retired.push_back(buf->p);
     buf->p = nullptr;
@@ -317,15 +310,6 @@ static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob,
   KML_CUDA(cudaMemcpyAsync(buf->p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
   *cur_n = n1;
-}
-
-static double sq_crit_of(double thr) {
-  // smallest double s with sqrt(s) >= thr  =>  (sqrt(d2) < thr) == (d2 < s)
-  if (!(thr > 0.0)) return 0.0;
-  double s = thr * thr;
-  while (std::sqrt(s) >= thr) s = std::nextafter(s, 0.0);
-  while (std::sqrt(s) < thr) s = std::nextafter(s, INFINITY);
-  return s;
 }
 
 struct SacBufs {
@@ -351,7 +335,7 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   else
     ensure_ktable(h, stride, 3, prm.ransac_probability, &h->sh->d_ktable_stereo, &h->sh->ktable_n_stereo);
   const int raw_len = (int)h->sh->raw_h.size();
-  const int cap_draws = std::min(raw_len / S, max_it + 1 + 256);
+  const int cap_draws = sac_cap_draws(raw_len, S, max_it);
   {  // the doubling round schedule must cover cap_draws with at most kRoundCap new draws per round
     int cum = 0;
     for (int r = 0; r + 1 < kSacRounds; ++r) cum += std::min(sac_round_draws(r, chunk), kRoundCap);

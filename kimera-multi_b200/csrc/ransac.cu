@@ -86,7 +86,7 @@ __host__ __device__ inline size_t sac_warp_smem(int stride) {
 
 template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
-  extern __shared__ __align__(16) uint16_t perm_s[];
+  KML_DYN_SMEM(uint16_t, perm_s);
   const int p = blockIdx.x;
   const int lane = threadIdx.x;
   const int N = a.N[p];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
 // known exactly (up to skipped samples): the next round covers all of them.
 template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
-  extern __shared__ __align__(16) uint16_t perm_s[];
+  KML_DYN_SMEM(uint16_t, perm_s);
   const int p = blockIdx.x;
   const int lane = threadIdx.x;
   SacState* st = &a.st[p];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 //                        beat the best count of the draws before it.
 //   sac_replay_kernel    lane 0 per problem replays Ransac::computeModel.
 __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+  KML_DYN_SMEM(double, smem_d);
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
 }
 
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+  KML_DYN_SMEM(double, smem_d);
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
 // separate the roots, ~8 % of the chains): compacted work list, one (draw, chain, root)
 // bisection per thread.
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+  KML_DYN_SMEM(double, smem_d);
   const unsigned n = *a.fb_count;
   for (unsigned it = blockIdx.x * kMonoChunk + threadIdx.x; it < n; it += gridDim.x * kMonoChunk) {
     const uint32_t item = a.fb_list[it];
@@ -349,7 +349,7 @@ constexpr int kCountThreads = 256;
 constexpr int kCountWarps = kCountThreads / 32;
 template <bool STAGED>  // STAGED: the problem's bearings fit in shared memory (else read through L1)
 __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+  KML_DYN_SMEM(double, smem_d);
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a)
 // ---------------------------------------------------------- stereo chunk
 template <bool STAGED>  // STAGED: the problem's point pairs fit in shared memory (else read through L1)
 __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a) {
-  extern __shared__ __align__(16) double smem_d[];
+  KML_DYN_SMEM(double, smem_d);
   const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
@@ -703,11 +703,11 @@ void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (sample_size == 8) {
     ensure_smem(sac_init_kernel<8, kMonoChunk>, sm);
     ensure_smem(sac_replay_kernel<8, kMonoChunk>, sm);
-    sac_init_kernel<8, kMonoChunk><<<a.P, 32, sm, s>>>(a);
+    KML_LAUNCH((sac_init_kernel<8, kMonoChunk>), a.P, 32, sm, s, a);
   } else {
     ensure_smem(sac_init_kernel<3, kStereoChunk>, sm);
     ensure_smem(sac_replay_kernel<3, kStereoChunk>, sm);
-    sac_init_kernel<3, kStereoChunk><<<a.P, 32, sm, s>>>(a);
+    KML_LAUNCH((sac_init_kernel<3, kStereoChunk>), a.P, 32, sm, s, a);
   }
 }
 
@@ -718,22 +718,22 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   ensure_smem(mono_front_kernel, sm);
   const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
-  mono_front_kernel<<<dim3(a.P, blocks), kMonoChunk, sm, s>>>(a);
+  KML_LAUNCH((mono_front_kernel), dim3(a.P, blocks), kMonoChunk, sm, s, a);
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
-  mono_isolate_kernel<<<dim3(a.P, blocks), kMonoChunk, 0, s>>>(a);
-  mono_isolate_deferred_kernel<<<kNumSMs * 4, kMonoChunk, sm2, s>>>(a);
-  mono_item_kernel<<<kNumSMs * 16, kItemThreads, 0, s>>>(a);
+  KML_LAUNCH((mono_isolate_kernel), dim3(a.P, blocks), kMonoChunk, 0, s, a);
+  KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, sm2, s, a);
+  KML_LAUNCH((mono_item_kernel), kNumSMs * 16, kItemThreads, 0, s, a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);
   if (sm4 <= 96 * 1024) {
     ensure_smem(mono_count_kernel<true>, sm4);
-    mono_count_kernel<true><<<dim3(a.P, blocks), kCountThreads, sm4, s>>>(a);
+    KML_LAUNCH((mono_count_kernel<true>), dim3(a.P, blocks), kCountThreads, sm4, s, a);
   } else {
-    mono_count_kernel<false><<<dim3(a.P, blocks), kCountThreads, 0, s>>>(a);
+    KML_LAUNCH((mono_count_kernel<false>), dim3(a.P, blocks), kCountThreads, 0, s, a);
   }
 #ifdef KML_FILTER_STATS
   if (round == kSacRounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
 #endif
-  sac_replay_kernel<8, kMonoChunk><<<a.P, 32, sac_warp_smem<8>(a.stride), s>>>(a, round);
+  KML_LAUNCH((sac_replay_kernel<8, kMonoChunk>), a.P, 32, sac_warp_smem<8>(a.stride), s, a, round);
   return 6;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
@@ -743,36 +743,36 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   if (sm <= 96 * 1024) {
     ensure_smem(stereo_chunk_kernel<true>, sm);
-    stereo_chunk_kernel<true><<<dim3(a.P, blocks), kStereoThreads, sm, s>>>(a);
+    KML_LAUNCH((stereo_chunk_kernel<true>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
   } else {
-    stereo_chunk_kernel<false><<<dim3(a.P, blocks), kStereoThreads, sizeof(double) * 12 * kStereoChunk, s>>>(a);
+    KML_LAUNCH((stereo_chunk_kernel<false>), dim3(a.P, blocks), kStereoThreads, sizeof(double) * 12 * kStereoChunk, s, a);
   }
-  sac_replay_kernel<3, kStereoChunk><<<a.P, 32, sac_warp_smem<3>(a.stride), s>>>(a, round);
+  KML_LAUNCH((sac_replay_kernel<3, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
   return 2;
 }
 void launch_mono_select(const SacArgs& a, cudaStream_t s) {
   if (a.P <= 0) return;
-  sac_select_kernel<true><<<a.P, 128, 0, s>>>(a);
+  KML_LAUNCH((sac_select_kernel<true>), a.P, 128, 0, s, a);
 }
 void launch_stereo_select(const SacArgs& a, cudaStream_t s) {
   if (a.P <= 0) return;
-  sac_select_kernel<false><<<a.P, 128, 0, s>>>(a);
+  KML_LAUNCH((sac_select_kernel<false>), a.P, 128, 0, s, a);
 }
 void launch_gather_bearings(const GatherArgs& g, cudaStream_t s) {
   if (g.P <= 0) return;
-  gather_bearings_kernel<<<g.P, 128, 0, s>>>(g);
+  KML_LAUNCH((gather_bearings_kernel), g.P, 128, 0, s, g);
 }
 void launch_gather_points(const StereoGatherArgs& g, cudaStream_t s) {
   if (g.g.P <= 0) return;
-  gather_points_kernel<<<g.g.P, 128, 0, s>>>(g);
+  KML_LAUNCH((gather_points_kernel), g.g.P, 128, 0, s, g);
 }
 void launch_mono_gate(const FinalizeArgs& f, cudaStream_t s) {
   if (f.P <= 0) return;
-  mono_gate_kernel<<<(f.P + 127) / 128, 128, 0, s>>>(f);
+  KML_LAUNCH((mono_gate_kernel), (f.P + 127) / 128, 128, 0, s, f);
 }
 void launch_finalize(const FinalizeArgs& f, cudaStream_t s) {
   if (f.P <= 0) return;
-  finalize_kernel<<<(f.P + 127) / 128, 128, 0, s>>>(f);
+  KML_LAUNCH((finalize_kernel), (f.P + 127) / 128, 128, 0, s, f);
 }
 
 }  // namespace kml

@@ -154,6 +154,18 @@ inline unsigned char* dynamic_smem() {
 
 }  // namespace kml_emu
 
+// launch + dynamic shared memory macros of csrc/common.cuh, emulated
+namespace kml_emu {
+inline Idx3 idx3(int x) { Idx3 r; r.x = (unsigned)x; r.y = 1; return r; }
+inline Idx3 idx3(unsigned x) { Idx3 r; r.x = x; r.y = 1; return r; }
+inline Idx3 idx3(const dim3& d) { Idx3 r; r.x = d.x; r.y = d.y; return r; }
+}  // namespace kml_emu
+template <class K> inline cudaError_t cudaFuncSetAttribute(K*, cudaFuncAttribute, int) { return cudaSuccess; }
+#define KML_UNPAREN(...) __VA_ARGS__
+#define KML_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kml_emu::launch(kml_emu::idx3(grid), (int)(block), (size_t)(smem), [&] { KML_UNPAREN kernel(__VA_ARGS__); })
+#define KML_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(kml_emu::dynamic_smem())
+
 #define threadIdx (kml_emu::S().tid)
 #define blockIdx (kml_emu::S().bid)
 #define blockDim (kml_emu::S().bdim)
@@ -183,6 +195,12 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   kml_emu::warp_barrier();
   return r;
 }
+static inline int __all_sync(unsigned m, bool pred) {
+  const unsigned b = __ballot_sync(m, pred);
+  const int n = kml_emu::S().w_alive[kml_emu::S().cur >> 5];
+  return b == (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+}
+static inline int __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
 template <class T, class V> static inline T atomicAdd(T* p, V v) { const T old = *p; *p = (T)(old + (T)v); return old; }
 template <class T, class V> static inline T atomicMin(T* p, V v) { const T old = *p; if ((T)v < old) *p = (T)v; return old; }
 template <class T, class V> static inline T atomicMax(T* p, V v) { const T old = *p; if ((T)v > old) *p = (T)v; return old; }

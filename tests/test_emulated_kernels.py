@@ -249,3 +249,111 @@ def test_matcher_kernels_edge_cases_against_the_oracle(oracle, hamemu):
                     iq0, im0 = np.nonzero(keep)[0], i0[keep, 0]
                 assert len(iq0) > 100
                 assert np.array_equal(got[p][0], iq0) and np.array_equal(got[p][1], im0), (norm, lowe, p)
+
+
+# ----------------------------------------------------------------------------------- RANSAC
+@pytest.fixture(scope="module")
+def ransacemu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libransacemu.so")
+    # -ffp-contract=off: the host equivalent of the -fmad=false ransac.cu is compiled with
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-Wall",
+                    "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-attributes",
+                    "-I/usr/local/cuda/include", "-I", os.path.join(ROOT, "tests", "emu"),
+                    os.path.join(ROOT, "tests", "emu", "ransac_emu.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+def emu_ransac(lib, mono, a, b, thr, prob=0.995, max_it=1000, seed=12345, full=False, force_generic=False):
+    """kml_ransac_nister_batch / kml_ransac_arun_batch with every kernel emulated; a, b: [P][N][3]."""
+    a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+    Pn, N = a.shape[0], a.shape[1]
+    models = np.zeros((Pn, 12))
+    ninl, it, bd = np.zeros(Pn, np.int32), np.zeros(Pn, np.int32), np.zeros(Pn, np.int32)
+    mask = np.zeros((Pn, max((N + 31) // 32, 1)), np.uint32)
+    rc = lib.ransacemu_batch(int(mono), Pn, N, _P(a, C.c_double), _P(b, C.c_double), C.c_double(thr),
+                             C.c_double(prob), max_it, C.c_uint32(seed), int(full), int(force_generic),
+                             _P(models, C.c_double), _P(ninl, C.c_int32), _P(it, C.c_int32), _P(bd, C.c_int32),
+                             _P(mask, C.c_uint32))
+    assert rc == 0
+    return dict(models=models, n_inliers=ninl, iterations=it, best_draw=bd, mask=mask)
+
+
+def _mask_to_indices(m, N):
+    return np.nonzero(np.unpackbits(m.view(np.uint8), bitorder="little")[:N])[0]
+
+
+def _same_as_oracle(o, g, p, N, tag):
+    assert o["iterations"] == g["iterations"][p], tag
+    assert o["best_draw"] == g["best_draw"][p], tag
+    assert o["n_inliers"] == g["n_inliers"][p], tag
+    assert np.array_equal(o["inliers"], _mask_to_indices(g["mask"][p], N)), tag
+    if o["best_draw"] >= 0:
+        assert np.array_equal(o["model"].ravel(), g["models"][p]), tag      # all 12 entries, bit for bit
+
+
+def _scene(rng, N, outlier_rate):
+    from scipy.spatial.transform import Rotation as Rot
+    X = np.c_[rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(2, 12, N)]
+    R = Rot.from_rotvec(rng.normal(size=3) * 0.2).as_matrix()
+    t = rng.uniform(-1, 1, 3)
+    X2 = (X - t) @ R + rng.normal(size=X.shape) * 0.02
+    out = rng.random(N) < outlier_rate
+    X2[out] = rng.uniform(-8, 8, (int(out.sum()), 3))
+    f1 = X / np.linalg.norm(X, axis=1, keepdims=True)
+    f2 = X2 + rng.normal(size=X.shape) * 1e-3
+    f2 /= np.linalg.norm(f2, axis=1, keepdims=True)
+    return X, X2, f1, f2
+
+
+def test_stereo_ransac_kernels_equal_the_oracle_loop(oracle, ransacemu):
+    """sac_init -> 6 x (stereo_chunk + sac_replay) -> sac_select, emulated, against the oracle's
+    sequential Ransac::computeModel: iteration counts, winning draw, inlier set and model bit-exact,
+    from clean to outlier-heavy problems (early exit to all 1 001 trials), invalid depths, fewer
+    points than a sample, and the full-hypotheses mode of BASELINE.json configs[3]."""
+    rng = np.random.default_rng(21)
+    Pn, N = 6, 120
+    p1, p2 = np.zeros((Pn, N, 3)), np.zeros((Pn, N, 3))
+    for p in range(Pn):
+        p1[p], p2[p], _, _ = _scene(rng, N, [0.05, 0.2, 0.4, 0.6, 0.8, 0.97][p])
+        if p == 2:
+            p1[p, ::7] = 0.0                                     # invalid depth on the query side
+    for thr in (0.5, 0.05):
+        g = emu_ransac(ransacemu, False, p1, p2, thr)
+        for p in range(Pn):
+            _same_as_oracle(oracle.ransac_arun(p1[p], p2[p], thr, 0.995, 1000, 12345), g, p, N, (thr, p))
+    assert g["iterations"].min() < 100 and g["iterations"].max() == 1001
+    g = emu_ransac(ransacemu, False, p1, p2, 0.5, seed=7, max_it=300, prob=0.99)
+    for p in range(Pn):
+        _same_as_oracle(oracle.ransac_arun(p1[p], p2[p], 0.5, 0.99, 300, 7), g, p, N, ("seed 7", p))
+    g = emu_ransac(ransacemu, False, p1, p2, 0.5, full=True)
+    assert (g["iterations"] == 1001).all()
+    g = emu_ransac(ransacemu, False, p1[:, :2], p2[:, :2], 0.5)
+    assert (g["best_draw"] == -1).all() and (g["n_inliers"] == 0).all()
+
+
+def test_mono_ransac_kernels_equal_the_oracle_loop(oracle, ransacemu):
+    """sac_init -> 6 x (mono_front, mono_isolate, mono_isolate_deferred, mono_item, mono_count,
+    sac_replay) -> sac_select, emulated, against the oracle's loop: the same bit-exact outcome on
+    the awkward scenes of the GPU corner-case test (every guard of the fast inlier filter), at
+    several thresholds, with the generic root-isolation path forced, and with too few points."""
+    from test_gpu_parity import _nister_case
+    rng = np.random.default_rng(2024)
+    kinds = ["plain", "low_parallax", "far_points", "near_centres", "non_unit", "duplicates"]
+    for thr, N, fg in [(1e-6, 60, False), (1e-9, 33, False), (1e-4, 9, False), (5e-8, 8, False), (1e-6, 40, True)]:
+        f1, f2 = np.zeros((len(kinds), N, 3)), np.zeros((len(kinds), N, 3))
+        for i, kind in enumerate(kinds):
+            f1[i], f2[i] = _nister_case(rng, N, kind)
+        g = emu_ransac(ransacemu, True, f1, f2, thr, force_generic=fg)
+        for i, kind in enumerate(kinds):
+            _same_as_oracle(oracle.ransac_nister(f1[i], f2[i], thr, 0.995, 1000, 12345), g, i, N, (thr, N, kind, fg))
+    # clean scenes stop early (adaptive k), through the same replay
+    Pn, N = 3, 100
+    f1, f2 = np.zeros((Pn, N, 3)), np.zeros((Pn, N, 3))
+    for p in range(Pn):
+        _, _, f1[p], f2[p] = _scene(rng, N, 0.05 * p)
+    g = emu_ransac(ransacemu, True, f1, f2, 1e-5, max_it=400)
+    for p in range(Pn):
+        _same_as_oracle(oracle.ransac_nister(f1[p], f2[p], 1e-5, 0.995, 400, 12345), g, p, N, ("clean", p))
+    assert g["iterations"].min() < 401
+    g = emu_ransac(ransacemu, True, f1[:, :5], f2[:, :5], 1e-6)
+    assert (g["best_draw"] == -1).all() and (g["n_inliers"] == 0).all()

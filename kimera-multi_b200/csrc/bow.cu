@@ -21,9 +21,7 @@
 //      accumulators, ties at the cut taken in ascending entry id, then a rank
 //      sort by (score desc, entry asc).
 // Bound: HBM/L2 gather bandwidth on the touched postings.
-#ifndef KML_HOST_EMULATION  // tests/emu/: the kernel below is also run on the host by the CPU suite
 #include "common.cuh"
-#endif
 #include "kernels.h"
 
 namespace kml {
@@ -40,11 +38,7 @@ __device__ __forceinline__ unsigned long long bow_term_fx(double q, double d) {
 }
 
 __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
-#ifndef KML_HOST_EMULATION
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-#else
-  unsigned char* smem_raw = kml_emu::dynamic_smem();
-#endif
+  KML_DYN_SMEM(unsigned char, smem_raw);
   unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem_raw);
   __shared__ uint32_t s_ids[kBowMaxWords];
   __shared__ float s_vals[kBowMaxWords];
@@ -266,7 +260,6 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
   if (tid == 0) a.out_count[obase] = keff;
 }
 
-#ifndef KML_HOST_EMULATION
 void launch_bow(const BowArgs& a, cudaStream_t s) {
   const int grid = a.B * a.n_db * a.n_tiles;
   if (grid <= 0) return;
@@ -277,8 +270,7 @@ void launch_bow(const BowArgs& a, cudaStream_t s) {
                                   (int)smem));
     configured = smem;
   }
-  bow_score_kernel<<<grid, kBowThreads, smem, s>>>(a);
+  KML_LAUNCH((bow_score_kernel), grid, kBowThreads, smem, s, a);
 }
-#endif
 
 }  // namespace kml

@@ -24,7 +24,11 @@ struct CudaError : std::runtime_error {
                              __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
   } while (0)
 
+#ifndef KML_HOST_EMULATION
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+#else
+constexpr int kNumSMs = 2;    // tests/emu/: grid-stride kernels sized by the SM count stay cheap to emulate
+#endif
 
 // Kernel launch and dynamic shared memory as macros, so that the CPU test suite can compile the
 // same .cu text for the host and run the kernels under tests/emu/cuda_emu.h (which defines its own

@@ -15,9 +15,7 @@
 // which is BFMatcher's observed order (distance asc, trainIdx asc).
 // Bound: POPC pipe (8 POPC32 per compare algorithmically, 5 executed after a carry-save
 // reduction on the LOP3 pipe), see DESIGN.md §5.2.
-#ifndef KML_HOST_EMULATION  // tests/emu/: the kernels below are also run on the host by the CPU suite
 #include "common.cuh"
-#endif
 #include "kernels.h"
 
 namespace kml {
@@ -216,24 +214,27 @@ __global__ void __launch_bounds__(256) lowe_compact_kernel(const uint32_t* __res
   if (threadIdx.x == 0) M[p] = base_s;
 }
 
-#ifndef KML_HOST_EMULATION
 void launch_hamming_jobs(const HamJob* d_jobs, int njobs, int norm, cudaStream_t s) {
   if (njobs <= 0) return;
-  if (norm == 1) hamming_knn2_kernel<true><<<njobs, kHamThreads, 0, s>>>(d_jobs);
-  else hamming_knn2_kernel<false><<<njobs, kHamThreads, 0, s>>>(d_jobs);
+  if (norm == 1) KML_LAUNCH((hamming_knn2_kernel<true>), njobs, kHamThreads, 0, s, d_jobs);
+  else KML_LAUNCH((hamming_knn2_kernel<false>), njobs, kHamThreads, 0, s, d_jobs);
 }
 void launch_knn2_reduce(const uint32_t* partial, int nranges, int nq, int64_t range_len, int norm,
                         uint32_t* idx, uint16_t* dist, cudaStream_t s) {
   if (nq <= 0) return;
-  knn2_reduce_kernel<<<(nq + 127) / 128, 128, 0, s>>>(partial, nranges, nq, range_len, knn_key_shift(norm), idx, dist);
+  KML_LAUNCH((knn2_reduce_kernel), (nq + 127) / 128, 128, 0, s, partial, nranges, nq, range_len, knn_key_shift(norm), idx, dist);
 }
 void launch_lowe_compact(const uint32_t* keys, const int* nq_arr, int key_stride, double lowe, int norm,
                          uint16_t* iq, uint16_t* im, int* M, int P, cudaStream_t s) {
   if (P <= 0) return;
-  lowe_compact_kernel<<<P, 256, 0, s>>>(keys, nq_arr, key_stride, lowe, knn_key_shift(norm), iq, im, M);
+  KML_LAUNCH((lowe_compact_kernel), P, 256, 0, s, keys, nq_arr, key_stride, lowe, knn_key_shift(norm), iq, im, M);
 }
 
 // ------------------------------------------------------------ peak probes
+#ifdef KML_HOST_EMULATION  // tests/emu/: pipe peaks mean nothing on a host
+double measure_popc_peak(cudaStream_t) { return 0.0; }
+double measure_fp64_peak(cudaStream_t) { return 0.0; }
+#else
 __global__ void popc_peak_kernel(uint32_t* out, int iters) {
   uint32_t a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
   uint32_t a4 = a0 * 11 + 4, a5 = a0 * 13 + 5, a6 = a0 * 17 + 6, a7 = a0 * 19 + 7;

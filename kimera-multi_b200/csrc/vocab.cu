@@ -175,9 +175,8 @@ int kml_transform_batch(kml_handle* h, int B, int F, const uint8_t* desc, int64_
   d_words.scratch(n); d_ids.scratch(n); d_vals.scratch(n); d_cnt.scratch(B);
   KML_CUDA(cudaMemcpyAsync(h->d_scratch.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaEventRecord(h->ev[0], s));
-  vocab_descend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_scratch.p, n, h->sh->d_voc_nodes.p, h->sh->voc_k,
-                                                                  h->sh->voc_L, d_words.p);
-  bow_assemble_kernel<<<B, kAsmThreads, 0, s>>>(d_words.p, F, h->sh->d_voc_w.p, d_ids.p, d_vals.p, d_cnt.p);
+  KML_LAUNCH((vocab_descend_kernel), (unsigned)((n + 255) / 256), 256, 0, s, h->d_scratch.p, n, h->sh->d_voc_nodes.p, h->sh->voc_k, h->sh->voc_L, d_words.p);
+  KML_LAUNCH((bow_assemble_kernel), B, kAsmThreads, 0, s, d_words.p, F, h->sh->d_voc_w.p, d_ids.p, d_vals.p, d_cnt.p);
   KML_CUDA(cudaEventRecord(h->ev[1], s));
   KML_CUDA(cudaGetLastError());
   h->stats.kernel_launches += 2;

@@ -20,10 +20,33 @@
 #include <string.h>
 #include <ucontext.h>
 
+// every system header the product sources use, BEFORE the CUDA keywords become macros
+// (libstdc++ spells some attributes __noinline__ / __forceinline__ itself)
+#include <dlfcn.h>
+#include <float.h>
+#include <limits.h>
+#include <time.h>
+
 #include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
 #include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#endif
 
 #define KML_HOST_EMULATION 1
 #undef __device__

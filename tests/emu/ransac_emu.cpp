@@ -5,10 +5,7 @@
 // run_sac / ransac_batch of lcd.cu (allocation sizes and SacArgs fields).
 #include "cuda_emu.h"
 
-// the CUDA runtime calls the launchers make, on host memory (cudaFuncSetAttribute: cuda_emu.h)
-extern "C" cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
-extern "C" const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
-
+// (the CUDA runtime calls the launchers make come from fake_cudart.cpp, linked in)
 #include "../../kimera-multi_b200/csrc/ransac.cu"
 #include "../../kimera-multi_b200/csrc/sac_host.h"
 

@@ -23,14 +23,20 @@ def _P(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+def _build_harness(tmp_path_factory, name, extra=()):
+    """tests/emu/<name>.cpp (which includes the .cu under test) + the fake CUDA runtime -> a shared library"""
+    so = str(tmp_path_factory.mktemp("emu") / ("lib%s.so" % name))
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
+                    "-Wno-unused-function", "-Wno-unused-variable", "-Wno-attributes", *extra,
+                    "-I/usr/local/cuda/include", "-I", emu, os.path.join(emu, name + ".cpp"),
+                    os.path.join(emu, "fake_cudart.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
 @pytest.fixture(scope="module")
 def bowemu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "libbowemu.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
-                    "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
-                    "-I", os.path.join(ROOT, "tests", "emu"),
-                    os.path.join(ROOT, "tests", "emu", "bow_emu.cpp"), "-o", so], check=True)
-    lib = C.CDLL(so)
+    lib = _build_harness(tmp_path_factory, "bow_emu")
     lib.bowemu_db_create.restype = C.c_void_p
     return lib
 
@@ -170,12 +176,7 @@ def test_bow_kernel_ragged_databases_small_tiles_and_nss(oracle, bowemu):
 # ---------------------------------------------------------------------------------- matcher
 @pytest.fixture(scope="module")
 def hamemu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "libhamemu.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
-                    "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
-                    "-I", os.path.join(ROOT, "tests", "emu"),
-                    os.path.join(ROOT, "tests", "emu", "hamming_emu.cpp"), "-o", so], check=True)
-    return C.CDLL(so)
+    return _build_harness(tmp_path_factory, "hamming_emu")
 
 
 def emu_knn2(lib, q, t, norm=0, range_len=1 << 20):
@@ -254,13 +255,8 @@ def test_matcher_kernels_edge_cases_against_the_oracle(oracle, hamemu):
 # ----------------------------------------------------------------------------------- RANSAC
 @pytest.fixture(scope="module")
 def ransacemu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "libransacemu.so")
     # -ffp-contract=off: the host equivalent of the -fmad=false ransac.cu is compiled with
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-Wall",
-                    "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-attributes",
-                    "-I/usr/local/cuda/include", "-I", os.path.join(ROOT, "tests", "emu"),
-                    os.path.join(ROOT, "tests", "emu", "ransac_emu.cpp"), "-o", so], check=True)
-    return C.CDLL(so)
+    return _build_harness(tmp_path_factory, "ransac_emu", extra=("-ffp-contract=off",))
 
 
 def emu_ransac(lib, mono, a, b, thr, prob=0.995, max_it=1000, seed=12345, full=False, force_generic=False):

@@ -128,6 +128,10 @@ inline void fibre_entry() {
 
 // Runs body() once per CUDA thread of a grid x block launch (1-D block, 1- or 2-D grid).
 inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::function<void()>& body) {
+  // one launch at a time: the emulator state and the kernels' __shared__ statics are global, and
+  // the library's query lanes call in from several host threads
+  static std::mutex launch_mu;
+  std::lock_guard<std::mutex> launch_lock(launch_mu);
   State& s = S();
   constexpr size_t kStack = 512 * 1024;
   if (block_threads < 1 || block_threads > 1024) throw std::runtime_error("kml_emu: bad block size");

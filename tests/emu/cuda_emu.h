@@ -81,6 +81,9 @@ struct State {
   uint64_t xchg[32][32];           // [warp][lane] exchange slots of the warp collectives
   std::vector<unsigned char> dyn;  // dynamic shared memory of the running CTA
   const std::function<void()>* body = nullptr;
+  int schedule = -1;               // 0 ascending, 1 descending, 2 random; -1 = read KML_EMU_SCHEDULE
+  uint64_t rng = 1;
+  std::vector<int> order;
 };
 inline State& S() { static State s; return s; }
 
@@ -133,6 +136,11 @@ inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::fun
   static std::mutex launch_mu;
   std::lock_guard<std::mutex> launch_lock(launch_mu);
   State& s = S();
+  if (s.schedule < 0) {
+    const char* e = getenv("KML_EMU_SCHEDULE");
+    s.schedule = (e && !strncmp(e, "reverse", 7)) ? 1 : (e && !strncmp(e, "random", 6)) ? 2 : 0;
+    if (s.schedule == 2 && e[6] == ':') s.rng = strtoull(e + 7, nullptr, 10) * 2 + 1;
+  }
   constexpr size_t kStack = 512 * 1024;
   if (block_threads < 1 || block_threads > 1024) throw std::runtime_error("kml_emu: bad block size");
   s.n = block_threads;
@@ -162,7 +170,22 @@ inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::fun
       while (s.alive > 0) {
         const int before = s.alive;
         const unsigned g0 = s.bar_gen;
-        for (int t = 0; t < block_threads; ++t) {
+        for (int k = 0; k < block_threads; ++k) {
+          // which fibre runs next: ascending thread id, descending, or a fresh random order per
+          // pass (KML_EMU_SCHEDULE=reverse | random[:seed]) — results must not depend on it
+          int t = k;
+          if (s.schedule == 1) t = block_threads - 1 - k;
+          else if (s.schedule == 2) {
+            if (k == 0) {
+              s.order.resize(block_threads);
+              for (int i = 0; i < block_threads; ++i) s.order[i] = i;
+              for (int i = block_threads - 1; i > 0; --i) {
+                s.rng = s.rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(s.order[i], s.order[(int)((s.rng >> 33) % (uint64_t)(i + 1))]);
+              }
+            }
+            t = s.order[k];
+          }
           if (s.done[t]) continue;
           s.cur = t;
           s.tid.x = t; s.tid.y = s.tid.z = 0;

@@ -353,3 +353,20 @@ def test_mono_ransac_kernels_equal_the_oracle_loop(oracle, ransacemu):
     assert g["iterations"].min() < 401
     g = emu_ransac(ransacemu, True, f1[:, :5], f2[:, :5], 1e-6)
     assert (g["best_draw"] == -1).all() and (g["n_inliers"] == 0).all()
+
+
+# ------------------------------------------------------------------------- schedule independence
+@pytest.mark.parametrize("schedule", ["reverse", "random:3"])
+def test_results_do_not_depend_on_the_thread_schedule(schedule):
+    """The emulator runs a CTA's threads in ascending order between rendezvous points; a GPU runs
+    them in any order.  The same tests under a descending and a per-pass random order (same
+    bit-exact expectations): the fixed-point BoW accumulation, the atomically compacted work lists
+    of the mono rounds and the count kernel's running bound must not care."""
+    if os.environ.get("KML_EMU_SCHEDULE"):
+        pytest.skip("already inside a schedule run")
+    import sys
+    env = dict(os.environ, KML_EMU_SCHEDULE=schedule)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-p", "no:cacheprovider",
+                        "-n", "4", "-k", "not schedule"], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=1200)
+    assert r.returncode == 0 and "6 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]

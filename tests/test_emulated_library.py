@@ -73,3 +73,13 @@ def test_gpu_parity_tests_against_the_emulated_library(libkml_emu):
     m = re.search(r"(\d+) passed", r.stdout)
     assert m and int(m.group(1)) >= 15, tail
     assert "failed" not in r.stdout.splitlines()[-1] and "skipped" not in r.stdout.splitlines()[-1], tail
+
+
+def test_smoke_entry_point_against_the_emulated_library(libkml_emu):
+    """__graft_entry__.smoke() (what the driver runs on cuda:0 before the bench) with the emulated
+    build behind the mirror: database fill, a 4-query batch, record-by-record parity with the oracle."""
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); import __graft_entry__ as g; import kml._lib as L; "
+            "lib = C.CDLL(%r); lib.kml_last_error.restype = C.c_char_p; lib.kml_last_error.argtypes = [C.c_void_p]; "
+            "L._lib = lib; g.smoke()" % (ROOT, libkml_emu))
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout and "parity with oracle" in r.stdout, r.stdout + r.stderr

@@ -143,6 +143,12 @@ inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::fun
   }
   constexpr size_t kStack = 512 * 1024;
   if (block_threads < 1 || block_threads > 1024) throw std::runtime_error("kml_emu: bad block size");
+  // a GPU refuses these with cudaErrorInvalidConfiguration; the emulator must not run them as no-ops
+  if (grid.x == 0 || grid.x > 2147483647u || grid.y > 65535u) {
+    fprintf(stderr, "kml_emu: launch with an invalid grid (%u x %u)\n", grid.x, grid.y);
+    throw std::runtime_error("kml_emu: invalid grid");
+  }
+  if (dyn_smem > 227 * 1024) throw std::runtime_error("kml_emu: more dynamic shared memory than an SM has");
   s.n = block_threads;
   s.ctx.resize(block_threads);
   s.done.assign(block_threads, 0);

@@ -24,6 +24,7 @@
  */
 #ifndef KML_H_
 #define KML_H_
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -45,7 +46,8 @@ extern "C" {
 #define KML_ERR_CUDA (-2)
 #define KML_ERR_NCCL (-3)
 #define KML_ERR_CAPACITY (-4)
-#define KML_ERR_STREAM_EXHAUSTED (-5) /* pre-drawn sample stream ran out */
+#define KML_ERR_STREAM_EXHAUSTED (-5) /* pre-drawn sample stream ran out (kept for ABI stability: the stream
+                                        * now covers every draw the reference loop can consume) */
 
 /* LcdParams / LcdTpParams (kimera_multi_lcd include/kimera_multi_lcd/types.h;
  * set once in loadAndInitialize, kimera_multi_lcd.patch:30-31).  Defaults:
@@ -189,6 +191,11 @@ int kml_query_batch_upload(kml_handle* h, int B, const uint64_t* q_robot,
                            const float* prev_vals, const uint8_t* desc, const double* bearings,
                            const double* points, int F);
 int kml_query_batch_run(kml_handle* h, kml_result* out, int cap_per_query, int32_t* counts);
+/* Page-locked host memory for the caller's batch arrays: an array allocated here is copied to the
+ * device from where it lies; ordinary (pageable) arrays are first staged through the handle's own
+ * pinned buffer.  Results are identical either way. */
+int kml_host_alloc(size_t bytes, void** out);
+int kml_host_free(void* p);
 
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2): idx/dist are [nq][2];
  * a missing neighbour is idx 0xFFFFFFFF, dist 0xFFFF.  ms_kernel (nullable)

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -21,6 +22,7 @@ struct NcclApi {
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 };
 
 static NcclApi* nccl_api(std::string* err) {
@@ -39,6 +41,7 @@ static NcclApi* nccl_api(std::string* err) {
       KML_SYM(Broadcast);
       KML_SYM(GetErrorString);
       KML_SYM(CommGetAsyncError);
+      KML_SYM(CommAbort);
 #undef KML_SYM
     }
   }
@@ -66,12 +69,53 @@ int comm_allgather(kml_handle* h, const void* d_send, void* d_recv, size_t bytes
   }
   NcclApi* api = nccl_api(&h->err);
   if (!api) return KML_ERR_NCCL;
+  if (!h->comm->comm) {
+    h->err = "communicator was aborted after an error";
+    return KML_ERR_NCCL;
+  }
   ncclResult_t r = api->AllGather(d_send, d_recv, bytes, ncclChar, h->comm->comm, h->stream);
   if (r != ncclSuccess) {
     h->err = std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(r) : "?");
     return KML_ERR_NCCL;
   }
   return KML_OK;
+}
+
+// Host wait for a stream that holds a collective: polls the stream like kml_handle::wait_stream,
+// and every millisecond asks NCCL for an asynchronous error (a peer that died, a network fault)
+// and checks a deadline (KML_NCCL_TIMEOUT_S, default 120 s) — either one aborts the communicator
+// and returns KML_ERR_NCCL instead of waiting for ever on a rank that never arrives.
+int comm_wait(kml_handle* h) {
+  NcclApi* api = h->comm ? nccl_api(nullptr) : nullptr;
+  static const double timeout_s = [] {
+    const char* e = getenv("KML_NCCL_TIMEOUT_S");
+    const double v = e ? atof(e) : 0.0;
+    return v > 0.0 ? v : 120.0;
+  }();
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (unsigned it = 0;; ++it) {
+    const cudaError_t e = cudaStreamQuery(h->stream);
+    if (e == cudaSuccess) return KML_OK;
+    if (e != cudaErrorNotReady) KML_CUDA(e);
+    if (api && (it & 63u) == 63u) {
+      ncclResult_t ar = ncclSuccess;
+      bool bad = api->CommGetAsyncError && api->CommGetAsyncError(h->comm->comm, &ar) == ncclSuccess && ar != ncclSuccess &&
+                 ar != ncclInProgress;
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      const double el = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+      if (bad || el > timeout_s) {
+        h->err = bad ? std::string("NCCL asynchronous error: ") + (api->GetErrorString ? api->GetErrorString(ar) : "?")
+                     : std::string("collective did not complete within KML_NCCL_TIMEOUT_S");
+        if (api->CommAbort) api->CommAbort(h->comm->comm);
+        h->comm->comm = nullptr;
+        return KML_ERR_NCCL;
+      }
+    }
+    struct timespec ts = {0, 20000};
+    nanosleep(&ts, nullptr);
+  }
 }
 
 }  // namespace kml

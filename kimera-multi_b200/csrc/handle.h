@@ -38,9 +38,8 @@ struct RobotDb {
   std::vector<uint32_t> ids;
   std::vector<float> vals;
   std::vector<uint64_t> entry_to_pose;
-  // dense frame index of the entry's keyframe, -1 = not looked up yet / frame not stored yet.
-  // Filled lazily by the batch query (relaxed atomic int stores of a value that never changes
-  // once set: frames are only ever added), sized by addBowVector.
+  // dense frame index of the entry's keyframe, -1 = frame not stored (yet); kept current by
+  // addBowVector / addVLCFrame
   std::vector<int32_t> entry_to_frame;
   std::map<uint64_t, uint32_t> pose_to_entry;
   // device CSR
@@ -48,6 +47,12 @@ struct RobotDb {
   uint32_t W = 0;
   DevBuf<uint32_t> row_ptr;
   DevBuf<uint2> postings;
+  // device copies of entry_to_pose / entry_to_frame (read by select_candidates_kernel): entries
+  // [0, synced) are on the device except the ones listed in frame_patches
+  DevBuf<uint64_t> d_entry_pose;
+  DevBuf<int32_t> d_entry_frame;
+  size_t synced = 0;
+  std::vector<uint32_t> frame_patches;
   uint32_t n_entries() const { return (uint32_t)entry_to_pose.size(); }
 };
 
@@ -81,8 +86,10 @@ struct kml_shared {
   kml::DevBuf<uint8_t> s_desc;     // [n_feat][32]
   kml::DevBuf<double> s_bear;      // [n_feat][3]
   kml::DevBuf<double> s_pts;       // [n_feat][3]
-  kml::DevBuf<int64_t> s_off;      // [n_frames]
-  bool s_off_dirty = true;
+  kml::DevBuf<int64_t> s_off;      // [n_frames] feature offset of every stored frame
+  kml::DevBuf<int32_t> s_F;        // [n_frames] features of every stored frame
+  size_t frames_synced = 0;        // frames whose (offset, F) are on the device
+  uint64_t version = 1;            // bumped by every add*: lanes re-upload their database views when it moved
 
   // ---- pre-drawn sample stream + k tables
   std::vector<uint32_t> raw_h;
@@ -124,6 +131,8 @@ struct kml_handle {
   // to produce, so equal-shaped batches never reallocate (cudaFree waits for the whole device,
   // i.e. for every other lane's kernels and pending collectives).  0 = size by the actual count.
   int pair_cap = 0;
+  uint64_t views_version = 0;  // kml_shared::version the handle's d_dbs array was built from
+  int views_n_db = 0, views_tile = 0, views_n_tiles = 0;
   std::string err;
   kml_stats stats = {};
 
@@ -166,6 +175,16 @@ struct kml_handle {
   kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
   kml::DevBuf<uint8_t> d_scratch, d_scratch2;
+  // batch records: the all-gather buffer of the sharded query (rank r's block at r * blk; a single
+  // GPU has one block), the merged records, the batch counters and their pinned host copies
+  kml::DevBuf<uint8_t> d_blocks, d_merged;
+  kml::DevBuf<kml::BatchStats> d_stats;
+  kml::DevBuf<uint64_t> d_qrobot, d_qpose;
+  kml::PinBuf<uint8_t> h_recs;
+  kml::PinBuf<kml::BatchStats> h_stats;
+  kml::PinBuf<uint8_t> h_in;     // pinned staging of a query batch that arrives in pageable memory
+  kml::DevBuf<uint8_t> d_in;     // the packed query batch on the device
+  size_t item_cap = 0;           // capacity of the mono rounds' item lists (grows after an overflow)
 
   kml::Comm* comm = nullptr;
 };

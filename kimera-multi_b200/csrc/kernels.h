@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/kml.h"
+
 namespace kml {
 
 // ------------------------------------------------------------- hamming.cu
@@ -29,6 +31,11 @@ struct BowDb {
   const uint2* postings;    // {entry, float bits of weight}, rows ascending in entry
   uint32_t W;               // number of word rows
   uint32_t n_entries;
+  // db_EntryId_to_PoseId_ and the dense frame-store index of every entry's keyframe (-1: the
+  // keyframe's VLC frame has not been stored), read by the device-side candidate selection
+  const uint64_t* entry_pose;   // [n_entries]
+  const int32_t* entry_frame;   // [n_entries]
+  uint64_t robot;
 };
 constexpr int kBowMaxWords = 1024;  // max words per BoW vector handled on device
 constexpr int kBowMaxK = 128;       // max max_results handled on device
@@ -90,9 +97,12 @@ struct SacArgs {
   double* item_q;        // [items] smallest candidate quality of the item (< 1e6), if status == 2
   double* item_model;    // [items][12] the candidate that attains it
   uint8_t* item_status;  // [items] 0 root not refined, 1 refined without usable candidate, 2 scored
-  uint16_t* samples;     // [P][cap_draws][S]
-  int32_t* valid;        // [P][cap_draws]
-  int32_t* counts;       // [P][cap_draws]
+  unsigned int item_cap; // capacity of the item arrays and of fb_list
+  unsigned int* overflow;  // set when a round needed more than item_cap items (results of the batch are void)
+  unsigned int* pending;   // nullable: sac_select counts the problems that are not done yet
+  uint16_t* samples;     // [P][kRoundCap][S] samples of the current round's draws, slot = draw - r_begin
+  int32_t* valid;        // [P][kRoundCap]
+  int32_t* counts;       // [P][kRoundCap]
   SacState* st;          // [P]
   double* best_model;    // [P][12]
   const double* ktable;  // [(Nmax+1)*(Nmax+1)] k as function of (N, best count)
@@ -109,16 +119,18 @@ struct SacArgs {
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
 constexpr int kStereoChunk = 64;    // hypotheses per CTA (stereo) and size of round 0
 constexpr int kStereoThreads = 128; // threads of a stereo CTA (4 counting warps)
-constexpr int kSacRounds = 6;      // 64,64,128,256,512 new draws, then everything that is left
+constexpr int kSacRounds = 6;      // rounds enqueued blindly: 64,64,128,256,512,512 new draws at most; more only while a problem is pending
 constexpr int kRoundCap = 512;     // most new draws any round evaluates per problem
 // upper bound of NEW draws evaluated per problem in round r (doubling schedule)
 __host__ __device__ inline int sac_round_draws(int round, int chunk) {
-  return round == 0 ? chunk : chunk << (round - 1);
+  return round == 0 ? chunk : (round > 8 ? chunk << 8 : chunk << (round - 1));
 }
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
 // one round = chunk kernel over the pending draw range + replay; returns #kernels launched
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s);
+// *a.pending += number of problems whose loop has not ended
+void launch_sac_pending(const SacArgs& a, cudaStream_t s);
 void launch_mono_select(const SacArgs& a, cudaStream_t s);
 void launch_stereo_select(const SacArgs& a, cudaStream_t s);
 
@@ -151,6 +163,21 @@ struct StereoGatherArgs {
   uint16_t* kq; uint16_t* km;                        // [P][stride]
 };
 void launch_gather_points(const StereoGatherArgs& g, cudaStream_t s);
+// Counters of one batch, accumulated by the kernels (device atomics) and read back with the
+// records: the logLcdStat() counters and the algorithmic work the rooflines are computed from.
+struct BatchStats {
+  unsigned long long postings;       // inverted-file postings touched (bow_score_kernel)
+  unsigned long long survivors;      // totalBoWMatches: candidates left after the alpha*nss cut
+  unsigned long long pairs;          // candidate pairs that entered verification
+  unsigned long long mono_ok;        // pairs that passed geometricVerificationNister
+  unsigned long long hyp_m, hyp_s;   // draws consumed by the reference loop (mono / stereo)
+  unsigned long long res_m, res_s;   // draws consumed x correspondences
+  unsigned long long eval_m, eval_s; // draws evaluated by the round schedule
+  unsigned int pending_m, pending_s; // problems whose loop has not ended after the enqueued rounds
+  unsigned int item_overflow;        // a mono round produced more (draw, root) items than the list holds
+  unsigned int pad;
+};
+
 // mono acceptance gate + final record assembly
 struct FinalizeArgs {
   int P;
@@ -158,10 +185,49 @@ struct FinalizeArgs {
   const SacState* st3; const int32_t* inl3; const int32_t* N3; const double* model3;
   int min_inliers; double min_ratio_mono; double min_ratio_stereo;
   int32_t* mono_ok;  // out (phase 1)
-  // phase 2 outputs
-  int32_t* status; int32_t* out_mono_inl; int32_t* out_stereo_inl; double* out_R; double* out_T;
+  // phase 2 outputs: the kml_result records of the batch, pair slot p = b*K + i -> recs[b*cap + i]
+  const PairDesc* pairs; int K; int cap;
+  kml_result* recs;
+  BatchStats* stats;
 };
 void launch_mono_gate(const FinalizeArgs& f, cudaStream_t s);
 void launch_finalize(const FinalizeArgs& f, cudaStream_t s);
+
+// ---------------------------------------------------------------- select.cu
+// detectLoop = detectLoopWithRobot over every resident robot database, steps 3-7 (SURVEY.md A.3;
+// /root/reference/images/kimera-multi.drawio:2571-2580) on the device: per query the per-database
+// result lists of the scorer are cut at alpha*nss, filtered (inter_robot_only, dist_local),
+// normalised by nss, and the top_k_verify best by (score desc, robot asc, pose asc) become the
+// query's records and candidate pairs.  Pair slot p = b*K + i is fixed, so every later kernel of
+// the batch has a static grid; a slot without a candidate (or without a stored frame) is inactive:
+// m_frame = -1, nq = 0.
+constexpr int kSelMaxK = 128;  // upper bound of top_k_verify and max_db_results on this path
+struct SelectArgs {
+  const BowDb* dbs; int n_db; int B; int n_tiles; int Kdb;
+  const uint32_t* bow_entry; const double* bow_score; const int32_t* bow_count;  // [B][n_db][n_tiles][Kdb]
+  const double* nss;                                                              // [B]
+  const uint64_t* q_robot; const uint64_t* q_pose;                                // [B]
+  double alpha, min_nss; int inter_robot_only; int dist_local;
+  int K, cap;
+  const uint8_t* s_desc; const int64_t* s_off; const int32_t* s_F;                // frame store
+  const uint8_t* q_desc; int qF;                                                  // query frames [B][qF][32]
+  kml_result* recs; int32_t* counts;                                              // [B][cap], [B]
+  PairDesc* pairs; HamJob* jobs; int32_t* nq; uint32_t* keys; int key_stride;     // [B*K]
+  BatchStats* stats;
+};
+void launch_select(const SelectArgs& a, cudaStream_t s);
+// flag word of this rank's record block: 1 if RANSAC problems are pending or the item lists
+// overflowed (the host continues / re-runs), else 0; also copies the overflow flag into the stats
+void launch_block_flags(BatchStats* stats, const unsigned int* overflow, int32_t* flag, cudaStream_t s);
+
+// Merge of the sharded query on the device: block r = { kml_result[B][cap_in]; int32 counts[B];
+// int32 error; pad } at base + r*blk_stride, every list already ranked by (score desc, robot
+// asc, pose asc); one warp per query keeps the best `cap` of the union.
+struct MergeArgs {
+  const uint8_t* base; size_t blk_stride; size_t counts_off; size_t err_off; int nranks; int B; int cap_in; int cap;
+  kml_result* out; int32_t* counts;
+  int32_t* err_out;  // max over the ranks' flag words
+};
+void launch_merge(const MergeArgs& a, cudaStream_t s);
 
 }  // namespace kml

@@ -22,6 +22,7 @@ namespace kml {
 int comm_nranks(const kml_handle* h);
 int comm_rank(const kml_handle* h);
 int comm_allgather(kml_handle* h, const void* d_send, void* d_recv, size_t bytes);
+int comm_wait(kml_handle* h);
 }  // namespace kml
 
 #define KML_API_BEGIN(h)                              \
@@ -67,11 +68,18 @@ static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_
   const uint32_t entry = db->n_entries();
   db->pose_to_entry[pose] = entry;
   db->entry_to_pose.push_back(pose);
-  db->entry_to_frame.push_back(-1);
+  {  // frameExists(robot, pose) already?  then the entry's dense frame index is known now
+    auto fit = h->sh->frames.find(RobotPoseId(db->robot, pose));
+    db->entry_to_frame.push_back(fit == h->sh->frames.end() ? -1 : fit->second.index);
+  }
   db->ids.insert(db->ids.end(), ids, ids + n);
   db->vals.insert(db->vals.end(), vals, vals + n);
   db->off.push_back((int64_t)db->ids.size());
   db->dirty = true;
+  {
+    std::lock_guard<std::mutex> lk(h->sh->mu);
+    h->sh->version++;
+  }
   return KML_OK;
 }
 
@@ -94,16 +102,21 @@ static void rebuild_csr(kml_handle* h, RobotDb* db) {
   db->dirty = false;
 }
 
+static void sync_db_maps(kml_handle* h, RobotDb* db);
 static BowDb db_view(kml_handle* h, RobotDb* db) {
   {
     std::lock_guard<std::mutex> lk(h->sh->mu);
     if (db->dirty) rebuild_csr(h, db);
+    sync_db_maps(h, db);
   }
   BowDb v;
   v.row_ptr = db->row_ptr.p;
   v.postings = db->postings.p;
   v.W = db->W;
   v.n_entries = db->n_entries();
+  v.entry_pose = db->d_entry_pose.p;
+  v.entry_frame = db->d_entry_frame.p;
+  v.robot = db->robot;
   return v;
 }
 
@@ -262,31 +275,24 @@ static int add_frames_host(kml_handle* h, uint64_t robot, const uint64_t* poses,
     rec.index = (int32_t)h->sh->frame_off_h.size();
     h->sh->frame_off_h.push_back(rec.feat_off);
     h->sh->frame_F_h.push_back(F);
-    auto prev = h->sh->frames.find(id);
-    if (prev != h->sh->frames.end()) {  // overwritten frame: drop the cached index of its BoW entry
-      auto dit = h->sh->dbs.find(robot);
-      if (dit != h->sh->dbs.end()) {
-        auto eit = dit->second->pose_to_entry.find(poses[i]);
-        if (eit != dit->second->pose_to_entry.end()) dit->second->entry_to_frame[eit->second] = -1;
+    h->sh->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
+    // the BoW entry of this keyframe (if it has one) now points at the stored frame
+    auto dit = h->sh->dbs.find(robot);
+    if (dit != h->sh->dbs.end()) {
+      auto eit = dit->second->pose_to_entry.find(poses[i]);
+      if (eit != dit->second->pose_to_entry.end()) {
+        dit->second->entry_to_frame[eit->second] = rec.index;
+        if (eit->second < dit->second->synced) dit->second->frame_patches.push_back(eit->second);
       }
     }
-    h->sh->frames[id] = rec;  // vlc_frames_[id] = frame (overwrite keeps the newest copy)
   }
   h->sh->n_feat = base + (int64_t)total;
-  h->sh->s_off_dirty = true;
+  {
+    std::lock_guard<std::mutex> lk(h->sh->mu);
+    h->sh->version++;
+  }
   KML_CUDA(cudaStreamSynchronize(h->stream));  // caller may free its buffers on return
   return KML_OK;
-}
-
-static void ensure_frame_offsets(kml_handle* h) {
-  std::lock_guard<std::mutex> lk(h->sh->mu);
-  if (!h->sh->s_off_dirty) return;
-  h->sh->s_off.scratch(std::max<size_t>(h->sh->frame_off_h.size(), 1));
-  if (!h->sh->frame_off_h.empty())
-    KML_CUDA(cudaMemcpyAsync(h->sh->s_off.p, h->sh->frame_off_h.data(), 8 * h->sh->frame_off_h.size(),
-                             cudaMemcpyHostToDevice, h->stream));
-  KML_CUDA(cudaStreamSynchronize(h->stream));
-  h->sh->s_off_dirty = false;
 }
 
 // ====================================================== RANSAC host helpers
@@ -319,16 +325,15 @@ struct SacBufs {
   DevBuf<int32_t>* inl;
 };
 
-// Runs one batched RANSAC (mono: S=8, stereo: S=3) over P problems whose
-// correspondences are already gathered in d_a/d_b.  Everything is enqueued on
-// the handle's stream; no host synchronisation.
-static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
-                    const int32_t* d_N, int stride, int full, SacBufs out, int mask_words) {
-  if (P <= 0) return;
-  const size_t Pa = std::max<size_t>((size_t)P, (size_t)h->pair_cap);  // allocation size, see kml_handle::pair_cap
+// Buffers and arguments of one batched RANSAC (mono: S=8, stereo: S=3) over P problems whose
+// correspondences are already gathered in d_a/d_b.  `pending` (nullable) receives the number of
+// problems whose loop has not ended when the select kernel runs.
+static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
+                           const int32_t* d_N, int stride, int full, SacBufs out, int mask_words,
+                           unsigned int* pending) {
+  const size_t Pa = (size_t)std::max(P, 1);
   const kml_params& prm = h->prm;
   const int S = mono ? 8 : 3;
-  const int chunk = mono ? kMonoChunk : kStereoChunk;
   const int max_it = mono ? prm.max_ransac_iterations_mono : prm.max_ransac_iterations;
   if (mono)
     ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->sh->d_ktable_mono, &h->sh->ktable_n_mono);
@@ -336,30 +341,31 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
     ensure_ktable(h, stride, 3, prm.ransac_probability, &h->sh->d_ktable_stereo, &h->sh->ktable_n_stereo);
   const int raw_len = (int)h->sh->raw_h.size();
   const int cap_draws = sac_cap_draws(raw_len, S, max_it);
-  {  // the doubling round schedule must cover cap_draws with at most kRoundCap new draws per round
-    int cum = 0;
-    for (int r = 0; r + 1 < kSacRounds; ++r) cum += std::min(sac_round_draws(r, chunk), kRoundCap);
-    if (cap_draws - cum > kRoundCap)
-      throw std::runtime_error("max_ransac_iterations too large for the RANSAC round schedule (limit 1279)");
-  }
   h->d_perm.scratch(Pa * stride);
-  h->d_samples.scratch(Pa * cap_draws * S);
+  h->d_samples.scratch(Pa * kRoundCap * 8);
   h->d_models.scratch(Pa * kRoundCap * 12);
+  h->d_fb_list.scratch(8);
   if (mono) {
     h->d_nsol.scratch(Pa * kRoundCap);
     h->d_esol.scratch(Pa * kRoundCap * 70);
     h->d_brk.scratch(Pa * kRoundCap * 40);
-    h->d_fb_list.scratch(Pa * kRoundCap * 20 + 2);
-    // (draw, root) items of a round: up to 20 brackets per draw (both Sturm chains)
-    const size_t max_items = Pa * kRoundCap * 20;
+    // (draw, root) items of a round: a draw has at most 10 real roots, a round at most kRoundCap
+    // draws per problem, but late rounds are large only for the few problems still running — the
+    // lists are sized for 2 items per (problem, slot) and the batch is re-run with larger lists
+    // if a round ever needs more (BatchStats::item_overflow / SacArgs::overflow)
+    const size_t worst = Pa * kRoundCap * 10;
+    size_t want = std::max<size_t>(h->item_cap, std::min<size_t>(worst, std::max<size_t>(Pa * kRoundCap * 2, 65536)));
+    want = std::min(want, worst);
+    h->item_cap = want;
+    h->d_fb_list.scratch(want + 8);
     h->d_item_base.scratch(Pa * kRoundCap);
-    h->d_item_list.scratch(max_items);
-    h->d_item_q.scratch(max_items);
-    h->d_item_model.scratch(max_items * 12);
-    h->d_item_status.scratch(max_items);
+    h->d_item_list.scratch(want);
+    h->d_item_q.scratch(want);
+    h->d_item_model.scratch(want * 12);
+    h->d_item_status.scratch(want);
   }
-  h->d_valid.scratch(Pa * cap_draws);
-  h->d_counts.scratch(Pa * cap_draws);
+  h->d_valid.scratch(Pa * kRoundCap);
+  h->d_counts.scratch(Pa * kRoundCap);
   out.st->scratch(Pa);
   out.best->scratch(Pa * 12);
   out.mask->scratch(Pa * mask_words);
@@ -369,7 +375,11 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.raw = h->sh->d_raw.p; a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = h->d_perm.p; a.samples = h->d_samples.p; a.models = h->d_models.p;
   a.fsol = h->d_esol.p; a.nroot = h->d_nsol.p; a.brk = h->d_brk.p;
-  a.fb_list = h->d_fb_list.p + 2; a.fb_count = h->d_fb_list.p; a.item_count = h->d_fb_list.p + 1;
+  // d_fb_list: [0] deferred counter, [1] item counter, [2] item-list overflow flag of the mono rounds,
+  // [3] pending counter of finish_sac, [4] the stereo problem's (never raised) overflow word, [8..] deferred list
+  a.fb_list = h->d_fb_list.p + 8; a.fb_count = h->d_fb_list.p; a.item_count = h->d_fb_list.p + 1;
+  a.overflow = h->d_fb_list.p + (mono ? 2 : 4); a.pending = pending;
+  a.item_cap = (unsigned int)std::min<size_t>(h->item_cap, 0xFFFFFFF0u);
   a.item_base = h->d_item_base.p; a.item_list = h->d_item_list.p; a.item_q = h->d_item_q.p;
   a.item_model = h->d_item_model.p; a.item_status = h->d_item_status.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
@@ -380,160 +390,185 @@ static void run_sac(kml_handle* h, bool mono, int P, const double* d_a, const do
   a.max_iterations = max_it; a.full = full;
   a.force_generic = getenv("KML_FORCE_GENERIC_ISOLATE") ? 1 : 0;
   a.inlier_mask = out.mask->p; a.mask_words = mask_words; a.n_inliers = out.inl->p;
-  KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * P, h->stream));
-  launch_sac_init(a, S, h->stream);
+  return a;
+}
+
+// init + the blind rounds + selectWithinDistance of the winners; everything is enqueued on the
+// handle's stream, no host synchronisation.  Round 0 evaluates one chunk; each later round covers
+// every trial the reference loop can still need (k never increases) up to the doubling schedule.
+static void enqueue_sac(kml_handle* h, bool mono, const SacArgs& a, SacBufs out) {
+  if (a.P <= 0) return;
+  cudaStream_t s = h->stream;
+  KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * a.P, s));
+  KML_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(unsigned int), s));
+  launch_sac_init(a, mono ? 8 : 3, s);
   h->stats.kernel_launches += 1;
-  // round 0 evaluates one chunk; each later round covers every trial the
-  // reference loop can still need (k never increases), plus a skip reserve
   for (int r = 0; r < kSacRounds; ++r)
-    h->stats.kernel_launches += mono ? launch_mono_round(a, r, h->stream) : launch_stereo_round(a, r, h->stream);
-  if (mono) launch_mono_select(a, h->stream); else launch_stereo_select(a, h->stream);
+    h->stats.kernel_launches += mono ? launch_mono_round(a, r, s) : launch_stereo_round(a, r, s);
+  if (mono) launch_mono_select(a, s); else launch_stereo_select(a, s);
   h->stats.kernel_launches += 1;
   KML_CUDA(cudaGetLastError());
 }
 
-// =========================================================== verification
-// Query-side frame arrays of the current verification call
-struct QuerySide {
-  const uint8_t* desc; const double* bear; const double* pts; int F;  // [slots][F][...]
-};
-
-struct VerifyOut {
-  std::vector<int32_t> status, M, mono_inl, stereo_inl;
-  std::vector<double> R, T;
-};
-
-// Full device pipeline over P pairs.  pairs[p] = {query slot, stored frame index}.
-static void verify_pairs(kml_handle* h, const std::vector<PairDesc>& pairs, const QuerySide& qs,
-                         VerifyOut* out) {
-  const int P = (int)pairs.size();
-  out->status.assign(P, 1); out->M.assign(P, 0); out->mono_inl.assign(P, 0);
-  out->stereo_inl.assign(P, 0); out->R.assign((size_t)P * 9, 0.0); out->T.assign((size_t)P * 12, 0.0);
-  h->stats.pairs_last = P;
-  if (P == 0) return;
-  ensure_frame_offsets(h);
-  const size_t Pa = std::max<size_t>((size_t)P, (size_t)h->pair_cap);  // allocation size, see kml_handle::pair_cap
-  const int stride = std::max(qs.F, 8);
-  const int mask_words = (stride + 31) / 32;
-  // ---- jobs
-  std::vector<HamJob> jobs(P);
-  std::vector<int32_t> nq(P, qs.F);
-  h->d_keys.scratch(Pa * stride * 2);
-  for (int p = 0; p < P; ++p) {
-    jobs[p].q = qs.desc + (size_t)pairs[p].q_slot * qs.F * 32;
-    jobs[p].nq = qs.F;
-    jobs[p].t = h->sh->s_desc.p + (size_t)h->sh->frame_off_h[pairs[p].m_frame] * 32;
-    jobs[p].nt = h->sh->frame_F_h[pairs[p].m_frame];
-    jobs[p].keys = h->d_keys.p + (size_t)p * stride * 2;
-  }
-  h->d_jobs.scratch(Pa); h->d_pairs.scratch(Pa); h->d_nq.scratch(Pa);
-  h->d_iq.scratch(Pa * stride); h->d_im.scratch(Pa * stride);
-  h->d_kq.scratch(Pa * stride); h->d_km.scratch(Pa * stride);
-  h->d_M.scratch(Pa); h->d_N3.scratch(Pa); h->d_mono_ok.scratch(Pa); h->d_status.scratch(Pa);
-  h->d_out_mono.scratch(Pa); h->d_out_stereo.scratch(Pa);
-  h->d_a.scratch(Pa * stride * 3); h->d_b.scratch(Pa * stride * 3);
-  h->d_outR.scratch(Pa * 9); h->d_outT.scratch(Pa * 12);
+// Host-driven continuation for the problems the blind rounds did not finish (many skipped
+// samples, or max_ransac_iterations beyond the blind schedule): rounds are added until every
+// problem's loop has ended by its own limits, then the winners are selected again.  Synchronous.
+// Returns false if the item lists overflowed (the caller re-runs with h->item_cap raised).
+static bool finish_sac(kml_handle* h, bool mono, const SacArgs& a0) {
+  if (a0.P <= 0) return true;
   cudaStream_t s = h->stream;
-  KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(HamJob) * P, cudaMemcpyHostToDevice, s));
-  KML_CUDA(cudaMemcpyAsync(h->d_pairs.p, pairs.data(), sizeof(PairDesc) * P, cudaMemcpyHostToDevice, s));
-  KML_CUDA(cudaMemcpyAsync(h->d_nq.p, nq.data(), sizeof(int32_t) * P, cudaMemcpyHostToDevice, s));
-  KML_CUDA(cudaMemsetAsync(h->d_outR.p, 0, sizeof(double) * 9 * P, s));
-  KML_CUDA(cudaMemsetAsync(h->d_outT.p, 0, sizeof(double) * 12 * P, s));
-  // ---- computeMatchedIndices
-  KML_CUDA(cudaEventRecord(h->ev[2], s));
-  launch_hamming_jobs(h->d_jobs.p, P, h->prm.matcher_norm, s);
-  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
-  h->stats.kernel_launches += 2;
-  KML_CUDA(cudaEventRecord(h->ev[3], s));
-  // ---- geometricVerificationNister
-  GatherArgs g;
-  g.P = P; g.pairs = h->d_pairs.p; g.qb = qs.bear; g.qp = qs.pts; g.qF = qs.F;
-  g.sb = h->sh->s_bear.p; g.sp = h->sh->s_pts.p; g.s_off = h->sh->s_off.p;
-  g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
-  g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;  // N3 reused as "N" of the mono stage
-  launch_gather_bearings(g, s);
-  h->stats.kernel_launches += 1;
-  SacBufs mono{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono};
-  run_sac(h, true, P, h->d_a.p, h->d_b.p, h->d_M.p, stride, 0, mono, mask_words);
-  FinalizeArgs f;
-  f.P = P; f.mono_st = h->d_st_mono.p; f.mono_inl = h->d_inl_mono.p; f.M = h->d_M.p;
-  f.mono_model = h->d_best_mono.p;
-  f.min_inliers = h->prm.geometric_verification_min_inlier_count;
-  f.min_ratio_mono = h->prm.ransac_inlier_percentage_mono;
-  f.min_ratio_stereo = h->prm.geometric_verification_min_inlier_percentage;
-  f.mono_ok = h->d_mono_ok.p;
-  launch_mono_gate(f, s);
-  h->stats.kernel_launches += 1;
-  KML_CUDA(cudaEventRecord(h->ev[4], s));
-  // ---- recoverPose
-  StereoGatherArgs sg;
-  sg.g = g;
-  sg.mono_mask = h->d_mask_mono.p; sg.mask_words = mask_words; sg.mono_ok = h->d_mono_ok.p;
-  sg.kq = h->d_kq.p; sg.km = h->d_km.p;
-  launch_gather_points(sg, s);
-  h->stats.kernel_launches += 1;
-  SacBufs st3{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
-  run_sac(h, false, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, st3, mask_words);
-  f.st3 = h->d_st_stereo.p; f.inl3 = h->d_inl_stereo.p; f.N3 = h->d_N3.p; f.model3 = h->d_best_stereo.p;
-  f.status = h->d_status.p; f.out_mono_inl = h->d_out_mono.p; f.out_stereo_inl = h->d_out_stereo.p;
-  f.out_R = h->d_outR.p; f.out_T = h->d_outT.p;
-  launch_finalize(f, s);
-  h->stats.kernel_launches += 1;
-  KML_CUDA(cudaEventRecord(h->ev[5], s));
-  // ---- results back
-  std::vector<SacState> stm(P), sts(P);
-  std::vector<int32_t> n3(P);
-  KML_CUDA(cudaMemcpyAsync(n3.data(), h->d_N3.p, 4 * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->status.data(), h->d_status.p, 4 * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->M.data(), h->d_M.p, 4 * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->mono_inl.data(), h->d_out_mono.p, 4 * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->stereo_inl.data(), h->d_out_stereo.p, 4 * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->R.data(), h->d_outR.p, 72 * (size_t)P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(out->T.data(), h->d_outT.p, 96 * (size_t)P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(stm.data(), h->d_st_mono.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
-  KML_CUDA(cudaMemcpyAsync(sts.data(), h->d_st_stereo.p, sizeof(SacState) * P, cudaMemcpyDeviceToHost, s));
-  h->wait_stream();
-  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
-  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
-  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
-  uint64_t hm = 0, hs = 0, nmono_ok = 0, rm = 0, rs = 0;
-  bool exhausted = false;
-  for (int p = 0; p < P; ++p) {
-    hm += (uint64_t)stm[p].draws;
-    hs += (uint64_t)sts[p].draws;
-    rm += (uint64_t)stm[p].draws * (uint64_t)out->M[p];
-    rs += (uint64_t)sts[p].draws * (uint64_t)n3[p];
-    exhausted |= stm[p].exhausted || sts[p].exhausted;
-    nmono_ok += out->status[p] != 1;
+  SacArgs a = a0;
+  a.pending = h->d_fb_list.p + 3;
+  unsigned int flags[2] = {0, 0};  // overflow, pending
+  bool again = false;
+  for (int r = kSacRounds;; ++r) {
+    KML_CUDA(cudaMemsetAsync(a.pending, 0, sizeof(unsigned int), s));
+    launch_sac_pending(a, s);
+    h->stats.kernel_launches += 1;
+    KML_CUDA(cudaMemcpyAsync(&flags[0], a.overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    KML_CUDA(cudaMemcpyAsync(&flags[1], a.pending, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    KML_CUDA(cudaStreamSynchronize(s));
+    if (flags[0]) return false;
+    if (!flags[1]) break;
+    again = true;
+    h->stats.kernel_launches += mono ? launch_mono_round(a, r, s) : launch_stereo_round(a, r, s);
+    KML_CUDA(cudaGetLastError());
   }
-  if (getenv("KML_DEBUG_TIMING")) {  // consumed vs evaluated draws (SacState::r_begin ends at the last evaluated draw)
-    uint64_t em = 0, es = 0;
-    int hist[8] = {0};
-    for (int p = 0; p < P; ++p) {
-      em += (uint64_t)stm[p].r_begin;
-      es += (uint64_t)sts[p].r_begin;
-      const int d = stm[p].draws;
-      ++hist[d <= 16 ? 0 : d <= 32 ? 1 : d <= 64 ? 2 : d <= 128 ? 3 : d <= 256 ? 4 : d <= 512 ? 5 : d <= 1000 ? 6 : 7];
-    }
-    fprintf(stderr, "[kml] mono draws consumed %llu evaluated %llu; stereo consumed %llu evaluated %llu; "
-            "mono consumed histogram <=16:%d <=32:%d <=64:%d <=128:%d <=256:%d <=512:%d <=1000:%d more:%d\n",
-            (unsigned long long)hm, (unsigned long long)em, (unsigned long long)hs, (unsigned long long)es,
-            hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
+  if (again) {
+    a.pending = nullptr;
+    if (mono) launch_mono_select(a, s); else launch_stereo_select(a, s);
+    h->stats.kernel_launches += 1;
   }
-  h->stats.mono_hypotheses_last = hm;
-  h->stats.stereo_hypotheses_last = hs;
-  h->stats.mono_residuals_last = rm;
-  h->stats.stereo_residuals_last = rs;
-  h->stats.total_geom_verifications_mono += P;
-  h->stats.total_geometric_verifications += nmono_ok;
-  if (exhausted) throw std::runtime_error("pre-drawn sample stream exhausted (too many skipped samples)");
+  return true;
 }
 
-// ============================================================ batch query
+// prepare + enqueue + finish for the single-problem entry points (synchronous)
+static SacArgs run_sac_sync(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
+                            const int32_t* d_N, int stride, int full, SacBufs out, int mask_words) {
+  for (int attempt = 0;; ++attempt) {
+    SacArgs a = prepare_sac(h, mono, P, d_a, d_b, d_N, stride, full, out, mask_words, nullptr);
+    enqueue_sac(h, mono, a, out);
+    if (finish_sac(h, mono, a)) return a;
+    if (attempt >= 6) throw std::runtime_error("RANSAC item lists keep overflowing");
+    h->item_cap = std::max<size_t>(h->item_cap * 4, 65536);  // larger lists, same deterministic run
+  }
+}
+
+// =========================================================== batch query
+// device views of the resident databases, the entry -> pose / frame maps and the frame table
+static void sync_db_maps(kml_handle* h, RobotDb* db) {
+  const size_t n = db->n_entries();
+  if (db->synced == n && db->frame_patches.empty()) return;
+  cudaStream_t s = h->stream;
+  db->d_entry_pose.reserve(std::max<size_t>(n, 1), db->synced, s);
+  db->d_entry_frame.reserve(std::max<size_t>(n, 1), db->synced, s);
+  if (n > db->synced) {
+    KML_CUDA(cudaMemcpyAsync(db->d_entry_pose.p + db->synced, db->entry_to_pose.data() + db->synced,
+                             8 * (n - db->synced), cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(db->d_entry_frame.p + db->synced, db->entry_to_frame.data() + db->synced,
+                             4 * (n - db->synced), cudaMemcpyHostToDevice, s));
+  }
+  if (db->frame_patches.size() > 64) {
+    if (db->synced)
+      KML_CUDA(cudaMemcpyAsync(db->d_entry_frame.p, db->entry_to_frame.data(), 4 * db->synced, cudaMemcpyHostToDevice, s));
+  } else {
+    for (uint32_t e : db->frame_patches)
+      if (e < db->synced)
+        KML_CUDA(cudaMemcpyAsync(db->d_entry_frame.p + e, db->entry_to_frame.data() + e, 4, cudaMemcpyHostToDevice, s));
+  }
+  KML_CUDA(cudaStreamSynchronize(s));
+  db->synced = n;
+  db->frame_patches.clear();
+}
+
+static void ensure_frame_offsets(kml_handle* h) {
+  std::lock_guard<std::mutex> lk(h->sh->mu);
+  kml_shared& sh = *h->sh;
+  const size_t n = sh.frame_off_h.size();
+  if (sh.frames_synced == n && sh.s_off.p) return;
+  cudaStream_t s = h->stream;
+  sh.s_off.reserve(std::max<size_t>(n, 1), sh.frames_synced, s);
+  sh.s_F.reserve(std::max<size_t>(n, 1), sh.frames_synced, s);
+  if (n > sh.frames_synced) {
+    KML_CUDA(cudaMemcpyAsync(sh.s_off.p + sh.frames_synced, sh.frame_off_h.data() + sh.frames_synced,
+                             8 * (n - sh.frames_synced), cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaMemcpyAsync(sh.s_F.p + sh.frames_synced, sh.frame_F_h.data() + sh.frames_synced,
+                             4 * (n - sh.frames_synced), cudaMemcpyHostToDevice, s));
+  }
+  KML_CUDA(cudaStreamSynchronize(s));
+  sh.frames_synced = n;
+}
+
+// d_dbs: this handle's device array of database views, rebuilt when any add* moved the version
+static void ensure_views(kml_handle* h) {
+  kml_shared& sh = *h->sh;
+  uint64_t ver;
+  {
+    std::lock_guard<std::mutex> lk(sh.mu);
+    ver = sh.version;
+  }
+  if (h->views_version == ver && h->d_dbs.p) return;
+  std::vector<BowDb> views;
+  uint32_t max_entries = 1;
+  for (auto& kv : sh.dbs) {
+    views.push_back(db_view(h, kv.second.get()));
+    max_entries = std::max(max_entries, views.back().n_entries);
+  }
+  h->views_n_db = (int)views.size();
+  bow_tiling(max_entries, &h->views_tile, &h->views_n_tiles);
+  h->d_dbs.scratch(std::max<size_t>(views.size(), 1));
+  if (!views.empty()) {
+    KML_CUDA(cudaMemcpyAsync(h->d_dbs.p, views.data(), sizeof(BowDb) * views.size(), cudaMemcpyHostToDevice, h->stream));
+    KML_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  h->views_version = ver;
+}
+
+// Device pointers of the uploaded query batch inside kml_handle::d_in (fixed layout per batch
+// shape (B, F): a steady stream of equal-shaped batches never moves them)
+struct BatchIn {
+  uint64_t *q_robot, *q_pose;
+  int64_t *qoff, *poff;
+  uint32_t *qids, *pids;
+  float *qvals, *pvals;
+  uint8_t* desc;
+  double *bear, *pts;
+  size_t bytes;
+};
+static BatchIn batch_layout(uint8_t* base, int B, int F) {
+  BatchIn L;
+  size_t o = 0;
+  auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return base + at; };
+  const size_t w_cap = (size_t)B * kBowMaxWords;  // check_bow caps a vector at kBowMaxWords
+  L.q_robot = reinterpret_cast<uint64_t*>(take(8 * (size_t)B));
+  L.q_pose = reinterpret_cast<uint64_t*>(take(8 * (size_t)B));
+  L.qoff = reinterpret_cast<int64_t*>(take(8 * ((size_t)B + 1)));
+  L.poff = reinterpret_cast<int64_t*>(take(8 * ((size_t)B + 1)));
+  L.qids = reinterpret_cast<uint32_t*>(take(4 * w_cap));
+  L.pids = reinterpret_cast<uint32_t*>(take(4 * w_cap));
+  L.qvals = reinterpret_cast<float*>(take(4 * w_cap));
+  L.pvals = reinterpret_cast<float*>(take(4 * w_cap));
+  L.desc = take((size_t)B * F * 32 + 32);
+  L.bear = reinterpret_cast<double*>(take((size_t)B * F * 24 + 24));
+  L.pts = reinterpret_cast<double*>(take((size_t)B * F * 24 + 24));
+  L.bytes = o;
+  return L;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,
                         const int64_t* bow_off, const uint32_t* ids, const float* vals,
                         const int64_t* prev_off, const uint32_t* prev_ids, const float* prev_vals,
-                        const uint8_t* desc, const double* bearings, const double* points, int F) {
+                        const uint8_t* desc, const double* bearings, const double* points, int F,
+                        bool wait) {
   if (B < 0 || F < 0 || F > 65535) return fail(h, KML_ERR_ARG, "query_batch: bad B or F");
   if (B > 0 && (!q_robot || !q_pose || !bow_off || !prev_off || !desc || !bearings || !points))
     return fail(h, KML_ERR_ARG, "query_batch: null argument");
@@ -544,156 +579,334 @@ static int batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uin
     if (rc != KML_OK) return rc;
   }
   h->B = B; h->qF = F;
-  h->q_robot_h.assign(q_robot, q_robot + B);
-  h->q_pose_h.assign(q_pose, q_pose + B);
   if (B == 0) return KML_OK;
   const size_t nw = (size_t)bow_off[B], np = (size_t)prev_off[B];
   cudaStream_t s = h->stream;
-  h->d_qoff.scratch(B + 1); h->d_poff.scratch(B + 1);
-  // word buffers are sized for the largest batch of this shape (check_bow caps a vector at
-  // kBowMaxWords), not for this batch's word count: a steady stream of B-query batches then never
-  // reallocates.  cudaFree waits for the whole device, and with several lanes in a sharded run a
-  // lane stuck there behind another lane's pending all-gather can close a wait cycle across ranks.
-  const size_t w_cap = (size_t)B * kBowMaxWords;
-  h->d_qids.scratch(w_cap); h->d_qvals.scratch(w_cap);
-  h->d_pids.scratch(w_cap); h->d_pvals.scratch(w_cap);
-  h->d_qdesc.scratch((size_t)B * F * 32 + 32);
-  h->d_qbear.scratch((size_t)B * F * 3 + 3); h->d_qpts.scratch((size_t)B * F * 3 + 3);
-  KML_CUDA(cudaMemcpyAsync(h->d_qoff.p, bow_off, 8 * (B + 1), cudaMemcpyHostToDevice, s));
-  KML_CUDA(cudaMemcpyAsync(h->d_poff.p, prev_off, 8 * (B + 1), cudaMemcpyHostToDevice, s));
-  if (nw) {
-    KML_CUDA(cudaMemcpyAsync(h->d_qids.p, ids, 4 * nw, cudaMemcpyHostToDevice, s));
-    KML_CUDA(cudaMemcpyAsync(h->d_qvals.p, vals, 4 * nw, cudaMemcpyHostToDevice, s));
-  }
-  if (np) {
-    KML_CUDA(cudaMemcpyAsync(h->d_pids.p, prev_ids, 4 * np, cudaMemcpyHostToDevice, s));
-    KML_CUDA(cudaMemcpyAsync(h->d_pvals.p, prev_vals, 4 * np, cudaMemcpyHostToDevice, s));
-  }
-  if (F) {
-    KML_CUDA(cudaMemcpyAsync(h->d_qdesc.p, desc, (size_t)B * F * 32, cudaMemcpyHostToDevice, s));
-    KML_CUDA(cudaMemcpyAsync(h->d_qbear.p, bearings, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
-    KML_CUDA(cudaMemcpyAsync(h->d_qpts.p, points, (size_t)B * F * 24, cudaMemcpyHostToDevice, s));
-  }
+  // The batch lives in ONE device buffer with a fixed layout per (B, F): sized for the largest
+  // batch of this shape, not for this batch's word count, so a steady stream of B-query batches
+  // never reallocates (cudaFree waits for the whole device, i.e. for every other lane's kernels
+  // and pending collectives).  Arrays the caller holds in pinned memory (kml_host_alloc) are
+  // copied from where they are; pageable ones are staged through the handle's pinned buffer, so
+  // every H2D copy is asynchronous to the host and to the other lanes.
+  const BatchIn L0 = batch_layout(nullptr, B, F);
+  h->d_in.scratch(L0.bytes);
+  const BatchIn D = batch_layout(h->d_in.p, B, F);
+  h->h_in.scratch(L0.bytes);
+  const BatchIn H = batch_layout(h->h_in.p, B, F);
+  auto put = [&](void* dev, void* stage, const void* src, size_t bytes) {
+    if (!bytes) return;
+    const void* from = src;
+    if (!is_pinned(src)) {
+      memcpy(stage, src, bytes);
+      from = stage;
+    }
+    KML_CUDA(cudaMemcpyAsync(dev, from, bytes, cudaMemcpyHostToDevice, s));
+  };
+  // the staging buffer may still feed the previous upload of this lane
   KML_CUDA(cudaStreamSynchronize(s));
+  put(D.q_robot, H.q_robot, q_robot, 8 * (size_t)B);
+  put(D.q_pose, H.q_pose, q_pose, 8 * (size_t)B);
+  put(D.qoff, H.qoff, bow_off, 8 * ((size_t)B + 1));
+  put(D.poff, H.poff, prev_off, 8 * ((size_t)B + 1));
+  put(D.qids, H.qids, ids, 4 * nw);
+  put(D.qvals, H.qvals, vals, 4 * nw);
+  put(D.pids, H.pids, prev_ids, 4 * np);
+  put(D.pvals, H.pvals, prev_vals, 4 * np);
+  put(D.desc, H.desc, desc, (size_t)B * F * 32);
+  put(D.bear, H.bear, bearings, (size_t)B * F * 24);
+  put(D.pts, H.pts, points, (size_t)B * F * 24);
+  if (wait) KML_CUDA(cudaStreamSynchronize(s));  // the caller may reuse its buffers on return
   return KML_OK;
 }
 
-struct BatchRecs {
-  std::vector<kml_result> recs;   // [B][cap]
-  std::vector<int32_t> counts;    // [B]
+// layout of one rank's record block: kml_result[B][cap] | int32 counts[B] | int32 error | pad
+struct BlockLayout {
+  size_t rec_bytes, counts_off, err_off, blk;
+};
+static BlockLayout block_layout(int B, int cap) {
+  BlockLayout L;
+  L.rec_bytes = sizeof(kml_result) * (size_t)B * cap;
+  L.counts_off = L.rec_bytes;
+  L.err_off = L.counts_off + sizeof(int32_t) * (size_t)B;
+  L.blk = (L.err_off + sizeof(int32_t) + 255) / 256 * 256;
+  return L;
+}
+
+// The whole query pipeline of the uploaded batch, enqueued on the handle's stream without a host
+// synchronisation: BoW scoring -> candidate selection -> kNN + Lowe -> mono 5-pt RANSAC -> stereo
+// Arun RANSAC -> records written to `blk` (this rank's block of the all-gather buffer).
+struct BatchPlan {
+  int B, K, cap, P, stride, mask_words;
+  SacArgs mono, stereo;
+  FinalizeArgs fin;
+  StereoGatherArgs sg;
 };
 
-static int batch_run(kml_handle* h, int cap, BatchRecs* br) {
+static void enqueue_tail(kml_handle* h, BatchPlan* pl, bool from_mono_select);
+
+static void batch_enqueue(kml_handle* h, int cap, uint8_t* blk, BatchPlan* pl) {
   const int B = h->B;
-  br->recs.assign((size_t)B * cap, kml_result{});
-  br->counts.assign(B, 0);
-  if (B == 0) return KML_OK;
-  struct PoliteScope {  // batches wait without spinning; single queries keep the low-latency spin
-    kml_handle* h;
-    PoliteScope(kml_handle* hh, bool on) : h(hh) { h->polite_wait = on; }
-    ~PoliteScope() { h->polite_wait = false; }
-  } scope(h, B >= 16);
-  struct PairCapScope {  // verification scratch sized for the most pairs a batch of this shape can yield
-    kml_handle* h;
-    PairCapScope(kml_handle* hh, int n) : h(hh) { h->pair_cap = n; }
-    ~PairCapScope() { h->pair_cap = 0; }
-  } cap_scope(h, B * std::max(0, std::min(h->prm.top_k_verify, cap)));
-  KML_CUDA(cudaEventRecord(h->ev[6], h->stream));
-  std::vector<RobotDb*> dbs;
-  for (auto& kv : h->sh->dbs) dbs.push_back(kv.second.get());
-  BowOut bo;
-  const auto tb0 = std::chrono::steady_clock::now();
-  run_bow(h, dbs, B, h->d_qoff.p, h->d_qids.p, h->d_qvals.p, h->d_poff.p, h->d_pids.p,
-          h->d_pvals.p, h->prm.max_db_results, nullptr, &bo);
-  const auto tb1 = std::chrono::steady_clock::now();
-  // candidate selection (detectLoop = detectLoopWithRobot over every robot DB)
-  const int K = std::min(h->prm.top_k_verify, cap);
-  std::vector<PairDesc> pairs;
-  std::vector<int> pair_rec;  // pair -> record index
-  std::vector<Cand> cands;
-  auto before = [](const Cand& x, const Cand& y) {  // (robot, pose) is unique: a total order
-    if (x.score != y.score) return x.score > y.score;
-    if (x.robot != y.robot) return x.robot < y.robot;
-    return x.pose < y.pose;
-  };
-  std::vector<Cand> found;
-  for (int b = 0; b < B; ++b) {
-    // the K best survivors of every database, kept as a sorted insertion list: most of the
-    // up to n_db * max_db_results survivors lose against the current K-th with one comparison
-    cands.clear();
-    size_t survivors = 0;
-    for (int d = 0; d < bo.n_db; ++d) {
-      const size_t l = (size_t)b * bo.n_db + d;
-      found.clear();
-      select_candidates(h, dbs[d], h->q_robot_h[b], h->q_pose_h[b], bo.nss[b],
-                        &bo.entry[l * bo.K], &bo.score[l * bo.K], bo.count[l], &found);
-      survivors += found.size();
-      for (const Cand& c : found) {
-        if (K <= 0 || ((int)cands.size() == K && !before(c, cands.back()))) continue;
-        size_t pos = cands.size();
-        if ((int)cands.size() < K) cands.push_back(c); else pos = cands.size() - 1;
-        while (pos > 0 && before(c, cands[pos - 1])) { cands[pos] = cands[pos - 1]; --pos; }
-        cands[pos] = c;
-      }
-    }
-    h->stats.total_bow_matches += survivors;
-    const int nv = (int)cands.size();
-    br->counts[b] = nv;
-    for (int i = 0; i < nv; ++i) {
-      kml_result& r = br->recs[(size_t)b * cap + i];
-      r.q_robot = h->q_robot_h[b]; r.q_pose = h->q_pose_h[b];
-      r.m_robot = cands[i].robot; r.m_pose = cands[i].pose;
-      r.norm_bow_score = cands[i].score;
-      int32_t* slot = &cands[i].db->entry_to_frame[cands[i].entry];
-      int32_t fidx = __atomic_load_n(slot, __ATOMIC_RELAXED);
-      if (fidx < 0) {
-        auto fit = h->sh->frames.find(RobotPoseId(cands[i].robot, cands[i].pose));
-        if (fit == h->sh->frames.end()) { r.status = 3; continue; }
-        fidx = fit->second.index;
-        __atomic_store_n(slot, fidx, __ATOMIC_RELAXED);
-      }
-      pairs.push_back({b, fidx});
-      pair_rec.push_back(b * cap + i);
-    }
+  const int K = std::max(0, std::min(h->prm.top_k_verify, cap));
+  const int P = B * K;
+  const BlockLayout bl = block_layout(B, cap);
+  cudaStream_t s = h->stream;
+  pl->B = B; pl->K = K; pl->cap = cap; pl->P = P;
+  ensure_frame_offsets(h);
+  ensure_views(h);
+  const int n_db = h->views_n_db;
+  const BatchIn D = batch_layout(h->d_in.p, B, h->qF);
+  kml_result* d_recs = reinterpret_cast<kml_result*>(blk);
+  int32_t* d_counts = reinterpret_cast<int32_t*>(blk + bl.counts_off);
+  h->d_stats.scratch(1);
+  KML_CUDA(cudaEventRecord(h->ev[6], s));
+  KML_CUDA(cudaMemsetAsync(blk, 0, bl.blk, s));
+  KML_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(BatchStats), s));
+  // ---- detectLoop: NSS factor + DBoW2 query against every resident database
+  const int n_tiles = h->views_n_tiles, Kdb = h->prm.max_db_results;
+  const size_t nlist = (size_t)B * std::max(n_db, 1) * n_tiles;
+  h->d_bow_entry.scratch(nlist * Kdb);
+  h->d_bow_score.scratch(nlist * Kdb);
+  h->d_bow_count.scratch(nlist);
+  h->d_nss.scratch(B);
+  KML_CUDA(cudaMemsetAsync(h->d_nss.p, 0, sizeof(double) * B, s));
+  KML_CUDA(cudaEventRecord(h->ev[0], s));
+  if (n_db > 0) {
+    BowArgs a;
+    a.dbs = h->d_dbs.p; a.n_db = n_db; a.B = B;
+    a.q_off = D.qoff; a.q_ids = D.qids; a.q_vals = D.qvals;
+    a.p_off = D.poff; a.p_ids = D.pids; a.p_vals = D.pvals;
+    a.K = Kdb; a.max_id = nullptr; a.tile_entries = h->views_tile; a.n_tiles = n_tiles;
+    a.out_entry = h->d_bow_entry.p; a.out_score = h->d_bow_score.p; a.out_count = h->d_bow_count.p;
+    a.nss = h->d_nss.p;
+    a.postings_touched = &h->d_stats.p->postings;
+    launch_bow(a, s);
+    h->stats.kernel_launches += 1;
   }
-  QuerySide qs{h->d_qdesc.p, h->d_qbear.p, h->d_qpts.p, h->qF};
-  VerifyOut vo;
-  const auto tb2 = std::chrono::steady_clock::now();
-  verify_pairs(h, pairs, qs, &vo);
-  const auto tb3 = std::chrono::steady_clock::now();
-  for (size_t p = 0; p < pairs.size(); ++p) {
-    kml_result& r = br->recs[pair_rec[p]];
-    r.n_matches = vo.M[p];
-    r.status = vo.status[p];
-    r.mono_inliers = vo.mono_inl[p];
-    r.stereo_inliers = vo.stereo_inl[p];
-    memcpy(r.R_mono, &vo.R[p * 9], 72);
-    memcpy(r.T, &vo.T[p * 12], 96);
+  KML_CUDA(cudaEventRecord(h->ev[1], s));
+  // ---- candidate selection, records, pair slots p = b*K + i
+  const int stride = std::max(h->qF, 8);
+  const int mask_words = (stride + 31) / 32;
+  pl->stride = stride; pl->mask_words = mask_words;
+  const size_t Pa = (size_t)std::max(P, 1);
+  h->d_keys.scratch(Pa * stride * 2);
+  h->d_jobs.scratch(Pa); h->d_pairs.scratch(Pa); h->d_nq.scratch(Pa);
+  h->d_iq.scratch(Pa * stride); h->d_im.scratch(Pa * stride);
+  h->d_kq.scratch(Pa * stride); h->d_km.scratch(Pa * stride);
+  h->d_M.scratch(Pa); h->d_N3.scratch(Pa); h->d_mono_ok.scratch(Pa);
+  h->d_a.scratch(Pa * stride * 3); h->d_b.scratch(Pa * stride * 3);
+  SelectArgs sa;
+  sa.dbs = h->d_dbs.p; sa.n_db = n_db; sa.B = B; sa.n_tiles = n_tiles; sa.Kdb = Kdb;
+  sa.bow_entry = h->d_bow_entry.p; sa.bow_score = h->d_bow_score.p; sa.bow_count = h->d_bow_count.p;
+  sa.nss = h->d_nss.p; sa.q_robot = D.q_robot; sa.q_pose = D.q_pose;
+  sa.alpha = h->prm.alpha; sa.min_nss = h->prm.min_nss_factor;
+  sa.inter_robot_only = h->prm.inter_robot_only; sa.dist_local = h->prm.dist_local;
+  sa.K = K; sa.cap = cap;
+  sa.s_desc = h->sh->s_desc.p; sa.s_off = h->sh->s_off.p; sa.s_F = h->sh->s_F.p;
+  sa.q_desc = D.desc; sa.qF = h->qF;
+  sa.recs = d_recs; sa.counts = d_counts;
+  sa.pairs = h->d_pairs.p; sa.jobs = h->d_jobs.p; sa.nq = h->d_nq.p; sa.keys = h->d_keys.p; sa.key_stride = stride;
+  sa.stats = h->d_stats.p;
+  launch_select(sa, s);
+  h->stats.kernel_launches += 1;
+  if (P == 0) {
+    for (int e = 2; e <= 5; ++e) KML_CUDA(cudaEventRecord(h->ev[e], s));
+    KML_CUDA(cudaEventRecord(h->ev[7], s));
+    KML_CUDA(cudaGetLastError());
+    return;
   }
-  KML_CUDA(cudaEventRecord(h->ev[7], h->stream));
-  h->wait_stream();
+  // ---- computeMatchedIndices
+  KML_CUDA(cudaEventRecord(h->ev[2], s));
+  launch_hamming_jobs(h->d_jobs.p, P, h->prm.matcher_norm, s);
+  launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
+  h->stats.kernel_launches += 2;
+  KML_CUDA(cudaEventRecord(h->ev[3], s));
+  // ---- geometricVerificationNister
+  GatherArgs g;
+  g.P = P; g.pairs = h->d_pairs.p; g.qb = D.bear; g.qp = D.pts; g.qF = h->qF;
+  g.sb = h->sh->s_bear.p; g.sp = h->sh->s_pts.p; g.s_off = h->sh->s_off.p;
+  g.iq = h->d_iq.p; g.im = h->d_im.p; g.M = h->d_M.p; g.stride = stride;
+  g.a = h->d_a.p; g.b = h->d_b.p; g.N = h->d_N3.p;  // N3 reused as "N" of the mono stage
+  launch_gather_bearings(g, s);
+  h->stats.kernel_launches += 1;
+  SacBufs mono{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono};
+  pl->mono = prepare_sac(h, true, P, h->d_a.p, h->d_b.p, h->d_M.p, stride, 0, mono, mask_words, &h->d_stats.p->pending_m);
+  SacBufs st3{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  pl->stereo = prepare_sac(h, false, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, st3, mask_words, &h->d_stats.p->pending_s);
+  enqueue_sac(h, true, pl->mono, mono);
+  FinalizeArgs& f = pl->fin;
+  f.P = P; f.mono_st = h->d_st_mono.p; f.mono_inl = h->d_inl_mono.p; f.M = h->d_M.p;
+  f.mono_model = h->d_best_mono.p;
+  f.min_inliers = h->prm.geometric_verification_min_inlier_count;
+  f.min_ratio_mono = h->prm.ransac_inlier_percentage_mono;
+  f.min_ratio_stereo = h->prm.geometric_verification_min_inlier_percentage;
+  f.mono_ok = h->d_mono_ok.p;
+  f.st3 = h->d_st_stereo.p; f.inl3 = h->d_inl_stereo.p; f.N3 = h->d_N3.p; f.model3 = h->d_best_stereo.p;
+  f.pairs = h->d_pairs.p; f.K = K; f.cap = cap; f.recs = d_recs; f.stats = h->d_stats.p;
+  pl->sg.g = g;
+  pl->sg.mono_mask = h->d_mask_mono.p; pl->sg.mask_words = mask_words; pl->sg.mono_ok = h->d_mono_ok.p;
+  pl->sg.kq = h->d_kq.p; pl->sg.km = h->d_km.p;
+  enqueue_tail(h, pl, false);
+}
+
+// mono acceptance gate -> recoverPose -> records.  Also the re-run after a host-driven
+// continuation of the mono rounds (from_mono_select: the winners' inlier sets are selected again).
+static void enqueue_tail(kml_handle* h, BatchPlan* pl, bool redo) {
+  cudaStream_t s = h->stream;
+  if (redo)  // the counters the first pass added for these stages, and its pending flags
+    KML_CUDA(cudaMemsetAsync(&h->d_stats.p->mono_ok, 0, sizeof(BatchStats) - offsetof(BatchStats, mono_ok), s));
+  launch_mono_gate(pl->fin, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaEventRecord(h->ev[4], s));
+  launch_gather_points(pl->sg, s);
+  h->stats.kernel_launches += 1;
+  SacBufs st3{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  enqueue_sac(h, false, pl->stereo, st3);
+  if (redo) finish_sac(h, false, pl->stereo);
+  launch_finalize(pl->fin, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaEventRecord(h->ev[5], s));
+  KML_CUDA(cudaEventRecord(h->ev[7], s));
+  KML_CUDA(cudaGetLastError());
+}
+
+static void batch_stats_to_host(kml_handle* h, const BatchStats& st) {
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_bow, h->ev[0], h->ev[1]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_match, h->ev[2], h->ev[3]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_mono, h->ev[3], h->ev[4]));
+  KML_CUDA(cudaEventElapsedTime(&h->stats.ms_stereo, h->ev[4], h->ev[5]));
   KML_CUDA(cudaEventElapsedTime(&h->stats.ms_total, h->ev[6], h->ev[7]));
-  if (getenv("KML_DEBUG_TIMING")) {
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, h->ev[6], h->ev[0]);
-    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&c, h->ev[5], h->ev[7]);
-    fprintf(stderr, "[kml] gaps: before bow %.3f ms, bow->match %.3f ms, after stereo %.3f ms\n", a, b, c);
-    auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
-      return std::chrono::duration<double, std::milli>(y - x).count();
-    };
-    fprintf(stderr, "[kml] host: run_bow (launch + wait + copy-out) %.3f ms, candidate selection %.3f ms, "
-            "verify_pairs (setup + launches + wait + copy-out) %.3f ms, record assembly %.3f ms\n",
-            ms(tb0, tb1), ms(tb1, tb2), ms(tb2, tb3), ms(tb3, std::chrono::steady_clock::now()));
+  h->stats.bow_postings_last = st.postings;
+  h->stats.pairs_last = st.pairs;
+  h->stats.mono_hypotheses_last = st.hyp_m;
+  h->stats.stereo_hypotheses_last = st.hyp_s;
+  h->stats.mono_residuals_last = st.res_m;
+  h->stats.stereo_residuals_last = st.res_s;
+  h->stats.total_bow_matches += st.survivors;
+  h->stats.total_geom_verifications_mono += st.pairs;
+  h->stats.total_geometric_verifications += st.mono_ok;
+  if (getenv("KML_DEBUG_TIMING"))
+    fprintf(stderr, "[kml] pairs %llu; mono draws consumed %llu evaluated %llu; stereo consumed %llu evaluated %llu; "
+            "ms bow %.3f match %.3f mono %.3f stereo %.3f total %.3f\n",
+            st.pairs, st.hyp_m, st.eval_m, st.hyp_s, st.eval_s, h->stats.ms_bow, h->stats.ms_match,
+            h->stats.ms_mono, h->stats.ms_stereo, h->stats.ms_total);
+}
+
+struct PoliteScope {  // batches wait without spinning; single queries keep the low-latency spin
+  kml_handle* h;
+  PoliteScope(kml_handle* hh, bool on) : h(hh) { h->polite_wait = on; }
+  ~PoliteScope() { h->polite_wait = false; }
+};
+
+// flag values of a record block (BlockLayout::err_off)
+enum { kBlkOk = 0, kBlkRedo = 1, kBlkFailed = 2 };
+
+// Runs the uploaded batch.  Common case: ONE enqueue of the whole pipeline (plus, when sharded,
+// the in-place ncclAllGather of the record blocks and the device merge), one D2H of the final
+// records into pinned memory, one host wait.  Every rank's block carries a flag word, so all
+// ranks take the same decision after the exchange: kBlkRedo = some rank has RANSAC problems the
+// blind rounds did not finish (or overflowed item lists) — it continues them from the host and
+// the exchange is repeated; kBlkFailed = some rank hit an error before the exchange — every
+// rank still enters the collective (nobody is left waiting) and every rank returns the error.
+static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int32_t* counts) {
+  const int B = h->B;
+  if (B == 0) return KML_OK;
+  if (h->prm.top_k_verify > kSelMaxK)
+    return fail(h, KML_ERR_CAPACITY, "query_batch: top_k_verify must be <= 128");
+  PoliteScope scope(h, B >= 16);
+  const int nr = sharded ? comm_nranks(h) : 1;
+  const int rank = sharded ? comm_rank(h) : 0;
+  const BlockLayout bl = block_layout(B, cap);
+  cudaStream_t s = h->stream;
+  h->d_blocks.scratch(bl.blk * nr);
+  if (nr > 1) h->d_merged.scratch(bl.blk);
+  h->h_recs.scratch(bl.blk);
+  h->h_stats.scratch(1);
+  h->d_stats.scratch(1);
+  uint8_t* blk = h->d_blocks.p + bl.blk * rank;
+  const bool dbg = getenv("KML_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  BatchPlan pl;
+  std::string local_err;
+  int local_rc = KML_OK;
+  bool enqueued = false;
+  for (int attempt = 0;; ++attempt) {
+    // ---- local pipeline (first pass) or the continuation the previous exchange asked for
+    if (local_rc == KML_OK) {
+      try {
+        if (!enqueued) {
+          batch_enqueue(h, cap, blk, &pl);
+          enqueued = true;
+        } else {
+          const BatchStats st = *h->h_stats.p;
+          unsigned int overflow = st.item_overflow;
+          if (!overflow && (st.pending_m || st.pending_s)) {
+            if (!finish_sac(h, true, pl.mono)) overflow = 1;
+            else enqueue_tail(h, &pl, true);
+          }
+          if (overflow) {  // larger item lists, same deterministic run from the top
+            if (attempt >= 6) throw std::runtime_error("query_batch: RANSAC item lists keep overflowing");
+            h->item_cap = std::max<size_t>(h->item_cap * 4, 65536);
+            batch_enqueue(h, cap, blk, &pl);
+          }
+        }
+        if (pl.P > 0) launch_block_flags(h->d_stats.p, pl.mono.overflow, reinterpret_cast<int32_t*>(blk + bl.err_off), s);
+        h->stats.kernel_launches += pl.P > 0;
+        KML_CUDA(cudaGetLastError());
+      } catch (const kml::CudaError& e) {
+        local_err = e.what(); local_rc = KML_ERR_CUDA; cudaGetLastError();
+      } catch (const std::exception& e) {
+        local_err = e.what(); local_rc = KML_ERR_ARG;
+      }
+    }
+    if (local_rc != KML_OK) {  // tell the peers; best effort if the device itself is gone
+      const int32_t flag = kBlkFailed;
+      cudaMemcpyAsync(blk + bl.err_off, &flag, sizeof(flag), cudaMemcpyHostToDevice, s);
+      cudaStreamSynchronize(s);
+      cudaGetLastError();
+      if (nr == 1) { h->err = local_err; return local_rc; }
+    }
+    // ---- exchange + merge (sharded), final records to pinned memory
+    const uint8_t* final_blk = blk;
+    if (nr > 1) {
+      const int rc = comm_allgather(h, blk, h->d_blocks.p, bl.blk);
+      if (rc != KML_OK) return rc;
+      MergeArgs m;
+      m.base = h->d_blocks.p; m.blk_stride = bl.blk; m.counts_off = bl.counts_off; m.err_off = bl.err_off;
+      m.nranks = nr; m.B = B; m.cap_in = cap; m.cap = cap;
+      m.out = reinterpret_cast<kml_result*>(h->d_merged.p);
+      m.counts = reinterpret_cast<int32_t*>(h->d_merged.p + bl.counts_off);
+      m.err_out = reinterpret_cast<int32_t*>(h->d_merged.p + bl.err_off);
+      KML_CUDA(cudaMemsetAsync(h->d_merged.p, 0, bl.blk, s));
+      launch_merge(m, s);
+      h->stats.kernel_launches += 1;
+      final_blk = h->d_merged.p;
+    }
+    KML_CUDA(cudaMemcpyAsync(h->h_recs.p, final_blk, bl.err_off + sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    KML_CUDA(cudaMemcpyAsync(h->h_stats.p, h->d_stats.p, sizeof(BatchStats), cudaMemcpyDeviceToHost, s));
+    const int wrc = nr > 1 ? comm_wait(h) : (h->wait_stream(), KML_OK);
+    if (wrc != KML_OK) return wrc;
+    const int32_t flag = *reinterpret_cast<const int32_t*>(h->h_recs.p + bl.err_off);
+    if (flag == kBlkOk) break;
+    if (flag >= kBlkFailed || local_rc != KML_OK) {
+      h->err = local_rc != KML_OK ? local_err : "query_batch_sharded: another rank failed before the exchange";
+      return local_rc != KML_OK ? local_rc : KML_ERR_NCCL;
+    }
+    if (attempt >= 40) return fail(h, KML_ERR_CUDA, "query_batch: RANSAC continuation did not converge");
+  }
+  batch_stats_to_host(h, *h->h_stats.p);
+  memcpy(out, h->h_recs.p, bl.rec_bytes);
+  memcpy(counts, h->h_recs.p + bl.counts_off, sizeof(int32_t) * (size_t)B);
+  if (dbg) {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[kml r%d] batch of %d: host wall %.3f ms (device total %.3f ms)\n", rank, B, ms, h->stats.ms_total);
   }
   return KML_OK;
 }
 
-static void copy_out(const BatchRecs& br, int B, int cap, kml_result* out, int32_t* counts) {
-  if (B == 0) return;
-  memcpy(out, br.recs.data(), sizeof(kml_result) * (size_t)B * cap);
-  memcpy(counts, br.counts.data(), sizeof(int32_t) * B);
-}
+// Query-side frame arrays of a single-pair verification call
+struct QuerySide {
+  const uint8_t* desc; const double* bear; const double* pts; int F;  // [slots][F][...]
+};
 
 // single stored frame as the "query side"
 static bool stored_query_side(kml_handle* h, uint64_t robot, uint64_t pose, QuerySide* qs) {
@@ -757,7 +970,7 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
     launch_gather_points(sg, s);
   }
   h->stats.kernel_launches += 1;
-  run_sac(h, mono, 1, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, bufs, mask_words);
+  run_sac_sync(h, mono, 1, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, bufs, mask_words);
   SacState st;
   int32_t N = 0, ninl = 0;
   std::vector<uint32_t> mask(mask_words);
@@ -771,7 +984,7 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
     KML_CUDA(cudaMemcpyAsync(km.data(), h->d_km.p, 2 * stride, cudaMemcpyDeviceToHost, s));
   }
   KML_CUDA(cudaStreamSynchronize(s));
-  if (st.exhausted) return fail(h, KML_ERR_STREAM_EXHAUSTED, "pre-drawn sample stream exhausted");
+  if (st.exhausted) return fail(h, KML_ERR_STREAM_EXHAUSTED, "pre-drawn sample stream exhausted");  // cannot happen: the stream covers the loop's own limits
   *n_valid_out = N;
   if (N < (mono ? 8 : 3)) return KML_TOO_FEW_POINTS;
   if (st.best_draw < 0) return KML_RANSAC_FAIL;
@@ -1045,18 +1258,14 @@ int kml_query_batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const 
                            const double* points, int F) {
   KML_API_BEGIN(h)
   return batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
-                      desc, bearings, points, F);
+                      desc, bearings, points, F, true);
   KML_API_END(h)
 }
 
 int kml_query_batch_run(kml_handle* h, kml_result* out, int cap, int32_t* counts) {
   KML_API_BEGIN(h)
   if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "query_batch_run: bad output");
-  BatchRecs br;
-  int rc = batch_run(h, cap, &br);
-  if (rc != KML_OK) return rc;
-  copy_out(br, h->B, cap, out, counts);
-  return KML_OK;
+  return batch_run(h, cap, false, out, counts);
   KML_API_END(h)
 }
 
@@ -1066,15 +1275,15 @@ int kml_query_batch(kml_handle* h, int B, const uint64_t* q_robot, const uint64_
                     const uint8_t* desc, const double* bearings, const double* points, int F,
                     kml_result* out, int cap, int32_t* counts) {
   KML_API_BEGIN(h)
-  int rc = batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
-                        desc, bearings, points, F);
-  if (rc != KML_OK) return rc;
   if (cap <= 0 || (B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "query_batch: bad output");
-  BatchRecs br;
-  rc = batch_run(h, cap, &br);
+  // the copies are only enqueued here: batch_run's single wait at the end covers them, and the
+  // caller's buffers are not read after this function returns
+  int rc = batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
+                        desc, bearings, points, F, false);
   if (rc != KML_OK) return rc;
-  copy_out(br, B, cap, out, counts);
-  return KML_OK;
+  rc = batch_run(h, cap, false, out, counts);
+  if (rc != KML_OK) cudaStreamSynchronize(h->stream);  // an early error return must not leave copies in flight
+  return rc;
   KML_API_END(h)
 }
 
@@ -1140,49 +1349,33 @@ int kml_merge_shard_records(const void* blocks, int nranks, int B, int cap_in, i
   return KML_OK;
 }
 
-// Sharded query: every rank runs the (identical) uploaded batch against its
-// own robot databases, then ONE ncclAllGather merges the fixed-size record
-// blocks; every rank re-ranks the union per query and keeps the best `cap`.
+// Sharded query: every rank runs the (identical) uploaded batch against its own robot databases
+// and writes its records into its block of the all-gather buffer; ONE in-place ncclAllGather
+// exchanges the blocks and a device kernel re-ranks the union per query (batch_run).
 int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* counts) {
   KML_API_BEGIN(h)
   if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "bad output");
-  const int B = h->B;
-  BatchRecs br;
-  const bool dbg = getenv("KML_DEBUG_TIMING") != nullptr;
-  const auto t0 = std::chrono::steady_clock::now();
-  int rc = batch_run(h, cap, &br);
-  if (rc != KML_OK) return rc;
-  const auto t1 = std::chrono::steady_clock::now();
-  const int nr = comm_nranks(h);
-  if (nr == 1) { copy_out(br, B, cap, out, counts); return KML_OK; }
-  if (B == 0) return KML_OK;
-  const size_t rec_bytes = sizeof(kml_result) * (size_t)B * cap;
-  const size_t blk = rec_bytes + sizeof(int32_t) * (size_t)B;
-  const size_t blk_al = (blk + 255) / 256 * 256;
-  h->d_scratch.scratch(blk_al);
-  h->d_scratch2.scratch(blk_al * nr);
-  h->h_stage.scratch(blk_al * nr);
-  memcpy(h->h_stage.p, br.recs.data(), rec_bytes);
-  memcpy(h->h_stage.p + rec_bytes, br.counts.data(), sizeof(int32_t) * B);
-  KML_CUDA(cudaMemcpyAsync(h->d_scratch.p, h->h_stage.p, blk, cudaMemcpyHostToDevice, h->stream));
-  rc = comm_allgather(h, h->d_scratch.p, h->d_scratch2.p, blk_al);
-  if (rc != KML_OK) return rc;
-  KML_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_scratch2.p, blk_al * nr, cudaMemcpyDeviceToHost, h->stream));
-  h->polite_wait = B >= 16;
-  h->wait_stream();
-  h->polite_wait = false;
-  const auto t2 = std::chrono::steady_clock::now();
-  merge_rank_blocks(h->h_stage.p, blk_al, rec_bytes, nr, B, cap, cap, out, counts);
-  if (dbg) {
-    const auto t3 = std::chrono::steady_clock::now();
-    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-      return std::chrono::duration<double, std::milli>(b - a).count();
-    };
-    fprintf(stderr, "[kml r%d] sharded batch: local query %.3f ms, all-gather + copies %.3f ms, merge %.3f ms\n",
-            comm_rank(h), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  return batch_run(h, cap, true, out, counts);
+  KML_API_END(h)
+}
+
+// Pinned host memory for the caller's batch buffers (and result block): arrays allocated here are
+// copied to the device from where they are, without the staging copy pageable memory needs.
+int kml_host_alloc(size_t bytes, void** out) {
+  if (!out) return KML_ERR_ARG;
+  *out = nullptr;
+  if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return KML_ERR_CUDA;
   }
   return KML_OK;
-  KML_API_END(h)
+}
+int kml_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return KML_ERR_CUDA;
+  }
+  return KML_OK;
 }
 
 // ------------------------------------------------- batched RANSAC (C4 etc.)
@@ -1205,7 +1398,7 @@ static int ransac_batch(kml_handle* h, bool mono, int P, int N, const double* a,
   SacBufs bufs = mono ? SacBufs{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono}
                       : SacBufs{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
   KML_CUDA(cudaEventRecord(h->ev[2], s));
-  run_sac(h, mono, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, full, bufs, mask_words);
+  run_sac_sync(h, mono, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, full, bufs, mask_words);
   KML_CUDA(cudaEventRecord(h->ev[3], s));
   std::vector<SacState> st(P);
   std::vector<uint32_t> mask((size_t)P * mask_words);

@@ -35,24 +35,9 @@ using geom::V3;
 // --------------------------------------------------------------- sampling
 // SampleConsensusProblem::drawIndexSample: for i<S swap(shuffled[i],
 // shuffled[i + rnd() % (N-i)]); rnd() = mt19937()>>1 (pre-drawn, host).
-// Draws [first, last) are appended to out[draw][S]; the shuffle state persists.
-template <int S>
-__device__ void draw_samples(uint16_t* perm_s, int N, const uint32_t* __restrict__ raw, int first,
-                             int last, uint16_t* out) {
-  for (int gd = first; gd < last; ++gd) {
-    for (int i = 0; i < S; ++i) {
-      const uint32_t r = raw[gd * S + i];
-      const int j = i + (int)(r % (uint32_t)(N - i));
-      const uint16_t t = perm_s[i];
-      perm_s[i] = perm_s[j];
-      perm_s[j] = t;
-    }
-    for (int i = 0; i < S; ++i) out[(size_t)gd * S + i] = perm_s[i];
-  }
-}
-
 // Warp version: the modulo of every (draw, i) is independent of the shuffle state, so all lanes
 // compute them (jrel_s, at most kRoundCap*S entries) and lane 0 is left with the swaps.
+// out[slot][S]: the samples of the round's draws [first, last), slot = draw - first.
 template <int S>
 __device__ void draw_samples_warp(uint16_t* perm_s, uint16_t* jrel_s, int N, const uint32_t* __restrict__ raw,
                                   int first, int last, uint16_t* out, int lane) {
@@ -72,7 +57,7 @@ __device__ void draw_samples_warp(uint16_t* perm_s, uint16_t* jrel_s, int N, con
         perm_s[j] = t;
       }
 #pragma unroll
-      for (int i = 0; i < S; ++i) out[(size_t)(first + d) * S + i] = perm_s[i];
+      for (int i = 0; i < S; ++i) out[(size_t)d * S + i] = perm_s[i];  // slot d of the round
     }
   }
   __syncwarp();
@@ -121,7 +106,7 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
   if (N >= S) {
     uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
                                                    sizeof(int32_t) * kRoundCap);
-    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * a.cap_draws * S, lane);
+    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * kRoundCap * S, lane);
   }
   for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
@@ -143,9 +128,9 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   for (int i = lane; i < N; i += 32) perm_s[i] = a.perm[(size_t)p * a.stride + i];
   {  // the round's (valid, count) results, fetched by the whole warp: count, or -1 for "no model"
     const int rb = st->r_begin, re = st->r_end;
-    const int32_t* gv = a.valid + (size_t)p * a.cap_draws;
-    const int32_t* gc = a.counts + (size_t)p * a.cap_draws;
-    for (int i = rb + lane; i < re; i += 32) vc_s[i - rb] = gv[i] ? gc[i] : -1;
+    const int32_t* gv = a.valid + (size_t)p * kRoundCap;
+    const int32_t* gc = a.counts + (size_t)p * kRoundCap;
+    for (int i = lane; i < re - rb; i += 32) vc_s[i] = gv[i] ? gc[i] : -1;
   }
   __syncwarp();
   int nb_w = 0, ne_w = 0, done_w = 1;
@@ -181,12 +166,13 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
       if (rem < 1) rem = 1;
       // k is only an upper bound (it shrinks whenever a better model shows
       // up), so the next round evaluates at most as many new draws as have
-      // been evaluated so far (doubling), except the last round, which
-      // covers everything that can still be needed plus the skip reserve.
-      const bool last = (round + 2 >= kSacRounds);
-      const int grow = last ? a.cap_draws : sac_round_draws(round + 1, CHUNK);
-      ne = min(a.cap_draws, nb + min(min(rem + 16, grow), kRoundCap));
-      if (round + 1 >= kSacRounds || nb >= a.cap_draws) { done = 1; exhausted = 1; }
+      // been evaluated so far (doubling, capped at kRoundCap).  The host enqueues
+      // kSacRounds rounds blindly and keeps adding rounds while a problem is
+      // pending, so every draw the reference loop can consume (max_iterations + 1
+      // counted trials + max_skip skipped samples = cap_draws) is reachable.
+      const int grow = min(sac_round_draws(round + 1, CHUNK), kRoundCap);
+      ne = min(a.cap_draws, nb + min(rem + 16, grow));
+      if (nb >= a.cap_draws) { done = 1; exhausted = 1; }  // unreachable: the loop ends by its own limits first
     }
     if (best_slot >= 0) {  // model_coefficients_ = model
       const double* m = a.models + ((size_t)p * kRoundCap + best_slot) * 12;
@@ -208,7 +194,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   ne_w = __shfl_sync(0xFFFFFFFFu, ne_w, 0);
   done_w = __shfl_sync(0xFFFFFFFFu, done_w, 0);
   if (!done_w) {
-    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, nb_w, ne_w, a.samples + (size_t)p * a.cap_draws * S, lane);
+    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, nb_w, ne_w, a.samples + (size_t)p * kRoundCap * S, lane);
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   }
 }
@@ -247,8 +233,8 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   const double* gb = a.b + (size_t)p * a.stride * 3;
   const int nh = min(kMonoChunk, st.r_end - d0);
   const bool live = tid < nh;
-  const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + (live ? tid : 0)) * 8;
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
+  const uint16_t* smp = a.samples + (live ? slot : (size_t)p * kRoundCap) * 8;
   geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * geom::kFrontOut);
 }
 
@@ -266,16 +252,16 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
   if (tid < nh) {
     nr = geom::mono_isolate_thread(a.fsol + slot * geom::kFrontOut, a.brk + slot * 2 * geom::kMaxBrackets,
                                    a.force_generic != 0);
-    a.nroot[slot] = nr & 0xFFFF;
     for (int chain = 0; chain < 2; ++chain)
       if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
         const int R = chain ? ((nr >> 8) & 255) : (nr & 255);
         const unsigned at = atomicAdd(a.fb_count, (unsigned)R);
+        if (at + (unsigned)R > a.item_cap) { *a.overflow = 1u; nr = 0; break; }  // the host re-runs the batch with larger lists
         for (int j = 0; j < R; ++j) a.fb_list[at + j] = (uint32_t)(((slot * 2 + chain) << 4) | j);
       }
   }
   // item ranges: one reservation per warp, lanes take consecutive sub-ranges
-  const int n = (nr & 255) + ((nr >> 8) & 255);
+  int n = (nr & 255) + ((nr >> 8) & 255);
   int incl = n;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -285,8 +271,15 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
   const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
   unsigned base = 0;
   if (lane == 0 && total > 0) base = atomicAdd(a.item_count, (unsigned)total);
-  base = __shfl_sync(0xFFFFFFFFu, base, 0) + (unsigned)(incl - n);
+  const unsigned wbase = __shfl_sync(0xFFFFFFFFu, base, 0);
+  base = wbase + (unsigned)(incl - n);
+  if (wbase + (unsigned)total > a.item_cap) {  // list full: no items for this warp's draws, flag the batch
+    if (lane == 0) *a.overflow = 1u;
+    n = 0;
+    nr = 0;
+  }
   if (tid < nh) {
+    a.nroot[slot] = nr & 0xFFFF;
     a.item_base[slot] = base;
     for (int r = 0; r < n; ++r) a.item_list[base + r] = (uint32_t)(slot * 32 + r);
   }
@@ -297,7 +290,7 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
 // bisection per thread.
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
   KML_DYN_SMEM(double, smem_d);
-  const unsigned n = *a.fb_count;
+  const unsigned n = min(*a.fb_count, a.item_cap);
   for (unsigned it = blockIdx.x * kMonoChunk + threadIdx.x; it < n; it += gridDim.x * kMonoChunk) {
     const uint32_t item = a.fb_list[it];
     const size_t slot = item >> 5;
@@ -311,18 +304,18 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacAr
 // thread = (draw, root) item over the whole round (grid-stride over the compacted list)
 constexpr int kItemThreads = 128;
 __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
-  const unsigned n = *a.item_count;
+  const unsigned n = min(*a.item_count, a.item_cap);
   for (unsigned it = blockIdx.x * kItemThreads + threadIdx.x; it < n; it += gridDim.x * kItemThreads) {
     const uint32_t code = a.item_list[it];
     const size_t slot = code >> 5;
     const int r = code & 31;
-    const int p = (int)(slot / kRoundCap), j = (int)(slot % kRoundCap);
+    const int p = (int)(slot / kRoundCap);
     const int R0 = a.nroot[slot] & 255;
     const double* fo = a.fsol + slot * geom::kFrontOut;
     const double* bk = a.brk + slot * 2 * geom::kMaxBrackets + 2 * r;
     const double* ga = a.a + (size_t)p * a.stride * 3;
     const double* gb = a.b + (size_t)p * a.stride * 3;
-    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + a.st[p].r_begin + j) * 8;
+    const uint16_t* smp = a.samples + slot * 8;
     double q = 0.0, M[12];
     const int status = geom::mono_item(fo, r >= R0 ? 1 : 0, bk[0], bk[1], ga, gb, smp, &q, M);
     a.item_status[it] = (uint8_t)status;
@@ -448,8 +441,8 @@ __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a)
         for (int g2 = g + 1; g2 < kGroups; ++g2) atomicMax(&s_cum[g2], cnt);
     }
     if (lane == 0) {
-      a.valid[(size_t)p * a.cap_draws + d0 + h] = v;
-      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
+      a.valid[slot0 + h] = v;
+      a.counts[slot0 + h] = cnt;
     }
     if (v && lane < 12) a.models[(slot0 + h) * 12 + lane] = s_mod[h][lane];
   }
@@ -485,7 +478,7 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
   const int nh = min(kStereoChunk, st.r_end - d0);
   if (tid < nh) {
     double M[12];
-    const uint16_t* smp = a.samples + ((size_t)p * a.cap_draws + d0 + tid) * 3;
+    const uint16_t* smp = a.samples + ((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid) * 3;
     const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
     geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
 #pragma unroll
@@ -517,8 +510,8 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
     if (!a.full && lane == 0)
       for (int g2 = g + 1; g2 < kGroups; ++g2) atomicMax(&s_cum[g2], cnt);
     if (lane == 0) {
-      a.valid[(size_t)p * a.cap_draws + d0 + h] = 1;  // threept_arun always yields a model
-      a.counts[(size_t)p * a.cap_draws + d0 + h] = cnt;
+      a.valid[(size_t)p * kRoundCap + blockIdx.y * kStereoChunk + h] = 1;  // threept_arun always yields a model
+      a.counts[(size_t)p * kRoundCap + blockIdx.y * kStereoChunk + h] = cnt;
     }
     if (lane < 12) a.models[((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + h) * 12 + lane] = smod[12 * h + lane];
   }
@@ -533,7 +526,10 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ int s_cnt;
   __shared__ double s_M[12];
-  if (tid == 0) s_cnt = 0;
+  if (tid == 0) {
+    s_cnt = 0;
+    if (!st.done && a.pending) atomicAdd(a.pending, 1u);  // the enqueued rounds did not end this problem's loop
+  }
   const int N = a.N[p];
   uint32_t* mask = a.inlier_mask + (size_t)p * a.mask_words;
   if (st.best_draw < 0) {  // model_ empty: inliers_.clear(), return false
@@ -579,6 +575,10 @@ __global__ void __launch_bounds__(128) sac_select_kernel(SacArgs a) {
 __global__ void __launch_bounds__(128) gather_bearings_kernel(GatherArgs g) {
   const int p = blockIdx.x;
   const PairDesc pd = g.pairs[p];
+  if (pd.m_frame < 0) {  // inactive pair slot (no candidate, or its frame is not stored)
+    if (threadIdx.x == 0) g.N[p] = 0;
+    return;
+  }
   const int M = g.M[p];
   const double* qb = g.qb + (size_t)pd.q_slot * g.qF * 3;
   const double* mb = g.sb + (size_t)g.s_off[pd.m_frame] * 3;
@@ -604,11 +604,11 @@ __global__ void __launch_bounds__(128) gather_points_kernel(StereoGatherArgs sg)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) base_s = 0;
   __syncthreads();
-  if (!sg.mono_ok[p]) {
+  const PairDesc pd = g.pairs[p];
+  if (!sg.mono_ok[p] || pd.m_frame < 0) {
     if (tid == 0) g.N[p] = 0;
     return;
   }
-  const PairDesc pd = g.pairs[p];
   const int M = g.M[p];
   const double* qp = g.qp + (size_t)pd.q_slot * g.qF * 3;
   const double* mp = g.sp + (size_t)g.s_off[pd.m_frame] * 3;
@@ -661,30 +661,65 @@ __global__ void mono_gate_kernel(FinalizeArgs f) {
   if (ok && (double)inl / (double)M < f.min_ratio_mono) ok = 0;
   f.mono_ok[p] = ok;
 }
+// One thread per pair slot: the acceptance gates of recoverPose and the pair's kml_result record
+// (VLCEdge fields + the counters /root/reference/evaluation/lc_result.py:134-137 reads); the
+// batch counters are reduced per warp and added to the BatchStats block.
 __global__ void finalize_kernel(FinalizeArgs f) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= f.P) return;
-  int status = 1;
-  int mono_inl = 0, stereo_inl = 0;
-  if (f.mono_ok[p]) {
-    status = 2;
-    mono_inl = f.mono_inl[p];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) f.out_R[(size_t)p * 9 + 3 * r + c] = f.mono_model[(size_t)p * 12 + 4 * r + c];
+  unsigned long long hm = 0, hs = 0, rm = 0, rs = 0, em = 0, es = 0, ok_m = 0;
+  if (p < f.P && f.pairs[p].m_frame >= 0) {
+    const int b = p / f.K, i = p - b * f.K;
+    kml_result* r = f.recs + (size_t)b * f.cap + i;
+    int status = 1;
+    int mono_inl = 0, stereo_inl = 0;
+    const SacState sm = f.mono_st[p];
+    const SacState s3 = f.st3[p];
     const int N3 = f.N3[p];
-    const int inl3 = f.inl3[p];
-    int ok = N3 >= 3 && f.st3[p].best_draw >= 0;
-    if (ok && inl3 < f.min_inliers) ok = 0;
-    if (ok && (double)inl3 / (double)N3 < f.min_ratio_stereo) ok = 0;
-    if (ok) {
-      status = 0;
-      stereo_inl = inl3;
-      for (int i = 0; i < 12; ++i) f.out_T[(size_t)p * 12 + i] = f.model3[(size_t)p * 12 + i];
+    if (f.mono_ok[p]) {
+      status = 2;
+      mono_inl = f.mono_inl[p];
+      for (int rr = 0; rr < 3; ++rr)
+        for (int c = 0; c < 3; ++c) r->R_mono[3 * rr + c] = f.mono_model[(size_t)p * 12 + 4 * rr + c];
+      const int inl3 = f.inl3[p];
+      int ok = N3 >= 3 && s3.best_draw >= 0;
+      if (ok && inl3 < f.min_inliers) ok = 0;
+      if (ok && (double)inl3 / (double)N3 < f.min_ratio_stereo) ok = 0;
+      if (ok) {
+        status = 0;
+        stereo_inl = inl3;
+        for (int k = 0; k < 12; ++k) r->T[k] = f.model3[(size_t)p * 12 + k];
+      }
+      ok_m = 1;
+    }
+    r->n_matches = f.M[p];
+    r->status = status;
+    r->mono_inliers = mono_inl;
+    r->stereo_inliers = stereo_inl;
+    hm = (unsigned long long)sm.draws;
+    rm = hm * (unsigned long long)f.M[p];
+    em = (unsigned long long)sm.r_begin;
+    if (f.mono_ok[p]) {  // the stereo problem of a pair that failed the mono gate was never set up
+      hs = (unsigned long long)s3.draws;
+      rs = hs * (unsigned long long)N3;
+      es = (unsigned long long)s3.r_begin;
     }
   }
-  f.status[p] = status;
-  f.out_mono_inl[p] = mono_inl;
-  f.out_stereo_inl[p] = stereo_inl;
+  unsigned long long v[7] = {hm, hs, rm, rs, em, es, ok_m};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    unsigned long long x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+    v[k] = x;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (v[0]) atomicAdd(&f.stats->hyp_m, v[0]);
+    if (v[1]) atomicAdd(&f.stats->hyp_s, v[1]);
+    if (v[2]) atomicAdd(&f.stats->res_m, v[2]);
+    if (v[3]) atomicAdd(&f.stats->res_s, v[3]);
+    if (v[4]) atomicAdd(&f.stats->eval_m, v[4]);
+    if (v[5]) atomicAdd(&f.stats->eval_s, v[5]);
+    if (v[6]) atomicAdd(&f.stats->mono_ok, v[6]);
+  }
 }
 
 // --------------------------------------------------------------- launchers
@@ -716,7 +751,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   const size_t sm = mono_smem();
   const size_t sm2 = sizeof(double) * geom::kIsoSlots * kMonoChunk;
   ensure_smem(mono_front_kernel, sm);
-  const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kMonoChunk));
+  const int draws = min(kRoundCap, sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   KML_LAUNCH((mono_front_kernel), dim3(a.P, blocks), kMonoChunk, sm, s, a);
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
@@ -739,7 +774,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
-  const int draws = min(kRoundCap, (round + 1 >= kSacRounds) ? a.cap_draws : sac_round_draws(round, kStereoChunk));
+  const int draws = min(kRoundCap, sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   if (sm <= 96 * 1024) {
     ensure_smem(stereo_chunk_kernel<true>, sm);
@@ -749,6 +784,16 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   }
   KML_LAUNCH((sac_replay_kernel<3, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
   return 2;
+}
+__global__ void sac_pending_kernel(SacArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool pend = p < a.P && !a.st[p].done;
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, pend);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(a.pending, (unsigned)__popc(bal));
+}
+void launch_sac_pending(const SacArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  KML_LAUNCH((sac_pending_kernel), (a.P + 127) / 128, 128, 0, s, a);
 }
 void launch_mono_select(const SacArgs& a, cudaStream_t s) {
   if (a.P <= 0) return;

@@ -14,16 +14,18 @@
 namespace kml {
 
 // pre-drawn sample stream: mt19937(seed)() >> 1, what libstdc++'s
-// uniform_int_distribution<int>(0, INT_MAX) returns; 8 values per draw for
-// max_it + 1 trials and a reserve of 256 skipped samples
+// uniform_int_distribution<int>(0, INT_MAX) returns; 8 values per draw for every
+// draw Ransac::computeModel can consume: max_it + 1 counted trials and max_skip = 10 * max_it
+// skipped samples, so the stream cannot run out before the loop's own limits end it
+inline int sac_max_draws(int max_it) { return max_it + 1 + 10 * std::max(max_it, 0); }
 inline void fill_raw_stream(uint32_t seed, int max_it, std::vector<uint32_t>* raw) {
-  const size_t draws = (size_t)max_it + 1 + 256;
+  const size_t draws = (size_t)sac_max_draws(max_it);
   raw->resize(draws * 8);
   std::mt19937 mt(seed);
   for (auto& r : *raw) r = (uint32_t)mt() >> 1;
 }
 // draws a problem with sample size S can take from the stream
-inline int sac_cap_draws(int raw_len, int S, int max_it) { return std::min(raw_len / S, max_it + 1 + 256); }
+inline int sac_cap_draws(int raw_len, int S, int max_it) { return std::min(raw_len / S, sac_max_draws(max_it)); }
 
 // k as a function of (N, best inlier count), [n1][n1]: the exact expressions of
 // opengv::sac::Ransac::computeModel evaluated with the host libm, so that the device replay

@@ -105,6 +105,7 @@ EXPORTS = [
     "kml_get_bow_vector", "kml_db_query", "kml_bow_score", "kml_detect_loop_with_robot",
     "kml_detect_loop", "kml_compute_matched_indices", "kml_geometric_verification_nister",
     "kml_recover_pose", "kml_query_batch", "kml_query_batch_upload", "kml_query_batch_run",
+    "kml_host_alloc", "kml_host_free",
     "kml_hamming_knn2", "kml_l1_knn2", "kml_hamming_knn2_bench", "kml_ransac_arun_batch",
     "kml_ransac_nister_batch", "kml_vocab_set", "kml_transform_batch", "kml_peak_popc", "kml_peak_fp64", "kml_timer_begin", "kml_timer_end", "kml_flush_l2", "kml_comm_unique_id",
     "kml_comm_init", "kml_query_batch_sharded",

@@ -30,6 +30,12 @@ cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  memset(a, 0, sizeof *a);
+  a->type = cudaMemoryTypeUnregistered;  // every host array takes the staging path of batch_upload
+  a->hostPointer = const_cast<void*>(p);
+  return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,

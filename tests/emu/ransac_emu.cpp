@@ -36,18 +36,18 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   std::vector<double> ktable;
   fill_ktable(n1, S, prob, &ktable);
   const size_t Pa = (size_t)P;
-  std::vector<uint16_t> perm(Pa * stride), samples(Pa * cap_draws * S);
+  std::vector<uint16_t> perm(Pa * stride), samples(Pa * kRoundCap * 8);
   std::vector<double> mods(Pa * kRoundCap * 12), fsol, brk, item_q, item_model, best(Pa * 12, 0.0);
-  std::vector<int32_t> nroot, valid(Pa * cap_draws), counts(Pa * cap_draws), inl(Pa);
-  std::vector<uint32_t> fb(2 + 2), item_base, item_list, mask(Pa * mask_words);
+  std::vector<int32_t> nroot, valid(Pa * kRoundCap), counts(Pa * kRoundCap), inl(Pa);
+  std::vector<uint32_t> fb(4 + 2), item_base, item_list, mask(Pa * mask_words);
   std::vector<uint8_t> item_status;
   std::vector<SacState> st(Pa);
   if (mono) {
-    const size_t max_items = Pa * kRoundCap * 20;
+    const size_t max_items = Pa * kRoundCap * 10;  // a draw has at most 10 real roots
     nroot.resize(Pa * kRoundCap);
     fsol.resize(Pa * kRoundCap * 70);
     brk.resize(Pa * kRoundCap * 40);
-    fb.resize(Pa * kRoundCap * 20 + 2);
+    fb.resize(max_items + 4);
     item_base.resize(Pa * kRoundCap);
     item_list.resize(max_items);
     item_q.resize(max_items);
@@ -59,7 +59,10 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.raw = raw.data(); a.raw_len = raw_len; a.cap_draws = cap_draws;
   a.perm = perm.data(); a.samples = samples.data(); a.models = mods.data();
   a.fsol = fsol.data(); a.nroot = nroot.data(); a.brk = brk.data();
-  a.fb_list = fb.data() + 2; a.fb_count = fb.data(); a.item_count = fb.data() + 1;
+  a.fb_list = fb.data() + 4; a.fb_count = fb.data(); a.item_count = fb.data() + 1;
+  a.overflow = fb.data() + 2; a.pending = nullptr;
+  a.item_cap = (unsigned int)(mono ? Pa * kRoundCap * 10 : 0);
+  fb[2] = 0;
   a.item_base = item_base.data(); a.item_list = item_list.data(); a.item_q = item_q.data();
   a.item_model = item_model.data(); a.item_status = item_status.data();
   a.valid = valid.data(); a.counts = counts.data(); a.st = st.data(); a.best_model = best.data();
@@ -72,6 +75,16 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   for (int r = 0; r < kSacRounds; ++r) {
     if (mono) launch_mono_round(a, r, nullptr); else launch_stereo_round(a, r, nullptr);
   }
+  // finish_sac of lcd.cu: rounds are added while a problem's loop has not ended
+  a.pending = fb.data() + 3;
+  for (int r = kSacRounds;; ++r) {
+    fb[3] = 0;
+    launch_sac_pending(a, nullptr);
+    if (fb[2]) return -4;  // item lists overflowed (cannot happen at the worst-case size used here)
+    if (!fb[3]) break;
+    if (mono) launch_mono_round(a, r, nullptr); else launch_stereo_round(a, r, nullptr);
+  }
+  a.pending = nullptr;
   if (mono) launch_mono_select(a, nullptr); else launch_stereo_select(a, nullptr);
   const int words_out = std::max((N + 31) / 32, 1);
   for (int p = 0; p < P; ++p) {

@@ -66,7 +66,7 @@ def test_gpu_parity_tests_against_the_emulated_library(libkml_emu):
     # not test_query_lanes_concurrent: the emulator serialises launches, so concurrent lanes show nothing
     # new there and take minutes; four xdist workers, each a process with its own emulator
     r = subprocess.run([sys.executable, "-m", "pytest", *EMULATED_GPU_TESTS, "-m", "gpu", "-p", "emu_plugin",
-                        "-q", "-p", "no:cacheprovider", "-n", "4",
+                        "-q", "-p", "no:cacheprovider", "-n", "4", "--timeout", "600", "--timeout-method", "thread",
                         "--deselect", "tests/test_gpu_parity.py::test_query_lanes_concurrent"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]

@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py — loop-closure queries/s on B200 (BASELINE.json metric).
 
-Workload (config C2): 6 robot databases x 5 000 keyframes per
-GPU (500 ORB-256 features / keyframe, synthetic k=10 L=6 vocabulary), queries
-in batches of 256, top_k_verify = 16 candidates verified per query
-(kNN + Lowe 0.9 -> mono 5-pt RANSAC -> stereo Arun RANSAC).  One "step" = one
-batch of 256 queries through the whole hot path.
+Workloads:
+  N = 1  config C2 (BASELINE.json configs[1], the one the metric is quoted on): 6 robot databases x
+         5 000 keyframes on one GPU, 500 ORB-256 features / keyframe, synthetic k=10 L=6
+         vocabulary, queries in batches of 256, top_k_verify = 16 candidates verified per query
+         (kNN + Lowe 0.9 -> mono 5-pt RANSAC -> stereo Arun RANSAC).
+  N > 1  config C5 (configs[4]): one robot database of 50 000 keyframes per GPU, the query batch
+         replicated on every rank, per-shard records merged by ONE ncclAllGather per step + a
+         device merge.  `--workload` overrides either default.
+One "step" = one batch of 256 queries through the whole hot path.
 
-  value : queries/s with the batch already resident in HBM (kml_query_batch_run),
-          timed on the device with CUDA events on the library's stream.
-  e2e   : the same through kml_query_batch with HOST buffers (H2D of the
-          batch + D2H of the records inside the timed region).
-  N > 1 : one process per GPU, databases sharded by robot (each rank holds its
-          own 6 x 5 000 shard), the batch is replicated on every rank and the
-          per-shard records are merged by ONE ncclAllGather per step; value =
-          (N * 256 shard-queries) / max-over-ranks step time  ("weak").
+  value : with the batch already resident in HBM (kml_query_batch_run / _sharded), timed on the
+          device with CUDA events; K steps per timed block, blocks repeated until the timed
+          region is >= 1 s, median block reported (max over ranks per block).
+          N > 1: value = N * 256 * K / t  counts (query, shard) units — every GPU processes every
+          query against its own shard (weak scaling in database size); `distinct_queries_per_s`
+          is value / N.
+  e2e   : the same through kml_query_batch (N = 1) or upload + sharded run (N > 1) with HOST
+          buffers in pinned memory: H2D of the batch + D2H of the records inside the timed region.
 
-`--impl reference` times the CPU oracle (scalar C++ restatement of the
-reference algorithms, all host threads) on bounded samples of the same
-workload.
+`--impl reference` times the CPU oracle (scalar C++ restatement of the reference algorithms, built
+with the reference's flags, all host threads) on the same workload.  No torch anywhere: ranks
+meet through kml/rendezvous.py (a TCP socket) and NCCL is driven by the library itself.
 """
 import argparse
 import faulthandler
@@ -34,21 +38,33 @@ sys.path.insert(0, os.path.join(ROOT, "kimera-multi_b200"))
 
 import numpy as np  # noqa: E402
 
-N_ROBOTS = 6          # per GPU; --workload c5 sets 1 x 50 000 (BASELINE.json configs[4])
+N_ROBOTS = 6
 N_KEYFRAMES = 5000
 BATCH = 256
 WORKLOAD = "C2"
 F = 500
 METRIC = "loop_closure_queries_per_s"
 UNIT = "queries/s"
+MIN_TIMED_S = 1.0
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d.get("hbm_gbs", 6650.0)), "measured"
-    return 6650.0, "fallback"
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram__bytes per launch of the BoW and Hamming kernels from the committed ncu capture"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return {}
+    return {}
 
 
 class ClockSampler(threading.Thread):
@@ -109,15 +125,26 @@ def fill_detector(det, world, robots, log):
     log("database of %d x %d keyframes resident in %.1fs" % (len(robots), N_KEYFRAMES, time.time() - t0))
 
 
-def make_batches(world, n, n_robots_total, B=BATCH):
+def fill_oracle(lcd, world, robots, n_keyframes):
+    from kml import synth
+    for ch in synth.build_database(world, robots, n_keyframes, chunk=1000):
+        for i, p in enumerate(ch["poses"]):
+            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
+            lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
+            lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+
+
+def make_batches(world, n, n_robots_total, B=BATCH, pin=None):
     from kml import synth
     out = []
     for k in range(n):
         q = synth.make_queries(world, B, N_KEYFRAMES, n_robots_total, key=k)
         fq, fp = q["frames"], q["prev"]
-        out.append((q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"],
-                    fp["bow_off"], fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"],
-                    fq["points"]))
+        b = (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"],
+             fp["bow_off"], fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+        if pin is not None:   # host buffers of the e2e arm: page-locked (kml_host_alloc)
+            b = tuple(pin(np.ascontiguousarray(x)) for x in b)
+        out.append(b)
     return out
 
 
@@ -125,25 +152,32 @@ def batch_bytes(b):
     return int(sum(np.asarray(x).nbytes for x in b))
 
 
-def run_reference(args, rank, world_size, log):
-    """CPU arm: the oracle (scalar C++ port of DBoW2 + BFMatcher + OpenGV paths)."""
+def workload_config(n, sharded):
+    return {"workload": "%s: %d robot DB%s x %d keyframes per GPU, %d ORB-256 features/keyframe, "
+                        "%d-query batches, top_k_verify 16, lowe 0.9, mono 5-pt + stereo Arun RANSAC "
+                        "(max 1000 it, p 0.995)" % (WORKLOAD, N_ROBOTS, "" if N_ROBOTS == 1 else "s", N_KEYFRAMES, F, BATCH),
+            "global_batch": BATCH, "n_robots_per_gpu": N_ROBOTS, "keyframes_per_robot": N_KEYFRAMES,
+            "parallelism": ("robot-sharded x%d, replicated query batch + 1 in-place ncclAllGather/step + device merge" % n)
+                           if sharded else "single GPU",
+            "l2": "256 MiB device memset (> 126 MB L2) before every timed block; each step re-reads ~200 MB (touched "
+                  "postings, <= 4 096 candidate frames, the batch) per lane, the query lanes interleaved; the e2e arm "
+                  "uses a distinct batch every step"}
+
+
+def run_reference(args, rank, log):
+    """CPU arm: the oracle (scalar C++ port of DBoW2 + BFMatcher + OpenGV paths), reference build flags."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kml_oracle as ko
     world, robots = build_world(0, log)
     lcd = ko.LoopClosureDetector()
-    from kml import synth
     t0 = time.time()
-    for ch in synth.build_database(world, robots, N_KEYFRAMES, chunk=1000):
-        for i, p in enumerate(ch["poses"]):
-            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
-            lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
-            lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+    fill_oracle(lcd, world, robots, N_KEYFRAMES)
     log("oracle database ready in %.1fs" % (time.time() - t0))
     threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
     sample = BATCH if threads >= 4 else 64  # a step = the whole 256-query batch of the GPU arm
-    batches = make_batches(world, args.steps + args.warmup, N_ROBOTS, B=sample)
+    batches = make_batches(world, args.steps + args.warmup, N_ROBOTS * max(args.gpus, 1), B=sample)
     times = []
     for i, b in enumerate(batches):
         t0 = time.perf_counter()
@@ -158,22 +192,22 @@ def run_reference(args, rank, world_size, log):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
         "data": "synthetic",
-        "config": workload_config(1),
+        "config": workload_config(1, False),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d-query batches of the %s workload per step, %d OpenMP threads" % (sample, WORKLOAD, threads)},
+                         "flags": "-O2 -ffp-contract=off -fopenmp, no -march=native (the reference's own build, README.md:116)",
+                         "sample": "%d-query batches of ONE %s shard per step, %d OpenMP threads" % (sample, WORKLOAD, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
-    return {"workload": "%s: %d robot DBs x %d keyframes per GPU, %d ORB-256 features/keyframe, "
-                        "%d-query batches, top_k_verify 16, lowe 0.9, mono 5-pt + stereo Arun RANSAC "
-                        "(max 1000 it, p 0.995)" % (WORKLOAD, N_ROBOTS, N_KEYFRAMES, F, BATCH),
-            "global_batch": BATCH, "n_robots_per_gpu": N_ROBOTS, "keyframes_per_robot": N_KEYFRAMES,
-            "parallelism": "robot-sharded x%d, replicated query batch + 1 ncclAllGather/step" % n if n > 1 else "single GPU",
-            "l2": "256 MiB device memset before the timed region; each step re-reads ~200 MB (touched postings, 4 096 candidate "
-                  "frames, the batch) per lane, the query lanes interleaved, against a 126 MB L2; the e2e arm uses a distinct batch every step"}
+def records_equal(a, ca, b, cb):
+    if not np.array_equal(ca, cb):
+        return False
+    for q in range(len(ca)):
+        if a[q, :ca[q]].tobytes() != b[q, :cb[q]].tobytes():
+            return False
+    return True
 
 
 def main():
@@ -184,67 +218,57 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kml", choices=["kml", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 side measurements")
     ap.add_argument("--lanes", type=int, default=0,
                     help="query batches kept in flight per GPU (0 = default, 4)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2: 6 robot DBs x 5 000 keyframes per GPU (the headline config); "
-                         "c5: one robot DB of 50 000 keyframes per GPU (BASELINE.json configs[4])")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5"],
+                    help="auto: c2 on one GPU (6 robot DBs x 5 000 keyframes, the headline config), c5 on several "
+                         "(one robot DB of 50 000 keyframes per GPU, BASELINE.json configs[4])")
+    ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
     ap.add_argument("--watchdog-s", type=int, default=1500,
                     help="dump every thread's stack and exit if the run has not finished by then (0 = off)")
     args = ap.parse_args()
     if args.watchdog_s > 0:
         # a wedged collective or lane thread must end the process, not hold the GPU box
         faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
-    if args.workload == "c5":
-        N_ROBOTS, N_KEYFRAMES, WORKLOAD = 1, 50000, "C5"
-    args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = args.workload if args.workload != "auto" else ("c5" if max(world_size, args.gpus) > 1 else "c2")
+    if wl == "c5":
+        N_ROBOTS, N_KEYFRAMES, WORKLOAD = 1, 50000, "C5"
+    args.warmup = max(args.warmup, 3) if args.impl == "kml" else max(args.warmup, 1)
     if world_size > 1 and args.lanes > 4:
-        # every lane launches its all-gather on its own stream in its own order; with more streams
-        # than hardware queues (8 by default) two lanes can share a queue, and a rank whose lane-0
-        # collective sits behind its lane-5 collective then waits on a peer that queued them the
-        # other way round (8 GPUs x 6 lanes did not finish in 200 s; <= 4 lanes never stalled).
-        # The driver reads this when the CUDA context is created.
         os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
     def log(msg):
         print("[bench r%d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
     if args.impl == "reference":
-        run_reference(args, rank, world_size, log)
+        run_reference(args, rank, log)
         return
 
     import kml
-    dist = None
-    if world_size > 1:
-        # NCCL prints its version / debug lines on stdout by default: keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("gloo", rank=rank, world_size=world_size)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    from kml import shard
+    from kml.rendezvous import Rendezvous
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries nothing but the JSON line
+    rdzv = Rendezvous()
+    barrier = rdzv.barrier
 
     kml.build()
     det = kml.LoopClosureDetector(device=local_rank)
     n_lanes = args.lanes if args.lanes > 0 else 4
     lanes = [det] + [det.create_lane() for _ in range(n_lanes - 1)]
-    if world_size > 1:
-        # one communicator per lane: lane i of every rank forms its own all-gather group, so the
-        # lanes' collectives never have to be ordered against each other
-        uids = [[kml.LoopClosureDetector.comm_unique_id() for _ in lanes] if rank == 0 else None]
-        dist.broadcast_object_list(uids, src=0)
-        # NCCL prints its version line on stdout while a communicator is created: point fd 1 at
-        # stderr for the duration so that stdout carries nothing but the JSON line
+    sharded = world_size > 1
+    if sharded:
+        # one communicator per lane: lane i of every rank forms its own all-gather group; the lanes'
+        # collectives are submitted in the batches' global sequence order (kml_query_batch_sharded_seq)
+        uids = rdzv.broadcast([kml.LoopClosureDetector.comm_unique_id() for _ in lanes] if rank == 0 else None)
         sys.stdout.flush()
-        saved = os.dup(1)
+        saved = os.dup(1)   # NCCL prints its version line on stdout while a communicator is created
         os.dup2(2, 1)
         try:
-            for ln, uid in zip(lanes, uids[0]):
+            for ln, uid in zip(lanes, uids):
                 ln.comm_init(world_size, rank, uid)
         finally:
             sys.stdout.flush()
@@ -252,104 +276,148 @@ def main():
             os.close(saved)
     world, robots = build_world(rank, log)
     fill_detector(det, world, robots, log)
-    n_batches = args.steps + args.warmup
-    batches = make_batches(world, min(n_batches, 6), N_ROBOTS * world_size)
-    sharded = world_size > 1
+    batches = make_batches(world, 6, N_ROBOTS * world_size)
     popc_peak = det.peak_popc()
     fp64_peak = det.peak_fp64()
+    seq = [0]           # next global batch sequence number (identical on every rank)
 
-    # ---------------- resident arm: device-timed steps
-    # Two query lanes (kml_create_lane) keep two batches in flight on the GPU: the tail rounds
-    # of one batch's RANSAC and the host-side candidate selection overlap the other batch.
+    def run_block(fn_per_lane):
+        """one timed block: every lane thread runs its share of the K steps; returns after all joined"""
+        threads = [threading.Thread(target=fn_per_lane, args=(li, ln)) for li, ln in enumerate(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+
+    # ---------------- warm-up + sharded parity (N > 1): the NCCL-merged records of every rank must equal
+    # the merge (kml/shard.py, the documented rule) of all ranks' local records
+    sharded_parity = None
     for li, ln in enumerate(lanes):
         for i in range(args.warmup):
             ln.query_batch_upload(*batches[(li + i) % len(batches)])
-            ln.query_batch_run(sharded=sharded)
+            if sharded:
+                det.comm_seq_reset(0)
+                ln.query_batch_run(sharded=True, seq=0)
+            else:
+                ln.query_batch_run()
+    if sharded:
+        ok = True
+        for k in range(2):
+            det.query_batch_upload(*batches[k])
+            loc, lcnt = det.query_batch_run(sharded=False)
+            det.comm_seq_reset(0)
+            mrg, mcnt = det.query_batch_run(sharded=True, seq=0)
+            blocks = rdzv.gather((loc, lcnt))
+            ref, rcnt = shard.merge_records(blocks, int(det.params.top_k_verify))
+            ok = ok and records_equal(ref, rcnt, mrg, mcnt) and int(rcnt.sum()) > 0
+        sharded_parity = all(rdzv.gather(bool(ok)))
+        log("sharded parity (NCCL all-gather + device merge == merge of the gathered local records): %s" % sharded_parity)
+    for li, ln in enumerate(lanes):
         ln.query_batch_upload(*batches[li % len(batches)])     # this lane's resident batch
-    barrier()
-    # clocks / throttle reasons are sampled on rank 0's GPU only: eight nvidia-smi pollers on one
-    # box compete with the lane threads for the host cores
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    K = args.steps
+
+    # ---------------- resident arm: device-timed blocks of K steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # rank 0's GPU only (host cores are scarce at N = 8)
     if sampler:
         sampler.start()
-    l0 = sum(ln.stats().kernel_launches for ln in lanes)
     last = {}
     lock = threading.Lock()
 
-    def resident_worker(ln, n):
-        for _ in range(n):
-            out_, counts_ = ln.query_batch_run(sharded=sharded)
+    def resident_lane(li, ln):
+        for st in range(li, K, n_lanes):
+            if sharded:
+                out_, counts_ = ln.query_batch_run(sharded=True, seq=seq[0] + st)
+            else:
+                out_, counts_ = ln.query_batch_run()
             with lock:
                 last["out"], last["counts"] = out_, counts_
 
-    shares = [args.steps // n_lanes + (1 if i < args.steps % n_lanes else 0) for i in range(n_lanes)]
-    det.flush_l2()
-    t0 = time.perf_counter()
-    det.timer_begin()
-    threads = [threading.Thread(target=resident_worker, args=(ln, n)) for ln, n in zip(lanes, shares)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    step_ms = det.timer_end(lanes)            # CUDA events: begin on lane 0, end after every lane's last kernel
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    launches = sum(ln.stats().kernel_launches for ln in lanes) - l0
+    block_ms, launches_blk = [], 0
+    total_s, blocks_done = 0.0, 0
+    while True:
+        barrier()
+        det.flush_l2()
+        if sharded:
+            det.comm_seq_reset(0)
+            seq[0] = 0
+        l0 = sum(ln.stats().kernel_launches for ln in lanes)
+        det.timer_begin()
+        run_block(resident_lane)
+        ms = det.timer_end(lanes)            # CUDA events: begin on lane 0, end after every lane's last kernel
+        launches_blk = sum(ln.stats().kernel_launches for ln in lanes) - l0
+        ms = rdzv.max(ms)                    # max over ranks
+        block_ms.append(ms)
+        total_s += ms * 1e-3
+        blocks_done += 1
+        if (total_s >= args.min_timed_s and blocks_done >= 3) or blocks_done >= 200:
+            break
     clocks = sampler.stop() if sampler else None
-    barrier()
+    step_ms = float(np.median(block_ms))
+    value = world_size * BATCH * K / (step_ms * 1e-3)
     out, counts = last["out"], last["counts"]
-    if dist is not None:
-        import torch
-        t = torch.tensor([step_ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t[0])
-    value = world_size * BATCH * args.steps / (step_ms * 1e-3)
 
-    # ---------------- e2e arm: host buffers in, records out, every step (distinct batch per step)
-    if not sharded:
-        for ln in lanes:
-            ln.query_batch(*batches[0])
-    barrier()
+    # ---------------- the same shard on ONE GPU without the exchange (N > 1 only; rank 0 alone, others idle)
+    single_same_workload = None
+    if sharded:
+        barrier()
+        if rank == 0:
+            def solo_lane(li, ln):
+                for st in range(li, K, n_lanes):
+                    ln.query_batch_run()
+            ts = []
+            for _ in range(3):
+                det.flush_l2()
+                det.timer_begin()
+                run_block(solo_lane)
+                ts.append(det.timer_end(lanes))
+            single_same_workload = BATCH * K / (float(np.median(ts)) * 1e-3)
+        barrier()
 
-    def e2e_worker(ln, idxs):
-        for i in idxs:
-            b = batches[(args.warmup + i) % len(batches)]
+    # ---------------- e2e arm: pinned host buffers in, records out, every step (distinct batch per step)
+    pbatches = make_batches(world, 6, N_ROBOTS * world_size, pin=kml.pinned_copy)
+
+    def e2e_lane(li, ln):
+        for st in range(li, K, n_lanes):
+            b = pbatches[st % len(pbatches)]
             if sharded:
                 ln.query_batch_upload(*b)
-                ln.query_batch_run(sharded=True)
+                ln.query_batch_run(sharded=True, seq=seq[0] + st)
             else:
                 ln.query_batch(*b)
 
-    det.flush_l2()
-    t0 = time.perf_counter()
-    threads = [threading.Thread(target=e2e_worker, args=(ln, range(li, args.steps, n_lanes)))
-               for li, ln in enumerate(lanes)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    e2e_t = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_t], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_t = float(t[0])
-    e2e_value = world_size * BATCH * args.steps / e2e_t
+    if sharded:
+        det.comm_seq_reset(0)
+    seq[0] = 0
+    run_block(e2e_lane)      # warm-up of the e2e path
+    e2e_ms, total_s, blocks_done = [], 0.0, 0
+    while True:
+        barrier()
+        det.flush_l2()
+        if sharded:
+            det.comm_seq_reset(0)
+        t0 = time.perf_counter()
+        run_block(e2e_lane)
+        dt = rdzv.max(time.perf_counter() - t0)
+        e2e_ms.append(dt * 1e3)
+        total_s += dt
+        blocks_done += 1
+        if (total_s >= args.min_timed_s and blocks_done >= 3) or blocks_done >= 200:
+            break
+    e2e_value = world_size * BATCH * K / (float(np.median(e2e_ms)) * 1e-3)
     h2d = batch_bytes(batches[0])
     d2h = int(out.nbytes + counts.nbytes)
 
     # ---------------- attribution pass: per-stage device time of ONE lane running alone
-    # (with two lanes in flight the per-stage CUDA events of a lane also span the other lane's
-    # kernels, so stage shares and rooflines come from this single-lane pass, outside the timed region)
-    K = min(args.steps, 10)
-    stage = {"bow": 0.0, "match": 0.0, "mono": 0.0, "stereo": 0.0}
+    KA = min(K, 10)
+    stage = {"bow": 0.0, "match": 0.0, "mono": 0.0, "stereo": 0.0, "total": 0.0}
     acc = {"postings": 0, "hyp_m": 0, "hyp_s": 0, "pairs": 0, "res_m": 0, "res_s": 0}
     det.query_batch_upload(*batches[0])
     barrier()
-    for _ in range(K):
-        det.query_batch_run(sharded=sharded)
+    for _ in range(KA):
+        det.query_batch_run()
         st = det.stats()
         stage["bow"] += st.ms_bow; stage["match"] += st.ms_match
-        stage["mono"] += st.ms_mono; stage["stereo"] += st.ms_stereo
+        stage["mono"] += st.ms_mono; stage["stereo"] += st.ms_stereo; stage["total"] += st.ms_total
         acc["postings"] += st.bow_postings_last; acc["hyp_m"] += st.mono_hypotheses_last
         acc["hyp_s"] += st.stereo_hypotheses_last; acc["pairs"] += st.pairs_last
         acc["res_m"] += st.mono_residuals_last; acc["res_s"] += st.stereo_residuals_last
@@ -359,75 +427,92 @@ def main():
 
     # ---------------- rooflines (algorithmic work / device time per stage)
     hbm_peak, peak_src = load_peaks()
+    traffic = load_traffic()
     compares = pairs * F * F
     roof = {
         "bow_scan": {"bound": "hbm", "achieved": postings * 8 / (stage["bow"] * 1e-3) / 1e9 if stage["bow"] else None,
                      "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-                     "algorithmic_bytes_per_step": postings * 8 / K, "ms_per_step": stage["bow"] / K},
+                     "algorithmic_bytes_per_step": postings * 8 / KA, "ms_per_step": stage["bow"] / KA,
+                     "traffic": traffic.get("bow_score_kernel_%s" % WORKLOAD.lower())},
         # algorithmic: 8 POPC32 per 256-bit compare; the kernel executes 5 (three carry-save adders fold
         # seven XOR words into two weight-1 and three weight-2 words first), so `achieved` can exceed
         # the pipe's peak; `frac` is the utilisation of the POPC pipe by what is actually executed
         "hamming_knn": {"bound": "popc", "achieved": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
                         "executed": compares * 5 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
                         "peak": popc_peak / 1e12, "unit": "T POPC32/s", "peak_source": "measured (kml_peak_popc, same run)",
-                        "compares_per_step": compares / K, "ms_per_step": stage["match"] / K},
+                        "compares_per_step": compares / KA, "ms_per_step": stage["match"] / KA,
+                        "traffic": traffic.get("hamming_knn2_kernel_%s" % WORKLOAD.lower())},
         # algorithmic flops of the reference loop: per consumed hypothesis the minimal
         # solver (mono 33 kflop, stereo 1.5 kflop) plus one residual per correspondence (mono 95, stereo 27 flop)
-        "mono_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_m / K, "residuals_per_step": res_m / K,
-                        "ms_per_step": stage["mono"] / K,
+        "mono_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_m / KA, "residuals_per_step": res_m / KA,
+                        "ms_per_step": stage["mono"] / KA,
                         "achieved": (hyp_m * 33e3 + res_m * 95.0) / (stage["mono"] * 1e-3) / 1e12 if stage["mono"] else None,
-                        "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "peak_source": "measured (kml_peak_fp64, same run)"},
-        "stereo_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_s / K, "residuals_per_step": res_s / K,
-                          "ms_per_step": stage["stereo"] / K,
+                        "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "peak_source": "measured (kml_peak_fp64, same run; FMA — the "
+                        "bit-exact contract forbids FMA, so half of it is the ceiling)", "traffic": None},
+        "stereo_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_s / KA, "residuals_per_step": res_s / KA,
+                          "ms_per_step": stage["stereo"] / KA,
                           "achieved": (hyp_s * 1.5e3 + res_s * 27.0) / (stage["stereo"] * 1e-3) / 1e12 if stage["stereo"] else None,
-                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "peak_source": "measured (kml_peak_fp64, same run)"},
+                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "peak_source": "measured (kml_peak_fp64, same run)",
+                          "traffic": None},
     }
-    for k in ("bow_scan", "hamming_knn", "mono_ransac", "stereo_ransac"):
+    for k in roof:
         if roof[k]["achieved"]:
             roof[k]["frac"] = roof[k]["achieved"] / roof[k]["peak"]
     if roof["hamming_knn"].get("executed"):
         roof["hamming_knn"]["frac_algorithmic"] = roof["hamming_knn"]["frac"]
         roof["hamming_knn"]["frac"] = roof["hamming_knn"]["executed"] / roof["hamming_knn"]["peak"]
-    # flop model: 5-pt hypothesis ~ 60 kflop solver + 8x4x10 scoring; residual 95 flop
     dominant = max(("bow", "match", "mono", "stereo"), key=lambda s: stage[s])
     dom_key = {"bow": "bow_scan", "match": "hamming_knn", "mono": "mono_ransac", "stereo": "stereo_ransac"}[dominant]
     roofline = dict(roof[dom_key])
     roofline["kernel"] = dom_key
     roofline.setdefault("achieved", None)
     roofline.setdefault("frac", None)
-    roofline["traffic"] = None
+    roofline.setdefault("traffic", None)
 
+    valid = counts[:, None] > np.arange(out.shape[1])[None]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K,
+        "warmup": args.warmup, "ms_per_step": step_ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64-fixed/f64", "data": "synthetic",
-        "config": workload_config(world_size), "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "config": workload_config(world_size, sharded), "clocks": clocks, "gpu_launches": int(launches_blk),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_buffers": "pinned (kml_host_alloc)", "timed_blocks": len(e2e_ms)},
         "roofline": roofline, "rooflines": roof,
-        "stage_ms_per_step": {k: v / K for k, v in stage.items()},
-        "stage_ms_source": "single-lane attribution pass of %d steps after the timed region" % K,
-        "wall_ms_per_step": wall_ms / args.steps, "lanes": n_lanes,
-        "loop_closures_last_step": int((out["status"][counts[:, None] > np.arange(out.shape[1])[None]] == 0).sum()),
+        "stage_ms_per_step": {k: v / KA for k, v in stage.items()},
+        "stage_ms_source": "single-lane attribution pass of %d steps after the timed region" % KA,
+        "timed_blocks": len(block_ms), "timed_region_s": float(np.sum(block_ms) * 1e-3),
+        "block_ms_min_median_max": [float(np.min(block_ms)), step_ms, float(np.max(block_ms))],
+        "lanes": n_lanes,
+        "loop_closures_last_step": int((out["status"][valid] == 0).sum()),
     }
+    if sharded:
+        line["unit_note"] = ("value counts (query, shard) units: every one of the %d GPUs scores and verifies every query "
+                             "against its own 50 000-keyframe shard" % world_size)
+        line["distinct_queries_per_s"] = value / world_size
+        line["sharded_parity"] = sharded_parity
+        line["single_gpu_same_workload"] = single_same_workload
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(world, robots, log)
+        fb = line["cpu_baseline"].get("fair_best")
+        if fb:
+            line["vs_fair_best"] = {"resident": value / fb["value"], "e2e": e2e_value / fb["value"],
+                                    "note": "the -O3 -march=native oracle (hardware POPCNT), same host, same batch"}
+    if rank == 0 and world_size == 1 and not args.no_configs:
+        try:
+            line["configs"] = side_configs(det, log, popc_peak, fp64_peak)
+        except Exception as e:  # noqa: BLE001 - side measurements never take the bench line down
+            line["configs"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     det.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    rdzv.close()
 
 
 def _oracle_rate(ko, world, robots, threads, sample, log, tag):
     """queries/s of one `sample`-query batch on a freshly filled oracle detector of module `ko`"""
-    from kml import synth
     lcd = ko.LoopClosureDetector()
     t0 = time.time()
-    for ch in synth.build_database(world, robots, N_KEYFRAMES, chunk=1000):
-        for i, p in enumerate(ch["poses"]):
-            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
-            lcd.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
-            lcd.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+    fill_oracle(lcd, world, robots, N_KEYFRAMES)
     log("oracle database (%s) ready in %.1fs" % (tag, time.time() - t0))
     b = make_batches(world, 1, N_ROBOTS, B=sample)[0]
     lcd.query_batch(*b, threads=threads)  # warm-up
@@ -478,6 +563,110 @@ def cpu_baseline(world, robots, log):
         v2, dt2 = _oracle_rate(native, world, robots, threads, sample, log, "-O3 -march=native")
         out["fair_best"] = {"value": v2, "unit": UNIT, "cores": threads, "flags": NATIVE_FLAGS,
                             "sample": "same batch, %.2fs" % dt2}
+    try:  # the real OpenCV matcher on one candidate pair: 500 x 500, k = 2
+        import cv2
+        rng = np.random.default_rng(3)
+        q = rng.integers(0, 256, (F, 32), np.uint8)
+        t = rng.integers(0, 256, (F, 32), np.uint8)
+        row = {}
+        for name, nthr in (("1_thread_ms", 1), ("all_threads_ms", 0)):
+            cv2.setNumThreads(nthr)
+            m = cv2.BFMatcher(cv2.NORM_HAMMING)
+            m.knnMatch(q, t, 2)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                m.knnMatch(q, t, 2)
+                ts.append(time.perf_counter() - t0)
+            row[name] = float(np.median(ts) * 1e3)
+        row["what"] = "cv2.BFMatcher(NORM_HAMMING).knnMatch(500 x 500, k=2), median of 20, OpenCV %s" % cv2.__version__
+        out["cv2_bfmatcher_pair"] = row
+    except Exception as e:  # noqa: BLE001
+        out["cv2_bfmatcher_pair"] = {"error": repr(e)}
+    return out
+
+
+def side_configs(det, log, popc_peak, fp64_peak):
+    """BASELINE.json configs that are not the bench line, measured in the same driver run: C1 (one
+    query against a 2 000-keyframe database: GPU latency through kml_query_batch with B = 1, oracle
+    single-threaded), C3 (Hamming sweep 500 x 1k..1M against the measured POPC peak) and C4 (4 096
+    stereo problems x 1 001 hypotheses x 500 correspondences, every hypothesis counted)."""
+    import kml
+    from kml import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kml_oracle as ko
+    out = {}
+    rng = np.random.default_rng(5)
+    sweep = []
+    for nt in (1000, 10000, 100000, 1000000):
+        q = rng.integers(0, 256, (500, 32), np.uint8)
+        t = rng.integers(0, 256, (nt, 32), np.uint8)
+        _, _, ms = det.hamming_knn2(q, t, reps=10)
+        row = {"nt": nt, "gpu_ms": ms, "gpu_compares_per_s": 500 * nt / (ms * 1e-3),
+               "frac_of_popc_peak_algorithmic": 500 * nt * 8 / (ms * 1e-3) / popc_peak,
+               "frac_of_popc_peak_executed": 500 * nt * 5 / (ms * 1e-3) / popc_peak}
+        if nt <= 100000:
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                t0 = time.perf_counter()
+                cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, 2)
+                row["cv2_1thread_ms"] = (time.perf_counter() - t0) * 1e3
+                cv2.setNumThreads(0)
+            except Exception:  # noqa: BLE001
+                pass
+        sweep.append(row)
+    out["C3_hamming_sweep"] = sweep
+    # C4
+    from scipy.spatial.transform import Rotation as Rot
+    P, N = 4096, 500
+    X = np.stack([rng.uniform(-5, 5, (P, N)), rng.uniform(-5, 5, (P, N)), rng.uniform(2, 12, (P, N))], axis=2)
+    R = Rot.from_rotvec(rng.normal(size=(P, 3)) * 0.2).as_matrix()
+    tt = rng.uniform(-1, 1, (P, 3))
+    X2 = np.einsum("pnj,pjk->pnk", X - tt[:, None, :], R) + rng.normal(size=X.shape) * 0.03
+    outl = rng.random((P, N)) < 0.35
+    X2[outl] = rng.uniform(-8, 8, (int(outl.sum()), 3))
+    det.ransac_arun_batch(X[:64], X2[:64], full_hypotheses=True)
+    g = det.ransac_arun_batch(X, X2, full_hypotheses=True)
+    hyp = float(P) * 1001
+    res = hyp * N
+    c4 = {"problems": P, "hypotheses_each": 1001, "correspondences": N, "gpu_ms": g["ms"],
+          "residuals_per_s": res / (g["ms"] * 1e-3),
+          "algorithmic_tflops": (hyp * 1.5e3 + res * 27) / (g["ms"] * 1e-3) / 1e12,
+          "frac_of_fp64_peak": (hyp * 1.5e3 + res * 27) / (g["ms"] * 1e-3) / fp64_peak}
+    t0 = time.perf_counter()
+    for p in range(2):
+        ko.ransac_arun(X[p], X2[p], 0.5, 1.0 - 1e-300, 1000, 12345)   # p ~ 1 keeps k large: all 1 001 trials
+    c4["oracle_ms_per_problem_1thread"] = (time.perf_counter() - t0) / 2 * 1e3
+    out["C4_stereo_ransac"] = c4
+    # C1
+    world = synth.World(500, F=500)
+    ref = ko.LoopClosureDetector()
+    d1 = kml.LoopClosureDetector(device=det.device)
+    for ch in synth.build_database(world, [0], 2000, chunk=1000):
+        d1.addBowVectors(ch["robot"], ch["poses"], ch["bow_off"], ch["bow_ids"], ch["bow_vals"])
+        d1.addVLCFrames(ch["robot"], ch["poses"], ch["desc"], ch["bearings"], ch["points"])
+    fill_oracle(ref, world, [0], 2000)
+    q = synth.make_queries(world, 8, 2000, 1)
+    fq, fp = q["frames"], q["prev"]
+    gpu_t, cpu_t, same = [], [], True
+    for b in range(8):
+        o0, o1 = fq["bow_off"][b], fq["bow_off"][b + 1]
+        p0, p1 = fp["bow_off"][b], fp["bow_off"][b + 1]
+        a = (q["q_robot"][b:b + 1] + 7, q["q_pose"][b:b + 1], np.array([0, o1 - o0]), fq["bow_ids"][o0:o1], fq["bow_vals"][o0:o1],
+             np.array([0, p1 - p0]), fp["bow_ids"][p0:p1], fp["bow_vals"][p0:p1], fq["desc"][b:b + 1], fq["bearings"][b:b + 1],
+             fq["points"][b:b + 1])
+        t0 = time.perf_counter()
+        r1, c1 = d1.query_batch(*a)
+        gpu_t.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        r0, c0 = ref.query_batch(*a, threads=1)
+        cpu_t.append(time.perf_counter() - t0)
+        same = same and np.array_equal(c0, c1) and np.array_equal(r0["mono_inliers"], r1["mono_inliers"])
+    out["C1_single_query"] = {"gpu_ms_per_query_median": float(np.median(gpu_t[1:]) * 1e3),
+                              "cpu_oracle_1thread_ms_per_query_median": float(np.median(cpu_t[1:]) * 1e3),
+                              "candidates_verified": int(c1[0]), "records_match_oracle": bool(same)}
+    d1.close()
     return out
 
 

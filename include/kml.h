@@ -314,6 +314,18 @@ int kml_comm_init(kml_handle* h, int nranks, int rank, const void* unique_id);
  * rank receives the merged, globally re-ranked list. */
 int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap_per_query,
                             int32_t* counts);
+/* Several query lanes of one rank exchanging concurrently (each lane has its own communicator):
+ * `seq` is the batch's global sequence number, the same on every rank; a lane's all-gather is
+ * enqueued only after the all-gathers of all lower sequence numbers of this detector family, so
+ * every rank submits its collectives to the GPU in one order.  kml_comm_seq_reset sets the next
+ * number expected (0 after kml_create). */
+int kml_query_batch_sharded_seq(kml_handle* h, uint64_t seq, kml_result* out, int cap_per_query,
+                                int32_t* counts);
+int kml_comm_seq_reset(kml_handle* h, uint64_t next_seq);
+/* the sharded query's device tail alone (merge_shards_kernel) on host blocks, laid out as for
+ * kml_merge_shard_records */
+int kml_merge_shard_records_device(kml_handle* h, const void* blocks, int nranks, int B, int cap_in, int cap,
+                                   kml_result* out, int32_t* counts);
 
 #ifdef __cplusplus
 }

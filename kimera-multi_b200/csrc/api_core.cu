@@ -107,6 +107,17 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
       delete h;
       return KML_ERR_ARG;
     }
+    if (h->prm.top_k_verify < 0 || h->prm.top_k_verify > kSelMaxK) {
+      g_create_err = "top_k_verify must be in [0,128]";
+      delete h;
+      return KML_ERR_ARG;
+    }
+    if (h->prm.max_ransac_iterations_mono < 0 || h->prm.max_ransac_iterations < 0 ||
+        h->prm.max_ransac_iterations_mono > 100000 || h->prm.max_ransac_iterations > 100000) {
+      g_create_err = "max_ransac_iterations(_mono) must be in [0,100000]";
+      delete h;
+      return KML_ERR_ARG;
+    }
     h->device = device;
     KML_CUDA(cudaSetDevice(device));
     KML_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

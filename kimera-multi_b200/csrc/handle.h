@@ -2,6 +2,7 @@
 #pragma once
 #include <time.h>
 
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <memory>
@@ -90,6 +91,10 @@ struct kml_shared {
   kml::DevBuf<int32_t> s_F;        // [n_frames] features of every stored frame
   size_t frames_synced = 0;        // frames whose (offset, F) are on the device
   uint64_t version = 1;            // bumped by every add*: lanes re-upload their database views when it moved
+  // kml_query_batch_sharded_seq: the lanes' all-gathers are enqueued in sequence-number order
+  std::mutex seq_mu;
+  std::condition_variable seq_cv;
+  uint64_t seq_next = 0;
 
   // ---- pre-drawn sample stream + k tables
   std::vector<uint32_t> raw_h;

@@ -807,11 +807,10 @@ enum { kBlkOk = 0, kBlkRedo = 1, kBlkFailed = 2 };
 // blind rounds did not finish (or overflowed item lists) — it continues them from the host and
 // the exchange is repeated; kBlkFailed = some rank hit an error before the exchange — every
 // rank still enters the collective (nobody is left waiting) and every rank returns the error.
-static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int32_t* counts) {
+static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int32_t* counts,
+                     const uint64_t* seq = nullptr) {
   const int B = h->B;
   if (B == 0) return KML_OK;
-  if (h->prm.top_k_verify > kSelMaxK)
-    return fail(h, KML_ERR_CAPACITY, "query_batch: top_k_verify must be <= 128");
   PoliteScope scope(h, B >= 16);
   const int nr = sharded ? comm_nranks(h) : 1;
   const int rank = sharded ? comm_rank(h) : 0;
@@ -868,7 +867,17 @@ static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int3
     // ---- exchange + merge (sharded), final records to pinned memory
     const uint8_t* final_blk = blk;
     if (nr > 1) {
-      const int rc = comm_allgather(h, blk, h->d_blocks.p, bl.blk);
+      int rc;
+      if (seq && attempt == 0) {  // this batch's turn among the lanes' collectives (same order on every rank)
+        std::unique_lock<std::mutex> lk(h->sh->seq_mu);
+        h->sh->seq_cv.wait(lk, [&] { return h->sh->seq_next >= *seq; });
+        rc = comm_allgather(h, blk, h->d_blocks.p, bl.blk);
+        if (h->sh->seq_next == *seq) h->sh->seq_next = *seq + 1;
+        lk.unlock();
+        h->sh->seq_cv.notify_all();
+      } else {
+        rc = comm_allgather(h, blk, h->d_blocks.p, bl.blk);
+      }
       if (rc != KML_OK) return rc;
       MergeArgs m;
       m.base = h->d_blocks.p; m.blk_stride = bl.blk; m.counts_off = bl.counts_off; m.err_off = bl.err_off;
@@ -1356,6 +1365,66 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap, int32_t* co
   KML_API_BEGIN(h)
   if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "bad output");
   return batch_run(h, cap, true, out, counts);
+  KML_API_END(h)
+}
+
+int kml_query_batch_sharded_seq(kml_handle* h, uint64_t seq, kml_result* out, int cap, int32_t* counts) {
+  KML_API_BEGIN(h)
+  if (cap <= 0 || (h->B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "bad output");
+  if (h->B == 0) {  // nothing to exchange, but the sequence must still advance
+    {
+      std::unique_lock<std::mutex> lk(h->sh->seq_mu);
+      h->sh->seq_cv.wait(lk, [&] { return h->sh->seq_next >= seq; });
+      if (h->sh->seq_next == seq) h->sh->seq_next = seq + 1;
+    }
+    h->sh->seq_cv.notify_all();
+    return KML_OK;
+  }
+  return batch_run(h, cap, true, out, counts, &seq);
+  KML_API_END(h)
+}
+int kml_comm_seq_reset(kml_handle* h, uint64_t next_seq) {
+  if (!h) return KML_ERR_ARG;
+  {
+    std::lock_guard<std::mutex> lk(h->sh->seq_mu);
+    h->sh->seq_next = next_seq;
+  }
+  h->sh->seq_cv.notify_all();
+  return KML_OK;
+}
+
+// merge_shards_kernel on host blocks (the device tail of the sharded query, callable without NCCL)
+int kml_merge_shard_records_device(kml_handle* h, const void* blocks, int nranks, int B, int cap_in, int cap,
+                                   kml_result* out, int32_t* counts) {
+  KML_API_BEGIN(h)
+  if (!blocks || nranks < 1 || B < 0 || cap_in < 1 || cap < 1 || (B > 0 && (!out || !counts)))
+    return fail(h, KML_ERR_ARG, "merge_shard_records_device: bad argument");
+  if (B == 0) return KML_OK;
+  const size_t rec_in = sizeof(kml_result) * (size_t)B * cap_in;
+  const size_t blk = rec_in + sizeof(int32_t) * (size_t)B;       // host layout: records | counts
+  const size_t dblk = (blk + sizeof(int32_t) + 255) / 256 * 256;  // device layout adds the flag word
+  const BlockLayout ol = block_layout(B, cap);
+  cudaStream_t s = h->stream;
+  h->d_blocks.scratch(dblk * nranks);
+  h->d_merged.scratch(ol.blk);
+  KML_CUDA(cudaMemsetAsync(h->d_blocks.p, 0, dblk * nranks, s));
+  for (int r = 0; r < nranks; ++r)
+    KML_CUDA(cudaMemcpyAsync(h->d_blocks.p + dblk * r, static_cast<const uint8_t*>(blocks) + blk * r, blk,
+                             cudaMemcpyHostToDevice, s));
+  MergeArgs m;
+  m.base = h->d_blocks.p; m.blk_stride = dblk; m.counts_off = rec_in; m.err_off = blk;
+  m.nranks = nranks; m.B = B; m.cap_in = cap_in; m.cap = cap;
+  m.out = reinterpret_cast<kml_result*>(h->d_merged.p);
+  m.counts = reinterpret_cast<int32_t*>(h->d_merged.p + ol.counts_off);
+  m.err_out = reinterpret_cast<int32_t*>(h->d_merged.p + ol.err_off);
+  KML_CUDA(cudaMemsetAsync(h->d_merged.p, 0, ol.blk, s));
+  launch_merge(m, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaGetLastError());
+  KML_CUDA(cudaMemcpyAsync(out, h->d_merged.p, ol.rec_bytes, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaMemcpyAsync(counts, h->d_merged.p + ol.counts_off, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  KML_CUDA(cudaStreamSynchronize(s));
+  return KML_OK;
   KML_API_END(h)
 }
 

@@ -39,6 +39,41 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+class _PinnedBlock:
+    """page-locked host memory from kml_host_alloc, freed with the last array that views it"""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        rc = lib().kml_host_alloc(C.c_size_t(max(int(nbytes), 1)), C.byref(self.ptr))
+        if rc != KML_OK:
+            raise KmlError(rc, "kml_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().kml_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (kml_host_alloc): batch arrays held like this are
+    copied to the device from where they lie, without the library's staging copy."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    blk = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_uint8 * max(n * dtype.itemsize, 1)).from_address(blk.ptr.value)
+    buf._kml_block = blk                       # keeps the block alive as long as any view exists
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_copy(a):
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 def _u32(a):
     return np.ascontiguousarray(a, dtype=np.uint32)
 
@@ -279,13 +314,37 @@ class LoopClosureDetector:
         self._check(lib().kml_query_batch_upload(self._h, *args))
         self._B = args[0]
 
-    def query_batch_run(self, sharded=False):
+    def query_batch_run(self, sharded=False, seq=None):
+        """Run the uploaded batch.  sharded: merge with the other ranks' shards (one ncclAllGather);
+        seq: global sequence number of this batch when several lanes of a rank exchange
+        concurrently (their collectives are then enqueued in seq order on every rank)."""
         B = self._B
         cap = int(self.params.top_k_verify)
         out = np.zeros((B, cap), RESULT_DTYPE)
         counts = np.zeros(B, np.int32)
+        if sharded and seq is not None:
+            self._check(lib().kml_query_batch_sharded_seq(self._h, C.c_uint64(int(seq)), out.ctypes.data_as(C.c_void_p),
+                                                          cap, _p(counts, C.c_int32)))
+            return out, counts
         fn = lib().kml_query_batch_sharded if sharded else lib().kml_query_batch_run
         self._check(fn(self._h, out.ctypes.data_as(C.c_void_p), cap, _p(counts, C.c_int32)))
+        return out, counts
+
+    def comm_seq_reset(self, next_seq=0):
+        """next sequence number kml_query_batch_sharded_seq waits for (shared by this detector's lanes)"""
+        self._check(lib().kml_comm_seq_reset(self._h, C.c_uint64(int(next_seq))))
+
+    def merge_shard_records_device(self, blocks, cap):
+        """merge_shards_kernel on host blocks [(records[B, cap_in], counts[B]), ...] (test hook of the
+        sharded query's device tail)"""
+        B = len(blocks[0][1])
+        cap_in = blocks[0][0].shape[1]
+        buf = b"".join(np.ascontiguousarray(rec).tobytes() + np.ascontiguousarray(cnt, np.int32).tobytes()
+                       for rec, cnt in blocks)
+        out = np.zeros((B, cap), RESULT_DTYPE)
+        counts = np.zeros(B, np.int32)
+        self._check(lib().kml_merge_shard_records_device(self._h, buf, len(blocks), B, cap_in, cap,
+                                                         out.ctypes.data_as(C.c_void_p), _p(counts, C.c_int32)))
         return out, counts
 
     def hamming_knn2(self, q, t, reps=0):

@@ -134,3 +134,83 @@ def test_ransac_batches_with_many_correspondences(oracle):
     assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][0], N))
     det.close()
 
+
+
+def _compare_records(out0, cnt0, out1, cnt1, B):
+    assert np.array_equal(cnt0, cnt1)
+    n_lc = 0
+    for b in range(B):
+        for i in range(cnt0[b]):
+            a, g = out0[b, i], out1[b, i]
+            for k in ("q_robot", "q_pose", "m_robot", "m_pose", "n_matches", "mono_inliers", "stereo_inliers", "status"):
+                assert a[k] == g[k], (b, i, k, a[k], g[k])
+            assert abs(a["norm_bow_score"] - g["norm_bow_score"]) <= 1e-6 * abs(a["norm_bow_score"])
+            if a["status"] != 1:
+                assert np.abs(a["R_mono"] - g["R_mono"]).max() <= 1e-6
+            if a["status"] == 0:
+                n_lc += 1
+                assert np.abs(a["T"] - g["T"]).max() <= 1e-6
+    return n_lc
+
+
+def _fill_both(det, ref, world, robots, n_keyframes):
+    """database chunks go to both detectors as they are generated (nothing is kept)"""
+    from kml import synth
+    for ch in synth.build_database(world, robots, n_keyframes, chunk=1000):
+        det.addBowVectors(ch["robot"], ch["poses"], ch["bow_off"], ch["bow_ids"], ch["bow_vals"])
+        det.addVLCFrames(ch["robot"], ch["poses"], ch["desc"], ch["bearings"], ch["points"])
+        for i, p in enumerate(ch["poses"]):
+            o0, o1 = ch["bow_off"][i], ch["bow_off"][i + 1]
+            ref.addBowVector(ch["robot"], int(p), ch["bow_ids"][o0:o1], ch["bow_vals"][o0:o1])
+            ref.addVLCFrame(ch["robot"], int(p), ch["desc"][i], ch["bearings"][i], ch["points"][i])
+
+
+def _batch_args(q):
+    fq, fp = q["frames"], q["prev"]
+    return (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+
+
+def test_c2_full_shape_batch_against_oracle(oracle):
+    """BASELINE.json configs[1] at full size: 6 robot databases x 5 000 keyframes, one 256-query batch,
+    top_k_verify 16 — every one of the <= 4 096 records against the oracle's sequential run."""
+    import kml
+    from kml import synth
+    world = synth.World(5000 // 4, F=500)
+    det, ref = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    _fill_both(det, ref, world, range(6), 5000)
+    q = synth.make_queries(world, 256, 5000, 6)
+    args = _batch_args(q)
+    out1, cnt1 = det.query_batch(*args)
+    out0, cnt0 = ref.query_batch(*args)
+    n_lc = _compare_records(out0, cnt0, out1, cnt1, 256)
+    assert int(cnt0.sum()) > 3000 and n_lc > 1000
+    # resident path, twice: same records (determinism of the device pipeline)
+    det.query_batch_upload(*args)
+    o2, c2 = det.query_batch_run()
+    o3, c3 = det.query_batch_run()
+    assert np.array_equal(c2, cnt1) and o2.tobytes() == out1.tobytes() and o3.tobytes() == out1.tobytes()
+    det.close()
+
+
+def test_c5_wide_database_with_frames_against_oracle(oracle):
+    """BASELINE.json configs[4], one rank's shard: ONE robot database of 50 000 keyframes WITH its
+    frames (three entry tiles of the scorer), 48-query batch through kml_query_batch against the oracle."""
+    import kml
+    from kml import synth
+    world = synth.World(50000 // 4, F=500)
+    det, ref = kml.LoopClosureDetector(), oracle.LoopClosureDetector()
+    _fill_both(det, ref, world, [0], 50000)
+    q = synth.make_queries(world, 48, 50000, 1, robots=np.full(48, 3))   # inter-robot queries (robot 3 asks robot 0)
+    args = _batch_args(q)
+    out1, cnt1 = det.query_batch(*args)
+    out0, cnt0 = ref.query_batch(*args)
+    n_lc = _compare_records(out0, cnt0, out1, cnt1, 48)
+    assert int(cnt0.sum()) >= 48 * 3 and n_lc >= 48
+    # an intra-robot batch exercises the dist_local window across the tiles
+    q2 = synth.make_queries(world, 16, 50000, 1, key=3)
+    args2 = _batch_args(q2)
+    o1, c1 = det.query_batch(*args2)
+    o0, c0 = ref.query_batch(*args2)
+    _compare_records(o0, c0, o1, c1, 16)
+    det.close()

@@ -68,9 +68,12 @@ def _same_order_modulo_ties(e0, s0, e1, s1):
         j = i
         while j < len(e0) and s0[j] == s0[i]:
             j += 1
-        if j == len(e0) and not (set(e1[i:j]) <= set(e0[i:j])) and False:
-            return False
         if j < len(e0) and set(e0[i:j]) != set(e1[i:j]):
+            return False
+        # the last tie group may be cut by max_results: both sides then hold a subset of one tie
+        # group of the database, which this list alone cannot enumerate — scores within tolerance and
+        # equal length (both checked by the caller) are what can be asserted, plus no entry twice
+        if j == len(e0) and len(set(e1[i:j])) != j - i:
             return False
         i = j
     return True

@@ -52,8 +52,8 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", float(d.get("bf16_tflops", 1660.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1660.0
 
 
 def load_traffic():
@@ -225,6 +225,8 @@ def main():
                     help="auto: c2 on one GPU (6 robot DBs x 5 000 keyframes, the headline config), c5 on several "
                          "(one robot DB of 50 000 keyframes per GPU, BASELINE.json configs[4])")
     ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
+    ap.add_argument("--matcher-engine", type=int, default=int(os.environ.get("KML_MATCHER_ENGINE", "1")), choices=[0, 1],
+                    help="kml_params.matcher_engine: 0 = POPC pipe, 1 = tensor cores (tcgen05 kind::i8)")
     ap.add_argument("--watchdog-s", type=int, default=1500,
                     help="dump every thread's stack and exit if the run has not finished by then (0 = off)")
     args = ap.parse_args()
@@ -256,7 +258,9 @@ def main():
     barrier = rdzv.barrier
 
     kml.build()
-    det = kml.LoopClosureDetector(device=local_rank)
+    prm = kml.default_params()
+    prm.matcher_engine = args.matcher_engine
+    det = kml.LoopClosureDetector(prm, device=local_rank)
     n_lanes = args.lanes if args.lanes > 0 else 4
     lanes = [det] + [det.create_lane() for _ in range(n_lanes - 1)]
     sharded = world_size > 1
@@ -426,7 +430,7 @@ def main():
     barrier()
 
     # ---------------- rooflines (algorithmic work / device time per stage)
-    hbm_peak, peak_src = load_peaks()
+    hbm_peak, peak_src, bf16_peak = load_peaks()
     traffic = load_traffic()
     compares = pairs * F * F
     roof = {
@@ -437,11 +441,21 @@ def main():
         # algorithmic: 8 POPC32 per 256-bit compare; the kernel executes 5 (three carry-save adders fold
         # seven XOR words into two weight-1 and three weight-2 words first), so `achieved` can exceed
         # the pipe's peak; `frac` is the utilisation of the POPC pipe by what is actually executed
-        "hamming_knn": {"bound": "popc", "achieved": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
-                        "executed": compares * 5 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
-                        "peak": popc_peak / 1e12, "unit": "T POPC32/s", "peak_source": "measured (kml_peak_popc, same run)",
-                        "compares_per_step": compares / KA, "ms_per_step": stage["match"] / KA,
-                        "traffic": traffic.get("hamming_knn2_kernel_%s" % WORKLOAD.lower())},
+        "hamming_knn": ({"bound": "popc", "achieved": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                         "executed": compares * 5 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                         "peak": popc_peak / 1e12, "unit": "T POPC32/s", "peak_source": "measured (kml_peak_popc, same run)",
+                         "compares_per_step": compares / KA, "ms_per_step": stage["match"] / KA, "engine": "popc",
+                         "traffic": traffic.get("hamming_knn2_kernel_%s" % WORKLOAD.lower())}
+                        if args.matcher_engine == 0 else
+                        # tensor-core engine: one 256-bit compare = 256 int8 MACs = 512 ops on tcgen05.mma kind::i8;
+                        # the same work expressed in POPC32 (8 per compare) is kept for comparison with the POPC pipe
+                        {"bound": "tensor", "achieved": compares * 512 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                         "peak": 2.0 * bf16_peak, "unit": "TOP/s (int8)",
+                         "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 tensor rate is nominally 2 x bf16)",
+                         "compares_per_step": compares / KA, "ms_per_step": stage["match"] / KA, "engine": "tcgen05 kind::i8",
+                         "equivalent_popc32_per_s": compares * 8 / (stage["match"] * 1e-3) / 1e12 if stage["match"] else None,
+                         "popc_peak": popc_peak / 1e12,
+                         "traffic": traffic.get("hamming_tc_kernel_%s" % WORKLOAD.lower())}),
         # algorithmic flops of the reference loop: per consumed hypothesis the minimal
         # solver (mono 33 kflop, stereo 1.5 kflop) plus one residual per correspondence (mono 95, stereo 27 flop)
         "mono_ransac": {"bound": "fp64", "hypotheses_per_step": hyp_m / KA, "residuals_per_step": res_m / KA,
@@ -458,6 +472,8 @@ def main():
     for k in roof:
         if roof[k]["achieved"]:
             roof[k]["frac"] = roof[k]["achieved"] / roof[k]["peak"]
+    if roof["hamming_knn"].get("equivalent_popc32_per_s"):
+        roof["hamming_knn"]["x_popc_pipe_peak"] = roof["hamming_knn"]["equivalent_popc32_per_s"] / roof["hamming_knn"]["popc_peak"]
     if roof["hamming_knn"].get("executed"):
         roof["hamming_knn"]["frac_algorithmic"] = roof["hamming_knn"]["frac"]
         roof["hamming_knn"]["frac"] = roof["hamming_knn"]["executed"] / roof["hamming_knn"]["peak"]

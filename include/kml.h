@@ -79,6 +79,13 @@ typedef struct kml_params {
   int32_t matcher_norm;     /* 0 = NORM_HAMMING (BASELINE.json north_star, default); 1 = NORM_L1 over the 32
                              * descriptor bytes = what upstream's DescriptorMatcher::create(3) really selects
                              * (kimera_multi_lcd.patch:34-35) */
+  int32_t matcher_engine;   /* NORM_HAMMING only: 0 = POPC pipe (LOP3 / POPC kernel), 1 = tensor cores (tcgen05.mma
+                             * kind::i8 on +-1 expanded descriptors, s32 accumulators in TMEM); same keys, bit for bit */
+  int32_t mono_algorithm;   /* ransac_2d2d_algorithm of /root/reference/params/D455/LcdParams.yaml:68-73:
+                             * 0 = NISTER (default, what geometricVerificationNister names), 1 = STEWENIUS */
+  int32_t ransac_use_1point_3d3d; /* /root/reference/params/D455/LcdParams.yaml:58: recoverPose takes the mono
+                             * rotation as given and samples ONE point pair per hypothesis (translation only) */
+  int32_t reserved0;
 } kml_params;
 
 /* One verified candidate (VLCEdge of kimera_distributed + the counters the

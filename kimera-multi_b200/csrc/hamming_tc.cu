@@ -1,0 +1,306 @@
+// hamming_tc.cu — brute-force ORB-256 Hamming kNN (k=2) on the 5th-generation tensor cores.
+//
+// Same contract as hamming.cu (cv::BFMatcher(NORM_HAMMING)::knnMatch(k=2) as called from
+// LoopClosureDetector::computeMatchedIndices — SURVEY.md A.4, B.1;
+// /root/reference/images/kimera-multi.drawio:2583-2586, 2638): per query descriptor the two
+// nearest train descriptors as packed keys (dist << 20 | trainIdx), ties to the lowest trainIdx.
+//
+// tcgen05.mma has no 1-bit kind and mma.sync b1 is emulated on sm_100a, so the
+// descriptors are expanded to int8 +-1 (bit 1 -> +1, bit 0 -> -1): for two 256-bit descriptors
+//     sum_k a_k b_k = 256 - 2 * hamming(a, b)      =>   hamming = (256 - dot) / 2,
+// exact in the s32 accumulator.  One CTA per job (query frame x train range), persistent over
+// the job list:
+//   * every thread expands packed descriptors into shared memory in the canonical K-major
+//     SWIZZLE_128B operand layout (rows of 128 bytes, 16-byte chunk c of row r stored at chunk
+//     c ^ (r & 7); two 128-byte K blocks per 256-element row);
+//   * one thread issues tcgen05.mma.cta_group::1.kind::i8, M = 128 query rows x N = 256 train
+//     rows x K = 32 per instruction, 8 instructions per tile, accumulators in TMEM (two 256-column
+//     buffers, so the tensor pipe works on tile t+1 while the CUDA cores read tile t);
+//   * the epilogue reads the accumulator back with tcgen05.ld (thread = query row, 32 columns per
+//     load) and keeps best / second best per row:  key = dot * (-2^19) + (2^27 + j)  is one
+//     IMAD, the update three integer min / max.
+// Bound: tensor pipe vs the 4 ALU instructions per distance of the epilogue.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace kml {
+
+#ifndef KML_HOST_EMULATION
+
+constexpr int kTcThreads = 256;                   // 8 warps
+constexpr int kTcM = 128, kTcN = 256;             // one MMA tile: 128 query rows x 256 train rows
+constexpr int kTcMTiles = 4;                      // query rows resident per pass: 512
+constexpr uint32_t kTcASlab = kTcM * 128;         // one K block of an A tile: 16 KB
+constexpr uint32_t kTcATile = 2 * kTcASlab;       // 32 KB
+constexpr uint32_t kTcBSlab = kTcN * 128;         // one K block of the B tile: 32 KB
+constexpr uint32_t kTcBTile = 2 * kTcBSlab;       // 64 KB
+constexpr uint32_t kTcSmemA = kTcMTiles * kTcATile;            // 128 KB
+constexpr uint32_t kTcSmemBytes = kTcSmemA + kTcBTile + 1024;  // + alignment slack
+
+// ---- tcgen05 / TMEM wrappers (PTX ISA, sm_100a) -----------------------------------------------
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// writes of the generic proxy (st.shared) must be made visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory operand descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 256, M = 128
+constexpr uint32_t kTcIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, bool accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 4 descriptor bits -> 4 int8 lanes of +1 / -1 (bit k of n in byte k)
+__device__ __forceinline__ uint32_t expand4(uint32_t n) {
+  const uint32_t w01 = (n * 0x00204081u) & 0x01010101u;
+  return w01 | ((w01 ^ 0x01010101u) * 0xFFu);
+}
+
+// Expansion of packed descriptors (32 B each) into an operand tile (two K-block slabs of rows x
+// 128 B, slab_bytes apart).  A work item is (row r, K block kb): one 128-bit load -> the 128 bytes
+// of row r in slab kb = eight 16-byte chunks, chunk c stored at chunk c ^ (r & 7) (SWIZZLE_128B).
+// Items are numbered it = 2 r + kb; a quarter warp (8 consecutive items = 4 rows x 2 K blocks)
+// stores chunk (j + 4 kb) & 7 in its j-th store, which lands on 8 distinct 16-byte bank groups.
+__device__ __forceinline__ uint4 tc_load_item(const uint8_t* __restrict__ src, int it, int nrows) {
+  return (it < 2 * nrows) ? __ldg(reinterpret_cast<const uint4*>(src) + it) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void tc_store_item(uint8_t* tile, uint32_t slab_bytes, int it, const uint4& x) {
+  const int r = it >> 1, kb = it & 1, sw = r & 7;
+  uint8_t* row = tile + (uint32_t)kb * slab_bytes + (uint32_t)r * 128u;
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = (j + 4 * kb) & 7;            // chunk c = bits [16c, 16c+16) of the 128-bit block
+    uint32_t h = w[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if ((c >> 1) == q) h = w[q];
+    h = (c & 1) ? (h >> 16) : (h & 0xFFFFu);
+    uint4 o;
+    o.x = expand4(h & 15u); o.y = expand4((h >> 4) & 15u); o.z = expand4((h >> 8) & 15u); o.w = expand4(h >> 12);
+    *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = o;
+  }
+}
+// rows [0, nrows) of `src` into `tile` (query side: no register prefetch needed, once per pass)
+__device__ __forceinline__ void tc_expand_rows(uint8_t* tile, uint32_t slab_bytes, const uint8_t* __restrict__ src,
+                                               int nrows, int tid) {
+  for (int it0 = 0; it0 < 2 * nrows; it0 += 2 * kTcThreads) {
+    const uint4 x0 = tc_load_item(src, it0 + tid, nrows);
+    const uint4 x1 = tc_load_item(src, it0 + kTcThreads + tid, nrows);
+    if (it0 + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + tid, x0);
+    if (it0 + kTcThreads + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + kTcThreads + tid, x1);
+  }
+}
+
+// one chunk of 32 accumulator columns -> four independent (best, second) chains (column i mod 4),
+// merged by the caller: keys are distinct (the train index sits in the low bits), so the two
+// smallest keys of a union are min(b0, b1) and min(max(b0, b1), min(s0, s1)).
+template <bool FULL>
+__device__ __forceinline__ void tc_chunk(const int32_t* v, uint32_t cj, int nvalid, uint32_t* b, uint32_t* s) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (FULL || i < nvalid) {
+      const uint32_t key = (uint32_t)(v[i] * -524288) + (cj + (uint32_t)i);
+      const uint32_t mx = max(b[i & 3], key);
+      b[i & 3] = min(b[i & 3], key);
+      s[i & 3] = min(s[i & 3], mx);
+    }
+  }
+}
+__device__ __forceinline__ void tc_merge2(uint32_t& b, uint32_t& s, uint32_t b1, uint32_t s1) {
+  const uint32_t nb = min(b, b1);
+  s = min(max(b, b1), min(s, s1));
+  b = nb;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob* __restrict__ jobs, int njobs) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_best[kTcMTiles * kTcM], s_second[kTcMTiles * kTcM];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTcSmemA;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;                      // which 128 columns of a tile this warp reads
+  const int row_in_tile = (warp & 3) * 32 + lane;  // TMEM lane == query row of the tile
+  if (warp == 0) tmem_alloc_512(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+  uint32_t ph[2] = {0u, 0u};  // phase parity of full[0], full[1] (every thread tracks both)
+
+  for (int job_i = blockIdx.x; job_i < njobs; job_i += gridDim.x) {
+    const HamJob job = jobs[job_i];
+    if (job.nq <= 0) continue;
+    for (int q0 = 0; q0 < job.nq; q0 += kTcMTiles * kTcM) {
+      const int nq = min(kTcMTiles * kTcM, job.nq - q0);
+      const int mtiles = (nq + kTcM - 1) / kTcM;
+      uint32_t best[kTcMTiles], second[kTcMTiles];
+#pragma unroll
+      for (int m = 0; m < kTcMTiles; ++m) best[m] = second[m] = 0xFFFFFFFFu;
+      // query side: up to 512 rows, tile m at sA + m * 32 KB
+      for (int m = 0; m < mtiles; ++m)
+        tc_expand_rows(sA + m * kTcATile, kTcASlab, job.q + (size_t)(q0 + m * kTcM) * 32, min(kTcM, nq - m * kTcM), tid);
+      // train side: one 256-row tile at a time; the packed rows of the NEXT tile are loaded into
+      // registers (2 items per thread) while the tensor pipe and the epilogue work on this one
+      uint4 pf0 = tc_load_item(job.t, tid, min(kTcN, job.nt));
+      uint4 pf1 = tc_load_item(job.t, kTcThreads + tid, min(kTcN, job.nt));
+      for (int n0 = 0; n0 < job.nt; n0 += kTcN) {
+        const int nn = min(kTcN, job.nt - n0);
+        if (tid < 2 * nn) tc_store_item(sB, kTcBSlab, tid, pf0);
+        if (kTcThreads + tid < 2 * nn) tc_store_item(sB, kTcBSlab, kTcThreads + tid, pf1);
+        if (n0 + kTcN < job.nt) {
+          const int nn1 = min(kTcN, job.nt - n0 - kTcN);
+          pf0 = tc_load_item(job.t + (size_t)(n0 + kTcN) * 32, tid, nn1);
+          pf1 = tc_load_item(job.t + (size_t)(n0 + kTcN) * 32, kTcThreads + tid, nn1);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        auto issue = [&](int m) {
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(m & 1) * kTcN;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t ko = (uint32_t)(k >> 2), ki = (uint32_t)(k & 3) * 32u;
+            tc_mma_i8(d, tc_desc(sA_u + (uint32_t)m * kTcATile + ko * kTcASlab + ki),
+                      tc_desc(sB_u + ko * kTcBSlab + ki), k > 0);
+          }
+          tc_commit(&full[m & 1]);
+        };
+        if (tid == 0) {
+          issue(0);
+          if (mtiles > 1) issue(1);
+        }
+        // chunks of 32 columns this thread reads in this tile: [half*128, half*128 + 128) cut at nn
+        const int jl0 = half * 128;
+        const int nch = nn > jl0 ? min(4, (nn - jl0 + 31) >> 5) : 0;
+        for (int m = 0; m < mtiles; ++m) {
+          const int buf = m & 1;
+          mbar_wait(&full[buf], ph[buf]);
+          ph[buf] ^= 1u;
+          tc_fence_after();
+          const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * kTcN + jl0);
+          uint32_t b[4], s[4];
+          b[0] = best[0]; s[0] = second[0];
+#pragma unroll
+          for (int mm = 1; mm < kTcMTiles; ++mm)
+            if (mm == m) { b[0] = best[mm]; s[0] = second[mm]; }
+          b[1] = b[2] = b[3] = 0xFFFFFFFFu;
+          s[1] = s[2] = s[3] = 0xFFFFFFFFu;
+          int32_t va[32], vb[32];
+          if (nch > 0) tmem_ld32(tbase, va);
+#pragma unroll 1
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();                                        // va = chunk c
+            if (c + 1 < nch) tmem_ld32(tbase + (uint32_t)((c + 1) * 32), vb);
+            {
+              const int jl = jl0 + c * 32;
+              const uint32_t cj = 0x08000000u + (uint32_t)(n0 + jl);
+              if (jl + 32 <= nn) tc_chunk<true>(va, cj, 32, b, s); else tc_chunk<false>(va, cj, nn - jl, b, s);
+            }
+            if (c + 1 < nch) {
+              tmem_ld_wait();                                      // vb = chunk c + 1
+              if (c + 2 < nch) tmem_ld32(tbase + (uint32_t)((c + 2) * 32), va);
+              const int jl = jl0 + (c + 1) * 32;
+              const uint32_t cj = 0x08000000u + (uint32_t)(n0 + jl);
+              if (jl + 32 <= nn) tc_chunk<true>(vb, cj, 32, b, s); else tc_chunk<false>(vb, cj, nn - jl, b, s);
+            }
+          }
+          tc_merge2(b[0], s[0], b[1], s[1]);
+          tc_merge2(b[2], s[2], b[3], s[3]);
+          tc_merge2(b[0], s[0], b[2], s[2]);
+#pragma unroll
+          for (int mm = 0; mm < kTcMTiles; ++mm)
+            if (mm == m) { best[mm] = b[0]; second[mm] = s[0]; }
+          tc_fence_before();
+          __syncthreads();  // every warp is done reading TMEM buffer `buf`
+          if (tid == 0 && m + 2 < mtiles) issue(m + 2);
+        }
+        // all MMAs of this train tile have completed (their commits were waited for): sB is free
+      }
+      // merge the two column halves of every row and write the keys
+      if (half == 1) {
+#pragma unroll
+        for (int m = 0; m < kTcMTiles; ++m) {
+          s_best[m * kTcM + row_in_tile] = best[m];
+          s_second[m * kTcM + row_in_tile] = second[m];
+        }
+      }
+      __syncthreads();
+      if (half == 0) {
+#pragma unroll
+        for (int m = 0; m < kTcMTiles; ++m) {
+          const int qi = m * kTcM + row_in_tile;
+          if (qi < nq) {
+            const uint32_t b1 = s_best[qi], s1 = s_second[qi];
+            const uint32_t b = min(best[m], b1);
+            const uint32_t s = min(max(best[m], b1), min(second[m], s1));
+            job.keys[2 * (size_t)(q0 + qi) + 0] = b;
+            job.keys[2 * (size_t)(q0 + qi) + 1] = s;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_512(tmem);
+}
+
+void launch_hamming_jobs_tc(const HamJob* d_jobs, int njobs, cudaStream_t s) {
+  if (njobs <= 0) return;
+  KML_CUDA(cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  const int grid = min(njobs, kNumSMs);
+  hamming_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(d_jobs, njobs);
+}
+
+#else  // the SIMT emulator has no tensor cores: the POPC kernel computes the same keys
+
+void launch_hamming_jobs_tc(const HamJob* d_jobs, int njobs, cudaStream_t s) { launch_hamming_jobs(d_jobs, njobs, 0, s); }
+
+#endif
+
+}  // namespace kml

@@ -17,6 +17,8 @@ struct HamJob {
 // norm: 0 = NORM_HAMMING (key = dist<<20 | idx, nt <= 2^20), 1 = NORM_L1 (key = dist<<18 | idx, nt <= 2^18)
 inline int knn_key_shift(int norm) { return norm == 1 ? 18 : 20; }
 void launch_hamming_jobs(const HamJob* d_jobs, int njobs, int norm, cudaStream_t s);
+// NORM_HAMMING on the tensor cores (hamming_tc.cu): same keys as launch_hamming_jobs(.., 0, ..)
+void launch_hamming_jobs_tc(const HamJob* d_jobs, int njobs, cudaStream_t s);
 void launch_knn2_reduce(const uint32_t* partial, int nranges, int nq, int64_t range_len, int norm,
                         uint32_t* idx, uint16_t* dist, cudaStream_t s);
 void launch_lowe_compact(const uint32_t* keys, const int* nq_arr, int key_stride, double lowe, int norm,

@@ -716,7 +716,8 @@ static void batch_enqueue(kml_handle* h, int cap, uint8_t* blk, BatchPlan* pl) {
   }
   // ---- computeMatchedIndices
   KML_CUDA(cudaEventRecord(h->ev[2], s));
-  launch_hamming_jobs(h->d_jobs.p, P, h->prm.matcher_norm, s);
+  if (h->prm.matcher_engine == 1) launch_hamming_jobs_tc(h->d_jobs.p, P, s);
+  else launch_hamming_jobs(h->d_jobs.p, P, h->prm.matcher_norm, s);
   launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, P, s);
   h->stats.kernel_launches += 2;
   KML_CUDA(cudaEventRecord(h->ev[3], s));
@@ -1211,7 +1212,8 @@ int kml_compute_matched_indices(kml_handle* h, uint64_t qr, uint64_t qp, uint64_
   job.keys = h->d_keys.p;
   KML_CUDA(cudaMemcpyAsync(h->d_jobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, s));
   KML_CUDA(cudaMemcpyAsync(h->d_nq.p, &qs.F, 4, cudaMemcpyHostToDevice, s));
-  launch_hamming_jobs(h->d_jobs.p, 1, h->prm.matcher_norm, s);
+  if (h->prm.matcher_engine == 1) launch_hamming_jobs_tc(h->d_jobs.p, 1, s);
+  else launch_hamming_jobs(h->d_jobs.p, 1, h->prm.matcher_norm, s);
   launch_lowe_compact(h->d_keys.p, h->d_nq.p, stride, h->prm.lowe_ratio, h->prm.matcher_norm, h->d_iq.p, h->d_im.p, h->d_M.p, 1, s);
   h->stats.kernel_launches += 2;
   KML_CUDA(cudaGetLastError());

@@ -49,6 +49,10 @@ class Params(C.Structure):
         ("ransac_seed", C.c_uint32),
         ("top_k_verify", C.c_int32),
         ("matcher_norm", C.c_int32),
+        ("matcher_engine", C.c_int32),
+        ("mono_algorithm", C.c_int32),
+        ("ransac_use_1point_3d3d", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

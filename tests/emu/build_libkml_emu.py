@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "kimera-multi_b200", "csrc")
-SOURCES = ["api_core", "hamming", "comm", "bow", "ransac", "lcd", "vocab", "select", "postfilter", "persist"]  # = the Makefile's OBJS
+SOURCES = ["api_core", "hamming", "hamming_tc", "comm", "bow", "ransac", "lcd", "vocab", "select", "postfilter", "persist"]  # = the Makefile's OBJS
 # -ffp-contract=off everywhere: what -fmad=false is for ransac.cu, and the other sources hold no
 # multiply-add that the GPU build may contract into an FMA with a different result
 FLAGS = ["-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",

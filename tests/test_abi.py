@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     p = kml.default_params()
     assert p.max_db_results == 50 and p.lowe_ratio == 0.9 and p.ransac_seed == 12345
     assert p.top_k_verify == 16 and abs(p.ransac_probability_mono - 0.995) < 1e-15
-    assert C.sizeof(kml.Params) == 152 and p.matcher_norm == 0
+    assert C.sizeof(kml.Params) == 168 and p.matcher_norm == 0 and p.matcher_engine == 1 and p.mono_algorithm == 0
 
 
 def test_no_cpu_fallback_without_device():

@@ -483,3 +483,47 @@ def test_l1_matcher_variant(oracle, small_world):
         assert np.array_equal(iq0, iq1) and np.array_equal(im0, im1)
     assert len(iq0) > 50   # same place (3, 203): matches survive under L1 as well
     det.close()
+
+
+def test_tensor_core_matcher_bit_exact(oracle, small_world):
+    """matcher_engine = 1: tcgen05.mma kind::i8 on +-1 expanded descriptors, accumulators in TMEM —
+    the packed (distance, trainIdx) keys must equal the POPC kernel's and the oracle's bit for bit,
+    standalone (sizes around the 128 x 256 tiling, duplicates, k > nTrain, empty sets) and inside
+    the batch query."""
+    import kml
+    from conftest import fill
+    prm = kml.default_params()
+    prm.matcher_engine = 1
+    det = kml.LoopClosureDetector(prm)
+    rng = np.random.default_rng(11)
+    for nq, nt in [(500, 500), (1, 2), (500, 1), (33, 0), (128, 256), (129, 257), (513, 255), (700, 1300),
+                   (64, 20000), (1100, 513)]:
+        q = rng.integers(0, 256, (nq, 32), np.uint8)
+        t = rng.integers(0, 256, (nt, 32), np.uint8)
+        if nt > 8:
+            t[5] = t[3]
+            t[nt - 1] = t[0]
+            q[0] = t[3]
+            q[nq - 1] = ~t[1]          # distance 256: the largest key
+        i1, d1, _ = det.hamming_knn2(q, t)
+        i0, d0 = oracle.hamming_knn2(q, t)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1), (nq, nt)
+    world, chunks, queries = small_world
+    fill(det, chunks, bulk=True)
+    ref = oracle.LoopClosureDetector()
+    fill(ref, chunks)
+    fq, fp = queries["frames"], queries["prev"]
+    args = (queries["q_robot"], queries["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    o1, c1 = det.query_batch(*args)
+    o0, c0 = ref.query_batch(*args)
+    assert np.array_equal(c0, c1)
+    for b in range(len(c0)):
+        for i in range(c0[b]):
+            for k in ("m_robot", "m_pose", "n_matches", "mono_inliers", "stereo_inliers", "status"):
+                assert o0[b, i][k] == o1[b, i][k], (b, i, k)
+    ch = chunks[0]
+    iq, im = det.computeMatchedIndices(0, int(ch["poses"][3]), 0, int(ch["poses"][7]))
+    jq, jm = ref.computeMatchedIndices(0, int(ch["poses"][3]), 0, int(ch["poses"][7]))
+    assert np.array_equal(iq, jq) and np.array_equal(im, jm)
+    det.close()

@@ -8,26 +8,27 @@
 //
 // One CTA per (query, robot database, entry tile):
 //   1. stage the query's sparse (word, weight) vector in shared memory;
-//   2. look up the CSR row of every query word, block-scan the row lengths;
-//   3. stream the touched postings with a flattened (word, posting) index so
-//      that consecutive threads read consecutive 8-byte postings of a row;
+//   2. look up the row {start, len} of every query word (one 8-byte load per word);
+//   3. stream the touched postings: a group of 8 lanes takes one row at a time and reads it with
+//      128-bit loads (two postings per lane and load; rows start on 16-byte boundaries);
 //   4. accumulate -(|q-d|-|q|-|d|)/2 per database entry into shared-memory
 //      accumulators.  The sum is kept in 2^-62 fixed point (u64 atomics), so
 //      it is the exactly rounded sum of the exact terms, independent of the
 //      accumulation order (DBoW2 sums the same terms in ascending word order
 //      in double; the two agree to ~1 ulp and bit-for-bit whenever the double
-//      sum is exact, e.g. for float32 wire weights);
-//   5. select the max_results best entries: 8-pass MSB radix select on the
-//      accumulators, ties at the cut taken in ascending entry id, then a rank
-//      sort by (score desc, entry asc).
-// Bound: HBM/L2 gather bandwidth on the touched postings.
+//      sum is exact, e.g. for float32 wire weights).  The thread whose add finds
+//      the accumulator at zero appends the entry to the CTA's TOUCHED LIST, so
+//      nothing later sweeps the dense tile;
+//   5. select the max_results best entries among the touched ones: MSB radix select (8 bits per
+//      pass, histogram scanned with warp shuffles) over the list, ties at the cut taken in
+//      ascending entry id, then a rank sort by (score desc, entry asc);
+// Bound: HBM/L2 gather of the touched rows.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace kml {
 
 constexpr int kBowThreads = 256;
-constexpr int kWordsPerThread = kBowMaxWords / kBowThreads;  // 4
 
 __device__ __forceinline__ unsigned long long bow_term_fx(double q, double d) {
   // DBoW2: value = fabs(q-d) - fabs(q) - fabs(d)  (<= 0); contribution to the
@@ -39,18 +40,18 @@ __device__ __forceinline__ unsigned long long bow_term_fx(double q, double d) {
 
 __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
   KML_DYN_SMEM(unsigned char, smem_raw);
+  // dynamic: accumulators [tile_entries] u64 | touched list [tile_entries] u16
   unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint16_t* touched = reinterpret_cast<uint16_t*>(smem_raw + (size_t)a.tile_entries * sizeof(unsigned long long));
   __shared__ uint32_t s_ids[kBowMaxWords];
   __shared__ float s_vals[kBowMaxWords];
-  __shared__ uint32_t s_row[kBowMaxWords];
-  __shared__ uint32_t s_pre[kBowMaxWords + 1];
+  __shared__ uint2 s_row[kBowMaxWords];
   __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_warp[kBowThreads / 32];
   __shared__ unsigned long long s_red[kBowThreads / 32];
   __shared__ unsigned long long s_sel_val[kBowMaxK];
   __shared__ uint32_t s_sel_ent[kBowMaxK];
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_need, s_cnt, s_nz;
+  __shared__ int s_need, s_cnt, s_ntouched, s_eq;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int bid = blockIdx.x;
@@ -66,11 +67,19 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
       db.n_entries > tile_lo ? min((uint32_t)a.tile_entries, db.n_entries - tile_lo) : 0u;
   const int max_id = a.max_id ? a.max_id[dbi] : -1;
 
+  // ---- stage the query, look up its rows, clear the accumulators
+  uint32_t tsum = 0;
   for (int i = tid; i < nq; i += kBowThreads) {
-    s_ids[i] = a.q_ids[q0 + i];
+    const uint32_t w = a.q_ids[q0 + i];
+    s_ids[i] = w;
     s_vals[i] = a.q_vals[q0 + i];
+    uint2 r = make_uint2(0u, 0u);
+    if (w < db.W) r = __ldg(db.rows + w);
+    s_row[i] = r;
+    tsum += r.y;
   }
   for (uint32_t e = tid; e < tile_n; e += kBowThreads) acc[e] = 0ull;
+  if (tid == 0) { s_ntouched = 0; s_cnt = 0; s_eq = 0; }
   __syncthreads();
 
   // ---- NSS factor: L1 score of the query against the previous BoW vector
@@ -97,130 +106,96 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
       a.nss[b] = (double)tot / kBowScale;
     }
   }
+  if (tile == 0 && a.postings_touched) {  // algorithmic postings counter: sum of the touched rows' lengths
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, o);
+    if (lane == 0 && tsum) atomicAdd(a.postings_touched, (unsigned long long)tsum);
+  }
 
-  // ---- row lookup + exclusive scan of the row lengths
-  uint32_t len[kWordsPerThread];
-  uint32_t tsum = 0;
+  // ---- stream the touched rows: 8 lanes per row, 128-bit loads (2 postings per lane)
+  {
+    const int grp = tid >> 3, gl = tid & 7;
+    const uint4* pool4 = reinterpret_cast<const uint4*>(db.postings);
+    for (int i = grp; i < nq; i += kBowThreads / 8) {
+      const uint2 r = s_row[i];
+      const double qv = (double)s_vals[i];
+      for (uint32_t k = 2u * gl; k < r.y; k += 16u) {
+        const uint4 p = __ldg(pool4 + ((r.x + k) >> 1));
 #pragma unroll
-  for (int u = 0; u < kWordsPerThread; ++u) {
-    const int i = tid * kWordsPerThread + u;
-    uint32_t l = 0;
-    if (i < nq) {
-      const uint32_t w = s_ids[i];
-      if (w < db.W) {
-        const uint32_t r0 = __ldg(db.row_ptr + w), r1 = __ldg(db.row_ptr + w + 1);
-        s_row[i] = r0;
-        l = r1 - r0;
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t e = h ? p.z : p.x, wb = h ? p.w : p.y;
+          if (k + h < r.y && e >= tile_lo && e - tile_lo < tile_n && (max_id < 0 || (int)e < max_id)) {
+            const unsigned long long fx = bow_term_fx(qv, (double)__uint_as_float(wb));
+            if (fx != 0ull) {
+              const unsigned long long old = atomicAdd(&acc[e - tile_lo], fx);
+              if (old == 0ull) touched[atomicAdd(&s_ntouched, 1)] = (uint16_t)(e - tile_lo);  // exactly one adder sees zero
+            }
+          }
+        }
       }
     }
-    len[u] = l;
-    tsum += l;
-  }
-  uint32_t incl = tsum;
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_warp[w];
-  uint32_t run = woff + incl - tsum;
-#pragma unroll
-  for (int u = 0; u < kWordsPerThread; ++u) {
-    const int i = tid * kWordsPerThread + u;
-    if (i < kBowMaxWords) s_pre[i] = run;
-    run += len[u];
-  }
-  if (tid == kBowThreads - 1) s_pre[kBowMaxWords] = run;
-  __syncthreads();
-  const uint32_t T = s_pre[kBowMaxWords];
-  if (tid == 0 && tile == 0 && a.postings_touched) atomicAdd(a.postings_touched, (unsigned long long)T);
-
-  // ---- stream the touched postings (flattened index -> coalesced rows)
-  for (uint32_t g = tid; g < T; g += kBowThreads) {
-    int lo = 0, hi = nq;  // largest i with s_pre[i] <= g
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_pre[mid] <= g) lo = mid; else hi = mid;
-    }
-    const uint2 p = __ldg(db.postings + (size_t)s_row[lo] + (g - s_pre[lo]));
-    const uint32_t e = p.x;
-    if (e >= tile_lo && e - tile_lo < tile_n && (max_id < 0 || (int)e < max_id)) {
-      const unsigned long long fx = bow_term_fx((double)s_vals[lo], (double)__uint_as_float(p.y));
-      atomicAdd(&acc[e - tile_lo], fx);
-    }
   }
   __syncthreads();
 
-  // ---- top-K: count non-zero accumulators
-  {
-    uint32_t c = 0;
-    for (uint32_t e = tid; e < tile_n; e += kBowThreads) c += (acc[e] != 0ull);
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    if (lane == 0) s_warp[warp] = c;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t tot = 0;
-      for (int w = 0; w < kBowThreads / 32; ++w) tot += s_warp[w];
-      s_nz = (int)tot;
-      s_need = min(a.K, (int)tot);
-      s_prefix = 0ull;
-      s_cnt = 0;
-    }
-    __syncthreads();
-  }
-  const int keff = min(a.K, s_nz);
+  // ---- top-K among the touched entries
+  const int nt = s_ntouched;
+  const int keff = min(a.K, nt);
   const size_t obase = ((size_t)(b * a.n_db + dbi) * a.n_tiles + tile);
   if (keff == 0) {
     if (tid == 0) a.out_count[obase] = 0;
     return;
   }
-  // 8-pass MSB radix select of the keff-th largest accumulator value
-  for (int pass = 7; pass >= 0; --pass) {
-    s_hist[tid] = 0;
-    __syncthreads();
-    const unsigned long long pref = s_prefix;
-    for (uint32_t e = tid; e < tile_n; e += kBowThreads) {
-      const unsigned long long v = acc[e];
-      if (v != 0ull && (pass == 7 || (v >> (8 * (pass + 1))) == pref))
-        atomicAdd(&s_hist[(uint32_t)(v >> (8 * pass)) & 255u], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // bins 255..0, 8 per lane: lane 0 owns the highest 8 bins
-      uint32_t h[8], lsum = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { h[k] = s_hist[255 - (lane * 8 + k)]; lsum += h[k]; }
-      uint32_t inc = lsum;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += v;
+  unsigned long long vk = 0ull;  // value of the keff-th best; 0 = every touched entry is selected
+  int need_eq = 0;
+  if (nt > a.K) {
+    if (tid == 0) { s_need = keff; s_prefix = 0ull; }
+    // 8-pass MSB radix select of the keff-th largest accumulator value over the touched list
+    for (int pass = 7; pass >= 0; --pass) {
+      s_hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long pref = s_prefix;
+      for (int i = tid; i < nt; i += kBowThreads) {
+        const unsigned long long v = acc[touched[i]];
+        if (pass == 7 || (v >> (8 * (pass + 1))) == pref)
+          atomicAdd(&s_hist[(uint32_t)(v >> (8 * pass)) & 255u], 1u);
       }
-      const uint32_t need = (uint32_t)s_need;
-      uint32_t before = inc - lsum;  // items in strictly higher bins than this lane's
-      const bool mine = before < need && inc >= need;
-      __syncwarp();
-      if (mine) {
+      __syncthreads();
+      if (warp == 0) {
+        // bins 255..0, 8 per lane: lane 0 owns the highest 8 bins
+        uint32_t h[8], lsum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (before < need && before + h[k] >= need) {
-            s_need = (int)(need - before);
-            s_prefix = (pref << 8) | (unsigned long long)(255 - (lane * 8 + k));
-            before = need;  // stop
-          } else if (before < need) {
-            before += h[k];
+        for (int k = 0; k < 8; ++k) { h[k] = s_hist[255 - (lane * 8 + k)]; lsum += h[k]; }
+        uint32_t inc = lsum;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        const uint32_t need = (uint32_t)s_need;
+        uint32_t before = inc - lsum;  // items in strictly higher bins than this lane's
+        const bool mine = before < need && inc >= need;
+        __syncwarp();
+        if (mine) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (before < need && before + h[k] >= need) {
+              s_need = (int)(need - before);
+              s_prefix = (pref << 8) | (unsigned long long)(255 - (lane * 8 + k));
+              if (pass == 0) s_eq = (int)h[k];  // how many touched entries hold exactly the cut value
+              before = need;  // stop
+            } else if (before < need) {
+              before += h[k];
+            }
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
+    vk = s_prefix;
+    need_eq = s_need;  // how many entries equal to vk to take
   }
-  const unsigned long long vk = s_prefix;  // value of the keff-th best
-  const int need_eq = s_need;              // how many entries equal to vk to take
   const int n_gt = keff - need_eq;
-  // entries strictly above the cut (unordered), then ties in ascending entry id
-  for (uint32_t e = tid; e < tile_n; e += kBowThreads) {
+  // entries strictly above the cut (unordered; the rank sort orders them)
+  for (int i = tid; i < nt; i += kBowThreads) {
+    const uint32_t e = touched[i];
     const unsigned long long v = acc[e];
     if (v > vk) {
       const int pos = atomicAdd(&s_cnt, 1);
@@ -229,18 +204,32 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
     }
   }
   __syncthreads();
-  if (warp == 0) {
-    int taken = 0;
-    for (uint32_t e0 = 0; e0 < tile_n && taken < need_eq; e0 += 32) {
-      const uint32_t e = e0 + lane;
-      const bool hit = e < tile_n && acc[e] == vk;
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
-      const int pos = taken + __popc(bal & ((1u << lane) - 1u));
-      if (hit && pos < need_eq) {
-        s_sel_val[n_gt + pos] = vk;
-        s_sel_ent[n_gt + pos] = e;
+  if (need_eq > 0) {
+    if (need_eq == s_eq) {
+      // the whole tie group is taken: any order
+      for (int i = tid; i < nt; i += kBowThreads) {
+        const uint32_t e = touched[i];
+        if (acc[e] == vk) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          s_sel_val[pos] = vk;
+          s_sel_ent[pos] = e;
+        }
       }
-      taken += __popc(bal);
+    } else if (warp == 0) {
+      // the cut splits a tie group (rare): ties are taken in ascending entry id, found by a
+      // sweep of the dense accumulators in entry order
+      int taken = 0;
+      for (uint32_t e0 = 0; e0 < tile_n && taken < need_eq; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const bool hit = e < tile_n && acc[e] == vk;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+        const int pos = taken + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < need_eq) {
+          s_sel_val[n_gt + pos] = vk;
+          s_sel_ent[n_gt + pos] = e;
+        }
+        taken += __popc(bal);
+      }
     }
   }
   __syncthreads();
@@ -260,17 +249,43 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
   if (tid == 0) a.out_count[obase] = keff;
 }
 
+// Applies one incremental update of an inverted file (bow_merge.h BowInvFile::plan_append): thread
+// i copies relocated row i, writes new posting i and sets row-table entry i; the three target
+// disjoint slots, so no ordering between them is needed.
+__global__ void bow_append_kernel(uint2* rows, uint2* pool, const uint4* __restrict__ copies, int n_copies,
+                                  const uint4* __restrict__ posts, int n_posts, const uint4* __restrict__ row_cmds,
+                                  int n_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_copies) {
+    const uint4 c = copies[i];  // {src, dst, n}
+    for (uint32_t k = 0; k < c.z; ++k) pool[c.y + k] = pool[c.x + k];
+  }
+  if (i < n_posts) {
+    const uint4 p = posts[i];   // {dst, entry, weight bits}
+    pool[p.x] = make_uint2(p.y, p.z);
+  }
+  if (i < n_rows) {
+    const uint4 r = row_cmds[i];  // {row, start, len}
+    rows[r.x] = make_uint2(r.y, r.z);
+  }
+}
+
 void launch_bow(const BowArgs& a, cudaStream_t s) {
   const int grid = a.B * a.n_db * a.n_tiles;
   if (grid <= 0) return;
-  const size_t smem = (size_t)a.tile_entries * sizeof(unsigned long long);
-  static size_t configured = 0;
-  if (smem > configured) {
-    KML_CUDA(cudaFuncSetAttribute(bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = smem;
-  }
+  const size_t smem = (size_t)a.tile_entries * (sizeof(unsigned long long) + sizeof(uint16_t));
+  // the opt-in is per device and costs microseconds: set it on every launch that needs it instead of
+  // caching it in a process-wide static (a second GPU in the same process would never get it)
+  if (smem > 48 * 1024)
+    KML_CUDA(cudaFuncSetAttribute(bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KML_LAUNCH((bow_score_kernel), grid, kBowThreads, smem, s, a);
+}
+
+void launch_bow_append(uint2* rows, uint2* pool, const uint4* copies, int n_copies, const uint4* posts, int n_posts,
+                       const uint4* row_cmds, int n_rows, cudaStream_t s) {
+  const int n = max(n_copies, max(n_posts, n_rows));
+  if (n <= 0) return;
+  KML_LAUNCH((bow_append_kernel), (n + 255) / 256, 256, 0, s, rows, pool, copies, n_copies, posts, n_posts, row_cmds, n_rows);
 }
 
 }  // namespace kml

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/kml.h"
+#include "bow_merge.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,11 +44,16 @@ struct RobotDb {
   // addBowVector / addVLCFrame
   std::vector<int32_t> entry_to_frame;
   std::map<uint64_t, uint32_t> pose_to_entry;
-  // device CSR
+  // device inverted file: row table + posting pool (bow_merge.h BowInvFile is the host mirror).
+  // dirty = the pool must be rebuilt from the log (first use, bulk load, or an append that did not
+  // fit); otherwise the postings of the vectors added since the last query wait in `pend_*` and
+  // are appended in place by the next query (cost independent of the database size).
   bool dirty = true;
-  uint32_t W = 0;
-  DevBuf<uint32_t> row_ptr;
+  BowInvFile inv;
+  DevBuf<uint2> rows;
   DevBuf<uint2> postings;
+  std::vector<uint32_t> pend_word, pend_entry, pend_wbits;
+  DevBuf<uint4> d_cmds;
   // device copies of entry_to_pose / entry_to_frame (read by select_candidates_kernel): entries
   // [0, synced) are on the device except the ones listed in frame_patches
   DevBuf<uint64_t> d_entry_pose;

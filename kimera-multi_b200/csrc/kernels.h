@@ -27,11 +27,11 @@ double measure_popc_peak(cudaStream_t s);
 double measure_fp64_peak(cudaStream_t s);
 
 // ----------------------------------------------------------------- bow.cu
-// Device view of one robot's inverted file (CSR over word ids).
+// Device view of one robot's inverted file: row w (= word id) holds pool[rows[w].x, + rows[w].y).
 struct BowDb {
-  const uint32_t* row_ptr;  // [W+1]
-  const uint2* postings;    // {entry, float bits of weight}, rows ascending in entry
-  uint32_t W;               // number of word rows
+  const uint2* rows;     // [W] {start (even: rows are 16-byte aligned), len}
+  const uint2* postings; // the pool: {entry, float bits of weight}, every row ascending in entry
+  uint32_t W;            // number of word rows
   uint32_t n_entries;
   // db_EntryId_to_PoseId_ and the dense frame-store index of every entry's keyframe (-1: the
   // keyframe's VLC frame has not been stored), read by the device-side candidate selection
@@ -66,6 +66,9 @@ struct BowArgs {
   unsigned long long* postings_touched;  // nullable: algorithmic postings counter
 };
 void launch_bow(const BowArgs& a, cudaStream_t s);
+// incremental update of an inverted file (bow_merge.h BowUpdate): row copies, new postings, row table
+void launch_bow_append(uint2* rows, uint2* pool, const uint4* copies, int n_copies, const uint4* posts, int n_posts,
+                       const uint4* row_cmds, int n_rows, cudaStream_t s);
 
 // -------------------------------------------------------------- ransac.cu
 // Per-pair RANSAC state (opengv::sac::Ransac::computeModel locals)

@@ -75,7 +75,17 @@ static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_
   db->ids.insert(db->ids.end(), ids, ids + n);
   db->vals.insert(db->vals.end(), vals, vals + n);
   db->off.push_back((int64_t)db->ids.size());
-  db->dirty = true;
+  if (!db->dirty) {  // the inverted file exists: queue this vector's postings for the in-place append
+    for (int i = 0; i < n; ++i) {
+      uint32_t bits;
+      memcpy(&bits, &vals[i], 4);
+      db->pend_word.push_back(ids[i]);
+      db->pend_entry.push_back(entry);
+      db->pend_wbits.push_back(bits);
+    }
+    // a bulk load is cheaper as one counting sort than as in-place appends
+    if (db->pend_word.size() > (size_t)(1u << 18) && db->pend_word.size() > db->inv.live / 2) db->dirty = true;
+  }
   {
     std::lock_guard<std::mutex> lk(h->sh->mu);
     h->sh->version++;
@@ -83,36 +93,75 @@ static int add_bow_host(kml_handle* h, RobotDb* db, uint64_t pose, const uint32_
   return KML_OK;
 }
 
-// rebuild the CSR inverted file of a robot (counting sort by word id; rows
-// come out ascending in entry id because entries are visited in order)
-static void rebuild_csr(kml_handle* h, RobotDb* db) {
-  static_assert(sizeof(BowPosting) == sizeof(uint2), "posting layout");
-  std::vector<uint32_t> row_ptr;
-  std::vector<BowPosting> post;
-  const uint32_t W = build_bow_csr(db->off, db->ids, db->vals, db->n_entries(), &row_ptr, &post);
-  db->row_ptr.scratch(row_ptr.size());
-  db->postings.scratch(std::max<size_t>(post.size(), 1));
-  KML_CUDA(cudaMemcpyAsync(db->row_ptr.p, row_ptr.data(), row_ptr.size() * 4,
-                           cudaMemcpyHostToDevice, h->stream));
-  if (!post.empty())
-    KML_CUDA(cudaMemcpyAsync(db->postings.p, post.data(), post.size() * sizeof(uint2),
-                             cudaMemcpyHostToDevice, h->stream));
+// Full (re)build of a robot's inverted file from its insertion log: counting sort by word id (rows
+// come out ascending in entry id because entries are visited in order), one upload.  Used for the
+// first query, after a bulk load, and when an incremental append does not fit (word beyond the row
+// table, pool full, more garbage than live postings).
+static void rebuild_invfile(kml_handle* h, RobotDb* db) {
+  static_assert(sizeof(BowPosting) == sizeof(uint2) && sizeof(BowRow) == sizeof(uint2), "inverted-file layout");
+  std::vector<BowRow> rows;
+  std::vector<BowPosting> pool;
+  db->inv.build(db->off, db->ids, db->vals, db->n_entries(), &rows, &pool);
+  if (db->rows.cap < rows.size() || db->postings.cap < db->inv.pool_cap) {
+    db->rows.scratch(rows.size());
+    db->postings.scratch((size_t)db->inv.pool_cap);
+  } else {
+    db->inv.pool_cap = db->postings.cap;  // keep the larger allocation
+  }
+  if (!rows.empty())
+    KML_CUDA(cudaMemcpyAsync(db->rows.p, rows.data(), rows.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+  if (!pool.empty())
+    KML_CUDA(cudaMemcpyAsync(db->postings.p, pool.data(), pool.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
   KML_CUDA(cudaStreamSynchronize(h->stream));
-  db->W = W;
+  db->pend_word.clear(); db->pend_entry.clear(); db->pend_wbits.clear();
   db->dirty = false;
+}
+
+// Appends the postings of the vectors added since the last query in place (BowInvFile::plan_append
+// + bow_append_kernel): O(new postings), independent of the database size — the deployment pattern
+// is one addBowVector per keyframe followed by a query
+// (/root/reference/launch/kimera_vio_jackal.launch:13-15).
+static void flush_appends(kml_handle* h, RobotDb* db) {
+  const size_t n = db->pend_word.size();
+  if (n == 0) return;
+  // (word, entry) order: stable sort by word keeps the entries of a word ascending
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return db->pend_word[x] < db->pend_word[y]; });
+  std::vector<uint32_t> w(n), e(n), b(n);
+  for (size_t i = 0; i < n; ++i) { w[i] = db->pend_word[order[i]]; e[i] = db->pend_entry[order[i]]; b[i] = db->pend_wbits[order[i]]; }
+  BowUpdate up;
+  if (!db->inv.plan_append(w.data(), e.data(), b.data(), n, &up)) {
+    rebuild_invfile(h, db);
+    return;
+  }
+  const size_t nc = up.copies.size(), np = up.posts.size(), nr = up.rows.size();
+  db->d_cmds.scratch(nc + np + nr);
+  cudaStream_t s = h->stream;
+  if (nc) KML_CUDA(cudaMemcpyAsync(db->d_cmds.p, up.copies.data(), nc * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(db->d_cmds.p + nc, up.posts.data(), np * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  KML_CUDA(cudaMemcpyAsync(db->d_cmds.p + nc + np, up.rows.data(), nr * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  launch_bow_append(db->rows.p, db->postings.p, db->d_cmds.p, (int)nc, db->d_cmds.p + nc, (int)np, db->d_cmds.p + nc + np, (int)nr, s);
+  h->stats.kernel_launches += 1;
+  KML_CUDA(cudaGetLastError());
+  KML_CUDA(cudaStreamSynchronize(s));  // `up` leaves scope; queries of other lanes follow
+  db->pend_word.clear(); db->pend_entry.clear(); db->pend_wbits.clear();
 }
 
 static void sync_db_maps(kml_handle* h, RobotDb* db);
 static BowDb db_view(kml_handle* h, RobotDb* db) {
   {
     std::lock_guard<std::mutex> lk(h->sh->mu);
-    if (db->dirty) rebuild_csr(h, db);
+    if (db->n_entries() > 0) {
+      if (db->dirty) rebuild_invfile(h, db);
+      else flush_appends(h, db);
+    }
     sync_db_maps(h, db);
   }
   BowDb v;
-  v.row_ptr = db->row_ptr.p;
+  v.rows = db->rows.p;
   v.postings = db->postings.p;
-  v.W = db->W;
+  v.W = db->n_entries() > 0 ? db->inv.W : 0u;
   v.n_entries = db->n_entries();
   v.entry_pose = db->d_entry_pose.p;
   v.entry_frame = db->d_entry_frame.p;

@@ -13,26 +13,70 @@ struct EmuDb {
   std::vector<float> vals;
   uint32_t n_entries = 0;
   bool dirty = true;
-  uint32_t W = 0;
-  std::vector<uint32_t> row_ptr;
-  std::vector<kml::BowPosting> post;
+  kml::BowInvFile inv;
+  std::vector<kml::BowRow> rows;
+  std::vector<kml::BowPosting> pool;
+  std::vector<uint32_t> pend_word, pend_entry, pend_wbits;
+  int rebuilds = 0, appends = 0;
 };
+// rebuild_invfile / flush_appends of lcd.cu on host vectors ("device" memory = the vectors)
+void sync_db(EmuDb* db) {
+  if (db->n_entries == 0) return;
+  if (!db->dirty && !db->pend_word.empty()) {
+    const size_t n = db->pend_word.size();
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return db->pend_word[x] < db->pend_word[y]; });
+    std::vector<uint32_t> w(n), e(n), b(n);
+    for (size_t i = 0; i < n; ++i) { w[i] = db->pend_word[order[i]]; e[i] = db->pend_entry[order[i]]; b[i] = db->pend_wbits[order[i]]; }
+    kml::BowUpdate up;
+    if (db->inv.plan_append(w.data(), e.data(), b.data(), n, &up)) {
+      static_assert(sizeof(kml::BowCopyCmd) == 16 && sizeof(kml::BowPostCmd) == 16 && sizeof(kml::BowRowCmd) == 16, "command layout");
+      kml::launch_bow_append(reinterpret_cast<uint2*>(db->rows.data()), reinterpret_cast<uint2*>(db->pool.data()),
+                             reinterpret_cast<const uint4*>(up.copies.data()), (int)up.copies.size(),
+                             reinterpret_cast<const uint4*>(up.posts.data()), (int)up.posts.size(),
+                             reinterpret_cast<const uint4*>(up.rows.data()), (int)up.rows.size(), nullptr);
+      db->appends++;
+    } else {
+      db->dirty = true;
+    }
+    db->pend_word.clear(); db->pend_entry.clear(); db->pend_wbits.clear();
+  }
+  if (db->dirty) {
+    db->inv.build(db->off, db->ids, db->vals, db->n_entries, &db->rows, &db->pool);
+    db->pool.resize((size_t)db->inv.pool_cap, kml::BowPosting{0xDEADBEEFu, 0xDEADBEEFu});  // device pool: unused slots are garbage
+    db->pend_word.clear(); db->pend_entry.clear(); db->pend_wbits.clear();
+    db->dirty = false;
+    db->rebuilds++;
+  }
+}
 }  // namespace
 
 extern "C" {
 
 void* bowemu_db_create() { return new EmuDb(); }
 void bowemu_db_destroy(void* p) { delete (EmuDb*)p; }
-// `count` vectors in CSR form, as kml_add_bow_bulk takes them
+int bowemu_db_rebuilds(void* p) { return ((EmuDb*)p)->rebuilds; }
+int bowemu_db_appends(void* p) { return ((EmuDb*)p)->appends; }
+// `count` vectors in CSR form, as kml_add_bow_bulk takes them (add_bow_host of lcd.cu: once the
+// inverted file exists the postings are queued for the in-place append)
 void bowemu_db_add(void* p, int count, const int64_t* off, const uint32_t* ids, const float* vals) {
   EmuDb* db = (EmuDb*)p;
   for (int i = 0; i < count; ++i) {
+    const uint32_t entry = db->n_entries;
     db->ids.insert(db->ids.end(), ids + off[i], ids + off[i + 1]);
     db->vals.insert(db->vals.end(), vals + off[i], vals + off[i + 1]);
     db->off.push_back((int64_t)db->ids.size());
     db->n_entries++;
+    if (!db->dirty)
+      for (int64_t k = off[i]; k < off[i + 1]; ++k) {
+        uint32_t bits;
+        memcpy(&bits, &vals[k], 4);
+        db->pend_word.push_back(ids[k]);
+        db->pend_entry.push_back(entry);
+        db->pend_wbits.push_back(bits);
+      }
   }
-  db->dirty = true;
 }
 
 // What run_bow (lcd.cu) does around the launch: views, tiling, one CTA per (query, db, tile),
@@ -48,14 +92,12 @@ int bowemu_query(void** dbs_, int n_db, int B, const int64_t* q_off, const uint3
   uint32_t max_entries = 1;
   for (int i = 0; i < n_db; ++i) {
     EmuDb* db = (EmuDb*)dbs_[i];
-    if (db->dirty) {
-      db->W = kml::build_bow_csr(db->off, db->ids, db->vals, db->n_entries, &db->row_ptr, &db->post);
-      db->dirty = false;
-    }
-    views[i].row_ptr = db->row_ptr.data();
-    views[i].postings = reinterpret_cast<const uint2*>(db->post.data());
-    views[i].W = db->W;
+    sync_db(db);
+    views[i].rows = reinterpret_cast<const uint2*>(db->rows.data());
+    views[i].postings = reinterpret_cast<const uint2*>(db->pool.data());
+    views[i].W = db->n_entries ? db->inv.W : 0u;
     views[i].n_entries = db->n_entries;
+    views[i].entry_pose = nullptr; views[i].entry_frame = nullptr; views[i].robot = (uint64_t)i;
     max_entries = std::max(max_entries, db->n_entries);
   }
   int tile = 0, n_tiles = 0;
@@ -80,7 +122,7 @@ int bowemu_query(void** dbs_, int n_db, int B, const int64_t* q_off, const uint3
   a.postings_touched = &touched;
   kml_emu::Idx3 grid;
   grid.x = (unsigned)(B * n_db * n_tiles); grid.y = 1;
-  kml_emu::launch(grid, kml::kBowThreads, (size_t)tile * sizeof(unsigned long long), [&] { kml::bow_score_kernel(a); });
+  kml_emu::launch(grid, kml::kBowThreads, (size_t)tile * (sizeof(unsigned long long) + sizeof(uint16_t)), [&] { kml::bow_score_kernel(a); });
   kml::merge_bow_tiles(t_entry.data(), t_score.data(), t_count.data(), B, n_db, n_tiles, K, out_entry, out_score,
                        out_count);
   if (postings_touched) *postings_touched = touched;

@@ -90,9 +90,16 @@ def _check_against_oracle(db, qi, qv, K, max_id, e1, s1):
     return len(e0)
 
 
+def _bow_tile(n, cap=20480):
+    """bow_tiling of csrc/bow_merge.h: equal tiles of at most `cap` entries, a multiple of 256"""
+    nt = (n + cap - 1) // cap
+    t = (n + nt - 1) // nt
+    return max(256, (t + 255) // 256 * 256)
+
+
 def test_bow_kernel_database_spanning_several_entry_tiles(oracle, bowemu):
     """The scenario of tests/test_wide_database.py (one database of 60 000 entries = three
-    24 576-entry tiles, exact duplicates on both sides of every tile boundary, max_id cuts inside
+    equal entry tiles, exact duplicates on both sides of every tile boundary, max_id cuts inside
     the first and the last tile) through the emulated kernel and the product's tile merge."""
     rng = np.random.default_rng(77)
     n, words, vocab = 60000, 40, 3000
@@ -100,7 +107,8 @@ def test_bow_kernel_database_spanning_several_entry_tiles(oracle, bowemu):
     ids = (np.arange(words)[None, :] * (vocab // words) + base).astype(np.uint32)
     vals = rng.random((n, words)).astype(np.float32) + np.float32(0.01)
     vals = (vals / vals.sum(axis=1, keepdims=True)).astype(np.float32)
-    dup = [5, 24575, 24576, 49151, 49152, 59999]
+    T = _bow_tile(n)
+    dup = [5, T - 1, T, 2 * T - 1, 2 * T, 59999]
     for e in dup[1:]:
         ids[e], vals[e] = ids[dup[0]], vals[dup[0]]
     det = EmuDb(bowemu)
@@ -370,3 +378,33 @@ def test_results_do_not_depend_on_the_thread_schedule(schedule):
                         "-n", "4", "-k", "not schedule"], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=1200)
     assert r.returncode == 0 and "6 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_bow_incremental_appends_equal_a_rebuild(oracle, bowemu):
+    """BowInvFile::plan_append + bow_append_kernel (csrc/bow_merge.h, bow.cu): vectors added after
+    the first query are appended to the resident inverted file in place; the scorer must return the
+    oracle's results after every step, and the rows must have been appended, not rebuilt."""
+    rng = np.random.default_rng(9)
+    vocab, words = 400, 20
+
+    def vec():
+        ids = np.sort(rng.choice(vocab, words, replace=False)).astype(np.uint32)
+        v = rng.random(words).astype(np.float32) + np.float32(0.01)
+        return ids, (v / v.sum()).astype(np.float32)
+
+    det, db = EmuDb(bowemu), oracle.Database()
+    first = [vec() for _ in range(50)]
+    det.add_bulk(*_csr(first))
+    for i, v in first:
+        db.add(i, v)
+    for step in range(60):
+        new = [vec() for _ in range(1 + step % 3)]
+        det.add_bulk(*_csr(new))
+        for i, v in new:
+            db.add(i, v)
+        q = vec()
+        oe, osc, oc, _, _, _ = emu_query(bowemu, [det], [q], 20, [-1])
+        c = oc[0, 0]
+        assert _check_against_oracle(db, q[0], q[1], 20, -1, oe[0, 0, :c], osc[0, 0, :c]) > 0
+    assert bowemu.bowemu_db_rebuilds(det.h) <= 2 and bowemu.bowemu_db_appends(det.h) >= 55
+    det.close()

@@ -28,7 +28,8 @@
 
 namespace kml {
 
-constexpr int kBowThreads = 256;
+constexpr int kBowThreads = 256;      // databases whose tile leaves room for several CTAs per SM
+constexpr int kBowThreadsWide = 512;  // wide tiles (> 96 KB of shared memory): one CTA per SM, twice the threads
 
 __device__ __forceinline__ unsigned long long bow_term_fx(double q, double d) {
   // DBoW2: value = fabs(q-d) - fabs(q) - fabs(d)  (<= 0); contribution to the
@@ -38,7 +39,8 @@ __device__ __forceinline__ unsigned long long bow_term_fx(double q, double d) {
   return s > 0.0 ? (unsigned long long)s : 0ull;
 }
 
-__global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bow_score_kernel(BowArgs a) {
   KML_DYN_SMEM(unsigned char, smem_raw);
   // dynamic: accumulators [tile_entries] u64 | touched list [tile_entries] u16
   unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -47,7 +49,10 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
   __shared__ float s_vals[kBowMaxWords];
   __shared__ uint2 s_row[kBowMaxWords];
   __shared__ uint32_t s_hist[256];
-  __shared__ unsigned long long s_red[kBowThreads / 32];
+  __shared__ uint32_t s_pids[kBowMaxWords];  // previous BoW vector's word ids (NSS factor)
+  __shared__ unsigned long long s_red[THREADS / 32];
+  __shared__ unsigned long long s_bnd_val[32];  // boundary candidates of the early-exit select
+  __shared__ uint32_t s_bnd_ent[32];
   __shared__ unsigned long long s_sel_val[kBowMaxK];
   __shared__ uint32_t s_sel_ent[kBowMaxK];
   __shared__ unsigned long long s_prefix;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
 
   // ---- stage the query, look up its rows, clear the accumulators
   uint32_t tsum = 0;
-  for (int i = tid; i < nq; i += kBowThreads) {
+  for (int i = tid; i < nq; i += THREADS) {
     const uint32_t w = a.q_ids[q0 + i];
     s_ids[i] = w;
     s_vals[i] = a.q_vals[q0 + i];
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
     s_row[i] = r;
     tsum += r.y;
   }
-  for (uint32_t e = tid; e < tile_n; e += kBowThreads) acc[e] = 0ull;
+  for (uint32_t e = tid; e < tile_n; e += THREADS) acc[e] = 0ull;
   if (tid == 0) { s_ntouched = 0; s_cnt = 0; s_eq = 0; }
   __syncthreads();
 
@@ -86,15 +91,18 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
   if (a.nss != nullptr && dbi == 0 && tile == 0) {
     const int64_t p0 = a.p_off[b];
     const int np = (int)(a.p_off[b + 1] - p0);
+    const int nps = min(np, kBowMaxWords);
+    for (int i = tid; i < nps; i += THREADS) s_pids[i] = a.p_ids[p0 + i];
+    __syncthreads();
     unsigned long long part = 0ull;
-    for (int i = tid; i < nq; i += kBowThreads) {
+    for (int i = tid; i < nq; i += THREADS) {
       const uint32_t w = s_ids[i];
-      int lo = 0, hi = np;  // lower_bound
+      int lo = 0, hi = nps;  // lower_bound
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (a.p_ids[p0 + mid] < w) lo = mid + 1; else hi = mid;
+        if (s_pids[mid] < w) lo = mid + 1; else hi = mid;
       }
-      if (lo < np && a.p_ids[p0 + lo] == w)
+      if (lo < nps && s_pids[lo] == w)
         part += bow_term_fx((double)s_vals[i], (double)a.p_vals[p0 + lo]);
     }
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
     __syncthreads();
     if (tid == 0) {
       unsigned long long tot = 0ull;
-      for (int w = 0; w < kBowThreads / 32; ++w) tot += s_red[w];
+      for (int w = 0; w < THREADS / 32; ++w) tot += s_red[w];
       a.nss[b] = (double)tot / kBowScale;
     }
   }
@@ -111,26 +119,42 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
     if (lane == 0 && tsum) atomicAdd(a.postings_touched, (unsigned long long)tsum);
   }
 
-  // ---- stream the touched rows: 8 lanes per row, 128-bit loads (2 postings per lane)
+  // ---- stream the touched rows: 8 lanes per row, 128-bit loads (2 postings per lane); every
+  // group keeps the first load of four rows in flight (rows are short: the loop is latency-bound)
   {
+    constexpr int G = THREADS / 8;
     const int grp = tid >> 3, gl = tid & 7;
     const uint4* pool4 = reinterpret_cast<const uint4*>(db.postings);
-    for (int i = grp; i < nq; i += kBowThreads / 8) {
-      const uint2 r = s_row[i];
-      const double qv = (double)s_vals[i];
-      for (uint32_t k = 2u * gl; k < r.y; k += 16u) {
-        const uint4 p = __ldg(pool4 + ((r.x + k) >> 1));
+    auto add2 = [&](const uint4& p, uint32_t k, uint32_t len, double qv) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t e = h ? p.z : p.x, wb = h ? p.w : p.y;
-          if (k + h < r.y && e >= tile_lo && e - tile_lo < tile_n && (max_id < 0 || (int)e < max_id)) {
-            const unsigned long long fx = bow_term_fx(qv, (double)__uint_as_float(wb));
-            if (fx != 0ull) {
-              const unsigned long long old = atomicAdd(&acc[e - tile_lo], fx);
-              if (old == 0ull) touched[atomicAdd(&s_ntouched, 1)] = (uint16_t)(e - tile_lo);  // exactly one adder sees zero
-            }
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t e = h ? p.z : p.x, wb = h ? p.w : p.y;
+        if (k + h < len && e >= tile_lo && e - tile_lo < tile_n && (max_id < 0 || (int)e < max_id)) {
+          const unsigned long long fx = bow_term_fx(qv, (double)__uint_as_float(wb));
+          if (fx != 0ull) {
+            const unsigned long long old = atomicAdd(&acc[e - tile_lo], fx);
+            if (old == 0ull) touched[atomicAdd(&s_ntouched, 1)] = (uint16_t)(e - tile_lo);  // exactly one adder sees zero
           }
         }
+      }
+    };
+    for (int i0 = grp; i0 < nq; i0 += 4 * G) {
+      uint2 r[4];
+      uint4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * G;
+        r[u] = i < nq ? s_row[i] : make_uint2(0u, 0u);
+        p[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (2u * gl < r[u].y) p[u] = __ldg(pool4 + ((r[u].x + 2u * gl) >> 1));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * G;
+        if (i >= nq) continue;
+        const double qv = (double)s_vals[i];
+        add2(p[u], 2u * gl, r[u].y, qv);
+        for (uint32_t k = 2u * gl + 16u; k < r[u].y; k += 16u) add2(__ldg(pool4 + ((r[u].x + k) >> 1)), k, r[u].y, qv);
       }
     }
   }
@@ -144,16 +168,23 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
     if (tid == 0) a.out_count[obase] = 0;
     return;
   }
-  unsigned long long vk = 0ull;  // value of the keff-th best; 0 = every touched entry is selected
-  int need_eq = 0;
+  // The keff best by (value desc, entry asc).  MSB radix select over the touched list, 8 bits per
+  // pass, histogram scanned by warp 0 with shuffles.  After a pass every entry whose prefix is above
+  // the selected bin is in, every entry below it is out, and only the bin itself is undecided: as
+  // soon as the bin holds at most 32 entries the passes stop and one warp ranks those directly.
+  // Otherwise (many equal values) all 8 passes run and the cut falls inside a group of equal values,
+  // which is taken in ascending entry id.
+  int shift = 64;          // bits of the value below the decided prefix
+  int need_eq = keff;      // entries to take from the undecided set
+  int n_bnd = 0;           // size of the undecided set when the passes stopped early
   if (nt > a.K) {
-    if (tid == 0) { s_need = keff; s_prefix = 0ull; }
-    // 8-pass MSB radix select of the keff-th largest accumulator value over the touched list
+    if (tid == 0) { s_need = keff; s_prefix = 0ull; s_eq = nt; }
     for (int pass = 7; pass >= 0; --pass) {
-      s_hist[tid] = 0;
+      if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
+      if (s_eq <= 32) break;  // uniform: s_eq is only written between barriers
       const unsigned long long pref = s_prefix;
-      for (int i = tid; i < nt; i += kBowThreads) {
+      for (int i = tid; i < nt; i += THREADS) {
         const unsigned long long v = acc[touched[i]];
         if (pass == 7 || (v >> (8 * (pass + 1))) == pref)
           atomicAdd(&s_hist[(uint32_t)(v >> (8 * pass)) & 255u], 1u);
@@ -179,53 +210,77 @@ __global__ void __launch_bounds__(kBowThreads) bow_score_kernel(BowArgs a) {
             if (before < need && before + h[k] >= need) {
               s_need = (int)(need - before);
               s_prefix = (pref << 8) | (unsigned long long)(255 - (lane * 8 + k));
-              if (pass == 0) s_eq = (int)h[k];  // how many touched entries hold exactly the cut value
-              before = need;  // stop
+              s_eq = (int)h[k];  // entries in the undecided bin
+              before = need;     // stop
             } else if (before < need) {
               before += h[k];
             }
           }
         }
       }
+      shift = 8 * pass;
       __syncthreads();
     }
-    vk = s_prefix;
-    need_eq = s_need;  // how many entries equal to vk to take
+    need_eq = s_need;
+    n_bnd = s_eq;
   }
+  const unsigned long long pref = (nt > a.K) ? s_prefix : 0ull;
   const int n_gt = keff - need_eq;
-  // entries strictly above the cut (unordered; the rank sort orders them)
-  for (int i = tid; i < nt; i += kBowThreads) {
-    const uint32_t e = touched[i];
-    const unsigned long long v = acc[e];
-    if (v > vk) {
-      const int pos = atomicAdd(&s_cnt, 1);
-      s_sel_val[pos] = v;
-      s_sel_ent[pos] = e;
+  // decided entries (prefix above the bin; everything when nt <= K) in any order, the undecided
+  // ones to the boundary buffer (early exit) — the rank sort below orders the output
+  if (nt <= a.K) {
+    for (int i = tid; i < nt; i += THREADS) {
+      const uint32_t e = touched[i];
+      s_sel_val[i] = acc[e];
+      s_sel_ent[i] = e;
     }
-  }
-  __syncthreads();
-  if (need_eq > 0) {
-    if (need_eq == s_eq) {
-      // the whole tie group is taken: any order
-      for (int i = tid; i < nt; i += kBowThreads) {
-        const uint32_t e = touched[i];
-        if (acc[e] == vk) {
-          const int pos = atomicAdd(&s_cnt, 1);
-          s_sel_val[pos] = vk;
-          s_sel_ent[pos] = e;
+  } else {
+    if (tid == 0) s_ntouched = 0;  // reused as the boundary counter
+    __syncthreads();
+    for (int i = tid; i < nt; i += THREADS) {
+      const uint32_t e = touched[i];
+      const unsigned long long v = acc[e];
+      const unsigned long long hi = shift >= 64 ? 0ull : (v >> shift);
+      if (hi > pref) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        s_sel_val[pos] = v;
+        s_sel_ent[pos] = e;
+      } else if (hi == pref && n_bnd <= 32) {
+        const int pos = atomicAdd(&s_ntouched, 1);
+        s_bnd_val[pos] = v;
+        s_bnd_ent[pos] = e;
+      }
+    }
+    __syncthreads();
+    if (n_bnd <= 32) {
+      // one warp ranks the undecided entries by (value desc, entry asc) and takes the first need_eq
+      if (warp == 0) {
+        const bool have = lane < n_bnd;
+        const unsigned long long v = have ? s_bnd_val[lane] : 0ull;
+        const uint32_t e = have ? s_bnd_ent[lane] : 0xFFFFFFFFu;
+        int rank = 0;
+        for (int j = 0; j < n_bnd; ++j) {
+          const unsigned long long vj = s_bnd_val[j];
+          const uint32_t ej = s_bnd_ent[j];
+          rank += (vj > v) || (vj == v && ej < e);
+        }
+        if (have && rank < need_eq) {
+          s_sel_val[n_gt + rank] = v;
+          s_sel_ent[n_gt + rank] = e;
         }
       }
     } else if (warp == 0) {
-      // the cut splits a tie group (rare): ties are taken in ascending entry id, found by a
-      // sweep of the dense accumulators in entry order
+      // all 8 passes ran: the undecided entries all hold exactly the value `pref`, more than 32 of
+      // them (rare).  Ties are taken in ascending entry id, found by a sweep of the dense
+      // accumulators in entry order.
       int taken = 0;
       for (uint32_t e0 = 0; e0 < tile_n && taken < need_eq; e0 += 32) {
         const uint32_t e = e0 + lane;
-        const bool hit = e < tile_n && acc[e] == vk;
+        const bool hit = e < tile_n && acc[e] == pref;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
         const int pos = taken + __popc(bal & ((1u << lane) - 1u));
         if (hit && pos < need_eq) {
-          s_sel_val[n_gt + pos] = vk;
+          s_sel_val[n_gt + pos] = pref;
           s_sel_ent[n_gt + pos] = e;
         }
         taken += __popc(bal);
@@ -276,9 +331,14 @@ void launch_bow(const BowArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)a.tile_entries * (sizeof(unsigned long long) + sizeof(uint16_t));
   // the opt-in is per device and costs microseconds: set it on every launch that needs it instead of
   // caching it in a process-wide static (a second GPU in the same process would never get it)
-  if (smem > 48 * 1024)
-    KML_CUDA(cudaFuncSetAttribute(bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KML_LAUNCH((bow_score_kernel), grid, kBowThreads, smem, s, a);
+  if (smem > 96 * 1024) {
+    KML_CUDA(cudaFuncSetAttribute(bow_score_kernel<kBowThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KML_LAUNCH((bow_score_kernel<kBowThreadsWide>), grid, kBowThreadsWide, smem, s, a);
+  } else {
+    if (smem > 48 * 1024)
+      KML_CUDA(cudaFuncSetAttribute(bow_score_kernel<kBowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KML_LAUNCH((bow_score_kernel<kBowThreads>), grid, kBowThreads, smem, s, a);
+  }
 }
 
 void launch_bow_append(uint2* rows, uint2* pool, const uint4* copies, int n_copies, const uint4* posts, int n_posts,

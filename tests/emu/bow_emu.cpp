@@ -122,7 +122,7 @@ int bowemu_query(void** dbs_, int n_db, int B, const int64_t* q_off, const uint3
   a.postings_touched = &touched;
   kml_emu::Idx3 grid;
   grid.x = (unsigned)(B * n_db * n_tiles); grid.y = 1;
-  kml_emu::launch(grid, kml::kBowThreads, (size_t)tile * (sizeof(unsigned long long) + sizeof(uint16_t)), [&] { kml::bow_score_kernel(a); });
+  kml::launch_bow(a, nullptr);
   kml::merge_bow_tiles(t_entry.data(), t_score.data(), t_count.data(), B, n_db, n_tiles, K, out_entry, out_score,
                        out_count);
   if (postings_touched) *postings_touched = touched;

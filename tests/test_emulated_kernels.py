@@ -408,3 +408,37 @@ def test_bow_incremental_appends_equal_a_rebuild(oracle, bowemu):
         assert _check_against_oracle(db, q[0], q[1], 20, -1, oe[0, 0, :c], osc[0, 0, :c]) > 0
     assert bowemu.bowemu_db_rebuilds(det.h) <= 2 and bowemu.bowemu_db_appends(det.h) >= 55
     det.close()
+
+
+def test_bow_cut_inside_a_large_tie_group(oracle, bowemu):
+    """100 copies of one vector among 300 others, K = 50: the cut falls inside a group of exactly
+    equal scores larger than a warp (all eight radix passes run, then the dense sweep): the copies
+    with the lowest entry ids are taken, in ascending id; K = 120 takes the whole group and fills up
+    with the runners-up (early-exit path)."""
+    rng = np.random.default_rng(4)
+    vocab, words = 500, 16
+
+    def vec():
+        ids = np.sort(rng.choice(vocab, words, replace=False)).astype(np.uint32)
+        v = rng.random(words).astype(np.float32) + np.float32(0.01)
+        return ids, (v / v.sum()).astype(np.float32)
+
+    twin = vec()
+    vecs = [vec() for _ in range(300)]
+    twin_at = sorted(rng.choice(400, 100, replace=False).tolist())
+    allv, k = [], 0
+    for e in range(400):
+        if e in twin_at:
+            allv.append(twin)
+        else:
+            allv.append(vecs[k]); k += 1
+    det, db = EmuDb(bowemu), oracle.Database()
+    det.add_bulk(*_csr(allv))
+    for i, v in allv:
+        db.add(i, v)
+    oe, osc, oc, _, _, _ = emu_query(bowemu, [det], [twin], 50, [-1])
+    assert oc[0, 0] == 50 and list(oe[0, 0]) == twin_at[:50] and np.all(np.abs(osc[0, 0] - 1.0) < 1e-6)
+    oe, osc, oc, _, _, _ = emu_query(bowemu, [det], [twin], 120, [-1])
+    assert oc[0, 0] == 120 and list(oe[0, 0, :100]) == twin_at
+    assert _check_against_oracle(db, twin[0], twin[1], 120, -1, oe[0, 0, :120], osc[0, 0, :120]) == 120
+    det.close()

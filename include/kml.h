@@ -175,7 +175,8 @@ int kml_compute_matched_indices(kml_handle* h, uint64_t q_robot, uint64_t q_pose
 int kml_geometric_verification_nister(kml_handle* h, uint64_t q_robot, uint64_t q_pose,
                                       uint64_t m_robot, uint64_t m_pose, uint32_t* inl_q,
                                       uint32_t* inl_m, int* count, double* R);
-/* T = T_query_match row-major 3x4; R_prior may be NULL (unused by Arun) */
+/* T = T_query_match row-major 3x4; R_prior may be NULL.  Arun's 3-point solver does not read it;
+ * with kml_params.ransac_use_1point_3d3d it IS the rotation and hypotheses are single point pairs */
 int kml_recover_pose(kml_handle* h, uint64_t q_robot, uint64_t q_pose, uint64_t m_robot,
                      uint64_t m_pose, uint32_t* inl_q, uint32_t* inl_m, int* count,
                      const double* R_prior, double* T);
@@ -226,6 +227,12 @@ int kml_ransac_arun_batch(kml_handle* h, int P, int N, const double* p1, const d
                           int full_hypotheses, double* models, int32_t* n_inliers,
                           int32_t* iterations, int32_t* best_draw, uint32_t* inlier_mask,
                           float* ms_kernel);
+/* Row f4, ransac_use_1point_3d3d (/root/reference/params/D455/LcdParams.yaml:58): the point-cloud
+ * problem with the rotation given, R [P][9] row-major; a hypothesis is ONE correspondence,
+ * model = [R | p1_i - R p2_i], residual and thresholds as kml_ransac_arun_batch. */
+int kml_ransac_onepoint_batch(kml_handle* h, int P, int N, const double* p1, const double* p2, const double* R,
+                              int full_hypotheses, double* models, int32_t* n_inliers, int32_t* iterations,
+                              int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel);
 /* Batched Ransac<CentralRelativePoseSacProblem>(NISTER): f1/f2 [P][N][3]. */
 int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const double* f2,
                             int full_hypotheses, double* models, int32_t* n_inliers,

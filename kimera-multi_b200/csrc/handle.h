@@ -105,8 +105,8 @@ struct kml_shared {
   // ---- pre-drawn sample stream + k tables
   std::vector<uint32_t> raw_h;
   kml::DevBuf<uint32_t> d_raw;
-  int ktable_n_mono = 0, ktable_n_stereo = 0;
-  kml::DevBuf<double> d_ktable_mono, d_ktable_stereo;
+  int ktable_n_mono = 0, ktable_n_stereo = 0, ktable_n_stereo1 = 0;
+  kml::DevBuf<double> d_ktable_mono, d_ktable_stereo, d_ktable_stereo1;  // sample sizes 8, 3, 1
 
   // ---- vocabulary tree (row f1: TemplatedVocabulary::transform)
   int voc_k = 0, voc_L = 0;
@@ -186,6 +186,7 @@ struct kml_handle {
   kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
   kml::DevBuf<uint8_t> d_scratch, d_scratch2;
+  kml::DevBuf<double> d_prior;   // rotation prior of the single-pair recoverPose (row f4)
   // batch records: the all-gather buffer of the sharded query (rank r's block at r * blk; a single
   // GPU has one block), the merged records, the batch counters and their pinned host copies
   kml::DevBuf<uint8_t> d_blocks, d_merged;

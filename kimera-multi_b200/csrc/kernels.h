@@ -117,6 +117,10 @@ struct SacArgs {
   int max_iterations;
   int full;              // evaluate every draw up to max_iterations+1 (no adaptive stop)
   int force_generic;     // test hook (env KML_FORCE_GENERIC_ISOLATE): skip the register fast path of stage 2
+  // stereo, row f4 (ransac_use_1point_3d3d): the rotation is given per problem, prior[p] = row-major
+  // 3x4 whose left 3x3 block is R (the mono model); a draw is ONE correspondence, model = [R | p1 - R p2]
+  int onept;
+  const double* prior;   // [P][12]
   uint32_t* inlier_mask; // [P][mask_words]
   int mask_words;
   int32_t* n_inliers;    // [P]

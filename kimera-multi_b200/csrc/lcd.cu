@@ -379,13 +379,16 @@ struct SacBufs {
 // problems whose loop has not ended when the select kernel runs.
 static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
                            const int32_t* d_N, int stride, int full, SacBufs out, int mask_words,
-                           unsigned int* pending) {
+                           unsigned int* pending, const double* d_prior = nullptr) {
   const size_t Pa = (size_t)std::max(P, 1);
   const kml_params& prm = h->prm;
-  const int S = mono ? 8 : 3;
+  const bool onept = !mono && d_prior != nullptr;  // row f4: rotation given, 1-point samples
+  const int S = mono ? 8 : (onept ? 1 : 3);
   const int max_it = mono ? prm.max_ransac_iterations_mono : prm.max_ransac_iterations;
   if (mono)
     ensure_ktable(h, stride, 8, prm.ransac_probability_mono, &h->sh->d_ktable_mono, &h->sh->ktable_n_mono);
+  else if (onept)
+    ensure_ktable(h, stride, 1, prm.ransac_probability, &h->sh->d_ktable_stereo1, &h->sh->ktable_n_stereo1);
   else
     ensure_ktable(h, stride, 3, prm.ransac_probability, &h->sh->d_ktable_stereo, &h->sh->ktable_n_stereo);
   const int raw_len = (int)h->sh->raw_h.size();
@@ -432,8 +435,10 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.item_base = h->d_item_base.p; a.item_list = h->d_item_list.p; a.item_q = h->d_item_q.p;
   a.item_model = h->d_item_model.p; a.item_status = h->d_item_status.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
-  a.ktable = mono ? h->sh->d_ktable_mono.p : h->sh->d_ktable_stereo.p;
-  a.ktable_n = mono ? h->sh->ktable_n_mono : h->sh->ktable_n_stereo;
+  a.ktable = mono ? h->sh->d_ktable_mono.p : onept ? h->sh->d_ktable_stereo1.p : h->sh->d_ktable_stereo.p;
+  a.ktable_n = mono ? h->sh->ktable_n_mono : onept ? h->sh->ktable_n_stereo1 : h->sh->ktable_n_stereo;
+  a.onept = onept ? 1 : 0;
+  a.prior = d_prior;
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
   a.sq_crit = sq_crit_of(prm.ransac_threshold);
   a.max_iterations = max_it; a.full = full;
@@ -450,7 +455,7 @@ static void enqueue_sac(kml_handle* h, bool mono, const SacArgs& a, SacBufs out)
   cudaStream_t s = h->stream;
   KML_CUDA(cudaMemsetAsync(out.best->p, 0, sizeof(double) * 12 * a.P, s));
   KML_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(unsigned int), s));
-  launch_sac_init(a, mono ? 8 : 3, s);
+  launch_sac_init(a, mono ? 8 : (a.onept ? 1 : 3), s);
   h->stats.kernel_launches += 1;
   for (int r = 0; r < kSacRounds; ++r)
     h->stats.kernel_launches += mono ? launch_mono_round(a, r, s) : launch_stereo_round(a, r, s);
@@ -493,9 +498,10 @@ static bool finish_sac(kml_handle* h, bool mono, const SacArgs& a0) {
 
 // prepare + enqueue + finish for the single-problem entry points (synchronous)
 static SacArgs run_sac_sync(kml_handle* h, bool mono, int P, const double* d_a, const double* d_b,
-                            const int32_t* d_N, int stride, int full, SacBufs out, int mask_words) {
+                            const int32_t* d_N, int stride, int full, SacBufs out, int mask_words,
+                            const double* d_prior = nullptr) {
   for (int attempt = 0;; ++attempt) {
-    SacArgs a = prepare_sac(h, mono, P, d_a, d_b, d_N, stride, full, out, mask_words, nullptr);
+    SacArgs a = prepare_sac(h, mono, P, d_a, d_b, d_N, stride, full, out, mask_words, nullptr, d_prior);
     enqueue_sac(h, mono, a, out);
     if (finish_sac(h, mono, a)) return a;
     if (attempt >= 6) throw std::runtime_error("RANSAC item lists keep overflowing");
@@ -781,7 +787,8 @@ static void batch_enqueue(kml_handle* h, int cap, uint8_t* blk, BatchPlan* pl) {
   SacBufs mono{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono};
   pl->mono = prepare_sac(h, true, P, h->d_a.p, h->d_b.p, h->d_M.p, stride, 0, mono, mask_words, &h->d_stats.p->pending_m);
   SacBufs st3{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
-  pl->stereo = prepare_sac(h, false, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, st3, mask_words, &h->d_stats.p->pending_s);
+  pl->stereo = prepare_sac(h, false, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, st3, mask_words, &h->d_stats.p->pending_s,
+                           h->prm.ransac_use_1point_3d3d ? h->d_best_mono.p : nullptr);
   enqueue_sac(h, true, pl->mono, mono);
   FinalizeArgs& f = pl->fin;
   f.P = P; f.mono_st = h->d_st_mono.p; f.mono_inl = h->d_inl_mono.p; f.M = h->d_M.p;
@@ -982,7 +989,7 @@ static bool stored_query_side(kml_handle* h, uint64_t robot, uint64_t pose, Quer
 // gather + RANSAC on caller-provided index lists for ONE stored pair
 static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint64_t mr,
                         uint64_t mp, uint32_t* inl_q, uint32_t* inl_m, int* count, double* model12,
-                        int* n_valid_out) {
+                        int* n_valid_out, const double* R_prior = nullptr) {
   if (!inl_q || !inl_m || !count || *count < 0) return fail(h, KML_ERR_ARG, "bad index lists");
   QuerySide qs;
   if (!stored_query_side(h, qr, qp, &qs)) return KML_NO_FRAME;
@@ -1029,7 +1036,16 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
     launch_gather_points(sg, s);
   }
   h->stats.kernel_launches += 1;
-  run_sac_sync(h, mono, 1, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, bufs, mask_words);
+  const double* d_prior = nullptr;
+  if (!mono && R_prior && h->prm.ransac_use_1point_3d3d) {  // row f4: the rotation is given
+    double pr[12] = {R_prior[0], R_prior[1], R_prior[2], 0.0, R_prior[3], R_prior[4], R_prior[5], 0.0,
+                     R_prior[6], R_prior[7], R_prior[8], 0.0};
+    h->d_prior.scratch(12);
+    KML_CUDA(cudaMemcpyAsync(h->d_prior.p, pr, sizeof(pr), cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaStreamSynchronize(s));
+    d_prior = h->d_prior.p;
+  }
+  run_sac_sync(h, mono, 1, h->d_a.p, h->d_b.p, h->d_N3.p, stride, 0, bufs, mask_words, d_prior);
   SacState st;
   int32_t N = 0, ninl = 0;
   std::vector<uint32_t> mask(mask_words);
@@ -1045,7 +1061,7 @@ static int sac_on_lists(kml_handle* h, bool mono, uint64_t qr, uint64_t qp, uint
   KML_CUDA(cudaStreamSynchronize(s));
   if (st.exhausted) return fail(h, KML_ERR_STREAM_EXHAUSTED, "pre-drawn sample stream exhausted");  // cannot happen: the stream covers the loop's own limits
   *n_valid_out = N;
-  if (N < (mono ? 8 : 3)) return KML_TOO_FEW_POINTS;
+  if (N < (mono ? 8 : 3)) return KML_TOO_FEW_POINTS;  // recoverPose needs three points in either stereo mode
   if (st.best_draw < 0) return KML_RANSAC_FAIL;
   const kml_params& P = h->prm;
   if (ninl < P.geometric_verification_min_inlier_count) return KML_TOO_FEW_INLIERS;
@@ -1299,12 +1315,13 @@ int kml_recover_pose(kml_handle* h, uint64_t qr, uint64_t qp, uint64_t mr, uint6
                      uint32_t* inl_q, uint32_t* inl_m, int* count, const double* R_prior,
                      double* T) {
   KML_API_BEGIN(h)
-  (void)R_prior;  // adapter.setR12(prior) is not read by threept_arun
+  // adapter.setR12(prior) is not read by threept_arun; with ransac_use_1point_3d3d the
+  // prior IS the rotation and one point pair per hypothesis gives the translation (row f4)
   if (!T) return fail(h, KML_ERR_ARG, "null output");
   h->stats.total_geometric_verifications += 1;
   double M[12];
   int nvalid = 0;
-  int rc = sac_on_lists(h, false, qr, qp, mr, mp, inl_q, inl_m, count, M, &nvalid);
+  int rc = sac_on_lists(h, false, qr, qp, mr, mp, inl_q, inl_m, count, M, &nvalid, R_prior);
   if (rc != KML_OK) return rc;
   memcpy(T, M, 96);
   return KML_OK;
@@ -1501,7 +1518,7 @@ int kml_host_free(void* p) {
 // ------------------------------------------------- batched RANSAC (C4 etc.)
 static int ransac_batch(kml_handle* h, bool mono, int P, int N, const double* a, const double* b,
                         int full, double* models, int32_t* n_inliers, int32_t* iterations,
-                        int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
+                        int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel, const double* R9 = nullptr) {
   if (P < 0 || N < 0 || N > 65535 || (P > 0 && N > 0 && (!a || !b))) return fail(h, KML_ERR_ARG, "ransac_batch: bad argument");
   if (P == 0) return KML_OK;
   const int stride = std::max(N, 8);
@@ -1517,8 +1534,19 @@ static int ransac_batch(kml_handle* h, bool mono, int P, int N, const double* a,
   }
   SacBufs bufs = mono ? SacBufs{&h->d_st_mono, &h->d_best_mono, &h->d_mask_mono, &h->d_inl_mono}
                       : SacBufs{&h->d_st_stereo, &h->d_best_stereo, &h->d_mask_stereo, &h->d_inl_stereo};
+  const double* d_prior = nullptr;
+  if (R9 && !mono) {  // 1-point problem: per-problem rotation as the left block of a 3x4
+    std::vector<double> pr((size_t)P * 12, 0.0);
+    for (int p = 0; p < P; ++p)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) pr[(size_t)p * 12 + 4 * r + c] = R9[(size_t)p * 9 + 3 * r + c];
+    h->d_prior.scratch(pr.size());
+    KML_CUDA(cudaMemcpyAsync(h->d_prior.p, pr.data(), pr.size() * 8, cudaMemcpyHostToDevice, s));
+    KML_CUDA(cudaStreamSynchronize(s));
+    d_prior = h->d_prior.p;
+  }
   KML_CUDA(cudaEventRecord(h->ev[2], s));
-  run_sac_sync(h, mono, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, full, bufs, mask_words);
+  run_sac_sync(h, mono, P, h->d_a.p, h->d_b.p, h->d_N3.p, stride, full, bufs, mask_words, d_prior);
   KML_CUDA(cudaEventRecord(h->ev[3], s));
   std::vector<SacState> st(P);
   std::vector<uint32_t> mask((size_t)P * mask_words);
@@ -1552,6 +1580,14 @@ int kml_ransac_arun_batch(kml_handle* h, int P, int N, const double* p1, const d
                           int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
   KML_API_BEGIN(h)
   return ransac_batch(h, false, P, N, p1, p2, full, models, n_inliers, iterations, best_draw, inlier_mask, ms_kernel);
+  KML_API_END(h)
+}
+int kml_ransac_onepoint_batch(kml_handle* h, int P, int N, const double* p1, const double* p2, const double* R,
+                              int full, double* models, int32_t* n_inliers, int32_t* iterations,
+                              int32_t* best_draw, uint32_t* inlier_mask, float* ms_kernel) {
+  KML_API_BEGIN(h)
+  if (P > 0 && !R) return fail(h, KML_ERR_ARG, "ransac_onepoint_batch: null rotation");
+  return ransac_batch(h, false, P, N, p1, p2, full, models, n_inliers, iterations, best_draw, inlier_mask, ms_kernel, R);
   KML_API_END(h)
 }
 int kml_ransac_nister_batch(kml_handle* h, int P, int N, const double* f1, const double* f2,

@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a)
 }
 
 // ---------------------------------------------------------- stereo chunk
-template <bool STAGED>  // STAGED: the problem's point pairs fit in shared memory (else read through L1)
+// ONEPT (row f4): rotation given, one correspondence per draw
+template <bool STAGED, bool ONEPT>  // STAGED: the problem's point pairs fit in shared memory (else read through L1)
 __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a) {
   KML_DYN_SMEM(double, smem_d);
   const int p = blockIdx.x;
@@ -478,9 +479,22 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
   const int nh = min(kStereoChunk, st.r_end - d0);
   if (tid < nh) {
     double M[12];
-    const uint16_t* smp = a.samples + ((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid) * 3;
-    const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
-    geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
+    if (ONEPT) {
+      const int i0 = a.samples[(size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid];
+      const double* R = a.prior + (size_t)p * 12;
+      const double* pa = s1 + 3 * i0;
+      const double* pb = s2 + 3 * i0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double r0 = R[4 * r], r1 = R[4 * r + 1], r2 = R[4 * r + 2];
+        M[4 * r] = r0; M[4 * r + 1] = r1; M[4 * r + 2] = r2;
+        M[4 * r + 3] = pa[r] - ((r0 * pb[0] + r1 * pb[1]) + r2 * pb[2]);
+      }
+    } else {
+      const uint16_t* smp = a.samples + ((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid) * 3;
+      const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
+      geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
+    }
 #pragma unroll
     for (int i = 0; i < 12; ++i) smod[12 * tid + i] = M[i];
   }
@@ -735,7 +749,11 @@ static void ensure_smem(K kernel, size_t bytes) {
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (a.P <= 0) return;
   const size_t sm = sample_size == 8 ? sac_warp_smem<8>(a.stride) : sac_warp_smem<3>(a.stride);
-  if (sample_size == 8) {
+  if (sample_size == 1) {
+    ensure_smem(sac_init_kernel<1, kStereoChunk>, sm);
+    ensure_smem(sac_replay_kernel<1, kStereoChunk>, sm);
+    KML_LAUNCH((sac_init_kernel<1, kStereoChunk>), a.P, 32, sm, s, a);
+  } else if (sample_size == 8) {
     ensure_smem(sac_init_kernel<8, kMonoChunk>, sm);
     ensure_smem(sac_replay_kernel<8, kMonoChunk>, sm);
     KML_LAUNCH((sac_init_kernel<8, kMonoChunk>), a.P, 32, sm, s, a);
@@ -776,11 +794,22 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   const size_t sm = stereo_smem(a.stride);
   const int draws = min(kRoundCap, sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
+  const size_t sm0 = sizeof(double) * 12 * kStereoChunk;
+  if (a.onept) {
+    if (sm <= 96 * 1024) {
+      ensure_smem(stereo_chunk_kernel<true, true>, sm);
+      KML_LAUNCH((stereo_chunk_kernel<true, true>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
+    } else {
+      KML_LAUNCH((stereo_chunk_kernel<false, true>), dim3(a.P, blocks), kStereoThreads, sm0, s, a);
+    }
+    KML_LAUNCH((sac_replay_kernel<1, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
+    return 2;
+  }
   if (sm <= 96 * 1024) {
-    ensure_smem(stereo_chunk_kernel<true>, sm);
-    KML_LAUNCH((stereo_chunk_kernel<true>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
+    ensure_smem(stereo_chunk_kernel<true, false>, sm);
+    KML_LAUNCH((stereo_chunk_kernel<true, false>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
   } else {
-    KML_LAUNCH((stereo_chunk_kernel<false>), dim3(a.P, blocks), kStereoThreads, sizeof(double) * 12 * kStereoChunk, s, a);
+    KML_LAUNCH((stereo_chunk_kernel<false, false>), dim3(a.P, blocks), kStereoThreads, sm0, s, a);
   }
   KML_LAUNCH((sac_replay_kernel<3, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
   return 2;

@@ -392,6 +392,15 @@ class LoopClosureDetector:
     def ransac_arun_batch(self, p1, p2, full_hypotheses=False):
         return self._ransac_batch(lib().kml_ransac_arun_batch, p1, p2, full_hypotheses)
 
+    def ransac_onepoint_batch(self, p1, p2, R, full_hypotheses=False):
+        """1-point stereo RANSAC with the rotations R [P, 3, 3] given (row f4)."""
+        R = _f64(R).reshape(-1, 9)
+        fn = lib().kml_ransac_onepoint_batch
+
+        def call(h, P, N, a, b, full, *rest):
+            return fn(h, P, N, a, b, _p(R, C.c_double), full, *rest)
+        return self._ransac_batch(call, p1, p2, full_hypotheses)
+
     def ransac_nister_batch(self, f1, f2, full_hypotheses=False):
         return self._ransac_batch(lib().kml_ransac_nister_batch, f1, f2, full_hypotheses)
 

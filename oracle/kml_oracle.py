@@ -43,6 +43,8 @@ class Params(C.Structure):
         ("ransac_seed", C.c_uint32),
         ("top_k_verify", C.c_int32),
         ("matcher_norm", C.c_int32),
+        ("mono_algorithm", C.c_int32),
+        ("ransac_use_1point_3d3d", C.c_int32),
     ]
 
 
@@ -244,6 +246,19 @@ def ransac_arun(p1, p2, thr=0.5, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_arun, p1, p2, thr, prob, max_iter, seed)
 
 
+def ransac_onepoint(p1, p2, R, thr=0.5, prob=0.995, max_iter=1000, seed=12345):
+    """Ransac over the 1-point stereo problem: rotation R given, model = [R | p1_i - R p2_i] (row f4)."""
+    a, b, R = _f64(p1).reshape(-1, 3), _f64(p2).reshape(-1, 3), _f64(R).reshape(9)
+    res = RansacResult()
+    inl = np.zeros(max(len(a), 1), np.uint32)
+    lib().kmo_ransac_onepoint(_p(a, C.c_double), _p(b, C.c_double), len(a), _p(R, C.c_double), C.c_double(thr),
+                              C.c_double(prob), int(max_iter), C.c_uint32(seed), C.byref(res), _p(inl, C.c_uint32))
+    return dict(success=bool(res.success), iterations=res.iterations, skipped=res.skipped,
+                draws=res.draws, best_draw=res.best_draw, n_inliers=res.n_inliers,
+                model=np.array(res.model).reshape(3, 4),
+                inliers=inl[:res.n_inliers].copy() if res.success else np.zeros(0, np.uint32))
+
+
 def ransac_nister(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_nister, f1, f2, thr, prob, max_iter, seed)
 
@@ -308,15 +323,19 @@ class LoopClosureDetector:
             _p(iq, C.c_uint32), _p(im, C.c_uint32), C.byref(cnt), _p(R, C.c_double))
         return bool(ok), iq[:cnt.value].copy(), im[:cnt.value].copy(), R
 
-    def recoverPose(self, qr, qp, mr, mp, inl_q, inl_m):
+    def recoverPose(self, qr, qp, mr, mp, inl_q, inl_m, R_prior=None):
         iq, im = _u32(inl_q).copy(), _u32(inl_m).copy()
         cnt = C.c_int(len(iq))
         T = np.zeros((3, 4))
         if len(iq) == 0:
             iq, im = np.zeros(1, np.uint32), np.zeros(1, np.uint32)
-        ok = lib().kmo_lcd_recover_pose(
+        pr = None
+        if R_prior is not None:
+            R_prior = _f64(R_prior)
+            pr = _p(R_prior, C.c_double)
+        ok = lib().kmo_lcd_recover_pose_prior(
             self._h, C.c_uint64(qr), C.c_uint64(qp), C.c_uint64(mr), C.c_uint64(mp),
-            _p(iq, C.c_uint32), _p(im, C.c_uint32), C.byref(cnt), _p(T, C.c_double))
+            _p(iq, C.c_uint32), _p(im, C.c_uint32), C.byref(cnt), pr, _p(T, C.c_double))
         return bool(ok), iq[:cnt.value].copy(), im[:cnt.value].copy(), T
 
     def query_batch(self, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,

@@ -53,6 +53,8 @@ typedef struct kmo_params {
   uint32_t ransac_seed;
   int32_t top_k_verify;
   int32_t matcher_norm; /* 0 NORM_HAMMING, 1 NORM_L1 (upstream's create(3)) */
+  int32_t mono_algorithm;          /* 0 NISTER, 1 STEWENIUS (/root/reference/params/D455/LcdParams.yaml:68-73) */
+  int32_t ransac_use_1point_3d3d;  /* LcdParams.yaml:58: recoverPose with the mono rotation given, 1-point samples */
 } kmo_params;
 
 void kmo_default_params(kmo_params* p);
@@ -153,6 +155,13 @@ int kmo_lcd_geometric_verification_nister(kmo_lcd*, uint64_t qr, uint64_t qp,
 int kmo_lcd_recover_pose(kmo_lcd*, uint64_t qr, uint64_t qp, uint64_t mr,
                          uint64_t mp, uint32_t* inl_q, uint32_t* inl_m,
                          int* count, double* T);
+/* the same with a rotation prior (row-major 3x3, nullable): used iff ransac_use_1point_3d3d */
+int kmo_lcd_recover_pose_prior(kmo_lcd*, uint64_t qr, uint64_t qp, uint64_t mr,
+                               uint64_t mp, uint32_t* inl_q, uint32_t* inl_m,
+                               int* count, const double* R_prior, double* T);
+/* Ransac over the 1-point problem: rotation R (3x3) given, model = [R | p1_i - R p2_i] */
+void kmo_ransac_onepoint(const double* p1, const double* p2, int N, const double* R, double thr,
+                         double prob, int max_iter, uint32_t seed, kmo_ransac_result* res, uint32_t* inliers);
 
 /* One verified candidate of a query (the record the product also emits). */
 typedef struct kmo_result {

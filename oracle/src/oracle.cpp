@@ -230,6 +230,34 @@ struct ArunProblem {
   }
 };
 
+// Row f4 (/root/reference/params/D455/LcdParams.yaml:58 ransac_use_1point_3d3d): the point-cloud
+// problem with the rotation given (recoverPose's R_prior = the mono rotation).  One correspondence
+// fixes the translation, t = p1_i - R p2_i, so the sample size is 1; residual and thresholds are
+// PointCloudSacProblem's (A.8).
+struct OnePointProblem {
+  const double* p1; const double* p2; int N; double R[9];
+  bool compute(const uint16_t* s, double* model) const {
+    const double* a = p1 + 3 * s[0];
+    const double* b = p2 + 3 * s[0];
+    for (int r = 0; r < 3; ++r) {
+      model[4 * r + 0] = R[3 * r + 0]; model[4 * r + 1] = R[3 * r + 1]; model[4 * r + 2] = R[3 * r + 2];
+      model[4 * r + 3] = a[r] - ((R[3 * r + 0] * b[0] + R[3 * r + 1] * b[1]) + R[3 * r + 2] * b[2]);
+    }
+    return true;
+  }
+  int count(const double* m, double thr) const {
+    int c = 0;
+    for (int i = 0; i < N; ++i) c += (std::sqrt(arun_sqdist(m, p1 + 3 * i, p2 + 3 * i)) < thr);
+    return c;
+  }
+  int select(const double* m, double thr, uint32_t* out) const {
+    int c = 0;
+    for (int i = 0; i < N; ++i)
+      if (std::sqrt(arun_sqdist(m, p1 + 3 * i, p2 + 3 * i)) < thr) out[c++] = (uint32_t)i;
+    return c;
+  }
+};
+
 struct NisterProblem {
   const double* f1; const double* f2; int N;
   bool compute(const uint16_t* s, double* model) const { return mono_model(f1, f2, s, model); }
@@ -362,9 +390,15 @@ static int verify_pair(const kmo_lcd* L, const Frame& fq, const Frame& fm, kmo_r
   if (N3 < 3) return 2;
   kmo_ransac_result r3;
   std::vector<uint32_t> inl3(N3);
-  ArunProblem ap{p1.data(), p2.data(), N3};
-  ransac(ap, N3, 3, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations,
-         P.ransac_seed, &r3, inl3.data());
+  if (P.ransac_use_1point_3d3d) {
+    OnePointProblem op{p1.data(), p2.data(), N3, {0}};
+    memcpy(op.R, r->R_mono, sizeof(op.R));
+    ransac(op, N3, 1, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations, P.ransac_seed, &r3, inl3.data());
+  } else {
+    ArunProblem ap{p1.data(), p2.data(), N3};
+    ransac(ap, N3, 3, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations,
+           P.ransac_seed, &r3, inl3.data());
+  }
   if (!r3.success) return 2;
   if (r3.n_inliers < P.geometric_verification_min_inlier_count) return 2;
   if ((double)r3.n_inliers / (double)N3 < P.geometric_verification_min_inlier_percentage) return 2;
@@ -434,6 +468,8 @@ void kmo_default_params(kmo_params* p) {
   p->ransac_seed = 12345u;
   p->top_k_verify = 16;
   p->matcher_norm = 0;
+  p->mono_algorithm = 0;
+  p->ransac_use_1point_3d3d = 0;
 }
 
 double kmo_bow_score(const uint32_t* ids1, const float* vals1, int n1, const uint32_t* ids2,
@@ -607,6 +643,16 @@ int kmo_lcd_geometric_verification_nister(kmo_lcd* L, uint64_t qr, uint64_t qp, 
 
 int kmo_lcd_recover_pose(kmo_lcd* L, uint64_t qr, uint64_t qp, uint64_t mr, uint64_t mp,
                          uint32_t* inl_q, uint32_t* inl_m, int* count, double* T) {
+  return kmo_lcd_recover_pose_prior(L, qr, qp, mr, mp, inl_q, inl_m, count, nullptr, T);
+}
+void kmo_ransac_onepoint(const double* p1, const double* p2, int N, const double* R, double thr, double prob,
+                         int max_iter, uint32_t seed, kmo_ransac_result* res, uint32_t* inliers) {
+  OnePointProblem op{p1, p2, N, {0}};
+  memcpy(op.R, R, sizeof(op.R));
+  ransac(op, N, 1, thr, prob, max_iter, seed, res, inliers);
+}
+int kmo_lcd_recover_pose_prior(kmo_lcd* L, uint64_t qr, uint64_t qp, uint64_t mr, uint64_t mp,
+                               uint32_t* inl_q, uint32_t* inl_m, int* count, const double* R_prior, double* T) {
   auto q = L->vlc_frames_.find(RobotPoseId(qr, qp));
   auto m = L->vlc_frames_.find(RobotPoseId(mr, mp));
   if (q == L->vlc_frames_.end() || m == L->vlc_frames_.end()) return 0;
@@ -626,10 +672,16 @@ int kmo_lcd_recover_pose(kmo_lcd* L, uint64_t qr, uint64_t qp, uint64_t mr, uint
   if (N3 < 3) return 0;
   kmo_ransac_result r3;
   std::vector<uint32_t> inl3(N3);
-  ArunProblem ap{p1.data(), p2.data(), N3};
   const kmo_params& P = L->prm;
-  ransac(ap, N3, 3, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations,
-         P.ransac_seed, &r3, inl3.data());
+  if (P.ransac_use_1point_3d3d && R_prior) {
+    OnePointProblem op{p1.data(), p2.data(), N3, {0}};
+    memcpy(op.R, R_prior, sizeof(op.R));
+    ransac(op, N3, 1, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations, P.ransac_seed, &r3, inl3.data());
+  } else {
+    ArunProblem ap{p1.data(), p2.data(), N3};
+    ransac(ap, N3, 3, P.ransac_threshold, P.ransac_probability, P.max_ransac_iterations,
+           P.ransac_seed, &r3, inl3.data());
+  }
   if (!r3.success) return 0;
   if (r3.n_inliers < P.geometric_verification_min_inlier_count) return 0;
   if ((double)r3.n_inliers / (double)N3 < P.geometric_verification_min_inlier_percentage) return 0;

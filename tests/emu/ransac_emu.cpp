@@ -70,6 +70,7 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.threshold = threshold;
   a.sq_crit = sq_crit_of(threshold);
   a.max_iterations = max_it; a.full = full; a.force_generic = force_generic;
+  a.onept = 0; a.prior = nullptr;
   a.inlier_mask = mask.data(); a.mask_words = mask_words; a.n_inliers = inl.data();
   launch_sac_init(a, S, nullptr);
   for (int r = 0; r < kSacRounds; ++r) {

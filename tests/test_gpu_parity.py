@@ -527,3 +527,68 @@ def test_tensor_core_matcher_bit_exact(oracle, small_world):
     jq, jm = ref.computeMatchedIndices(0, int(ch["poses"][3]), 0, int(ch["poses"][7]))
     assert np.array_equal(iq, jq) and np.array_equal(im, jm)
     det.close()
+
+
+def test_one_point_stereo_ransac_given_rotation(oracle, small_world):
+    """Row f4 (/root/reference/params/D455/LcdParams.yaml:58 ransac_use_1point_3d3d): rotation given,
+    one correspondence per hypothesis.  The batched kernel, recoverPose with R_prior and the batch
+    query (which hands the mono rotation to the stereo stage) against the oracle, bit for bit."""
+    import kml
+    from kml import mask_to_indices
+    from conftest import fill
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(31)
+    prm = kml.default_params()
+    prm.ransac_use_1point_3d3d = 1
+    det = kml.LoopClosureDetector(prm)
+    P, N = 24, 300
+    p1 = np.zeros((P, N, 3)); p2 = np.zeros((P, N, 3)); Rs = np.zeros((P, 3, 3))
+    for p in range(P):
+        X = np.c_[rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(2, 12, N)]
+        R = Rot.from_rotvec(rng.normal(size=3) * 0.2).as_matrix(); t = rng.uniform(-1, 1, 3)
+        X2 = (X - t) @ R + rng.normal(size=X.shape) * 0.05
+        out = rng.random(N) < (0.2 + 0.03 * p)               # inlier ratios from 0.8 down to 0.1: 5 .. hundreds of draws
+        X2[out] = rng.uniform(-8, 8, (int(out.sum()), 3))
+        p1[p], p2[p], Rs[p] = X, X2, R
+    g = det.ransac_onepoint_batch(p1, p2, Rs)
+    for p in range(P):
+        o = oracle.ransac_onepoint(p1[p], p2[p], Rs[p], 0.5, 0.995, 1000, 12345)
+        assert o["iterations"] == g["iterations"][p] and o["best_draw"] == g["best_draw"][p], p
+        assert o["n_inliers"] == g["n_inliers"][p]
+        assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][p], N))
+        assert np.array_equal(o["model"], g["models"][p])                     # same operations, same bits
+    # batch query: the stereo stage takes the mono rotation as given
+    world, chunks, queries = small_world
+    fill(det, chunks, bulk=True)
+    oprm = oracle.default_params()
+    oprm.ransac_use_1point_3d3d = 1
+    ref = oracle.LoopClosureDetector(oprm)
+    fill(ref, chunks)
+    fq, fp = queries["frames"], queries["prev"]
+    args = (queries["q_robot"], queries["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    o1, c1 = det.query_batch(*args)
+    o0, c0 = ref.query_batch(*args)
+    assert np.array_equal(c0, c1)
+    n_lc = 0
+    for b in range(len(c0)):
+        for i in range(c0[b]):
+            for k in ("m_robot", "m_pose", "n_matches", "mono_inliers", "stereo_inliers", "status"):
+                assert o0[b, i][k] == o1[b, i][k], (b, i, k)
+            if o0[b, i]["status"] == 0:
+                n_lc += 1
+                assert np.abs(o0[b, i]["T"] - o1[b, i]["T"]).max() <= POSE_TOL
+                assert np.abs(np.asarray(o1[b, i]["T"]).reshape(3, 4)[:, :3] - np.asarray(o1[b, i]["R_mono"]).reshape(3, 3)).max() == 0
+    assert n_lc > 0
+    # the reference's call order with the prior: computeMatchedIndices -> Nister -> recoverPose(R_prior)
+    ch = chunks[0]
+    qa, ma = int(ch["poses"][3]), int(ch["poses"][3]) + 100   # two keyframes of the same place
+    iq, im = det.computeMatchedIndices(0, qa, 0, ma)
+    ok, jq, jm, R = det.geometricVerificationNister(0, qa, 0, ma, iq, im)
+    ok0, kq, km, R0 = ref.geometricVerificationNister(0, qa, 0, ma, iq, im)
+    assert ok and ok0 and np.array_equal(jq, kq) and np.array_equal(R, R0)
+    ok, sq, sm, T = det.recoverPose(0, qa, 0, ma, jq, jm, R_prior=R)
+    ok0, tq, tm, T0 = ref.recoverPose(0, qa, 0, ma, kq, km, R_prior=R0)
+    assert ok == ok0 and np.array_equal(sq, tq) and np.array_equal(sm, tm) and np.abs(T - T0).max() <= POSE_TOL
+    assert np.array_equal(T[:, :3], R)
+    det.close()

@@ -46,6 +46,7 @@ extern "C" {
 #define KML_ERR_CUDA (-2)
 #define KML_ERR_NCCL (-3)
 #define KML_ERR_CAPACITY (-4)
+#define KML_ERR_IO (-6)               /* shard file cannot be opened / read / written, or is corrupt */
 #define KML_ERR_STREAM_EXHAUSTED (-5) /* pre-drawn sample stream ran out (kept for ABI stability: the stream
                                         * now covers every draw the reference loop can consume) */
 
@@ -116,6 +117,22 @@ typedef struct kml_stats {
 typedef struct kml_handle kml_handle;
 
 void kml_default_params(kml_params* p);
+/* LcdParams.yaml -> kml_params: reads the flat "%YAML:1.0" key: value file the reference feeds its
+ * loop-closure detector (/root/reference/params/D455/LcdParams.yaml:1-74, located through
+ * params_folder, /root/reference/launch/kimera_vio_jackal.launch:37) on top of *p (call
+ * kml_default_params first; keys the file does not hold keep their value).  Mapping: alpha,
+ * max_db_results, min_nss_factor, min_temporal_matches, min_matches_per_island, max_intraisland_gap,
+ * max_nrFrames_between_islands, max_nrFrames_between_queries, lowe_ratio by name;
+ * recent_frames_window -> dist_local; ransac_threshold_2d2d / _3d3d -> ransac_threshold_mono /
+ * ransac_threshold; ransac_max_iterations and ransac_probability -> both RANSACs;
+ * min_nr_3d3d_inliers -> geometric_verification_min_inlier_count; ransac_randomize,
+ * ransac_use_1point_3d3d by name; ransac_2d2d_algorithm (OpenGV enum: 0 STEWENIUS, 1 NISTER) ->
+ * mono_algorithm (1, 0); matcher_type -> matcher_norm: with literal_matcher_enum != 0 the number is
+ * read as cv::DescriptorMatcher::create() reads it (3 = BRUTEFORCE_L1, 4 = BRUTEFORCE_HAMMING,
+ * kimera_multi_lcd.patch:34-35), else as the file's own comment table documents it (3 =
+ * BRUTEFORCE_HAMMING, LcdParams.yaml:40-46).  Returns KML_OK, or KML_ERR_ARG (unreadable file,
+ * unsupported matcher type); *n_mapped (nullable) = how many keys were taken. */
+int kml_params_from_yaml(const char* path, int literal_matcher_enum, kml_params* p, int* n_mapped);
 /* loadAndInitialize(params) on CUDA device `device` */
 int kml_create(const kml_params* p, int device, kml_handle** out);
 int kml_destroy(kml_handle* h);

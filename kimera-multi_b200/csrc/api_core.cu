@@ -1,5 +1,6 @@
 // api_core.cu — handle lifecycle, Hamming kNN entry points, peak probes.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <random>
 
@@ -60,6 +61,61 @@ void kml_default_params(kml_params* p) {
   p->ransac_use_1point_3d3d = 0;
 }
 
+int kml_params_from_yaml(const char* path, int literal_matcher_enum, kml_params* p, int* n_mapped) {
+  if (!path || !p) return KML_ERR_ARG;
+  FILE* f = fopen(path, "r");
+  if (!f) {
+    g_create_err = std::string("kml_params_from_yaml: cannot open ") + path;
+    return KML_ERR_ARG;
+  }
+  int n = 0, rc = KML_OK;
+  char line[1024];
+  while (fgets(line, sizeof line, f)) {
+    char* hash = strchr(line, '#');  // comments
+    if (hash) *hash = 0;
+    if (line[0] == '%' || !strchr(line, ':')) continue;  // "%YAML:1.0" directive, blank lines
+    char key[256];
+    double v = 0.0;
+    if (sscanf(line, " %255[^: \t] : %lf", key, &v) != 2) continue;
+    const std::string k(key);
+    const int iv = (int)v;
+    ++n;
+    if (k == "alpha") p->alpha = v;
+    else if (k == "max_db_results") p->max_db_results = iv;
+    else if (k == "min_nss_factor") p->min_nss_factor = v;
+    else if (k == "min_temporal_matches") p->min_temporal_matches = iv;
+    else if (k == "min_matches_per_island") p->min_matches_per_island = iv;
+    else if (k == "max_intraisland_gap") p->max_intraisland_gap = iv;
+    else if (k == "max_nrFrames_between_islands") p->max_nrFrames_between_islands = iv;
+    else if (k == "max_nrFrames_between_queries") p->max_nrFrames_between_queries = iv;
+    else if (k == "recent_frames_window") p->dist_local = iv;
+    else if (k == "lowe_ratio") p->lowe_ratio = v;
+    else if (k == "ransac_threshold_2d2d") p->ransac_threshold_mono = v;
+    else if (k == "ransac_threshold_3d3d") p->ransac_threshold = v;
+    else if (k == "ransac_max_iterations") { p->max_ransac_iterations_mono = iv; p->max_ransac_iterations = iv; }
+    else if (k == "ransac_probability") { p->ransac_probability_mono = v; p->ransac_probability = v; }
+    else if (k == "min_nr_3d3d_inliers") p->geometric_verification_min_inlier_count = iv;
+    else if (k == "ransac_randomize") p->ransac_randomize = iv;
+    else if (k == "ransac_use_1point_3d3d") p->ransac_use_1point_3d3d = iv ? 1 : 0;
+    else if (k == "ransac_2d2d_algorithm") p->mono_algorithm = (iv == 0) ? 1 : 0;  // OpenGV: 0 STEWENIUS, 1 NISTER
+    else if (k == "matcher_type") {
+      const int hamming = literal_matcher_enum ? 4 : 3, l1 = literal_matcher_enum ? 3 : 2;
+      if (iv == hamming) p->matcher_norm = 0;
+      else if (iv == l1) p->matcher_norm = 1;
+      else {
+        g_create_err = "kml_params_from_yaml: matcher_type selects a matcher this library does not implement";
+        rc = KML_ERR_ARG;
+      }
+    } else {
+      --n;  // a key of the file that does not parameterise this path (ORB extractor, PGO, ...)
+    }
+  }
+  fclose(f);
+  if (p->matcher_norm != 0) p->matcher_engine = 0;
+  if (n_mapped) *n_mapped = n;
+  return rc;
+}
+
 int kml_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -113,6 +169,11 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
     if (h->prm.matcher_norm != 0) h->prm.matcher_engine = 0;  // the tensor-core path computes NORM_HAMMING only
     if (h->prm.max_db_results > kBowMaxK || h->prm.max_db_results < 1) {
       g_create_err = "max_db_results must be in [1,128]";
+      delete h;
+      return KML_ERR_ARG;
+    }
+    if (h->prm.mono_algorithm != 0) {
+      g_create_err = "mono_algorithm 1 (STEWENIUS) is not built: only NISTER (0) runs on this path";
       delete h;
       return KML_ERR_ARG;
     }

@@ -34,7 +34,7 @@ int kml_save_shard(kml_handle* h, const char* path) {
   try {
     KML_CUDA(cudaSetDevice(h->device));
     File out(fopen(path, "wb"));
-    if (!out.f) { h->err = std::string("kml_save_shard: cannot open ") + path; return KML_ERR_ARG; }
+    if (!out.f) { h->err = std::string("kml_save_shard: cannot open ") + path; return KML_ERR_IO; }
     const uint32_t version = 1, n_robots = (uint32_t)h->sh->dbs.size();
     bool ok = out.w(kMagic, 8) && out.w(&version, 4) && out.w(&n_robots, 4);
     for (auto& kv : h->sh->dbs) {
@@ -67,7 +67,7 @@ int kml_save_shard(kml_handle* h, const char* path) {
       ok = ok && out.w(&robot, 8) && out.w(&pose, 8) && out.w(&F, 4) && out.w(desc.data(), desc.size()) &&
            out.w(bear.data(), 8 * bear.size()) && out.w(pts.data(), 8 * pts.size());
     }
-    if (!ok) { h->err = "kml_save_shard: write failed"; return KML_ERR_ARG; }
+    if (!ok) { h->err = "kml_save_shard: write failed"; return KML_ERR_IO; }
     return KML_OK;
   } catch (const std::exception& e) {
     h->err = e.what();
@@ -75,54 +75,63 @@ int kml_save_shard(kml_handle* h, const char* path) {
   }
 }
 
+// The file is not trusted: every count is bounded by what is left of the file before anything is
+// allocated, offsets must be non-decreasing with at most 1 024 words per vector (what addBowVector
+// accepts), and nothing is thrown across the C boundary.
 int kml_load_shard(kml_handle* h, const char* path) {
   if (!h || !path) return KML_ERR_ARG;
-  File in(fopen(path, "rb"));
-  if (!in.f) { h->err = std::string("kml_load_shard: cannot open ") + path; return KML_ERR_ARG; }
-  char magic[8];
-  uint32_t version = 0, n_robots = 0;
-  if (!in.r(magic, 8) || memcmp(magic, kMagic, 8) != 0 || !in.r(&version, 4) || version != 1 || !in.r(&n_robots, 4)) {
-    h->err = "kml_load_shard: not a shard file of version 1";
-    return KML_ERR_ARG;
+  try {
+    File in(fopen(path, "rb"));
+    if (!in.f) { h->err = std::string("kml_load_shard: cannot open ") + path; return KML_ERR_IO; }
+    if (fseek(in.f, 0, SEEK_END) != 0) { h->err = "kml_load_shard: cannot seek"; return KML_ERR_IO; }
+    const long fsize = ftell(in.f);
+    rewind(in.f);
+    auto left = [&]() -> uint64_t { const long at = ftell(in.f); return (fsize >= 0 && at >= 0 && at <= fsize) ? (uint64_t)(fsize - at) : 0; };
+    auto corrupt = [&](const char* what) { h->err = std::string("kml_load_shard: ") + what; return KML_ERR_IO; };
+    char magic[8];
+    uint32_t version = 0, n_robots = 0;
+    if (!in.r(magic, 8) || memcmp(magic, kMagic, 8) != 0 || !in.r(&version, 4) || version != 1 || !in.r(&n_robots, 4))
+      return corrupt("not a shard file of version 1");
+    for (uint32_t r = 0; r < n_robots; ++r) {
+      uint64_t robot = 0, n = 0;
+      if (!in.r(&robot, 8) || !in.r(&n, 8)) return corrupt("truncated");
+      if (n > 0x7FFFFFFFull || (n + 1) * 8 + n * 8 > left()) return corrupt("entry count beyond the file");
+      std::vector<int64_t> off(n + 1);
+      std::vector<uint64_t> poses(n);
+      if (!in.r(off.data(), 8 * (n + 1)) || !in.r(poses.data(), 8 * n) || off[0] != 0) return corrupt("truncated");
+      for (uint64_t i = 0; i < n; ++i)
+        if (off[i + 1] < off[i] || off[i + 1] - off[i] > 1024) return corrupt("corrupt vector offsets");
+      if ((uint64_t)off[n] * 8 > left()) return corrupt("word count beyond the file");
+      std::vector<uint32_t> ids((size_t)off[n]);
+      std::vector<float> vals((size_t)off[n]);
+      if (!in.r(ids.data(), 4 * ids.size()) || !in.r(vals.data(), 4 * vals.size())) return corrupt("truncated");
+      const int rc = kml_add_bow_bulk(h, robot, poses.data(), (int)n, off.data(), ids.data(), vals.data());
+      if (rc != KML_OK) return rc;
+    }
+    uint64_t n_frames = 0;
+    if (!in.r(&n_frames, 8)) return corrupt("truncated");
+    std::vector<uint8_t> desc;
+    std::vector<double> bear, pts;
+    for (uint64_t i = 0; i < n_frames; ++i) {
+      uint64_t robot = 0, pose = 0;
+      int32_t F = 0;
+      if (!in.r(&robot, 8) || !in.r(&pose, 8) || !in.r(&F, 4) || F < 0 || F > 65535) return corrupt("truncated");
+      if ((uint64_t)F * 80 > left()) return corrupt("frame beyond the file");
+      desc.resize((size_t)F * 32); bear.resize((size_t)F * 3); pts.resize((size_t)F * 3);
+      if (!in.r(desc.data(), desc.size()) || !in.r(bear.data(), 8 * bear.size()) || !in.r(pts.data(), 8 * pts.size()))
+        return corrupt("truncated");
+      const int rc = kml_add_frame(h, robot, pose, desc.data(), bear.data(), pts.data(), F);
+      if (rc != KML_OK) return rc;
+    }
+    return KML_OK;
+  } catch (const kml::CudaError& e) {
+    h->err = e.what();
+    cudaGetLastError();
+    return KML_ERR_CUDA;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return KML_ERR_IO;
   }
-  for (uint32_t r = 0; r < n_robots; ++r) {
-    uint64_t robot = 0, n = 0;
-    if (!in.r(&robot, 8) || !in.r(&n, 8) || n > (1ull << 31)) { h->err = "kml_load_shard: truncated"; return KML_ERR_ARG; }
-    std::vector<int64_t> off(n + 1);
-    std::vector<uint64_t> poses(n);
-    if (!in.r(off.data(), 8 * (n + 1)) || !in.r(poses.data(), 8 * n) || off[0] != 0 || off[n] < 0) {
-      h->err = "kml_load_shard: truncated";
-      return KML_ERR_ARG;
-    }
-    std::vector<uint32_t> ids((size_t)off[n]);
-    std::vector<float> vals((size_t)off[n]);
-    if (!in.r(ids.data(), 4 * ids.size()) || !in.r(vals.data(), 4 * vals.size())) {
-      h->err = "kml_load_shard: truncated";
-      return KML_ERR_ARG;
-    }
-    const int rc = kml_add_bow_bulk(h, robot, poses.data(), (int)n, off.data(), ids.data(), vals.data());
-    if (rc != KML_OK) return rc;
-  }
-  uint64_t n_frames = 0;
-  if (!in.r(&n_frames, 8)) { h->err = "kml_load_shard: truncated"; return KML_ERR_ARG; }
-  std::vector<uint8_t> desc;
-  std::vector<double> bear, pts;
-  for (uint64_t i = 0; i < n_frames; ++i) {
-    uint64_t robot = 0, pose = 0;
-    int32_t F = 0;
-    if (!in.r(&robot, 8) || !in.r(&pose, 8) || !in.r(&F, 4) || F < 0 || F > 65535) {
-      h->err = "kml_load_shard: truncated";
-      return KML_ERR_ARG;
-    }
-    desc.resize((size_t)F * 32); bear.resize((size_t)F * 3); pts.resize((size_t)F * 3);
-    if (!in.r(desc.data(), desc.size()) || !in.r(bear.data(), 8 * bear.size()) || !in.r(pts.data(), 8 * pts.size())) {
-      h->err = "kml_load_shard: truncated";
-      return KML_ERR_ARG;
-    }
-    const int rc = kml_add_frame(h, robot, pose, desc.data(), bear.data(), pts.data(), F);
-    if (rc != KML_OK) return rc;
-  }
-  return KML_OK;
 }
 
 }  // extern "C"

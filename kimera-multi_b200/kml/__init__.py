@@ -31,6 +31,20 @@ def default_params():
     return p
 
 
+def params_from_yaml(path, literal_matcher_enum=False, base=None):
+    """LcdParams.yaml (the reference's OpenCV-FileStorage parameter file,
+    /root/reference/params/D455/LcdParams.yaml) -> Params, on top of `base` (default_params() if None).
+    literal_matcher_enum: read matcher_type as cv::DescriptorMatcher::create() does (3 = L1) instead of
+    as the file's own comment table documents it (3 = Hamming)."""
+    p = base if base is not None else default_params()
+    n = C.c_int(0)
+    rc = lib().kml_params_from_yaml(str(path).encode(), int(bool(literal_matcher_enum)), C.byref(p), C.byref(n))
+    if rc != KML_OK:
+        raise KmlError(rc, (lib().kml_last_error(None) or b"").decode())
+    p.n_mapped = n.value
+    return p
+
+
 def device_count():
     return lib().kml_device_count()
 

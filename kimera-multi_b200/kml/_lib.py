@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libkml.so")
 KML_OK = 0
 KML_NO_DB, KML_NO_PREV_BOW, KML_NSS_TOO_LOW, KML_NO_MATCH, KML_NO_FRAME = 1, 2, 3, 4, 5
 KML_TOO_FEW_POINTS, KML_RANSAC_FAIL, KML_TOO_FEW_INLIERS, KML_INTER_ROBOT_ONLY = 6, 7, 8, 9
-KML_ERR_ARG, KML_ERR_CUDA, KML_ERR_NCCL, KML_ERR_CAPACITY, KML_ERR_STREAM_EXHAUSTED = -1, -2, -3, -4, -5
+KML_ERR_ARG, KML_ERR_CUDA, KML_ERR_NCCL, KML_ERR_CAPACITY, KML_ERR_STREAM_EXHAUSTED, KML_ERR_IO = -1, -2, -3, -4, -5, -6
 KML_UNIQUE_ID_BYTES = 128
 
 
@@ -103,7 +103,7 @@ LCD_STATUS = ["LOOP_DETECTED", "NO_MATCHES", "LOW_NSS_FACTOR", "LOW_SCORE", "NO_
               "FAILED_TEMPORAL_CONSTRAINT", "FAILED_GEOM_VERIFICATION", "FAILED_POSE_RECOVERY"]
 
 EXPORTS = [
-    "kml_default_params", "kml_create", "kml_create_lane", "kml_destroy", "kml_last_error", "kml_get_stats",
+    "kml_default_params", "kml_params_from_yaml", "kml_create", "kml_create_lane", "kml_destroy", "kml_last_error", "kml_get_stats",
     "kml_device_count", "kml_add_bow", "kml_add_bow_bulk", "kml_add_frame",
     "kml_add_frames_bulk", "kml_frame_exists", "kml_bow_exists", "kml_num_bow_for_robot",
     "kml_get_bow_vector", "kml_db_query", "kml_bow_score", "kml_detect_loop_with_robot",

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "kimera-multi_b2
 import bench, kml
 nkf = int(os.environ.get("KML_NKF", "5000")); warm = int(os.environ.get("KML_WARM", "1")); steps = int(os.environ.get("KML_STEPS", "1"))
 bench.N_KEYFRAMES = nkf
+bench.N_ROBOTS = int(os.environ.get("KML_NROBOTS", str(bench.N_ROBOTS)))
 prm = kml.default_params(); prm.matcher_engine = int(os.environ.get("KML_MATCHER_ENGINE", "1"))
 det = kml.LoopClosureDetector(prm)
 world, robots = bench.build_world(0, lambda m: None)

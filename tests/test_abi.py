@@ -79,3 +79,33 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
     out = run_c_client(tmp_path)
     if kml.device_count() == 0:
         assert "no device, create refused" in out and "no CPU fallback" in out
+
+
+def test_params_from_the_reference_yaml(tmp_path):
+    """kml_params_from_yaml on the reference's own parameter file (OpenCV FileStorage dialect) and on
+    a copy of its text when the reference tree is not there (GPU box)."""
+    import kml
+    ref = "/root/reference/params/D455/LcdParams.yaml"
+    text = ("%YAML:1.0\n# LoopClosureDetector parameters:\nuse_nss: 1\nalpha: 0.4\nmin_temporal_matches: 1\n"
+            "recent_frames_window: 100\nmax_db_results: 50\nmin_nss_factor: 0.05\nmin_matches_per_island: 1\n"
+            "max_intraisland_gap: 3\nmax_nrFrames_between_islands: 3\nmax_nrFrames_between_queries: 2\n\n"
+            "lowe_ratio: 0.7\nmatcher_type: 3\nnfeatures: 700\nmin_nr_2d2d_inliers: 10\nmin_nr_3d3d_inliers: 5\n"
+            "ransac_threshold_2d2d: 1e-06\nransac_threshold_3d3d: 0.3\nransac_use_1point_3d3d: 1  # if 1, use rotation\n"
+            "ransac_max_iterations: 500\nransac_probability: 0.995\nransac_randomize: 0\n"
+            "ransac_2d2d_algorithm: 0 # Stewenius\n")
+    paths = [str(tmp_path / "LcdParams.yaml")]
+    open(paths[0], "w").write(text)
+    if os.path.exists(ref):
+        paths.append(ref)
+    for path in paths:
+        p = kml.params_from_yaml(path)
+        assert p.alpha == 0.4 and p.max_db_results == 50 and p.min_nss_factor == 0.05 and p.dist_local == 100
+        assert p.lowe_ratio == 0.7 and p.ransac_threshold_mono == 1e-6 and p.ransac_threshold == 0.3
+        assert p.max_ransac_iterations == 500 and p.max_ransac_iterations_mono == 500 and p.ransac_probability == 0.995
+        assert p.geometric_verification_min_inlier_count == 5 and p.ransac_randomize == 0
+        assert p.ransac_use_1point_3d3d == 1 and p.mono_algorithm == 1           # 0 = STEWENIUS in OpenGV's enum
+        assert p.matcher_norm == 0 and p.n_mapped >= 19                          # "3: BRUTEFORCE_HAMMING" per the file's comment
+        q = kml.params_from_yaml(path, literal_matcher_enum=True)                # create(3) = BRUTEFORCE_L1
+        assert q.matcher_norm == 1 and q.matcher_engine == 0
+    with pytest.raises(kml.KmlError):
+        kml.params_from_yaml(str(tmp_path / "missing.yaml"))

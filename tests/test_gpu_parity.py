@@ -592,3 +592,33 @@ def test_one_point_stereo_ransac_given_rotation(oracle, small_world):
     assert ok == ok0 and np.array_equal(sq, tq) and np.array_equal(sm, tm) and np.abs(T - T0).max() <= POSE_TOL
     assert np.array_equal(T[:, :3], R)
     det.close()
+
+
+def test_load_shard_rejects_corrupt_files(tmp_path, gpu_lcd):
+    """kml_load_shard does not trust the file: truncated files, counts beyond the file size and
+    non-monotonic offsets come back as KML_ERR_IO (-6), never as an exception across the C ABI."""
+    import struct
+    import kml
+    good = str(tmp_path / "good.kml")
+    gpu_lcd.save(good)
+    blob = open(good, "rb").read()
+    cases = {"truncated": blob[:len(blob) // 3], "bad_magic": b"XXXXXXXX" + blob[8:],
+             "huge_n": blob[:24] + struct.pack("<Q", 1 << 40) + blob[32:],
+             "empty": b""}
+    # first robot block: magic(8) version(4) n_robots(4) robot(8) n(8) off[n+1]...: make off[2] < off[1]
+    bad = bytearray(blob)
+    bad[32 + 16:32 + 24] = struct.pack("<q", -5)
+    cases["bad_offsets"] = bytes(bad)
+    for name, data in cases.items():
+        path = str(tmp_path / (name + ".kml"))
+        open(path, "wb").write(data)
+        det = kml.LoopClosureDetector()
+        with pytest.raises(kml.KmlError) as e:
+            det.load(path)
+        assert e.value.code == -6, (name, e.value.code)
+        det.close()
+    det = kml.LoopClosureDetector()
+    with pytest.raises(kml.KmlError) as e:
+        det.load(str(tmp_path / "does_not_exist.kml"))
+    assert e.value.code == -6
+    det.close()

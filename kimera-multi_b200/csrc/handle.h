@@ -105,6 +105,9 @@ struct kml_shared {
   // ---- pre-drawn sample stream + k tables
   std::vector<uint32_t> raw_h;
   kml::DevBuf<uint32_t> d_raw;
+  // per-N sample tables (kernels.h SacArgs::sample_tab) for sample sizes 8, 3, 1
+  kml::DevBuf<uint16_t> d_samptab[3];
+  int samptab_nmax[3] = {-1, -1, -1};
   int ktable_n_mono = 0, ktable_n_stereo = 0, ktable_n_stereo1 = 0;
   kml::DevBuf<double> d_ktable_mono, d_ktable_stereo, d_ktable_stereo1;  // sample sizes 8, 3, 1
 

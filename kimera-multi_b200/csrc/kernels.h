@@ -105,6 +105,14 @@ struct SacArgs {
   unsigned int item_cap; // capacity of the item arrays and of fb_list
   unsigned int* overflow;  // set when a round needed more than item_cap items (results of the batch are void)
   unsigned int* pending;   // nullable: sac_select counts the problems that are not done yet
+  // Every problem starts from the identity permutation and the same pre-drawn stream, so its sample
+  // sequence depends only on its number of correspondences N: sample_tab[N][draw][S] (N <=
+  // tab_nmax) holds it for every draw the loop can consume, built once per (S, seed).  When it is
+  // there the kernels read their samples from it and neither sac_init nor sac_replay draws
+  // anything (the per-problem shuffle state `perm` and `samples` are unused).  Null for problems
+  // larger than the table: the warp-serial per-problem sampler runs instead.
+  const uint16_t* sample_tab;
+  int tab_nmax;
   uint16_t* samples;     // [P][kRoundCap][S] samples of the current round's draws, slot = draw - r_begin
   int32_t* valid;        // [P][kRoundCap]
   int32_t* counts;       // [P][kRoundCap]
@@ -135,6 +143,10 @@ __host__ __device__ inline int sac_round_draws(int round, int chunk) {
   return round == 0 ? chunk : (round > 8 ? chunk << 8 : chunk << (round - 1));
 }
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
+// tab[N][cap_draws][S] for N in [0, nmax]: the draws of SampleConsensusProblem::drawIndexSample
+// from a fresh shuffle state (one warp per N)
+void launch_sample_table(const uint32_t* raw, int cap_draws, int sample_size, int nmax, uint16_t* tab, cudaStream_t s);
+constexpr int kSampleTabMaxN = 1024;  // larger problems keep the per-problem sampler
 // one round = chunk kernel over the pending draw range + replay; returns #kernels launched
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s);
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s);

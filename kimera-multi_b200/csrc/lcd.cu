@@ -367,6 +367,31 @@ static void ensure_ktable(kml_handle* h, int Nmax, int sample_size, double prob,
   *cur_n = n1;
 }
 
+// sample_tab[N][cap_draws][S] for N <= nmax (SacArgs::sample_tab), built on first use; nullptr
+// for problems beyond kSampleTabMaxN correspondences (the per-problem sampler runs instead)
+static const uint16_t* ensure_sample_table(kml_handle* h, int S, int nmax, int cap_draws, int* tab_nmax) {
+  if (nmax > kSampleTabMaxN || getenv("KML_NO_SAMPLE_TABLE")) return nullptr;
+  const int slot = S == 8 ? 0 : S == 3 ? 1 : 2;
+  std::lock_guard<std::mutex> lk(h->sh->mu);
+  kml_shared& sh = *h->sh;
+  if (sh.samptab_nmax[slot] < nmax) {
+    const int n1 = std::min(kSampleTabMaxN, std::max(nmax, 512));
+    if (sh.d_samptab[slot].p) {  // another lane's kernels may still read the old table
+      sh.retired.push_back(sh.d_samptab[slot].p);
+      sh.d_samptab[slot].p = nullptr;
+      sh.d_samptab[slot].cap = 0;
+    }
+    sh.d_samptab[slot].scratch((size_t)(n1 + 1) * cap_draws * S);
+    launch_sample_table(sh.d_raw.p, cap_draws, S, n1, sh.d_samptab[slot].p, h->stream);
+    h->stats.kernel_launches += 1;
+    KML_CUDA(cudaGetLastError());
+    KML_CUDA(cudaStreamSynchronize(h->stream));
+    sh.samptab_nmax[slot] = n1;
+  }
+  *tab_nmax = sh.samptab_nmax[slot];
+  return sh.d_samptab[slot].p;
+}
+
 struct SacBufs {
   DevBuf<SacState>* st;
   DevBuf<double>* best;
@@ -439,6 +464,8 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.ktable_n = mono ? h->sh->ktable_n_mono : onept ? h->sh->ktable_n_stereo1 : h->sh->ktable_n_stereo;
   a.onept = onept ? 1 : 0;
   a.prior = d_prior;
+  a.tab_nmax = 0;
+  a.sample_tab = ensure_sample_table(h, S, stride, cap_draws, &a.tab_nmax);
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
   a.sq_crit = sq_crit_of(prm.ransac_threshold);
   a.max_iterations = max_it; a.full = full;

@@ -69,6 +69,30 @@ __host__ __device__ inline size_t sac_warp_smem(int stride) {
   return sac_perm_bytes(stride) + sizeof(int32_t) * kRoundCap + sizeof(uint16_t) * kRoundCap * S;
 }
 
+// samples of draw `gd` of problem p (N correspondences): from the per-N table, or from the
+// round's per-problem buffer (slot = gd - r_begin)
+template <int S>
+__device__ __forceinline__ const uint16_t* sac_sample(const SacArgs& a, int p, int N, int gd, int slot) {
+  if (a.sample_tab) return a.sample_tab + ((size_t)N * a.cap_draws + gd) * S;
+  return a.samples + ((size_t)p * kRoundCap + slot) * S;
+}
+
+// tab[N][cap_draws][S]: one warp per N replays drawIndexSample over the whole stream
+template <int S>
+__global__ void __launch_bounds__(32) sample_table_kernel(const uint32_t* __restrict__ raw, int cap_draws, int nmax,
+                                                          uint16_t* __restrict__ tab) {
+  KML_DYN_SMEM(uint16_t, perm_s);
+  const int N = blockIdx.x, lane = threadIdx.x;
+  if (N < S || N > nmax) return;
+  uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(nmax));
+  for (int i = lane; i < N; i += 32) perm_s[i] = (uint16_t)i;
+  __syncwarp();
+  for (int first = 0; first < cap_draws; first += kRoundCap) {
+    const int last = min(cap_draws, first + kRoundCap);
+    draw_samples_warp<S>(perm_s, jrel_s, N, raw, first, last, tab + ((size_t)N * cap_draws + first) * S, lane);
+  }
+}
+
 template <int S, int CHUNK>
 __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
   KML_DYN_SMEM(uint16_t, perm_s);
@@ -76,7 +100,9 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
   const int lane = threadIdx.x;
   const int N = a.N[p];
   SacState* st = &a.st[p];
-  for (int i = lane; i < N; i += 32) perm_s[i] = (uint16_t)i;
+  const bool tab = a.sample_tab != nullptr;
+  if (!tab)
+    for (int i = lane; i < N; i += 32) perm_s[i] = (uint16_t)i;
   bool unit = true;
   if (S == 8) {  // unit bearings are the precondition of the fast inlier filter (geom::mono_inlier_fast)
     const double* ga = a.a + (size_t)p * a.stride * 3;
@@ -103,12 +129,14 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
     st->r_end = (N < S) ? 0 : min(CHUNK, a.cap_draws);
   }
   __syncwarp();
-  if (N >= S) {
-    uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
-                                                   sizeof(int32_t) * kRoundCap);
-    draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * kRoundCap * S, lane);
+  if (!tab) {
+    if (N >= S) {
+      uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
+                                                     sizeof(int32_t) * kRoundCap);
+      draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * kRoundCap * S, lane);
+    }
+    for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   }
-  for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
 }
 
@@ -125,7 +153,9 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   const int N = a.N[p];
   int32_t* vc_s = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride));
   uint16_t* jrel_s = reinterpret_cast<uint16_t*>(vc_s + kRoundCap);
-  for (int i = lane; i < N; i += 32) perm_s[i] = a.perm[(size_t)p * a.stride + i];
+  const bool tab = a.sample_tab != nullptr;
+  if (!tab)
+    for (int i = lane; i < N; i += 32) perm_s[i] = a.perm[(size_t)p * a.stride + i];
   {  // the round's (valid, count) results, fetched by the whole warp: count, or -1 for "no model"
     const int rb = st->r_begin, re = st->r_end;
     const int32_t* gv = a.valid + (size_t)p * kRoundCap;
@@ -193,7 +223,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
   nb_w = __shfl_sync(0xFFFFFFFFu, nb_w, 0);
   ne_w = __shfl_sync(0xFFFFFFFFu, ne_w, 0);
   done_w = __shfl_sync(0xFFFFFFFFu, done_w, 0);
-  if (!done_w) {
+  if (!done_w && !tab) {
     draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, nb_w, ne_w, a.samples + (size_t)p * kRoundCap * S, lane);
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   }
@@ -234,7 +264,8 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   const int nh = min(kMonoChunk, st.r_end - d0);
   const bool live = tid < nh;
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
-  const uint16_t* smp = a.samples + (live ? slot : (size_t)p * kRoundCap) * 8;
+  const int js = live ? blockIdx.y * kMonoChunk + tid : 0;
+  const uint16_t* smp = sac_sample<8>(a, p, a.N[p], st.r_begin + js, js);
   geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * geom::kFrontOut);
 }
 
@@ -315,7 +346,8 @@ __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
     const double* bk = a.brk + slot * 2 * geom::kMaxBrackets + 2 * r;
     const double* ga = a.a + (size_t)p * a.stride * 3;
     const double* gb = a.b + (size_t)p * a.stride * 3;
-    const uint16_t* smp = a.samples + slot * 8;
+    const int js = (int)(slot % kRoundCap);
+    const uint16_t* smp = sac_sample<8>(a, p, a.N[p], a.st[p].r_begin + js, js);
     double q = 0.0, M[12];
     const int status = geom::mono_item(fo, r >= R0 ? 1 : 0, bk[0], bk[1], ga, gb, smp, &q, M);
     a.item_status[it] = (uint8_t)status;
@@ -480,7 +512,7 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
   if (tid < nh) {
     double M[12];
     if (ONEPT) {
-      const int i0 = a.samples[(size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid];
+      const int i0 = *sac_sample<1>(a, p, N, d0 + tid, blockIdx.y * kStereoChunk + tid);
       const double* R = a.prior + (size_t)p * 12;
       const double* pa = s1 + 3 * i0;
       const double* pb = s2 + 3 * i0;
@@ -491,7 +523,7 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
         M[4 * r + 3] = pa[r] - ((r0 * pb[0] + r1 * pb[1]) + r2 * pb[2]);
       }
     } else {
-      const uint16_t* smp = a.samples + ((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + tid) * 3;
+      const uint16_t* smp = sac_sample<3>(a, p, N, d0 + tid, blockIdx.y * kStereoChunk + tid);
       const int i0 = smp[0], i1 = smp[1], i2 = smp[2];
       geom::arun3(s1 + 3 * i0, s1 + 3 * i1, s1 + 3 * i2, s2 + 3 * i0, s2 + 3 * i1, s2 + 3 * i2, M);
     }
@@ -746,6 +778,19 @@ static void ensure_smem(K kernel, size_t bytes) {
     KML_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+void launch_sample_table(const uint32_t* raw, int cap_draws, int sample_size, int nmax, uint16_t* tab, cudaStream_t s) {
+  const size_t sm = sac_perm_bytes(nmax) + sizeof(uint16_t) * kRoundCap * 8;
+  if (sample_size == 8) {
+    ensure_smem(sample_table_kernel<8>, sm);
+    KML_LAUNCH((sample_table_kernel<8>), nmax + 1, 32, sm, s, raw, cap_draws, nmax, tab);
+  } else if (sample_size == 3) {
+    ensure_smem(sample_table_kernel<3>, sm);
+    KML_LAUNCH((sample_table_kernel<3>), nmax + 1, 32, sm, s, raw, cap_draws, nmax, tab);
+  } else {
+    ensure_smem(sample_table_kernel<1>, sm);
+    KML_LAUNCH((sample_table_kernel<1>), nmax + 1, 32, sm, s, raw, cap_draws, nmax, tab);
+  }
+}
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (a.P <= 0) return;
   const size_t sm = sample_size == 8 ? sac_warp_smem<8>(a.stride) : sac_warp_smem<3>(a.stride);

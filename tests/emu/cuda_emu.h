@@ -80,6 +80,7 @@ struct State {
   unsigned w_gen[32] = {0};
   uint64_t xchg[32][32];           // [warp][lane] exchange slots of the warp collectives
   std::vector<unsigned char> dyn;  // dynamic shared memory of the running CTA
+  size_t dyn_bytes = 0;
   const std::function<void()>* body = nullptr;
   int schedule = -1;               // 0 ascending, 1 descending, 2 random; -1 = read KML_EMU_SCHEDULE
   uint64_t rng = 1;
@@ -153,7 +154,10 @@ inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::fun
   s.ctx.resize(block_threads);
   s.done.assign(block_threads, 0);
   while ((int)s.stacks.size() < block_threads) s.stacks.push_back((char*)malloc(kStack));
-  s.dyn.assign(dyn_smem + 16, 0xCD);  // uninitialised on a GPU: poison it
+  // uninitialised on a GPU: poison it; 64 canary bytes behind it catch a CTA that writes past its
+  // dynamic shared memory (compute-sanitizer is closed on the GPU pool, so the bounds are checked here)
+  s.dyn.assign(dyn_smem + 16 + 64, 0xCD);
+  s.dyn_bytes = dyn_smem;
   s.body = &body;
   s.bdim.x = block_threads; s.bdim.y = s.bdim.z = 1;
   s.gdim = grid;
@@ -200,6 +204,15 @@ inline void launch(Idx3 grid, int block_threads, size_t dyn_smem, const std::fun
         // every pass must retire a thread or pass a barrier eventually; 1e6 idle passes = deadlock
         guard = (s.alive == before && s.bar_gen == g0) ? guard + 1 : 0;
         if (guard > 1000000) throw std::runtime_error("kml_emu: CTA deadlocked at a barrier");
+      }
+      {  // canary behind the CTA's dynamic shared memory
+        const unsigned char* base = (const unsigned char*)(((uintptr_t)s.dyn.data() + 15) & ~(uintptr_t)15);
+        for (size_t i = s.dyn_bytes; i < s.dyn_bytes + 48; ++i)
+          if (base[i] != 0xCD) {
+            fprintf(stderr, "kml_emu: CTA (%u,%u) wrote %zu bytes past its %zu bytes of dynamic shared memory\n", bx, by,
+                    i - s.dyn_bytes + 1, s.dyn_bytes);
+            throw std::runtime_error("kml_emu: dynamic shared memory overrun");
+          }
       }
     }
 }

@@ -71,6 +71,14 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.sq_crit = sq_crit_of(threshold);
   a.max_iterations = max_it; a.full = full; a.force_generic = force_generic;
   a.onept = 0; a.prior = nullptr;
+  // per-N sample table (ensure_sample_table of lcd.cu) unless the caller asks for the per-problem sampler
+  std::vector<uint16_t> samptab;
+  a.sample_tab = nullptr; a.tab_nmax = 0;
+  if (stride <= kSampleTabMaxN && !getenv("KML_NO_SAMPLE_TABLE")) {
+    samptab.resize((size_t)(stride + 1) * cap_draws * S);
+    launch_sample_table(raw.data(), cap_draws, S, stride, samptab.data(), nullptr);
+    a.sample_tab = samptab.data(); a.tab_nmax = stride;
+  }
   a.inlier_mask = mask.data(); a.mask_words = mask_words; a.n_inliers = inl.data();
   launch_sac_init(a, S, nullptr);
   for (int r = 0; r < kSacRounds; ++r) {

@@ -10,6 +10,7 @@ including databases wider than one accumulator tile (BASELINE.json configs[4], 5
 per database), which no GPU run of round 1 reached."""
 import ctypes as C
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -377,7 +378,8 @@ def test_results_do_not_depend_on_the_thread_schedule(schedule):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-p", "no:cacheprovider",
                         "-n", "4", "-k", "not schedule"], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=1200)
-    assert r.returncode == 0 and "6 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert r.returncode == 0 and m and int(m.group(1)) >= 9 and "failed" not in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
 def test_bow_incremental_appends_equal_a_rebuild(oracle, bowemu):
@@ -442,3 +444,23 @@ def test_bow_cut_inside_a_large_tie_group(oracle, bowemu):
     assert oc[0, 0] == 120 and list(oe[0, 0, :100]) == twin_at
     assert _check_against_oracle(db, twin[0], twin[1], 120, -1, oe[0, 0, :120], osc[0, 0, :120]) == 120
     det.close()
+
+
+def test_ransac_per_problem_sampler_without_the_table(oracle, ransacemu):
+    """KML_NO_SAMPLE_TABLE: the warp-serial per-problem sampler of sac_init / sac_replay (what problems
+    with more than 1 024 correspondences use) must give the outcome the per-N sample table gives."""
+    rng = np.random.default_rng(5)
+    p1, p2 = np.zeros((3, 90, 3)), np.zeros((3, 90, 3))
+    for p in range(3):
+        p1[p], p2[p], _, _ = _scene(rng, 90, [0.3, 0.6, 0.9][p])
+    g1 = emu_ransac(ransacemu, False, p1, p2, 0.5)
+    os.environ["KML_NO_SAMPLE_TABLE"] = "1"
+    try:
+        g0 = emu_ransac(ransacemu, False, p1, p2, 0.5)
+    finally:
+        del os.environ["KML_NO_SAMPLE_TABLE"]
+    for k in ("iterations", "best_draw", "n_inliers", "mask", "models"):
+        assert np.array_equal(g0[k], g1[k]), k
+    for p in range(3):
+        o = oracle.ransac_arun(p1[p], p2[p], 0.5, 0.995, 1000, 12345)
+        assert o["iterations"] == g0["iterations"][p] and o["best_draw"] == g0["best_draw"][p]

@@ -187,6 +187,7 @@ struct kml_handle {
   kml::DevBuf<uint8_t> d_item_status;
   kml::DevBuf<kml::SacState> d_st_mono, d_st_stereo;
   kml::DevBuf<uint32_t> d_mask_mono, d_mask_stereo;
+  kml::DevBuf<int32_t> d_active;  // [0..1] counters, [2..] the two active lists of the RANSAC rounds
   kml::PinBuf<uint8_t> h_stage;  // generic pinned staging
   kml::DevBuf<uint8_t> d_scratch, d_scratch2;
   kml::DevBuf<double> d_prior;   // rotation prior of the single-pair recoverPose (row f4)

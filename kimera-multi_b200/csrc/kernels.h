@@ -116,6 +116,10 @@ struct SacArgs {
   uint16_t* samples;     // [P][kRoundCap][S] samples of the current round's draws, slot = draw - r_begin
   int32_t* valid;        // [P][kRoundCap]
   int32_t* counts;       // [P][kRoundCap]
+  // active lists of the rounds: active[(r & 1) * P + i], i < n_active[r & 1], are the problems round r
+  // works on (sac_init writes list 0, the replay of round r writes the list of round r + 1)
+  int32_t* active;       // [2][P]
+  unsigned int* n_active;  // [2]
   SacState* st;          // [P]
   double* best_model;    // [P][12]
   const double* ktable;  // [(Nmax+1)*(Nmax+1)] k as function of (N, best count)
@@ -136,11 +140,15 @@ struct SacArgs {
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
 constexpr int kStereoChunk = 64;    // hypotheses per CTA (stereo) and size of round 0
 constexpr int kStereoThreads = 128; // threads of a stereo CTA (4 counting warps)
-constexpr int kSacRounds = 6;      // rounds enqueued blindly: 64,64,128,256,512,512 new draws at most; more only while a problem is pending
+constexpr int kSacRounds = 7;      // rounds enqueued blindly: 32,32,64,128,256,512,512 new draws at most; more only while a problem is pending
 constexpr int kRoundCap = 512;     // most new draws any round evaluates per problem
-// upper bound of NEW draws evaluated per problem in round r (doubling schedule)
+// upper bound of NEW draws evaluated per problem in round r: half a chunk (one warp of draws) in
+// rounds 0 and 1, then doubling.  Nearly half of the candidate pairs of a batch end within 16
+// trials (few correspondences, or an overwhelming inlier ratio): a 32-draw first round evaluates
+// 16 draws too many for them, a 64-draw one 48.
 __host__ __device__ inline int sac_round_draws(int round, int chunk) {
-  return round == 0 ? chunk : (round > 8 ? chunk << 8 : chunk << (round - 1));
+  const int first = chunk / 2;
+  return round == 0 ? first : (round > 9 ? first << 9 : first << (round - 1));
 }
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
 // tab[N][cap_draws][S] for N in [0, nmax]: the draws of SampleConsensusProblem::drawIndexSample

@@ -443,6 +443,7 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   }
   h->d_valid.scratch(Pa * kRoundCap);
   h->d_counts.scratch(Pa * kRoundCap);
+  h->d_active.scratch(2 * Pa + 2);
   out.st->scratch(Pa);
   out.best->scratch(Pa * 12);
   out.mask->scratch(Pa * mask_words);
@@ -460,6 +461,7 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.item_base = h->d_item_base.p; a.item_list = h->d_item_list.p; a.item_q = h->d_item_q.p;
   a.item_model = h->d_item_model.p; a.item_status = h->d_item_status.p;
   a.valid = h->d_valid.p; a.counts = h->d_counts.p; a.st = out.st->p; a.best_model = out.best->p;
+  a.n_active = reinterpret_cast<unsigned int*>(h->d_active.p); a.active = h->d_active.p + 2;
   a.ktable = mono ? h->sh->d_ktable_mono.p : onept ? h->sh->d_ktable_stereo1.p : h->sh->d_ktable_stereo.p;
   a.ktable_n = mono ? h->sh->ktable_n_mono : onept ? h->sh->ktable_n_stereo1 : h->sh->ktable_n_stereo;
   a.onept = onept ? 1 : 0;

@@ -126,27 +126,28 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
     st->k = 1.0;
     st->done = (N < S) ? 1 : 0;  // getSamples(): N < sample_size => loop exits, no model
     st->r_begin = 0;
-    st->r_end = (N < S) ? 0 : min(CHUNK, a.cap_draws);
+    st->r_end = (N < S) ? 0 : min(sac_round_draws(0, CHUNK), a.cap_draws);
   }
   __syncwarp();
   if (!tab) {
     if (N >= S) {
       uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
                                                      sizeof(int32_t) * kRoundCap);
-      draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(CHUNK, a.cap_draws), a.samples + (size_t)p * kRoundCap * S, lane);
+      draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(sac_round_draws(0, CHUNK), a.cap_draws),
+                           a.samples + (size_t)p * kRoundCap * S, lane);
     }
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   }
   if (a.n_inliers && lane == 0) a.n_inliers[p] = 0;
+  if (lane == 0 && N >= S) a.active[atomicAdd(&a.n_active[0], 1u)] = p;  // round 0 works on every solvable problem
 }
 
 // Ransac::computeModel control flow, replayed over the draws of one round.
 // k never increases, so after a round the number of trials still required is
 // known exactly (up to skipped samples): the next round covers all of them.
 template <int S, int CHUNK>
-__global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
+__device__ void sac_replay_body(const SacArgs& a, int round, int p) {
   KML_DYN_SMEM(uint16_t, perm_s);
-  const int p = blockIdx.x;
   const int lane = threadIdx.x;
   SacState* st = &a.st[p];
   if (st->done) return;
@@ -227,6 +228,27 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
     draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, nb_w, ne_w, a.samples + (size_t)p * kRoundCap * S, lane);
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
   }
+  // the problems the next round still works on (order is irrelevant: every buffer is indexed by p)
+  if (!done_w && lane == 0) {
+    const int nx = (round + 1) & 1;
+    a.active[(size_t)nx * a.P + atomicAdd(&a.n_active[nx], 1u)] = p;
+  }
+}
+// Every per-round kernel walks the round's ACTIVE LIST (written by sac_init for round 0 and by the
+// previous round's replay afterwards) with a grid that shrinks with the round: a late round
+// launches a few hundred CTAs for the handful of problems still running instead of one CTA per
+// problem slot that finds `done` and leaves.
+#define KML_ACTIVE_LOOP(body_call)                                                    \
+  const int32_t* list_ = a.active + (size_t)(round & 1) * a.P;                        \
+  const int n_act_ = (int)a.n_active[round & 1];                                      \
+  for (int ai_ = blockIdx.x; ai_ < n_act_; ai_ += gridDim.x) {                        \
+    const int p = list_[ai_];                                                         \
+    body_call;                                                                        \
+    __syncthreads(); /* shared memory of the body is reused by the next problem */    \
+  }
+template <int S, int CHUNK>
+__global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
+  KML_ACTIVE_LOOP((sac_replay_body<S, CHUNK>(a, round, p)))
 }
 
 // ------------------------------------------------------------ mono round
@@ -251,9 +273,8 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 //                        the fast inlier filter, stopping once the draw cannot
 //                        beat the best count of the draws before it.
 //   sac_replay_kernel    lane 0 per problem replays Ransac::computeModel.
-__global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
+__device__ void mono_front_body(const SacArgs& a, int p) {
   KML_DYN_SMEM(double, smem_d);
-  const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
@@ -268,10 +289,11 @@ __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a) {
   const uint16_t* smp = sac_sample<8>(a, p, a.N[p], st.r_begin + js, js);
   geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * geom::kFrontOut);
 }
+__global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a, int round) {
+  KML_ACTIVE_LOOP(mono_front_body(a, p))
+}
 
-__global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
-  KML_DYN_SMEM(double, smem_d);
-  const int p = blockIdx.x;
+__device__ void mono_isolate_body(const SacArgs& a, int p) {
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
@@ -314,6 +336,9 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a) {
     a.item_base[slot] = base;
     for (int r = 0; r < n; ++r) a.item_list[base + r] = (uint32_t)(slot * 32 + r);
   }
+}
+__global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a, int round) {
+  KML_ACTIVE_LOOP(mono_isolate_body(a, p))
 }
 
 // Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
@@ -373,9 +398,8 @@ __global__ void fstats_print_kernel() {
 constexpr int kCountThreads = 256;
 constexpr int kCountWarps = kCountThreads / 32;
 template <bool STAGED>  // STAGED: the problem's bearings fit in shared memory (else read through L1)
-__global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a) {
+__device__ void mono_count_body(const SacArgs& a, int p) {
   KML_DYN_SMEM(double, smem_d);
-  const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
@@ -479,13 +503,16 @@ __global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a)
     if (v && lane < 12) a.models[(slot0 + h) * 12 + lane] = s_mod[h][lane];
   }
 }
+template <bool STAGED>
+__global__ void __launch_bounds__(kCountThreads, 2) mono_count_kernel(SacArgs a, int round) {
+  KML_ACTIVE_LOOP(mono_count_body<STAGED>(a, p))
+}
 
 // ---------------------------------------------------------- stereo chunk
 // ONEPT (row f4): rotation given, one correspondence per draw
 template <bool STAGED, bool ONEPT>  // STAGED: the problem's point pairs fit in shared memory (else read through L1)
-__global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a) {
+__device__ void stereo_chunk_body(const SacArgs& a, int p) {
   KML_DYN_SMEM(double, smem_d);
-  const int p = blockIdx.x;
   const SacState st = a.st[p];
   if (st.done) return;
   const int d0 = st.r_begin + blockIdx.y * kStereoChunk;
@@ -561,6 +588,10 @@ __global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a)
     }
     if (lane < 12) a.models[((size_t)p * kRoundCap + blockIdx.y * kStereoChunk + h) * 12 + lane] = smod[12 * h + lane];
   }
+}
+template <bool STAGED, bool ONEPT>
+__global__ void __launch_bounds__(kStereoThreads) stereo_chunk_kernel(SacArgs a, int round) {
+  KML_ACTIVE_LOOP((stereo_chunk_body<STAGED, ONEPT>(a, p)))
 }
 
 // ------------------------------------------------ selectWithinDistance
@@ -793,6 +824,7 @@ void launch_sample_table(const uint32_t* raw, int cap_draws, int sample_size, in
 }
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   if (a.P <= 0) return;
+  KML_CUDA(cudaMemsetAsync(a.n_active, 0, 2 * sizeof(unsigned int), s));
   const size_t sm = sample_size == 8 ? sac_warp_smem<8>(a.stride) : sac_warp_smem<3>(a.stride);
   if (sample_size == 1) {
     ensure_smem(sac_init_kernel<1, kStereoChunk>, sm);
@@ -809,6 +841,11 @@ void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s) {
   }
 }
 
+// CTAs along x for round r: the active list shrinks as problems finish, and so does the grid
+static int active_grid(int P, int round) {
+  const int cap = round <= 1 ? kNumSMs * 16 : round == 2 ? kNumSMs * 8 : round == 3 ? kNumSMs * 4 : kNumSMs * 2;
+  return max(1, min(P, cap));
+}
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem();
@@ -816,22 +853,24 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   ensure_smem(mono_front_kernel, sm);
   const int draws = min(kRoundCap, sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
-  KML_LAUNCH((mono_front_kernel), dim3(a.P, blocks), kMonoChunk, sm, s, a);
+  const int gx = active_grid(a.P, round);
+  KML_LAUNCH((mono_front_kernel), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
-  KML_LAUNCH((mono_isolate_kernel), dim3(a.P, blocks), kMonoChunk, 0, s, a);
+  KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
+  KML_LAUNCH((mono_isolate_kernel), dim3(gx, blocks), kMonoChunk, 0, s, a, round);
   KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, sm2, s, a);
   KML_LAUNCH((mono_item_kernel), kNumSMs * 16, kItemThreads, 0, s, a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);
   if (sm4 <= 96 * 1024) {
     ensure_smem(mono_count_kernel<true>, sm4);
-    KML_LAUNCH((mono_count_kernel<true>), dim3(a.P, blocks), kCountThreads, sm4, s, a);
+    KML_LAUNCH((mono_count_kernel<true>), dim3(gx, blocks), kCountThreads, sm4, s, a, round);
   } else {
-    KML_LAUNCH((mono_count_kernel<false>), dim3(a.P, blocks), kCountThreads, 0, s, a);
+    KML_LAUNCH((mono_count_kernel<false>), dim3(gx, blocks), kCountThreads, 0, s, a, round);
   }
 #ifdef KML_FILTER_STATS
   if (round == kSacRounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
 #endif
-  KML_LAUNCH((sac_replay_kernel<8, kMonoChunk>), a.P, 32, sac_warp_smem<8>(a.stride), s, a, round);
+  KML_LAUNCH((sac_replay_kernel<8, kMonoChunk>), gx, 32, sac_warp_smem<8>(a.stride), s, a, round);
   return 6;
 }
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
@@ -840,23 +879,25 @@ int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   const int draws = min(kRoundCap, sac_round_draws(round, kStereoChunk));
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   const size_t sm0 = sizeof(double) * 12 * kStereoChunk;
+  const int gx = active_grid(a.P, round);
+  KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
   if (a.onept) {
     if (sm <= 96 * 1024) {
       ensure_smem(stereo_chunk_kernel<true, true>, sm);
-      KML_LAUNCH((stereo_chunk_kernel<true, true>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
+      KML_LAUNCH((stereo_chunk_kernel<true, true>), dim3(gx, blocks), kStereoThreads, sm, s, a, round);
     } else {
-      KML_LAUNCH((stereo_chunk_kernel<false, true>), dim3(a.P, blocks), kStereoThreads, sm0, s, a);
+      KML_LAUNCH((stereo_chunk_kernel<false, true>), dim3(gx, blocks), kStereoThreads, sm0, s, a, round);
     }
-    KML_LAUNCH((sac_replay_kernel<1, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
+    KML_LAUNCH((sac_replay_kernel<1, kStereoChunk>), gx, 32, sac_warp_smem<3>(a.stride), s, a, round);
     return 2;
   }
   if (sm <= 96 * 1024) {
     ensure_smem(stereo_chunk_kernel<true, false>, sm);
-    KML_LAUNCH((stereo_chunk_kernel<true, false>), dim3(a.P, blocks), kStereoThreads, sm, s, a);
+    KML_LAUNCH((stereo_chunk_kernel<true, false>), dim3(gx, blocks), kStereoThreads, sm, s, a, round);
   } else {
-    KML_LAUNCH((stereo_chunk_kernel<false, false>), dim3(a.P, blocks), kStereoThreads, sm0, s, a);
+    KML_LAUNCH((stereo_chunk_kernel<false, false>), dim3(gx, blocks), kStereoThreads, sm0, s, a, round);
   }
-  KML_LAUNCH((sac_replay_kernel<3, kStereoChunk>), a.P, 32, sac_warp_smem<3>(a.stride), s, a, round);
+  KML_LAUNCH((sac_replay_kernel<3, kStereoChunk>), gx, 32, sac_warp_smem<3>(a.stride), s, a, round);
   return 2;
 }
 __global__ void sac_pending_kernel(SacArgs a) {

@@ -71,6 +71,8 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.sq_crit = sq_crit_of(threshold);
   a.max_iterations = max_it; a.full = full; a.force_generic = force_generic;
   a.onept = 0; a.prior = nullptr;
+  std::vector<int32_t> active(2 * Pa + 2, 0);
+  a.n_active = reinterpret_cast<unsigned int*>(active.data()); a.active = active.data() + 2;
   // per-N sample table (ensure_sample_table of lcd.cu) unless the caller asks for the per-problem sampler
   std::vector<uint16_t> samptab;
   a.sample_tab = nullptr; a.tab_nmax = 0;

@@ -384,8 +384,7 @@ def main():
         for st in range(li, K, n_lanes):
             b = pbatches[st % len(pbatches)]
             if sharded:
-                ln.query_batch_upload(*b)
-                ln.query_batch_run(sharded=True, seq=seq[0] + st)
+                ln.query_batch(*b, sharded=True, seq=seq[0] + st)
             else:
                 ln.query_batch(*b)
 

@@ -353,6 +353,14 @@ int kml_query_batch_sharded(kml_handle* h, kml_result* out, int cap_per_query,
 int kml_query_batch_sharded_seq(kml_handle* h, uint64_t seq, kml_result* out, int cap_per_query,
                                 int32_t* counts);
 int kml_comm_seq_reset(kml_handle* h, uint64_t next_seq);
+/* kml_query_batch for the sharded detector: host buffers in (every rank passes the same batch),
+ * merged records out; the copies are enqueued in front of the pipeline and covered by its single
+ * wait.  use_seq = 0 ignores `seq` (one lane per rank). */
+int kml_query_batch_sharded_host(kml_handle* h, int use_seq, uint64_t seq, int B, const uint64_t* q_robot,
+                                 const uint64_t* q_pose, const int64_t* bow_off, const uint32_t* ids,
+                                 const float* vals, const int64_t* prev_off, const uint32_t* prev_ids,
+                                 const float* prev_vals, const uint8_t* desc, const double* bearings,
+                                 const double* points, int F, kml_result* out, int cap_per_query, int32_t* counts);
 /* the sharded query's device tail alone (merge_shards_kernel) on host blocks, laid out as for
  * kml_merge_shard_records */
 int kml_merge_shard_records_device(kml_handle* h, const void* blocks, int nranks, int B, int cap_in, int cap,

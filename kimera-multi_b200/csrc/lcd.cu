@@ -1480,6 +1480,22 @@ int kml_query_batch_sharded_seq(kml_handle* h, uint64_t seq, kml_result* out, in
   return batch_run(h, cap, true, out, counts, &seq);
   KML_API_END(h)
 }
+int kml_query_batch_sharded_host(kml_handle* h, int use_seq, uint64_t seq, int B, const uint64_t* q_robot,
+                                 const uint64_t* q_pose, const int64_t* bow_off, const uint32_t* ids,
+                                 const float* vals, const int64_t* prev_off, const uint32_t* prev_ids,
+                                 const float* prev_vals, const uint8_t* desc, const double* bearings,
+                                 const double* points, int F, kml_result* out, int cap, int32_t* counts) {
+  KML_API_BEGIN(h)
+  if (cap <= 0 || (B > 0 && (!out || !counts))) return fail(h, KML_ERR_ARG, "query_batch_sharded_host: bad output");
+  int rc = batch_upload(h, B, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
+                        desc, bearings, points, F, false);
+  if (rc != KML_OK) return rc;  // argument errors are the same on every rank (same batch): nobody enters the collective
+  if (B == 0) return use_seq ? kml_query_batch_sharded_seq(h, seq, out, cap, counts) : KML_OK;
+  rc = batch_run(h, cap, true, out, counts, use_seq ? &seq : nullptr);
+  if (rc != KML_OK) cudaStreamSynchronize(h->stream);
+  return rc;
+  KML_API_END(h)
+}
 int kml_comm_seq_reset(kml_handle* h, uint64_t next_seq) {
   if (!h) return KML_ERR_ARG;
   {

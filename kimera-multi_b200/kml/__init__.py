@@ -311,14 +311,19 @@ class LoopClosureDetector:
         return keep, args
 
     def query_batch(self, q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids, prev_vals,
-                    desc, bearings, points):
-        """B full loop-closure queries, host buffers in, records out (kml_query_batch)."""
+                    desc, bearings, points, sharded=False, seq=None):
+        """B full loop-closure queries, host buffers in, records out (kml_query_batch; with
+        sharded=True kml_query_batch_sharded_host: every rank passes the same batch)."""
         keep, args = self._batch_args(q_robot, q_pose, bow_off, ids, vals, prev_off, prev_ids,
                                       prev_vals, desc, bearings, points)
         B = args[0]
         cap = int(self.params.top_k_verify)
         out = np.zeros((B, cap), RESULT_DTYPE)
         counts = np.zeros(B, np.int32)
+        if sharded:
+            self._check(lib().kml_query_batch_sharded_host(self._h, int(seq is not None), C.c_uint64(int(seq or 0)), *args,
+                                                           out.ctypes.data_as(C.c_void_p), cap, _p(counts, C.c_int32)))
+            return out, counts
         self._check(lib().kml_query_batch(self._h, *args, out.ctypes.data_as(C.c_void_p), cap,
                                           _p(counts, C.c_int32)))
         return out, counts

@@ -112,7 +112,7 @@ EXPORTS = [
     "kml_host_alloc", "kml_host_free",
     "kml_hamming_knn2", "kml_l1_knn2", "kml_hamming_knn2_bench", "kml_ransac_arun_batch",
     "kml_ransac_nister_batch", "kml_ransac_onepoint_batch", "kml_vocab_set", "kml_transform_batch", "kml_peak_popc", "kml_peak_fp64", "kml_timer_begin", "kml_timer_end", "kml_flush_l2", "kml_comm_unique_id",
-    "kml_comm_init", "kml_query_batch_sharded", "kml_query_batch_sharded_seq", "kml_comm_seq_reset",
+    "kml_comm_init", "kml_query_batch_sharded", "kml_query_batch_sharded_seq", "kml_query_batch_sharded_host", "kml_comm_seq_reset",
     "kml_merge_shard_records_device",
     "kml_save_shard", "kml_load_shard", "kml_merge_shard_records", "kml_compute_islands", "kml_check_temporal_constraint", "kml_detect_loop_islands", "kml_add_frame_msg",
 ]

@@ -70,7 +70,7 @@ def _rank(rank, world, port, key, q):
             handle.query_batch_upload(*args)
             loc, lcnt = handle.query_batch_run(sharded=False)
             if k == 2:
-                mrg, mcnt = handle.query_batch_run(sharded=True)          # un-sequenced entry point
+                mrg, mcnt = handle.query_batch(*args, sharded=True)       # host buffers in, un-sequenced
             else:
                 mrg, mcnt = handle.query_batch_run(sharded=True, seq=k)   # sequenced, one batch per lane
             blocks = r.gather((loc, lcnt))

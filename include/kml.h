@@ -83,7 +83,8 @@ typedef struct kml_params {
   int32_t matcher_engine;   /* NORM_HAMMING only: 0 = POPC pipe (LOP3 / POPC kernel), 1 = tensor cores (tcgen05.mma
                              * kind::i8 on +-1 expanded descriptors, s32 accumulators in TMEM); same keys, bit for bit */
   int32_t mono_algorithm;   /* ransac_2d2d_algorithm of /root/reference/params/D455/LcdParams.yaml:68-73:
-                             * 0 = NISTER (default, what geometricVerificationNister names), 1 = STEWENIUS */
+                             * 0 = NISTER (default, what geometricVerificationNister names), 1 = STEWENIUS (action
+                             * matrix of the same ten constraints; real solutions) */
   int32_t ransac_use_1point_3d3d; /* /root/reference/params/D455/LcdParams.yaml:58: recoverPose takes the mono
                              * rotation as given and samples ONE point pair per hypothesis (translation only) */
   int32_t reserved0;

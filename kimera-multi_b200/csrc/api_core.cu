@@ -172,8 +172,8 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
       delete h;
       return KML_ERR_ARG;
     }
-    if (h->prm.mono_algorithm != 0) {
-      g_create_err = "mono_algorithm 1 (STEWENIUS) is not built: only NISTER (0) runs on this path";
+    if (h->prm.mono_algorithm != 0 && h->prm.mono_algorithm != 1) {
+      g_create_err = "mono_algorithm must be 0 (NISTER) or 1 (STEWENIUS)";
       delete h;
       return KML_ERR_ARG;
     }

@@ -30,7 +30,17 @@ namespace geom {
 
 constexpr int kTphSlots = 200;    // stage 1
 constexpr int kIsoSlots = 88;     // stage 2
-constexpr int kFrontOut = 70;     // nz[11] p1[8] p2[8] p3[7] basis[36]
+constexpr int kFrontOut = 70;     // NISTER: nz[11] p1[8] p2[8] p3[7] basis[36]
+// STEWENIUS (row f4): charpoly[11] (unused 23) basis[36] at the same offset 34, then the six
+// non-trivial rows of the action matrix [6][10]
+constexpr int kFrontOutStew = 130;
+constexpr int kStewRowsOff = 70;
+// column of Nister's monomial order [x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1]
+// in the degree order [x3 x2y x2z xy2 xyz xz2 y3 y2z yz2 z3 | x2 xy xz y2 yz z2 x y z 1]
+__host__ __device__ constexpr int stew_slot(int i) {
+  constexpr int col[20] = {0, 6, 1, 3, 2, 10, 7, 13, 4, 11, 5, 12, 16, 8, 14, 17, 9, 15, 18, 19};
+  return (i / 20) * 20 + col[i % 20];
+}
 constexpr int kMaxBrackets = 20;  // <= 10 per chain
 constexpr int kTRootGrid = 32;
 constexpr int kTRootDepth = 48;
@@ -70,7 +80,8 @@ __device__ __forceinline__ double conv_r(const double* a, const double* b, int k
 // Column C itself is never read again, and rows 0..3 are neither pivot candidates nor
 // outputs once C >= 4 (only rows 4..9 feed B(z)): those updates are skipped; every value
 // that is used later is produced by the same operations as in a full sweep.
-template <int STRIDE, int C>
+// FULL: every row is updated (the Stewenius variant reads rows 0..5 of the reduced system).
+template <int STRIDE, int C, bool FULL = false>
 __device__ __forceinline__ void gj_step(double* sm, bool& failed) {
 #define S(i) sm[(i) * STRIDE]
   int pr = C;
@@ -98,7 +109,7 @@ __device__ __forceinline__ void gj_step(double* sm, bool& failed) {
     S(C * 20 + j) = prow[j];
   }
 #pragma unroll 1
-  for (int r = (C >= 4 ? 4 : 0); r < 10; ++r) {
+  for (int r = ((C >= 4 && !FULL) ? 4 : 0); r < 10; ++r) {
     if (r == C) continue;
     double* row = sm + r * 20 * STRIDE;
     const double f = row[C * STRIDE];
@@ -108,12 +119,63 @@ __device__ __forceinline__ void gj_step(double* sm, bool& failed) {
 #undef S
 }
 
+// Characteristic polynomial det(lambda I - H) of the 10x10 matrix H[r][c] = S(r*20 + 10 + c)
+// (row f4; oracle/src/geom.hpp charpoly10): elimination to Hessenberg form with first-maximum
+// pivoting, then the recurrence over the leading minors, whose polynomials P[k] (k <= 9, k + 1
+// coefficients, monic) live in the dead left halves S(k*20 + 0..9).  c[0..10] ascending, c[10] = 1.
+template <int STRIDE>
+__device__ __noinline__ void charpoly10_s(double* sm, double* c) {
+#define H(r, cc) sm[((r) * 20 + 10 + (cc)) * STRIDE]
+#define P(k, j) sm[((k) * 20 + (j)) * STRIDE]
+  const int n = 10;
+  for (int m = 1; m < n - 1; ++m) {
+    double x = 0.0;
+    int i = m;
+    for (int j = m; j < n; ++j)
+      if (fabs(H(j, m - 1)) > fabs(x)) { x = H(j, m - 1); i = j; }
+    if (i != m) {
+      for (int j = m - 1; j < n; ++j) { const double t = H(i, j); H(i, j) = H(m, j); H(m, j) = t; }
+      for (int j = 0; j < n; ++j) { const double t = H(j, i); H(j, i) = H(j, m); H(j, m) = t; }
+    }
+    if (x != 0.0) {
+      for (int i2 = m + 1; i2 < n; ++i2) {
+        double y = H(i2, m - 1);
+        if (y != 0.0) {
+          y = kdiv(y, x);
+          H(i2, m - 1) = y;
+          for (int j = m; j < n; ++j) H(i2, j) = H(i2, j) - y * H(m, j);
+          for (int j = 0; j < n; ++j) H(j, m) = H(j, m) + y * H(j, i2);
+        }
+      }
+    }
+  }
+  P(0, 0) = 1.0;
+  for (int k = 1; k <= n; ++k) {
+    const int col = k - 1;
+    const double h = H(col, col);
+    // the new polynomial goes to c[] first: P(k-1, .) is still read below
+    for (int j = 0; j <= k; ++j) c[j] = (j >= 1 ? P(k - 1, j - 1) : 0.0) - (j <= k - 1 ? h * P(k - 1, j) : 0.0);
+    double prod = 1.0;
+    for (int i = 1; i <= k - 1; ++i) {
+      const int row = col - i;
+      prod = prod * H(row + 1, row);
+      const double sc = H(row, col) * prod;
+      for (int j = 0; j <= k - 1 - i; ++j) c[j] = c[j] - sc * P(k - 1 - i, j);
+    }
+    if (k < n)
+      for (int j = 0; j <= k; ++j) P(k, j) = c[j];
+  }
+#undef H
+#undef P
+}
+
 // ============================================================== stage 1
 // sm: this thread's slot 0.  ga/gb: the problem's correspondences (query /
 // match bearings, [N][3]); smp: the 8 sample indices.  Writes the 70 doubles
 // of kFrontOut to `out` (NaN basis if the constraint system was singular).
 // `alive` = false makes the thread a passenger (barriers only, no output).
-template <int STRIDE, bool SYNC>
+// ALG 0 = NISTER (kFrontOut doubles out), 1 = STEWENIUS (kFrontOutStew doubles out).
+template <int STRIDE, bool SYNC, int ALG = 0>
 __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, const double* __restrict__ gb,
                                   const uint16_t* __restrict__ smp, bool alive, double* __restrict__ out) {
 #define S(i) sm[(i) * STRIDE]
@@ -191,23 +253,51 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
     for (int i = 0; i < 36; ++i) out[34 + i] = B[i];
   }
   // ------------------------------------- phase 2: constraint matrix 10x20
-  {
+  if constexpr (ALG == 1) {  // the same ten constraints, columns in the degree order of the Stewenius solver
+#define SA(i) S(stew_slot(i))
+#include "fivept_build.inc"
+#undef SA
+  } else {
 #define SA(i) S(i)
 #include "fivept_build.inc"
 #undef SA
   }
   KML_PHASE();
   // ----------------------------------------------- phase 3: Gauss-Jordan
-  gj_step<STRIDE, 0>(sm, failed); gj_step<STRIDE, 1>(sm, failed); gj_step<STRIDE, 2>(sm, failed);
-  gj_step<STRIDE, 3>(sm, failed); gj_step<STRIDE, 4>(sm, failed); gj_step<STRIDE, 5>(sm, failed);
-  gj_step<STRIDE, 6>(sm, failed); gj_step<STRIDE, 7>(sm, failed); gj_step<STRIDE, 8>(sm, failed);
-  gj_step<STRIDE, 9>(sm, failed);
+  constexpr bool FULL = ALG == 1;
+  gj_step<STRIDE, 0, FULL>(sm, failed); gj_step<STRIDE, 1, FULL>(sm, failed); gj_step<STRIDE, 2, FULL>(sm, failed);
+  gj_step<STRIDE, 3, FULL>(sm, failed); gj_step<STRIDE, 4, FULL>(sm, failed); gj_step<STRIDE, 5, FULL>(sm, failed);
+  gj_step<STRIDE, 6, FULL>(sm, failed); gj_step<STRIDE, 7, FULL>(sm, failed); gj_step<STRIDE, 8, FULL>(sm, failed);
+  gj_step<STRIDE, 9, FULL>(sm, failed);
   KML_PHASE();
   if (alive && failed) {
 #pragma unroll 1
     for (int i = 0; i < 36; ++i) out[34 + i] = nan("");
   }
-  {
+  if constexpr (ALG == 1) {
+    // ------------------- phase 4 (STEWENIUS): action matrix of x, characteristic polynomial
+    // rows 0..5 = -B[0..5] of the reduced system [I | B]; rows 6..9 = unit rows (x*x = x2, x*y = xy,
+    // x*z = xz, x*1 = x) — written over the dead rows 6..9 of B
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i)
+#pragma unroll 1
+      for (int j = 0; j < 10; ++j) {
+        const double v = -S(i * 20 + 10 + j);
+        S(i * 20 + 10 + j) = v;
+        if (alive) out[kStewRowsOff + i * 10 + j] = v;
+      }
+#pragma unroll 1
+    for (int i = 6; i < 10; ++i)
+#pragma unroll 1
+      for (int j = 0; j < 10; ++j) S(i * 20 + 10 + j) = 0.0;
+    S(6 * 20 + 10 + 0) = 1.0; S(7 * 20 + 10 + 1) = 1.0; S(8 * 20 + 10 + 2) = 1.0; S(9 * 20 + 10 + 6) = 1.0;
+    double cp[11];
+    charpoly10_s<STRIDE>(sm, cp);
+    if (alive) {
+#pragma unroll 1
+      for (int k = 0; k < 11; ++k) out[k] = cp[k];
+    }
+  } else {
     // --------------------------------- phase 4: B(z), cofactors, n(z)
     // B(z) entries as polynomials in z (ascending), rows 4..9 of the reduced system:
     // c0[r], c1[r] of degree 3, c2[r] of degree 4 (rows 0..3 of A are dead)
@@ -594,6 +684,72 @@ __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, 
   return ok;
 }
 
+// STEWENIUS (row f4): E from the eigenvalue x of the action matrix whose six non-trivial rows are
+// fo[kStewRowsOff + 10 j + k]: the eigenvector v = [x2, xy, xz, v3, v4, v5, x, y, z, 1] solves
+// rows 0..5 of (M - x I) v = 0, six equations in (v3, v4, v5, y, z), Gaussian elimination with
+// first-maximum row pivoting (oracle/src/geom.hpp stewenius_yz); then E = ((x X + y Y) + z Z) + W.
+__device__ __noinline__ bool essential_from_root_stew(const double* __restrict__ fo, double x, double* E) {
+  const double x2 = x * x;
+  double C[6][5], d[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double* a = fo + kStewRowsOff + 10 * j;
+    C[j][0] = a[3]; C[j][1] = a[4]; C[j][2] = a[5];
+    C[j][3] = a[1] * x + a[7];
+    C[j][4] = a[2] * x + a[8];
+    d[j] = -((a[0] * x2 + a[6] * x) + a[9]);
+  }
+  d[0] = d[0] + x * x2;
+  C[1][3] = C[1][3] - x2;
+  C[2][4] = C[2][4] - x2;
+  C[3][0] = C[3][0] - x;
+  C[4][1] = C[4][1] - x;
+  C[5][2] = C[5][2] - x;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    int pr = c;
+    double pv = fabs(C[c][c]);
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      const double v = fabs(C[r][c]);
+      if (v > pv) { pv = v; pr = r; }
+    }
+    if (!(pv > 0.0)) return false;
+    // swap rows c and pr without dynamic register indexing
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r)
+      if (r == pr) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { const double t = C[c][j]; C[c][j] = C[r][j]; C[r][j] = t; }
+        const double t = d[c]; d[c] = d[r]; d[r] = t;
+      }
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = kdiv(C[r][c], C[c][c]);
+#pragma unroll
+      for (int j = c + 1; j < 5; ++j) C[r][j] = C[r][j] - f * C[c][j];
+      d[r] = d[r] - f * d[c];
+    }
+  }
+  double u[5];
+#pragma unroll
+  for (int c = 4; c >= 0; --c) {
+    double sacc = d[c];
+#pragma unroll
+    for (int j = c + 1; j < 5; ++j) sacc = sacc - C[c][j] * u[j];
+    u[c] = kdiv(sacc, C[c][c]);
+  }
+  const double y = u[3], z = u[4];
+  bool ok = true;
+#pragma unroll 1
+  for (int e = 0; e < 9; ++e) {
+    const double v = ((x * fo[34 + e] + y * fo[34 + 9 + e]) + z * fo[34 + 18 + e]) + fo[34 + 27 + e];
+    if (!isfinite(v)) ok = false;
+    E[e] = v;
+  }
+  return ok;
+}
+
 // Decomposition of one essential matrix: Ra = U W V^T, Rb = U W^T V^T, t = s0 u2.
 __device__ __forceinline__ void essential_candidates(const double* E, double* Ra, double* Rb, double* tt) {
   double U[9], Sv[3], V[9];
@@ -658,12 +814,13 @@ __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, cons
 // (R, t) candidates on the 8 sample points (sequential sums) and keep the first
 // smallest one below the reference's initial quality 1e6.
 // returns 0 root not refined, 1 refined but nothing usable, 2 *q_out / M_out written
+template <int ALG = 0>
 __device__ __forceinline__ int mono_item(const double* __restrict__ fo, int chain, double lo, double hi,
                                          const double* __restrict__ ga, const double* __restrict__ gb,
                                          const uint16_t* __restrict__ smp, double* q_out, double* M_out) {
   double z, E[9];
-  if (!refine_root(fo, chain, lo, hi, &z)) return 0;
-  if (!essential_from_root(fo, z, E)) return 1;
+  if (!refine_root(fo, chain, lo, hi, &z)) return 0;  // NISTER: root z of n(z); STEWENIUS: eigenvalue x
+  if (ALG == 1 ? !essential_from_root_stew(fo, z, E) : !essential_from_root(fo, z, E)) return 1;
   double Ra[9], Rb[9], tt[3];
   essential_candidates(E, Ra, Rb, tt);
   const V3 t = {tt[0], tt[1], tt[2]};

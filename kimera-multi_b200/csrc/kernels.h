@@ -89,7 +89,9 @@ struct SacArgs {
   uint16_t* perm;        // [P][stride] persistent shuffle state
   int cap_draws;         // draws available per problem (raw_len / S)
   double* models;        // [P][kRoundCap][12] models of the draws of the current round
-  double* fsol;          // mono: [P][kRoundCap][70] stage-1 output per draw of the round
+  int alg;               // mono: 0 = NISTER, 1 = STEWENIUS (row f4)
+  int fo_stride;         // mono: doubles of stage-1 output per draw (geom::kFrontOut / kFrontOutStew)
+  double* fsol;          // mono: [P][kRoundCap][fo_stride] stage-1 output per draw of the round
   int32_t* nroot;        // mono: [P][kRoundCap] R0 | R1<<8 real-root counts of the two chains
   double* brk;           // mono: [P][kRoundCap][20][2] isolating brackets
   uint32_t* fb_list;     // mono: deferred root isolations of the round, slot*2 + chain

@@ -424,7 +424,7 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   h->d_fb_list.scratch(8);
   if (mono) {
     h->d_nsol.scratch(Pa * kRoundCap);
-    h->d_esol.scratch(Pa * kRoundCap * 70);
+    h->d_esol.scratch(Pa * kRoundCap * (prm.mono_algorithm == 1 ? 130 : 70));
     h->d_brk.scratch(Pa * kRoundCap * 40);
     // (draw, root) items of a round: a draw has at most 10 real roots, a round at most kRoundCap
     // draws per problem, but late rounds are large only for the few problems still running — the
@@ -466,6 +466,8 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.ktable_n = mono ? h->sh->ktable_n_mono : onept ? h->sh->ktable_n_stereo1 : h->sh->ktable_n_stereo;
   a.onept = onept ? 1 : 0;
   a.prior = d_prior;
+  a.alg = (mono && prm.mono_algorithm == 1) ? 1 : 0;
+  a.fo_stride = a.alg == 1 ? 130 : 70;  // geom::kFrontOutStew / kFrontOut (static_assert in ransac.cu)
   a.tab_nmax = 0;
   a.sample_tab = ensure_sample_table(h, S, stride, cap_draws, &a.tab_nmax);
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;

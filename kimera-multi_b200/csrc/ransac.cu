@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 //                        the fast inlier filter, stopping once the draw cannot
 //                        beat the best count of the draws before it.
 //   sac_replay_kernel    lane 0 per problem replays Ransac::computeModel.
+template <int ALG>
 __device__ void mono_front_body(const SacArgs& a, int p) {
   KML_DYN_SMEM(double, smem_d);
   const SacState st = a.st[p];
@@ -287,10 +288,11 @@ __device__ void mono_front_body(const SacArgs& a, int p) {
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
   const int js = live ? blockIdx.y * kMonoChunk + tid : 0;
   const uint16_t* smp = sac_sample<8>(a, p, a.N[p], st.r_begin + js, js);
-  geom::mono_front_thread<kMonoChunk, true>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * geom::kFrontOut);
+  geom::mono_front_thread<kMonoChunk, true, ALG>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * a.fo_stride);
 }
+template <int ALG>
 __global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a, int round) {
-  KML_ACTIVE_LOOP(mono_front_body(a, p))
+  KML_ACTIVE_LOOP(mono_front_body<ALG>(a, p))
 }
 
 __device__ void mono_isolate_body(const SacArgs& a, int p) {
@@ -303,7 +305,7 @@ __device__ void mono_isolate_body(const SacArgs& a, int p) {
   const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
   int nr = 0;
   if (tid < nh) {
-    nr = geom::mono_isolate_thread(a.fsol + slot * geom::kFrontOut, a.brk + slot * 2 * geom::kMaxBrackets,
+    nr = geom::mono_isolate_thread(a.fsol + slot * a.fo_stride, a.brk + slot * 2 * geom::kMaxBrackets,
                                    a.force_generic != 0);
     for (int chain = 0; chain < 2; ++chain)
       if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
@@ -352,13 +354,14 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacAr
     const size_t slot = item >> 5;
     const int chain = (item >> 4) & 1, root = item & 15;
     const int R0 = a.nroot[slot] & 255;
-    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * geom::kFrontOut, chain, root,
+    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * a.fo_stride, chain, root,
                                                    a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
   }
 }
 
 // thread = (draw, root) item over the whole round (grid-stride over the compacted list)
 constexpr int kItemThreads = 128;
+template <int ALG>
 __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
   const unsigned n = min(*a.item_count, a.item_cap);
   for (unsigned it = blockIdx.x * kItemThreads + threadIdx.x; it < n; it += gridDim.x * kItemThreads) {
@@ -367,14 +370,14 @@ __global__ void __launch_bounds__(kItemThreads, 4) mono_item_kernel(SacArgs a) {
     const int r = code & 31;
     const int p = (int)(slot / kRoundCap);
     const int R0 = a.nroot[slot] & 255;
-    const double* fo = a.fsol + slot * geom::kFrontOut;
+    const double* fo = a.fsol + slot * a.fo_stride;
     const double* bk = a.brk + slot * 2 * geom::kMaxBrackets + 2 * r;
     const double* ga = a.a + (size_t)p * a.stride * 3;
     const double* gb = a.b + (size_t)p * a.stride * 3;
     const int js = (int)(slot % kRoundCap);
     const uint16_t* smp = sac_sample<8>(a, p, a.N[p], a.st[p].r_begin + js, js);
     double q = 0.0, M[12];
-    const int status = geom::mono_item(fo, r >= R0 ? 1 : 0, bk[0], bk[1], ga, gb, smp, &q, M);
+    const int status = geom::mono_item<ALG>(fo, r >= R0 ? 1 : 0, bk[0], bk[1], ga, gb, smp, &q, M);
     a.item_status[it] = (uint8_t)status;
     if (status == 2) {
       a.item_q[it] = q;
@@ -800,6 +803,7 @@ __global__ void finalize_kernel(FinalizeArgs f) {
 }
 
 // --------------------------------------------------------------- launchers
+static_assert(geom::kFrontOut == 70 && geom::kFrontOutStew == 130, "lcd.cu sizes the stage-1 buffer with these");
 static size_t mono_smem() { return sizeof(double) * geom::kTphSlots * kMonoChunk; }
 static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
 
@@ -850,16 +854,22 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem();
   const size_t sm2 = sizeof(double) * geom::kIsoSlots * kMonoChunk;
-  ensure_smem(mono_front_kernel, sm);
   const int draws = min(kRoundCap, sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   const int gx = active_grid(a.P, round);
-  KML_LAUNCH((mono_front_kernel), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
+  if (a.alg == 1) {
+    ensure_smem(mono_front_kernel<1>, sm);
+    KML_LAUNCH((mono_front_kernel<1>), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
+  } else {
+    ensure_smem(mono_front_kernel<0>, sm);
+    KML_LAUNCH((mono_front_kernel<0>), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
+  }
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
   KML_LAUNCH((mono_isolate_kernel), dim3(gx, blocks), kMonoChunk, 0, s, a, round);
   KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, sm2, s, a);
-  KML_LAUNCH((mono_item_kernel), kNumSMs * 16, kItemThreads, 0, s, a);
+  if (a.alg == 1) KML_LAUNCH((mono_item_kernel<1>), kNumSMs * 16, kItemThreads, 0, s, a);
+  else KML_LAUNCH((mono_item_kernel<0>), kNumSMs * 16, kItemThreads, 0, s, a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);
   if (sm4 <= 96 * 1024) {
     ensure_smem(mono_count_kernel<true>, sm4);

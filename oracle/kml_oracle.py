@@ -211,6 +211,22 @@ def fivept_nister(f1, f2):
     return E[:n].copy()
 
 
+def fivept_stewenius(f1, f2):
+    """row f4: the Stewenius solver's real solutions (same conventions as fivept_nister)"""
+    f1, f2 = _f64(f1).reshape(5, 3), _f64(f2).reshape(5, 3)
+    E = np.zeros((10, 3, 3))
+    n = lib().kmo_fivept_stewenius(_p(f1, C.c_double), _p(f2, C.c_double), _p(E, C.c_double))
+    return E[:n].copy()
+
+
+def mono_model_alg(f1, f2, sample8, algorithm):
+    f1, f2 = _f64(f1).reshape(-1, 3), _f64(f2).reshape(-1, 3)
+    s8 = np.ascontiguousarray(sample8, np.uint16)
+    m = np.zeros(12)
+    ok = lib().kmo_mono_model_alg(_p(f1, C.c_double), _p(f2, C.c_double), _p(s8, C.c_uint16), _p(m, C.c_double), int(algorithm))
+    return bool(ok), m.reshape(3, 4)
+
+
 def mono_model(f1, f2, sample8):
     f1, f2 = _f64(f1).reshape(-1, 3), _f64(f2).reshape(-1, 3)
     s = np.ascontiguousarray(sample8, dtype=np.uint16)
@@ -261,6 +277,10 @@ def ransac_onepoint(p1, p2, R, thr=0.5, prob=0.995, max_iter=1000, seed=12345):
 
 def ransac_nister(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_nister, f1, f2, thr, prob, max_iter, seed)
+
+
+def ransac_stewenius(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
+    return _ransac(lib().kmo_ransac_stewenius, f1, f2, thr, prob, max_iter, seed)
 
 
 class LoopClosureDetector:

@@ -93,6 +93,10 @@ void kmo_arun3(const double* p1, const double* p2, double* model);
 /* f1,f2: 5 unit bearings each [5][3]; returns number of essential matrices
  * written to E[10][9] (row-major, f1^T E f2 = 0) */
 int kmo_fivept_nister(const double* f1, const double* f2, double* E);
+/* row f4: the Stewenius variant (action matrix; real solutions), same conventions */
+int kmo_fivept_stewenius(const double* f1, const double* f2, double* E);
+int kmo_mono_model_alg(const double* f1, const double* f2, const uint16_t* sample8, double* model, int algorithm);
+
 /* proper SVD used by both solvers: A = U diag(S) V^T, det U = det V = +1 */
 void kmo_svd3(const double* A, double* U, double* S, double* V);
 /* mono model from an 8-point sample (5 solve + 3 disambiguate); returns 0
@@ -121,6 +125,8 @@ void kmo_ransac_arun(const double* p1, const double* p2, int N, double thr,
 void kmo_ransac_nister(const double* f1, const double* f2, int N, double thr,
                        double prob, int max_iter, uint32_t seed,
                        kmo_ransac_result* res, uint32_t* inliers);
+void kmo_ransac_stewenius(const double* f1, const double* f2, int N, double thr, double prob, int max_iter,
+                          uint32_t seed, kmo_ransac_result* res, uint32_t* inliers);
 
 /* ---- A.3-A.8  LoopClosureDetector -------------------------------------- */
 typedef struct kmo_lcd kmo_lcd;

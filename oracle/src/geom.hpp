@@ -408,20 +408,18 @@ static inline int roots_unit(const double* p, int n, double* roots) {
   return nr;
 }
 
-// A.6 fivept_nister: f1 = bearings in frame 1 (query), f2 = frame 2 (match);
-// solves f1^T E f2 = 0 with E = [t12]x R12.  Returns #solutions, E row-major.
-static inline int fivept_nister(const double f1[5][3], const double f2[5][3], double E[10][9]) {
+// null space basis B (X, Y, Z, W) and the 10x20 cubic constraint matrix A in Nister's column order
+// [x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1]
+static inline void fivept_constraints(const double f1[5][3], const double f2[5][3], double B[4][9], double A[10][20]) {
   double Q[5][9];
   for (int k = 0; k < 5; ++k)
     for (int j = 0; j < 3; ++j)
       for (int i = 0; i < 3; ++i) Q[k][3 * j + i] = f2[k][i] * f1[k][j];
-  double B[4][9];
   nullspace5x9(Q, B);  // B[0]=X, B[1]=Y, B[2]=Z, B[3]=W (row-major 3x3 each)
   // entries of E(x,y,z) as deg1 polynomials
   double Ep[9][4];
   for (int e = 0; e < 9; ++e)
     for (int b = 0; b < 4; ++b) Ep[e][b] = B[b][e];
-  double A[10][20];
   for (int r = 0; r < 10; ++r)
     for (int c = 0; c < 20; ++c) A[r][c] = 0.0;
   // row 0: det(E)
@@ -464,7 +462,10 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
         for (int k = 0; k < 3; ++k) pmul21_acc(EEt[i][k], Ep[3 * k + j], row);
       }
   }
-  // Gauss-Jordan with partial pivoting on the first 10 columns
+}
+
+// Gauss-Jordan with partial pivoting (first maximum) on the first 10 columns; false = singular
+static inline bool fivept_gauss_jordan(double A[10][20]) {
   for (int c = 0; c < 10; ++c) {
     int pr = c;
     double pv = std::fabs(A[c][c]);
@@ -472,7 +473,7 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
       double v = std::fabs(A[r][c]);
       if (v > pv) { pv = v; pr = r; }
     }
-    if (!(pv > 0.0)) return 0;  // singular constraint system
+    if (!(pv > 0.0)) return false;  // singular constraint system
     if (pr != c)
       for (int j = 0; j < 20; ++j) { double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
     const double inv = 1.0 / A[c][c];  // pivot row scaled by the reciprocal (one division per pivot)
@@ -483,6 +484,15 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
       for (int j = 0; j < 20; ++j) A[r][j] = A[r][j] - f * A[c][j];
     }
   }
+  return true;
+}
+
+// A.6 fivept_nister: f1 = bearings in frame 1 (query), f2 = frame 2 (match);
+// solves f1^T E f2 = 0 with E = [t12]x R12.  Returns #solutions, E row-major.
+static inline int fivept_nister(const double f1[5][3], const double f2[5][3], double E[10][9]) {
+  double B[4][9], A[10][20];
+  fivept_constraints(f1, f2, B, A);
+  if (!fivept_gauss_jordan(A)) return 0;
   // B(z): rows <k>=<e>-z<f>, <l>=<g>-z<h>, <m>=<i>-z<j>; columns [x y 1];
   // coefficients ascending in z.
   double Bz[3][3][5];
@@ -549,10 +559,159 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
   return ns;
 }
 
+// Row f4: fivept_stewenius (opengv/src/relative_pose/modules/fivept_stewenius/modules.cpp), selected by
+// ransac_2d2d_algorithm: 0 (/root/reference/params/D455/LcdParams.yaml:73).  Same null space and the same
+// ten cubic constraints as Nister's solver, but the columns are ordered by degree
+//   [x3 x2y x2z xy2 xyz xz2 y3 y2z yz2 z3 | x2 xy xz y2 yz z2 x y z 1],
+// Gauss-Jordan on the ten cubic monomials expresses each of them in the quotient-ring basis
+// b = [x2 xy xz y2 yz z2 x y z 1], and the ACTION MATRIX of multiplication by x in that basis,
+//   rows 0..5 = -B[0..5] (x*x2 = x3, x*xy = x2y, x*xz = x2z, x*y2 = xy2, x*yz = xyz, x*z2 = xz2),
+//   rows 6..9 = unit rows (x*x = x2, x*y = xy, x*z = xz, x*1 = x),
+// has the solutions' x as eigenvalues and b(solution) as eigenvectors.  Upstream hands the 10x10
+// matrix to Eigen's complex EigenSolver and keeps the real part of every (also complex) eigenvector;
+// the restatement keeps the REAL solutions: eigenvalues = real roots of the characteristic polynomial
+// (elimination to Hessenberg form with first-maximum pivoting, then the recurrence over leading
+// minors), found by the same Sturm / bisection / Newton code as Nister's polynomial, and for every
+// root the eigenvector from rows 0..5 of (M - x I) v = 0 with v = [x2, xy, xz, v3, v4, v5, x, y, z, 1]:
+// six equations, five unknowns (v3, v4, v5, y, z), Gaussian elimination with first-maximum row pivoting.
+static const int kStewCol[20] = {0, 6, 1, 3, 2, 10, 7, 13, 4, 11, 5, 12, 16, 8, 14, 17, 9, 15, 18, 19};  // new column of Nister column c
+
+// characteristic polynomial det(lambda I - M) of a 10x10 matrix, ascending coefficients c[0..10] (c[10] = 1)
+static inline void charpoly10(double H[10][10], double* c) {
+  const int n = 10;
+  for (int m = 1; m < n - 1; ++m) {
+    double x = 0.0;
+    int i = m;
+    for (int j = m; j < n; ++j)
+      if (std::fabs(H[j][m - 1]) > std::fabs(x)) { x = H[j][m - 1]; i = j; }
+    if (i != m) {
+      for (int j = m - 1; j < n; ++j) { const double t = H[i][j]; H[i][j] = H[m][j]; H[m][j] = t; }
+      for (int j = 0; j < n; ++j) { const double t = H[j][i]; H[j][i] = H[j][m]; H[j][m] = t; }
+    }
+    if (x != 0.0) {
+      for (int i2 = m + 1; i2 < n; ++i2) {
+        double y = H[i2][m - 1];
+        if (y != 0.0) {
+          y = y / x;
+          H[i2][m - 1] = y;
+          for (int j = m; j < n; ++j) H[i2][j] = H[i2][j] - y * H[m][j];
+          for (int j = 0; j < n; ++j) H[j][m] = H[j][m] + y * H[j][i2];
+        }
+      }
+    }
+  }
+  // P[k] = characteristic polynomial of the leading k x k block, monic: P[k][k] = 1
+  double P[11][11];
+  for (int k = 0; k <= n; ++k)
+    for (int j = 0; j <= n; ++j) P[k][j] = 0.0;
+  P[0][0] = 1.0;
+  for (int k = 1; k <= n; ++k) {
+    const int col = k - 1;
+    const double h = H[col][col];
+    for (int j = 0; j <= k; ++j) P[k][j] = (j >= 1 ? P[k - 1][j - 1] : 0.0) - (j <= k - 1 ? h * P[k - 1][j] : 0.0);
+    double prod = 1.0;
+    for (int i = 1; i <= k - 1; ++i) {
+      const int row = col - i;
+      prod = prod * H[row + 1][row];
+      const double sc = H[row][col] * prod;
+      for (int j = 0; j <= k - 1 - i; ++j) P[k][j] = P[k][j] - sc * P[k - 1 - i][j];
+    }
+  }
+  for (int j = 0; j <= n; ++j) c[j] = P[n][j];
+}
+
+// y, z of the solution with eigenvalue x from the six non-trivial rows a[6][10] of the action matrix
+static inline bool stewenius_yz(const double a[6][10], double x, double* y, double* z) {
+  const double x2 = x * x;
+  double C[6][5], d[6];
+  for (int j = 0; j < 6; ++j) {
+    C[j][0] = a[j][3]; C[j][1] = a[j][4]; C[j][2] = a[j][5];
+    C[j][3] = a[j][1] * x + a[j][7];
+    C[j][4] = a[j][2] * x + a[j][8];
+    d[j] = -((a[j][0] * x2 + a[j][6] * x) + a[j][9]);
+  }
+  d[0] = d[0] + x * x2;   // row 0: lambda * v0 = x * x2
+  C[1][3] = C[1][3] - x2;  // row 1: lambda * v1 = x * (x y)
+  C[2][4] = C[2][4] - x2;  // row 2: lambda * v2 = x * (x z)
+  C[3][0] = C[3][0] - x;   // rows 3..5: lambda * v3, v4, v5
+  C[4][1] = C[4][1] - x;
+  C[5][2] = C[5][2] - x;
+  for (int c = 0; c < 5; ++c) {
+    int pr = c;
+    double pv = std::fabs(C[c][c]);
+    for (int r = c + 1; r < 6; ++r) {
+      const double v = std::fabs(C[r][c]);
+      if (v > pv) { pv = v; pr = r; }
+    }
+    if (!(pv > 0.0)) return false;
+    if (pr != c) {
+      for (int j = 0; j < 5; ++j) { const double t = C[c][j]; C[c][j] = C[pr][j]; C[pr][j] = t; }
+      const double t = d[c]; d[c] = d[pr]; d[pr] = t;
+    }
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = C[r][c] / C[c][c];
+      for (int j = c + 1; j < 5; ++j) C[r][j] = C[r][j] - f * C[c][j];
+      d[r] = d[r] - f * d[c];
+    }
+  }
+  double u[5];
+  for (int c = 4; c >= 0; --c) {
+    double sacc = d[c];
+    for (int j = c + 1; j < 5; ++j) sacc = sacc - C[c][j] * u[j];
+    u[c] = sacc / C[c][c];
+  }
+  *y = u[3];
+  *z = u[4];
+  return true;
+}
+
+static inline int fivept_stewenius(const double f1[5][3], const double f2[5][3], double E[10][9]) {
+  double B[4][9], An[10][20], A[10][20];
+  fivept_constraints(f1, f2, B, An);
+  for (int r = 0; r < 10; ++r)
+    for (int c = 0; c < 20; ++c) A[r][kStewCol[c]] = An[r][c];
+  if (!fivept_gauss_jordan(A)) return 0;
+  double M[6][10], H[10][10];
+  for (int i = 0; i < 10; ++i)
+    for (int j = 0; j < 10; ++j) H[i][j] = 0.0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 10; ++j) { M[i][j] = -A[i][10 + j]; H[i][j] = M[i][j]; }
+  H[6][0] = 1.0; H[7][1] = 1.0; H[8][2] = 1.0; H[9][6] = 1.0;
+  double cp[11], rp[11];
+  charpoly10(H, cp);
+  for (int k = 0; k < 11; ++k) rp[k] = cp[10 - k];
+  double xr[20];
+  int nroots = 0;
+  {
+    double r[10];
+    int n = roots_unit(cp, 10, r);
+    for (int i = 0; i < n; ++i) xr[nroots++] = r[i];
+    n = roots_unit(rp, 10, r);
+    for (int i = 0; i < n; ++i) {
+      if (r[i] == 1.0 || r[i] == 0.0) continue;
+      if (nroots < 10) xr[nroots++] = 1.0 / r[i];
+    }
+  }
+  int ns = 0;
+  for (int k = 0; k < nroots && ns < 10; ++k) {
+    const double x = xr[k];
+    double y, z;
+    if (!stewenius_yz(M, x, &y, &z)) continue;
+    bool ok = true;
+    for (int e = 0; e < 9; ++e) {
+      const double v = ((x * B[0][e] + y * B[1][e]) + z * B[2][e]) + B[3][e];
+      if (!std::isfinite(v)) ok = false;
+      E[ns][e] = v;
+    }
+    if (ok) ++ns;
+  }
+  return ns;
+}
+
 // A.6 computeModelCoefficients for NISTER: sample of 8 (5 solve + 3 extra).
 // f1/f2 are the full correspondence arrays [N][3]; model = [R12|t12] 3x4.
 static inline bool mono_model(const double* f1, const double* f2, const uint16_t* sample,
-                              double* model) {
+                              double* model, int algorithm = 0) {
   double a[5][3], b[5][3];
   for (int k = 0; k < 5; ++k)
     for (int i = 0; i < 3; ++i) {
@@ -560,7 +719,7 @@ static inline bool mono_model(const double* f1, const double* f2, const uint16_t
       b[k][i] = f2[3 * sample[k] + i];
     }
   double E[10][9];
-  int ne = fivept_nister(a, b, E);
+  int ne = algorithm == 1 ? fivept_stewenius(a, b, E) : fivept_nister(a, b, E);
   double best = 1000000.0;
   bool found = false;
   for (int e = 0; e < ne; ++e) {

@@ -258,9 +258,9 @@ struct OnePointProblem {
   }
 };
 
-struct NisterProblem {
-  const double* f1; const double* f2; int N;
-  bool compute(const uint16_t* s, double* model) const { return mono_model(f1, f2, s, model); }
+struct NisterProblem {  // CentralRelativePoseSacProblem: algorithm 0 = NISTER, 1 = STEWENIUS (row f4)
+  const double* f1; const double* f2; int N; int algorithm = 0;
+  bool compute(const uint16_t* s, double* model) const { return mono_model(f1, f2, s, model, algorithm); }
   int count(const double* m, double thr) const {
     double tinv[3];
     mono_tinv(m, tinv);
@@ -362,7 +362,7 @@ static int verify_pair(const kmo_lcd* L, const Frame& fq, const Frame& fm, kmo_r
     }
   kmo_ransac_result rr;
   std::vector<uint32_t> inl(std::max(M, 1));
-  NisterProblem np{b1.data(), b2.data(), M};
+  NisterProblem np{b1.data(), b2.data(), M, P.mono_algorithm};
   ransac(np, M, 8, P.ransac_threshold_mono, P.ransac_probability_mono,
          P.max_ransac_iterations_mono, P.ransac_seed, &rr, inl.data());
   if (!rr.success) return 1;
@@ -535,8 +535,23 @@ void kmo_ransac_arun(const double* p1, const double* p2, int N, double thr, doub
 }
 void kmo_ransac_nister(const double* f1, const double* f2, int N, double thr, double prob,
                        int max_iter, uint32_t seed, kmo_ransac_result* res, uint32_t* inliers) {
-  NisterProblem np{f1, f2, N};
+  NisterProblem np{f1, f2, N, 0};
   ransac(np, N, 8, thr, prob, max_iter, seed, res, inliers);
+}
+void kmo_ransac_stewenius(const double* f1, const double* f2, int N, double thr, double prob,
+                          int max_iter, uint32_t seed, kmo_ransac_result* res, uint32_t* inliers) {
+  NisterProblem np{f1, f2, N, 1};
+  ransac(np, N, 8, thr, prob, max_iter, seed, res, inliers);
+}
+int kmo_fivept_stewenius(const double* f1, const double* f2, double* E) {
+  double a[5][3], b[5][3], Es[10][9];
+  memcpy(a, f1, sizeof(a)); memcpy(b, f2, sizeof(b));
+  int n = fivept_stewenius(a, b, Es);
+  memcpy(E, Es, sizeof(double) * 9 * n);
+  return n;
+}
+int kmo_mono_model_alg(const double* f1, const double* f2, const uint16_t* sample8, double* model, int algorithm) {
+  return mono_model(f1, f2, sample8, model, algorithm) ? 1 : 0;
 }
 
 kmo_lcd* kmo_lcd_create(const kmo_params* p) {
@@ -624,8 +639,8 @@ int kmo_lcd_geometric_verification_nister(kmo_lcd* L, uint64_t qr, uint64_t qp, 
     }
   kmo_ransac_result rr;
   std::vector<uint32_t> inl(std::max(M, 1));
-  NisterProblem np{b1.data(), b2.data(), M};
   const kmo_params& P = L->prm;
+  NisterProblem np{b1.data(), b2.data(), M, P.mono_algorithm};
   ransac(np, M, 8, P.ransac_threshold_mono, P.ransac_probability_mono,
          P.max_ransac_iterations_mono, P.ransac_seed, &rr, inl.data());
   if (!rr.success) return 0;

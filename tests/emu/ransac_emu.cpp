@@ -45,7 +45,7 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   if (mono) {
     const size_t max_items = Pa * kRoundCap * 10;  // a draw has at most 10 real roots
     nroot.resize(Pa * kRoundCap);
-    fsol.resize(Pa * kRoundCap * 70);
+    fsol.resize(Pa * kRoundCap * 130);
     brk.resize(Pa * kRoundCap * 40);
     fb.resize(max_items + 4);
     item_base.resize(Pa * kRoundCap);
@@ -71,6 +71,8 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.sq_crit = sq_crit_of(threshold);
   a.max_iterations = max_it; a.full = full; a.force_generic = force_generic;
   a.onept = 0; a.prior = nullptr;
+  a.alg = (mono && getenv("KML_EMU_STEWENIUS")) ? 1 : 0;
+  a.fo_stride = a.alg == 1 ? 130 : 70;
   std::vector<int32_t> active(2 * Pa + 2, 0);
   a.n_active = reinterpret_cast<unsigned int*>(active.data()); a.active = active.data() + 2;
   // per-N sample table (ensure_sample_table of lcd.cu) unless the caller asks for the per-problem sampler

@@ -464,3 +464,25 @@ def test_ransac_per_problem_sampler_without_the_table(oracle, ransacemu):
     for p in range(3):
         o = oracle.ransac_arun(p1[p], p2[p], 0.5, 0.995, 1000, 12345)
         assert o["iterations"] == g0["iterations"][p] and o["best_draw"] == g0["best_draw"][p]
+
+
+def test_mono_ransac_stewenius_kernels_equal_the_oracle_loop(oracle, ransacemu):
+    """Row f4, ransac_2d2d_algorithm: 0 (/root/reference/params/D455/LcdParams.yaml:73): the mono round
+    with the Stewenius front stage (degree-ordered constraint matrix, full Gauss-Jordan, action matrix,
+    characteristic polynomial) and eigenvector item stage, emulated, against the oracle's loop with
+    its Stewenius restatement: iteration counts, winning draw, inlier set and model bit-exact."""
+    from test_gpu_parity import _nister_case
+    rng = np.random.default_rng(77)
+    kinds = ["plain", "low_parallax", "far_points", "near_centres", "duplicates"]
+    os.environ["KML_EMU_STEWENIUS"] = "1"
+    try:
+        for thr, N in [(1e-6, 60), (1e-8, 33), (1e-4, 9)]:
+            f1, f2 = np.zeros((len(kinds), N, 3)), np.zeros((len(kinds), N, 3))
+            for i, kind in enumerate(kinds):
+                f1[i], f2[i] = _nister_case(rng, N, kind)
+            g = emu_ransac(ransacemu, True, f1, f2, thr)
+            for p in range(len(kinds)):
+                o = oracle.ransac_stewenius(f1[p], f2[p], thr, 0.995, 1000, 12345)
+                _same_as_oracle(o, g, p, N, (kinds[p], thr))
+    finally:
+        del os.environ["KML_EMU_STEWENIUS"]

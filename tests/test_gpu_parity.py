@@ -622,3 +622,71 @@ def test_load_shard_rejects_corrupt_files(tmp_path, gpu_lcd):
         det.load(str(tmp_path / "does_not_exist.kml"))
     assert e.value.code == -6
     det.close()
+
+
+def test_stewenius_five_point_algorithm(oracle, small_world):
+    """Row f4 (/root/reference/params/D455/LcdParams.yaml:73 ransac_2d2d_algorithm: 0 # Stewenius):
+    kml_params.mono_algorithm = 1 — the mono RANSAC with the action-matrix solver, standalone, in
+    geometricVerificationNister and in the batch query, bit-exact against the oracle's restatement;
+    and it agrees with the Nister solver on what matters (same loop closures on the small world)."""
+    import kml
+    from kml import mask_to_indices
+    from conftest import fill
+    rng = np.random.default_rng(41)
+    prm = kml.default_params()
+    prm.mono_algorithm = 1
+    det = kml.LoopClosureDetector(prm)
+    kinds = ["plain", "low_parallax", "far_points", "near_centres", "non_unit", "duplicates"]
+    for thr, N in [(1e-6, 80), (1e-9, 33), (1e-4, 9), (5e-8, 8)]:
+        f1, f2 = np.zeros((len(kinds), N, 3)), np.zeros((len(kinds), N, 3))
+        for i, kind in enumerate(kinds):
+            f1[i], f2[i] = _nister_case(rng, N, kind)
+        prm2 = kml.default_params()
+        prm2.mono_algorithm = 1
+        prm2.ransac_threshold_mono = thr
+        d2 = kml.LoopClosureDetector(prm2)
+        g = d2.ransac_nister_batch(f1, f2)
+        for p in range(len(kinds)):
+            o = oracle.ransac_stewenius(f1[p], f2[p], thr, 0.995, 1000, 12345)
+            assert o["iterations"] == g["iterations"][p] and o["best_draw"] == g["best_draw"][p], (kinds[p], thr)
+            assert o["n_inliers"] == g["n_inliers"][p]
+            assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][p], N))
+            if o["best_draw"] >= 0:
+                assert np.array_equal(o["model"], g["models"][p]), (kinds[p], thr)
+        d2.close()
+    world, chunks, queries = small_world
+    fill(det, chunks, bulk=True)
+    oprm = oracle.default_params()
+    oprm.mono_algorithm = 1
+    ref = oracle.LoopClosureDetector(oprm)
+    fill(ref, chunks)
+    fq, fp = queries["frames"], queries["prev"]
+    args = (queries["q_robot"], queries["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+            fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    o1, c1 = det.query_batch(*args)
+    o0, c0 = ref.query_batch(*args)
+    assert np.array_equal(c0, c1)
+    n_lc = 0
+    for b in range(len(c0)):
+        for i in range(c0[b]):
+            for k in ("m_robot", "m_pose", "n_matches", "mono_inliers", "stereo_inliers", "status"):
+                assert o0[b, i][k] == o1[b, i][k], (b, i, k)
+            if o0[b, i]["status"] == 0:
+                n_lc += 1
+                assert np.abs(o0[b, i]["T"] - o1[b, i]["T"]).max() <= POSE_TOL
+    assert n_lc > 0
+    # the two solvers find the same loop closures (statuses), not necessarily the same winning draws
+    nis = kml.LoopClosureDetector()
+    fill(nis, chunks, bulk=True)
+    o2, c2 = nis.query_batch(*args)
+    assert np.array_equal(c1, c2)
+    agree = sum(int(o1[b, i]["status"] == o2[b, i]["status"]) for b in range(len(c1)) for i in range(c1[b]))
+    assert agree >= 0.95 * int(c1.sum())
+    ch = chunks[0]
+    qa, ma = int(ch["poses"][3]), int(ch["poses"][3]) + 100
+    iq, im = det.computeMatchedIndices(0, qa, 0, ma)
+    ok, jq, jm, R = det.geometricVerificationNister(0, qa, 0, ma, iq, im)
+    ok0, kq, km, R0 = ref.geometricVerificationNister(0, qa, 0, ma, iq, im)
+    assert ok == ok0 and np.array_equal(jq, kq) and np.array_equal(R, R0)
+    nis.close()
+    det.close()

@@ -273,25 +273,29 @@ __global__ void __launch_bounds__(32) sac_replay_kernel(SacArgs a, int round) {
 //                        the fast inlier filter, stopping once the draw cannot
 //                        beat the best count of the draws before it.
 //   sac_replay_kernel    lane 0 per problem replays Ransac::computeModel.
+// The front kernel's CTA is ONE warp of draws (its 200 shared-memory slots per draw set the
+// occupancy: 51 KB per CTA, four CTAs per SM): the first rounds evaluate 32 draws per problem, and a
+// 64-thread CTA would hold a second warp's worth of shared memory for nothing.
+constexpr int kFrontChunk = 32;
 template <int ALG>
 __device__ void mono_front_body(const SacArgs& a, int p) {
   KML_DYN_SMEM(double, smem_d);
   const SacState st = a.st[p];
   if (st.done) return;
-  const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
+  const int d0 = st.r_begin + blockIdx.y * kFrontChunk;
   if (d0 >= st.r_end) return;
   const int tid = threadIdx.x;
   const double* ga = a.a + (size_t)p * a.stride * 3;
   const double* gb = a.b + (size_t)p * a.stride * 3;
-  const int nh = min(kMonoChunk, st.r_end - d0);
+  const int nh = min(kFrontChunk, st.r_end - d0);
   const bool live = tid < nh;
-  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
-  const int js = live ? blockIdx.y * kMonoChunk + tid : 0;
+  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kFrontChunk + tid;
+  const int js = live ? blockIdx.y * kFrontChunk + tid : 0;
   const uint16_t* smp = sac_sample<8>(a, p, a.N[p], st.r_begin + js, js);
-  geom::mono_front_thread<kMonoChunk, true, ALG>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * a.fo_stride);
+  geom::mono_front_thread<kFrontChunk, true, ALG>(smem_d + tid, ga, gb, smp, live, a.fsol + slot * a.fo_stride);
 }
 template <int ALG>
-__global__ void __launch_bounds__(kMonoChunk, 2) mono_front_kernel(SacArgs a, int round) {
+__global__ void __launch_bounds__(kFrontChunk, 4) mono_front_kernel(SacArgs a, int round) {
   KML_ACTIVE_LOOP(mono_front_body<ALG>(a, p))
 }
 
@@ -804,7 +808,7 @@ __global__ void finalize_kernel(FinalizeArgs f) {
 
 // --------------------------------------------------------------- launchers
 static_assert(geom::kFrontOut == 70 && geom::kFrontOutStew == 130, "lcd.cu sizes the stage-1 buffer with these");
-static size_t mono_smem() { return sizeof(double) * geom::kTphSlots * kMonoChunk; }
+static size_t mono_smem() { return sizeof(double) * geom::kTphSlots * kFrontChunk; }
 static size_t stereo_smem(int stride) { return sizeof(double) * (6 * (size_t)stride + 12 * kStereoChunk); }
 
 template <class K>
@@ -857,12 +861,13 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   const int draws = min(kRoundCap, sac_round_draws(round, kMonoChunk));
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   const int gx = active_grid(a.P, round);
+  const int fblocks = (draws + kFrontChunk - 1) / kFrontChunk;
   if (a.alg == 1) {
     ensure_smem(mono_front_kernel<1>, sm);
-    KML_LAUNCH((mono_front_kernel<1>), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
+    KML_LAUNCH((mono_front_kernel<1>), dim3(gx, fblocks), kFrontChunk, sm, s, a, round);
   } else {
     ensure_smem(mono_front_kernel<0>, sm);
-    KML_LAUNCH((mono_front_kernel<0>), dim3(gx, blocks), kMonoChunk, sm, s, a, round);
+    KML_LAUNCH((mono_front_kernel<0>), dim3(gx, fblocks), kFrontChunk, sm, s, a, round);
   }
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list

@@ -208,6 +208,7 @@ int kml_create(const kml_params* p, int device, kml_handle** out) {
 }
 
 void kml_comm_destroy_internal(kml_handle* h);
+void kml_graph_destroy_internal(kml_handle* h);
 
 // A query lane: a second handle that SHARES the parent's databases, frame store, RANSAC
 // constants and vocabulary (read-only while queries run) but owns its stream, events and
@@ -238,6 +239,7 @@ int kml_destroy(kml_handle* h) {
   if (!h) return KML_ERR_ARG;
   cudaSetDevice(h->device);
   kml_comm_destroy_internal(h);
+  kml_graph_destroy_internal(h);
   if (h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);

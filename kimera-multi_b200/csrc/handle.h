@@ -201,6 +201,8 @@ struct kml_handle {
   kml::PinBuf<uint8_t> h_in;     // pinned staging of a query batch that arrives in pageable memory
   kml::DevBuf<uint8_t> d_in;     // the packed query batch on the device
   size_t item_cap = 0;           // capacity of the mono rounds' item lists (grows after an overflow)
+  bool capturing = false;        // a stream capture of the batch pipeline is in progress (lcd.cu)
+  void* graph_cache = nullptr;   // lcd.cu GraphCache: the captured pipeline of small batches
 
   kml::Comm* comm = nullptr;
 };

@@ -89,6 +89,7 @@ struct SacArgs {
   uint16_t* perm;        // [P][stride] persistent shuffle state
   int cap_draws;         // draws available per problem (raw_len / S)
   double* models;        // [P][kRoundCap][12] models of the draws of the current round
+  int first, n_rounds;   // round schedule (sac_round_draws): draws of round 0, rounds enqueued blindly
   int alg;               // mono: 0 = NISTER, 1 = STEWENIUS (row f4)
   int fo_stride;         // mono: doubles of stage-1 output per draw (geom::kFrontOut / kFrontOutStew)
   double* fsol;          // mono: [P][kRoundCap][fo_stride] stage-1 output per draw of the round
@@ -142,15 +143,20 @@ struct SacArgs {
 constexpr int kMonoChunk = 64;     // hypotheses per CTA (mono) and size of round 0
 constexpr int kStereoChunk = 64;    // hypotheses per CTA (stereo) and size of round 0
 constexpr int kStereoThreads = 128; // threads of a stereo CTA (4 counting warps)
-constexpr int kSacRounds = 7;      // rounds enqueued blindly: 32,32,64,128,256,512,512 new draws at most; more only while a problem is pending
 constexpr int kRoundCap = 512;     // most new draws any round evaluates per problem
-// upper bound of NEW draws evaluated per problem in round r: half a chunk (one warp of draws) in
-// rounds 0 and 1, then doubling.  Nearly half of the candidate pairs of a batch end within 16
-// trials (few correspondences, or an overwhelming inlier ratio): a 32-draw first round evaluates
-// 16 draws too many for them, a 64-draw one 48.
-__host__ __device__ inline int sac_round_draws(int round, int chunk) {
-  const int first = chunk / 2;
-  return round == 0 ? first : (round > 9 ? first << 9 : first << (round - 1));
+// Round schedule (SacArgs::first, SacArgs::n_rounds).  Round r evaluates at most `first` new draws
+// per problem for r = 0, 1, then doubles (first << (r - 1)), capped at kRoundCap.  Throughput mode
+// (batches of >= 16 queries): first = 32, 7 blind rounds = 32,32,64,128,256,512,512 — nearly half of
+// the candidate pairs of a batch end within 16 trials, and a draw evaluated for nothing costs
+// throughput.  Latency mode (small batches: the GPU is idle anyway and every round is a chain of
+// six dependent kernel latencies): first = 128, 4 blind rounds = 128,128,256,512.  The outcome does
+// not depend on the schedule (the replay consumes draws in order); more rounds are added by the host
+// only while a problem is pending.
+constexpr int kSacFirstThroughput = 32, kSacRoundsThroughput = 7;
+constexpr int kSacFirstLatency = 128, kSacRoundsLatency = 4;
+__host__ __device__ inline int sac_round_draws(int round, int first) {
+  const int d = round == 0 ? first : (round > 9 ? first << 9 : first << (round - 1));
+  return d < kRoundCap ? d : kRoundCap;
 }
 void launch_sac_init(const SacArgs& a, int sample_size, cudaStream_t s);
 // tab[N][cap_draws][S] for N in [0, nmax]: the draws of SampleConsensusProblem::drawIndexSample

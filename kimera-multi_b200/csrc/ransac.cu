@@ -126,14 +126,14 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
     st->k = 1.0;
     st->done = (N < S) ? 1 : 0;  // getSamples(): N < sample_size => loop exits, no model
     st->r_begin = 0;
-    st->r_end = (N < S) ? 0 : min(sac_round_draws(0, CHUNK), a.cap_draws);
+    st->r_end = (N < S) ? 0 : min(sac_round_draws(0, a.first), a.cap_draws);
   }
   __syncwarp();
   if (!tab) {
     if (N >= S) {
       uint16_t* jrel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(perm_s) + sac_perm_bytes(a.stride) +
                                                      sizeof(int32_t) * kRoundCap);
-      draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(sac_round_draws(0, CHUNK), a.cap_draws),
+      draw_samples_warp<S>(perm_s, jrel_s, N, a.raw, 0, min(sac_round_draws(0, a.first), a.cap_draws),
                            a.samples + (size_t)p * kRoundCap * S, lane);
     }
     for (int i = lane; i < N; i += 32) a.perm[(size_t)p * a.stride + i] = perm_s[i];
@@ -201,7 +201,7 @@ __device__ void sac_replay_body(const SacArgs& a, int round, int p) {
       // kSacRounds rounds blindly and keeps adding rounds while a problem is
       // pending, so every draw the reference loop can consume (max_iterations + 1
       // counted trials + max_skip skipped samples = cap_draws) is reachable.
-      const int grow = min(sac_round_draws(round + 1, CHUNK), kRoundCap);
+      const int grow = sac_round_draws(round + 1, a.first);
       ne = min(a.cap_draws, nb + min(rem + 16, grow));
       if (nb >= a.cap_draws) { done = 1; exhausted = 1; }  // unreachable: the loop ends by its own limits first
     }
@@ -858,7 +858,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem();
   const size_t sm2 = sizeof(double) * geom::kIsoSlots * kMonoChunk;
-  const int draws = min(kRoundCap, sac_round_draws(round, kMonoChunk));
+  const int draws = sac_round_draws(round, a.first);
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   const int gx = active_grid(a.P, round);
   const int fblocks = (draws + kFrontChunk - 1) / kFrontChunk;
@@ -883,7 +883,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
     KML_LAUNCH((mono_count_kernel<false>), dim3(gx, blocks), kCountThreads, 0, s, a, round);
   }
 #ifdef KML_FILTER_STATS
-  if (round == kSacRounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
+  if (round == a.n_rounds - 1) fstats_print_kernel<<<1, 1, 0, s>>>();
 #endif
   KML_LAUNCH((sac_replay_kernel<8, kMonoChunk>), gx, 32, sac_warp_smem<8>(a.stride), s, a, round);
   return 6;
@@ -891,7 +891,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
 int launch_stereo_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = stereo_smem(a.stride);
-  const int draws = min(kRoundCap, sac_round_draws(round, kStereoChunk));
+  const int draws = sac_round_draws(round, a.first);
   const int blocks = (draws + kStereoChunk - 1) / kStereoChunk;
   const size_t sm0 = sizeof(double) * 12 * kStereoChunk;
   const int gx = active_grid(a.P, round);

@@ -71,6 +71,8 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   a.sq_crit = sq_crit_of(threshold);
   a.max_iterations = max_it; a.full = full; a.force_generic = force_generic;
   a.onept = 0; a.prior = nullptr;
+  a.first = getenv("KML_EMU_LATENCY_SCHEDULE") ? kSacFirstLatency : kSacFirstThroughput;
+  a.n_rounds = getenv("KML_EMU_LATENCY_SCHEDULE") ? kSacRoundsLatency : kSacRoundsThroughput;
   a.alg = (mono && getenv("KML_EMU_STEWENIUS")) ? 1 : 0;
   a.fo_stride = a.alg == 1 ? 130 : 70;
   std::vector<int32_t> active(2 * Pa + 2, 0);
@@ -85,12 +87,12 @@ int ransacemu_batch(int mono, int P, int N, const double* a_in, const double* b_
   }
   a.inlier_mask = mask.data(); a.mask_words = mask_words; a.n_inliers = inl.data();
   launch_sac_init(a, S, nullptr);
-  for (int r = 0; r < kSacRounds; ++r) {
+  for (int r = 0; r < a.n_rounds; ++r) {
     if (mono) launch_mono_round(a, r, nullptr); else launch_stereo_round(a, r, nullptr);
   }
   // finish_sac of lcd.cu: rounds are added while a problem's loop has not ended
   a.pending = fb.data() + 3;
-  for (int r = kSacRounds;; ++r) {
+  for (int r = a.n_rounds;; ++r) {
     fb[3] = 0;
     launch_sac_pending(a, nullptr);
     if (fb[2]) return -4;  // item lists overflowed (cannot happen at the worst-case size used here)

@@ -486,3 +486,24 @@ def test_mono_ransac_stewenius_kernels_equal_the_oracle_loop(oracle, ransacemu):
                 _same_as_oracle(o, g, p, N, (kinds[p], thr))
     finally:
         del os.environ["KML_EMU_STEWENIUS"]
+
+
+def test_ransac_outcome_does_not_depend_on_the_round_schedule(oracle, ransacemu):
+    """Latency schedule (128, 128, 256, 512 draws per round, small problem sets) against the throughput
+    schedule (32, 32, 64, ...): the replay consumes draws in order, so iterations, winner, inlier set
+    and model are the same, and the oracle's."""
+    from test_gpu_parity import _nister_case
+    rng = np.random.default_rng(8)
+    f1, f2 = np.zeros((4, 50, 3)), np.zeros((4, 50, 3))
+    for i, kind in enumerate(["plain", "low_parallax", "duplicates", "far_points"]):
+        f1[i], f2[i] = _nister_case(rng, 50, kind)
+    g0 = emu_ransac(ransacemu, True, f1, f2, 1e-6)
+    os.environ["KML_EMU_LATENCY_SCHEDULE"] = "1"
+    try:
+        g1 = emu_ransac(ransacemu, True, f1, f2, 1e-6)
+    finally:
+        del os.environ["KML_EMU_LATENCY_SCHEDULE"]
+    for k in ("iterations", "best_draw", "n_inliers", "mask", "models"):
+        assert np.array_equal(g0[k], g1[k]), k
+    for p in range(4):
+        _same_as_oracle(oracle.ransac_nister(f1[p], f2[p], 1e-6, 0.995, 1000, 12345), g1, p, 50, p)

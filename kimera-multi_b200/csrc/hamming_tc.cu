@@ -171,7 +171,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
   uint32_t ph[2] = {0u, 0u};  // phase parity of full[0], full[1] (every thread tracks both)
 
-  for (int job_i = blockIdx.x; job_i < njobs; job_i += gridDim.x) {
+  // A CTA takes a CONTIGUOUS range of the job list: the candidate pairs of one query frame are
+  // consecutive jobs with the same query side, whose expansion is then reused (it is a fifth of
+  // the CUDA-core work of a pair).
+  const int j_lo = (int)(((long long)njobs * blockIdx.x) / gridDim.x);
+  const int j_hi = (int)(((long long)njobs * (blockIdx.x + 1)) / gridDim.x);
+  const uint8_t* a_src = nullptr;  // what sA currently holds: rows [a_q0, a_q0 + a_nq) of a_src
+  int a_q0 = -1, a_nq = -1;
+  for (int job_i = j_lo; job_i < j_hi; ++job_i) {
     const HamJob job = jobs[job_i];
     if (job.nq <= 0) continue;
     for (int q0 = 0; q0 < job.nq; q0 += kTcMTiles * kTcM) {
@@ -180,9 +187,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
       uint32_t best[kTcMTiles], second[kTcMTiles];
 #pragma unroll
       for (int m = 0; m < kTcMTiles; ++m) best[m] = second[m] = 0xFFFFFFFFu;
-      // query side: up to 512 rows, tile m at sA + m * 32 KB
-      for (int m = 0; m < mtiles; ++m)
-        tc_expand_rows(sA + m * kTcATile, kTcASlab, job.q + (size_t)(q0 + m * kTcM) * 32, min(kTcM, nq - m * kTcM), tid);
+      // query side: up to 512 rows, tile m at sA + m * 32 KB (kept if the previous job left the same rows there)
+      if (!(job.q == a_src && q0 == a_q0 && nq == a_nq)) {
+        for (int m = 0; m < mtiles; ++m)
+          tc_expand_rows(sA + m * kTcATile, kTcASlab, job.q + (size_t)(q0 + m * kTcM) * 32, min(kTcM, nq - m * kTcM), tid);
+        a_src = job.q; a_q0 = q0; a_nq = nq;
+      }
       // train side: one 256-row tile at a time; the packed rows of the NEXT tile are loaded into
       // registers (2 items per thread) while the tensor pipe and the epilogue work on this one
       uint4 pf0 = tc_load_item(job.t, tid, min(kTcN, job.nt));

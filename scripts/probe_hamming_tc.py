@@ -3,7 +3,8 @@ sys.path.insert(0, "kimera-multi_b200"); sys.path.insert(0, "oracle")
 import numpy as np, kml, kml_oracle as ko
 prm = kml.default_params(); prm.matcher_engine = 1
 det = kml.LoopClosureDetector(prm)
-d0 = kml.LoopClosureDetector()
+p0 = kml.default_params(); p0.matcher_engine = 0
+d0 = kml.LoopClosureDetector(p0)
 rng = np.random.default_rng(1)
 for nq, nt in [(128, 256), (500, 500), (513, 255), (64, 20000)]:
     q = rng.integers(0, 256, (nq, 32), np.uint8); t = rng.integers(0, 256, (nt, 32), np.uint8)

@@ -466,8 +466,11 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.ktable_n = mono ? h->sh->ktable_n_mono : onept ? h->sh->ktable_n_stereo1 : h->sh->ktable_n_stereo;
   a.onept = onept ? 1 : 0;
   a.prior = d_prior;
-  // latency mode for small problem sets (a single query's 16 candidate pairs, the single-pair entry points)
-  const bool latency = P <= 256;
+  // latency schedule for small problem sets (a single query's 16 candidate pairs, the single-pair entry
+  // points) and for every stereo problem: a 3-point (or 1-point) hypothesis costs a few hundred flops, the
+  // mono inliers it runs on are mostly inliers again (k is small), so a stereo round is six-fold cheaper
+  // than its launch chain and fewer, larger rounds win even when the GPU is busy
+  const bool latency = P <= 256 || (!mono && !full);
   a.first = latency ? kSacFirstLatency : kSacFirstThroughput;
   a.n_rounds = latency ? kSacRoundsLatency : kSacRoundsThroughput;
   a.alg = (mono && prm.mono_algorithm == 1) ? 1 : 0;

@@ -467,10 +467,10 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.onept = onept ? 1 : 0;
   a.prior = d_prior;
   // latency schedule for small problem sets (a single query's 16 candidate pairs, the single-pair entry
-  // points) and for every stereo problem: a 3-point (or 1-point) hypothesis costs a few hundred flops, the
-  // mono inliers it runs on are mostly inliers again (k is small), so a stereo round is six-fold cheaper
-  // than its launch chain and fewer, larger rounds win even when the GPU is busy
-  const bool latency = P <= 256 || (!mono && !full);
+  // points).  (Tried and dropped: the latency schedule for every stereo problem — 128-draw rounds made the
+  // stereo stage of a C2 batch slower, 0.48 -> 0.60 ms: the extra draws' inlier counts cost more than the
+  // three rounds they save.)
+  const bool latency = P <= 256;
   a.first = latency ? kSacFirstLatency : kSacFirstThroughput;
   a.n_rounds = latency ? kSacRoundsLatency : kSacRoundsThroughput;
   a.alg = (mono && prm.mono_algorithm == 1) ? 1 : 0;

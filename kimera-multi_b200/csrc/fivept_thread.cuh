@@ -604,10 +604,50 @@ __device__ __noinline__ int mono_isolate_generic(const double* __restrict__ fo, 
   return R0 | (R1 << 8) | ((int)def0 << 16) | ((int)def1 << 17);
 #undef S
 }
-// the deferred case of one (draw, chain): brackets by bisection on the Sturm count
+// Second grid of the deferred chains (oracle: kRootGrid2): 256 cells on (-1, 1], the rule of the first
+// grid (sign change across the cell, or p(x_i) == 0).  If the number of bracketing cells equals the
+// chain's root count R they are the isolating brackets and root j's is returned; four independent
+// Horner recurrences are in flight at a time.
+constexpr int kTRootGrid2 = 256;
+__device__ __noinline__ bool isolate_grid2(const double* cr, int R, int j, double* lo, double* hi) {
+  int nb = 0, cell_j = -1;
+  double fprev = horner_r<10>(cr, -1.0);
+#pragma unroll 1
+  for (int i0 = 1; i0 <= kTRootGrid2; i0 += 4) {
+    double f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) f[u] = horner_r<10>(cr, -1.0 + (double)(i0 + u) * (2.0 / kTRootGrid2));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double fi = f[u];
+      const bool hit = (fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0;
+      if (hit) {
+        if (nb == j) cell_j = i0 + u - 1;
+        ++nb;
+      }
+      fprev = fi;
+    }
+  }
+  if (nb != R || cell_j < 0) return false;
+  *lo = -1.0 + (double)cell_j * (2.0 / kTRootGrid2);
+  *hi = -1.0 + (double)(cell_j + 1) * (2.0 / kTRootGrid2);
+  return true;
+}
+// the deferred case of one (draw, chain, root): the finer grid first, else bisection on the Sturm count
 template <int STRIDE>
-__device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain, int root,
+__device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain, int root, int R,
                                              double* __restrict__ brk) {
+  {
+    double cr[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) cr[k] = chain ? fo[10 - k] : fo[k];
+    double lo, hi;
+    if (isolate_grid2(cr, R, root, &lo, &hi)) {
+      brk[2 * root] = lo;
+      brk[2 * root + 1] = hi;
+      return;
+    }
+  }
 #define S(i) sm[(i) * STRIDE]
 #pragma unroll 1
   for (int k = 0; k < 11; ++k) S(11 + k) = fo[k];

@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacAr
     const uint32_t item = a.fb_list[it];
     const size_t slot = item >> 5;
     const int chain = (item >> 4) & 1, root = item & 15;
-    const int R0 = a.nroot[slot] & 255;
+    const int R0 = a.nroot[slot] & 255, R1 = (a.nroot[slot] >> 8) & 255;
     geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * a.fo_stride, chain, root,
-                                                   a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
+                                                   chain ? R1 : R0, a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
   }
 }
 

@@ -326,6 +326,7 @@ static inline int sturm_count(const Sturm* st, double x) {
 }
 
 static const int kRootGrid = 32;    // sign-test cells on (-1,1]
+static const int kRootGrid2 = 256;  // second, finer grid for the chains the first one does not separate
 static const int kRootDepth = 48;   // max Sturm bisection depth per root
 static const int kRootBisect = 6;   // sign bisection steps on the isolated bracket
 static const int kRootNewton = 6;   // bracketed Newton steps that follow
@@ -368,6 +369,21 @@ static inline int roots_unit(const double* p, int n, double* roots) {
     }
   }
   const bool grid_ok = (nb == R);
+  // Second grid, 256 cells, for the ~8 % of the polynomials whose first grid shows fewer bracketing
+  // cells than roots (two roots in one cell): the same rule on x_i = -1 + i/128.  Only if that fails
+  // too (roots closer than 1/128, or a numerically multiple root) the Sturm count is bisected.
+  bool cells2[kRootGrid2];
+  int nb2 = 0;
+  if (R > 0 && !grid_ok) {
+    double fprev = horner(c0, d0, -1.0);
+    for (int i = 1; i <= kRootGrid2; ++i) {
+      const double fi = horner(c0, d0, -1.0 + (double)i * (2.0 / kRootGrid2));
+      cells2[i - 1] = (fprev < 0.0 && fi > 0.0) || (fprev > 0.0 && fi < 0.0) || fi == 0.0;
+      nb2 += cells2[i - 1] ? 1 : 0;
+      fprev = fi;
+    }
+  }
+  const bool grid2_ok = !grid_ok && (nb2 == R);
   int cell = -1;
   for (int j = 0; j < R; ++j) {
     double lo = -1.0, hi = 1.0;
@@ -375,6 +391,10 @@ static inline int roots_unit(const double* p, int n, double* roots) {
       do { ++cell; } while (!((cells >> cell) & 1u));
       lo = -1.0 + (double)cell * (2.0 / kRootGrid);
       hi = -1.0 + (double)(cell + 1) * (2.0 / kRootGrid);
+    } else if (grid2_ok) {
+      do { ++cell; } while (!cells2[cell]);
+      lo = -1.0 + (double)cell * (2.0 / kRootGrid2);
+      hi = -1.0 + (double)(cell + 1) * (2.0 / kRootGrid2);
     } else {
       int vlo = vm1, vhi = vp1, jj = j;
       for (int depth = 0; depth < kRootDepth; ++depth) {

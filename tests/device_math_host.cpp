@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #define KML_HOST_EMULATION 1
+#define __host__
 #define __device__
 #define __global__
 #define __forceinline__ inline
@@ -69,7 +70,7 @@ int dmh_mono_model(const double* f1, const double* f2, const uint16_t* sample8, 
       const int R = chain ? R1 : R0;
       for (int j = 0; j < R; ++j) {
         double iso[kIsoSlots];
-        mono_isolate_deferred_thread<1>(iso, fo, chain, j, brk + (chain ? 2 * R0 : 0));
+        mono_isolate_deferred_thread<1>(iso, fo, chain, j, R, brk + (chain ? 2 * R0 : 0));
       }
     }
   const int n = R0 + R1;

@@ -51,7 +51,7 @@ constexpr int kTRootNewton = 6;
 template <int STRIDE>
 __device__ __noinline__ double horner_s(const double* c, int deg, double x) {
   double r = c[deg * STRIDE];
-  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i * STRIDE];
+  for (int i = deg - 1; i >= 0; --i) r = kfma(r, x, c[i * STRIDE]);
   return r;
 }
 // coefficient k of a*b, strided operands
@@ -59,7 +59,7 @@ template <int STRIDE>
 __device__ __noinline__ double conv_s(const double* a, int da, const double* b, int db, int k) {
   double r = 0.0;
   const int i0 = max(0, k - db), i1 = min(da, k);
-  for (int i = i0; i <= i1; ++i) r = r + a[i * STRIDE] * b[(k - i) * STRIDE];
+  for (int i = i0; i <= i1; ++i) r = kfma(a[i * STRIDE], b[(k - i) * STRIDE], r);
   return r;
 }
 
@@ -70,7 +70,7 @@ __device__ __forceinline__ double conv_r(const double* a, const double* b, int k
   double r = 0.0;
 #pragma unroll
   for (int i = 0; i <= DA; ++i)
-    if (i >= k - DB && i <= k) r = r + a[i] * b[k - i];
+    if (i >= k - DB && i <= k) r = kfma(a[i], b[k - i], r);
   return r;
 }
 
@@ -114,13 +114,13 @@ __device__ __forceinline__ void gj_step(double* sm, bool& failed) {
     double* row = sm + r * 20 * STRIDE;
     const double f = row[C * STRIDE];
 #pragma unroll
-    for (int j = C + 1; j < 20; ++j) row[j * STRIDE] = row[j * STRIDE] - f * prow[j];
+    for (int j = C + 1; j < 20; ++j) row[j * STRIDE] = kfma(-f, prow[j], row[j * STRIDE]);
   }
 #undef S
 }
 
 // Characteristic polynomial det(lambda I - H) of the 10x10 matrix H[r][c] = S(r*20 + 10 + c)
-// (row f4; oracle/src/geom.hpp charpoly10): elimination to Hessenberg form with first-maximum
+// (row f4; contract: DESIGN.md §4.12): elimination to Hessenberg form with first-maximum
 // pivoting, then the recurrence over the leading minors, whose polynomials P[k] (k <= 9, k + 1
 // coefficients, monic) live in the dead left halves S(k*20 + 0..9).  c[0..10] ascending, c[10] = 1.
 template <int STRIDE>
@@ -143,8 +143,8 @@ __device__ __noinline__ void charpoly10_s(double* sm, double* c) {
         if (y != 0.0) {
           y = kdiv(y, x);
           H(i2, m - 1) = y;
-          for (int j = m; j < n; ++j) H(i2, j) = H(i2, j) - y * H(m, j);
-          for (int j = 0; j < n; ++j) H(j, m) = H(j, m) + y * H(j, i2);
+          for (int j = m; j < n; ++j) H(i2, j) = kfma(-y, H(m, j), H(i2, j));
+          for (int j = 0; j < n; ++j) H(j, m) = kfma(y, H(j, i2), H(j, m));
         }
       }
     }
@@ -154,13 +154,13 @@ __device__ __noinline__ void charpoly10_s(double* sm, double* c) {
     const int col = k - 1;
     const double h = H(col, col);
     // the new polynomial goes to c[] first: P(k-1, .) is still read below
-    for (int j = 0; j <= k; ++j) c[j] = (j >= 1 ? P(k - 1, j - 1) : 0.0) - (j <= k - 1 ? h * P(k - 1, j) : 0.0);
+    for (int j = 0; j <= k; ++j) c[j] = j <= k - 1 ? kfma(-h, P(k - 1, j), j >= 1 ? P(k - 1, j - 1) : 0.0) : P(k - 1, j - 1);
     double prod = 1.0;
     for (int i = 1; i <= k - 1; ++i) {
       const int row = col - i;
       prod = prod * H(row + 1, row);
       const double sc = H(row, col) * prod;
-      for (int j = 0; j <= k - 1 - i; ++j) c[j] = c[j] - sc * P(k - 1 - i, j);
+      for (int j = 0; j <= k - 1 - i; ++j) c[j] = kfma(-sc, P(k - 1 - i, j), c[j]);
     }
     if (k < n)
       for (int j = 0; j <= k; ++j) P(k, j) = c[j];
@@ -204,7 +204,7 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
     for (int k = 0; k < 5; ++k) {
       double s2 = 0.0;
 #pragma unroll
-      for (int i = k; i < 9; ++i) s2 = s2 + A[i * 5 + k] * A[i * 5 + k];
+      for (int i = k; i < 9; ++i) s2 = kfma(A[i * 5 + k], A[i * 5 + k], s2);
       const double nrm = ksqrt(s2);
       const double alpha = (A[k * 5 + k] >= 0.0) ? -nrm : nrm;
 #pragma unroll
@@ -212,17 +212,17 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
       V[k * 9 + k] = V[k * 9 + k] - alpha;
       double n2 = 0.0;
 #pragma unroll
-      for (int i = k; i < 9; ++i) n2 = n2 + V[k * 9 + i] * V[k * 9 + i];
+      for (int i = k; i < 9; ++i) n2 = kfma(V[k * 9 + i], V[k * 9 + i], n2);
       N2[k] = n2;
       if (n2 > 0.0) {
 #pragma unroll
         for (int j = k; j < 5; ++j) {
           double d = 0.0;
 #pragma unroll
-          for (int i = k; i < 9; ++i) d = d + V[k * 9 + i] * A[i * 5 + j];
+          for (int i = k; i < 9; ++i) d = kfma(V[k * 9 + i], A[i * 5 + j], d);
           const double f = kdiv(2.0 * d, n2);
 #pragma unroll
-          for (int i = k; i < 9; ++i) A[i * 5 + j] = A[i * 5 + j] - f * V[k * 9 + i];
+          for (int i = k; i < 9; ++i) A[i * 5 + j] = kfma(-f, V[k * 9 + i], A[i * 5 + j]);
         }
       }
     }
@@ -237,10 +237,10 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
         if (!(n2 > 0.0)) continue;
         double d = 0.0;
 #pragma unroll
-        for (int i = k; i < 9; ++i) d = d + V[k * 9 + i] * e[i];
+        for (int i = k; i < 9; ++i) d = kfma(V[k * 9 + i], e[i], d);
         const double f = kdiv(2.0 * d, n2);
 #pragma unroll
-        for (int i = k; i < 9; ++i) e[i] = e[i] - f * V[k * 9 + i];
+        for (int i = k; i < 9; ++i) e[i] = kfma(-f, V[k * 9 + i], e[i]);
       }
 #pragma unroll
       for (int i = 0; i < 9; ++i) B[b * 9 + i] = e[i];
@@ -351,7 +351,7 @@ template <int DEG>
 __device__ __forceinline__ double horner_r(const double* c, double x) {
   double r = c[DEG];
 #pragma unroll
-  for (int i = DEG - 1; i >= 0; --i) r = r * x + c[i];
+  for (int i = DEG - 1; i >= 0; --i) r = kfma(r, x, c[i]);
   return r;
 }
 
@@ -380,7 +380,7 @@ __device__ __noinline__ int sturm_build_s(double* sm, bool reversed, unsigned lo
       for (int i = 0; i <= da; ++i) SS(i) = SS(oa + i);  // remainder r[0..da] in scratch 0..10
       for (int d = da; d >= db; --d) {
         const double f = kdiv(SS(d), SS(ob + db));
-        for (int i = 0; i < db; ++i) SS(d - db + i) = SS(d - db + i) - f * SS(ob + i);
+        for (int i = 0; i < db; ++i) SS(d - db + i) = kfma(-f, SS(ob + i), SS(d - db + i));
         SS(d) = 0.0;
       }
       int dr = db - 1;
@@ -445,7 +445,7 @@ __device__ __noinline__ int isolate_unit_s(double* sm, unsigned long long degs, 
       const double x = -1.0 + (double)i * (2.0 / kTRootGrid);
       double r = cr[10];
 #pragma unroll
-      for (int k = 9; k >= 0; --k) r = r * x + cr[k];
+      for (int k = 9; k >= 0; --k) r = kfma(r, x, cr[k]);
       neg |= (unsigned long long)(r < 0.0) << i;
       pos |= (unsigned long long)(r > 0.0) << i;
       zer |= (unsigned long long)(r == 0.0) << i;
@@ -506,12 +506,12 @@ __device__ __forceinline__ bool sturm_step(const double* pa, const double* pb, d
   {
     const double f = kdiv(r[DB + 1], pb[DB]);
 #pragma unroll
-    for (int i = 0; i < DB; ++i) r[1 + i] = r[1 + i] - f * pb[i];
+    for (int i = 0; i < DB; ++i) r[1 + i] = kfma(-f, pb[i], r[1 + i]);
   }
   {
     const double f = kdiv(r[DB], pb[DB]);
 #pragma unroll
-    for (int i = 0; i < DB; ++i) r[i] = r[i] - f * pb[i];
+    for (int i = 0; i < DB; ++i) r[i] = kfma(-f, pb[i], r[i]);
   }
   if (r[DB - 1] == 0.0) return false;  // the degree drops by more than one
   const double sc = fabs(r[DB - 1]);
@@ -717,7 +717,7 @@ __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, 
   bool ok = true;
 #pragma unroll 1
   for (int e = 0; e < 9; ++e) {
-    const double v = ((x * fo[34 + e] + y * fo[34 + 9 + e]) + z * fo[34 + 18 + e]) + fo[34 + 27 + e];
+    const double v = kfma(z, fo[34 + 18 + e], kfma(y, fo[34 + 9 + e], kfma(x, fo[34 + e], fo[34 + 27 + e])));
     if (!isfinite(v)) ok = false;
     E[e] = v;
   }
@@ -727,7 +727,7 @@ __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, 
 // STEWENIUS (row f4): E from the eigenvalue x of the action matrix whose six non-trivial rows are
 // fo[kStewRowsOff + 10 j + k]: the eigenvector v = [x2, xy, xz, v3, v4, v5, x, y, z, 1] solves
 // rows 0..5 of (M - x I) v = 0, six equations in (v3, v4, v5, y, z), Gaussian elimination with
-// first-maximum row pivoting (oracle/src/geom.hpp stewenius_yz); then E = ((x X + y Y) + z Z) + W.
+// first-maximum row pivoting (contract: DESIGN.md §4.12); then E = ((x X + y Y) + z Z) + W.
 __device__ __noinline__ bool essential_from_root_stew(const double* __restrict__ fo, double x, double* E) {
   const double x2 = x * x;
   double C[6][5], d[6];
@@ -735,11 +735,11 @@ __device__ __noinline__ bool essential_from_root_stew(const double* __restrict__
   for (int j = 0; j < 6; ++j) {
     const double* a = fo + kStewRowsOff + 10 * j;
     C[j][0] = a[3]; C[j][1] = a[4]; C[j][2] = a[5];
-    C[j][3] = a[1] * x + a[7];
-    C[j][4] = a[2] * x + a[8];
-    d[j] = -((a[0] * x2 + a[6] * x) + a[9]);
+    C[j][3] = kfma(a[1], x, a[7]);
+    C[j][4] = kfma(a[2], x, a[8]);
+    d[j] = -kfma(a[0], x2, kfma(a[6], x, a[9]));
   }
-  d[0] = d[0] + x * x2;
+  d[0] = kfma(x, x2, d[0]);
   C[1][3] = C[1][3] - x2;
   C[2][4] = C[2][4] - x2;
   C[3][0] = C[3][0] - x;
@@ -767,8 +767,8 @@ __device__ __noinline__ bool essential_from_root_stew(const double* __restrict__
     for (int r = c + 1; r < 6; ++r) {
       const double f = kdiv(C[r][c], C[c][c]);
 #pragma unroll
-      for (int j = c + 1; j < 5; ++j) C[r][j] = C[r][j] - f * C[c][j];
-      d[r] = d[r] - f * d[c];
+      for (int j = c + 1; j < 5; ++j) C[r][j] = kfma(-f, C[c][j], C[r][j]);
+      d[r] = kfma(-f, d[c], d[r]);
     }
   }
   double u[5];
@@ -776,14 +776,14 @@ __device__ __noinline__ bool essential_from_root_stew(const double* __restrict__
   for (int c = 4; c >= 0; --c) {
     double sacc = d[c];
 #pragma unroll
-    for (int j = c + 1; j < 5; ++j) sacc = sacc - C[c][j] * u[j];
+    for (int j = c + 1; j < 5; ++j) sacc = kfma(-C[c][j], u[j], sacc);
     u[c] = kdiv(sacc, C[c][c]);
   }
   const double y = u[3], z = u[4];
   bool ok = true;
 #pragma unroll 1
   for (int e = 0; e < 9; ++e) {
-    const double v = ((x * fo[34 + e] + y * fo[34 + 9 + e]) + z * fo[34 + 18 + e]) + fo[34 + 27 + e];
+    const double v = kfma(z, fo[34 + 18 + e], kfma(y, fo[34 + 9 + e], kfma(x, fo[34 + e], fo[34 + 27 + e])));
     if (!isfinite(v)) ok = false;
     E[e] = v;
   }
@@ -800,8 +800,8 @@ __device__ __forceinline__ void essential_candidates(const double* E, double* Ra
     for (int c = 0; c < 3; ++c) {
       const double a0 = U[3 * r + 0], a1 = U[3 * r + 1], a2 = U[3 * r + 2];
       const double b0 = V[3 * c + 0], b1 = V[3 * c + 1], b2 = V[3 * c + 2];
-      Ra[3 * r + c] = (a1 * b0 - a0 * b1) + a2 * b2;
-      Rb[3 * r + c] = (a0 * b1 - a1 * b0) + a2 * b2;
+      Ra[3 * r + c] = kfma(a2, b2, kfma(a1, b0, -(a0 * b1)));
+      Rb[3 * r + c] = kfma(a2, b2, kfma(a0, b1, -(a1 * b0)));
     }
   tt[0] = Sv[0] * U[2];
   tt[1] = Sv[0] * U[5];
@@ -827,22 +827,22 @@ __device__ __forceinline__ void candidate_model(const double* Ra, const double* 
 __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, const V3& t, const double* tinv,
                                                    const V3& f1, const V3& f2, double* r_pos, double* r_neg) {
   V3 f2u;
-  f2u.x = (R[0] * f2.x + R[1] * f2.y) + R[2] * f2.z;
-  f2u.y = (R[3] * f2.x + R[4] * f2.y) + R[5] * f2.z;
-  f2u.z = (R[6] * f2.x + R[7] * f2.y) + R[8] * f2.z;
+  f2u.x = kfma(R[2], f2.z, kfma(R[1], f2.y, R[0] * f2.x));
+  f2u.y = kfma(R[5], f2.z, kfma(R[4], f2.y, R[3] * f2.x));
+  f2u.z = kfma(R[8], f2.z, kfma(R[7], f2.y, R[6] * f2.x));
   const double b0 = dot(t, f1), b1 = dot(t, f2u);
   const double d12 = dot(f1, f2u);
   const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
-  const double det = A00 * A11 - A01 * A10;
-  const double l0 = (A11 * b0 - A01 * b1) / det;
-  const double l1 = (A00 * b1 - A10 * b0) / det;
+  const double det = kfma(A00, A11, -(A01 * A10));
+  const double l0 = kfma(A11, b0, -(A01 * b1)) / det;
+  const double l1 = kfma(A00, b1, -(A10 * b0)) / det;
   V3 p, q;
-  p.x = 0.5 * (l0 * f1.x + (t.x + l1 * f2u.x));
-  p.y = 0.5 * (l0 * f1.y + (t.y + l1 * f2u.y));
-  p.z = 0.5 * (l0 * f1.z + (t.z + l1 * f2u.z));
-  q.x = ((R[0] * p.x + R[3] * p.y) + R[6] * p.z) + tinv[0];
-  q.y = ((R[1] * p.x + R[4] * p.y) + R[7] * p.z) + tinv[1];
-  q.z = ((R[2] * p.x + R[5] * p.y) + R[8] * p.z) + tinv[2];
+  p.x = 0.5 * kfma(l0, f1.x, kfma(l1, f2u.x, t.x));
+  p.y = 0.5 * kfma(l0, f1.y, kfma(l1, f2u.y, t.y));
+  p.z = 0.5 * kfma(l0, f1.z, kfma(l1, f2u.z, t.z));
+  q.x = kfma(R[6], p.z, kfma(R[3], p.y, kfma(R[0], p.x, tinv[0])));
+  q.y = kfma(R[7], p.z, kfma(R[4], p.y, kfma(R[1], p.x, tinv[1])));
+  q.z = kfma(R[8], p.z, kfma(R[5], p.y, kfma(R[2], p.x, tinv[2])));
   const double np = sqrt(dot(p, p)), nq = sqrt(dot(q, q));
   const double x1 = dot(f1, p) / np;
   const double x2 = dot(f2, q) / nq;
@@ -867,8 +867,8 @@ __device__ __forceinline__ int mono_item(const double* __restrict__ fo, int chai
   double ta[3], tb[3];  // -R^T t of the +t candidates (mono_tinv)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    ta[c] = -((Ra[c] * tt[0] + Ra[3 + c] * tt[1]) + Ra[6 + c] * tt[2]);
-    tb[c] = -((Rb[c] * tt[0] + Rb[3 + c] * tt[1]) + Rb[6 + c] * tt[2]);
+    ta[c] = -kfma(Ra[6 + c], tt[2], kfma(Ra[3 + c], tt[1], Ra[c] * tt[0]));
+    tb[c] = -kfma(Rb[6 + c], tt[2], kfma(Rb[3 + c], tt[1], Rb[c] * tt[0]));
   }
   double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
 #pragma unroll 1

@@ -7,8 +7,9 @@
 //     SURVEY.md A.8; /root/reference/images/kimera-multi.drawio:2595-2598, 2654),
 //   - triangulate2 + bearing reprojection residual of
 //     CentralRelativePoseSacProblem (drawio:2589-2592, 2646).
-// Compiled with -fmad=false: every multiply and add below is rounded on its
-// own, exactly as written.  fp64 div and sqrt are IEEE on sm_100a.
+// Compiled with -fmad=false: the compiler contracts nothing; the fused multiply-adds of the
+// contract are the explicit kfma() calls (the oracle writes fma() at the same places), every
+// other multiply and add is rounded on its own.  fp64 div and sqrt are IEEE on sm_100a.
 // Division, square root and the larger routines are deliberately NOT inlined:
 // the mono kernel runs 16 warps per SM in different phases of a long program,
 // so its instruction footprint must stay inside the SM's instruction cache
@@ -26,46 +27,47 @@ namespace geom {
 #ifdef KML_FILTER_STATS
 __device__ unsigned long long g_fstats[12];
 #endif
+KML_DI double kfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 KML_DN double kdiv(double a, double b) { return a / b; }
 KML_DN double ksqrt(double a) { return sqrt(a); }
 
 struct V3 {
   double x, y, z;
 };
-KML_DI double dot(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+KML_DI double dot(const V3& a, const V3& b) { return kfma(a.z, b.z, kfma(a.y, b.y, a.x * b.x)); }
 KML_DI V3 cross(const V3& a, const V3& b) {
   V3 c;
-  c.x = a.y * b.z - a.z * b.y;
-  c.y = a.z * b.x - a.x * b.z;
-  c.z = a.x * b.y - a.y * b.x;
+  c.x = kfma(a.y, b.z, -(a.z * b.y));
+  c.y = kfma(a.z, b.x, -(a.x * b.z));
+  c.z = kfma(a.x, b.y, -(a.y * b.x));
   return c;
 }
 
 // polynomial value, ascending coefficients
 KML_DN double horner(const double* c, int deg, double x) {
   double r = c[deg];
-  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i];
+  for (int i = deg - 1; i >= 0; --i) r = kfma(r, x, c[i]);
   return r;
 }
 
 // One Hestenes rotation on columns (p,q) of G (3x3 row-major), accumulated in W.
 KML_DN bool jacobi_pair(double* G, double* W, int p, int q) {
-  const double a = (G[p] * G[p] + G[3 + p] * G[3 + p]) + G[6 + p] * G[6 + p];
-  const double b = (G[q] * G[q] + G[3 + q] * G[3 + q]) + G[6 + q] * G[6 + q];
-  const double g = (G[p] * G[q] + G[3 + p] * G[3 + q]) + G[6 + p] * G[6 + q];
+  const double a = kfma(G[6 + p], G[6 + p], kfma(G[3 + p], G[3 + p], G[p] * G[p]));
+  const double b = kfma(G[6 + q], G[6 + q], kfma(G[3 + q], G[3 + q], G[q] * G[q]));
+  const double g = kfma(G[6 + p], G[6 + q], kfma(G[3 + p], G[3 + q], G[p] * G[q]));
   if (g * g <= 1e-30 * a * b) return false;
   const double zeta = kdiv(b - a, 2.0 * g);
-  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(1.0 + zeta * zeta));
-  const double c = kdiv(1.0, ksqrt(1.0 + t * t));
+  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(kfma(zeta, zeta, 1.0)));
+  const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
   const double s = c * t;
 #pragma unroll 1
   for (int i = 0; i < 3; ++i) {
     const double gp = G[3 * i + p], gq = G[3 * i + q];
-    G[3 * i + p] = c * gp - s * gq;
-    G[3 * i + q] = s * gp + c * gq;
+    G[3 * i + p] = kfma(c, gp, -(s * gq));
+    G[3 * i + q] = kfma(s, gp, c * gq);
     const double wp = W[3 * i + p], wq = W[3 * i + q];
-    W[3 * i + p] = c * wp - s * wq;
-    W[3 * i + q] = s * wp + c * wq;
+    W[3 * i + p] = kfma(c, wp, -(s * wq));
+    W[3 * i + q] = kfma(s, wp, c * wq);
   }
   return true;
 }
@@ -89,7 +91,7 @@ KML_DN void svd3(const double* A, double* U, double* S, double* V) {
   }
   double n[3];
 #pragma unroll 1
-  for (int j = 0; j < 3; ++j) n[j] = ksqrt((G[j] * G[j] + G[3 + j] * G[3 + j]) + G[6 + j] * G[6 + j]);
+  for (int j = 0; j < 3; ++j) n[j] = ksqrt(kfma(G[6 + j], G[6 + j], kfma(G[3 + j], G[3 + j], G[j] * G[j])));
   // stable descending order of the three column norms
   int i0 = 0, i1 = 1, i2 = 2;
   if (n[i1] > n[i0]) { const int t = i0; i0 = i1; i1 = t; }
@@ -129,22 +131,22 @@ KML_DN void svd3(const double* A, double* U, double* S, double* V) {
 // order as svd3 above; column pairs are template parameters so G and W never leave registers).
 template <int P, int Q>
 KML_DI bool jacobi_pair_r(double (&G)[9], double (&W)[9]) {
-  const double a = (G[P] * G[P] + G[3 + P] * G[3 + P]) + G[6 + P] * G[6 + P];
-  const double b = (G[Q] * G[Q] + G[3 + Q] * G[3 + Q]) + G[6 + Q] * G[6 + Q];
-  const double g = (G[P] * G[Q] + G[3 + P] * G[3 + Q]) + G[6 + P] * G[6 + Q];
+  const double a = kfma(G[6 + P], G[6 + P], kfma(G[3 + P], G[3 + P], G[P] * G[P]));
+  const double b = kfma(G[6 + Q], G[6 + Q], kfma(G[3 + Q], G[3 + Q], G[Q] * G[Q]));
+  const double g = kfma(G[6 + P], G[6 + Q], kfma(G[3 + P], G[3 + Q], G[P] * G[Q]));
   if (g * g <= 1e-30 * a * b) return false;
   const double zeta = kdiv(b - a, 2.0 * g);
-  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(1.0 + zeta * zeta));
-  const double c = kdiv(1.0, ksqrt(1.0 + t * t));
+  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(kfma(zeta, zeta, 1.0)));
+  const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
   const double s = c * t;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double gp = G[3 * i + P], gq = G[3 * i + Q];
-    G[3 * i + P] = c * gp - s * gq;
-    G[3 * i + Q] = s * gp + c * gq;
+    G[3 * i + P] = kfma(c, gp, -(s * gq));
+    G[3 * i + Q] = kfma(s, gp, c * gq);
     const double wp = W[3 * i + P], wq = W[3 * i + Q];
-    W[3 * i + P] = c * wp - s * wq;
-    W[3 * i + Q] = s * wp + c * wq;
+    W[3 * i + P] = kfma(c, wp, -(s * wq));
+    W[3 * i + Q] = kfma(s, wp, c * wq);
   }
   return true;
 }
@@ -171,7 +173,7 @@ KML_DI void svd3_r(const double* A, double* U, double* S, double* V) {
   }
   double n[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) n[j] = ksqrt((G[j] * G[j] + G[3 + j] * G[3 + j]) + G[6 + j] * G[6 + j]);
+  for (int j = 0; j < 3; ++j) n[j] = ksqrt(kfma(G[6 + j], G[6 + j], kfma(G[3 + j], G[3 + j], G[j] * G[j])));
   // stable descending order of the three column norms
   int i0 = 0, i1 = 1, i2 = 2;
   double n0 = n[0], n1 = n[1], n2 = n[2];
@@ -236,7 +238,7 @@ KML_DN void arun3(const double* a1, const double* b1, const double* c1, const do
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + d2[r] * d1[c];
+      for (int c = 0; c < 3; ++c) H[3 * r + c] = kfma(d2[r], d1[c], H[3 * r + c]);
   }
   double U[9], S[3], V[9];
   svd3_r(H, U, S, V);
@@ -244,50 +246,49 @@ KML_DN void arun3(const double* a1, const double* b1, const double* c1, const do
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      M[4 * r + c] = (V[3 * r + 0] * U[3 * c + 0] + V[3 * r + 1] * U[3 * c + 1]) +
-                     V[3 * r + 2] * U[3 * c + 2];
+      M[4 * r + c] = kfma(V[3 * r + 2], U[3 * c + 2], kfma(V[3 * r + 1], U[3 * c + 1], V[3 * r + 0] * U[3 * c + 0]));
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const double rc = (M[4 * r + 0] * m2[0] + M[4 * r + 1] * m2[1]) + M[4 * r + 2] * m2[2];
+    const double rc = kfma(M[4 * r + 2], m2[2], kfma(M[4 * r + 1], m2[1], M[4 * r + 0] * m2[0]));
     M[4 * r + 3] = m1[r] - rc;
   }
 }
 
 KML_DI double arun_sqdist(const double* M, double p1x, double p1y, double p1z, double p2x,
                           double p2y, double p2z) {
-  const double x = ((M[0] * p2x + M[1] * p2y) + M[2] * p2z) + M[3];
-  const double y = ((M[4] * p2x + M[5] * p2y) + M[6] * p2z) + M[7];
-  const double z = ((M[8] * p2x + M[9] * p2y) + M[10] * p2z) + M[11];
+  const double x = kfma(M[2], p2z, kfma(M[1], p2y, kfma(M[0], p2x, M[3])));
+  const double y = kfma(M[6], p2z, kfma(M[5], p2y, kfma(M[4], p2x, M[7])));
+  const double z = kfma(M[10], p2z, kfma(M[9], p2y, kfma(M[8], p2x, M[11])));
   const double ex = p1x - x, ey = p1y - y, ez = p1z - z;
-  return (ex * ex + ey * ey) + ez * ez;
+  return kfma(ez, ez, kfma(ey, ey, ex * ex));
 }
 
 // ------------------------------------------------------- mono residual
 // (1 - f1.p^) + (1 - f2.q^), p = triangulate2(f1, f2 | R12, t12), q = R^T p - R^T t
 KML_DI void mono_tinv(const double* M, double* tinv) {
-  tinv[0] = -((M[0] * M[3] + M[4] * M[7]) + M[8] * M[11]);
-  tinv[1] = -((M[1] * M[3] + M[5] * M[7]) + M[9] * M[11]);
-  tinv[2] = -((M[2] * M[3] + M[6] * M[7]) + M[10] * M[11]);
+  tinv[0] = -kfma(M[8], M[11], kfma(M[4], M[7], M[0] * M[3]));
+  tinv[1] = -kfma(M[9], M[11], kfma(M[5], M[7], M[1] * M[3]));
+  tinv[2] = -kfma(M[10], M[11], kfma(M[6], M[7], M[2] * M[3]));
 }
 KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, const V3& f2) {
   const V3 t = {M[3], M[7], M[11]};
   V3 f2u;
-  f2u.x = (M[0] * f2.x + M[1] * f2.y) + M[2] * f2.z;
-  f2u.y = (M[4] * f2.x + M[5] * f2.y) + M[6] * f2.z;
-  f2u.z = (M[8] * f2.x + M[9] * f2.y) + M[10] * f2.z;
+  f2u.x = kfma(M[2], f2.z, kfma(M[1], f2.y, M[0] * f2.x));
+  f2u.y = kfma(M[6], f2.z, kfma(M[5], f2.y, M[4] * f2.x));
+  f2u.z = kfma(M[10], f2.z, kfma(M[9], f2.y, M[8] * f2.x));
   const double b0 = dot(t, f1), b1 = dot(t, f2u);
   const double d12 = dot(f1, f2u);
   const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
-  const double det = A00 * A11 - A01 * A10;
-  const double l0 = kdiv(A11 * b0 - A01 * b1, det);
-  const double l1 = kdiv(A00 * b1 - A10 * b0, det);
+  const double det = kfma(A00, A11, -(A01 * A10));
+  const double l0 = kdiv(kfma(A11, b0, -(A01 * b1)), det);
+  const double l1 = kdiv(kfma(A00, b1, -(A10 * b0)), det);
   V3 p, q;
-  p.x = 0.5 * (l0 * f1.x + (t.x + l1 * f2u.x));
-  p.y = 0.5 * (l0 * f1.y + (t.y + l1 * f2u.y));
-  p.z = 0.5 * (l0 * f1.z + (t.z + l1 * f2u.z));
-  q.x = ((M[0] * p.x + M[4] * p.y) + M[8] * p.z) + tinv[0];
-  q.y = ((M[1] * p.x + M[5] * p.y) + M[9] * p.z) + tinv[1];
-  q.z = ((M[2] * p.x + M[6] * p.y) + M[10] * p.z) + tinv[2];
+  p.x = 0.5 * kfma(l0, f1.x, kfma(l1, f2u.x, t.x));
+  p.y = 0.5 * kfma(l0, f1.y, kfma(l1, f2u.y, t.y));
+  p.z = 0.5 * kfma(l0, f1.z, kfma(l1, f2u.z, t.z));
+  q.x = kfma(M[8], p.z, kfma(M[4], p.y, kfma(M[0], p.x, tinv[0])));
+  q.y = kfma(M[9], p.z, kfma(M[5], p.y, kfma(M[1], p.x, tinv[1])));
+  q.z = kfma(M[10], p.z, kfma(M[6], p.y, kfma(M[2], p.x, tinv[2])));
   const double np = ksqrt(dot(p, p)), nq = ksqrt(dot(q, q));
   const double e1 = 1.0 - kdiv(dot(f1, p), np);
   const double e2 = 1.0 - kdiv(dot(f2, q), nq);

@@ -10,7 +10,8 @@
 //        (opengv/src/point_cloud/methods.cpp, PointCloudSacProblem.cpp)
 // The ARITHMETIC CONTRACT (operation order, fixed sweep counts, tie rules) is
 // written out in DESIGN.md §4; the CUDA kernels implement the same contract
-// independently.  Compile with -ffp-contract=off.
+// independently.  Compile with -ffp-contract=off: the fused multiply-adds of the contract are the
+// explicit kfma() calls, nothing else is contracted.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -18,14 +19,18 @@
 
 namespace kmo {
 
+// The contract's fused multiply-add: a*b + c rounded once.  Written out wherever the contract fuses
+// (never left to the compiler: -ffp-contract=off); the CUDA kernels write __fma_rn at the same places.
+static inline double kfma(double a, double b, double c) { return __builtin_fma(a, b, c); }
+
 // ---------------------------------------------------------------- 3-vectors
 static inline double dot3(const double* a, const double* b) {
-  return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+  return kfma(a[2], b[2], kfma(a[1], b[1], a[0] * b[0]));
 }
 static inline void cross3(const double* a, const double* b, double* c) {
-  c[0] = a[1] * b[2] - a[2] * b[1];
-  c[1] = a[2] * b[0] - a[0] * b[2];
-  c[2] = a[0] * b[1] - a[1] * b[0];
+  c[0] = kfma(a[1], b[2], -(a[2] * b[1]));
+  c[1] = kfma(a[2], b[0], -(a[0] * b[2]));
+  c[2] = kfma(a[0], b[1], -(a[1] * b[0]));
 }
 // y = M x (M row-major 3x3)
 static inline void matvec3(const double* M, const double* x, double* y) {
@@ -55,29 +60,29 @@ static inline void svd3(const double* A, double* U, double* S, double* V) {
     bool rotated = false;
     for (int k = 0; k < 3; ++k) {
       const int p = P[k], q = Q[k];
-      double a = (G[p] * G[p] + G[3 + p] * G[3 + p]) + G[6 + p] * G[6 + p];
-      double b = (G[q] * G[q] + G[3 + q] * G[3 + q]) + G[6 + q] * G[6 + q];
-      double g = (G[p] * G[q] + G[3 + p] * G[3 + q]) + G[6 + p] * G[6 + q];
+      double a = kfma(G[6 + p], G[6 + p], kfma(G[3 + p], G[3 + p], G[p] * G[p]));
+      double b = kfma(G[6 + q], G[6 + q], kfma(G[3 + q], G[3 + q], G[q] * G[q]));
+      double g = kfma(G[6 + p], G[6 + q], kfma(G[3 + p], G[3 + q], G[p] * G[q]));
       if (g * g <= 1e-30 * a * b) continue;
       rotated = true;
       double zeta = (b - a) / (2.0 * g);
-      double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-      double c = 1.0 / std::sqrt(1.0 + t * t);
+      double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(kfma(zeta, zeta, 1.0)));
+      double c = 1.0 / std::sqrt(kfma(t, t, 1.0));
       double s = c * t;
       for (int i = 0; i < 3; ++i) {
         double gp = G[3 * i + p], gq = G[3 * i + q];
-        G[3 * i + p] = c * gp - s * gq;
-        G[3 * i + q] = s * gp + c * gq;
+        G[3 * i + p] = kfma(c, gp, -(s * gq));
+        G[3 * i + q] = kfma(s, gp, c * gq);
         double wp = W[3 * i + p], wq = W[3 * i + q];
-        W[3 * i + p] = c * wp - s * wq;
-        W[3 * i + q] = s * wp + c * wq;
+        W[3 * i + p] = kfma(c, wp, -(s * wq));
+        W[3 * i + q] = kfma(s, wp, c * wq);
       }
     }
     if (!rotated) break;
   }
   double n[3];
   for (int j = 0; j < 3; ++j)
-    n[j] = std::sqrt((G[j] * G[j] + G[3 + j] * G[3 + j]) + G[6 + j] * G[6 + j]);
+    n[j] = std::sqrt(kfma(G[6 + j], G[6 + j], kfma(G[3 + j], G[3 + j], G[j] * G[j])));
   // stable descending order of the three column norms
   int i0 = 0, i1 = 1, i2 = 2;
   if (n[i1] > n[i0]) { int t = i0; i0 = i1; i1 = t; }
@@ -130,7 +135,7 @@ static inline void arun3(const double* a1, const double* b1, const double* c1,
     double d1[3], d2[3];
     for (int i = 0; i < 3; ++i) { d1[i] = P1[k][i] - m1[i]; d2[i] = P2[k][i] - m2[i]; }
     for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + d2[r] * d1[c];
+      for (int c = 0; c < 3; ++c) H[3 * r + c] = kfma(d2[r], d1[c], H[3 * r + c]);
   }
   double U[9], S[3], V[9];
   svd3(H, U, S, V);
@@ -138,21 +143,20 @@ static inline void arun3(const double* a1, const double* b1, const double* c1,
   double* R = model;  // write into strided 3x4
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c)
-      R[4 * r + c] = (V[3 * r + 0] * U[3 * c + 0] + V[3 * r + 1] * U[3 * c + 1]) +
-                     V[3 * r + 2] * U[3 * c + 2];
+      R[4 * r + c] = kfma(V[3 * r + 2], U[3 * c + 2], kfma(V[3 * r + 1], U[3 * c + 1], V[3 * r + 0] * U[3 * c + 0]));
   for (int r = 0; r < 3; ++r) {
-    double rc = (R[4 * r + 0] * m2[0] + R[4 * r + 1] * m2[1]) + R[4 * r + 2] * m2[2];
+    double rc = kfma(R[4 * r + 2], m2[2], kfma(R[4 * r + 1], m2[1], R[4 * r + 0] * m2[0]));
     model[4 * r + 3] = m1[r] - rc;
   }
 }
 
 // squared 3-D residual |p1 - (R p2 + t)|^2 with the contract's op order
 static inline double arun_sqdist(const double* M, const double* p1, const double* p2) {
-  double x = ((M[0] * p2[0] + M[1] * p2[1]) + M[2] * p2[2]) + M[3];
-  double y = ((M[4] * p2[0] + M[5] * p2[1]) + M[6] * p2[2]) + M[7];
-  double z = ((M[8] * p2[0] + M[9] * p2[1]) + M[10] * p2[2]) + M[11];
+  double x = kfma(M[2], p2[2], kfma(M[1], p2[1], kfma(M[0], p2[0], M[3])));
+  double y = kfma(M[6], p2[2], kfma(M[5], p2[1], kfma(M[4], p2[0], M[7])));
+  double z = kfma(M[10], p2[2], kfma(M[9], p2[1], kfma(M[8], p2[0], M[11])));
   double ex = p1[0] - x, ey = p1[1] - y, ez = p1[2] - z;
-  return (ex * ex + ey * ey) + ez * ez;
+  return kfma(ez, ez, kfma(ey, ey, ex * ex));
 }
 
 // ---------------------------------------------------------- mono residual
@@ -161,28 +165,28 @@ static inline double arun_sqdist(const double* M, const double* p1, const double
 // M = [R12 | t12] row-major 3x4; tinv = -(R^T t) is passed precomputed.
 static inline void mono_tinv(const double* M, double* tinv) {
   double t[3] = {M[3], M[7], M[11]};
-  tinv[0] = -((M[0] * t[0] + M[4] * t[1]) + M[8] * t[2]);
-  tinv[1] = -((M[1] * t[0] + M[5] * t[1]) + M[9] * t[2]);
-  tinv[2] = -((M[2] * t[0] + M[6] * t[1]) + M[10] * t[2]);
+  tinv[0] = -kfma(M[8], t[2], kfma(M[4], t[1], M[0] * t[0]));
+  tinv[1] = -kfma(M[9], t[2], kfma(M[5], t[1], M[1] * t[0]));
+  tinv[2] = -kfma(M[10], t[2], kfma(M[6], t[1], M[2] * t[0]));
 }
 static inline double mono_residual(const double* M, const double* tinv,
                                    const double* f1, const double* f2) {
   const double t[3] = {M[3], M[7], M[11]};
   double f2u[3];
-  f2u[0] = (M[0] * f2[0] + M[1] * f2[1]) + M[2] * f2[2];
-  f2u[1] = (M[4] * f2[0] + M[5] * f2[1]) + M[6] * f2[2];
-  f2u[2] = (M[8] * f2[0] + M[9] * f2[1]) + M[10] * f2[2];
+  f2u[0] = kfma(M[2], f2[2], kfma(M[1], f2[1], M[0] * f2[0]));
+  f2u[1] = kfma(M[6], f2[2], kfma(M[5], f2[1], M[4] * f2[0]));
+  f2u[2] = kfma(M[10], f2[2], kfma(M[9], f2[1], M[8] * f2[0]));
   double b0 = dot3(t, f1), b1 = dot3(t, f2u);
   double d12 = dot3(f1, f2u);
   double A00 = dot3(f1, f1), A01 = -d12, A10 = d12, A11 = -dot3(f2u, f2u);
-  double det = A00 * A11 - A01 * A10;
-  double l0 = (A11 * b0 - A01 * b1) / det;
-  double l1 = (A00 * b1 - A10 * b0) / det;
+  double det = kfma(A00, A11, -(A01 * A10));
+  double l0 = kfma(A11, b0, -(A01 * b1)) / det;
+  double l1 = kfma(A00, b1, -(A10 * b0)) / det;
   double p[3], q[3];
-  for (int i = 0; i < 3; ++i) p[i] = 0.5 * (l0 * f1[i] + (t[i] + l1 * f2u[i]));
-  q[0] = ((M[0] * p[0] + M[4] * p[1]) + M[8] * p[2]) + tinv[0];
-  q[1] = ((M[1] * p[0] + M[5] * p[1]) + M[9] * p[2]) + tinv[1];
-  q[2] = ((M[2] * p[0] + M[6] * p[1]) + M[10] * p[2]) + tinv[2];
+  for (int i = 0; i < 3; ++i) p[i] = 0.5 * kfma(l0, f1[i], kfma(l1, f2u[i], t[i]));
+  q[0] = kfma(M[8], p[2], kfma(M[4], p[1], kfma(M[0], p[0], tinv[0])));
+  q[1] = kfma(M[9], p[2], kfma(M[5], p[1], kfma(M[1], p[0], tinv[1])));
+  q[2] = kfma(M[10], p[2], kfma(M[6], p[1], kfma(M[2], p[0], tinv[2])));
   double np = std::sqrt(dot3(p, p)), nq = std::sqrt(dot3(q, q));
   double e1 = 1.0 - dot3(f1, p) / np;
   double e2 = 1.0 - dot3(f2, q) / nq;
@@ -212,12 +216,12 @@ static const int M23[10][4] = {
 static inline void pmul11(const double* a, const double* b, double* out) {
   for (int k = 0; k < 10; ++k) out[k] = 0.0;
   for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) out[M12[i][j]] = out[M12[i][j]] + a[i] * b[j];
+    for (int j = 0; j < 4; ++j) out[M12[i][j]] = kfma(a[i], b[j], out[M12[i][j]]);
 }
 // out(deg3) += a(deg2)*b(deg1)
 static inline void pmul21_acc(const double* a, const double* b, double* out) {
   for (int i = 0; i < 10; ++i)
-    for (int j = 0; j < 4; ++j) out[M23[i][j]] = out[M23[i][j]] + a[i] * b[j];
+    for (int j = 0; j < 4; ++j) out[M23[i][j]] = kfma(a[i], b[j], out[M23[i][j]]);
 }
 
 // Null space of the 5x9 epipolar system by Householder QR of its transpose:
@@ -230,20 +234,20 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
   double vn2[5];
   for (int k = 0; k < 5; ++k) {
     double s2 = 0.0;
-    for (int i = k; i < 9; ++i) s2 = s2 + A[i][k] * A[i][k];
+    for (int i = k; i < 9; ++i) s2 = kfma(A[i][k], A[i][k], s2);
     double nrm = std::sqrt(s2);
     double alpha = (A[k][k] >= 0.0) ? -nrm : nrm;
     for (int i = 0; i < 9; ++i) v[k][i] = (i < k) ? 0.0 : A[i][k];
     v[k][k] = v[k][k] - alpha;
     double n2 = 0.0;
-    for (int i = k; i < 9; ++i) n2 = n2 + v[k][i] * v[k][i];
+    for (int i = k; i < 9; ++i) n2 = kfma(v[k][i], v[k][i], n2);
     vn2[k] = n2;
     if (n2 > 0.0) {
       for (int j = k; j < 5; ++j) {
         double d = 0.0;
-        for (int i = k; i < 9; ++i) d = d + v[k][i] * A[i][j];
+        for (int i = k; i < 9; ++i) d = kfma(v[k][i], A[i][j], d);
         double f = (2.0 * d) / n2;
-        for (int i = k; i < 9; ++i) A[i][j] = A[i][j] - f * v[k][i];
+        for (int i = k; i < 9; ++i) A[i][j] = kfma(-f, v[k][i], A[i][j]);
       }
     }
   }
@@ -253,9 +257,9 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
     for (int k = 4; k >= 0; --k) {
       if (!(vn2[k] > 0.0)) continue;
       double d = 0.0;
-      for (int i = k; i < 9; ++i) d = d + v[k][i] * x[i];
+      for (int i = k; i < 9; ++i) d = kfma(v[k][i], x[i], d);
       double f = (2.0 * d) / vn2[k];
-      for (int i = k; i < 9; ++i) x[i] = x[i] - f * v[k][i];
+      for (int i = k; i < 9; ++i) x[i] = kfma(-f, v[k][i], x[i]);
     }
     for (int i = 0; i < 9; ++i) basis[b][i] = x[i];
   }
@@ -264,14 +268,14 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
 // ---- univariate polynomials, coefficients ascending (c[0] + c[1] z + ...)
 static inline double horner(const double* c, int deg, double x) {
   double r = c[deg];
-  for (int i = deg - 1; i >= 0; --i) r = r * x + c[i];
+  for (int i = deg - 1; i >= 0; --i) r = kfma(r, x, c[i]);
   return r;
 }
 // out = a*b  (degrees da, db), accumulation in (i,j) loop order
 static inline void upmul(const double* a, int da, const double* b, int db, double* out) {
   for (int k = 0; k <= da + db; ++k) out[k] = 0.0;
   for (int i = 0; i <= da; ++i)
-    for (int j = 0; j <= db; ++j) out[i + j] = out[i + j] + a[i] * b[j];
+    for (int j = 0; j <= db; ++j) out[i + j] = kfma(a[i], b[j], out[i + j]);
 }
 
 // Sturm chain of a degree-10 polynomial.  chain[k] has degree deg[k];
@@ -299,7 +303,7 @@ static inline void sturm_build(const double* p, int n, Sturm* st) {
     for (int i = 0; i <= da; ++i) r[i] = a[i];
     for (int d = da; d >= db; --d) {
       double f = r[d] / b[db];
-      for (int i = 0; i < db; ++i) r[d - db + i] = r[d - db + i] - f * b[i];
+      for (int i = 0; i < db; ++i) r[d - db + i] = kfma(-f, b[i], r[d - db + i]);
       r[d] = 0.0;
     }
     int dr = db - 1;
@@ -501,7 +505,7 @@ static inline bool fivept_gauss_jordan(double A[10][20]) {
     for (int r = 0; r < 10; ++r) {
       if (r == c) continue;
       double f = A[r][c];
-      for (int j = 0; j < 20; ++j) A[r][j] = A[r][j] - f * A[c][j];
+      for (int j = 0; j < 20; ++j) A[r][j] = kfma(-f, A[c][j], A[r][j]);
     }
   }
   return true;
@@ -570,7 +574,7 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
     double y = horner(p2, 7, z) / d;
     bool ok = true;
     for (int e = 0; e < 9; ++e) {
-      double v = ((x * B[0][e] + y * B[1][e]) + z * B[2][e]) + B[3][e];
+      double v = kfma(z, B[2][e], kfma(y, B[1][e], kfma(x, B[0][e], B[3][e])));
       if (!std::isfinite(v)) ok = false;
       E[ns][e] = v;
     }
@@ -614,8 +618,8 @@ static inline void charpoly10(double H[10][10], double* c) {
         if (y != 0.0) {
           y = y / x;
           H[i2][m - 1] = y;
-          for (int j = m; j < n; ++j) H[i2][j] = H[i2][j] - y * H[m][j];
-          for (int j = 0; j < n; ++j) H[j][m] = H[j][m] + y * H[j][i2];
+          for (int j = m; j < n; ++j) H[i2][j] = kfma(-y, H[m][j], H[i2][j]);
+          for (int j = 0; j < n; ++j) H[j][m] = kfma(y, H[j][i2], H[j][m]);
         }
       }
     }
@@ -628,13 +632,13 @@ static inline void charpoly10(double H[10][10], double* c) {
   for (int k = 1; k <= n; ++k) {
     const int col = k - 1;
     const double h = H[col][col];
-    for (int j = 0; j <= k; ++j) P[k][j] = (j >= 1 ? P[k - 1][j - 1] : 0.0) - (j <= k - 1 ? h * P[k - 1][j] : 0.0);
+    for (int j = 0; j <= k; ++j) P[k][j] = j <= k - 1 ? kfma(-h, P[k - 1][j], j >= 1 ? P[k - 1][j - 1] : 0.0) : P[k - 1][j - 1];
     double prod = 1.0;
     for (int i = 1; i <= k - 1; ++i) {
       const int row = col - i;
       prod = prod * H[row + 1][row];
       const double sc = H[row][col] * prod;
-      for (int j = 0; j <= k - 1 - i; ++j) P[k][j] = P[k][j] - sc * P[k - 1 - i][j];
+      for (int j = 0; j <= k - 1 - i; ++j) P[k][j] = kfma(-sc, P[k - 1 - i][j], P[k][j]);
     }
   }
   for (int j = 0; j <= n; ++j) c[j] = P[n][j];
@@ -646,11 +650,11 @@ static inline bool stewenius_yz(const double a[6][10], double x, double* y, doub
   double C[6][5], d[6];
   for (int j = 0; j < 6; ++j) {
     C[j][0] = a[j][3]; C[j][1] = a[j][4]; C[j][2] = a[j][5];
-    C[j][3] = a[j][1] * x + a[j][7];
-    C[j][4] = a[j][2] * x + a[j][8];
-    d[j] = -((a[j][0] * x2 + a[j][6] * x) + a[j][9]);
+    C[j][3] = kfma(a[j][1], x, a[j][7]);
+    C[j][4] = kfma(a[j][2], x, a[j][8]);
+    d[j] = -kfma(a[j][0], x2, kfma(a[j][6], x, a[j][9]));
   }
-  d[0] = d[0] + x * x2;   // row 0: lambda * v0 = x * x2
+  d[0] = kfma(x, x2, d[0]);   // row 0: lambda * v0 = x * x2
   C[1][3] = C[1][3] - x2;  // row 1: lambda * v1 = x * (x y)
   C[2][4] = C[2][4] - x2;  // row 2: lambda * v2 = x * (x z)
   C[3][0] = C[3][0] - x;   // rows 3..5: lambda * v3, v4, v5
@@ -670,14 +674,14 @@ static inline bool stewenius_yz(const double a[6][10], double x, double* y, doub
     }
     for (int r = c + 1; r < 6; ++r) {
       const double f = C[r][c] / C[c][c];
-      for (int j = c + 1; j < 5; ++j) C[r][j] = C[r][j] - f * C[c][j];
-      d[r] = d[r] - f * d[c];
+      for (int j = c + 1; j < 5; ++j) C[r][j] = kfma(-f, C[c][j], C[r][j]);
+      d[r] = kfma(-f, d[c], d[r]);
     }
   }
   double u[5];
   for (int c = 4; c >= 0; --c) {
     double sacc = d[c];
-    for (int j = c + 1; j < 5; ++j) sacc = sacc - C[c][j] * u[j];
+    for (int j = c + 1; j < 5; ++j) sacc = kfma(-C[c][j], u[j], sacc);
     u[c] = sacc / C[c][c];
   }
   *y = u[3];
@@ -719,7 +723,7 @@ static inline int fivept_stewenius(const double f1[5][3], const double f2[5][3],
     if (!stewenius_yz(M, x, &y, &z)) continue;
     bool ok = true;
     for (int e = 0; e < 9; ++e) {
-      const double v = ((x * B[0][e] + y * B[1][e]) + z * B[2][e]) + B[3][e];
+      const double v = kfma(z, B[2][e], kfma(y, B[1][e], kfma(x, B[0][e], B[3][e])));
       if (!std::isfinite(v)) ok = false;
       E[ns][e] = v;
     }
@@ -752,8 +756,8 @@ static inline bool mono_model(const double* f1, const double* f2, const uint16_t
       for (int c = 0; c < 3; ++c) {
         double u0 = U[3 * r + 0], u1 = U[3 * r + 1], u2 = U[3 * r + 2];
         double v0 = V[3 * c + 0], v1 = V[3 * c + 1], v2 = V[3 * c + 2];
-        Ra[3 * r + c] = (u1 * v0 - u0 * v1) + u2 * v2;
-        Rb[3 * r + c] = (u0 * v1 - u1 * v0) + u2 * v2;
+        Ra[3 * r + c] = kfma(u2, v2, kfma(u1, v0, -(u0 * v1)));
+        Rb[3 * r + c] = kfma(u2, v2, kfma(u0, v1, -(u1 * v0)));
       }
     double tt[3] = {S[0] * U[2], S[0] * U[5], S[0] * U[8]};
     for (int cand = 0; cand < 4; ++cand) {

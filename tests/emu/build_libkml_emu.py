@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "kimera-multi_b200", "csrc")
 SOURCES = ["api_core", "hamming", "hamming_tc", "comm", "bow", "ransac", "lcd", "vocab", "select", "postfilter", "persist"]  # = the Makefile's OBJS
 # -ffp-contract=off everywhere: what -fmad=false is for ransac.cu, and the other sources hold no
 # multiply-add that the GPU build may contract into an FMA with a different result
-FLAGS = ["-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+FLAGS = ["-O2", "-ffp-contract=off", "-mfma", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
          "-Wno-unused-variable", "-Wno-attributes", "-I/usr/local/cuda/include", "-I", HERE,
          "-I", os.path.join(ROOT, "include")]
 

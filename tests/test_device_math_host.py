@@ -23,7 +23,7 @@ def _dp(a):
 def dmh(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("dmh") / "libdmh.so")
     # -ffp-contract=off is the host equivalent of nvcc -fmad=false (kimera-multi_b200/Makefile)
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-Wall",
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-mfma", "-std=c++17", "-shared", "-fPIC", "-Wall",
                     "-Wno-unknown-pragmas", "-Wno-unused-function",
                     os.path.join(ROOT, "tests", "device_math_host.cpp"), "-o", so], check=True)
     lib = C.CDLL(so)

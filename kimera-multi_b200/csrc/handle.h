@@ -203,6 +203,8 @@ struct kml_handle {
   size_t item_cap = 0;           // capacity of the mono rounds' item lists (grows after an overflow)
   bool capturing = false;        // a stream capture of the batch pipeline is in progress (lcd.cu)
   void* graph_cache = nullptr;   // lcd.cu GraphCache: the captured pipeline of small batches
+  void* enqueue_graph = nullptr; // lcd.cu EnqueueGraph: the captured local pipeline of throughput batches
+  bool graph_replayed = false;   // the batch in flight was enqueued by a graph replay (no stage events)
 
   kml::Comm* comm = nullptr;
 };

@@ -907,6 +907,10 @@ struct PoliteScope {  // batches wait without spinning; single queries keep the 
 
 // flag values of a record block (BlockLayout::err_off)
 enum { kBlkOk = 0, kBlkRedo = 1, kBlkFailed = 2 };
+// replays the captured local pipeline of this batch shape if there is one (defined with the graph code below)
+extern "C" {
+static bool batch_enqueue_graph(kml_handle* h, int cap, uint8_t* blk, BatchPlan* pl);
+}
 
 // Runs the uploaded batch.  Common case: ONE enqueue of the whole pipeline (plus, when sharded,
 // the in-place ncclAllGather of the record blocks and the device merge), one D2H of the final
@@ -941,7 +945,8 @@ static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int3
     if (local_rc == KML_OK) {
       try {
         if (!enqueued) {
-          batch_enqueue(h, cap, blk, &pl);
+          h->graph_replayed = batch_enqueue_graph(h, cap, blk, &pl);
+          if (!h->graph_replayed) batch_enqueue(h, cap, blk, &pl);
           enqueued = true;
         } else {
           const BatchStats st = *h->h_stats.p;
@@ -1010,7 +1015,7 @@ static int batch_run(kml_handle* h, int cap, bool sharded, kml_result* out, int3
     }
     if (attempt >= 40) return fail(h, KML_ERR_CUDA, "query_batch: RANSAC continuation did not converge");
   }
-  batch_stats_to_host(h, *h->h_stats.p);
+  batch_stats_to_host(h, *h->h_stats.p, h->graph_replayed);
   memcpy(out, h->h_recs.p, bl.rec_bytes);
   memcpy(counts, h->h_recs.p + bl.counts_off, sizeof(int32_t) * (size_t)B);
   if (dbg) {
@@ -1419,7 +1424,74 @@ static uint64_t graph_key(kml_handle* h, int cap) {
   for (uint64_t v : vals) k = mix64(k, v);
   return k ? k : 1;
 }
+// The local pipeline of a throughput batch (B >= 16: BoW scoring ... records in this rank's block, ~75
+// kernels and ~25 memsets) as ONE graph launch.  Several lanes enqueue batches concurrently, and with
+// eager launches the host side (a few hundred driver calls per batch, all lanes behind one context
+// lock) is what the GPU waits for between the short RANSAC kernels.  The copies, the exchange of a
+// sharded query and the host-driven continuation stay outside: batch_run goes on exactly as after an
+// eager enqueue, with the BatchPlan remembered from the capture.  Same keying as the small-batch graph.
+struct EnqueueGraph {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t key = 0, seen = 0;
+  bool disabled = false;
+  BatchPlan plan;
+  unsigned long long launches = 0;
+};
+static bool batch_enqueue_graph(kml_handle* h, int cap, uint8_t* blk, BatchPlan* pl) {
+  if (h->B < 16 || getenv("KML_NO_GRAPH")) return false;
+  if (!h->enqueue_graph) h->enqueue_graph = new EnqueueGraph();
+  EnqueueGraph* g = static_cast<EnqueueGraph*>(h->enqueue_graph);
+  if (g->disabled) return false;
+  if (!h->d_in.p || !h->d_stats.p) { g->seen = 0; return false; }
+  ensure_frame_offsets(h);
+  ensure_views(h);
+  const uint64_t key = mix64(graph_key(h, cap), (uint64_t)(uintptr_t)blk);
+  cudaStream_t s = h->stream;
+  if (!(g->exec && g->key == key)) {
+    if (g->seen != key) {  // first sight of this shape: the eager run allocates and builds every table
+      g->seen = key;
+      return false;
+    }
+    if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long l0 = h->stats.kernel_launches;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      h->capturing = true;
+      try {
+        batch_enqueue(h, cap, blk, &g->plan);
+      } catch (const std::exception&) {
+        ok = false;
+      }
+      h->capturing = false;
+      if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !graph) ok = false;
+    }
+    g->launches = h->stats.kernel_launches - l0;
+    h->stats.kernel_launches = l0;
+    if (ok && cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok || mix64(graph_key(h, cap), (uint64_t)(uintptr_t)blk) != key) {  // capture failed, or something moved under it
+      cudaGetLastError();
+      if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+      g->disabled = !ok;
+      g->seen = 0;
+      return false;
+    }
+    g->key = key;
+  }
+  KML_CUDA(cudaEventRecord(h->ev[6], s));
+  KML_CUDA(cudaGraphLaunch(g->exec, s));
+  KML_CUDA(cudaEventRecord(h->ev[7], s));
+  h->stats.kernel_launches += g->launches;
+  *pl = g->plan;
+  return true;
+}
 void kml_graph_destroy_internal(kml_handle* h) {
+  if (EnqueueGraph* e = static_cast<EnqueueGraph*>(h->enqueue_graph)) {
+    if (e->exec) cudaGraphExecDestroy(e->exec);
+    delete e;
+    h->enqueue_graph = nullptr;
+  }
   GraphCache* g = static_cast<GraphCache*>(h->graph_cache);
   if (!g) return;
   if (g->exec) cudaGraphExecDestroy(g->exec);
@@ -1490,6 +1562,7 @@ static int batch_run_graph(kml_handle* h, int cap, kml_result* out, int32_t* cou
 }
 #else
 void kml_graph_destroy_internal(kml_handle*) {}
+static bool batch_enqueue_graph(kml_handle*, int, uint8_t*, BatchPlan*) { return false; }
 #endif
 
 int kml_query_batch_upload(kml_handle* h, int B, const uint64_t* q_robot, const uint64_t* q_pose,

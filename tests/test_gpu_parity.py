@@ -179,6 +179,48 @@ def test_query_batch(oracle_lcd, gpu_lcd, small_world):
     assert len(cnt3) == 0
 
 
+def test_throughput_batch_graph_replay(oracle_lcd, gpu_lcd, small_world, monkeypatch):
+    """Batches of >= 16 queries: from the second run of a shape on the local pipeline is one replayed
+    graph.  Same records as the eager run and as the oracle, also after another shape in between and
+    with KML_NO_GRAPH; a replay is recognised by its missing per-stage events."""
+    from kml import synth
+    world, chunks, _ = small_world
+
+    def mk(n):
+        q = synth.make_queries(world, n, 400, 2)
+        fq, fp = q["frames"], q["prev"]
+        return (q["q_robot"], q["q_pose"], fq["bow_off"], fq["bow_ids"], fq["bow_vals"], fp["bow_off"],
+                fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
+    a24, a20 = mk(24), mk(20)
+    out0, cnt0 = oracle_lcd.query_batch(*a24)
+    monkeypatch.delenv("KML_NO_GRAPH", raising=False)
+    runs, replayed, launches = [], [], []
+    for _ in range(5):  # eager (allocates), eager (the addresses settled), capture + replay, replay ...
+        l0 = gpu_lcd.stats().kernel_launches
+        runs.append(gpu_lcd.query_batch(*a24))
+        st = gpu_lcd.stats()
+        replayed.append(st.ms_mono == 0.0 and st.ms_total > 0.0)
+        launches.append(st.kernel_launches - l0)
+    assert not replayed[0] and replayed[2:] == [True, True, True], replayed
+    assert len(set(launches)) == 1, launches
+    _check_records(out0, cnt0, *runs[0])
+    for out, c in runs[1:]:
+        assert out.tobytes() == runs[0][0].tobytes() and np.array_equal(c, runs[0][1])
+    other = gpu_lcd.query_batch(*a20)
+    _check_records(*oracle_lcd.query_batch(*a20), *other)
+    back = [gpu_lcd.query_batch(*a24) for _ in range(3)]
+    for out, c in back:
+        assert out.tobytes() == runs[0][0].tobytes() and np.array_equal(c, runs[0][1])
+    # the resident two-phase variant replays too
+    gpu_lcd.query_batch_upload(*a24)
+    for _ in range(3):
+        out, c = gpu_lcd.query_batch_run()
+        assert out.tobytes() == runs[0][0].tobytes()
+    monkeypatch.setenv("KML_NO_GRAPH", "1")
+    out, c = gpu_lcd.query_batch(*a24)
+    assert gpu_lcd.stats().ms_mono > 0.0 and out.tobytes() == runs[0][0].tobytes()
+
+
 def test_query_lanes_concurrent(gpu_lcd, small_world):
     """Two lanes (kml_create_lane) sharing one database, driven from two host
     threads at once, return byte-identical records to the parent handle."""

@@ -633,7 +633,115 @@ __device__ __noinline__ bool isolate_grid2(const double* cr, int R, int j, doubl
   *hi = -1.0 + (double)(cell_j + 1) * (2.0 / kTRootGrid2);
   return true;
 }
+// ---- warp-cooperative Sturm fallback ------------------------------------------------------------
+// For the chains the second grid cannot separate either (roots closer than 1/128, numerically
+// multiple roots) the serial thread below spends ~70 us on one chain: ~120 IEEE divisions of the
+// remainder sequence and, per bisection step, eleven Horner recurrences one after the other.  The
+// warp does the same operations side by side: lane i owns coefficient i of a remainder update,
+// lane k evaluates chain member k, the sign changes are counted from two ballots.  Every value is
+// produced by the same operations in the same order as in sturm_build_s / sturm_count_s /
+// isolate_unit_s(mode 1).  w: 80 doubles of shared memory per warp (the triangular chain, offsets
+// wtri(k), and the remainder in w[66..76]).
+constexpr int kWarpSturmSlots = 80;
+__device__ __forceinline__ int wtri(int k) { return 11 * k - (k * (k - 1)) / 2; }
+__device__ __noinline__ int sturm_build_w(double* w, const double* __restrict__ fo, bool reversed, int lane,
+                                          unsigned long long* degs_out) {
+  int n = 10;
+  while (n > 0 && fo[reversed ? 10 - n : n] == 0.0) --n;
+  if (lane <= n) w[lane] = fo[reversed ? 10 - lane : lane];
+  unsigned long long degs = (unsigned long long)n;
+  int len = 1;
+  if (n >= 1) {
+    if (lane < n) w[wtri(1) + lane] = (double)(lane + 1) * fo[reversed ? 10 - (lane + 1) : (lane + 1)];
+    degs |= (unsigned long long)(n - 1) << 4;
+    len = 2;
+    __syncwarp();
+    double* r = w + 66;
+    while (len < 12) {
+      const int db = (int)((degs >> (4 * (len - 1))) & 15u);
+      if (db <= 0) break;
+      const int da = (int)((degs >> (4 * (len - 2))) & 15u);
+      const int oa = wtri(len - 2), ob = wtri(len - 1), oc = wtri(len);
+      if (lane <= da) r[lane] = w[oa + lane];
+      __syncwarp();
+      for (int d = da; d >= db; --d) {
+        const double f = kdiv(r[d], w[ob + db]);
+        __syncwarp();
+        if (lane < db) r[d - db + lane] = kfma(-f, w[ob + lane], r[d - db + lane]);
+        if (lane == 31) r[d] = 0.0;
+        __syncwarp();
+      }
+      int dr = db - 1;
+      while (dr >= 0 && r[dr] == 0.0) --dr;
+      if (dr < 0) break;  // exact gcd reached
+      const double sc = fabs(r[dr]);
+      if (lane <= dr) w[oc + lane] = -kdiv(r[lane], sc);
+      degs |= (unsigned long long)dr << (4 * len);
+      ++len;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  *degs_out = degs;
+  return len;
+}
+// sign changes of the chain at x (sturm_count_s): lane k evaluates member k
+__device__ __forceinline__ int sturm_count_w(const double* w, unsigned long long degs, int len, double x, int lane) {
+  double v = 0.0;
+  if (lane < len) {
+    const int dg = (int)((degs >> (4 * lane)) & 15u);
+    const double* c = w + wtri(lane);
+    v = c[dg];
+    for (int i = dg - 1; i >= 0; --i) v = kfma(v, x, c[i]);
+  }
+  const unsigned pos = __ballot_sync(0xFFFFFFFFu, v > 0.0), neg = __ballot_sync(0xFFFFFFFFu, v < 0.0);
+  int changes = 0, last = 0;
+  for (int k = 0; k < len; ++k) {
+    const int s = (int)((pos >> k) & 1u) - (int)((neg >> k) & 1u);
+    if (s != 0) {
+      if (last != 0 && s != last) ++changes;
+      last = s;
+    }
+  }
+  return changes;
+}
+// bracket of root j of the chain in w by bisection on the count (isolate_unit_s, mode 1)
+__device__ __noinline__ void isolate_root_w(const double* w, unsigned long long degs, int len, int j,
+                                            double* __restrict__ brk, int lane) {
+  if ((int)(degs & 15u) < 1) return;
+  const int vm1 = sturm_count_w(w, degs, len, -1.0, lane), vp1 = sturm_count_w(w, degs, len, 1.0, lane);
+  int R = vm1 - vp1;
+  if (R > 10) R = 10;
+  if (j >= R) return;
+  double lo = -1.0, hi = 1.0;
+  int vlo = vm1, vhi = vp1, jj = j;
+  for (int depth = 0; depth < kTRootDepth; ++depth) {
+    if (vlo - vhi == 1) break;
+    const double mid = 0.5 * (lo + hi);
+    const int vm = sturm_count_w(w, degs, len, mid, lane);
+    const int left = vlo - vm;
+    if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+  }
+  if (lane == 0) {
+    brk[2 * j] = lo;
+    brk[2 * j + 1] = hi;
+  }
+}
+// the second grid of one (draw, chain, root) entry; false = the warp's Sturm fallback has to do it
+__device__ __forceinline__ bool mono_isolate_deferred_grid(const double* __restrict__ fo, int chain, int root, int R,
+                                                           double* __restrict__ brk) {
+  double cr[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) cr[k] = chain ? fo[10 - k] : fo[k];
+  double lo, hi;
+  if (!isolate_grid2(cr, R, root, &lo, &hi)) return false;
+  brk[2 * root] = lo;
+  brk[2 * root + 1] = hi;
+  return true;
+}
+
 // the deferred case of one (draw, chain, root): the finer grid first, else bisection on the Sturm count
+// (serial form: tests/device_math_host.cpp; the kernel runs mono_isolate_deferred_grid + the warp fallback)
 template <int STRIDE>
 __device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain, int root, int R,
                                              double* __restrict__ brk) {

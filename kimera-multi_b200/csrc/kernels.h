@@ -131,7 +131,8 @@ struct SacArgs {
   double sq_crit;        // stereo: smallest s with sqrt(s) >= threshold
   int max_iterations;
   int full;              // evaluate every draw up to max_iterations+1 (no adaptive stop)
-  int force_generic;     // test hook (env KML_FORCE_GENERIC_ISOLATE): skip the register fast path of stage 2
+  int force_generic;     // test hooks: bit 0 (env KML_FORCE_GENERIC_ISOLATE) skip the register fast path of stage 2;
+                         // bit 1 (env KML_NO_ROOT_GRID2) skip the 256-cell grid, every deferred chain is bisected
   // stereo, row f4 (ransac_use_1point_3d3d): the rotation is given per problem, prior[p] = row-major
   // 3x4 whose left 3x3 block is R (the mono model); a draw is ONE correspondence, model = [R | p1 - R p2]
   int onept;

@@ -480,7 +480,7 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   a.threshold = mono ? prm.ransac_threshold_mono : prm.ransac_threshold;
   a.sq_crit = sq_crit_of(prm.ransac_threshold);
   a.max_iterations = max_it; a.full = full;
-  a.force_generic = getenv("KML_FORCE_GENERIC_ISOLATE") ? 1 : 0;
+  a.force_generic = (getenv("KML_FORCE_GENERIC_ISOLATE") ? 1 : 0) | (getenv("KML_NO_ROOT_GRID2") ? 2 : 0);
   a.inlier_mask = out.mask->p; a.mask_words = mask_words; a.n_inliers = out.inl->p;
   return a;
 }

@@ -310,7 +310,7 @@ __device__ void mono_isolate_body(const SacArgs& a, int p) {
   int nr = 0;
   if (tid < nh) {
     nr = geom::mono_isolate_thread(a.fsol + slot * a.fo_stride, a.brk + slot * 2 * geom::kMaxBrackets,
-                                   a.force_generic != 0);
+                                   (a.force_generic & 1) != 0);
     for (int chain = 0; chain < 2; ++chain)
       if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
         const int R = chain ? ((nr >> 8) & 255) : (nr & 255);
@@ -350,16 +350,45 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a, int
 // Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
 // separate the roots, ~8 % of the chains): compacted work list, one (draw, chain, root)
 // bisection per thread.
+// Every thread tries the 256-cell grid for its entry; the entries it does not resolve are then taken
+// one after the other by the whole warp (geom::sturm_build_w / isolate_root_w), the chain being built
+// once for the roots of the same (draw, chain), which sit next to each other in the list.
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
-  KML_DYN_SMEM(double, smem_d);
+  __shared__ double wsm[kMonoChunk / 32][geom::kWarpSturmSlots];
+  const int lane = threadIdx.x & 31;
+  double* w = wsm[threadIdx.x >> 5];
   const unsigned n = min(*a.fb_count, a.item_cap);
-  for (unsigned it = blockIdx.x * kMonoChunk + threadIdx.x; it < n; it += gridDim.x * kMonoChunk) {
-    const uint32_t item = a.fb_list[it];
-    const size_t slot = item >> 5;
-    const int chain = (item >> 4) & 1, root = item & 15;
-    const int R0 = a.nroot[slot] & 255, R1 = (a.nroot[slot] >> 8) & 255;
-    geom::mono_isolate_deferred_thread<kMonoChunk>(smem_d + threadIdx.x, a.fsol + slot * a.fo_stride, chain, root,
-                                                   chain ? R1 : R0, a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
+  for (unsigned it0 = blockIdx.x * kMonoChunk + (threadIdx.x & ~31u); it0 < n; it0 += gridDim.x * kMonoChunk) {
+    const unsigned it = it0 + lane;
+    uint32_t item = 0;
+    bool ok = true;
+    if (it < n) {
+      item = a.fb_list[it];
+      const size_t slot = item >> 5;
+      const int chain = (item >> 4) & 1, root = item & 15;
+      const int R0 = a.nroot[slot] & 255, R1 = (a.nroot[slot] >> 8) & 255;
+      ok = !(a.force_generic & 2) &&  // test hook: every deferred chain through the Sturm fallback
+           geom::mono_isolate_deferred_grid(a.fsol + slot * a.fo_stride, chain, root, chain ? R1 : R0,
+                                            a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
+    }
+    unsigned fail = __ballot_sync(0xFFFFFFFFu, !ok);
+    uint32_t built = 0xFFFFFFFFu;
+    unsigned long long degs = 0ull;
+    int len = 0;
+    while (fail) {
+      const int src = __ffs(fail) - 1;
+      fail &= fail - 1u;
+      const uint32_t e = __shfl_sync(0xFFFFFFFFu, item, src);
+      const size_t slot = e >> 5;
+      const int chain = (e >> 4) & 1, root = e & 15;
+      if ((e >> 4) != built) {
+        __syncwarp();
+        len = geom::sturm_build_w(w, a.fsol + slot * a.fo_stride, chain != 0, lane, &degs);
+        built = e >> 4;
+      }
+      const int R0 = a.nroot[slot] & 255;
+      geom::isolate_root_w(w, degs, len, root, a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0), lane);
+    }
   }
 }
 
@@ -857,7 +886,6 @@ static int active_grid(int P, int round) {
 int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   if (a.P <= 0) return 0;
   const size_t sm = mono_smem();
-  const size_t sm2 = sizeof(double) * geom::kIsoSlots * kMonoChunk;
   const int draws = sac_round_draws(round, a.first);
   const int blocks = (draws + kMonoChunk - 1) / kMonoChunk;
   const int gx = active_grid(a.P, round);
@@ -872,7 +900,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
   KML_LAUNCH((mono_isolate_kernel), dim3(gx, blocks), kMonoChunk, 0, s, a, round);
-  KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, sm2, s, a);
+  KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, 0, s, a);
   if (a.alg == 1) KML_LAUNCH((mono_item_kernel<1>), kNumSMs * 16, kItemThreads, 0, s, a);
   else KML_LAUNCH((mono_item_kernel<0>), kNumSMs * 16, kItemThreads, 0, s, a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);

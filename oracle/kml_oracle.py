@@ -279,6 +279,11 @@ def ransac_nister(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_nister, f1, f2, thr, prob, max_iter, seed)
 
 
+def debug_root_grid2(on):
+    """test knob: 0 = skip the 256-cell root grid (pairs with the library's KML_NO_ROOT_GRID2)"""
+    lib().kmo_debug_root_grid2(C.c_int(int(on)))
+
+
 def ransac_stewenius(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_stewenius, f1, f2, thr, prob, max_iter, seed)
 

@@ -127,6 +127,9 @@ void kmo_ransac_nister(const double* f1, const double* f2, int N, double thr,
                        kmo_ransac_result* res, uint32_t* inliers);
 void kmo_ransac_stewenius(const double* f1, const double* f2, int N, double thr, double prob, int max_iter,
                           uint32_t seed, kmo_ransac_result* res, uint32_t* inliers);
+/* test knob: 0 = root isolation skips the 256-cell grid (the library's KML_NO_ROOT_GRID2), so that every
+ * chain the 32-cell grid does not separate goes through the Sturm bisection on both sides */
+void kmo_debug_root_grid2(int on);
 
 /* ---- A.3-A.8  LoopClosureDetector -------------------------------------- */
 typedef struct kmo_lcd kmo_lcd;

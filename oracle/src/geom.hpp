@@ -331,6 +331,7 @@ static inline int sturm_count(const Sturm* st, double x) {
 
 static const int kRootGrid = 32;    // sign-test cells on (-1,1]
 static const int kRootGrid2 = 256;  // second, finer grid for the chains the first one does not separate
+static int g_root_grid2 = 1;        // test knob (kmo_debug_root_grid2): 0 = skip it, every such chain is bisected
 static const int kRootDepth = 48;   // max Sturm bisection depth per root
 static const int kRootBisect = 6;   // sign bisection steps on the isolated bracket
 static const int kRootNewton = 6;   // bracketed Newton steps that follow
@@ -378,7 +379,7 @@ static inline int roots_unit(const double* p, int n, double* roots) {
   // too (roots closer than 1/128, or a numerically multiple root) the Sturm count is bisected.
   bool cells2[kRootGrid2];
   int nb2 = 0;
-  if (R > 0 && !grid_ok) {
+  if (R > 0 && !grid_ok && g_root_grid2) {
     double fprev = horner(c0, d0, -1.0);
     for (int i = 1; i <= kRootGrid2; ++i) {
       const double fi = horner(c0, d0, -1.0 + (double)i * (2.0 / kRootGrid2));
@@ -387,7 +388,7 @@ static inline int roots_unit(const double* p, int n, double* roots) {
       fprev = fi;
     }
   }
-  const bool grid2_ok = !grid_ok && (nb2 == R);
+  const bool grid2_ok = !grid_ok && g_root_grid2 && (nb2 == R);
   int cell = -1;
   for (int j = 0; j < R; ++j) {
     double lo = -1.0, hi = 1.0;

@@ -538,6 +538,7 @@ void kmo_ransac_nister(const double* f1, const double* f2, int N, double thr, do
   NisterProblem np{f1, f2, N, 0};
   ransac(np, N, 8, thr, prob, max_iter, seed, res, inliers);
 }
+void kmo_debug_root_grid2(int on) { kmo::g_root_grid2 = on; }
 void kmo_ransac_stewenius(const double* f1, const double* f2, int N, double thr, double prob,
                           int max_iter, uint32_t seed, kmo_ransac_result* res, uint32_t* inliers) {
   NisterProblem np{f1, f2, N, 1};

@@ -21,6 +21,9 @@
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline void __syncthreads() {}  // never reached: SYNC = false
+// the warp-cooperative Sturm fallback is not called here (a single host thread: the serial form is)
+static inline void __syncwarp() {}
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 using std::max;
 using std::min;

@@ -344,13 +344,19 @@ def test_mono_ransac_kernels_equal_the_oracle_loop(oracle, ransacemu):
     from test_gpu_parity import _nister_case
     rng = np.random.default_rng(2024)
     kinds = ["plain", "low_parallax", "far_points", "near_centres", "non_unit", "duplicates"]
-    for thr, N, fg in [(1e-6, 60, False), (1e-9, 33, False), (1e-4, 9, False), (5e-8, 8, False), (1e-6, 40, True)]:
+    # fg: 1 = generic stage-2 path; 2 = no 256-cell grid on either side, so that every chain the first grid
+    # does not separate goes through the warp-cooperative Sturm bisection (rare otherwise)
+    for thr, N, fg in [(1e-6, 60, 0), (1e-9, 33, 0), (1e-4, 9, 0), (5e-8, 8, 0), (1e-6, 40, 1), (1e-6, 48, 2), (1e-7, 30, 3)]:
         f1, f2 = np.zeros((len(kinds), N, 3)), np.zeros((len(kinds), N, 3))
         for i, kind in enumerate(kinds):
             f1[i], f2[i] = _nister_case(rng, N, kind)
         g = emu_ransac(ransacemu, True, f1, f2, thr, force_generic=fg)
-        for i, kind in enumerate(kinds):
-            _same_as_oracle(oracle.ransac_nister(f1[i], f2[i], thr, 0.995, 1000, 12345), g, i, N, (thr, N, kind, fg))
+        oracle.debug_root_grid2(0 if fg & 2 else 1)
+        try:
+            for i, kind in enumerate(kinds):
+                _same_as_oracle(oracle.ransac_nister(f1[i], f2[i], thr, 0.995, 1000, 12345), g, i, N, (thr, N, kind, fg))
+        finally:
+            oracle.debug_root_grid2(1)
     # clean scenes stop early (adaptive k), through the same replay
     Pn, N = 3, 100
     f1, f2 = np.zeros((Pn, N, 3)), np.zeros((Pn, N, 3))

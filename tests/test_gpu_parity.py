@@ -479,13 +479,25 @@ def test_mono_generic_isolation_path(oracle, monkeypatch):
     f1 = np.zeros((4, N, 3)); f2 = np.zeros((4, N, 3))
     for i, kind in enumerate(["plain", "far_points", "low_parallax", "duplicates"]):
         f1[i], f2[i] = _nister_case(rng, N, kind)
-    g = det.ransac_nister_batch(f1, f2)
-    for i in range(4):
-        o = oracle.ransac_nister(f1[i], f2[i], 1e-6, 0.995, 1000, 12345)
-        assert o["iterations"] == g["iterations"][i] and o["best_draw"] == g["best_draw"][i]
-        assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][i], N))
-        if o["best_draw"] >= 0:
-            assert np.array_equal(o["model"], g["models"][i])
+
+    def check():
+        g = det.ransac_nister_batch(f1, f2)
+        for i in range(4):
+            o = oracle.ransac_nister(f1[i], f2[i], 1e-6, 0.995, 1000, 12345)
+            assert o["iterations"] == g["iterations"][i] and o["best_draw"] == g["best_draw"][i]
+            assert np.array_equal(o["inliers"], mask_to_indices(g["mask"][i], N))
+            if o["best_draw"] >= 0:
+                assert np.array_equal(o["model"], g["models"][i])
+    check()
+    # the Sturm fallback of the deferred chains is warp-cooperative and rare (chains neither sign grid
+    # separates): without the 256-cell grid, on both sides, every deferred chain goes through it
+    monkeypatch.delenv("KML_FORCE_GENERIC_ISOLATE")
+    monkeypatch.setenv("KML_NO_ROOT_GRID2", "1")
+    oracle.debug_root_grid2(0)
+    try:
+        check()
+    finally:
+        oracle.debug_root_grid2(1)
     det.close()
 
 

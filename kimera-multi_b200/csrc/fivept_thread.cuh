@@ -685,16 +685,8 @@ __device__ __noinline__ int sturm_build_w(double* w, const double* __restrict__ 
   *degs_out = degs;
   return len;
 }
-// sign changes of the chain at x (sturm_count_s): lane k evaluates member k
-__device__ __forceinline__ int sturm_count_w(const double* w, unsigned long long degs, int len, double x, int lane) {
-  double v = 0.0;
-  if (lane < len) {
-    const int dg = (int)((degs >> (4 * lane)) & 15u);
-    const double* c = w + wtri(lane);
-    v = c[dg];
-    for (int i = dg - 1; i >= 0; --i) v = kfma(v, x, c[i]);
-  }
-  const unsigned pos = __ballot_sync(0xFFFFFFFFu, v > 0.0), neg = __ballot_sync(0xFFFFFFFFu, v < 0.0);
+// sign changes of a chain of `len` members from the sign ballots of its values (sturm_count_s)
+__device__ __forceinline__ int sturm_changes(unsigned pos, unsigned neg, int len) {
   int changes = 0, last = 0;
   for (int k = 0; k < len; ++k) {
     const int s = (int)((pos >> k) & 1u) - (int)((neg >> k) & 1u);
@@ -705,43 +697,104 @@ __device__ __forceinline__ int sturm_count_w(const double* w, unsigned long long
   }
   return changes;
 }
-// bracket of root j of the chain in w by bisection on the count (isolate_unit_s, mode 1)
-__device__ __noinline__ void isolate_root_w(const double* w, unsigned long long degs, int len, int j,
-                                            double* __restrict__ brk, int lane) {
+// value of chain member k at x
+__device__ __forceinline__ double sturm_member_w(const double* w, unsigned long long degs, int k, double x) {
+  const int dg = (int)((degs >> (4 * k)) & 15u);
+  const double* c = w + wtri(k);
+  double v = c[dg];
+  for (int i = dg - 1; i >= 0; --i) v = kfma(v, x, c[i]);
+  return v;
+}
+// Brackets of all real roots in (-1, 1] of the chain in w by bisection on the count
+// (isolate_unit_s, mode 1, for every root).  Two roots at a time: each half-warp evaluates the (at
+// most 11) members at its own midpoint, one pair of ballots serves both.
+__device__ __noinline__ void isolate_roots_w(const double* w, unsigned long long degs, int len,
+                                             double* __restrict__ brk, int lane) {
   if ((int)(degs & 15u) < 1) return;
-  const int vm1 = sturm_count_w(w, degs, len, -1.0, lane), vp1 = sturm_count_w(w, degs, len, 1.0, lane);
+  const int half = lane >> 4, hl = lane & 15;
+  int vm1, vp1;
+  {  // counts at -1 (lower half-warp) and +1 (upper half-warp)
+    const double v = hl < len ? sturm_member_w(w, degs, hl, half ? 1.0 : -1.0) : 0.0;
+    const unsigned pos = __ballot_sync(0xFFFFFFFFu, v > 0.0), neg = __ballot_sync(0xFFFFFFFFu, v < 0.0);
+    vm1 = sturm_changes(pos & 0xFFFFu, neg & 0xFFFFu, len);
+    vp1 = sturm_changes(pos >> 16, neg >> 16, len);
+  }
   int R = vm1 - vp1;
   if (R > 10) R = 10;
-  if (j >= R) return;
-  double lo = -1.0, hi = 1.0;
-  int vlo = vm1, vhi = vp1, jj = j;
-  for (int depth = 0; depth < kTRootDepth; ++depth) {
-    if (vlo - vhi == 1) break;
-    const double mid = 0.5 * (lo + hi);
-    const int vm = sturm_count_w(w, degs, len, mid, lane);
-    const int left = vlo - vm;
-    if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
-  }
-  if (lane == 0) {
-    brk[2 * j] = lo;
-    brk[2 * j + 1] = hi;
+  for (int j0 = 0; j0 < R; j0 += 2) {
+    const int j = j0 + half;
+    const bool active = j < R;
+    double lo = -1.0, hi = 1.0;
+    int vlo = vm1, vhi = vp1, jj = j;
+    for (int depth = 0; depth < kTRootDepth; ++depth) {
+      const bool done = !active || (vlo - vhi == 1);
+      if (__all_sync(0xFFFFFFFFu, done)) break;
+      const double mid = 0.5 * (lo + hi);
+      const double v = hl < len ? sturm_member_w(w, degs, hl, mid) : 0.0;
+      const unsigned pos = __ballot_sync(0xFFFFFFFFu, v > 0.0), neg = __ballot_sync(0xFFFFFFFFu, v < 0.0);
+      const int vm = sturm_changes((pos >> (16 * half)) & 0xFFFFu, (neg >> (16 * half)) & 0xFFFFu, len);
+      if (!done) {
+        const int left = vlo - vm;
+        if (jj < left) { hi = mid; vhi = vm; } else { jj -= left; lo = mid; vlo = vm; }
+      }
+    }
+    if (active && hl == 0) {
+      brk[2 * j] = lo;
+      brk[2 * j + 1] = hi;
+    }
   }
 }
-// the second grid of one (draw, chain, root) entry; false = the warp's Sturm fallback has to do it
-__device__ __forceinline__ bool mono_isolate_deferred_grid(const double* __restrict__ fo, int chain, int root, int R,
-                                                           double* __restrict__ brk) {
+// The second grid (isolate_grid2) of one chain by the whole warp: lane l evaluates x_i for i = l, l + 32, ...;
+// true = the bracketing cells are the R isolating brackets (written), false = the Sturm fallback has to do it.
+__device__ __noinline__ bool isolate_grid2_w(const double* __restrict__ fo, bool reversed, int R, double* __restrict__ brk,
+                                             int lane) {
   double cr[11];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) cr[k] = chain ? fo[10 - k] : fo[k];
-  double lo, hi;
-  if (!isolate_grid2(cr, R, root, &lo, &hi)) return false;
-  brk[2 * root] = lo;
-  brk[2 * root + 1] = hi;
+  for (int k = 0; k < 11; ++k) cr[k] = reversed ? fo[10 - k] : fo[k];
+  unsigned neg[9], pos[9], zer[9];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const int i = 32 * b + lane;
+    const double f = horner_r<10>(cr, -1.0 + (double)i * (2.0 / kTRootGrid2));
+    const bool in = i <= kTRootGrid2;
+    neg[b] = __ballot_sync(0xFFFFFFFFu, in && f < 0.0);
+    pos[b] = __ballot_sync(0xFFFFFFFFu, in && f > 0.0);
+    zer[b] = __ballot_sync(0xFFFFFFFFu, in && f == 0.0);
+  }
+  // cell c = (x_c, x_{c+1}]: sign change across it, or p(x_{c+1}) == 0
+  unsigned hit[8];
+  int nb = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const unsigned negs = (neg[b] >> 1) | (neg[b + 1] << 31), poss = (pos[b] >> 1) | (pos[b + 1] << 31);
+    const unsigned zers = (zer[b] >> 1) | (zer[b + 1] << 31);
+    hit[b] = (neg[b] & poss) | (pos[b] & negs) | zers;
+    nb += __popc(hit[b]);
+  }
+  if (nb != R) return false;
+  if (lane < R) {  // lane j takes the j-th bracketing cell
+    int skip = lane, cell = -1;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int c = __popc(hit[b]);
+      if (cell < 0) {
+        if (skip < c) {
+          unsigned m = hit[b];
+          for (int t = 0; t < skip; ++t) m &= m - 1u;
+          cell = 32 * b + __ffs(m) - 1;
+        } else {
+          skip -= c;
+        }
+      }
+    }
+    brk[2 * lane] = -1.0 + (double)cell * (2.0 / kTRootGrid2);
+    brk[2 * lane + 1] = -1.0 + (double)(cell + 1) * (2.0 / kTRootGrid2);
+  }
   return true;
 }
 
 // the deferred case of one (draw, chain, root): the finer grid first, else bisection on the Sturm count
-// (serial form: tests/device_math_host.cpp; the kernel runs mono_isolate_deferred_grid + the warp fallback)
+// (serial form, one thread per root: tests/device_math_host.cpp; the kernel runs the warp forms above)
 template <int STRIDE>
 __device__ void mono_isolate_deferred_thread(double* sm, const double* __restrict__ fo, int chain, int root, int R,
                                              double* __restrict__ brk) {

@@ -312,11 +312,10 @@ __device__ void mono_isolate_body(const SacArgs& a, int p) {
     nr = geom::mono_isolate_thread(a.fsol + slot * a.fo_stride, a.brk + slot * 2 * geom::kMaxBrackets,
                                    (a.force_generic & 1) != 0);
     for (int chain = 0; chain < 2; ++chain)
-      if ((nr >> (16 + chain)) & 1) {  // one deferred item per root of the chain
-        const int R = chain ? ((nr >> 8) & 255) : (nr & 255);
-        const unsigned at = atomicAdd(a.fb_count, (unsigned)R);
-        if (at + (unsigned)R > a.item_cap) { *a.overflow = 1u; nr = 0; break; }  // the host re-runs the batch with larger lists
-        for (int j = 0; j < R; ++j) a.fb_list[at + j] = (uint32_t)(((slot * 2 + chain) << 4) | j);
+      if ((nr >> (16 + chain)) & 1) {  // one deferred item per chain
+        const unsigned at = atomicAdd(a.fb_count, 1u);
+        if (at + 1u > a.item_cap) { *a.overflow = 1u; nr = 0; break; }  // the host re-runs the batch with larger lists
+        a.fb_list[at] = (uint32_t)(slot * 2 + chain);
       }
   }
   // item ranges: one reservation per warp, lanes take consecutive sub-ranges
@@ -348,47 +347,30 @@ __global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a, int
 }
 
 // Deferred root isolations of the round ((draw, chain) pairs whose 32-cell grid did not
-// separate the roots, ~8 % of the chains): compacted work list, one (draw, chain, root)
-// bisection per thread.
-// Every thread tries the 256-cell grid for its entry; the entries it does not resolve are then taken
-// one after the other by the whole warp (geom::sturm_build_w / isolate_root_w), the chain being built
-// once for the roots of the same (draw, chain), which sit next to each other in the list.
+// separate the roots, ~8 % of the chains): compacted work list of chains.
+// One WARP per deferred chain (grid-stride over the compacted list): the 256-cell grid evaluated side by
+// side (geom::isolate_grid2_w), and for the chains it does not separate either the Sturm chain and the
+// bisections (geom::sturm_build_w / isolate_roots_w).
 __global__ void __launch_bounds__(kMonoChunk) mono_isolate_deferred_kernel(SacArgs a) {
   __shared__ double wsm[kMonoChunk / 32][geom::kWarpSturmSlots];
-  const int lane = threadIdx.x & 31;
-  double* w = wsm[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* w = wsm[wib];
   const unsigned n = min(*a.fb_count, a.item_cap);
-  for (unsigned it0 = blockIdx.x * kMonoChunk + (threadIdx.x & ~31u); it0 < n; it0 += gridDim.x * kMonoChunk) {
-    const unsigned it = it0 + lane;
-    uint32_t item = 0;
-    bool ok = true;
-    if (it < n) {
-      item = a.fb_list[it];
-      const size_t slot = item >> 5;
-      const int chain = (item >> 4) & 1, root = item & 15;
-      const int R0 = a.nroot[slot] & 255, R1 = (a.nroot[slot] >> 8) & 255;
-      ok = !(a.force_generic & 2) &&  // test hook: every deferred chain through the Sturm fallback
-           geom::mono_isolate_deferred_grid(a.fsol + slot * a.fo_stride, chain, root, chain ? R1 : R0,
-                                            a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0));
-    }
-    unsigned fail = __ballot_sync(0xFFFFFFFFu, !ok);
-    uint32_t built = 0xFFFFFFFFu;
-    unsigned long long degs = 0ull;
-    int len = 0;
-    while (fail) {
-      const int src = __ffs(fail) - 1;
-      fail &= fail - 1u;
-      const uint32_t e = __shfl_sync(0xFFFFFFFFu, item, src);
-      const size_t slot = e >> 5;
-      const int chain = (e >> 4) & 1, root = e & 15;
-      if ((e >> 4) != built) {
-        __syncwarp();
-        len = geom::sturm_build_w(w, a.fsol + slot * a.fo_stride, chain != 0, lane, &degs);
-        built = e >> 4;
-      }
-      const int R0 = a.nroot[slot] & 255;
-      geom::isolate_root_w(w, degs, len, root, a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0), lane);
-    }
+  constexpr unsigned kWarps = kMonoChunk / 32;
+  for (unsigned it = blockIdx.x * kWarps + wib; it < n; it += gridDim.x * kWarps) {
+    const uint32_t item = a.fb_list[it];
+    const size_t slot = item >> 1;
+    const bool chain = item & 1u;
+    const int R0 = a.nroot[slot] & 255, R1 = (a.nroot[slot] >> 8) & 255;
+    const double* fo = a.fsol + slot * a.fo_stride;
+    double* brk = a.brk + slot * 2 * geom::kMaxBrackets + (chain ? 2 * R0 : 0);
+    if (!(a.force_generic & 2) &&  // test hook: every deferred chain through the Sturm fallback
+        geom::isolate_grid2_w(fo, chain, chain ? R1 : R0, brk, lane))
+      continue;
+    unsigned long long degs;
+    __syncwarp();
+    const int len = geom::sturm_build_w(w, fo, chain, lane, &degs);
+    geom::isolate_roots_w(w, degs, len, brk, lane);
   }
 }
 
@@ -900,7 +882,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
   KML_LAUNCH((mono_isolate_kernel), dim3(gx, blocks), kMonoChunk, 0, s, a, round);
-  KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 4, kMonoChunk, 0, s, a);
+  KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 16, kMonoChunk, 0, s, a);
   if (a.alg == 1) KML_LAUNCH((mono_item_kernel<1>), kNumSMs * 16, kItemThreads, 0, s, a);
   else KML_LAUNCH((mono_item_kernel<0>), kNumSMs * 16, kItemThreads, 0, s, a);
   const size_t sm4 = sizeof(double) * 6 * (size_t)((a.stride + 31) & ~31);

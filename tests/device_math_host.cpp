@@ -24,6 +24,7 @@ static inline void __syncthreads() {}  // never reached: SYNC = false
 // the warp-cooperative Sturm fallback is not called here (a single host thread: the serial form is)
 static inline void __syncwarp() {}
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline int __all_sync(unsigned, bool p) { return p ? 1 : 0; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 using std::max;
 using std::min;

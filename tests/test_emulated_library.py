@@ -75,7 +75,7 @@ def test_gpu_parity_tests_against_the_emulated_library(libkml_emu):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 24, tail
+    assert m and int(m.group(1)) >= 25, tail
     assert "failed" not in r.stdout.splitlines()[-1] and "skipped" not in r.stdout.splitlines()[-1], tail
 
 

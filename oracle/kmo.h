@@ -21,8 +21,9 @@
  * (see tests/test_oracle.py; the same external implementations wrote the
  * committed fixture tests/golden/golden_v1.npz checked by tests/test_golden.py).
  *
- * All fp64 arithmetic is compiled with -ffp-contract=off (no FMA) so that
- * the operation order written in the sources is the operation order executed.
+ * All fp64 arithmetic is compiled with -ffp-contract=off so that the operation
+ * order written in the sources is the operation order executed; the fused
+ * multiply-adds of the contract are explicit kfma() calls (src/geom.hpp).
  */
 #ifndef KMO_H_
 #define KMO_H_

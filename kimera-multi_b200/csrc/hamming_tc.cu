@@ -141,6 +141,39 @@ __device__ __forceinline__ void tc_chunk(const int32_t* v, uint32_t cj, int nval
     }
   }
 }
+// The same, on 16-bit keys two to a register (VIMNMX.U16x2 / VIMNMX3.U16x2).  Inside one (query tile,
+// train tile, 128-column half) a key fits 16 bits: ham << 7 | local column, ham = (256 - dot) / 2 <= 256,
+// i.e. -64 dot + 16384 + column.  Register lane 0 follows the even columns, lane 1 the odd ones; two
+// registers (four columns) are ordered against each other first, so four keys cost five min / max
+// instructions instead of twelve, plus one IMAD each.  Columns past the valid ones become 0xFFFF.
+template <int C, bool FULL>
+__device__ __forceinline__ void tc_chunk16(const int32_t* v, int nvalid, uint32_t* pb, uint32_t* ps) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int i0 = 4 * g;
+    uint32_t P[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + 2 * h;
+      const uint32_t k0 = 16384u + (uint32_t)(C * 32 + i), k1 = 16384u + (uint32_t)(C * 32 + i + 1);
+      uint32_t x = (uint32_t)(v[i] * -64) + (k0 | (k1 << 16));
+      x = (uint32_t)(v[i + 1] * -4194304) + x;
+      if (!FULL) {
+        if (i >= nvalid) x |= 0x0000FFFFu;
+        if (i + 1 >= nvalid) x |= 0xFFFF0000u;
+      }
+      P[h] = x;
+    }
+    const uint32_t lo = __vminu2(P[0], P[1]), hi = __vmaxu2(P[0], P[1]);
+    const uint32_t t = __vmaxu2(pb[g & 1], lo);
+    pb[g & 1] = __vminu2(pb[g & 1], lo);
+    ps[g & 1] = __vimin3_u16x2(t, ps[g & 1], hi);
+  }
+}
+// 16-bit key of a region -> the kernel's 32-bit key ham << 20 | train index (0xFFFF -> no key)
+__device__ __forceinline__ uint32_t tc_key32(uint32_t k16, uint32_t col0) {
+  return k16 == 0xFFFFu ? 0xFFFFFFFFu : ((k16 >> 7) << 20) + (col0 + (k16 & 127u));
+}
 __device__ __forceinline__ void tc_merge2(uint32_t& b, uint32_t& s, uint32_t b1, uint32_t s1) {
   const uint32_t nb = min(b, b1);
   s = min(max(b, b1), min(s, s1));
@@ -232,38 +265,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
           ph[buf] ^= 1u;
           tc_fence_after();
           const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * kTcN + jl0);
-          uint32_t b[4], s[4];
-          b[0] = best[0]; s[0] = second[0];
-#pragma unroll
-          for (int mm = 1; mm < kTcMTiles; ++mm)
-            if (mm == m) { b[0] = best[mm]; s[0] = second[mm]; }
-          b[1] = b[2] = b[3] = 0xFFFFFFFFu;
-          s[1] = s[2] = s[3] = 0xFFFFFFFFu;
+          // this thread's region: row `row_in_tile` of tile m x the <= 128 columns [jl0, jl0 + 128) of the train tile
+          uint32_t pb[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, ps[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
           int32_t va[32], vb[32];
-          if (nch > 0) tmem_ld32(tbase, va);
-#pragma unroll 1
-          for (int c = 0; c < nch; c += 2) {
-            tmem_ld_wait();                                        // va = chunk c
-            if (c + 1 < nch) tmem_ld32(tbase + (uint32_t)((c + 1) * 32), vb);
-            {
-              const int jl = jl0 + c * 32;
-              const uint32_t cj = 0x08000000u + (uint32_t)(n0 + jl);
-              if (jl + 32 <= nn) tc_chunk<true>(va, cj, 32, b, s); else tc_chunk<false>(va, cj, nn - jl, b, s);
-            }
-            if (c + 1 < nch) {
-              tmem_ld_wait();                                      // vb = chunk c + 1
-              if (c + 2 < nch) tmem_ld32(tbase + (uint32_t)((c + 2) * 32), va);
-              const int jl = jl0 + (c + 1) * 32;
-              const uint32_t cj = 0x08000000u + (uint32_t)(n0 + jl);
-              if (jl + 32 <= nn) tc_chunk<true>(vb, cj, 32, b, s); else tc_chunk<false>(vb, cj, nn - jl, b, s);
-            }
+          const int nloc = nn - jl0;  // valid columns of the region (may exceed 128)
+          if (nch > 0) {
+            tmem_ld32(tbase, va);
+            tmem_ld_wait();                                        // va = chunk 0
+            if (nch > 1) tmem_ld32(tbase + 32u, vb);
+            if (nloc >= 32) tc_chunk16<0, true>(va, 32, pb, ps); else tc_chunk16<0, false>(va, nloc, pb, ps);
           }
-          tc_merge2(b[0], s[0], b[1], s[1]);
-          tc_merge2(b[2], s[2], b[3], s[3]);
-          tc_merge2(b[0], s[0], b[2], s[2]);
+          if (nch > 1) {
+            tmem_ld_wait();                                        // vb = chunk 1
+            if (nch > 2) tmem_ld32(tbase + 64u, va);
+            if (nloc >= 64) tc_chunk16<1, true>(vb, 32, pb, ps); else tc_chunk16<1, false>(vb, nloc - 32, pb, ps);
+          }
+          if (nch > 2) {
+            tmem_ld_wait();                                        // va = chunk 2
+            if (nch > 3) tmem_ld32(tbase + 96u, vb);
+            if (nloc >= 96) tc_chunk16<2, true>(va, 32, pb, ps); else tc_chunk16<2, false>(va, nloc - 64, pb, ps);
+          }
+          if (nch > 3) {
+            tmem_ld_wait();                                        // vb = chunk 3
+            if (nloc >= 128) tc_chunk16<3, true>(vb, 32, pb, ps); else tc_chunk16<3, false>(vb, nloc - 96, pb, ps);
+          }
+          // the region's two smallest keys as 32-bit keys, merged into the row's running pair
+          const uint32_t col0 = (uint32_t)(n0 + jl0);
+          uint32_t lb = tc_key32(pb[0] & 0xFFFFu, col0), ls = tc_key32(ps[0] & 0xFFFFu, col0);
+          tc_merge2(lb, ls, tc_key32(pb[0] >> 16, col0), tc_key32(ps[0] >> 16, col0));
+          tc_merge2(lb, ls, tc_key32(pb[1] & 0xFFFFu, col0), tc_key32(ps[1] & 0xFFFFu, col0));
+          tc_merge2(lb, ls, tc_key32(pb[1] >> 16, col0), tc_key32(ps[1] >> 16, col0));
 #pragma unroll
           for (int mm = 0; mm < kTcMTiles; ++mm)
-            if (mm == m) { best[mm] = b[0]; second[mm] = s[0]; }
+            if (mm == m) tc_merge2(best[mm], second[mm], lb, ls);
           tc_fence_before();
           __syncthreads();  // every warp is done reading TMEM buffer `buf`
           if (tid == 0 && m + 2 < mtiles) issue(m + 2);

@@ -142,6 +142,13 @@ __global__ void __launch_bounds__(32) sac_init_kernel(SacArgs a) {
   if (lane == 0 && N >= S) a.active[atomicAdd(&a.n_active[0], 1u)] = p;  // round 0 works on every solvable problem
 }
 
+// `(double)iterations < k` for a non-negative integer count, as an integer limit: iterations < ceil(k)
+// (NaN and k <= 0 never hold; beyond INT_MAX always does for any count the loop can reach)
+__device__ __forceinline__ int sac_k_limit(double k) {
+  if (!(k > 0.0)) return 0;
+  if (k >= 2147483647.0) return INT_MAX;
+  return (int)ceil(k);
+}
 // Ransac::computeModel control flow, replayed over the draws of one round.
 // k never increases, so after a round the number of trials still required is
 // known exactly (up to skipped samples): the next round covers all of them.
@@ -172,8 +179,12 @@ __device__ void sac_replay_body(const SacArgs& a, int round, int p) {
     const int max_skip = a.max_iterations * 10;
     const int r_begin = st->r_begin, r_end = st->r_end;
     int best_slot = -1;
+    // the loop condition in integers (one lane walks up to 512 draws: every cycle of this chain is latency
+    // of the round); klim changes only when a better model shows up
+    int klim = a.full ? INT_MAX : sac_k_limit(k);
+#pragma unroll 4
     for (int gd = r_begin; gd < r_end; ++gd) {
-      if (!((a.full || (double)iterations < k) && skipped < max_skip)) { done = 1; break; }
+      if (!(iterations < klim && skipped < max_skip)) { done = 1; break; }
       ++draws;
       const int n = vc_s[gd - r_begin];
       if (n < 0) { ++skipped; continue; }
@@ -182,6 +193,7 @@ __device__ void sac_replay_body(const SacArgs& a, int round, int p) {
         best_draw = gd;
         best_slot = gd - r_begin;
         k = a.ktable[(size_t)N * a.ktable_n + n];
+        if (!a.full) klim = sac_k_limit(k);
       }
       ++iterations;
       if (iterations > a.max_iterations) { done = 1; break; }

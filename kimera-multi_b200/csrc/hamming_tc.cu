@@ -98,31 +98,33 @@ __device__ __forceinline__ uint32_t expand4(uint32_t n) {
 __device__ __forceinline__ uint4 tc_load_item(const uint8_t* __restrict__ src, int it, int nrows) {
   return (it < 2 * nrows) ? __ldg(reinterpret_cast<const uint4*>(src) + it) : make_uint4(0u, 0u, 0u, 0u);
 }
-__device__ __forceinline__ void tc_store_item(uint8_t* tile, uint32_t slab_bytes, int it, const uint4& x) {
-  const int r = it >> 1, kb = it & 1, sw = r & 7;
+// The expansion itself is a table look-up: lut[d] = the eight +-1 bytes of descriptor byte d (2 KB of shared
+// memory, filled by the CTA when it starts), two look-ups per 16-byte chunk instead of ~20 integer instructions.
+__device__ __forceinline__ void tc_store_item(uint8_t* tile, uint32_t slab_bytes, int it, const uint4& x, const uint2* lut) {
+  const int r = it >> 1, kb = it & 1;
   uint8_t* row = tile + (uint32_t)kb * slab_bytes + (uint32_t)r * 128u;
-  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+  // K block 1 starts with its upper four chunks (c = (j + 4 kb) & 7 = j ^ 4 kb): rotate the words once, then
+  // store j holds chunk j of the rotated block and goes to chunk position j ^ s2
+  const uint32_t w[4] = {kb ? x.z : x.x, kb ? x.w : x.y, kb ? x.x : x.z, kb ? x.y : x.w};
+  const int s2 = (r & 7) ^ (4 * kb);
+  const unsigned char* lb = reinterpret_cast<const unsigned char*>(lut);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = (j + 4 * kb) & 7;            // chunk c = bits [16c, 16c+16) of the 128-bit block
-    uint32_t h = w[0];
-#pragma unroll
-    for (int q = 1; q < 4; ++q)
-      if ((c >> 1) == q) h = w[q];
-    h = (c & 1) ? (h >> 16) : (h & 0xFFFFu);
-    uint4 o;
-    o.x = expand4(h & 15u); o.y = expand4((h >> 4) & 15u); o.z = expand4((h >> 8) & 15u); o.w = expand4(h >> 12);
-    *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = o;
+    const uint32_t h = w[j >> 1];
+    const uint32_t o0 = (j & 1) ? ((h >> 13) & 0x7F8u) : ((h << 3) & 0x7F8u);   // 8 * descriptor byte 2c
+    const uint32_t o1 = (j & 1) ? ((h >> 21) & 0x7F8u) : ((h >> 5) & 0x7F8u);   // 8 * descriptor byte 2c + 1
+    const uint2 e0 = *reinterpret_cast<const uint2*>(lb + o0), e1 = *reinterpret_cast<const uint2*>(lb + o1);
+    *reinterpret_cast<uint4*>(row + ((j ^ s2) << 4)) = make_uint4(e0.x, e0.y, e1.x, e1.y);
   }
 }
 // rows [0, nrows) of `src` into `tile` (query side: no register prefetch needed, once per pass)
 __device__ __forceinline__ void tc_expand_rows(uint8_t* tile, uint32_t slab_bytes, const uint8_t* __restrict__ src,
-                                               int nrows, int tid) {
+                                               int nrows, int tid, const uint2* lut) {
   for (int it0 = 0; it0 < 2 * nrows; it0 += 2 * kTcThreads) {
     const uint4 x0 = tc_load_item(src, it0 + tid, nrows);
     const uint4 x1 = tc_load_item(src, it0 + kTcThreads + tid, nrows);
-    if (it0 + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + tid, x0);
-    if (it0 + kTcThreads + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + kTcThreads + tid, x1);
+    if (it0 + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + tid, x0, lut);
+    if (it0 + kTcThreads + tid < 2 * nrows) tc_store_item(tile, slab_bytes, it0 + kTcThreads + tid, x1, lut);
   }
 }
 
@@ -185,12 +187,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
   __shared__ __align__(8) uint64_t full[2];
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t s_best[kTcMTiles * kTcM], s_second[kTcMTiles * kTcM];
+  __shared__ uint2 s_lut[256];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTcSmemA;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;                      // which 128 columns of a tile this warp reads
   const int row_in_tile = (warp & 3) * 32 + lane;  // TMEM lane == query row of the tile
+  s_lut[threadIdx.x & 255] = make_uint2(expand4(threadIdx.x & 15u), expand4((threadIdx.x >> 4) & 15u));
   if (warp == 0) tmem_alloc_512(&tmem_slot);
   if (tid == 0) {
     mbar_init(&full[0], 1);
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
       // query side: up to 512 rows, tile m at sA + m * 32 KB (kept if the previous job left the same rows there)
       if (!(job.q == a_src && q0 == a_q0 && nq == a_nq)) {
         for (int m = 0; m < mtiles; ++m)
-          tc_expand_rows(sA + m * kTcATile, kTcASlab, job.q + (size_t)(q0 + m * kTcM) * 32, min(kTcM, nq - m * kTcM), tid);
+          tc_expand_rows(sA + m * kTcATile, kTcASlab, job.q + (size_t)(q0 + m * kTcM) * 32, min(kTcM, nq - m * kTcM), tid, s_lut);
         a_src = job.q; a_q0 = q0; a_nq = nq;
       }
       // train side: one 256-row tile at a time; the packed rows of the NEXT tile are loaded into
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
       uint4 pf1 = tc_load_item(job.t, kTcThreads + tid, min(kTcN, job.nt));
       for (int n0 = 0; n0 < job.nt; n0 += kTcN) {
         const int nn = min(kTcN, job.nt - n0);
-        if (tid < 2 * nn) tc_store_item(sB, kTcBSlab, tid, pf0);
-        if (kTcThreads + tid < 2 * nn) tc_store_item(sB, kTcBSlab, kTcThreads + tid, pf1);
+        if (tid < 2 * nn) tc_store_item(sB, kTcBSlab, tid, pf0, s_lut);
+        if (kTcThreads + tid < 2 * nn) tc_store_item(sB, kTcBSlab, kTcThreads + tid, pf1, s_lut);
         if (n0 + kTcN < job.nt) {
           const int nn1 = min(kTcN, job.nt - n0 - kTcN);
           pf0 = tc_load_item(job.t + (size_t)(n0 + kTcN) * 32, tid, nn1);

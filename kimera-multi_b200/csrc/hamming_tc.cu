@@ -17,9 +17,10 @@
 //     rows x K = 32 per instruction, 8 instructions per tile, accumulators in TMEM (two 256-column
 //     buffers, so the tensor pipe works on tile t+1 while the CUDA cores read tile t);
 //   * the epilogue reads the accumulator back with tcgen05.ld (thread = query row, 32 columns per
-//     load) and keeps best / second best per row:  key = dot * (-2^19) + (2^27 + j)  is one
-//     IMAD, the update three integer min / max.
-// Bound: tensor pipe vs the 4 ALU instructions per distance of the epilogue.
+//     load) and keeps best / second best per row on 16-bit keys, two to a register (tc_chunk16):
+//     one IMAD per distance, five packed min / max per four distances; the 32-bit key
+//     hamming << 20 | train index is formed once per (query tile, train tile, 128-column half).
+// Bound: the CUDA-core side (2.25 instructions per distance + the expansion), DESIGN.md §5.2.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -128,22 +129,9 @@ __device__ __forceinline__ void tc_expand_rows(uint8_t* tile, uint32_t slab_byte
   }
 }
 
-// one chunk of 32 accumulator columns -> four independent (best, second) chains (column i mod 4),
-// merged by the caller: keys are distinct (the train index sits in the low bits), so the two
-// smallest keys of a union are min(b0, b1) and min(max(b0, b1), min(s0, s1)).
-template <bool FULL>
-__device__ __forceinline__ void tc_chunk(const int32_t* v, uint32_t cj, int nvalid, uint32_t* b, uint32_t* s) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (FULL || i < nvalid) {
-      const uint32_t key = (uint32_t)(v[i] * -524288) + (cj + (uint32_t)i);
-      const uint32_t mx = max(b[i & 3], key);
-      b[i & 3] = min(b[i & 3], key);
-      s[i & 3] = min(s[i & 3], mx);
-    }
-  }
-}
-// The same, on 16-bit keys two to a register (VIMNMX.U16x2 / VIMNMX3.U16x2).  Inside one (query tile,
+// The two smallest keys of a row.  Keys are distinct (the train index sits in the low bits), so the two
+// smallest keys of a union of two (best, second) pairs are min(b0, b1) and min(max(b0, b1), min(s0, s1)).
+// The epilogue works on 16-bit keys two to a register (VIMNMX.U16x2 / VIMNMX3.U16x2).  Inside one (query tile,
 // train tile, 128-column half) a key fits 16 bits: ham << 7 | local column, ham = (256 - dot) / 2 <= 256,
 // i.e. -64 dot + 16384 + column.  Register lane 0 follows the even columns, lane 1 the odd ones; two
 // registers (four columns) are ordered against each other first, so four keys cost five min / max

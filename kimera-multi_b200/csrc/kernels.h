@@ -155,6 +155,9 @@ constexpr int kRoundCap = 512;     // most new draws any round evaluates per pro
 // only while a problem is pending.
 constexpr int kSacFirstThroughput = 32, kSacRoundsThroughput = 7;
 constexpr int kSacFirstLatency = 128, kSacRoundsLatency = 4;
+// A single query (<= 32 candidate pairs): 512, 512 — every round is a chain of six kernels whose latency does not
+// depend on the number of draws at this size, and 16 pairs x 512 draws are a fraction of one wave.
+constexpr int kSacFirstSingle = 512, kSacRoundsSingle = 2, kSacSingleMaxP = 32;
 __host__ __device__ inline int sac_round_draws(int round, int first) {
   const int d = round == 0 ? first : (round > 9 ? first << 9 : first << (round - 1));
   return d < kRoundCap ? d : kRoundCap;

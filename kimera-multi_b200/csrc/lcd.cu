@@ -470,9 +470,9 @@ static SacArgs prepare_sac(kml_handle* h, bool mono, int P, const double* d_a, c
   // points).  (Tried and dropped: the latency schedule for every stereo problem — 128-draw rounds made the
   // stereo stage of a C2 batch slower, 0.48 -> 0.60 ms: the extra draws' inlier counts cost more than the
   // three rounds they save.)
-  const bool latency = P <= 256;
-  a.first = latency ? kSacFirstLatency : kSacFirstThroughput;
-  a.n_rounds = latency ? kSacRoundsLatency : kSacRoundsThroughput;
+  const bool latency = P <= 256, single = P <= kSacSingleMaxP;
+  a.first = single ? kSacFirstSingle : latency ? kSacFirstLatency : kSacFirstThroughput;
+  a.n_rounds = single ? kSacRoundsSingle : latency ? kSacRoundsLatency : kSacRoundsThroughput;
   a.alg = (mono && prm.mono_algorithm == 1) ? 1 : 0;
   a.fo_stride = a.alg == 1 ? 130 : 70;  // geom::kFrontOutStew / kFrontOut (static_assert in ransac.cu)
   a.tab_nmax = 0;

@@ -311,14 +311,17 @@ __global__ void __launch_bounds__(kFrontChunk, 4) mono_front_kernel(SacArgs a, i
   KML_ACTIVE_LOOP(mono_front_body<ALG>(a, p))
 }
 
+// One warp of draws per CTA, like the front kernel: the first rounds evaluate 32 draws per problem, and the
+// second warp of a 64-thread CTA would only hold registers (9 instead of 18 working warps per SM).
+constexpr int kIsoChunk = 32;
 __device__ void mono_isolate_body(const SacArgs& a, int p) {
   const SacState st = a.st[p];
   if (st.done) return;
-  const int d0 = st.r_begin + blockIdx.y * kMonoChunk;
+  const int d0 = st.r_begin + blockIdx.y * kIsoChunk;
   if (d0 >= st.r_end) return;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nh = min(kMonoChunk, st.r_end - d0);
-  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kMonoChunk + tid;
+  const int nh = min(kIsoChunk, st.r_end - d0);
+  const size_t slot = (size_t)p * kRoundCap + blockIdx.y * kIsoChunk + tid;
   int nr = 0;
   if (tid < nh) {
     nr = geom::mono_isolate_thread(a.fsol + slot * a.fo_stride, a.brk + slot * 2 * geom::kMaxBrackets,
@@ -354,7 +357,7 @@ __device__ void mono_isolate_body(const SacArgs& a, int p) {
     for (int r = 0; r < n; ++r) a.item_list[base + r] = (uint32_t)(slot * 32 + r);
   }
 }
-__global__ void __launch_bounds__(kMonoChunk) mono_isolate_kernel(SacArgs a, int round) {
+__global__ void __launch_bounds__(kIsoChunk) mono_isolate_kernel(SacArgs a, int round) {
   KML_ACTIVE_LOOP(mono_isolate_body(a, p))
 }
 
@@ -893,7 +896,7 @@ int launch_mono_round(const SacArgs& a, int round, cudaStream_t s) {
   }
   KML_CUDA(cudaMemsetAsync(a.fb_count, 0, 2 * sizeof(unsigned int), s));  // fb_count, item_count
   KML_CUDA(cudaMemsetAsync(a.n_active + ((round + 1) & 1), 0, sizeof(unsigned int), s));  // the next round's list
-  KML_LAUNCH((mono_isolate_kernel), dim3(gx, blocks), kMonoChunk, 0, s, a, round);
+  KML_LAUNCH((mono_isolate_kernel), dim3(gx, (draws + kIsoChunk - 1) / kIsoChunk), kIsoChunk, 0, s, a, round);
   KML_LAUNCH((mono_isolate_deferred_kernel), kNumSMs * 16, kMonoChunk, 0, s, a);
   if (a.alg == 1) KML_LAUNCH((mono_item_kernel<1>), kNumSMs * 16, kItemThreads, 0, s, a);
   else KML_LAUNCH((mono_item_kernel<0>), kNumSMs * 16, kItemThreads, 0, s, a);

@@ -242,6 +242,7 @@ template <class K> inline cudaError_t cudaFuncSetAttribute(K*, cudaFuncAttribute
 
 static inline void __syncthreads() { kml_emu::block_barrier(); }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { kml_emu::warp_barrier(); }
+static inline void __threadfence() {}  // one OS thread: program order is memory order
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return kml_emu::exchange(v, src, true); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
   return kml_emu::exchange(v, (kml_emu::S().cur & 31) ^ m, true);

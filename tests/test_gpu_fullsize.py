@@ -171,6 +171,24 @@ def _batch_args(q):
             fp["bow_ids"], fp["bow_vals"], fq["desc"], fq["bearings"], fq["points"])
 
 
+def _csr_take(off, ids, vals, idx):
+    n = (off[1:] - off[:-1])[idx]
+    o = np.zeros(len(idx) + 1, np.int64)
+    o[1:] = np.cumsum(n)
+    sel = np.concatenate([np.arange(off[i], off[i + 1]) for i in idx]) if len(idx) else np.zeros(0, np.int64)
+    return o, ids[sel], vals[sel]
+
+
+def _batch_args_of(q, idx):
+    """the batch made of queries idx (any order, any subset) of q"""
+    idx = np.asarray(idx)
+    fq, fp = q["frames"], q["prev"]
+    qo, qi, qv = _csr_take(fq["bow_off"], fq["bow_ids"], fq["bow_vals"], idx)
+    po, pi, pv = _csr_take(fp["bow_off"], fp["bow_ids"], fp["bow_vals"], idx)
+    return (q["q_robot"][idx], q["q_pose"][idx], qo, qi, qv, po, pi, pv,
+            fq["desc"][idx], fq["bearings"][idx], fq["points"][idx])
+
+
 def test_c2_full_shape_batch_against_oracle(oracle):
     """BASELINE.json configs[1] at full size: 6 robot databases x 5 000 keyframes, one 256-query batch,
     top_k_verify 16 — every one of the <= 4 096 records against the oracle's sequential run."""
@@ -190,6 +208,14 @@ def test_c2_full_shape_batch_against_oracle(oracle):
     o2, c2 = det.query_batch_run()
     o3, c3 = det.query_batch_run()
     assert np.array_equal(c2, cnt1) and o2.tobytes() == out1.tobytes() and o3.tobytes() == out1.tobytes()
+    # size-independent properties: a query's records do not depend on its place in the batch nor on the
+    # batch it travels in (permuted batch; the batch cut in two uneven parts; a single query)
+    perm = np.random.default_rng(9).permutation(256)
+    op, cp = det.query_batch(*_batch_args_of(q, perm))
+    assert np.array_equal(cp, cnt1[perm]) and op.tobytes() == out1[perm].tobytes()
+    for part in (np.arange(0, 100), np.arange(100, 256), np.array([17])):
+        oq, cq = det.query_batch(*_batch_args_of(q, part))
+        assert np.array_equal(cq, cnt1[part]) and oq.tobytes() == out1[part].tobytes()
     det.close()
 
 

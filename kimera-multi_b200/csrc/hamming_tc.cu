@@ -19,7 +19,7 @@
 //   * the epilogue reads the accumulator back with tcgen05.ld (thread = query row, 32 columns per
 //     load) and keeps best / second best per row on 16-bit keys, two to a register (tc_chunk16):
 //     one IMAD per distance, five packed min / max per four distances; the 32-bit key
-//     hamming << 20 | train index is formed once per (query tile, train tile, 128-column half).
+//     hamming << 20 | train index is formed once per (query tile, train tile, 64-column quarter).
 // Bound: the CUDA-core side (2.25 instructions per distance + the expansion), DESIGN.md §5.2.
 #include "common.cuh"
 #include "kernels.h"
@@ -28,7 +28,7 @@ namespace kml {
 
 #ifndef KML_HOST_EMULATION
 
-constexpr int kTcThreads = 256;                   // 8 warps
+constexpr int kTcThreads = 512;                   // 16 warps: four per TMEM lane quarter, each reads 64 of a tile's 256 columns
 constexpr int kTcM = 128, kTcN = 256;             // one MMA tile: 128 query rows x 256 train rows
 constexpr int kTcMTiles = 4;                      // query rows resident per pass: 512
 constexpr uint32_t kTcASlab = kTcM * 128;         // one K block of an A tile: 16 KB
@@ -132,7 +132,7 @@ __device__ __forceinline__ void tc_expand_rows(uint8_t* tile, uint32_t slab_byte
 // The two smallest keys of a row.  Keys are distinct (the train index sits in the low bits), so the two
 // smallest keys of a union of two (best, second) pairs are min(b0, b1) and min(max(b0, b1), min(s0, s1)).
 // The epilogue works on 16-bit keys two to a register (VIMNMX.U16x2 / VIMNMX3.U16x2).  Inside one (query tile,
-// train tile, 128-column half) a key fits 16 bits: ham << 7 | local column, ham = (256 - dot) / 2 <= 256,
+// train tile, 64-column quarter) a key fits 16 bits: ham << 7 | local column, ham = (256 - dot) / 2 <= 256,
 // i.e. -64 dot + 16384 + column.  Register lane 0 follows the even columns, lane 1 the odd ones; two
 // registers (four columns) are ordered against each other first, so four keys cost five min / max
 // instructions instead of twelve, plus one IMAD each.  Columns past the valid ones become 0xFFFF.
@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t full[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t s_best[kTcMTiles * kTcM], s_second[kTcMTiles * kTcM];
+  __shared__ uint32_t s_best[3][kTcMTiles * kTcM], s_second[3][kTcMTiles * kTcM];
   __shared__ uint2 s_lut[256];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTcSmemA;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2;                      // which 128 columns of a tile this warp reads
+  const int quarter = warp >> 2;                   // which 64 columns of a tile this warp reads
   const int row_in_tile = (warp & 3) * 32 + lane;  // TMEM lane == query row of the tile
   s_lut[threadIdx.x & 255] = make_uint2(expand4(threadIdx.x & 15u), expand4((threadIdx.x >> 4) & 15u));
   if (warp == 0) tmem_alloc_512(&tmem_slot);
@@ -220,16 +220,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
       }
       // train side: one 256-row tile at a time; the packed rows of the NEXT tile are loaded into
       // registers (2 items per thread) while the tensor pipe and the epilogue work on this one
+      static_assert(kTcThreads == 2 * kTcN, "one (row, K block) item of the train tile per thread");
       uint4 pf0 = tc_load_item(job.t, tid, min(kTcN, job.nt));
-      uint4 pf1 = tc_load_item(job.t, kTcThreads + tid, min(kTcN, job.nt));
       for (int n0 = 0; n0 < job.nt; n0 += kTcN) {
         const int nn = min(kTcN, job.nt - n0);
         if (tid < 2 * nn) tc_store_item(sB, kTcBSlab, tid, pf0, s_lut);
-        if (kTcThreads + tid < 2 * nn) tc_store_item(sB, kTcBSlab, kTcThreads + tid, pf1, s_lut);
         if (n0 + kTcN < job.nt) {
           const int nn1 = min(kTcN, job.nt - n0 - kTcN);
           pf0 = tc_load_item(job.t + (size_t)(n0 + kTcN) * 32, tid, nn1);
-          pf1 = tc_load_item(job.t + (size_t)(n0 + kTcN) * 32, kTcThreads + tid, nn1);
         }
         fence_proxy_async();
         __syncthreads();
@@ -248,38 +246,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
           issue(0);
           if (mtiles > 1) issue(1);
         }
-        // chunks of 32 columns this thread reads in this tile: [half*128, half*128 + 128) cut at nn
-        const int jl0 = half * 128;
-        const int nch = nn > jl0 ? min(4, (nn - jl0 + 31) >> 5) : 0;
+        // chunks of 32 columns this thread reads in this tile: [quarter*64, quarter*64 + 64) cut at nn
+        const int jl0 = quarter * 64;
+        const int nch = nn > jl0 ? min(2, (nn - jl0 + 31) >> 5) : 0;
         for (int m = 0; m < mtiles; ++m) {
           const int buf = m & 1;
           mbar_wait(&full[buf], ph[buf]);
           ph[buf] ^= 1u;
           tc_fence_after();
           const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * kTcN + jl0);
-          // this thread's region: row `row_in_tile` of tile m x the <= 128 columns [jl0, jl0 + 128) of the train tile
+          // this thread's region: row `row_in_tile` of tile m x the <= 64 columns [jl0, jl0 + 64) of the train tile
+          // (one register buffer: with sixteen warps the other warps cover the TMEM load's latency)
           uint32_t pb[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, ps[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-          int32_t va[32], vb[32];
-          const int nloc = nn - jl0;  // valid columns of the region (may exceed 128)
+          int32_t va[32];
+          const int nloc = nn - jl0;  // valid columns of the region (may exceed 64)
           if (nch > 0) {
             tmem_ld32(tbase, va);
             tmem_ld_wait();                                        // va = chunk 0
-            if (nch > 1) tmem_ld32(tbase + 32u, vb);
             if (nloc >= 32) tc_chunk16<0, true>(va, 32, pb, ps); else tc_chunk16<0, false>(va, nloc, pb, ps);
           }
           if (nch > 1) {
-            tmem_ld_wait();                                        // vb = chunk 1
-            if (nch > 2) tmem_ld32(tbase + 64u, va);
-            if (nloc >= 64) tc_chunk16<1, true>(vb, 32, pb, ps); else tc_chunk16<1, false>(vb, nloc - 32, pb, ps);
-          }
-          if (nch > 2) {
-            tmem_ld_wait();                                        // va = chunk 2
-            if (nch > 3) tmem_ld32(tbase + 96u, vb);
-            if (nloc >= 96) tc_chunk16<2, true>(va, 32, pb, ps); else tc_chunk16<2, false>(va, nloc - 64, pb, ps);
-          }
-          if (nch > 3) {
-            tmem_ld_wait();                                        // vb = chunk 3
-            if (nloc >= 128) tc_chunk16<3, true>(vb, 32, pb, ps); else tc_chunk16<3, false>(vb, nloc - 96, pb, ps);
+            tmem_ld32(tbase + 32u, va);
+            tmem_ld_wait();                                        // va = chunk 1
+            if (nloc >= 64) tc_chunk16<1, true>(va, 32, pb, ps); else tc_chunk16<1, false>(va, nloc - 32, pb, ps);
           }
           // the region's two smallest keys as 32-bit keys, merged into the row's running pair
           const uint32_t col0 = (uint32_t)(n0 + jl0);
@@ -296,23 +285,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamJob*
         }
         // all MMAs of this train tile have completed (their commits were waited for): sB is free
       }
-      // merge the two column halves of every row and write the keys
-      if (half == 1) {
+      // merge the four column quarters of every row and write the keys
+      if (quarter > 0) {
 #pragma unroll
         for (int m = 0; m < kTcMTiles; ++m) {
-          s_best[m * kTcM + row_in_tile] = best[m];
-          s_second[m * kTcM + row_in_tile] = second[m];
+          s_best[quarter - 1][m * kTcM + row_in_tile] = best[m];
+          s_second[quarter - 1][m * kTcM + row_in_tile] = second[m];
         }
       }
       __syncthreads();
-      if (half == 0) {
+      if (quarter == 0) {
 #pragma unroll
         for (int m = 0; m < kTcMTiles; ++m) {
           const int qi = m * kTcM + row_in_tile;
           if (qi < nq) {
-            const uint32_t b1 = s_best[qi], s1 = s_second[qi];
-            const uint32_t b = min(best[m], b1);
-            const uint32_t s = min(max(best[m], b1), min(second[m], s1));
+            uint32_t b = best[m], s = second[m];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) tc_merge2(b, s, s_best[o][qi], s_second[o][qi]);
             job.keys[2 * (size_t)(q0 + qi) + 0] = b;
             job.keys[2 * (size_t)(q0 + qi) + 1] = s;
           }

@@ -249,6 +249,30 @@ def test_query_lanes_concurrent(gpu_lcd, small_world):
     assert len(got) == 8
     for out, c in got.values():
         assert np.array_equal(c, cnt) and out.tobytes() == ref.tobytes()
+    # throughput batches (>= 16 queries: each lane captures and replays its own graph of the local pipeline
+    # while the other lane is enqueueing or capturing), six runs per lane
+    from kml import synth
+    q24 = synth.make_queries(world, 24, 400, 2, key=5)
+    f24, p24 = q24["frames"], q24["prev"]
+    args24 = (q24["q_robot"], q24["q_pose"], f24["bow_off"], f24["bow_ids"], f24["bow_vals"], p24["bow_off"],
+              p24["bow_ids"], p24["bow_vals"], f24["desc"], f24["bearings"], f24["points"])
+    ref24, cnt24 = gpu_lcd.query_batch(*args24)
+    got24 = {}
+
+    def work24(i):
+        try:
+            for rep in range(6):
+                got24[(i, rep)] = lanes[i].query_batch(*args24)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work24, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert len(got24) == 12
+    for out, c in got24.values():
+        assert np.array_equal(c, cnt24) and out.tobytes() == ref24.tobytes()
     # the parent still sees frames added through a lane (shared store)
     ch = chunks[0]
     lanes[0].addVLCFrame(7, 1, ch["desc"][0], ch["bearings"][0], ch["points"][0])

@@ -378,16 +378,18 @@ __device__ __noinline__ int sturm_build_s(double* sm, bool reversed, unsigned lo
       const int da = (int)((degs >> (4 * (len - 2))) & 15u);
       const int oa = tri_off(len - 2), ob = tri_off(len - 1), oc = tri_off(len);
       for (int i = 0; i <= da; ++i) SS(i) = SS(oa + i);  // remainder r[0..da] in scratch 0..10
+      const bool unit_lc = len - 1 >= 2;  // a remainder's leading coefficient is exactly +-1
       for (int d = da; d >= db; --d) {
-        const double f = kdiv(SS(d), SS(ob + db));
+        const double f = unit_lc ? SS(d) * SS(ob + db) : kdiv(SS(d), SS(ob + db));
         for (int i = 0; i < db; ++i) SS(d - db + i) = kfma(-f, SS(ob + i), SS(d - db + i));
         SS(d) = 0.0;
       }
       int dr = db - 1;
       while (dr >= 0 && SS(dr) == 0.0) --dr;
       if (dr < 0) break;  // exact gcd reached
-      const double sc = fabs(SS(dr));
-      for (int i = 0; i <= dr; ++i) SS(oc + i) = -kdiv(SS(i), sc);
+      const double inv = kdiv(1.0, fabs(SS(dr)));
+      for (int i = 0; i < dr; ++i) SS(oc + i) = -(SS(i) * inv);
+      SS(oc + dr) = SS(dr) > 0.0 ? -1.0 : 1.0;
       degs |= (unsigned long long)dr << (4 * len);
       ++len;
     }
@@ -497,32 +499,34 @@ struct SturmSigns {
     if (sp_ != 0) { if (last_p != 0 && sp_ != last_p) ++ch_p; last_p = sp_; }
   }
 };
-// remainder of pa (degree DB+1) by pb (degree DB), negated and scaled by 1/|leading|: degree DB-1
-template <int DB>
+// remainder of pa (degree DB+1) by pb (degree DB), negated and scaled by 1/|leading|: degree DB-1.
+// UNIT: pb is itself a remainder, whose leading coefficient is exactly +-1 (dividing = multiplying).
+template <int DB, bool UNIT>
 __device__ __forceinline__ bool sturm_step(const double* pa, const double* pb, double* pc) {
   double r[DB + 2];
 #pragma unroll
   for (int i = 0; i <= DB + 1; ++i) r[i] = pa[i];
   {
-    const double f = kdiv(r[DB + 1], pb[DB]);
+    const double f = UNIT ? r[DB + 1] * pb[DB] : kdiv(r[DB + 1], pb[DB]);
 #pragma unroll
     for (int i = 0; i < DB; ++i) r[1 + i] = kfma(-f, pb[i], r[1 + i]);
   }
   {
-    const double f = kdiv(r[DB], pb[DB]);
+    const double f = UNIT ? r[DB] * pb[DB] : kdiv(r[DB], pb[DB]);
 #pragma unroll
     for (int i = 0; i < DB; ++i) r[i] = kfma(-f, pb[i], r[i]);
   }
   if (r[DB - 1] == 0.0) return false;  // the degree drops by more than one
-  const double sc = fabs(r[DB - 1]);
+  const double inv = kdiv(1.0, fabs(r[DB - 1]));
 #pragma unroll
-  for (int i = 0; i <= DB - 1; ++i) pc[i] = -kdiv(r[i], sc);
+  for (int i = 0; i < DB - 1; ++i) pc[i] = -(r[i] * inv);
+  pc[DB - 1] = r[DB - 1] > 0.0 ? -1.0 : 1.0;
   return true;
 }
 template <int DB>
 __device__ __forceinline__ bool sturm_tail(const double* pa, const double* pb, SturmSigns& sg) {
   double pc[DB];
-  if (!sturm_step<DB>(pa, pb, pc)) return false;
+  if (!sturm_step<DB, (DB < 9)>(pa, pb, pc)) return false;  // DB = 9: the divisor is the derivative, not a remainder
   sg.add(horner_r<DB - 1>(pc, -1.0), horner_r<DB - 1>(pc, 1.0));
   if constexpr (DB - 1 >= 1) return sturm_tail<DB - 1>(pb, pc, sg);
   return true;
@@ -664,8 +668,9 @@ __device__ __noinline__ int sturm_build_w(double* w, const double* __restrict__ 
       const int oa = wtri(len - 2), ob = wtri(len - 1), oc = wtri(len);
       if (lane <= da) r[lane] = w[oa + lane];
       __syncwarp();
+      const bool unit_lc = len - 1 >= 2;  // a remainder's leading coefficient is exactly +-1
       for (int d = da; d >= db; --d) {
-        const double f = kdiv(r[d], w[ob + db]);
+        const double f = unit_lc ? r[d] * w[ob + db] : kdiv(r[d], w[ob + db]);
         __syncwarp();
         if (lane < db) r[d - db + lane] = kfma(-f, w[ob + lane], r[d - db + lane]);
         if (lane == 31) r[d] = 0.0;
@@ -674,8 +679,9 @@ __device__ __noinline__ int sturm_build_w(double* w, const double* __restrict__ 
       int dr = db - 1;
       while (dr >= 0 && r[dr] == 0.0) --dr;
       if (dr < 0) break;  // exact gcd reached
-      const double sc = fabs(r[dr]);
-      if (lane <= dr) w[oc + lane] = -kdiv(r[lane], sc);
+      const double inv = kdiv(1.0, fabs(r[dr]));
+      if (lane < dr) w[oc + lane] = -(r[lane] * inv);
+      if (lane == dr) w[oc + lane] = r[dr] > 0.0 ? -1.0 : 1.0;
       degs |= (unsigned long long)dr << (4 * len);
       ++len;
       __syncwarp();

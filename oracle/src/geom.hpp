@@ -279,7 +279,7 @@ static inline void upmul(const double* a, int da, const double* b, int db, doubl
 }
 
 // Sturm chain of a degree-10 polynomial.  chain[k] has degree deg[k];
-// every remainder is negated and scaled by 1/|leading coefficient|.
+// every remainder is negated and scaled by 1/|leading coefficient| (its own leading coefficient is -+1 exactly).
 struct Sturm {
   double c[12][11];
   int deg[12];
@@ -301,17 +301,22 @@ static inline void sturm_build(const double* p, int n, Sturm* st) {
     int da = st->deg[st->len - 2], db = st->deg[st->len - 1];
     double r[11];
     for (int i = 0; i <= da; ++i) r[i] = a[i];
+    // a remainder's leading coefficient is exactly +-1 (below): dividing by it is multiplying by it
+    const bool unit_lc = st->len - 1 >= 2;
     for (int d = da; d >= db; --d) {
-      double f = r[d] / b[db];
+      double f = unit_lc ? r[d] * b[db] : r[d] / b[db];
       for (int i = 0; i < db; ++i) r[d - db + i] = kfma(-f, b[i], r[d - db + i]);
       r[d] = 0.0;
     }
     int dr = db - 1;
     while (dr >= 0 && r[dr] == 0.0) --dr;
     if (dr < 0) break;  // exact gcd reached
-    double sc = std::fabs(r[dr]);
+    // negated and scaled by the reciprocal of |leading coefficient| (one division per remainder); the
+    // leading coefficient itself is set to -+1 exactly
+    const double inv = 1.0 / std::fabs(r[dr]);
     double* o = st->c[st->len];
-    for (int i = 0; i <= dr; ++i) o[i] = -(r[i] / sc);
+    for (int i = 0; i < dr; ++i) o[i] = -(r[i] * inv);
+    o[dr] = r[dr] > 0.0 ? -1.0 : 1.0;
     st->deg[st->len] = dr;
     st->len++;
   }

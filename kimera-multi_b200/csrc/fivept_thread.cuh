@@ -190,7 +190,7 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
   // matrix, the reflectors and the basis live in registers.
   double B[36];
   {
-    double A[45], V[45], N2[5];
+    double A[45], V[45], N2[5], BETA[5];  // BETA = 2 / |v|^2: one division per reflector
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       const double* fq = ga + 3 * sidx[j];
@@ -214,13 +214,14 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
 #pragma unroll
       for (int i = k; i < 9; ++i) n2 = kfma(V[k * 9 + i], V[k * 9 + i], n2);
       N2[k] = n2;
+      BETA[k] = kdiv(2.0, n2);
       if (n2 > 0.0) {
 #pragma unroll
         for (int j = k; j < 5; ++j) {
           double d = 0.0;
 #pragma unroll
           for (int i = k; i < 9; ++i) d = kfma(V[k * 9 + i], A[i * 5 + j], d);
-          const double f = kdiv(2.0 * d, n2);
+          const double f = d * BETA[k];
 #pragma unroll
           for (int i = k; i < 9; ++i) A[i * 5 + j] = kfma(-f, V[k * 9 + i], A[i * 5 + j]);
         }
@@ -238,7 +239,7 @@ __device__ void mono_front_thread(double* sm, const double* __restrict__ ga, con
         double d = 0.0;
 #pragma unroll
         for (int i = k; i < 9; ++i) d = kfma(V[k * 9 + i], e[i], d);
-        const double f = kdiv(2.0 * d, n2);
+        const double f = d * BETA[k];
 #pragma unroll
         for (int i = k; i < 9; ++i) e[i] = kfma(-f, V[k * 9 + i], e[i]);
       }
@@ -1001,8 +1002,9 @@ __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, cons
   const double d12 = dot(f1, f2u);
   const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
   const double det = kfma(A00, A11, -(A01 * A10));
-  const double l0 = kfma(A11, b0, -(A01 * b1)) / det;
-  const double l1 = kfma(A00, b1, -(A10 * b0)) / det;
+  const double rdet = 1.0 / det;
+  const double l0 = kfma(A11, b0, -(A01 * b1)) * rdet;
+  const double l1 = kfma(A00, b1, -(A10 * b0)) * rdet;
   V3 p, q;
   p.x = 0.5 * kfma(l0, f1.x, kfma(l1, f2u.x, t.x));
   p.y = 0.5 * kfma(l0, f1.y, kfma(l1, f2u.y, t.y));

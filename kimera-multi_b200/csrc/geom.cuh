@@ -56,8 +56,9 @@ KML_DN bool jacobi_pair(double* G, double* W, int p, int q) {
   const double b = kfma(G[6 + q], G[6 + q], kfma(G[3 + q], G[3 + q], G[q] * G[q]));
   const double g = kfma(G[6 + p], G[6 + q], kfma(G[3 + p], G[3 + q], G[p] * G[q]));
   if (g * g <= 1e-30 * a * b) return false;
-  const double zeta = kdiv(b - a, 2.0 * g);
-  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(kfma(zeta, zeta, 1.0)));
+  const double h = b - a, tg = 2.0 * g;  // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = h / tg, times 2|g|: one division
+  const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
+  const double t = kdiv(sgn * fabs(tg), fabs(h) + ksqrt(kfma(h, h, tg * tg)));
   const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
   const double s = c * t;
 #pragma unroll 1
@@ -135,8 +136,9 @@ KML_DI bool jacobi_pair_r(double (&G)[9], double (&W)[9]) {
   const double b = kfma(G[6 + Q], G[6 + Q], kfma(G[3 + Q], G[3 + Q], G[Q] * G[Q]));
   const double g = kfma(G[6 + P], G[6 + Q], kfma(G[3 + P], G[3 + Q], G[P] * G[Q]));
   if (g * g <= 1e-30 * a * b) return false;
-  const double zeta = kdiv(b - a, 2.0 * g);
-  const double t = kdiv(zeta >= 0.0 ? 1.0 : -1.0, fabs(zeta) + ksqrt(kfma(zeta, zeta, 1.0)));
+  const double h = b - a, tg = 2.0 * g;  // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = h / tg, times 2|g|: one division
+  const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
+  const double t = kdiv(sgn * fabs(tg), fabs(h) + ksqrt(kfma(h, h, tg * tg)));
   const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
   const double s = c * t;
 #pragma unroll
@@ -280,8 +282,9 @@ KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, c
   const double d12 = dot(f1, f2u);
   const double A00 = dot(f1, f1), A01 = -d12, A10 = d12, A11 = -dot(f2u, f2u);
   const double det = kfma(A00, A11, -(A01 * A10));
-  const double l0 = kdiv(kfma(A11, b0, -(A01 * b1)), det);
-  const double l1 = kdiv(kfma(A00, b1, -(A10 * b0)), det);
+  const double rdet = kdiv(1.0, det);
+  const double l0 = kfma(A11, b0, -(A01 * b1)) * rdet;
+  const double l1 = kfma(A00, b1, -(A10 * b0)) * rdet;
   V3 p, q;
   p.x = 0.5 * kfma(l0, f1.x, kfma(l1, f2u.x, t.x));
   p.y = 0.5 * kfma(l0, f1.y, kfma(l1, f2u.y, t.y));

@@ -50,7 +50,7 @@ static inline void matTvec3(const double* M, const double* x, double* y) {
 // A = U diag(S) V^T with S sorted descending, U = [u0 u1 u0xu1],
 // V = [v0 v1 v0xv1] (both det +1).  The third singular value is reported as
 // the norm of the third rotated column.  At most 12 sweeps over the pairs
-// (0,1),(0,2),(1,2); a rotation is skipped when g*g <= 1e-30*a*b.
+// (0,1),(0,2),(1,2); a rotation is skipped when g*g <= 1e-30*a*b; t = sgn 2|g| / (|b-a| + sqrt((b-a)^2 + 4g^2)).
 static const int kSvdSweeps = 12;
 static inline void svd3(const double* A, double* U, double* S, double* V) {
   double G[9], W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -65,8 +65,11 @@ static inline void svd3(const double* A, double* U, double* S, double* V) {
       double g = kfma(G[6 + p], G[6 + q], kfma(G[3 + p], G[3 + q], G[p] * G[q]));
       if (g * g <= 1e-30 * a * b) continue;
       rotated = true;
-      double zeta = (b - a) / (2.0 * g);
-      double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(kfma(zeta, zeta, 1.0)));
+      // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (b - a) / (2 g), multiplied through by 2|g|:
+      // one division instead of two
+      const double h = b - a, tg = 2.0 * g;
+      const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
+      double t = (sgn * std::fabs(tg)) / (std::fabs(h) + std::sqrt(kfma(h, h, tg * tg)));
       double c = 1.0 / std::sqrt(kfma(t, t, 1.0));
       double s = c * t;
       for (int i = 0; i < 3; ++i) {
@@ -180,8 +183,9 @@ static inline double mono_residual(const double* M, const double* tinv,
   double d12 = dot3(f1, f2u);
   double A00 = dot3(f1, f1), A01 = -d12, A10 = d12, A11 = -dot3(f2u, f2u);
   double det = kfma(A00, A11, -(A01 * A10));
-  double l0 = kfma(A11, b0, -(A01 * b1)) / det;
-  double l1 = kfma(A00, b1, -(A10 * b0)) / det;
+  const double rdet = 1.0 / det;
+  double l0 = kfma(A11, b0, -(A01 * b1)) * rdet;
+  double l1 = kfma(A00, b1, -(A10 * b0)) * rdet;
   double p[3], q[3];
   for (int i = 0; i < 3; ++i) p[i] = 0.5 * kfma(l0, f1[i], kfma(l1, f2u[i], t[i]));
   q[0] = kfma(M[8], p[2], kfma(M[4], p[1], kfma(M[0], p[0], tinv[0])));
@@ -231,7 +235,7 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
   for (int r = 0; r < 5; ++r)
     for (int c = 0; c < 9; ++c) A[c][r] = Q[r][c];
   double v[5][9];
-  double vn2[5];
+  double vn2[5], beta[5];  // beta = 2 / |v|^2: one division per reflector
   for (int k = 0; k < 5; ++k) {
     double s2 = 0.0;
     for (int i = k; i < 9; ++i) s2 = kfma(A[i][k], A[i][k], s2);
@@ -242,11 +246,12 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
     double n2 = 0.0;
     for (int i = k; i < 9; ++i) n2 = kfma(v[k][i], v[k][i], n2);
     vn2[k] = n2;
+    beta[k] = 2.0 / n2;
     if (n2 > 0.0) {
       for (int j = k; j < 5; ++j) {
         double d = 0.0;
         for (int i = k; i < 9; ++i) d = kfma(v[k][i], A[i][j], d);
-        double f = (2.0 * d) / n2;
+        double f = d * beta[k];
         for (int i = k; i < 9; ++i) A[i][j] = kfma(-f, v[k][i], A[i][j]);
       }
     }
@@ -258,7 +263,7 @@ static inline void nullspace5x9(const double Q[5][9], double basis[4][9]) {
       if (!(vn2[k] > 0.0)) continue;
       double d = 0.0;
       for (int i = k; i < 9; ++i) d = kfma(v[k][i], x[i], d);
-      double f = (2.0 * d) / vn2[k];
+      double f = d * beta[k];
       for (int i = k; i < 9; ++i) x[i] = kfma(-f, v[k][i], x[i]);
     }
     for (int i = 0; i < 9; ++i) basis[b][i] = x[i];

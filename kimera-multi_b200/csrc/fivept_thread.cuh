@@ -875,13 +875,13 @@ __device__ __noinline__ bool essential_from_root(const double* __restrict__ fo, 
   double c[8];
 #pragma unroll
   for (int i = 0; i < 7; ++i) c[i] = fo[27 + i];
-  const double d = horner_r<6>(c, z);
+  const double rd = kdiv(1.0, horner_r<6>(c, z));
 #pragma unroll
   for (int i = 0; i < 8; ++i) c[i] = fo[11 + i];
-  const double x = kdiv(horner_r<7>(c, z), d);
+  const double x = horner_r<7>(c, z) * rd;
 #pragma unroll
   for (int i = 0; i < 8; ++i) c[i] = fo[19 + i];
-  const double y = kdiv(horner_r<7>(c, z), d);
+  const double y = horner_r<7>(c, z) * rd;
   bool ok = true;
 #pragma unroll 1
   for (int e = 0; e < 9; ++e) {

@@ -101,12 +101,14 @@ KML_DN void svd3(const double* A, double* U, double* S, double* V) {
   S[0] = n[i0]; S[1] = n[i1]; S[2] = n[i2];
   V3 u0, u1;
   if (n[i0] > 0.0) {
-    u0.x = kdiv(G[i0], n[i0]); u0.y = kdiv(G[3 + i0], n[i0]); u0.z = kdiv(G[6 + i0], n[i0]);
+    const double r0 = kdiv(1.0, n[i0]);
+    u0.x = G[i0] * r0; u0.y = G[3 + i0] * r0; u0.z = G[6 + i0] * r0;
   } else {
     u0.x = 1.0; u0.y = 0.0; u0.z = 0.0;
   }
   if (n[i1] > 0.0) {
-    u1.x = kdiv(G[i1], n[i1]); u1.y = kdiv(G[3 + i1], n[i1]); u1.z = kdiv(G[6 + i1], n[i1]);
+    const double r1 = kdiv(1.0, n[i1]);
+    u1.x = G[i1] * r1; u1.y = G[3 + i1] * r1; u1.z = G[6 + i1] * r1;
   } else {
     int k = 0;
     double m = fabs(u0.x);
@@ -186,13 +188,15 @@ KML_DI void svd3_r(const double* A, double* U, double* S, double* V) {
   V3 u0, u1;
   if (n0 > 0.0) {
     const V3 g0 = column_of(G, i0);
-    u0.x = kdiv(g0.x, n0); u0.y = kdiv(g0.y, n0); u0.z = kdiv(g0.z, n0);
+    const double r0 = kdiv(1.0, n0);
+    u0.x = g0.x * r0; u0.y = g0.y * r0; u0.z = g0.z * r0;
   } else {
     u0.x = 1.0; u0.y = 0.0; u0.z = 0.0;
   }
   if (n1 > 0.0) {
     const V3 g1 = column_of(G, i1);
-    u1.x = kdiv(g1.x, n1); u1.y = kdiv(g1.y, n1); u1.z = kdiv(g1.z, n1);
+    const double r1 = kdiv(1.0, n1);
+    u1.x = g1.x * r1; u1.y = g1.y * r1; u1.z = g1.z * r1;
   } else {
     int k = 0;
     double m = fabs(u0.x);

@@ -94,12 +94,14 @@ static inline void svd3(const double* A, double* U, double* S, double* V) {
   S[0] = n[i0]; S[1] = n[i1]; S[2] = n[i2];
   double u0[3], u1[3], u2[3], v0[3], v1[3], v2[3];
   if (n[i0] > 0.0) {
-    for (int i = 0; i < 3; ++i) u0[i] = G[3 * i + i0] / n[i0];
+    const double r0 = 1.0 / n[i0];
+    for (int i = 0; i < 3; ++i) u0[i] = G[3 * i + i0] * r0;
   } else {
     u0[0] = 1.0; u0[1] = 0.0; u0[2] = 0.0;
   }
   if (n[i1] > 0.0) {
-    for (int i = 0; i < 3; ++i) u1[i] = G[3 * i + i1] / n[i1];
+    const double r1 = 1.0 / n[i1];
+    for (int i = 0; i < 3; ++i) u1[i] = G[3 * i + i1] * r1;
   } else {
     // rank <= 1: any unit vector orthogonal to u0 (deterministic choice)
     int k = 0;
@@ -580,9 +582,9 @@ static inline int fivept_nister(const double f1[5][3], const double f2[5][3], do
   int ns = 0;
   for (int k = 0; k < nroots && ns < 10; ++k) {
     double z = zr[k];
-    double d = horner(p3, 6, z);
-    double x = horner(p1, 7, z) / d;
-    double y = horner(p2, 7, z) / d;
+    double rd = 1.0 / horner(p3, 6, z);
+    double x = horner(p1, 7, z) * rd;
+    double y = horner(p2, 7, z) * rd;
     bool ok = true;
     for (int e = 0; e < 9; ++e) {
       double v = kfma(z, B[2][e], kfma(y, B[1][e], kfma(x, B[0][e], B[3][e])));

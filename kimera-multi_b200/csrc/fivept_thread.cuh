@@ -1012,9 +1012,8 @@ __device__ __forceinline__ void mono_residual_pair(const double* R /*3x3*/, cons
   q.x = kfma(R[6], p.z, kfma(R[3], p.y, kfma(R[0], p.x, tinv[0])));
   q.y = kfma(R[7], p.z, kfma(R[4], p.y, kfma(R[1], p.x, tinv[1])));
   q.z = kfma(R[8], p.z, kfma(R[5], p.y, kfma(R[2], p.x, tinv[2])));
-  const double np = sqrt(dot(p, p)), nq = sqrt(dot(q, q));
-  const double x1 = dot(f1, p) / np;
-  const double x2 = dot(f2, q) / nq;
+  const double x1 = dot(f1, p) * krsqrt(dot(p, p));
+  const double x2 = dot(f2, q) * krsqrt(dot(q, q));
   *r_pos = (1.0 - x1) + (1.0 - x2);
   *r_neg = (1.0 + x1) + (1.0 + x2);
 }

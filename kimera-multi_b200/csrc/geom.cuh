@@ -16,6 +16,7 @@
 // (profiles/r01b: the fully inlined build stalled on instruction fetch).
 #pragma once
 #include <math.h>
+#include <string.h>
 #include <stdint.h>
 
 #define KML_DI __device__ __forceinline__
@@ -29,6 +30,20 @@ __device__ unsigned long long g_fstats[12];
 #endif
 KML_DI double kfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 KML_DN double kdiv(double a, double b) { return a / b; }
+// the contract's reciprocal square root: magic-constant start, four Newton steps — no sqrt, no division
+KML_DI double krsqrt(double x) {
+  unsigned long long i;
+  memcpy(&i, &x, 8);
+  i = 0x5FE6EB50C7B537A9ull - (i >> 1);
+  double y;
+  memcpy(&y, &i, 8);
+  const double h = 0.5 * x;
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  return y;
+}
 KML_DN double ksqrt(double a) { return sqrt(a); }
 
 struct V3 {
@@ -59,7 +74,7 @@ KML_DN bool jacobi_pair(double* G, double* W, int p, int q) {
   const double h = b - a, tg = 2.0 * g;  // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = h / tg, times 2|g|: one division
   const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
   const double t = kdiv(sgn * fabs(tg), fabs(h) + ksqrt(kfma(h, h, tg * tg)));
-  const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
+  const double c = krsqrt(kfma(t, t, 1.0));
   const double s = c * t;
 #pragma unroll 1
   for (int i = 0; i < 3; ++i) {
@@ -141,7 +156,7 @@ KML_DI bool jacobi_pair_r(double (&G)[9], double (&W)[9]) {
   const double h = b - a, tg = 2.0 * g;  // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = h / tg, times 2|g|: one division
   const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
   const double t = kdiv(sgn * fabs(tg), fabs(h) + ksqrt(kfma(h, h, tg * tg)));
-  const double c = kdiv(1.0, ksqrt(kfma(t, t, 1.0)));
+  const double c = krsqrt(kfma(t, t, 1.0));
   const double s = c * t;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -296,9 +311,8 @@ KML_DI double mono_residual(const double* M, const double* tinv, const V3& f1, c
   q.x = kfma(M[8], p.z, kfma(M[4], p.y, kfma(M[0], p.x, tinv[0])));
   q.y = kfma(M[9], p.z, kfma(M[5], p.y, kfma(M[1], p.x, tinv[1])));
   q.z = kfma(M[10], p.z, kfma(M[6], p.y, kfma(M[2], p.x, tinv[2])));
-  const double np = ksqrt(dot(p, p)), nq = ksqrt(dot(q, q));
-  const double e1 = 1.0 - kdiv(dot(f1, p), np);
-  const double e2 = 1.0 - kdiv(dot(f2, q), nq);
+  const double e1 = 1.0 - dot(f1, p) * krsqrt(dot(p, p));
+  const double e2 = 1.0 - dot(f2, q) * krsqrt(dot(q, q));
   return e1 + e2;
 }
 

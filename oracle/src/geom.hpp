@@ -22,6 +22,22 @@ namespace kmo {
 // The contract's fused multiply-add: a*b + c rounded once.  Written out wherever the contract fuses
 // (never left to the compiler: -ffp-contract=off); the CUDA kernels write __fma_rn at the same places.
 static inline double kfma(double a, double b, double c) { return __builtin_fma(a, b, c); }
+// The contract's reciprocal square root: a fixed sequence of integer and IEEE operations (no sqrt, no
+// division) — the magic-constant start value (3.4 % off at most) and four Newton steps y <- y (3/2 - (x/2) y^2),
+// each squaring the error; the result is within a few ulp of 1/sqrt(x) and the same bits everywhere.
+static inline double krsqrt(double x) {
+  uint64_t i;
+  std::memcpy(&i, &x, 8);
+  i = 0x5FE6EB50C7B537A9ull - (i >> 1);
+  double y;
+  std::memcpy(&y, &i, 8);
+  const double h = 0.5 * x;
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  y = y * kfma(-(h * y), y, 1.5);
+  return y;
+}
 
 // ---------------------------------------------------------------- 3-vectors
 static inline double dot3(const double* a, const double* b) {
@@ -70,7 +86,7 @@ static inline void svd3(const double* A, double* U, double* S, double* V) {
       const double h = b - a, tg = 2.0 * g;
       const double sgn = (h == 0.0 || (h > 0.0) == (g > 0.0)) ? 1.0 : -1.0;
       double t = (sgn * std::fabs(tg)) / (std::fabs(h) + std::sqrt(kfma(h, h, tg * tg)));
-      double c = 1.0 / std::sqrt(kfma(t, t, 1.0));
+      double c = krsqrt(kfma(t, t, 1.0));
       double s = c * t;
       for (int i = 0; i < 3; ++i) {
         double gp = G[3 * i + p], gq = G[3 * i + q];
@@ -193,9 +209,8 @@ static inline double mono_residual(const double* M, const double* tinv,
   q[0] = kfma(M[8], p[2], kfma(M[4], p[1], kfma(M[0], p[0], tinv[0])));
   q[1] = kfma(M[9], p[2], kfma(M[5], p[1], kfma(M[1], p[0], tinv[1])));
   q[2] = kfma(M[10], p[2], kfma(M[6], p[1], kfma(M[2], p[0], tinv[2])));
-  double np = std::sqrt(dot3(p, p)), nq = std::sqrt(dot3(q, q));
-  double e1 = 1.0 - dot3(f1, p) / np;
-  double e2 = 1.0 - dot3(f2, q) / nq;
+  double e1 = 1.0 - dot3(f1, p) * krsqrt(dot3(p, p));
+  double e2 = 1.0 - dot3(f2, q) * krsqrt(dot3(q, q));
   return e1 + e2;
 }
 

@@ -284,6 +284,14 @@ def debug_root_grid2(on):
     lib().kmo_debug_root_grid2(C.c_int(int(on)))
 
 
+def krsqrt(x):
+    """the contract's reciprocal square root, elementwise"""
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    lib().kmo_krsqrt(_p(x, C.c_double), C.c_int(x.size), _p(out, C.c_double))
+    return out
+
+
 def ransac_stewenius(f1, f2, thr=1e-6, prob=0.995, max_iter=1000, seed=12345):
     return _ransac(lib().kmo_ransac_stewenius, f1, f2, thr, prob, max_iter, seed)
 

@@ -100,6 +100,8 @@ int kmo_mono_model_alg(const double* f1, const double* f2, const uint16_t* sampl
 
 /* proper SVD used by both solvers: A = U diag(S) V^T, det U = det V = +1 */
 void kmo_svd3(const double* A, double* U, double* S, double* V);
+/* the contract's reciprocal square root (geom.hpp krsqrt) on n values */
+void kmo_krsqrt(const double* x, int n, double* out);
 /* mono model from an 8-point sample (5 solve + 3 disambiguate); returns 0
  * if no valid model */
 int kmo_mono_model(const double* f1, const double* f2, const uint16_t* sample8,

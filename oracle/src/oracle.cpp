@@ -516,6 +516,7 @@ int kmo_fivept_nister(const double* f1, const double* f2, double* E) {
   return n;
 }
 void kmo_svd3(const double* A, double* U, double* S, double* V) { svd3(A, U, S, V); }
+void kmo_krsqrt(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = krsqrt(x[i]); }
 int kmo_mono_model(const double* f1, const double* f2, const uint16_t* sample8, double* model) {
   return mono_model(f1, f2, sample8, model) ? 1 : 0;
 }

@@ -35,6 +35,7 @@ using namespace kml::geom;
 
 extern "C" {
 
+void dmh_krsqrt(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = krsqrt(x[i]); }
 void dmh_svd3(const double* A, double* U, double* S, double* V) { svd3(A, U, S, V); }
 void dmh_svd3_r(const double* A, double* U, double* S, double* V) { svd3_r(A, U, S, V); }
 

@@ -45,6 +45,24 @@ def _device_mono_model(dmh, f1, f2, s, force_generic):
     return bool(ok), m, info
 
 
+def test_contract_rsqrt_same_bits_and_within_three_ulp(oracle, dmh):
+    """krsqrt is the one non-IEEE primitive of the contract: the device source and the oracle
+    return the same bits, within 3 ulp of 1/sqrt(x), over 25 decades; zero, infinity and NaN included in the
+    bit comparison."""
+    rng = np.random.default_rng(4)
+    x = rng.uniform(1.0, 2.0, 200000) * 2.0 ** rng.integers(-400, 400, 200000)
+    x = np.concatenate([x, [0.0, 1.0, 4.0, 1e-300, 1e300, np.inf, np.nan]])
+    a = oracle.krsqrt(x)
+    b = np.zeros_like(x)
+    dmh.dmh_krsqrt(_dp(x), C.c_int(x.size), _dp(b))
+    assert a.tobytes() == b.tobytes()
+    fin = np.isfinite(x) & (x > 0)
+    ref = 1.0 / np.sqrt(x[fin].astype(np.longdouble))
+    err = np.abs((a[fin] - ref) / ref).astype(np.float64)
+    assert err.max() <= 3 * 2.0 ** -53, err.max()
+    assert a[x == 1.0][0] > 0.999999999999999 and abs(a[x == 4.0][0] - 0.5) < 1e-15
+
+
 def test_svd3_both_device_variants_equal_the_oracle(oracle, dmh):
     rng = np.random.default_rng(5)
     for k in range(3000):
